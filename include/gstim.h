@@ -1,0 +1,192 @@
+/* gstim.h — C ABI of the B200-native Pauli-frame sampler (libgstim.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of quantumlib/Stim that this library replaces:
+ * the FrameSimulator bulk sampler behind `stim detect`, `stim sample`,
+ * `stim.Circuit.compile_detector_sampler()` and `stim.Circuit.compile_sampler()`.
+ * The reference has no FFI for this path (FrameSimulator<W> is a header template instantiated in
+ * its callers); each entry point below names the reference call it replaces. All paths are
+ * relative to /root/reference/.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints. No C++/torch types.
+ *   - every function returns 0 on success or a GSTIM_ERR_* code; the message is available from
+ *     gstim_last_error(). The C++/Python shim re-raises INVALID_ARGUMENT as
+ *     std::invalid_argument/ValueError and OUT_OF_RANGE as std::out_of_range/IndexError, matching
+ *     the exception types the reference throws (src/stim/main_namespaced.cc:113-122 and pybind).
+ *   - a sampler handle is NOT thread-safe (like the reference object, which owns a mutable RNG);
+ *     distinct handles are independent. Calls are synchronous: on return the results are in the
+ *     caller's buffer.
+ *   - the caller owns every input and output buffer; the library owns device memory and streams.
+ *   - there is NO CPU fallback: creating a sampler without a usable CUDA device fails with
+ *     GSTIM_ERR_CUDA.
+ *   - successive sample calls on one handle continue the random stream (they never repeat shots),
+ *     as with the reference samplers (src/stim/py/compiled_detector_sampler.pybind.cc:180-196).
+ */
+#ifndef GSTIM_H
+#define GSTIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSTIM_OK 0
+#define GSTIM_ERR_INVALID_ARGUMENT 1 /* std::invalid_argument in the reference */
+#define GSTIM_ERR_OUT_OF_RANGE 2     /* std::out_of_range in the reference */
+#define GSTIM_ERR_CUDA 3
+#define GSTIM_ERR_OOM 4
+#define GSTIM_ERR_IO 5
+#define GSTIM_ERR_INTERNAL 6
+
+/* which record a sampler produces */
+#define GSTIM_MODE_DETECTORS 0    /* detection events + observables (stim detect / compile_detector_sampler) */
+#define GSTIM_MODE_MEASUREMENTS 1 /* measurement record (stim sample / compile_sampler) */
+
+/* output flags */
+#define GSTIM_BIT_PACKED 0x01u   /* uint8[shots, ceil(n/8)] little-endian bits (b8); else one byte per bit */
+#define GSTIM_PREPEND_OBS 0x02u  /* observables before detectors in each shot (--prepend_observables) */
+#define GSTIM_APPEND_OBS 0x04u   /* observables after detectors in each shot (--append_observables) */
+#define GSTIM_SEPARATE_OBS 0x08u /* observables into obs_out (separate_observables=True / --obs_out) */
+
+typedef struct gstim_sampler gstim_sampler;
+
+/* mirrors stim::CircuitStats (src/stim/circuit/circuit_instruction.h:30-50) + the chosen device plan */
+typedef struct gstim_stats {
+    uint64_t num_qubits;       /* highest qubit index + 1 */
+    uint64_t num_measurements;
+    uint64_t num_detectors;
+    uint64_t num_observables;
+    uint64_t max_lookback;
+    uint64_t active_qubits;    /* qubits kept in the frame after compaction */
+    uint64_t program_words;    /* lowered instruction stream length (uint32 words) */
+    uint64_t num_batches;      /* concurrent batches in the stream */
+    uint64_t num_barriers;     /* batches that need a block-wide barrier */
+    uint64_t num_noise_sites;  /* Philox site counter at the end of the circuit */
+    uint64_t num_collapse_sites;
+    uint32_t threads;          /* threads per block */
+    uint32_t lanes_per_item;   /* G */
+    uint32_t slots;            /* concurrent items per batch pass */
+    uint32_t max_columns;      /* largest K (128-shot columns per block) that fits in shared memory */
+    uint32_t chunk_words;
+    uint32_t smem_bytes_max;   /* dynamic shared memory at max_columns */
+} gstim_stats;
+
+int gstim_version(void);
+
+/* Message of the most recent failure on this thread (never NULL). */
+const char *gstim_last_error(void);
+
+/* Number of usable CUDA devices (0 when none / no driver). */
+int gstim_device_count(void);
+
+/* Parse + validate a circuit on the host only (no GPU needed): fills the CircuitStats part of *out.
+ * Replaces: Circuit::compute_stats()  src/stim/circuit/circuit.cc:719-725 */
+int gstim_circuit_stats(const char *circuit_text, size_t text_len, gstim_stats *out);
+
+/* Host-only lowering (no GPU needed): circuit text -> the uint32 instruction stream the interpreter
+ * kernel executes (format: stim_b200/csrc/program.h), with barrier flags computed for `slots`
+ * concurrent thread groups and cut into chunks of `chunk_words` words (0 = library default).
+ * plan_out receives the 14 uint32 fields of GstimPlan (program.h). Call with words == NULL to get
+ * the required length in *n_words. No reference analogue (new subsystem: the lowering). */
+int gstim_lower_text(
+    const char *circuit_text,
+    size_t text_len,
+    int mode,
+    uint32_t slots,
+    uint32_t chunk_words,
+    uint32_t *words,
+    size_t *n_words,
+    uint32_t plan_out[16]);
+
+/* Parse + lower + upload a circuit given in Stim's circuit file format.
+ * Replaces: CompiledDetectorSampler(circuit, rng)  src/stim/py/compiled_detector_sampler.pybind.cc:28-32
+ *           CompiledMeasurementSampler(ref, circuit, skip_ref, rng)  src/stim/py/compiled_measurement_sampler.pybind.cc:26-29
+ *           Circuit::from_file + FrameSimulator construction in src/stim/cmd/command_detect.cc:65-77,
+ *           src/stim/cmd/command_sample.cc:58-69
+ * mode: GSTIM_MODE_*.  device: CUDA ordinal.  seed: Philox key. */
+int gstim_create_from_text(
+    const char *circuit_text, size_t text_len, int mode, uint64_t seed, int device, gstim_sampler **out);
+
+void gstim_destroy(gstim_sampler *s);
+
+int gstim_get_stats(const gstim_sampler *s, gstim_stats *out);
+
+/* Copy of the lowered instruction stream (for inspection / the program-level emulator in oracle/).
+ * Call with words == NULL to get the length in *n_words. */
+int gstim_get_program(const gstim_sampler *s, uint32_t *words, size_t *n_words);
+
+/* Binds the noiseless reference sample that is XORed into measurement results
+ * (MODE_MEASUREMENTS only). bits: num_measurements bits, little-endian packed. NULL = all zero
+ * (== skip_reference_sample=True).
+ * Replaces: the `reference_sample` argument of sample_batch_measurements
+ *           src/stim/simulators/frame_simulator_util.h:103-109, :123-130 */
+int gstim_set_reference_sample(gstim_sampler *s, const uint8_t *bits, size_t n_bits);
+
+/* Shot offset (in shots) the next call will start at; lets a caller reproduce / resume a range. */
+int gstim_get_shot_offset(const gstim_sampler *s, uint64_t *offset);
+int gstim_set_shot_offset(gstim_sampler *s, uint64_t offset);
+
+/* Detection-event sampling into HOST memory, shot-major.
+ * Replaces: CompiledDetectorSampler::sample_to_numpy  src/stim/py/compiled_detector_sampler.pybind.cc:34-86
+ *           sample_batch_detection_events<W>         src/stim/simulators/frame_simulator_util.h:48-50
+ * dets_out: [shots][n] where n = D (+L with PREPEND/APPEND); with GSTIM_BIT_PACKED each shot is
+ *   ceil(n/8) bytes, else n bytes of 0/1. dets_shot_stride = bytes between consecutive shots
+ *   (0 = dense). obs_out/obs_shot_stride likewise for the L observables when GSTIM_SEPARATE_OBS. */
+int gstim_sample_detectors(
+    gstim_sampler *s,
+    uint64_t shots,
+    uint32_t flags,
+    void *dets_out,
+    int64_t dets_shot_stride,
+    void *obs_out,
+    int64_t obs_shot_stride);
+
+/* Measurement sampling into HOST memory, shot-major.
+ * Replaces: CompiledMeasurementSampler::sample_to_numpy  src/stim/py/compiled_measurement_sampler.pybind.cc:31-35
+ *           sample_batch_measurements<W>                 src/stim/simulators/frame_simulator_util.inl:291-315 */
+int gstim_sample_measurements(gstim_sampler *s, uint64_t shots, uint32_t flags, void *out, int64_t shot_stride);
+
+/* Same as the two calls above but the output buffers are DEVICE pointers on the sampler's device
+ * and only the bit-packed (b8) layout is produced. Results stay in HBM (no PCIe traffic). */
+int gstim_sample_detectors_device(
+    gstim_sampler *s,
+    uint64_t shots,
+    uint32_t flags,
+    void *dets_out_dev,
+    int64_t dets_shot_stride,
+    void *obs_out_dev,
+    int64_t obs_shot_stride);
+int gstim_sample_measurements_device(gstim_sampler *s, uint64_t shots, void *out_dev, int64_t shot_stride);
+
+/* Streaming to files in Stim's result formats "01", "b8", "r8", "hits", "dets", "ptb64".
+ * Replaces: sample_batch_detection_events_writing_results_to_disk  src/stim/simulators/frame_simulator_util.h:67-77
+ *           sample_batch_measurements_writing_results_to_disk      src/stim/simulators/frame_simulator_util.h:123-130
+ * fd / obs_fd are open file descriptors owned by the caller (obs_fd < 0 = none).
+ * Error behaviour follows the reference: ptb64 needs shots % 64 == 0 (invalid_argument,
+ * src/stim/io/measure_record_writer.h:123-125); combining prepend/append/obs_out is out_of_range
+ * (src/stim/simulators/frame_simulator_util.inl:127-129). */
+int gstim_sample_detectors_to_fd(
+    gstim_sampler *s, uint64_t shots, uint32_t flags, int fd, const char *format, int obs_fd, const char *obs_format);
+int gstim_sample_measurements_to_fd(gstim_sampler *s, uint64_t shots, int fd, const char *format);
+
+/* Per-detector and per-observable flip counts over `shots` fresh shots: counts[D+L] (uint64),
+ * written to HOST memory; counts_dev (optional, may be NULL) receives the same on the device so a
+ * multi-GPU caller can allreduce it (NCCL sum over uint64[D+L]) without a host round trip. */
+int gstim_detector_flip_counts(gstim_sampler *s, uint64_t shots, uint64_t *counts_host, void *counts_dev);
+
+/* Kernel launches issued by the most recent sampling call (for bench accounting). */
+int gstim_last_launch_count(const gstim_sampler *s, uint64_t *launches);
+
+/* 128-shot columns per thread block (K) used by the most recent sampling call. Together with the seed
+ * and the shot offset this pins the random stream (DESIGN.md "RNG addressing"). */
+int gstim_last_block_columns(const gstim_sampler *s, uint32_t *columns);
+
+/* Device-time (CUDA events, ms) of the interpreter and transposer kernels in the most recent call. */
+int gstim_last_kernel_ms(const gstim_sampler *s, float *interp_ms, float *transpose_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSTIM_H */

@@ -1,0 +1,74 @@
+"""TEST INFRASTRUCTURE (oracle) — never imported by the product path (stim_b200/).
+
+numpy restatement of the two random primitives the device noise generator is specified with
+(DESIGN.md "RNG addressing"):
+
+  * Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
+    Pinned against the Random123 known-answer vectors in tests/test_oracle_philox.py.
+  * exp_draw: Exp(1) variate from a uniform u32 using only IEEE-754 double + - * / in a fixed order,
+    so the CUDA kernel (stim_b200/csrc/kernels.cu: exp_draw) reproduces it bit for bit.
+
+These replace, in distribution, the reference's std::mt19937_64 + std::geometric_distribution
+(/root/reference/src/stim/util_bot/probability_util.cc:23-43): floor(Exp(1)/lambda) with
+lambda = -log1p(-p) is exactly Geometric(p).
+"""
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK32 = np.uint64(0xFFFFFFFF)
+
+TAG_EVENT = 0x45564E54
+TAG_COLLAPSE = 0x434F4C4C
+TAG_CLOCK = 0x434C4F4B
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """All arguments broadcastable integer arrays (values < 2**32). Returns 4 uint32 arrays."""
+    c0, c1, c2, c3 = np.broadcast_arrays(*(np.asarray(a, dtype=np.uint64) for a in (c0, c1, c2, c3)))
+    c0 = c0.copy()
+    c1 = c1.copy()
+    c2 = c2.copy()
+    c3 = c3.copy()
+    k0 = int(k0) & 0xFFFFFFFF
+    k1 = int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK32
+        n0 = hi1 ^ c1 ^ np.uint64(k0)
+        n2 = hi0 ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, lo1, n2, lo0
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return tuple(a.astype(np.uint32) for a in (c0, c1, c2, c3))
+
+
+_COEFS = [1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0, 1.0]
+_LN2 = 0.6931471805599453
+_SQRT2 = 1.4142135623730951
+
+
+def exp_draw(r):
+    """-ln((r + 1/2) / 2**32) for uint32 r, evaluated exactly like the device code."""
+    r = np.asarray(r, dtype=np.uint64)
+    v = np.uint64(2) * r + np.uint64(1)  # odd, < 2**33, exact in float64
+    vf = v.astype(np.float64)
+    # t = floor(log2 v): frexp gives vf = mant * 2**e with mant in [0.5, 1) -> t = e - 1 (exact for integers < 2**53)
+    _, e = np.frexp(vf)
+    t = e.astype(np.int64) - 1
+    m = vf * np.ldexp(1.0, -t)  # exact scaling into [1, 2)
+    big = m > _SQRT2
+    m = np.where(big, m * 0.5, m)
+    t = np.where(big, t + 1, t)
+    s = (m - 1.0) / (m + 1.0)
+    s2 = s * s
+    poly = np.full_like(s, 1.0 / 21.0)
+    for c in _COEFS:
+        poly = poly * s2 + c
+    lnm = (2.0 * s) * poly
+    lnx = lnm + (t - 33).astype(np.float64) * _LN2
+    return -lnx

@@ -1,0 +1,343 @@
+"""stim_b200 — B200-native Pauli-frame sampler, drop-in for the sampling hot path of quantumlib/Stim.
+
+Host-side mirror of the reference's Python surface for this path (same names, argument meaning and
+error behaviour), on top of the C ABI in include/gstim.h:
+
+    stim.Circuit(...).compile_detector_sampler(seed=...)  -> Circuit.compile_detector_sampler
+        /root/reference/src/stim/py/compiled_detector_sampler.pybind.cc
+    stim.Circuit(...).compile_sampler(...)                -> Circuit.compile_sampler
+        /root/reference/src/stim/py/compiled_measurement_sampler.pybind.cc
+
+All sampling runs in hand-written sm_100a CUDA kernels (stim_b200/csrc/kernels.cu). There is no CPU
+fallback: without libgstim.so or without a CUDA device, constructing a sampler raises.
+"""
+import os
+from typing import Optional, Tuple, Union
+
+import ctypes
+import numpy as np
+
+from . import _native
+from ._native import GstimCudaError, GstimStats
+
+__all__ = ["Circuit", "CompiledDetectorSampler", "CompiledMeasurementSampler", "GstimCudaError"]
+
+
+def _seed_to_u64(seed) -> int:
+    """seed=None -> OS entropy, like make_py_seeded_rng (/root/reference/src/stim/py/base.pybind.cc:23-35)."""
+    if seed is None:
+        return int.from_bytes(os.urandom(8), "little")
+    if not isinstance(seed, (int, np.integer)) or isinstance(seed, bool):
+        raise ValueError("Expected seed to be None or a 64 bit unsigned integer.")
+    seed = int(seed)
+    if seed < 0 or seed >= 1 << 64:
+        raise ValueError("Expected seed to be None or a 64 bit unsigned integer.")
+    return seed
+
+
+def _path_str(p, what) -> str:
+    if hasattr(p, "__fspath__"):
+        p = os.fspath(p)
+    if not isinstance(p, str):
+        raise ValueError(f"Don't know how to write {what}{p!r}")
+    return p
+
+
+class Circuit:
+    """A stabilizer circuit in Stim's text format. Only what the sampling path needs is mirrored."""
+
+    def __init__(self, stim_program_text: str = ""):
+        if not isinstance(stim_program_text, str):
+            raise TypeError("stim_program_text must be a str")
+        self._text = stim_program_text
+        st = GstimStats()
+        data = self._text.encode("utf-8")
+        _native.check(_native.lib().gstim_circuit_stats(data, len(data), ctypes.byref(st)))
+        self._stats = st
+
+    @staticmethod
+    def from_file(file) -> "Circuit":
+        if hasattr(file, "read"):
+            return Circuit(file.read())
+        with open(os.fspath(file), "r") as f:
+            return Circuit(f.read())
+
+    def __str__(self) -> str:
+        return self._text
+
+    @property
+    def num_qubits(self) -> int:
+        return int(self._stats.num_qubits)
+
+    @property
+    def num_measurements(self) -> int:
+        return int(self._stats.num_measurements)
+
+    @property
+    def num_detectors(self) -> int:
+        return int(self._stats.num_detectors)
+
+    @property
+    def num_observables(self) -> int:
+        return int(self._stats.num_observables)
+
+    def compile_detector_sampler(self, *, seed=None, device: int = 0) -> "CompiledDetectorSampler":
+        return CompiledDetectorSampler(self, seed=seed, device=device)
+
+    def compile_sampler(self, *, skip_reference_sample: bool = False, seed=None, reference_sample=None,
+                        device: int = 0) -> "CompiledMeasurementSampler":
+        return CompiledMeasurementSampler(
+            self, skip_reference_sample=skip_reference_sample, seed=seed, reference_sample=reference_sample, device=device)
+
+
+class _Sampler:
+    def __init__(self, circuit: Circuit, mode: int, seed, device: int):
+        if isinstance(circuit, str):
+            circuit = Circuit(circuit)
+        self._circuit = circuit
+        self._handle = ctypes.c_void_p()
+        data = str(circuit).encode("utf-8")
+        _native.check(_native.lib().gstim_create_from_text(
+            data, len(data), mode, ctypes.c_uint64(_seed_to_u64(seed)), int(device), ctypes.byref(self._handle)))
+        st = GstimStats()
+        _native.check(_native.lib().gstim_get_stats(self._handle, ctypes.byref(st)))
+        self.stats = st
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            _native.lib().gstim_destroy(h)
+            self._handle = ctypes.c_void_p()
+
+    # -- introspection used by tests / bench ---------------------------------------------------
+    def program_words(self) -> np.ndarray:
+        n = ctypes.c_size_t(0)
+        _native.check(_native.lib().gstim_get_program(self._handle, None, ctypes.byref(n)))
+        out = np.empty(n.value, dtype=np.uint32)
+        _native.check(_native.lib().gstim_get_program(self._handle, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n)))
+        return out
+
+    @property
+    def shot_offset(self) -> int:
+        v = ctypes.c_uint64(0)
+        _native.check(_native.lib().gstim_get_shot_offset(self._handle, ctypes.byref(v)))
+        return int(v.value)
+
+    @shot_offset.setter
+    def shot_offset(self, value: int):
+        _native.check(_native.lib().gstim_set_shot_offset(self._handle, ctypes.c_uint64(int(value))))
+
+    def last_launch_count(self) -> int:
+        v = ctypes.c_uint64(0)
+        _native.check(_native.lib().gstim_last_launch_count(self._handle, ctypes.byref(v)))
+        return int(v.value)
+
+    def last_block_columns(self) -> int:
+        v = ctypes.c_uint32(0)
+        _native.check(_native.lib().gstim_last_block_columns(self._handle, ctypes.byref(v)))
+        return int(v.value)
+
+    def last_kernel_ms(self) -> Tuple[float, float]:
+        a, b = ctypes.c_float(0), ctypes.c_float(0)
+        _native.check(_native.lib().gstim_last_kernel_ms(self._handle, ctypes.byref(a), ctypes.byref(b)))
+        return float(a.value), float(b.value)
+
+
+def _prepare_out(buf, shots: int, n_bits: int, bit_packed: bool):
+    """Validates / allocates an output array like numpy.pybind.cc:20-102 does.
+
+    Returns (array_to_return, native_target, copy_back) where native_target is a C-contiguous-in-dim-1 array."""
+    width = (n_bits + 7) // 8 if bit_packed else n_bits
+    dtype = np.uint8 if bit_packed else np.bool_
+    if buf is None:
+        arr = np.empty((shots, width), dtype=dtype)
+        return arr, arr, False
+    if not isinstance(buf, np.ndarray) or buf.dtype != dtype:
+        raise ValueError("Output buffer wasn't a numpy.ndarray[np.%s]." % ("uint8" if bit_packed else "bool_"))
+    if buf.ndim != 2:
+        raise ValueError("Output buffer wasn't two dimensional.")
+    if buf.shape != (shots, width):
+        raise ValueError(
+            f"Expected output buffer to have shape=({shots}, {width}) but its shape is ({buf.shape[0]}, {buf.shape[1]}).")
+    if buf.size == 0 or (buf.strides[1] == 1 and buf.strides[0] >= width):
+        return buf, buf, False
+    tmp = np.empty((shots, width), dtype=dtype)  # exotic strides: sample densely, then scatter
+    return buf, tmp, True
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None or a.size == 0 else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _stride(a: Optional[np.ndarray]) -> int:
+    return 0 if a is None or a.size == 0 else int(a.strides[0])
+
+
+class CompiledDetectorSampler(_Sampler):
+    """Mirror of stim.CompiledDetectorSampler (compiled_detector_sampler.pybind.cc:151-421)."""
+
+    def __init__(self, circuit: Circuit, *, seed=None, device: int = 0):
+        super().__init__(circuit, _native.MODE_DETECTORS, seed, device)
+
+    def sample(
+        self,
+        shots: int,
+        *,
+        prepend_observables: bool = False,
+        append_observables: bool = False,
+        separate_observables: bool = False,
+        bit_packed: bool = False,
+        dets_out: Optional[np.ndarray] = None,
+        obs_out: Optional[np.ndarray] = None,
+    ) -> Union[np.ndarray, Tuple[np.ndarray, np.ndarray]]:
+        if separate_observables and (append_observables or prepend_observables):
+            raise ValueError(
+                "Can't specify separate_observables=True with append_observables=True or prepend_observables=True")
+        shots = int(shots)
+        if shots < 0:
+            raise ValueError("shots must be non-negative")
+        D, L = int(self.stats.num_detectors), int(self.stats.num_observables)
+        n_main = D + (L if append_observables else 0) + (L if prepend_observables else 0)
+        want_obs = separate_observables or obs_out is not None
+        det_ret, det_native, det_copy = _prepare_out(dets_out, shots, n_main, bit_packed)
+        obs_ret = obs_native = None
+        obs_copy = False
+        if want_obs:
+            obs_ret, obs_native, obs_copy = _prepare_out(obs_out, shots, L, bit_packed)
+        if append_observables and prepend_observables:
+            # The reference concatenates obs + dets + obs in this case (compiled_detector_sampler.pybind.cc:64-75).
+            both = self.sample(shots, append_observables=True, separate_observables=False, bit_packed=False,
+                               obs_out=obs_native if (want_obs and not bit_packed) else None)
+            full = np.concatenate([both[:, D:], both], axis=1)
+            res = np.packbits(full, axis=1, bitorder="little") if bit_packed else full
+            det_native[...] = res
+            if want_obs and bit_packed:
+                obs_native[...] = np.packbits(both[:, D:], axis=1, bitorder="little")
+        else:
+            flags = (_native.BIT_PACKED if bit_packed else 0) | (_native.PREPEND_OBS if prepend_observables else 0) | (
+                _native.APPEND_OBS if append_observables else 0)
+            if want_obs:
+                if flags & (_native.PREPEND_OBS | _native.APPEND_OBS):
+                    # obs_out together with prepend/append: two passes would resample; emit obs from the main rows.
+                    _native.check(_native.lib().gstim_sample_detectors(
+                        self._handle, shots, flags, _ptr(det_native), _stride(det_native), None, 0))
+                    main_bits = np.unpackbits(det_native, axis=1, bitorder="little")[:, :n_main] if bit_packed else det_native
+                    ob = main_bits[:, :L] if prepend_observables else main_bits[:, D:D + L]
+                    obs_native[...] = np.packbits(ob, axis=1, bitorder="little") if bit_packed else ob
+                else:
+                    flags |= _native.SEPARATE_OBS
+                    _native.check(_native.lib().gstim_sample_detectors(
+                        self._handle, shots, flags, _ptr(det_native), _stride(det_native), _ptr(obs_native),
+                        _stride(obs_native)))
+            else:
+                _native.check(_native.lib().gstim_sample_detectors(
+                    self._handle, shots, flags, _ptr(det_native), _stride(det_native), None, 0))
+        if det_copy:
+            det_ret[...] = det_native
+        if obs_copy:
+            obs_ret[...] = obs_native
+        if separate_observables:
+            return det_ret, obs_ret
+        return det_ret
+
+    def sample_bit_packed(self, shots: int, *, prepend_observables: bool = False, append_observables: bool = False) -> np.ndarray:
+        """[DEPRECATED in the reference] use sample(..., bit_packed=True)."""
+        return self.sample(shots, prepend_observables=prepend_observables, append_observables=append_observables, bit_packed=True)
+
+    def sample_write(
+        self,
+        shots: int,
+        *,
+        filepath,
+        format: str = "01",
+        obs_out_filepath=None,
+        obs_out_format: str = "01",
+        prepend_observables: bool = False,
+        append_observables: bool = False,
+    ) -> None:
+        path = _path_str(filepath, "to ")
+        obs_path = None if obs_out_filepath is None else _path_str(obs_out_filepath, "observables to ")
+        flags = (_native.PREPEND_OBS if prepend_observables else 0) | (_native.APPEND_OBS if append_observables else 0)
+        with open(path, "wb") as f:
+            of = open(obs_path, "wb") if obs_path is not None else None
+            try:
+                _native.check(_native.lib().gstim_sample_detectors_to_fd(
+                    self._handle, int(shots), flags, f.fileno(), format.encode(), of.fileno() if of else -1,
+                    obs_out_format.encode()))
+            finally:
+                if of:
+                    of.close()
+
+    def sample_device(self, shots: int, dets_ptr: int, *, dets_shot_stride: int = 0, obs_ptr: int = 0,
+                      obs_shot_stride: int = 0, append_observables: bool = False, prepend_observables: bool = False) -> None:
+        """Bit-packed results written straight to DEVICE memory (raw pointers, e.g. tensor.data_ptr())."""
+        flags = _native.BIT_PACKED | (_native.PREPEND_OBS if prepend_observables else 0) | (
+            _native.APPEND_OBS if append_observables else 0) | (_native.SEPARATE_OBS if obs_ptr else 0)
+        _native.check(_native.lib().gstim_sample_detectors_device(
+            self._handle, int(shots), flags, ctypes.c_void_p(dets_ptr or None), dets_shot_stride,
+            ctypes.c_void_p(obs_ptr or None), obs_shot_stride))
+
+    def flip_counts(self, shots: int, counts_dev_ptr: int = 0) -> np.ndarray:
+        """uint64[D+L] flip counts over `shots` fresh shots (device copy optional, for NCCL allreduce)."""
+        n = int(self.stats.num_detectors + self.stats.num_observables)
+        out = np.zeros(n, dtype=np.uint64)
+        _native.check(_native.lib().gstim_detector_flip_counts(
+            self._handle, int(shots), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(counts_dev_ptr or None)))
+        return out
+
+    def __repr__(self) -> str:
+        return f"stim_b200.CompiledDetectorSampler({self._circuit!r})"
+
+
+class CompiledMeasurementSampler(_Sampler):
+    """Mirror of stim.CompiledMeasurementSampler (compiled_measurement_sampler.pybind.cc:26-290)."""
+
+    def __init__(self, circuit: Circuit, *, skip_reference_sample: bool = False, seed=None, reference_sample=None,
+                 device: int = 0):
+        if reference_sample is not None and skip_reference_sample:
+            raise ValueError("reference_sample is specified but skip_reference_sample=True")
+        super().__init__(circuit, _native.MODE_MEASUREMENTS, seed, device)
+        M = int(self.stats.num_measurements)
+        if reference_sample is not None:
+            ref = np.asarray(reference_sample)
+            if ref.dtype == np.bool_ and ref.shape == (M,):
+                packed = np.packbits(ref, bitorder="little")
+            elif ref.dtype == np.uint8 and ref.shape == ((M + 7) // 8,):
+                packed = np.ascontiguousarray(ref)
+            else:
+                raise ValueError(
+                    "reference_sample must be a numpy array of dtype bool_ with shape (num_measurements,) or of dtype "
+                    "uint8 with shape (ceil(num_measurements / 8),).")
+            self._set_reference(packed)
+        elif not skip_reference_sample:
+            from ._reference_sample import reference_sample_bits
+            self._set_reference(reference_sample_bits(str(circuit), M))
+
+    def _set_reference(self, packed: np.ndarray):
+        M = int(self.stats.num_measurements)
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        _native.check(_native.lib().gstim_set_reference_sample(self._handle, _ptr(packed) if M else None, M))
+
+    def sample(self, shots: int, *, bit_packed: bool = False) -> np.ndarray:
+        shots = int(shots)
+        M = int(self.stats.num_measurements)
+        ret, native, _ = _prepare_out(None, shots, M, bit_packed)
+        flags = _native.BIT_PACKED if bit_packed else 0
+        _native.check(_native.lib().gstim_sample_measurements(self._handle, shots, flags, _ptr(native), _stride(native)))
+        return ret
+
+    def sample_bit_packed(self, shots: int) -> np.ndarray:
+        """[DEPRECATED in the reference] use sample(..., bit_packed=True)."""
+        return self.sample(shots, bit_packed=True)
+
+    def sample_write(self, shots: int, *, filepath, format: str = "01") -> None:
+        path = _path_str(filepath, "to ")
+        with open(path, "wb") as f:
+            _native.check(_native.lib().gstim_sample_measurements_to_fd(self._handle, int(shots), f.fileno(), format.encode()))
+
+    def sample_device(self, shots: int, out_ptr: int, *, shot_stride: int = 0) -> None:
+        _native.check(_native.lib().gstim_sample_measurements_device(
+            self._handle, int(shots), ctypes.c_void_p(out_ptr or None), shot_stride))
+
+    def __repr__(self) -> str:
+        return f"stim_b200.CompiledMeasurementSampler({self._circuit!r})"

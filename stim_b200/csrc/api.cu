@@ -1,0 +1,1015 @@
+// api.cu — the C ABI (include/gstim.h) and the host scheduler behind it.
+//
+// The host scheduler replaces the batching loops of the reference
+// (/root/reference/src/stim/simulators/frame_simulator_util.inl:22-35, 207-288, 291-372):
+// it picks the per-block shot count from the shared-memory budget, cuts a request into chunks whose
+// bit-major staging table fits a fixed HBM budget, launches interpreter + transposer per chunk on
+// one stream, and drains results to the caller.
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gstim.h"
+#include "circuit.h"
+#include "kernels.cuh"
+#include "lowering.h"
+#include "writers.h"
+
+using namespace gstim;
+
+namespace {
+
+thread_local std::string g_last_error = "";
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string &m) : std::runtime_error(m) {}
+};
+struct OomError : std::runtime_error {
+    explicit OomError(const std::string &m) : std::runtime_error(m) {}
+};
+struct IoError : std::runtime_error {
+    explicit IoError(const std::string &m) : std::runtime_error(m) {}
+};
+
+#define CK(expr)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess) {                                                                          \
+            if (_e == cudaErrorMemoryAllocation) {                                                        \
+                cudaGetLastError();                                                                       \
+                throw OomError(std::string("CUDA out of memory in ") + #expr);                            \
+            }                                                                                             \
+            throw CudaError(std::string("CUDA error '") + cudaGetErrorString(_e) + "' in " + #expr);      \
+        }                                                                                                 \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) {
+            return;
+        }
+        if (p) {
+            cudaFree(p);
+            p = nullptr;
+            cap = 0;
+        }
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+    }
+    ~DevBuf() {
+        if (p) {
+            cudaFree(p);
+        }
+    }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) {
+            return;
+        }
+        if (p) {
+            cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+        }
+        CK(cudaMallocHost(&p, bytes));
+        cap = bytes;
+    }
+    ~PinnedBuf() {
+        if (p) {
+            cudaFreeHost(p);
+        }
+    }
+};
+
+uint32_t env_u32(const char *name, uint32_t dflt) {
+    const char *v = getenv(name);
+    if (v == nullptr || *v == '\0') {
+        return dflt;
+    }
+    return (uint32_t)strtoul(v, nullptr, 10);
+}
+
+}  // namespace
+
+struct gstim_sampler {
+    int device = 0;
+    int mode = 0;
+    uint64_t seed = 0;
+    uint64_t next_col = 0;  // global 128-shot column index the next call starts at
+
+    Circuit circuit;
+    LoweredCircuit lc;
+    GstimPlan plan{};
+    std::vector<uint32_t> words;
+
+    // launch configuration
+    uint32_t threads = 0, G_log2 = 0, slots = 0, K_max = 0, chunk_words = 0;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    DevBuf d_prog, d_table, d_rec, d_rowmap, d_stage[2], d_counts;
+    PinnedBuf h_stage[2];
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ready[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> events;
+    std::vector<uint8_t> ref_bits;  // one byte per measurement (0/1)
+
+    uint64_t last_launches = 0;
+    uint32_t last_K = 0;
+    float last_interp_ms = 0, last_transpose_ms = 0;
+
+    ~gstim_sampler() {
+        for (auto e : events) {
+            cudaEventDestroy(e);
+        }
+        for (auto e : stage_done) {
+            if (e) {
+                cudaEventDestroy(e);
+            }
+        }
+        for (auto e : stage_ready) {
+            if (e) {
+                cudaEventDestroy(e);
+            }
+        }
+        if (stream) {
+            cudaStreamDestroy(stream);
+        }
+        if (copy_stream) {
+            cudaStreamDestroy(copy_stream);
+        }
+    }
+};
+
+namespace {
+
+uint32_t n_rows_of(const gstim_sampler *s) {
+    return s->mode == GSTIM_MODE_DETECTORS ? s->plan.num_det + s->plan.num_obs : s->plan.num_meas;
+}
+
+// Largest single-item payload in the circuit decides the minimum chunk size.
+uint32_t max_targets_in_one_item(const Circuit &c) {
+    uint32_t m = 0;
+    for (const auto &op : c.ops) {
+        if (op.gate->cat == GateCat::REPEAT) {
+            m = std::max(m, max_targets_in_one_item(c.blocks[op.block_index]));
+        } else if (
+            op.gate->cat == GateCat::CORR || op.gate->cat == GateCat::DETECTOR || op.gate->cat == GateCat::OBSERVABLE_INCLUDE) {
+            m = std::max<uint32_t>(m, (uint32_t)op.targets.size());
+        }
+    }
+    return m;
+}
+
+void configure(gstim_sampler *s) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, s->device));
+    s->num_sms = prop.multiProcessorCount;
+    s->smem_optin = prop.sharedMemPerBlockOptin;
+
+    // chunk size: 2048 words unless a single item needs more
+    uint32_t need = 4 * (max_targets_in_one_item(s->circuit) + 64);
+    uint32_t chunk = 2048;
+    while (chunk < need) {
+        chunk <<= 1;
+    }
+    s->chunk_words = env_u32("GSTIM_CHUNK_WORDS", chunk);
+
+    s->lc = lower_circuit(s->circuit, (uint32_t)s->mode, s->chunk_words - GSTIM_HDR_WORDS);
+
+    // slots: cover the batch size below which 95% of all items live
+    std::vector<std::pair<uint32_t, uint64_t>> sizes;
+    for (const auto &b : s->lc.batches) {
+        uint32_t n = (uint32_t)(b.res_off.size() - 1);
+        sizes.push_back({n, n});
+    }
+    std::sort(sizes.begin(), sizes.end());
+    uint64_t acc = 0;
+    uint32_t p95 = 1;
+    for (auto &e : sizes) {
+        acc += e.second;
+        p95 = e.first;
+        if (acc * 100 >= s->lc.total_items * 95) {
+            break;
+        }
+    }
+    uint32_t slots = std::min<uint32_t>(1024, std::max<uint32_t>(32, (p95 + 31) / 32 * 32));
+    slots = env_u32("GSTIM_SLOTS", slots);
+
+    // K_max from the shared-memory budget
+    uint32_t Q = s->lc.num_qubits;
+    uint32_t q_pitch = Q | 1u;
+    size_t fixed = interp_smem_bytes(q_pitch, Q, 0, s->chunk_words);
+    size_t per_k = (size_t)2 * q_pitch * 16 + 16;
+    if (fixed + per_k > s->smem_optin) {
+        throw std::invalid_argument(
+            "Circuit frame (" + std::to_string(Q) + " active qubits) does not fit in " + std::to_string(s->smem_optin) +
+            " bytes of shared memory; the HBM-tiled frame path is not implemented yet.");
+    }
+    uint32_t K_max = (uint32_t)std::min<size_t>((s->smem_optin - fixed) / per_k, 32);
+
+    // lanes per item: fill up to ~512 threads
+    uint32_t target_threads = env_u32("GSTIM_THREADS", 512);
+    uint32_t G_log2 = 0;
+    while ((2u << G_log2) <= 32 && slots * (2u << G_log2) <= target_threads && (2u << G_log2) <= K_max) {
+        G_log2++;
+    }
+    G_log2 = env_u32("GSTIM_G_LOG2", G_log2);
+    uint32_t G = 1u << G_log2;
+    K_max = K_max / G * G;
+    K_max = std::min(K_max, env_u32("GSTIM_KMAX", K_max));
+    K_max = std::max(K_max / G * G, G);
+    s->slots = slots;
+    s->G_log2 = G_log2;
+    s->threads = slots * G;
+    s->K_max = K_max;
+    if (s->threads > 1024) {
+        throw std::invalid_argument("internal: thread count exceeds 1024");
+    }
+
+    s->words = serialize_program(s->lc, slots, s->chunk_words, &s->plan);
+    s->d_prog.ensure(s->words.size() * 4);
+    CK(cudaMemcpy(s->d_prog.p, s->words.data(), s->words.size() * 4, cudaMemcpyHostToDevice));
+    CK(interp_set_max_smem(interp_smem_bytes(q_pitch, Q, K_max, s->chunk_words)));
+}
+
+uint32_t choose_K(const gstim_sampler *s, uint64_t shots) {
+    uint32_t G = 1u << s->G_log2;
+    uint64_t cols = (shots + GSTIM_COL_SHOTS - 1) / GSTIM_COL_SHOTS;
+    // aim for at least two blocks per SM before growing the block
+    uint64_t k = cols / ((uint64_t)2 * s->num_sms);
+    k = k / G * G;
+    if (k < G) {
+        k = G;
+    }
+    if (k > s->K_max) {
+        k = s->K_max;
+    }
+    return (uint32_t)k;
+}
+
+cudaEvent_t get_event(gstim_sampler *s, size_t i) {
+    while (s->events.size() <= i) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        s->events.push_back(e);
+    }
+    return s->events[i];
+}
+
+struct RowMaps {
+    std::vector<uint32_t> main, obs;
+};
+
+RowMaps detector_row_maps(const gstim_sampler *s, uint32_t flags) {
+    RowMaps r;
+    uint32_t D = s->plan.num_det, L = s->plan.num_obs;
+    if (flags & GSTIM_PREPEND_OBS) {
+        for (uint32_t l = 0; l < L; l++) {
+            r.main.push_back(D + l);
+        }
+    }
+    for (uint32_t d = 0; d < D; d++) {
+        r.main.push_back(d);
+    }
+    if (flags & GSTIM_APPEND_OBS) {
+        for (uint32_t l = 0; l < L; l++) {
+            r.main.push_back(D + l);
+        }
+    }
+    if (flags & GSTIM_SEPARATE_OBS) {
+        for (uint32_t l = 0; l < L; l++) {
+            r.obs.push_back(D + l);
+        }
+    }
+    return r;
+}
+
+RowMaps measurement_row_maps(const gstim_sampler *s) {
+    RowMaps r;
+    uint32_t M = s->plan.num_meas;
+    r.main.resize(M);
+    for (uint32_t m = 0; m < M; m++) {
+        uint32_t inv = m < s->ref_bits.size() && s->ref_bits[m] ? 1u : 0u;
+        r.main[m] = m | (inv << 31);
+    }
+    return r;
+}
+
+// One pass of the sampler over `shots` shots. For every chunk, `sink(chunk_first_shot, chunk_shots,
+// table, row_words)` is called after the interpreter kernel has been enqueued on s->stream.
+template <typename SINK>
+void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
+    CK(cudaSetDevice(s->device));
+    s->last_launches = 0;
+    s->last_interp_ms = 0;
+    s->last_transpose_ms = 0;
+    if (shots == 0) {
+        return;
+    }
+    const uint32_t K = choose_K(s, shots);
+    s->last_K = K;
+    const uint32_t B = K * GSTIM_COL_SHOTS;
+    const uint32_t Q = s->plan.num_qubits, q_pitch = s->plan.q_pitch;
+    const size_t smem = interp_smem_bytes(q_pitch, Q, K, s->chunk_words);
+    const uint32_t rows = n_rows_of(s);
+    const uint64_t total_blocks = (shots + B - 1) / B;
+
+    // chunking: bit-major staging table limited to ~2 GiB
+    const uint64_t table_budget = (uint64_t)env_u32("GSTIM_TABLE_MB", 2048) << 20;
+    const uint64_t bytes_per_block = (uint64_t)std::max<uint32_t>(rows, 1) * K * 16;
+    uint64_t max_blocks = std::max<uint64_t>(table_budget / bytes_per_block, (uint64_t)s->num_sms);
+    max_blocks = std::min(max_blocks, total_blocks);
+    uint32_t grid_cap = (uint32_t)s->num_sms;  // one resident block per SM (shared memory bound)
+    s->d_table.ensure(bytes_per_block * max_blocks);
+    if (s->mode == GSTIM_MODE_DETECTORS) {
+        s->d_rec.ensure((size_t)grid_cap * s->plan.rec_ring * K * 16);
+    }
+
+    size_t ev = 0;
+    uint64_t done_blocks = 0;
+    while (done_blocks < total_blocks) {
+        const uint64_t nb = std::min(max_blocks, total_blocks - done_blocks);
+        const uint64_t first_shot = done_blocks * B;
+        const uint64_t chunk_shots = std::min<uint64_t>(nb * B, shots - first_shot);
+        InterpParams p{};
+        p.prog = (const uint32_t *)s->d_prog.p;
+        p.n_chunks = s->plan.n_chunks;
+        p.chunk_words = s->chunk_words;
+        p.Q = Q;
+        p.q_pitch = q_pitch;
+        p.K = K;
+        p.G_log2 = s->G_log2;
+        p.slots = s->slots;
+        p.n_blocks = (uint32_t)nb;
+        p.col0_base = s->next_col + done_blocks * K;
+        p.seed_lo = (uint32_t)s->seed;
+        p.seed_hi = (uint32_t)(s->seed >> 32);
+        p.out_row_stride = nb * K;
+        p.rec_mask = s->mode == GSTIM_MODE_DETECTORS ? s->plan.rec_ring - 1 : 0xFFFFFFFFu;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(nb, grid_cap);
+        if (s->mode == GSTIM_MODE_DETECTORS) {
+            p.out = (uint4 *)s->d_table.p;
+            p.rec = (uint4 *)s->d_rec.p;
+            p.rec_row_stride = K;
+            p.rec_block_stride = 0;
+            p.rec_cta_stride = (uint64_t)s->plan.rec_ring * K;
+        } else {
+            p.out = nullptr;
+            p.rec = (uint4 *)s->d_table.p;
+            p.rec_row_stride = nb * K;
+            p.rec_block_stride = K;
+            p.rec_cta_stride = 0;
+        }
+        cudaEvent_t e0 = get_event(s, ev++), e1 = get_event(s, ev++), e2 = get_event(s, ev++);
+        CK(cudaEventRecord(e0, s->stream));
+        CK(launch_interp(p, grid, s->threads, smem, s->stream));
+        CK(cudaEventRecord(e1, s->stream));
+        s->last_launches++;
+        sink(first_shot, chunk_shots, (const uint32_t *)s->d_table.p, (uint64_t)nb * K * 4);
+        CK(cudaEventRecord(e2, s->stream));
+        done_blocks += nb;
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    for (size_t i = 0; i + 3 <= ev; i += 3) {
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, s->events[i], s->events[i + 1]));
+        CK(cudaEventElapsedTime(&b, s->events[i + 1], s->events[i + 2]));
+        s->last_interp_ms += a;
+        s->last_transpose_ms += b;
+    }
+    s->next_col += total_blocks * K;
+}
+
+void upload_row_map(gstim_sampler *s, const std::vector<uint32_t> &m, size_t offset_words) {
+    if (!m.empty()) {
+        CK(cudaMemcpyAsync(
+            (uint32_t *)s->d_rowmap.p + offset_words, m.data(), m.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+}
+
+void transpose_to(
+    gstim_sampler *s,
+    const uint32_t *table,
+    uint64_t row_words,
+    const uint32_t *d_map,
+    uint32_t n_bits,
+    uint64_t n_shots,
+    uint8_t *out,
+    uint64_t pitch) {
+    TransposeParams t{};
+    t.table = table;
+    t.row_words = row_words;
+    t.row_map = d_map;
+    t.n_bits = n_bits;
+    t.n_shots = n_shots;
+    t.out = out;
+    t.out_pitch = pitch;
+    CK(launch_transpose_b8(t, s->stream));
+    if (n_bits && n_shots) {
+        s->last_launches++;
+    }
+}
+
+// device-resident dense b8 output
+void sample_to_device(
+    gstim_sampler *s,
+    uint64_t shots,
+    const RowMaps &maps,
+    uint8_t *main_out,
+    int64_t main_stride,
+    uint8_t *obs_out,
+    int64_t obs_stride) {
+    const uint32_t nb_main = (uint32_t)maps.main.size(), nb_obs = (uint32_t)maps.obs.size();
+    const uint64_t main_pitch = main_stride ? (uint64_t)main_stride : (nb_main + 7) / 8;
+    const uint64_t obs_pitch = obs_stride ? (uint64_t)obs_stride : (nb_obs + 7) / 8;
+    CK(cudaSetDevice(s->device));
+    s->d_rowmap.ensure((size_t)(nb_main + nb_obs + 1) * 4);
+    upload_row_map(s, maps.main, 0);
+    upload_row_map(s, maps.obs, nb_main);
+    const uint32_t *dm = (const uint32_t *)s->d_rowmap.p;
+    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t row_words) {
+        if (main_out && nb_main) {
+            transpose_to(s, table, row_words, dm, nb_main, n, main_out + first * main_pitch, main_pitch);
+        }
+        if (obs_out && nb_obs) {
+            transpose_to(s, table, row_words, dm + nb_main, nb_obs, n, obs_out + first * obs_pitch, obs_pitch);
+        }
+    });
+}
+
+void unpack_bits(const uint8_t *packed, size_t n_bits, uint8_t *out) {
+    static const auto lut = [] {
+        std::vector<uint64_t> t(256);
+        for (int v = 0; v < 256; v++) {
+            uint64_t w = 0;
+            for (int k = 0; k < 8; k++) {
+                w |= (uint64_t)((v >> k) & 1) << (8 * k);
+            }
+            t[v] = w;
+        }
+        return t;
+    }();
+    size_t full = n_bits / 8;
+    for (size_t i = 0; i < full; i++) {
+        memcpy(out + 8 * i, &lut[packed[i]], 8);
+    }
+    for (size_t k = full * 8; k < n_bits; k++) {
+        out[k] = (packed[k >> 3] >> (k & 7)) & 1;
+    }
+}
+
+// host output: transposed chunks are staged in device memory, copied to pinned host memory on a
+// second stream (double buffered) and scattered into the caller's (possibly strided / unpacked) rows.
+void sample_to_host(
+    gstim_sampler *s,
+    uint64_t shots,
+    const RowMaps &maps,
+    bool bit_packed,
+    uint8_t *main_out,
+    int64_t main_stride,
+    uint8_t *obs_out,
+    int64_t obs_stride) {
+    const uint32_t nb_main = (uint32_t)maps.main.size(), nb_obs = (uint32_t)maps.obs.size();
+    const uint64_t main_bytes = (nb_main + 7) / 8, obs_bytes = (nb_obs + 7) / 8;
+    const uint64_t main_row = bit_packed ? main_bytes : nb_main, obs_row = bit_packed ? obs_bytes : nb_obs;
+    const uint64_t main_pitch = main_stride ? (uint64_t)main_stride : main_row;
+    const uint64_t obs_pitch = obs_stride ? (uint64_t)obs_stride : obs_row;
+    const uint64_t stage_pitch = main_bytes + obs_bytes;  // per shot in the staging buffers
+    CK(cudaSetDevice(s->device));
+    s->d_rowmap.ensure((size_t)(nb_main + nb_obs + 1) * 4);
+    upload_row_map(s, maps.main, 0);
+    upload_row_map(s, maps.obs, nb_main);
+    const uint32_t *dm = (const uint32_t *)s->d_rowmap.p;
+    for (int i = 0; i < 2; i++) {
+        if (!s->stage_done[i]) {
+            CK(cudaEventCreateWithFlags(&s->stage_done[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->stage_ready[i], cudaEventDisableTiming));
+        }
+    }
+
+    struct Pending {
+        bool active = false;
+        uint64_t first = 0, n = 0;
+    } pending[2];
+    auto drain = [&](int b) {
+        if (!pending[b].active) {
+            return;
+        }
+        CK(cudaEventSynchronize(s->stage_done[b]));
+        const uint8_t *h = (const uint8_t *)s->h_stage[b].p;
+        const uint64_t first = pending[b].first, n = pending[b].n;
+        const uint8_t *hm = h, *ho = h + n * main_bytes;
+        if (main_out && nb_main) {
+            for (uint64_t i = 0; i < n; i++) {
+                uint8_t *dst = main_out + (first + i) * main_pitch;
+                if (bit_packed) {
+                    memcpy(dst, hm + i * main_bytes, main_bytes);
+                } else {
+                    unpack_bits(hm + i * main_bytes, nb_main, dst);
+                }
+            }
+        }
+        if (obs_out && nb_obs) {
+            for (uint64_t i = 0; i < n; i++) {
+                uint8_t *dst = obs_out + (first + i) * obs_pitch;
+                if (bit_packed) {
+                    memcpy(dst, ho + i * obs_bytes, obs_bytes);
+                } else {
+                    unpack_bits(ho + i * obs_bytes, nb_obs, dst);
+                }
+            }
+        }
+        pending[b].active = false;
+    };
+
+    int cur = 0;
+    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t row_words) {
+        drain(cur);  // buffer about to be reused
+        s->d_stage[cur].ensure(n * stage_pitch + 16);
+        s->h_stage[cur].ensure(n * stage_pitch + 16);
+        uint8_t *dmain = (uint8_t *)s->d_stage[cur].p;
+        uint8_t *dobs = dmain + n * main_bytes;
+        if (nb_main) {
+            transpose_to(s, table, row_words, dm, nb_main, n, dmain, main_bytes);
+        }
+        if (nb_obs) {
+            transpose_to(s, table, row_words, dm + nb_main, nb_obs, n, dobs, obs_bytes);
+        }
+        // copy on the second stream so the next chunk's interpreter overlaps the PCIe drain
+        CK(cudaEventRecord(s->stage_ready[cur], s->stream));
+        CK(cudaStreamWaitEvent(s->copy_stream, s->stage_ready[cur], 0));
+        CK(cudaMemcpyAsync(s->h_stage[cur].p, s->d_stage[cur].p, n * stage_pitch, cudaMemcpyDeviceToHost, s->copy_stream));
+        CK(cudaEventRecord(s->stage_done[cur], s->copy_stream));
+        pending[cur].active = true;
+        pending[cur].first = first;
+        pending[cur].n = n;
+        cur ^= 1;
+    });
+    drain(cur);
+    drain(cur ^ 1);
+}
+
+void check_flag_combo(uint32_t flags) {
+    int n = ((flags & GSTIM_PREPEND_OBS) != 0) + ((flags & GSTIM_APPEND_OBS) != 0) + ((flags & GSTIM_SEPARATE_OBS) != 0);
+    if (n > 1) {
+        throw std::out_of_range("Can't combine --prepend_observables, --append_observables, or --obs_out");
+    }
+}
+
+template <typename F>
+int guarded(F &&f) {
+    try {
+        f();
+        return GSTIM_OK;
+    } catch (const std::invalid_argument &e) {
+        g_last_error = e.what();
+        return GSTIM_ERR_INVALID_ARGUMENT;
+    } catch (const std::out_of_range &e) {
+        g_last_error = e.what();
+        return GSTIM_ERR_OUT_OF_RANGE;
+    } catch (const OomError &e) {
+        g_last_error = e.what();
+        return GSTIM_ERR_OOM;
+    } catch (const CudaError &e) {
+        g_last_error = e.what();
+        return GSTIM_ERR_CUDA;
+    } catch (const IoError &e) {
+        g_last_error = e.what();
+        return GSTIM_ERR_IO;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return GSTIM_ERR_INTERNAL;
+    }
+}
+
+void require(bool cond, const char *msg) {
+    if (!cond) {
+        throw std::invalid_argument(msg);
+    }
+}
+
+struct FdFile {
+    FILE *f = nullptr;
+    explicit FdFile(int fd) {
+        int d = dup(fd);
+        if (d < 0) {
+            throw IoError("dup() failed on the output file descriptor.");
+        }
+        f = fdopen(d, "wb");
+        if (!f) {
+            close(d);
+            throw IoError("fdopen() failed on the output file descriptor.");
+        }
+    }
+    ~FdFile() {
+        if (f) {
+            fclose(f);
+        }
+    }
+};
+
+// Streams shots to a file in any format; chunked through the host sampler.
+void sample_to_file(
+    gstim_sampler *s,
+    uint64_t shots,
+    const std::vector<uint32_t> &map,
+    FILE *f,
+    Format fmt,
+    char p1,
+    char p2,
+    size_t transition,
+    const std::vector<uint32_t> *obs_map,
+    FILE *obs_f,
+    Format obs_fmt) {
+    const uint32_t nb = (uint32_t)map.size();
+    const uint32_t nbo = obs_map ? (uint32_t)obs_map->size() : 0;
+    if ((fmt == Format::PTB64 || (obs_f && obs_fmt == Format::PTB64)) && shots % 64 != 0) {
+        throw std::invalid_argument("shots must be a multiple of 64 to use ptb64 format.");
+    }
+    // Host-side encoders work on b8 rows, or on the bit-major rows for ptb64.
+    CK(cudaSetDevice(s->device));
+    s->d_rowmap.ensure((size_t)(nb + nbo + 1) * 4);
+    upload_row_map(s, map, 0);
+    if (obs_map) {
+        upload_row_map(s, *obs_map, nb);
+    }
+    const uint32_t *dm = (const uint32_t *)s->d_rowmap.p;
+    const uint64_t nbytes = (nb + 7) / 8, nbytes_o = (nbo + 7) / 8;
+    std::vector<uint8_t> host;
+    std::vector<uint32_t> host_table;
+    auto emit = [&](const uint32_t *table,
+                    uint64_t row_words,
+                    uint64_t n,
+                    const std::vector<uint32_t> &m,
+                    const uint32_t *d_m,
+                    uint64_t bytes,
+                    FILE *out,
+                    Format of,
+                    char c1,
+                    char c2,
+                    size_t tr) {
+        if (of == Format::PTB64) {
+            uint32_t rows = n_rows_of(s);
+            host_table.resize((size_t)rows * row_words);
+            CK(cudaMemcpyAsync(host_table.data(), table, host_table.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            write_ptb64(out, host_table.data(), row_words, m.data(), m.size(), n);
+        } else {
+            s->d_stage[0].ensure(n * bytes + 16);
+            transpose_to(s, table, row_words, d_m, (uint32_t)m.size(), n, (uint8_t *)s->d_stage[0].p, bytes);
+            host.resize(n * bytes + 1);
+            CK(cudaMemcpyAsync(host.data(), s->d_stage[0].p, n * bytes, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            write_shots(out, host.data(), bytes, n, m.size(), of, c1, c2, tr);
+        }
+    };
+    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t row_words) {
+        (void)first;
+        if (obs_f && obs_map) {
+            emit(table, row_words, n, *obs_map, dm + nb, nbytes_o, obs_f, obs_fmt, 'L', 'L', nbo);
+        }
+        emit(table, row_words, n, map, dm, nbytes, f, fmt, p1, p2, transition);
+    });
+    if (fflush(f) != 0 || (obs_f && fflush(obs_f) != 0)) {
+        throw IoError("Failed to flush result data.");
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int gstim_version(void) {
+    return 1;
+}
+
+const char *gstim_last_error(void) {
+    return g_last_error.c_str();
+}
+
+int gstim_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gstim_circuit_stats(const char *circuit_text, size_t text_len, gstim_stats *out) {
+    return guarded([&] {
+        require(circuit_text != nullptr && out != nullptr, "NULL argument.");
+        Circuit c = Circuit::from_text(std::string_view(circuit_text, text_len));
+        // lowering validates what the parser cannot (record lookbacks, bit targets) without touching a GPU
+        LoweredCircuit lc = lower_circuit(c, GSTIM_MODE_DETECTORS, 2048 - GSTIM_HDR_WORDS);
+        memset(out, 0, sizeof(*out));
+        out->num_qubits = lc.stats.num_qubits;
+        out->num_measurements = lc.stats.num_measurements;
+        out->num_detectors = lc.stats.num_detectors;
+        out->num_observables = lc.stats.num_observables;
+        out->max_lookback = lc.stats.max_lookback;
+        out->active_qubits = lc.num_qubits;
+        out->num_batches = lc.batches.size();
+        out->num_noise_sites = lc.num_sites;
+        out->num_collapse_sites = lc.num_csites;
+    });
+}
+
+int gstim_lower_text(
+    const char *circuit_text,
+    size_t text_len,
+    int mode,
+    uint32_t slots,
+    uint32_t chunk_words,
+    uint32_t *words,
+    size_t *n_words,
+    uint32_t plan_out[16]) {
+    return guarded([&] {
+        require(circuit_text != nullptr && n_words != nullptr, "NULL argument.");
+        require(mode == GSTIM_MODE_DETECTORS || mode == GSTIM_MODE_MEASUREMENTS, "bad mode.");
+        require(slots >= 1, "slots must be positive.");
+        Circuit c = Circuit::from_text(std::string_view(circuit_text, text_len));
+        if (chunk_words == 0) {
+            uint32_t need = 4 * (max_targets_in_one_item(c) + 64);
+            chunk_words = 2048;
+            while (chunk_words < need) {
+                chunk_words <<= 1;
+            }
+        }
+        LoweredCircuit lc = lower_circuit(c, (uint32_t)mode, chunk_words - GSTIM_HDR_WORDS);
+        GstimPlan plan;
+        std::vector<uint32_t> w = serialize_program(lc, slots, chunk_words, &plan);
+        if (plan_out != nullptr) {
+            memset(plan_out, 0, 16 * sizeof(uint32_t));
+            memcpy(plan_out, &plan, sizeof(plan));
+        }
+        if (words == nullptr) {
+            *n_words = w.size();
+            return;
+        }
+        require(*n_words >= w.size(), "program buffer too small.");
+        memcpy(words, w.data(), w.size() * 4);
+        *n_words = w.size();
+    });
+}
+
+int gstim_create_from_text(const char *circuit_text, size_t text_len, int mode, uint64_t seed, int device, gstim_sampler **out) {
+    return guarded([&] {
+        require(out != nullptr, "out must not be NULL.");
+        *out = nullptr;
+        require(circuit_text != nullptr, "circuit_text must not be NULL.");
+        require(mode == GSTIM_MODE_DETECTORS || mode == GSTIM_MODE_MEASUREMENTS, "mode must be GSTIM_MODE_DETECTORS or GSTIM_MODE_MEASUREMENTS.");
+        auto s = std::make_unique<gstim_sampler>();
+        s->mode = mode;
+        s->seed = seed;
+        s->device = device;
+        s->circuit = Circuit::from_text(std::string_view(circuit_text, text_len));
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            cudaGetLastError();
+            // Validate the circuit first so argument errors surface identically with or without a GPU...
+            lower_circuit(s->circuit, (uint32_t)mode, 2048 - GSTIM_HDR_WORDS);
+            // ...but there is no CPU fallback.
+            throw CudaError("No usable CUDA device: this library has no CPU fallback.");
+        }
+        require(device >= 0 && device < n, "CUDA device ordinal out of range.");
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        configure(s.get());
+        *out = s.release();
+    });
+}
+
+void gstim_destroy(gstim_sampler *s) {
+    if (s) {
+        cudaSetDevice(s->device);
+        delete s;
+    }
+}
+
+int gstim_get_stats(const gstim_sampler *s, gstim_stats *out) {
+    return guarded([&] {
+        require(s && out, "NULL argument.");
+        memset(out, 0, sizeof(*out));
+        out->num_qubits = s->lc.stats.num_qubits;
+        out->num_measurements = s->lc.stats.num_measurements;
+        out->num_detectors = s->lc.stats.num_detectors;
+        out->num_observables = s->lc.stats.num_observables;
+        out->max_lookback = s->lc.stats.max_lookback;
+        out->active_qubits = s->lc.num_qubits;
+        out->program_words = s->words.size();
+        out->num_batches = s->plan.n_batches;
+        out->num_barriers = s->plan.n_barriers;
+        out->num_noise_sites = s->lc.num_sites;
+        out->num_collapse_sites = s->lc.num_csites;
+        out->threads = s->threads;
+        out->lanes_per_item = 1u << s->G_log2;
+        out->slots = s->slots;
+        out->max_columns = s->K_max;
+        out->chunk_words = s->chunk_words;
+        out->smem_bytes_max = (uint32_t)interp_smem_bytes(s->plan.q_pitch, s->plan.num_qubits, s->K_max, s->chunk_words);
+    });
+}
+
+int gstim_get_program(const gstim_sampler *s, uint32_t *words, size_t *n_words) {
+    return guarded([&] {
+        require(s && n_words, "NULL argument.");
+        if (words == nullptr) {
+            *n_words = s->words.size();
+            return;
+        }
+        require(*n_words >= s->words.size(), "program buffer too small.");
+        memcpy(words, s->words.data(), s->words.size() * 4);
+        *n_words = s->words.size();
+    });
+}
+
+int gstim_set_reference_sample(gstim_sampler *s, const uint8_t *bits, size_t n_bits) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(s->mode == GSTIM_MODE_MEASUREMENTS, "Reference samples only apply to measurement samplers.");
+        if (bits == nullptr) {
+            s->ref_bits.clear();
+            return;
+        }
+        require(n_bits == s->plan.num_meas, "reference sample must have num_measurements bits.");
+        s->ref_bits.resize(n_bits);
+        for (size_t k = 0; k < n_bits; k++) {
+            s->ref_bits[k] = (bits[k >> 3] >> (k & 7)) & 1;
+        }
+    });
+}
+
+int gstim_get_shot_offset(const gstim_sampler *s, uint64_t *offset) {
+    return guarded([&] {
+        require(s && offset, "NULL argument.");
+        *offset = s->next_col * GSTIM_COL_SHOTS;
+    });
+}
+
+int gstim_set_shot_offset(gstim_sampler *s, uint64_t offset) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(offset % GSTIM_COL_SHOTS == 0, "shot offset must be a multiple of 128.");
+        s->next_col = offset / GSTIM_COL_SHOTS;
+    });
+}
+
+int gstim_sample_detectors(
+    gstim_sampler *s, uint64_t shots, uint32_t flags, void *dets_out, int64_t dets_shot_stride, void *obs_out, int64_t obs_shot_stride) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(s->mode == GSTIM_MODE_DETECTORS, "Not a detector sampler.");
+        require(dets_shot_stride >= 0 && obs_shot_stride >= 0, "negative strides are not supported.");
+        check_flag_combo(flags);
+        RowMaps maps = detector_row_maps(s, flags);
+        sample_to_host(
+            s, shots, maps, (flags & GSTIM_BIT_PACKED) != 0, (uint8_t *)dets_out, dets_shot_stride, (uint8_t *)obs_out, obs_shot_stride);
+    });
+}
+
+int gstim_sample_measurements(gstim_sampler *s, uint64_t shots, uint32_t flags, void *out, int64_t shot_stride) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(s->mode == GSTIM_MODE_MEASUREMENTS, "Not a measurement sampler.");
+        require(shot_stride >= 0, "negative strides are not supported.");
+        RowMaps maps = measurement_row_maps(s);
+        sample_to_host(s, shots, maps, (flags & GSTIM_BIT_PACKED) != 0, (uint8_t *)out, shot_stride, nullptr, 0);
+    });
+}
+
+int gstim_sample_detectors_device(
+    gstim_sampler *s, uint64_t shots, uint32_t flags, void *dets_out_dev, int64_t dets_shot_stride, void *obs_out_dev, int64_t obs_shot_stride) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(s->mode == GSTIM_MODE_DETECTORS, "Not a detector sampler.");
+        require(dets_shot_stride >= 0 && obs_shot_stride >= 0, "negative strides are not supported.");
+        check_flag_combo(flags);
+        RowMaps maps = detector_row_maps(s, flags);
+        sample_to_device(s, shots, maps, (uint8_t *)dets_out_dev, dets_shot_stride, (uint8_t *)obs_out_dev, obs_shot_stride);
+    });
+}
+
+int gstim_sample_measurements_device(gstim_sampler *s, uint64_t shots, void *out_dev, int64_t shot_stride) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(s->mode == GSTIM_MODE_MEASUREMENTS, "Not a measurement sampler.");
+        require(shot_stride >= 0, "negative strides are not supported.");
+        RowMaps maps = measurement_row_maps(s);
+        sample_to_device(s, shots, maps, (uint8_t *)out_dev, shot_stride, nullptr, 0);
+    });
+}
+
+int gstim_sample_detectors_to_fd(
+    gstim_sampler *s, uint64_t shots, uint32_t flags, int fd, const char *format, int obs_fd, const char *obs_format) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(s->mode == GSTIM_MODE_DETECTORS, "Not a detector sampler.");
+        Format fmt = parse_format(format);
+        Format ofmt = obs_fd >= 0 ? parse_format(obs_format) : Format::F01;
+        uint32_t f = flags & (GSTIM_PREPEND_OBS | GSTIM_APPEND_OBS);
+        if (obs_fd >= 0) {
+            f |= GSTIM_SEPARATE_OBS;
+        }
+        check_flag_combo(f);
+        RowMaps maps = detector_row_maps(s, f);
+        FdFile out(fd);
+        std::unique_ptr<FdFile> obs;
+        if (obs_fd >= 0) {
+            obs = std::make_unique<FdFile>(obs_fd);
+        }
+        char c1 = 'D', c2 = 'L';
+        size_t tr = s->plan.num_det;
+        if (f & GSTIM_PREPEND_OBS) {
+            c1 = 'L';
+            c2 = 'D';
+            tr = s->plan.num_obs;
+        }
+        sample_to_file(s, shots, maps.main, out.f, fmt, c1, c2, tr, obs ? &maps.obs : nullptr, obs ? obs->f : nullptr, ofmt);
+    });
+}
+
+int gstim_sample_measurements_to_fd(gstim_sampler *s, uint64_t shots, int fd, const char *format) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(s->mode == GSTIM_MODE_MEASUREMENTS, "Not a measurement sampler.");
+        Format fmt = parse_format(format);
+        RowMaps maps = measurement_row_maps(s);
+        FdFile out(fd);
+        sample_to_file(s, shots, maps.main, out.f, fmt, 'M', 'M', maps.main.size(), nullptr, nullptr, Format::F01);
+    });
+}
+
+int gstim_detector_flip_counts(gstim_sampler *s, uint64_t shots, uint64_t *counts_host, void *counts_dev) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(s->mode == GSTIM_MODE_DETECTORS, "Not a detector sampler.");
+        const uint32_t rows = n_rows_of(s);
+        CK(cudaSetDevice(s->device));
+        s->d_counts.ensure((size_t)std::max<uint32_t>(rows, 1) * 8);
+        CK(cudaMemsetAsync(s->d_counts.p, 0, (size_t)rows * 8, s->stream));
+        run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t row_words) {
+            (void)first;
+            CK(launch_row_popcount(table, row_words, rows, n, (unsigned long long *)s->d_counts.p, s->stream));
+            s->last_launches++;
+        });
+        if (counts_dev) {
+            CK(cudaMemcpyAsync(counts_dev, s->d_counts.p, (size_t)rows * 8, cudaMemcpyDeviceToDevice, s->stream));
+        }
+        if (counts_host) {
+            CK(cudaMemcpyAsync(counts_host, s->d_counts.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, s->stream));
+        }
+        CK(cudaStreamSynchronize(s->stream));
+    });
+}
+
+int gstim_last_launch_count(const gstim_sampler *s, uint64_t *launches) {
+    return guarded([&] {
+        require(s && launches, "NULL argument.");
+        *launches = s->last_launches;
+    });
+}
+
+int gstim_last_block_columns(const gstim_sampler *s, uint32_t *columns) {
+    return guarded([&] {
+        require(s && columns, "NULL argument.");
+        *columns = s->last_K;
+    });
+}
+
+int gstim_last_kernel_ms(const gstim_sampler *s, float *interp_ms, float *transpose_ms) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        if (interp_ms) {
+            *interp_ms = s->last_interp_ms;
+        }
+        if (transpose_ms) {
+            *transpose_ms = s->last_transpose_ms;
+        }
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// kernels.cuh — launch parameter blocks shared between kernels.cu and api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "program.h"
+
+namespace gstim {
+
+struct InterpParams {
+    const uint32_t *prog;      // lowered program in global memory (16-byte aligned, n_chunks*chunk_words words)
+    uint32_t n_chunks;
+    uint32_t chunk_words;
+    uint32_t Q;                // compact qubit count
+    uint32_t q_pitch;          // shared-memory row pitch (uint4 units), odd
+    uint32_t K;                // 128-shot columns per thread block
+    uint32_t G_log2;           // log2(lanes per item)
+    uint32_t slots;            // blockDim.x >> G_log2
+    uint32_t n_blocks;         // shot blocks in this launch
+    uint64_t col0_base;        // global column index (shot/128) of block 0
+    uint32_t seed_lo, seed_hi; // Philox key
+    uint4 *rec;                // measurement record rows
+    uint64_t rec_block_stride; // uint4 units between consecutive shot blocks (measurement mode: rows live in the table)
+    uint64_t rec_cta_stride;   // uint4 units between CTAs (detector mode: per-CTA L2-resident ring)
+    uint64_t rec_row_stride;   // uint4 units between consecutive record rows
+    uint32_t rec_mask;         // ring mask (detector mode) or 0xFFFFFFFF
+    uint4 *out;                // detector/observable rows (bit-major); block g owns uint4 columns [g*K,(g+1)*K)
+    uint64_t out_row_stride;   // uint4 units
+};
+
+// Shared memory the interpreter needs for (Q, K, chunk_words).
+size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words);
+cudaError_t launch_interp(const InterpParams &p, uint32_t grid, uint32_t threads, size_t smem, cudaStream_t stream);
+cudaError_t interp_set_max_smem(size_t smem);
+
+struct TransposeParams {
+    const uint32_t *table;     // bit-major rows: table[row * row_words + shot_word]
+    uint64_t row_words;        // uint32 words per row
+    const uint32_t *row_map;   // n_bits entries: source row | invert<<31
+    uint32_t n_bits;           // bits per shot in the output
+    uint64_t n_shots;          // shots to emit (may be less than row_words*32)
+    uint8_t *out;              // dense shot-major output
+    uint64_t out_pitch;        // bytes per shot in `out` (>= ceil(n_bits/8))
+};
+cudaError_t launch_transpose_b8(const TransposeParams &p, cudaStream_t stream);
+
+// popcount of every row of a bit-major table over the first n_shots shots -> counts[row] (uint64, accumulated)
+cudaError_t launch_row_popcount(
+    const uint32_t *table, uint64_t row_words, uint32_t n_rows, uint64_t n_shots, unsigned long long *counts, cudaStream_t stream);
+
+}  // namespace gstim

@@ -1,0 +1,1057 @@
+// lowering.cc — see lowering.h.
+#include "lowering.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+
+namespace gstim {
+
+uint32_t Batch::words() const {
+    if (op == GOP_XORROWS) {
+        return GSTIM_HDR_WORDS + (uint32_t)dst.size() + (uint32_t)off.size() + (uint32_t)idx.size();
+    }
+    return GSTIM_HDR_WORDS + (uint32_t)payload.size();
+}
+
+namespace {
+
+constexpr uint32_t RES_WRITE = 1u << 31;
+constexpr uint32_t ITEM_X = 1u << 30;  // component flags in OBS_PAULI / FEEDBACK / CORR payload words
+constexpr uint32_t ITEM_Z = 1u << 31;
+
+// Probability -> event rate per shot of the exponential clock. The reference narrows every
+// probability to float before sampling (probability_util.h:47, measure_record_batch.inl:52).
+double rate_of(double p) {
+    float f = (float)p;
+    if (!(f > 0)) {
+        return 0.0;
+    }
+    if (f >= 1) {
+        return std::numeric_limits<double>::infinity();
+    }
+    return -std::log1p(-(double)f);
+}
+
+uint32_t thr(double frac) {
+    double v = std::floor(frac * 4294967296.0);
+    if (!(v > 0)) {
+        return 0;
+    }
+    if (v >= 4294967295.0) {
+        return 0xFFFFFFFFu;
+    }
+    return (uint32_t)v;
+}
+
+struct Key {
+    uint32_t op = 0, flags = 0, aux = 0, extra = 0;
+    double lambda = 0;
+    uint32_t t1 = 0, t2 = 0, t3 = 0;
+    const uint32_t *table = nullptr;  // NOISE2 PAULI_CHANNEL_2 thresholds (15 words) or null
+};
+
+struct Lowerer {
+    LoweredCircuit lc;
+    uint32_t max_words;
+    uint32_t Q = 0;
+    uint32_t res_clock = 0, res_flag = 0, res_rec0 = 0, res_out0 = 0;
+    uint32_t rec_mask = 0xFFFFFFFFu;
+
+    // running counters (the RNG addressing contract)
+    uint32_t site = 0, csite = 0;
+    uint64_t meas = 0;
+    uint64_t det = 0;
+
+    // current batch
+    Batch cur;
+    bool open = false;
+    bool cur_uses_site = false, cur_uses_csite = false, cur_uses_rec = false;
+    uint32_t stamp = 1;
+    std::vector<uint32_t> rd_stamp, wr_stamp;
+
+    explicit Lowerer(uint32_t max_words) : max_words(max_words) {}
+
+    uint32_t q_of(uint32_t target) const {
+        uint32_t v = target & T_VALUE_MASK;
+        return lc.qubit_map[v];
+    }
+    uint32_t rec_res(uint64_t m) const {
+        return res_rec0 + (uint32_t)(m & rec_mask);
+    }
+    uint64_t rec_abs(uint32_t target, const char *gate) const {
+        uint64_t k = target & T_VALUE_MASK;
+        if (k == 0 || k > meas) {
+            throw std::out_of_range(
+                std::string("Referred to a measurement record before the beginning of time in ") + gate + ".");
+        }
+        return meas - k;
+    }
+
+    void flush() {
+        if (!open) {
+            return;
+        }
+        if (cur.op == GOP_XORROWS) {
+            cur.n_items = (uint32_t)cur.dst.size();
+        }
+        lc.max_items = std::max(lc.max_items, (uint32_t)(cur.res_off.size() - 1));
+        lc.total_items += cur.res_off.size() - 1;
+        lc.batches.push_back(std::move(cur));
+        cur = Batch();
+        open = false;
+        stamp++;
+    }
+
+    bool same_key(const Key &k) const {
+        if (cur.op != k.op || cur.flags != k.flags || cur.aux != k.aux || cur.extra != k.extra || cur.t1 != k.t1 ||
+            cur.t2 != k.t2 || cur.t3 != k.t3) {
+            return false;
+        }
+        if (memcmp(&cur.lambda, &k.lambda, sizeof(double)) != 0) {
+            return false;
+        }
+        if (k.table != nullptr && memcmp(cur.payload.data(), k.table, 15 * sizeof(uint32_t)) != 0) {
+            return false;
+        }
+        return true;
+    }
+
+    // Adds one item. `res` lists resource ids, RES_WRITE-tagged when written.
+    // use_*: whether this op consumes that counter (continuity is then required inside a batch).
+    void add(
+        const Key &k,
+        const uint32_t *item_words,
+        uint32_t n_item_words,
+        const uint32_t *res,
+        uint32_t n_res,
+        bool use_site,
+        uint32_t site_v,
+        bool use_csite,
+        uint32_t csite_v,
+        bool use_rec,
+        uint32_t rec_v,
+        bool never_merge = false) {
+        bool ok = open && !never_merge && same_key(k) && cur.op != GOP_CORR;
+        if (ok) {
+            uint32_t n = cur.n_items;
+            if ((use_site && cur.site0 + n != site_v) || (use_csite && cur.csite0 + n != csite_v) ||
+                (use_rec && cur.rec0 + n != rec_v)) {
+                ok = false;
+            }
+        }
+        if (ok && cur.words() + n_item_words + GSTIM_HDR_WORDS > max_words) {
+            ok = false;
+        }
+        if (ok) {
+            for (uint32_t i = 0; i < n_res; i++) {
+                uint32_t r = res[i] & ~RES_WRITE;
+                if (wr_stamp[r] == stamp || ((res[i] & RES_WRITE) && rd_stamp[r] == stamp)) {
+                    ok = false;
+                    break;
+                }
+            }
+        }
+        if (!ok) {
+            flush();
+            open = true;
+            cur.op = k.op;
+            cur.flags = k.flags;
+            cur.aux = k.aux;
+            cur.extra = k.extra;
+            cur.lambda = k.lambda;
+            cur.t1 = k.t1;
+            cur.t2 = k.t2;
+            cur.t3 = k.t3;
+            cur.site0 = site_v;
+            cur.csite0 = csite_v;
+            cur.rec0 = rec_v;
+            cur.res_off.push_back(0);
+            if (k.table != nullptr) {
+                cur.payload.assign(k.table, k.table + 15);
+            }
+        }
+        cur.payload.insert(cur.payload.end(), item_words, item_words + n_item_words);
+        for (uint32_t i = 0; i < n_res; i++) {
+            uint32_t r = res[i] & ~RES_WRITE;
+            if (res[i] & RES_WRITE) {
+                wr_stamp[r] = stamp;
+            } else {
+                rd_stamp[r] = stamp;
+            }
+            cur.res.push_back(res[i]);
+        }
+        cur.res_off.push_back((uint32_t)cur.res.size());
+        cur.n_items++;
+    }
+
+    // ---- op emitters -------------------------------------------------------------------------
+    void cliff1(uint32_t mat, uint32_t q) {
+        Key k;
+        k.op = GOP_CLIFF1;
+        k.aux = mat;
+        uint32_t r = q | RES_WRITE;
+        add(k, &q, 1, &r, 1, false, 0, false, 0, false, 0);
+    }
+    void cliff2(uint32_t mat, uint32_t q1, uint32_t q2) {
+        Key k;
+        k.op = GOP_CLIFF2;
+        k.aux = mat;
+        uint32_t w = q1 | (q2 << 16);
+        uint32_t r[2] = {q1 | RES_WRITE, q2 | RES_WRITE};
+        add(k, &w, 1, r, 2, false, 0, false, 0, false, 0);
+    }
+    void feedback(uint64_t rec_index, uint32_t q, uint32_t comps) {
+        Key k;
+        k.op = GOP_FEEDBACK;
+        uint32_t w[2] = {(uint32_t)(rec_index & rec_mask), q | comps};
+        uint32_t r[2] = {rec_res(rec_index), q | RES_WRITE};
+        add(k, w, 2, r, 2, false, 0, false, 0, false, 0);
+    }
+    // basis/kind measurement or reset of one qubit. Allocates csite (+ rec and site when it records).
+    void measure(uint32_t basis, uint32_t kind, uint32_t q) {
+        Key k;
+        k.op = GOP_MEASURE;
+        k.aux = basis | (kind << 2);
+        bool records = kind != GK_R;
+        uint32_t r[2] = {q | RES_WRITE, 0};
+        uint32_t nr = 1;
+        if (records) {
+            r[1] = rec_res(meas) | RES_WRITE;
+            nr = 2;
+        }
+        add(k, &q, 1, r, nr, false, 0, true, csite, records, (uint32_t)meas);
+        csite++;
+        if (records) {
+            meas++;
+            site++;
+        }
+    }
+    // Result-flip noise on record rows [rec_first, rec_first+n) whose sites are [site_first, ...).
+    void rec_noise(double p, const std::vector<uint32_t> &clock_qubits, uint64_t rec_first, uint32_t site_first) {
+        double lam = rate_of(p);
+        if (lam == 0) {
+            return;
+        }
+        Key k;
+        k.op = GOP_NOISE1;
+        k.flags = GF_REC;
+        k.lambda = lam;
+        for (size_t i = 0; i < clock_qubits.size(); i++) {
+            uint32_t q = clock_qubits[i];
+            uint32_t r[2] = {q | RES_WRITE, rec_res(rec_first + i) | RES_WRITE};
+            add(k, &q, 1, r, 2, true, site_first + (uint32_t)i, false, 0, true, (uint32_t)(rec_first + i));
+        }
+    }
+    void noise1(double lam, uint32_t cats, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t q, uint32_t flags, uint64_t rec_index) {
+        Key k;
+        k.op = GOP_NOISE1;
+        k.flags = flags;
+        k.aux = cats;
+        k.lambda = lam;
+        k.t1 = t1;
+        k.t2 = t2;
+        k.t3 = t3;
+        uint32_t r[2] = {q | RES_WRITE, 0};
+        uint32_t nr = 1;
+        if (flags & GF_REC) {
+            r[1] = rec_res(rec_index) | RES_WRITE;
+            nr = 2;
+        }
+        add(k, &q, 1, r, nr, true, site, false, 0, (flags & GF_REC) != 0, (uint32_t)rec_index);
+    }
+    void rec_zero(uint64_t rec_index) {
+        Key k;
+        k.op = GOP_RECZERO;
+        uint32_t r = rec_res(rec_index) | RES_WRITE;
+        add(k, nullptr, 0, &r, 1, false, 0, false, 0, true, (uint32_t)rec_index);
+    }
+    void xor_rows(uint32_t dst_row, const std::vector<uint64_t> &recs, bool accum) {
+        Key k;
+        k.op = GOP_XORROWS;
+        k.flags = accum ? GF_ACCUM : 0;
+        std::vector<uint32_t> r;
+        r.push_back((res_out0 + dst_row) | RES_WRITE);
+        for (uint64_t m : recs) {
+            r.push_back(rec_res(m));
+        }
+        // XORROWS payload is kept split (dst/off/idx); make room before add() decides on merging.
+        uint32_t need = 2 + (uint32_t)recs.size();
+        if (open && cur.op == GOP_XORROWS && cur.words() + need + GSTIM_HDR_WORDS > max_words) {
+            flush();
+        }
+        add(k, nullptr, 0, r.data(), (uint32_t)r.size(), false, 0, false, 0, false, 0);
+        if (cur.off.empty()) {
+            cur.off.push_back(0);
+        }
+        cur.dst.push_back(dst_row);
+        for (uint64_t m : recs) {
+            cur.idx.push_back((uint32_t)(m & rec_mask));
+        }
+        cur.off.push_back((uint32_t)cur.idx.size());
+    }
+    void obs_pauli(uint32_t dst_row, uint32_t q, uint32_t comps) {
+        Key k;
+        k.op = GOP_OBS_PAULI;
+        uint32_t w[2] = {dst_row, q | comps};
+        uint32_t r[2] = {(res_out0 + dst_row) | RES_WRITE, q};
+        add(k, w, 2, r, 2, false, 0, false, 0, false, 0);
+    }
+
+    // ---- gate lowering -----------------------------------------------------------------------
+    void do_cliff1_list(uint32_t mat, const std::vector<uint32_t> &qs) {
+        for (uint32_t q : qs) {
+            cliff1(mat, q);
+        }
+    }
+    // pairs given as compact qubits or bit targets (T_REC/T_SWEEP words kept raw)
+    void do_controlled(const GateInfo &g, uint32_t a, uint32_t b) {
+        bool a_bit = (a & (T_REC | T_SWEEP)) != 0, b_bit = (b & (T_REC | T_SWEEP)) != 0;
+        if (!a_bit && !b_bit) {
+            cliff2(g.param, q_of(a), q_of(b));
+            return;
+        }
+        std::string name = g.name;
+        // Which side is the classical control, and which Pauli does it apply?
+        uint32_t comps = 0;
+        uint32_t bit = 0, qt = 0;
+        if (name == "CX" || name == "CY") {
+            if (b_bit) {
+                throw std::invalid_argument(
+                    std::string("Controlled ") + (name == "CX" ? "X" : "Y") + " had a bit as its target, instead of its control.");
+            }
+            bit = a;
+            qt = b;
+            comps = name == "CX" ? ITEM_X : (ITEM_X | ITEM_Z);
+        } else if (name == "XCZ" || name == "YCZ") {
+            if (a_bit) {
+                throw std::invalid_argument(
+                    std::string("Controlled ") + (name == "XCZ" ? "X" : "Y") + " had a bit as its target, instead of its control.");
+            }
+            bit = b;
+            qt = a;
+            comps = name == "XCZ" ? ITEM_X : (ITEM_X | ITEM_Z);
+        } else {  // CZ: either side may be the bit; both bits -> no effect
+            if (a_bit && b_bit) {
+                return;
+            }
+            bit = a_bit ? a : b;
+            qt = a_bit ? b : a;
+            comps = ITEM_Z;
+        }
+        if (bit & T_SWEEP) {
+            return;  // no sweep data when sampling (frame_simulator.inl:146-148)
+        }
+        feedback(rec_abs(bit, g.name), q_of(qt), comps);
+    }
+
+    void do_measure_gate(const Instruction &op) {
+        uint32_t basis = op.gate->param & 3, kind = op.gate->param >> 2;
+        uint64_t rec_first = meas;
+        uint32_t site_first = site;
+        std::vector<uint32_t> qs;
+        for (uint32_t t : op.targets) {
+            uint32_t q = q_of(t);
+            measure(basis, kind, q);
+            qs.push_back(q);
+        }
+        if (kind != GK_R && !op.args.empty()) {
+            rec_noise(op.args[0], qs, rec_first, site_first);
+        }
+    }
+
+    void do_mpad(const Instruction &op) {
+        uint64_t rec_first = meas;
+        uint32_t site_first = site;
+        for (size_t i = 0; i < op.targets.size(); i++) {
+            rec_zero(meas);
+            meas++;
+            site++;
+        }
+        double lam = op.args.empty() ? 0 : rate_of(op.args[0]);
+        if (lam != 0) {
+            for (size_t i = 0; i < op.targets.size(); i++) {
+                Key k;
+                k.op = GOP_NOISE1;
+                k.flags = GF_REC | GF_NOFRAME;
+                k.lambda = lam;
+                k.extra = Q + 1;  // clock = global clock (index Q)
+                uint32_t r[2] = {res_clock | RES_WRITE, rec_res(rec_first + i) | RES_WRITE};
+                uint32_t dummy = Q;
+                add(k, &dummy, 1, r, 2, true, site_first + (uint32_t)i, false, 0, true, (uint32_t)(rec_first + i));
+            }
+        }
+    }
+
+    struct Product {
+        std::vector<std::pair<uint32_t, uint32_t>> terms;  // (compact qubit, xz bits: 1=x 2=z), sorted by ORIGINAL index
+        std::vector<uint32_t> bits;                        // classical bit targets
+    };
+    // Splits a combiner-joined target list into products; multiplies same-qubit terms.
+    std::vector<Product> read_products(const Instruction &op, bool allow_bits) {
+        std::vector<Product> out;
+        size_t k = 0;
+        const auto &ts = op.targets;
+        while (k < ts.size()) {
+            size_t end = k + 1;
+            while (end < ts.size() && ts[end] == T_COMBINER) {
+                end += 2;
+            }
+            std::vector<std::pair<uint32_t, uint32_t>> acc;  // original qubit -> xz
+            bool imag = false;
+            Product p;
+            for (size_t j = k; j < end; j += 2) {
+                uint32_t t = ts[j];
+                if (t & (T_REC | T_SWEEP)) {
+                    if (!allow_bits) {
+                        throw std::invalid_argument(std::string("Found an unsupported target in ") + op.gate->name + ".");
+                    }
+                    p.bits.push_back(t);
+                    continue;
+                }
+                uint32_t q = t & T_VALUE_MASK;
+                uint32_t xz = ((t & T_PAULI_X) ? 1u : 0u) | ((t & T_PAULI_Z) ? 2u : 0u);
+                bool found = false;
+                for (auto &e : acc) {
+                    if (e.first == q) {
+                        if (e.second != 0 && xz != 0 && e.second != xz) {
+                            imag = !imag;
+                        }
+                        e.second ^= xz;
+                        found = true;
+                    }
+                }
+                if (!found) {
+                    acc.push_back({q, xz});
+                }
+            }
+            if (imag) {
+                throw std::invalid_argument(
+                    std::string("Acted on an anti-Hermitian operator (e.g. X0*Z0 instead of Y0) in ") + op.gate->name + ".");
+            }
+            std::sort(acc.begin(), acc.end());
+            for (auto &e : acc) {
+                if (e.second != 0) {
+                    p.terms.push_back({lc.qubit_map[e.first], e.second});
+                }
+            }
+            out.push_back(std::move(p));
+            k = end;
+        }
+        return out;
+    }
+
+    // gate_decomposition.cc:88-161: conjugate each product to a Z on its first qubit, measure, undo.
+    void do_mpp(const Instruction &op) {
+        std::vector<uint32_t> h_xz, h_yz, cx_pairs, ms;
+        std::vector<uint8_t> merged(Q, 0);
+        const GateInfo *CX = find_gate("CX");
+        uint64_t rec_first = 0;
+        uint32_t site_first = 0;
+        auto flush_group = [&]() {
+            if (ms.empty()) {
+                return;
+            }
+            do_cliff1_list(0x6, h_xz);
+            do_cliff1_list(0xB, h_yz);
+            for (size_t i = 0; i < cx_pairs.size(); i += 2) {
+                cliff2(CX->param, cx_pairs[i], cx_pairs[i + 1]);
+            }
+            rec_first = meas;
+            site_first = site;
+            for (uint32_t q : ms) {
+                measure(GB_Z, GK_M, q);
+            }
+            if (!op.args.empty()) {
+                rec_noise(op.args[0], ms, rec_first, site_first);
+            }
+            for (size_t i = 0; i < cx_pairs.size(); i += 2) {
+                cliff2(CX->param, cx_pairs[i], cx_pairs[i + 1]);
+            }
+            do_cliff1_list(0xB, h_yz);
+            do_cliff1_list(0x6, h_xz);
+            h_xz.clear();
+            h_yz.clear();
+            cx_pairs.clear();
+            ms.clear();
+            std::fill(merged.begin(), merged.end(), 0);
+        };
+        for (const Product &p : read_products(op, false)) {
+            if (p.terms.empty()) {
+                flush_group();
+                Instruction pad;
+                pad.gate = find_gate("MPAD");
+                pad.args = op.args;
+                pad.targets = {0};
+                do_mpad(pad);
+                continue;
+            }
+            bool overlap = false;
+            for (auto &e : p.terms) {
+                overlap |= merged[e.first] != 0;
+            }
+            if (overlap) {
+                flush_group();
+            }
+            bool first = true;
+            for (auto &e : p.terms) {
+                merged[e.first] = 1;
+                if (e.second & 1) {
+                    ((e.second & 2) ? h_yz : h_xz).push_back(e.first);
+                }
+                if (first) {
+                    ms.push_back(e.first);
+                    first = false;
+                } else {
+                    cx_pairs.push_back(e.first);
+                    cx_pairs.push_back(ms.back());
+                }
+            }
+        }
+        flush_group();
+    }
+
+    // gate_decomposition.cc:163-243. SPP and SPP_DAG act identically on the frame.
+    void do_spp(const Instruction &op) {
+        const GateInfo *CX = find_gate("CX");
+        for (const Product &p : read_products(op, true)) {
+            if (p.terms.empty()) {
+                continue;
+            }
+            std::vector<uint32_t> h_xz, h_yz;
+            uint32_t focus = p.terms[0].first;
+            for (auto &e : p.terms) {
+                if (e.second & 1) {
+                    ((e.second & 2) ? h_yz : h_xz).push_back(e.first);
+                }
+            }
+            auto cx_layer = [&]() {
+                for (size_t i = 1; i < p.terms.size(); i++) {
+                    cliff2(CX->param, p.terms[i].first, focus);
+                }
+                for (uint32_t b : p.bits) {
+                    if (b & T_SWEEP) {
+                        continue;
+                    }
+                    feedback(rec_abs(b, op.gate->name), focus, ITEM_X);
+                }
+            };
+            do_cliff1_list(0x6, h_xz);
+            do_cliff1_list(0xB, h_yz);
+            cx_layer();
+            cliff1(0xD, focus);  // S / S_DAG : z ^= x
+            cx_layer();
+            do_cliff1_list(0xB, h_yz);
+            do_cliff1_list(0x6, h_xz);
+        }
+    }
+
+    // frame_simulator.inl:842-902 + gate_decomposition.cc:245-274.
+    void do_mpair(const Instruction &op) {
+        uint32_t basis = op.gate->param;
+        const GateInfo *conj = find_gate(basis == GB_X ? "CX" : basis == GB_Y ? "CY" : "XCZ");
+        std::vector<uint8_t> used(Q, 0);
+        std::vector<uint32_t> seg;
+        auto flush_seg = [&]() {
+            if (seg.empty()) {
+                return;
+            }
+            for (size_t i = 0; i < seg.size(); i += 2) {
+                cliff2(conj->param, seg[i], seg[i + 1]);
+            }
+            uint64_t rec_first = meas;
+            uint32_t site_first = site;
+            std::vector<uint32_t> ms;
+            for (size_t i = 0; i < seg.size(); i += 2) {
+                measure(basis, GK_M, seg[i]);
+                ms.push_back(seg[i]);
+            }
+            if (!op.args.empty()) {
+                rec_noise(op.args[0], ms, rec_first, site_first);
+            }
+            for (size_t i = 0; i < seg.size(); i += 2) {
+                cliff2(conj->param, seg[i], seg[i + 1]);
+            }
+            seg.clear();
+            std::fill(used.begin(), used.end(), 0);
+        };
+        for (size_t i = 0; i < op.targets.size(); i += 2) {
+            uint32_t a = q_of(op.targets[i]), b = q_of(op.targets[i + 1]);
+            if (used[a] || used[b]) {
+                flush_seg();
+            }
+            used[a] = used[b] = 1;
+            seg.push_back(a);
+            seg.push_back(b);
+        }
+        flush_seg();
+    }
+
+    void do_noise1_gate(const Instruction &op) {
+        double lam = rate_of(op.args[0]);
+        uint32_t cats, t1 = 0, t2 = 0, t3 = 0;
+        switch (op.gate->param) {
+            case 1:
+                cats = 0x55;  // X X X X
+                break;
+            case 2:
+                cats = 0xAA;  // Z
+                break;
+            case 3:
+                cats = 0xFF;  // Y
+                break;
+            default:  // DEPOLARIZE1: uniform over X, Z, Y (frame_simulator.inl:636-641: 1->X, 2->Z, 3->Y)
+                cats = 1u | (2u << 2) | (3u << 4) | (3u << 6);
+                t1 = thr(1.0 / 3.0);
+                t2 = thr(2.0 / 3.0);
+                t3 = t2;
+                break;
+        }
+        for (uint32_t t : op.targets) {
+            if (lam != 0) {
+                noise1(lam, cats, t1, t2, t3, q_of(t), 0, 0);
+            }
+            site++;
+        }
+    }
+
+    void do_depolarize2(const Instruction &op) {
+        double lam = rate_of(op.args[0]);
+        Key k;
+        k.op = GOP_NOISE2;
+        k.lambda = lam;
+        for (size_t i = 0; i < op.targets.size(); i += 2) {
+            if (lam != 0) {
+                uint32_t a = q_of(op.targets[i]), b = q_of(op.targets[i + 1]);
+                uint32_t w = a | (b << 16);
+                uint32_t r[2] = {a | RES_WRITE, b | RES_WRITE};
+                add(k, &w, 1, r, 2, true, site, false, 0, false, 0);
+            }
+            site++;
+        }
+    }
+
+    // One site with the channel's total probability, then a category draw: same joint distribution
+    // as the ELSE_CORRELATED_ERROR chain of tableau_simulator.h:291-324.
+    void do_pauli_channel_1(const Instruction &op) {
+        double px = op.args[0], py = op.args[1], pz = op.args[2];
+        double tot = px + py + pz;
+        double lam = rate_of(std::min(tot, 1.0));
+        uint32_t t1 = 0, t2 = 0, cats = 0;
+        if (tot > 0) {
+            t1 = thr(px / tot);
+            t2 = thr((px + py) / tot);
+            uint32_t last = pz > 0 ? 2u : py > 0 ? 3u : 1u;
+            cats = 1u | (3u << 2) | (last << 4) | (last << 6);
+        }
+        for (uint32_t t : op.targets) {
+            if (lam != 0) {
+                noise1(lam, cats, t1, t2, t2, q_of(t), 0, 0);
+            }
+            site++;
+        }
+    }
+
+    void do_pauli_channel_2(const Instruction &op) {
+        double tot = 0;
+        for (double p : op.args) {
+            tot += p;
+        }
+        double lam = rate_of(std::min(tot, 1.0));
+        uint32_t table[15];
+        uint32_t last = 1;
+        double cum = 0;
+        for (int i = 0; i < 15; i++) {
+            cum += op.args[i];
+            table[i] = tot > 0 ? thr(cum / tot) : 0;
+            if (op.args[i] > 0) {
+                last = (uint32_t)i + 1;
+            }
+        }
+        Key k;
+        k.op = GOP_NOISE2;
+        k.flags = GF_TABLE;
+        k.aux = last;
+        k.lambda = lam;
+        k.table = table;
+        for (size_t i = 0; i < op.targets.size(); i += 2) {
+            if (lam != 0) {
+                uint32_t a = q_of(op.targets[i]), b = q_of(op.targets[i + 1]);
+                uint32_t w = a | (b << 16);
+                uint32_t r[2] = {a | RES_WRITE, b | RES_WRITE};
+                add(k, &w, 1, r, 2, true, site, false, 0, false, 0);
+            }
+            site++;
+        }
+    }
+
+    void do_corr(const Instruction &op) {
+        Key k;
+        k.op = GOP_CORR;
+        k.flags = op.gate->param ? GF_RESET_FLAG : 0;
+        k.lambda = rate_of(op.args[0]);
+        std::vector<uint32_t> words, res;
+        res.push_back(res_flag | RES_WRITE);
+        for (uint32_t t : op.targets) {
+            uint32_t q = q_of(t);
+            words.push_back(q | ((t & T_PAULI_X) ? ITEM_X : 0) | ((t & T_PAULI_Z) ? ITEM_Z : 0));
+            res.push_back(q | RES_WRITE);
+        }
+        uint32_t clock = words.empty() ? Q : (words[0] & 0xFFFFFF);
+        if (words.empty()) {
+            res.push_back(res_clock | RES_WRITE);
+        }
+        k.extra = clock;
+        if (k.lambda != 0 || (k.flags & GF_RESET_FLAG)) {
+            flush();
+            // dedupe resources (a qubit may appear twice in the Pauli list)
+            std::sort(res.begin(), res.end());
+            res.erase(std::unique(res.begin(), res.end()), res.end());
+            add(k, words.data(), (uint32_t)words.size(), res.data(), (uint32_t)res.size(), true, site, false, 0, false, 0, true);
+            cur.n_items = (uint32_t)words.size();
+            flush();
+        }
+        site++;
+    }
+
+    void do_heralded(const Instruction &op) {
+        double tot;
+        uint32_t t1, t2, t3;
+        uint32_t cats = 1u | (2u << 2) | (3u << 4) | (0u << 6);  // X, Z, Y, I
+        if (op.gate->cat == GateCat::HERALDED_ERASE) {
+            tot = op.args[0];
+            t1 = 1u << 30;
+            t2 = 2u << 30;
+            t3 = 3u << 30;
+        } else {
+            double hi = op.args[0], hx = op.args[1], hy = op.args[2], hz = op.args[3];
+            tot = hi + hx + hy + hz;
+            t1 = tot > 0 ? thr(hx / tot) : 0;
+            t2 = tot > 0 ? thr((hx + hz) / tot) : 0;
+            t3 = tot > 0 ? thr((hx + hz + hy) / tot) : 0;
+        }
+        double lam = rate_of(std::min(tot, 1.0));
+        uint64_t rec_first = meas;
+        uint32_t site_first = site;
+        for (size_t i = 0; i < op.targets.size(); i++) {
+            rec_zero(meas);
+            meas++;
+            site++;
+        }
+        if (lam != 0) {
+            uint32_t save = site;
+            for (size_t i = 0; i < op.targets.size(); i++) {
+                site = site_first + (uint32_t)i;
+                noise1(lam, cats, t1, t2, t3, q_of(op.targets[i]), GF_REC, rec_first + i);
+            }
+            site = save;
+        }
+    }
+
+    void do_detector(const Instruction &op) {
+        if (lc.mode == 0) {
+            std::vector<uint64_t> recs;
+            for (uint32_t t : op.targets) {
+                recs.push_back(rec_abs(t, "DETECTOR"));
+            }
+            xor_rows((uint32_t)det, recs, false);
+        } else {
+            for (uint32_t t : op.targets) {
+                rec_abs(t, "DETECTOR");
+            }
+        }
+        det++;
+    }
+
+    void do_observable(const Instruction &op) {
+        uint32_t row = (uint32_t)lc.stats.num_detectors + (uint32_t)op.args[0];
+        std::vector<uint64_t> recs;
+        for (uint32_t t : op.targets) {
+            if (t & T_REC) {
+                recs.push_back(rec_abs(t, "OBSERVABLE_INCLUDE"));
+            }
+        }
+        if (lc.mode != 0) {
+            return;
+        }
+        if (!recs.empty()) {
+            xor_rows(row, recs, true);
+        }
+        for (uint32_t t : op.targets) {
+            if (!(t & T_REC)) {
+                // X target reads the z component, Z target reads x, Y both (frame_simulator.inl:240-246)
+                uint32_t comps = ((t & T_PAULI_X) ? ITEM_Z : 0) | ((t & T_PAULI_Z) ? ITEM_X : 0);
+                obs_pauli(row, q_of(t), comps);
+            }
+        }
+    }
+
+    void do_op(const Instruction &op) {
+        const GateInfo &g = *op.gate;
+        switch (g.cat) {
+            case GateCat::NOOP:
+                break;
+            case GateCat::CLIFF1:
+                for (uint32_t t : op.targets) {
+                    cliff1(g.param, q_of(t));
+                }
+                break;
+            case GateCat::CLIFF2:
+                for (size_t i = 0; i < op.targets.size(); i += 2) {
+                    do_controlled(g, op.targets[i], op.targets[i + 1]);
+                }
+                break;
+            case GateCat::MEASURE:
+                do_measure_gate(op);
+                break;
+            case GateCat::MPAD:
+                do_mpad(op);
+                break;
+            case GateCat::MPP:
+                do_mpp(op);
+                break;
+            case GateCat::SPP:
+                do_spp(op);
+                break;
+            case GateCat::MPAIR:
+                do_mpair(op);
+                break;
+            case GateCat::NOISE1:
+                do_noise1_gate(op);
+                break;
+            case GateCat::DEPOLARIZE2:
+                do_depolarize2(op);
+                break;
+            case GateCat::PAULI_CHANNEL_1:
+                do_pauli_channel_1(op);
+                break;
+            case GateCat::PAULI_CHANNEL_2:
+                do_pauli_channel_2(op);
+                break;
+            case GateCat::CORR:
+                do_corr(op);
+                break;
+            case GateCat::HERALDED_ERASE:
+            case GateCat::HERALDED_PAULI_CHANNEL_1:
+                do_heralded(op);
+                break;
+            case GateCat::DETECTOR:
+                do_detector(op);
+                break;
+            case GateCat::OBSERVABLE_INCLUDE:
+                do_observable(op);
+                break;
+            case GateCat::REPEAT:
+                break;
+        }
+    }
+};
+
+void mark_used(const Circuit &c, std::vector<uint8_t> &used) {
+    for (const auto &op : c.ops) {
+        if (op.gate->cat == GateCat::REPEAT) {
+            mark_used(c.blocks[op.block_index], used);
+            continue;
+        }
+        if (op.gate->cat == GateCat::MPAD || op.gate->targets == TR_NONE) {
+            continue;
+        }
+        if (std::string(op.gate->name) == "QUBIT_COORDS") {
+            continue;
+        }
+        for (uint32_t t : op.targets) {
+            if (t == T_COMBINER || (t & (T_REC | T_SWEEP))) {
+                continue;
+            }
+            used[t & T_VALUE_MASK] = 1;
+        }
+    }
+}
+
+}  // namespace
+
+LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words) {
+    Lowerer lw(max_batch_words);
+    LoweredCircuit &lc = lw.lc;
+    lc.mode = mode;
+    lc.stats = compute_stats(c);
+    if (lc.stats.num_measurements >= (1ull << 32) || lc.stats.num_detectors + lc.stats.num_observables >= (1ull << 32)) {
+        throw std::invalid_argument("Circuit has more than 2^32 measurements or detectors; not supported.");
+    }
+
+    // qubit compaction: every qubit value that appears as a target of any instruction except QUBIT_COORDS.
+    std::vector<uint8_t> used(lc.stats.num_qubits, 0);
+    mark_used(c, used);
+    lc.qubit_map.assign(lc.stats.num_qubits, UINT32_MAX);
+    uint32_t Q = 0;
+    for (size_t q = 0; q < used.size(); q++) {
+        if (used[q]) {
+            lc.qubit_map[q] = Q++;
+        }
+    }
+    if (Q > 65535) {
+        throw std::invalid_argument("Circuits with more than 65535 active qubits are not supported by this build.");
+    }
+    lc.num_qubits = Q;
+    lw.Q = Q;
+
+    // record addressing
+    uint64_t rec_slots;
+    if (mode == 0) {
+        uint32_t ring = 1;
+        while (ring < lc.stats.max_lookback) {
+            ring <<= 1;
+        }
+        lc.rec_ring = ring;
+        lw.rec_mask = ring - 1;
+        rec_slots = ring;
+    } else {
+        lc.rec_ring = 0;
+        lw.rec_mask = 0xFFFFFFFFu;
+        rec_slots = std::max<uint64_t>(lc.stats.num_measurements, 1);
+    }
+    lw.res_clock = Q;
+    lw.res_flag = Q + 1;
+    lw.res_rec0 = Q + 2;
+    lw.res_out0 = lw.res_rec0 + (uint32_t)rec_slots;
+    lc.num_resources = lw.res_out0 + (uint32_t)(lc.stats.num_detectors + lc.stats.num_observables) + 1;
+    lw.rd_stamp.assign(lc.num_resources, 0);
+    lw.wr_stamp.assign(lc.num_resources, 0);
+
+    // Start of every shot: x <- 0, z <- random for all qubits (frame_simulator.inl:153-163).
+    // Collapse sites 0..Q-1 are reserved for this.
+    for (uint32_t q = 0; q < Q; q++) {
+        lw.measure(GB_Z, GK_R, q);
+    }
+    // Observable rows start at zero.
+    if (mode == 0) {
+        for (uint64_t l = 0; l < lc.stats.num_observables; l++) {
+            lw.xor_rows((uint32_t)(lc.stats.num_detectors + l), {}, false);
+        }
+    }
+    c.for_each_operation([&](const Instruction &op) {
+        lw.do_op(op);
+    });
+    lw.flush();
+    lc.num_sites = lw.site;
+    lc.num_csites = lw.csite;
+    return std::move(lw.lc);
+}
+
+std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint32_t chunk_words, GstimPlan *plan) {
+    std::vector<uint32_t> out;
+    const uint32_t NONE = 0xFFFFFFFFu, MULTI = 0xFFFFFFFEu;
+    std::vector<uint32_t> w_epoch(lc.num_resources, 0), w_slot(lc.num_resources, NONE);
+    std::vector<uint32_t> r_epoch(lc.num_resources, 0), r_slot(lc.num_resources, NONE);
+    uint32_t epoch = 1;
+    uint32_t n_barriers = 0;
+
+    auto put_header = [&](uint32_t op, uint32_t words) {
+        size_t base = out.size();
+        out.resize(base + GSTIM_HDR_WORDS, 0);
+        out[base + GH_OP] = op;
+        out[base + GH_WORDS] = words;
+    };
+
+    for (Batch &b : lc.batches) {
+        // ---- hazard analysis: does any item need data last touched by another thread group? ----
+        size_t n_haz = b.res_off.size() - 1;
+        bool barrier = false;
+        for (size_t i = 0; i < n_haz && !barrier; i++) {
+            uint32_t slot = (uint32_t)(i % slots);
+            for (uint32_t j = b.res_off[i]; j < b.res_off[i + 1]; j++) {
+                uint32_t r = b.res[j] & ~RES_WRITE;
+                bool wr = (b.res[j] & RES_WRITE) != 0;
+                if (w_epoch[r] == epoch && w_slot[r] != slot) {
+                    barrier = true;
+                    break;
+                }
+                if (wr && r_epoch[r] == epoch && r_slot[r] != slot) {
+                    barrier = true;
+                    break;
+                }
+            }
+        }
+        if (barrier) {
+            epoch++;
+            n_barriers++;
+            b.flags |= GF_BARRIER;
+        } else {
+            b.flags &= ~GF_BARRIER;
+        }
+        for (size_t i = 0; i < n_haz; i++) {
+            uint32_t slot = (uint32_t)(i % slots);
+            for (uint32_t j = b.res_off[i]; j < b.res_off[i + 1]; j++) {
+                uint32_t r = b.res[j] & ~RES_WRITE;
+                if (b.res[j] & RES_WRITE) {
+                    w_epoch[r] = epoch;
+                    w_slot[r] = slot;
+                } else if (r_epoch[r] != epoch) {
+                    r_epoch[r] = epoch;
+                    r_slot[r] = slot;
+                } else if (r_slot[r] != slot) {
+                    r_slot[r] = MULTI;
+                }
+            }
+        }
+
+        // ---- serialise ----
+        uint32_t words = b.words();
+        uint32_t pos = (uint32_t)(out.size() % chunk_words);
+        if (words + GSTIM_HDR_WORDS > chunk_words) {
+            throw std::logic_error("internal: batch larger than a program chunk");
+        }
+        if (pos + words + GSTIM_HDR_WORDS > chunk_words) {
+            put_header(GOP_NEXT_CHUNK, GSTIM_HDR_WORDS);
+            out.resize((out.size() / chunk_words + 1) * (size_t)chunk_words, 0);
+        }
+        size_t base = out.size();
+        out.resize(base + GSTIM_HDR_WORDS, 0);
+        out[base + GH_OP] = b.op | (b.flags << 8) | (b.aux << 16);
+        out[base + GH_N] = b.n_items;
+        out[base + GH_WORDS] = words;
+        out[base + GH_EXTRA] = b.extra;
+        uint64_t lb;
+        memcpy(&lb, &b.lambda, 8);
+        out[base + GH_LAMBDA_LO] = (uint32_t)lb;
+        out[base + GH_LAMBDA_HI] = (uint32_t)(lb >> 32);
+        out[base + GH_SITE0] = b.site0;
+        out[base + GH_CSITE0] = b.csite0;
+        out[base + GH_REC0] = b.rec0;
+        out[base + GH_T1] = b.t1;
+        out[base + GH_T2] = b.t2;
+        out[base + GH_T3] = b.t3;
+        if (b.op == GOP_XORROWS) {
+            out.insert(out.end(), b.dst.begin(), b.dst.end());
+            out.insert(out.end(), b.off.begin(), b.off.end());
+            out.insert(out.end(), b.idx.begin(), b.idx.end());
+        } else {
+            out.insert(out.end(), b.payload.begin(), b.payload.end());
+        }
+    }
+    put_header(GOP_END, GSTIM_HDR_WORDS);
+    out.resize((out.size() + chunk_words - 1) / chunk_words * (size_t)chunk_words, 0);
+
+    if (plan != nullptr) {
+        memset(plan, 0, sizeof(*plan));
+        plan->num_qubits = lc.num_qubits;
+        plan->q_pitch = lc.num_qubits | 1u;
+        plan->num_meas = (uint32_t)lc.stats.num_measurements;
+        plan->num_det = (uint32_t)lc.stats.num_detectors;
+        plan->num_obs = (uint32_t)lc.stats.num_observables;
+        plan->rec_ring = lc.rec_ring;
+        plan->n_words = (uint32_t)out.size();
+        plan->chunk_words = chunk_words;
+        plan->n_chunks = (uint32_t)(out.size() / chunk_words);
+        plan->slots = slots;
+        plan->mode = lc.mode;
+        plan->max_items = lc.max_items;
+        plan->n_batches = (uint32_t)lc.batches.size();
+        plan->n_barriers = n_barriers;
+    }
+    return out;
+}
+
+}  // namespace gstim

@@ -1,0 +1,56 @@
+// lowering.h — Circuit -> flat instruction stream (program.h) for the sm_100a interpreter.
+//
+// No reference analogue (Stim re-walks the Circuit per batch, frame_simulator.inl:166-170).
+// What the lowering does, and the reference behaviour each step preserves:
+//   * REPEAT unrolled in execution order           (circuit.h:181-193 for_each_operation)
+//   * MPP / SPP / MXX,MYY,MZZ decomposed            (gate_decomposition.cc:88-274, frame_simulator.inl:842-902)
+//   * PAULI_CHANNEL_1/2 folded to one site + choice (distribution of tableau_simulator.h:291-324)
+//   * rec[-k] resolved to absolute indices, bad lookback -> std::out_of_range (measure_record_batch.inl:83-94)
+//   * bit-as-target of CX/CY -> std::invalid_argument (frame_simulator.inl:399-402, 421-424)
+//   * inverted targets ignored, sweep controls are no-ops (frame_simulator.inl:146-148, 176)
+//   * qubit indices compacted to the set of qubits that appear in the circuit
+// RNG addressing (site / collapse-site / record counters) is part of the output; DESIGN.md §RNG.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "circuit.h"
+#include "program.h"
+
+namespace gstim {
+
+struct Batch {
+    uint32_t op = 0, flags = 0, aux = 0, extra = 0;
+    double lambda = 0;
+    uint32_t site0 = 0, csite0 = 0, rec0 = 0;
+    uint32_t t1 = 0, t2 = 0, t3 = 0;
+    uint32_t n_items = 0;
+    std::vector<uint32_t> payload;  // op specific (see program.h)
+    // XORROWS is assembled from these three at serialisation time:
+    std::vector<uint32_t> dst, off, idx;
+    // resources (for the hazard pass): per item, [begin,end) into res; bit31 of an entry = write.
+    std::vector<uint32_t> res_off;
+    std::vector<uint32_t> res;
+    uint32_t words() const;
+};
+
+struct LoweredCircuit {
+    CircuitStats stats;
+    uint32_t mode = 0;             // 0 detectors, 1 measurements
+    uint32_t num_qubits = 0;       // compacted
+    uint32_t rec_ring = 0;
+    uint32_t num_resources = 0;
+    std::vector<uint32_t> qubit_map;  // original index -> compact index or UINT32_MAX
+    std::vector<Batch> batches;
+    uint32_t max_items = 0;
+    uint64_t total_items = 0;
+    uint64_t num_sites = 0, num_csites = 0;
+};
+
+// Pass 1: semantics. Throws std::invalid_argument / std::out_of_range like the reference would.
+LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words);
+
+// Pass 2: hazard analysis for `slots` concurrent thread groups + serialisation into chunks.
+std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint32_t chunk_words, GstimPlan *plan);
+
+}  // namespace gstim

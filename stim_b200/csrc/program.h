@@ -1,0 +1,98 @@
+// program.h — the lowered instruction stream shared by the host lowering (lowering.cc)
+// and the sm_100a interpreter kernel (kernels.cu).
+//
+// There is no counterpart of this format in the reference: Stim's FrameSimulator walks the
+// Circuit object directly (/root/reference/src/stim/simulators/frame_simulator.inl:166-170, 915-1113).
+// Here the circuit is flattened once on the host (REPEAT unrolled, MPP/MXX/SPP decomposed,
+// PAULI_CHANNEL folded to a single site, qubit indices compacted, rec[-k] made absolute) into
+// a flat array of uint32 words that a thread block streams through shared memory.
+//
+// A program is a sequence of BATCHES. A batch = 12 header words + payload. Every item of a
+// batch touches resources (qubits, record rows, output rows) disjoint from every other item
+// of the same batch, so items are executed concurrently, item i by thread-group (i % slots).
+// The program is cut into CHUNKS of chunk_words words; no batch straddles a chunk boundary
+// (the tail of a chunk is an OP_NEXT_CHUNK header). Chunks are what the kernel's bulk-async
+// (TMA 1D) copies move into the shared-memory ring.
+#pragma once
+#include <stdint.h>
+
+#define GSTIM_HDR_WORDS 12u
+
+// Shots are simulated in "columns" of 128 shots (one uint4 per qubit per column).
+#define GSTIM_COL_SHOTS 128u
+
+enum GstimOp : uint32_t {
+    GOP_END = 0,         // end of program
+    GOP_NEXT_CHUNK = 1,  // rest of this chunk is padding
+    GOP_CLIFF1 = 2,      // aux = 2x2 GF(2) matrix: bit0 x'<-x, bit1 x'<-z, bit2 z'<-x, bit3 z'<-z. item: qubit
+    GOP_CLIFF2 = 3,      // aux = 4x4 GF(2) matrix over (x1,z1,x2,z2), 4 bits per output. item: q1 | q2<<16
+    GOP_NOISE1 = 4,      // single-target Pauli noise site per item. item: qubit (clock + frame target)
+    GOP_NOISE2 = 5,      // two-target Pauli noise site per item. item: q1 | q2<<16 (clock = q1)
+    GOP_MEASURE = 6,     // aux = basis | kind<<2. item: qubit
+    GOP_RECZERO = 7,     // zero record rows rec0 .. rec0+n-1 (no payload)
+    GOP_XORROWS = 8,     // out row (^)= XOR of record rows. payload: dst[n], off[n+1], idx[...]
+    GOP_OBS_PAULI = 9,   // out row ^= frame component. payload per item: dst row, qubit | x<<30 | z<<31
+    GOP_FEEDBACK = 10,   // frame ^= record row. payload per item: rec index, qubit | x<<30 | z<<31
+    GOP_CORR = 11,       // E / ELSE_CORRELATED_ERROR: one site, payload = Pauli targets qubit | x<<30 | z<<31
+};
+
+// header word indices
+enum GstimHdr : uint32_t {
+    GH_OP = 0,       // op | flags<<8 | aux<<16
+    GH_N = 1,        // number of items
+    GH_WORDS = 2,    // total words of this batch (header + payload)
+    GH_EXTRA = 3,    // op specific (NOISE: clock override qubit+1 or 0; CORR: clock qubit)
+    GH_LAMBDA_LO = 4,  // lambda = -log1p(-p) as IEEE double (lo word)
+    GH_LAMBDA_HI = 5,
+    GH_SITE0 = 6,    // noise-site index of item 0 (item i uses site0+i)
+    GH_CSITE0 = 7,   // collapse-site index of item 0
+    GH_REC0 = 8,     // absolute measurement index of item 0
+    GH_T1 = 9,       // NOISE1: category thresholds on a uniform u32
+    GH_T2 = 10,
+    GH_T3 = 11,
+};
+
+// header flags (bits 8..15 of word 0)
+#define GF_BARRIER 0x01u     // __syncthreads() before executing this batch
+#define GF_REC 0x02u         // NOISE1: every event also flips bit in record row rec0+i (heralds, M(p) noise)
+#define GF_ACCUM 0x04u       // XORROWS: dst ^= value (instead of dst = value)
+#define GF_RESET_FLAG 0x08u  // CORR: clear the "correlated error occurred" row first (E vs ELSE)
+#define GF_TABLE 0x10u       // NOISE2: 15 cumulative u32 thresholds follow the header (PAULI_CHANNEL_2)
+#define GF_NOFRAME 0x20u     // NOISE1: item is not a frame qubit (MPAD noise); clock = GH_EXTRA-1
+
+// CLIFF2 matrix of CX (the interpreter has a dedicated path for it; circuit.cc static_asserts the value)
+#define GSTIM_MAT_CX 0x85A1u
+
+// MEASURE aux encoding
+#define GB_X 0u
+#define GB_Y 1u
+#define GB_Z 2u
+#define GK_M 0u   // measure, keep
+#define GK_MR 1u  // measure, reset
+#define GK_R 2u   // reset only (no record)
+
+// NOISE1 aux: four 2-bit Pauli categories c0..c3 (bit0 = flip x, bit1 = flip z), c_j at bits 2j..2j+1.
+//   v = uniform u32;  v < T1 -> c0;  v < T2 -> c1;  v < T3 -> c2;  else c3.
+
+// Philox counter tags (4th counter word)
+#define GTAG_EVENT 0x45564E54u     // 'EVNT' per noise event:  ctr = (site, k_event, col0, tag)
+#define GTAG_COLLAPSE 0x434F4C4Cu  // 'COLL' per collapse:     ctr = (csite, global column, 0, tag)
+#define GTAG_CLOCK 0x434C4F4Bu     // 'CLOK' clock init:       ctr = (qubit, 0, col0, tag)
+
+// Plan: everything the kernel needs besides the program words.
+struct GstimPlan {
+    uint32_t num_qubits;     // compacted qubit count Q (frame rows)
+    uint32_t q_pitch;        // Q rounded up to odd (shared-memory row pitch in uint4)
+    uint32_t num_meas;       // M
+    uint32_t num_det;        // D
+    uint32_t num_obs;        // L
+    uint32_t rec_ring;       // power of two >= max lookback distance (detector mode), else 0
+    uint32_t n_words;        // program length in words (multiple of chunk_words)
+    uint32_t chunk_words;    // chunk size
+    uint32_t n_chunks;
+    uint32_t slots;          // thread groups the hazard analysis assumed (threads / lanes_per_item)
+    uint32_t mode;           // 0 = detectors(+observables), 1 = measurements
+    uint32_t max_items;      // largest batch
+    uint32_t n_batches;
+    uint32_t n_barriers;
+};
