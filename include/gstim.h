@@ -183,6 +183,10 @@ int gstim_last_launch_count(const gstim_sampler *s, uint64_t *launches);
  * and the shot offset this pins the random stream (DESIGN.md "RNG addressing"). */
 int gstim_last_block_columns(const gstim_sampler *s, uint32_t *columns);
 
+/* Device time (CUDA events on the library's stream, ms) from the first kernel start to the last kernel
+ * end of the most recent sampling call. */
+int gstim_last_call_ms(const gstim_sampler *s, float *ms);
+
 /* Device-time (CUDA events, ms) of the interpreter and transposer kernels in the most recent call. */
 int gstim_last_kernel_ms(const gstim_sampler *s, float *interp_ms, float *transpose_ms);
 

@@ -137,6 +137,11 @@ class _Sampler:
         _native.check(_native.lib().gstim_last_block_columns(self._handle, ctypes.byref(v)))
         return int(v.value)
 
+    def last_call_ms(self) -> float:
+        v = ctypes.c_float(0)
+        _native.check(_native.lib().gstim_last_call_ms(self._handle, ctypes.byref(v)))
+        return float(v.value)
+
     def last_kernel_ms(self) -> Tuple[float, float]:
         a, b = ctypes.c_float(0), ctypes.c_float(0)
         _native.check(_native.lib().gstim_last_kernel_ms(self._handle, ctypes.byref(a), ctypes.byref(b)))

@@ -76,6 +76,7 @@ _SIGNATURES = [
     ("gstim_detector_flip_counts", ctypes.c_int, [_P, ctypes.c_uint64, _P, _P]),
     ("gstim_last_launch_count", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
     ("gstim_last_block_columns", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32)]),
+    ("gstim_last_call_ms", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
     ("gstim_last_kernel_ms", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
 ]
 

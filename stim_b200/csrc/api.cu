@@ -16,6 +16,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gstim.h"
@@ -133,7 +134,8 @@ struct gstim_sampler {
 
     uint64_t last_launches = 0;
     uint32_t last_K = 0;
-    float last_interp_ms = 0, last_transpose_ms = 0;
+    float last_interp_ms = 0, last_transpose_ms = 0, last_call_ms = 0;
+    cudaEvent_t call_start = nullptr, call_end = nullptr;
 
     ~gstim_sampler() {
         for (auto e : events) {
@@ -148,6 +150,10 @@ struct gstim_sampler {
             if (e) {
                 cudaEventDestroy(e);
             }
+        }
+        if (call_start) {
+            cudaEventDestroy(call_start);
+            cudaEventDestroy(call_end);
         }
         if (stream) {
             cudaStreamDestroy(stream);
@@ -321,6 +327,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
     s->last_launches = 0;
     s->last_interp_ms = 0;
     s->last_transpose_ms = 0;
+    s->last_call_ms = 0;
     if (shots == 0) {
         return;
     }
@@ -343,6 +350,11 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         s->d_rec.ensure((size_t)grid_cap * s->plan.rec_ring * K * 16);
     }
 
+    if (!s->call_start) {
+        CK(cudaEventCreate(&s->call_start));
+        CK(cudaEventCreate(&s->call_end));
+    }
+    CK(cudaEventRecord(s->call_start, s->stream));
     size_t ev = 0;
     uint64_t done_blocks = 0;
     while (done_blocks < total_blocks) {
@@ -387,7 +399,9 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         CK(cudaEventRecord(e2, s->stream));
         done_blocks += nb;
     }
+    CK(cudaEventRecord(s->call_end, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    CK(cudaEventElapsedTime(&s->last_call_ms, s->call_start, s->call_end));
     for (size_t i = 0; i + 3 <= ev; i += 3) {
         float a = 0, b = 0;
         CK(cudaEventElapsedTime(&a, s->events[i], s->events[i + 1]));
@@ -505,46 +519,72 @@ void sample_to_host(
         }
     }
 
+    // Pinned (page-locked) caller memory + packed layout: DMA straight into the caller's rows.
+    auto is_pinned = [](const void *ptr) {
+        if (ptr == nullptr) {
+            return true;
+        }
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return attr.type == cudaMemoryTypeHost;
+    };
+    const bool direct = bit_packed && is_pinned(main_out) && is_pinned(obs_out);
+
     struct Pending {
         bool active = false;
         uint64_t first = 0, n = 0;
     } pending[2];
+    auto scatter_rows = [&](const uint8_t *src, uint64_t src_bytes, uint32_t n_bits, uint8_t *dst0, uint64_t pitch, uint64_t n) {
+        const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        const unsigned nt = n * src_bytes < (1u << 20) ? 1u : hw;
+        auto work = [&](uint64_t a, uint64_t b) {
+            for (uint64_t i = a; i < b; i++) {
+                uint8_t *dst = dst0 + i * pitch;
+                if (bit_packed) {
+                    memcpy(dst, src + i * src_bytes, src_bytes);
+                } else {
+                    unpack_bits(src + i * src_bytes, n_bits, dst);
+                }
+            }
+        };
+        if (nt == 1) {
+            work(0, n);
+            return;
+        }
+        std::vector<std::thread> ts;
+        for (unsigned t = 0; t < nt; t++) {
+            ts.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+        }
+        for (auto &t : ts) {
+            t.join();
+        }
+    };
     auto drain = [&](int b) {
         if (!pending[b].active) {
             return;
         }
         CK(cudaEventSynchronize(s->stage_done[b]));
+        pending[b].active = false;
+        if (direct) {
+            return;
+        }
         const uint8_t *h = (const uint8_t *)s->h_stage[b].p;
         const uint64_t first = pending[b].first, n = pending[b].n;
-        const uint8_t *hm = h, *ho = h + n * main_bytes;
         if (main_out && nb_main) {
-            for (uint64_t i = 0; i < n; i++) {
-                uint8_t *dst = main_out + (first + i) * main_pitch;
-                if (bit_packed) {
-                    memcpy(dst, hm + i * main_bytes, main_bytes);
-                } else {
-                    unpack_bits(hm + i * main_bytes, nb_main, dst);
-                }
-            }
+            scatter_rows(h, main_bytes, nb_main, main_out + first * main_pitch, main_pitch, n);
         }
         if (obs_out && nb_obs) {
-            for (uint64_t i = 0; i < n; i++) {
-                uint8_t *dst = obs_out + (first + i) * obs_pitch;
-                if (bit_packed) {
-                    memcpy(dst, ho + i * obs_bytes, obs_bytes);
-                } else {
-                    unpack_bits(ho + i * obs_bytes, nb_obs, dst);
-                }
-            }
+            scatter_rows(h + n * main_bytes, obs_bytes, nb_obs, obs_out + first * obs_pitch, obs_pitch, n);
         }
-        pending[b].active = false;
     };
 
     int cur = 0;
     run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t row_words) {
         drain(cur);  // buffer about to be reused
         s->d_stage[cur].ensure(n * stage_pitch + 16);
-        s->h_stage[cur].ensure(n * stage_pitch + 16);
         uint8_t *dmain = (uint8_t *)s->d_stage[cur].p;
         uint8_t *dobs = dmain + n * main_bytes;
         if (nb_main) {
@@ -556,7 +596,19 @@ void sample_to_host(
         // copy on the second stream so the next chunk's interpreter overlaps the PCIe drain
         CK(cudaEventRecord(s->stage_ready[cur], s->stream));
         CK(cudaStreamWaitEvent(s->copy_stream, s->stage_ready[cur], 0));
-        CK(cudaMemcpyAsync(s->h_stage[cur].p, s->d_stage[cur].p, n * stage_pitch, cudaMemcpyDeviceToHost, s->copy_stream));
+        if (direct) {
+            if (main_out && nb_main) {
+                CK(cudaMemcpy2DAsync(
+                    main_out + first * main_pitch, main_pitch, dmain, main_bytes, main_bytes, n, cudaMemcpyDeviceToHost, s->copy_stream));
+            }
+            if (obs_out && nb_obs) {
+                CK(cudaMemcpy2DAsync(
+                    obs_out + first * obs_pitch, obs_pitch, dobs, obs_bytes, obs_bytes, n, cudaMemcpyDeviceToHost, s->copy_stream));
+            }
+        } else {
+            s->h_stage[cur].ensure(n * stage_pitch + 16);
+            CK(cudaMemcpyAsync(s->h_stage[cur].p, s->d_stage[cur].p, n * stage_pitch, cudaMemcpyDeviceToHost, s->copy_stream));
+        }
         CK(cudaEventRecord(s->stage_done[cur], s->copy_stream));
         pending[cur].active = true;
         pending[cur].first = first;
@@ -997,6 +1049,13 @@ int gstim_last_block_columns(const gstim_sampler *s, uint32_t *columns) {
     return guarded([&] {
         require(s && columns, "NULL argument.");
         *columns = s->last_K;
+    });
+}
+
+int gstim_last_call_ms(const gstim_sampler *s, float *ms) {
+    return guarded([&] {
+        require(s && ms, "NULL argument.");
+        *ms = s->last_call_ms;
     });
 }
 
