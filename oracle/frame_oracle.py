@@ -178,14 +178,7 @@ TWO_QUBIT = {
 }
 
 
-def rate_of(p):
-    """Probability (narrowed to float like the reference, probability_util.h:47) -> events per shot."""
-    f = float(np.float32(p))
-    if not f > 0:
-        return 0.0
-    if f >= 1:
-        return math.inf
-    return -math.log1p(-f)
+rate_of = px.lam_fx  # probability -> per-shot event rate in fixed-point clock units (2**-56 nat)
 
 
 def thr(frac):
@@ -228,68 +221,76 @@ class FrameOracle:
         self.rec = []   # list of uint32[W] rows (flips)
         self.dets = []  # list of uint32[W]
         self.obs = {}
-        self.site = 0
-        self.csite = 0
+        self.ngroup = 0  # noise group counter   (Philox counter word 0 of event draws)
+        self.mgroup = 0  # measure group counter (Philox counter word 0 of collapse draws)
         # exponential clocks: one per qubit + one global (index Q); DESIGN.md "RNG addressing"
         q = np.arange(self.Q + 1, dtype=np.uint64)[:, None]
         c2 = (self.col0 & np.uint64(0xFFFFFFFF))[None, :]
         c3 = (np.uint64(px.TAG_CLOCK) ^ (self.col0 >> np.uint64(32)))[None, :]
         r = px.philox4x32_10(q, 0, c2, c3, self.k0, self.k1)
-        self.clk = px.exp_draw(r[0])  # [Q+1, nb]
+        self.clk = np.array([[px.exp_draw_fx(int(v)) for v in row] for row in r[0]], dtype=np.uint64).reshape(self.Q + 1, self.nb)
 
     # -- randomness ---------------------------------------------------------------------------
-    def collapse_words(self, csite):
-        """128 fresh random bits per column for collapse site `csite` -> uint32[W]."""
+    def collapse_words(self, mgroup, q):
+        """128 fresh random bits per column for the collapse of qubit q in measure group mgroup -> uint32[W]."""
         cols = (self.col0[:, None] + np.arange(self.K, dtype=np.uint64)[None, :]).reshape(-1)
-        r = px.philox4x32_10(csite, 0, cols & np.uint64(0xFFFFFFFF), np.uint64(px.TAG_COLLAPSE) ^ (cols >> np.uint64(32)),
+        r = px.philox4x32_10(mgroup, q, cols & np.uint64(0xFFFFFFFF), np.uint64(px.TAG_COLLAPSE) ^ (cols >> np.uint64(32)),
                              self.k0, self.k1)
         return np.stack(r, axis=1).reshape(-1)
 
-    def run_sites(self, clocks, lam, sites, on_event):
-        """Geometric-skip sampling of len(sites) independent sites over all blocks.
+    def run_sites(self, clocks, lam, group, on_event):
+        """Geometric-skip sampling of len(clocks) independent sites (distinct clock qubits) over all blocks.
 
-        clocks: clock index per site (all distinct). on_event(i, g, shot, r) with r = 4 uint32.
-        Event positions follow floor(E/lambda) skipping == RareErrorIterator (probability_util.cc:33-43)."""
-        clocks = np.asarray(clocks)
+        on_event(i, g, shot, r) with r = 4 uint32 of the event's Philox draw. Event positions follow
+        floor(E/lambda) skipping == RareErrorIterator (probability_util.cc:33-43), in exact integer arithmetic."""
+        clocks = [int(c) for c in clocks]
         n = len(clocks)
         if n == 0 or lam == 0:
             return
-        E = self.clk[clocks, :]  # [n, nb] copy
         B = self.B
-        pos = np.zeros((n, self.nb), dtype=np.int64)
-        kev = np.zeros((n, self.nb), dtype=np.int64)
-        active = np.ones((n, self.nb), dtype=bool)
-        sites = np.asarray(sites, dtype=np.uint64)
-        while active.any():
-            with np.errstate(invalid="ignore"):
-                rem = (B - pos).astype(np.float64) * lam
-            done = active & (E >= rem)
-            E = np.where(done, E - rem, E)
-            active &= ~done
-            idx = np.argwhere(active)
-            if len(idx) == 0:
-                break
-            ii, gg = idx[:, 0], idx[:, 1]
-            e = E[ii, gg]
-            with np.errstate(divide="ignore"):
-                jd = np.floor(e / lam)
-            left = B - pos[ii, gg] - 1
-            j = np.where(jd >= left, left, jd).astype(np.int64)
-            shot = pos[ii, gg] + j
-            c2 = self.col0[gg] & np.uint64(0xFFFFFFFF)
-            c3 = np.uint64(px.TAG_EVENT) ^ (self.col0[gg] >> np.uint64(32))
-            r = px.philox4x32_10(sites[ii], kev[ii, gg].astype(np.uint64), c2, c3, self.k0, self.k1)
-            for t in range(len(ii)):
-                on_event(int(ii[t]), int(gg[t]), int(shot[t]), (int(r[0][t]), int(r[1][t]), int(r[2][t]), int(r[3][t])))
-            E[ii, gg] = px.exp_draw(r[0])
-            pos[ii, gg] = shot + 1
-            kev[ii, gg] += 1
-            active[ii, gg] = pos[ii, gg] < B
+        need = min(B * lam, px.REM_SAT)
+        E = self.clk[clocks, :]  # [n, nb] copy (uint64)
+        hit = E < np.uint64(need)
+        E = np.where(hit, E, E - np.uint64(min(need, (1 << 64) - 1)))
+        for i, g in np.argwhere(hit):
+            i, g = int(i), int(g)
+            e = int(E[i, g])
+            pos = kev = 0
+            c2 = int(self.col0[g]) & 0xFFFFFFFF
+            c3 = px.TAG_EVENT ^ (int(self.col0[g]) >> 32)
+            while pos < B:
+                rem = min((B - pos) * lam, px.REM_SAT)
+                if e >= rem:
+                    e -= rem
+                    break
+                j = min(e // lam, B - pos - 1)
+                shot = pos + j
+                r = px.philox4x32_10(group, clocks[i] | (kev << 16), c2, c3, self.k0, self.k1)
+                r = tuple(int(v) for v in r)
+                on_event(i, g, shot, r)
+                e = px.exp_draw_fx(r[0])
+                pos = shot + 1
+                kev += 1
+            E[i, g] = e
         self.clk[clocks, :] = E
 
     def _flip(self, arr, g, shot):
         w = g * self.K * 4 + (shot >> 5)
         arr[w] ^= np.uint32(1 << (shot & 31))
+
+    # -- group bookkeeping (DESIGN.md "RNG addressing") -----------------------------------------
+    @staticmethod
+    def _runs(keys_per_target):
+        """Splits targets into maximal runs in which no qubit repeats. keys_per_target: list of tuples of qubits."""
+        runs, start, seen = [], 0, set()
+        for i, ks in enumerate(keys_per_target):
+            if any(k in seen for k in ks):
+                runs.append((start, i))
+                start, seen = i, set()
+            seen.update(ks)
+        if start < len(keys_per_target):
+            runs.append((start, len(keys_per_target)))
+        return runs
 
     # -- primitive ops --------------------------------------------------------------------------
     def rec_at(self, lookback, what):
@@ -297,10 +298,9 @@ class FrameOracle:
             raise IndexError("Referred to a measurement record before the beginning of time in %s." % what)
         return self.rec[len(self.rec) - lookback]
 
-    def measure(self, basis, kind, q):
+    def measure(self, basis, kind, q, mgroup):
         """M/MX/MY :173-208, R/RX/RY :211-219,255-274, MR/MRX/MRY :277-317 (one target)."""
-        rnd = self.collapse_words(self.csite)
-        self.csite += 1
+        rnd = self.collapse_words(mgroup, q)
         x, z = self.x[q], self.z[q]
         if basis == "Z":
             m = x.copy()
@@ -318,26 +318,29 @@ class FrameOracle:
             x[:] = (m ^ rnd) if kind == "M" else rnd
         if kind != "R":
             self.rec.append(m)
-            self.site += 1
 
-    def rec_noise(self, p, clock_qubits, rec_first, site_first):
-        """Result flips of M(p) etc. (measure_record_batch.inl:49-62)."""
+    def measure_list(self, basis, kind, qs, args):
+        """One measurement-type instruction on qubits qs (may repeat): collapse groups + optional result noise."""
+        rec_first = len(self.rec)
+        for a, b in self._runs([(q,) for q in qs]):
+            g = self.mgroup
+            self.mgroup += 1
+            for q in qs[a:b]:
+                self.measure(basis, kind, q, g)
+        if kind != "R" and args:
+            self.rec_noise(args[0], qs, rec_first)
+
+    def rec_noise(self, p, clock_qubits, rec_first):
+        """Result flips of M(p) etc. (measure_record_batch.inl:49-62). One noise group per run of distinct qubits."""
         lam = rate_of(p)
-        # process in runs of distinct clocks (a repeated target must see the previous run's clock)
-        start = 0
-        n = len(clock_qubits)
-        while start < n:
-            end = start
-            seen = set()
-            while end < n and clock_qubits[end] not in seen:
-                seen.add(clock_qubits[end])
-                end += 1
+        for a, b in self._runs([(q,) for q in clock_qubits]):
+            g = self.ngroup
+            self.ngroup += 1
 
-            def ev(i, g, shot, r, start=start):
-                self._flip(self.rec[rec_first + start + i], g, shot)
+            def ev(i, blk, shot, r, a=a):
+                self._flip(self.rec[rec_first + a + i], blk, shot)
 
-            self.run_sites(clock_qubits[start:end], lam, [site_first + start + i for i in range(end - start)], ev)
-            start = end
+            self.run_sites(clock_qubits[a:b], lam, g, ev)
 
     def cliff1(self, name, q):
         x, z = self.x[q], self.z[q]
@@ -425,15 +428,16 @@ class FrameOracle:
         return out
 
     def do_mpad(self, args, n):
-        rec_first, site_first = len(self.rec), self.site
+        rec_first = len(self.rec)
         for _ in range(n):
             self.rec.append(np.zeros(self.W, dtype=np.uint32))  # :905-912
-            self.site += 1
         if args:
             lam = rate_of(args[0])
-            for i in range(n):  # all share the global clock -> strictly sequential
-                self.run_sites([self.Q], lam, [site_first + i],
-                               lambda _i, g, shot, r, i=i: self._flip(self.rec[rec_first + i], g, shot))
+            for i in range(n):  # all share the global clock -> one noise group each, strictly sequential
+                g = self.ngroup
+                self.ngroup += 1
+                self.run_sites([self.Q], lam, g,
+                               lambda _i, blk, shot, r, i=i: self._flip(self.rec[rec_first + i], blk, shot))
 
     def do_mpp(self, args, targets):
         """decompose_mpp_operation, gate_decomposition.cc:88-161."""
@@ -449,11 +453,7 @@ class FrameOracle:
                 self.cliff1("H_YZ", q)
             for a, b in cx:
                 self.cliff2("CX", a, b)
-            rec_first, site_first = len(self.rec), self.site
-            for q in ms:
-                self.measure("Z", "M", q)
-            if args:
-                self.rec_noise(args[0], list(ms), rec_first, site_first)
+            self.measure_list("Z", "M", list(ms), args)
             for a, b in cx:
                 self.cliff2("CX", a, b)
             for q in h_yz:
@@ -521,11 +521,7 @@ class FrameOracle:
                 return
             for a, b in seg:
                 self.cliff2(conj, a, b)
-            rec_first, site_first = len(self.rec), self.site
-            for a, _ in seg:
-                self.measure(basis, "M", a)
-            if args:
-                self.rec_noise(args[0], [a for a, _ in seg], rec_first, site_first)
+            self.measure_list(basis, "M", [a for a, _ in seg], args)
             for a, b in seg:
                 self.cliff2(conj, a, b)
             seg.clear()
@@ -543,47 +539,31 @@ class FrameOracle:
     # -- noise channels ---------------------------------------------------------------------------
     def noise1(self, lam, cats, t1, t2, t3, qs, rec_first=None):
         """One Pauli-choice site per target (:633-643, :664-695, :779-839). qs may repeat."""
-        site_first = self.site
-        self.site += len(qs)
-        if lam == 0:
-            return
-        start, n = 0, len(qs)
-        while start < n:
-            end, seen = start, set()
-            while end < n and qs[end] not in seen:
-                seen.add(qs[end])
-                end += 1
+        for a, b in self._runs([(q,) for q in qs]):
+            g = self.ngroup
+            self.ngroup += 1
 
-            def ev(i, g, shot, r, start=start):
+            def ev(i, blk, shot, r, a=a):
                 v = r[1]
                 cat = cats[0] if v < t1 else cats[1] if v < t2 else cats[2] if v < t3 else cats[3]
-                q = qs[start + i]
+                q = qs[a + i]
                 if cat & 1:
-                    self._flip(self.x[q], g, shot)
+                    self._flip(self.x[q], blk, shot)
                 if cat & 2:
-                    self._flip(self.z[q], g, shot)
+                    self._flip(self.z[q], blk, shot)
                 if rec_first is not None:
-                    self._flip(self.rec[rec_first + start + i], g, shot)
+                    self._flip(self.rec[rec_first + a + i], blk, shot)
 
-            self.run_sites(qs[start:end], lam, [site_first + start + i for i in range(end - start)], ev)
-            start = end
+            self.run_sites(qs[a:b], lam, g, ev)
 
     def noise2(self, lam, pairs, table=None, last=0):
         """DEPOLARIZE2 :646-661 / PAULI_CHANNEL_2 (tableau_simulator.h:291-324 folded to one draw)."""
-        site_first = self.site
-        self.site += len(pairs)
-        if lam == 0:
-            return
-        start, n = 0, len(pairs)
-        while start < n:
-            end, seen = start, set()
-            while end < n and pairs[end][0] not in seen and pairs[end][1] not in seen:
-                seen.add(pairs[end][0])
-                seen.add(pairs[end][1])
-                end += 1
+        for a0, b0 in self._runs(pairs):
+            g = self.ngroup
+            self.ngroup += 1
 
-            def ev(i, g, shot, r, start=start):
-                a, b = pairs[start + i]
+            def ev(i, blk, shot, r, a0=a0):
+                a, b = pairs[a0 + i]
                 v = r[1]
                 if table is None:
                     pr = 1 + ((v * 15) >> 32)
@@ -597,30 +577,28 @@ class FrameOracle:
                     c1, c2 = pr >> 2, pr & 3
                     f = (((c1 + 1) >> 1) & 1, c1 >> 1, ((c2 + 1) >> 1) & 1, c2 >> 1)
                 if f[0]:
-                    self._flip(self.x[a], g, shot)
+                    self._flip(self.x[a], blk, shot)
                 if f[1]:
-                    self._flip(self.z[a], g, shot)
+                    self._flip(self.z[a], blk, shot)
                 if f[2]:
-                    self._flip(self.x[b], g, shot)
+                    self._flip(self.x[b], blk, shot)
                 if f[3]:
-                    self._flip(self.z[b], g, shot)
+                    self._flip(self.z[b], blk, shot)
 
-            self.run_sites([p[0] for p in pairs[start:end]], lam,
-                           [site_first + start + i for i in range(end - start)], ev)
-            start = end
+            self.run_sites([p[0] for p in pairs[a0:b0]], lam, g, ev)
 
     def corr(self, p, targets, reset):
         """do_CORRELATED_ERROR / do_ELSE_CORRELATED_ERROR :747-776."""
         if reset:
             self.flag[:] = 0
         lam = rate_of(p)
-        site = self.site
-        self.site += 1
+        g = self.ngroup
+        self.ngroup += 1
         tq = [(self.qmap[t & T_VAL], bool(t & T_X), bool(t & T_Z)) for t in targets]
         clock = tq[0][0] if tq else self.Q
 
-        def ev(i, g, shot, r):
-            w = g * self.K * 4 + (shot >> 5)
+        def ev(i, blk, shot, r):
+            w = blk * self.K * 4 + (shot >> 5)
             bit = np.uint32(1 << (shot & 31))
             if not (self.flag[w] & bit):
                 self.flag[w] |= bit
@@ -630,13 +608,14 @@ class FrameOracle:
                     if fz:
                         self.z[q][w] ^= bit
 
-        self.run_sites([clock], lam, [site], ev)
+        self.run_sites([clock], lam, g, ev)
 
     # -- driver -------------------------------------------------------------------------------------
     def run(self):
-        # reset_all :153-163 — x = 0, z = random for every qubit; collapse sites 0..Q-1
-        for q in range(self.Q):
-            self.measure("Z", "R", q)
+        # reset_all :153-163 — x = 0, z = random for every qubit; measure group 0
+        self.measure_list("Z", "R", list(range(self.Q)), [])
+        if self.Q == 0:
+            self.mgroup = 1
         for name, args, targets in flatten(self.ops):
             self.do_op(name, args, targets)
         return self
@@ -653,12 +632,7 @@ class FrameOracle:
                 self.controlled(name, targets[i], targets[i + 1])
         elif name in MEASURES:
             basis, kind = MEASURES[name]
-            rec_first, site_first = len(self.rec), self.site
-            qs = [qm[t & T_VAL] for t in targets]  # '!' ignored :176
-            for q in qs:
-                self.measure(basis, kind, q)
-            if kind != "R" and args:
-                self.rec_noise(args[0], qs, rec_first, site_first)
+            self.measure_list(basis, kind, [qm[t & T_VAL] for t in targets], args)  # '!' ignored :176
         elif name == "MPAD":
             self.do_mpad(args, len(targets))
         elif name == "MPP":

@@ -72,3 +72,38 @@ def exp_draw(r):
     lnm = (2.0 * s) * poly
     lnx = lnm + (t - 33).astype(np.float64) * _LN2
     return -lnx
+
+
+# ---------------------------------------------------------------------------------------------
+# Fixed-point exponential clock (spec v2, DESIGN.md "RNG addressing"): all integer arithmetic, so the
+# device (stim_b200/csrc/kernels.cu: exp_draw_fx) and this oracle agree bit for bit by construction.
+# Unit = 2**-56 nat.
+# ---------------------------------------------------------------------------------------------
+from .log2_table import LN2_Q24, LOG2_T  # noqa: E402
+
+FX_SHIFT = 56
+LAM_MAX = 1 << 62
+REM_SAT = 1 << 63
+
+
+def exp_draw_fx(r: int) -> int:
+    """-ln((r + 1/2) / 2**32) in units of 2**-56, via a 256-entry log2 table with linear interpolation."""
+    v = 2 * int(r) + 1
+    t = v.bit_length() - 1
+    vn = v << (32 - t)
+    frac = vn & 0xFFFFFFFF
+    i, f = frac >> 24, frac & 0xFFFFFF
+    log2m = LOG2_T[i] + (((LOG2_T[i + 1] - LOG2_T[i]) * f) >> 24)
+    return ((33 << 32) - ((t << 32) + log2m)) * LN2_Q24
+
+
+def lam_fx(p: float) -> int:
+    """Per-shot event rate of probability p (narrowed to float32 like the reference) in clock units."""
+    import math
+
+    f = float(np.float32(p))
+    if not f > 0:
+        return 0
+    if f >= 1:
+        return LAM_MAX
+    return min(int(math.ldexp(-math.log1p(-f), FX_SHIFT)), LAM_MAX)

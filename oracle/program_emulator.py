@@ -10,15 +10,13 @@ a time, and additionally checks the stream's concurrency contract (a race detect
 It lets the host lowering be validated on a machine without a GPU: emulator(lowered program) must equal
 oracle.frame_oracle (reference semantics on the circuit text) bit for bit.
 """
-import struct
-
 import numpy as np
 
 from . import philox as px
 
 HDR = 12
 (OP_END, OP_NEXT, OP_CLIFF1, OP_CLIFF2, OP_NOISE1, OP_NOISE2, OP_MEASURE, OP_RECZERO, OP_XORROWS, OP_OBS_PAULI,
- OP_FEEDBACK, OP_CORR) = range(12)
+ OP_FEEDBACK, OP_CORR, OP_QMAP) = range(13)
 F_BARRIER, F_REC, F_ACCUM, F_RESET, F_TABLE, F_NOFRAME = 1, 2, 4, 8, 16, 32
 
 PLAN_FIELDS = ["num_qubits", "q_pitch", "num_meas", "num_det", "num_obs", "rec_ring", "n_words", "chunk_words", "n_chunks",
@@ -27,6 +25,24 @@ PLAN_FIELDS = ["num_qubits", "q_pitch", "num_meas", "num_det", "num_obs", "rec_r
 
 def plan_dict(plan_words):
     return {k: int(plan_words[i]) for i, k in enumerate(PLAN_FIELDS)}
+
+
+def read_qmap(w, plan):
+    """physical frame row -> logical qubit index, from the GOP_QMAP batches at the head of the program."""
+    Q = plan["num_qubits"]
+    table = list(range(Q + 1))
+    chunk = plan["chunk_words"]
+    pc = 0
+    while True:
+        op = int(w[pc]) & 0xFF
+        if op == OP_NEXT:
+            pc = (pc // chunk + 1) * chunk
+        elif op == OP_QMAP:
+            n, words, base = int(w[pc + 1]), int(w[pc + 2]), int(w[pc + 3])
+            table[base: base + n] = [int(v) for v in w[pc + HDR: pc + HDR + n]]
+            pc += words
+        else:
+            return table
 
 
 class RaceError(AssertionError):
@@ -52,9 +68,10 @@ class Emulator:
         n_rec = plan["rec_ring"] if self.mode == 0 else max(plan["num_meas"], 1)
         self.rec = np.zeros((n_rec, W), dtype=np.uint32)
         self.out = np.zeros((plan["num_det"] + plan["num_obs"], W), dtype=np.uint32)
-        q = np.arange(self.Q + 1, dtype=np.uint64)
+        self.logical_of = read_qmap(self.w, plan)
+        q = np.asarray(self.logical_of, dtype=np.uint64)
         r = px.philox4x32_10(q, 0, col0 & 0xFFFFFFFF, px.TAG_CLOCK ^ (col0 >> 32), self.k0, self.k1)
-        self.clk = px.exp_draw(r[0])
+        self.clk = [px.exp_draw_fx(int(v)) for v in r[0]]
         # race detector state: resource -> (slot that wrote, set of slots that read) since the last barrier
         self.writer = {}
         self.readers = {}
@@ -90,31 +107,28 @@ class Emulator:
     def flip(self, arr, shot):
         arr[shot >> 5] ^= np.uint32(1 << (shot & 31))
 
-    def run_site(self, clock, lam, site, on_event):
-        E = float(self.clk[clock])
+    def run_site(self, clock, lam, group, on_event):
+        E = self.clk[clock]
         pos, kev, B = 0, 0, self.B
         while pos < B:
-            with np.errstate(invalid="ignore", over="ignore"):
-                rem = np.float64(B - pos) * np.float64(lam)
+            rem = min((B - pos) * lam, px.REM_SAT)
             if E >= rem:
-                E = float(np.float64(E) - rem)
+                E -= rem
                 break
-            with np.errstate(divide="ignore"):
-                jd = np.floor(np.float64(E) / np.float64(lam))
-            left = B - pos - 1
-            j = left if jd >= left else int(jd)
+            j = min(E // lam, B - pos - 1)
             shot = pos + j
-            r = px.philox4x32_10(site, kev, self.col0 & 0xFFFFFFFF, px.TAG_EVENT ^ (self.col0 >> 32), self.k0, self.k1)
+            r = px.philox4x32_10(group, self.logical_of[clock] | (kev << 16), self.col0 & 0xFFFFFFFF, px.TAG_EVENT ^ (self.col0 >> 32),
+                                 self.k0, self.k1)
             r = tuple(int(v) for v in r)
             on_event(shot, r)
-            E = float(px.exp_draw(np.uint64(r[0])))
+            E = px.exp_draw_fx(r[0])
             pos = shot + 1
             kev += 1
         self.clk[clock] = E
 
-    def collapse(self, csite):
+    def collapse(self, mgroup, q):
         cols = np.uint64(self.col0) + np.arange(self.K, dtype=np.uint64)
-        r = px.philox4x32_10(csite, 0, cols & np.uint64(0xFFFFFFFF), np.uint64(px.TAG_COLLAPSE) ^ (cols >> np.uint64(32)),
+        r = px.philox4x32_10(mgroup, self.logical_of[q], cols & np.uint64(0xFFFFFFFF), np.uint64(px.TAG_COLLAPSE) ^ (cols >> np.uint64(32)),
                              self.k0, self.k1)
         return np.stack(r, axis=1).reshape(-1)
 
@@ -133,9 +147,12 @@ class Emulator:
             if op == OP_NEXT:
                 pc = (pc // chunk + 1) * chunk
                 continue
+            if op == OP_QMAP:
+                pc += int(w[pc + 2])
+                continue
             n, words, extra = int(w[pc + 1]), int(w[pc + 2]), int(w[pc + 3])
             assert pc // chunk == (pc + words - 1) // chunk, "batch straddles a chunk"
-            lam = struct.unpack("<d", struct.pack("<II", int(w[pc + 4]), int(w[pc + 5])))[0]
+            lam = int(w[pc + 4]) | (int(w[pc + 5]) << 32)
             site0, csite0, rec0 = int(w[pc + 6]), int(w[pc + 7]), int(w[pc + 8])
             t1, t2, t3 = int(w[pc + 9]), int(w[pc + 10]), int(w[pc + 11])
             pay = w[pc + HDR: pc + words]
@@ -180,7 +197,7 @@ class Emulator:
                         if flags & F_REC:
                             self.flip(self.rec[(rec0 + i) & self.rec_mask], shot)
 
-                    self.run_site(q, lam, (site0 + i) & 0xFFFFFFFF, ev)
+                    self.run_site(q, lam, site0, ev)
             elif op == OP_NOISE2:
                 table = [int(v) for v in pay[:15]] if flags & F_TABLE else None
                 items = pay[15:] if flags & F_TABLE else pay
@@ -206,13 +223,13 @@ class Emulator:
                             if on:
                                 self.flip(arr, shot)
 
-                    self.run_site(q1, lam, (site0 + i) & 0xFFFFFFFF, ev)
+                    self.run_site(q1, lam, site0, ev)
             elif op == OP_MEASURE:
                 basis, kind = aux & 3, (aux >> 2) & 3
                 for i in range(n):
                     q = int(pay[i])
                     self.touch(i % S, q, True)
-                    rnd = self.collapse((csite0 + i) & 0xFFFFFFFF)
+                    rnd = self.collapse(csite0, q)
                     x, z = self.x[q].copy(), self.z[q].copy()
                     if basis == 2:
                         m, nx, nz = x, (x if kind == 0 else np.zeros_like(x)), rnd
@@ -285,6 +302,9 @@ class Emulator:
                     self.run_site(extra, lam, site0, ev)
             else:
                 raise ValueError(f"bad opcode {op} at word {pc}")
+            if op in (OP_NOISE1, OP_NOISE2):
+                self.writer.clear()  # the kernel ends noise batches with a block barrier (event queue)
+                self.readers.clear()
             pc += words
         return self
 

@@ -125,7 +125,7 @@ struct gstim_sampler {
 
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    DevBuf d_prog, d_table, d_rec, d_rowmap, d_stage[2], d_counts;
+    DevBuf d_prog, d_qmap, d_table, d_rec, d_rowmap, d_stage[2], d_counts;
     PinnedBuf h_stage[2];
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
     cudaEvent_t stage_ready[2] = {nullptr, nullptr};
@@ -222,7 +222,7 @@ void configure(gstim_sampler *s) {
     // K_max from the shared-memory budget
     uint32_t Q = s->lc.num_qubits;
     uint32_t q_pitch = Q | 1u;
-    size_t fixed = interp_smem_bytes(q_pitch, Q, 0, s->chunk_words);
+    size_t fixed = interp_smem_bytes(q_pitch, Q, 0, s->chunk_words, s->lc.max_items);
     size_t per_k = (size_t)2 * q_pitch * 16 + 16;
     if (fixed + per_k > s->smem_optin) {
         throw std::invalid_argument(
@@ -253,7 +253,9 @@ void configure(gstim_sampler *s) {
     s->words = serialize_program(s->lc, slots, s->chunk_words, &s->plan);
     s->d_prog.ensure(s->words.size() * 4);
     CK(cudaMemcpy(s->d_prog.p, s->words.data(), s->words.size() * 4, cudaMemcpyHostToDevice));
-    CK(interp_set_max_smem(interp_smem_bytes(q_pitch, Q, K_max, s->chunk_words)));
+    s->d_qmap.ensure(s->lc.logical_of.size() * 4);
+    CK(cudaMemcpy(s->d_qmap.p, s->lc.logical_of.data(), s->lc.logical_of.size() * 4, cudaMemcpyHostToDevice));
+    CK(interp_set_max_smem(interp_smem_bytes(q_pitch, Q, K_max, s->chunk_words, s->lc.max_items)));
 }
 
 uint32_t choose_K(const gstim_sampler *s, uint64_t shots) {
@@ -335,7 +337,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
     s->last_K = K;
     const uint32_t B = K * GSTIM_COL_SHOTS;
     const uint32_t Q = s->plan.num_qubits, q_pitch = s->plan.q_pitch;
-    const size_t smem = interp_smem_bytes(q_pitch, Q, K, s->chunk_words);
+    const size_t smem = interp_smem_bytes(q_pitch, Q, K, s->chunk_words, s->plan.max_items);
     const uint32_t rows = n_rows_of(s);
     const uint64_t total_blocks = (shots + B - 1) / B;
 
@@ -363,6 +365,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         const uint64_t chunk_shots = std::min<uint64_t>(nb * B, shots - first_shot);
         InterpParams p{};
         p.prog = (const uint32_t *)s->d_prog.p;
+        p.logical_of = (const uint32_t *)s->d_qmap.p;
         p.n_chunks = s->plan.n_chunks;
         p.chunk_words = s->chunk_words;
         p.Q = Q;
@@ -371,6 +374,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         p.G_log2 = s->G_log2;
         p.slots = s->slots;
         p.n_blocks = (uint32_t)nb;
+        p.max_items = s->plan.max_items;
         p.col0_base = s->next_col + done_blocks * K;
         p.seed_lo = (uint32_t)s->seed;
         p.seed_hi = (uint32_t)(s->seed >> 32);
@@ -882,7 +886,7 @@ int gstim_get_stats(const gstim_sampler *s, gstim_stats *out) {
         out->slots = s->slots;
         out->max_columns = s->K_max;
         out->chunk_words = s->chunk_words;
-        out->smem_bytes_max = (uint32_t)interp_smem_bytes(s->plan.q_pitch, s->plan.num_qubits, s->K_max, s->chunk_words);
+        out->smem_bytes_max = (uint32_t)interp_smem_bytes(s->plan.q_pitch, s->plan.num_qubits, s->K_max, s->chunk_words, s->plan.max_items);
     });
 }
 

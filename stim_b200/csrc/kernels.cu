@@ -15,6 +15,9 @@
 
 #include <algorithm>
 
+#define GSTIM_TABLE_QUAL __device__ const
+#include "log2_table.h"
+
 namespace gstim {
 
 // ------------------------------------------------------------------------------------------------
@@ -35,32 +38,17 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
-// Exp(1) variate from a uniform u32, using only IEEE double + - * / in a fixed order (no FMA
-// contraction, no libm), so the numpy oracle reproduces it bit for bit. u = (r + 1/2) / 2^32.
-__device__ __forceinline__ double exp_draw(uint32_t r) {
-    unsigned long long v = 2ull * r + 1ull;  // odd, < 2^33
-    int t = 63 - __clzll((long long)v);      // floor(log2 v), 0..32
-    double m = __dmul_rn((double)v, __longlong_as_double((long long)(1023 - t) << 52));  // v * 2^-t in [1,2)
-    if (m > 1.4142135623730951) {
-        m = __dmul_rn(m, 0.5);
-        t += 1;
-    }
-    double s = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0));
-    double s2 = __dmul_rn(s, s);
-    double poly = 1.0 / 21.0;
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0 / 19.0);
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0 / 17.0);
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0 / 15.0);
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0 / 13.0);
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0 / 11.0);
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0 / 9.0);
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0 / 7.0);
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0 / 5.0);
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0 / 3.0);
-    poly = __dadd_rn(__dmul_rn(poly, s2), 1.0);
-    double lnm = __dmul_rn(__dmul_rn(2.0, s), poly);
-    double lnx = __dadd_rn(lnm, __dmul_rn((double)(t - 33), 0.6931471805599453));
-    return -lnx;
+// Exp(1) variate from a uniform u32 in fixed point (unit 2^-56 nat): -ln((r + 1/2) / 2^32) through a
+// 256-entry log2 table with linear interpolation (max error 2e-6 nat). Integer-only, so the oracle
+// (oracle/philox.py: exp_draw_fx) reproduces it bit for bit. lt = table in shared memory: base[256], diff[256].
+__device__ __forceinline__ unsigned long long exp_draw_fx(uint32_t r, const uint32_t *lt) {
+    const unsigned long long v = 2ull * r + 1ull;  // odd, < 2^33
+    const int t = 63 - __clzll((long long)v);      // floor(log2 v), 0..32
+    const uint32_t frac = (uint32_t)(v << (32 - t));  // bits below the leading one, left aligned
+    const uint32_t i = frac >> 24, f = frac & 0xFFFFFFu;
+    const unsigned long long log2m = (unsigned long long)lt[i] + (((unsigned long long)lt[256 + i] * f) >> 24);
+    const unsigned long long lv = ((unsigned long long)t << 32) + log2m;
+    return ((33ull << 32) - lv) * (unsigned long long)GSTIM_LN2_Q24;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -104,19 +92,22 @@ __device__ __forceinline__ uint32_t bitmask(uint32_t aux, int bit) {
     return (uint32_t)0 - ((aux >> bit) & 1u);
 }
 
-size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words) {
+size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t max_items) {
     size_t b = 0;
-    b += (size_t)2 * K * q_pitch * 16;       // X, Z
-    b += (size_t)K * 16;                     // correlated-error flag row
-    b += ((size_t)(Q + 1) * 8 + 15) / 16 * 16;  // exponential clocks
-    b += (size_t)2 * chunk_words * 4;        // program ring
-    b += 32;                                 // mbarriers
+    b += (size_t)2 * K * q_pitch * 16;          // X, Z
+    b += (size_t)K * 16;                        // correlated-error flag row
+    b += ((size_t)(Q + 1) * 8 + 15) / 16 * 16;  // exponential clocks (u64 fixed point)
+    b += (size_t)2 * chunk_words * 4;           // program ring
+    b += 512 * 4;                               // log2 table
+    b += ((size_t)max_items * 2 + 15) / 16 * 16;  // event job queue
+    b += 32;                                    // mbarriers + queue counters
     return b;
 }
 
 struct Ctx {
     uint4 *X, *Z, *flag;
-    double *clk;
+    unsigned long long *clk;
+    const uint32_t *lt;
     uint32_t K, G, sub, slot, slots, q_pitch, B;
     uint64_t col0;
     uint32_t k0, k1;  // philox key
@@ -136,24 +127,39 @@ __device__ __forceinline__ void flip_rec(const Ctx &c, uint32_t rec_index, uint3
     *w ^= 1u << (shot & 31);
 }
 
-// Walks the events of one noise site over the block's B shots with the exponential clock E.
-// F(shot, r) is called for every event with the event's Philox draw r (r.x is consumed by the clock).
+__device__ __forceinline__ unsigned long long sat_mul(uint32_t n, unsigned long long lam) {
+    // min(n * lam, 2^63)
+    const unsigned long long lo = (unsigned long long)n * lam, hi = __umul64hi((unsigned long long)n, lam);
+    return (hi != 0 || lo >= (1ull << 63)) ? (1ull << 63) : lo;
+}
+
+// Walks the events of one noise site over the block's B shots with the exponential clock E (fixed point).
+// on_event(shot, r) is called for every event with the event's Philox draw r (r.x re-arms the clock).
+// Philox counter of the k-th event: (group, clock qubit | k << 16, col0 lo, TAG_EVENT ^ col0 hi).
 template <typename F>
-__device__ __forceinline__ void run_site(const Ctx &c, double &E, double lambda, uint32_t site, F &&on_event) {
+__device__ __forceinline__ void run_site(
+    const Ctx &c, unsigned long long &E, unsigned long long lam, float inv_lam, uint32_t group, uint32_t cq, F &&on_event) {
     uint32_t pos = 0, kev = 0;
     while (pos < c.B) {
-        double rem = __dmul_rn((double)(c.B - pos), lambda);
+        const unsigned long long rem = sat_mul(c.B - pos, lam);
         if (E >= rem) {
-            E = __dsub_rn(E, rem);
+            E -= rem;
             break;
         }
-        double jd = floor(__ddiv_rn(E, lambda));
-        uint32_t left = c.B - pos - 1;
-        uint32_t j = jd >= (double)left ? left : (uint32_t)jd;
-        uint32_t shot = pos + j;
-        uint4 r = philox4x32_10(site, kev, (uint32_t)c.col0, GTAG_EVENT ^ (uint32_t)(c.col0 >> 32), c.k0, c.k1);
+        // j = floor(E / lam), clamped to the shots left: float estimate + exact fix-up
+        const uint32_t left = c.B - pos - 1;
+        const float est = __ull2float_rz(E) * inv_lam;
+        uint32_t j = est >= (float)left ? left : (uint32_t)est;
+        while (j > 0 && (unsigned long long)j * lam > E) {
+            j--;
+        }
+        while (j < left && (unsigned long long)(j + 1) * lam <= E) {
+            j++;
+        }
+        const uint32_t shot = pos + j;
+        const uint4 r = philox4x32_10(group, cq | (kev << 16), (uint32_t)c.col0, GTAG_EVENT ^ (uint32_t)(c.col0 >> 32), c.k0, c.k1);
         on_event(shot, r);
-        E = exp_draw(r.x);
+        E = exp_draw_fx(r.x, c.lt);
         pos = shot + 1;
         kev++;
     }
@@ -182,11 +188,17 @@ __global__ void __launch_bounds__(1024, 1) gstim_interp_kernel(const InterpParam
     sp += (size_t)p.K * p.q_pitch * 16;
     c.flag = (uint4 *)sp;
     sp += (size_t)p.K * 16;
-    c.clk = (double *)sp;
+    c.clk = (unsigned long long *)sp;
     sp += ((size_t)(p.Q + 1) * 8 + 15) / 16 * 16;
     uint32_t *ring = (uint32_t *)sp;
     sp += (size_t)2 * p.chunk_words * 4;
+    uint32_t *lt = (uint32_t *)sp;
+    sp += 512 * 4;
+    uint16_t *jobq = (uint16_t *)sp;
+    sp += ((size_t)p.max_items * 2 + 15) / 16 * 16;
     uint64_t *mbar = (uint64_t *)sp;
+    uint32_t *jobn = (uint32_t *)(mbar + 2);  // two alternating event-queue counters
+    c.lt = lt;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t T = blockDim.x;
@@ -197,9 +209,16 @@ __global__ void __launch_bounds__(1024, 1) gstim_interp_kernel(const InterpParam
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        jobn[0] = 0;
+        jobn[1] = 0;
+    }
+    for (uint32_t i = tid; i < 256; i += T) {
+        lt[i] = GSTIM_LOG2_BASE[i];
+        lt[256 + i] = GSTIM_LOG2_DIFF[i];
     }
     __syncthreads();
     uint32_t phase0 = 0, phase1 = 0;
+    uint32_t qpar = 0;  // which queue counter the next noise batch uses
 
     for (uint32_t g = blockIdx.x; g < p.n_blocks; g += gridDim.x) {
         c.col0 = p.col0_base + (uint64_t)g * p.K;
@@ -218,8 +237,8 @@ __global__ void __launch_bounds__(1024, 1) gstim_interp_kernel(const InterpParam
         }
         // per-qubit exponential clocks (+ the global clock at index Q)
         for (uint32_t q = tid; q <= p.Q; q += T) {
-            uint4 r = philox4x32_10(q, 0, (uint32_t)c.col0, GTAG_CLOCK ^ (uint32_t)(c.col0 >> 32), c.k0, c.k1);
-            c.clk[q] = exp_draw(r.x);
+            uint4 r = philox4x32_10(p.logical_of[q], 0, (uint32_t)c.col0, GTAG_CLOCK ^ (uint32_t)(c.col0 >> 32), c.k0, c.k1);
+            c.clk[q] = exp_draw_fx(r.x, lt);
         }
         for (uint32_t k = tid; k < p.K; k += T) {
             c.flag[k] = make_uint4(0, 0, 0, 0);
@@ -306,55 +325,60 @@ __global__ void __launch_bounds__(1024, 1) gstim_interp_kernel(const InterpParam
                             }
                         }
                     } break;
-                    case GOP_NOISE1: {
+                    case GOP_NOISE1:
+                    case GOP_NOISE2: {
+                        // Pass A (item i -> thread group i % slots): advance each site's clock over the block's
+                        // B shots; sites whose clock runs out inside the block are pushed on a block-wide queue.
+                        // Pass B (any thread): drain the queue, so warps are full of event work instead of one
+                        // busy lane in five. Philox draws are addressed by (group, qubit), not by thread.
+                        const unsigned long long lam = ((unsigned long long)pw[pc + GH_LAMBDA_HI] << 32) | pw[pc + GH_LAMBDA_LO];
+                        const unsigned long long need = sat_mul(c.B, lam);
+                        const float inv_lam = 1.0f / __ull2float_rn(lam);
+                        const uint32_t group = pw[pc + GH_SITE0], rec0 = pw[pc + GH_REC0];
+                        const bool two = op == GOP_NOISE2;
+                        const bool table = two && (flags & GF_TABLE) != 0;
+                        const bool noframe = (flags & GF_NOFRAME) != 0;
+                        const uint32_t clock_override = pw[pc + GH_EXTRA];
+                        const uint32_t *items = table ? pay + 15 : pay;
+                        uint32_t *qn = &jobn[qpar];
                         if (c.sub == 0) {
-                            const double lambda = __hiloint2double((int)pw[pc + GH_LAMBDA_HI], (int)pw[pc + GH_LAMBDA_LO]);
-                            const double need = __dmul_rn((double)c.B, lambda);
-                            const uint32_t site0 = pw[pc + GH_SITE0], rec0 = pw[pc + GH_REC0];
-                            const uint32_t t1 = pw[pc + GH_T1], t2 = pw[pc + GH_T2], t3 = pw[pc + GH_T3];
-                            const bool noframe = (flags & GF_NOFRAME) != 0;
-                            const uint32_t clock_override = pw[pc + GH_EXTRA];
                             for (uint32_t i = c.slot; i < n; i += c.slots) {
-                                const uint32_t q = noframe ? clock_override - 1 : pay[i];
-                                double E = c.clk[q];
+                                const uint32_t q = noframe ? clock_override - 1 : (items[i] & 0xFFFF);
+                                const unsigned long long E = c.clk[q];
                                 if (E >= need) {
-                                    c.clk[q] = __dsub_rn(E, need);
-                                    continue;
+                                    c.clk[q] = E - need;
+                                } else {
+                                    jobq[atomicAdd(qn, 1u)] = (uint16_t)i;
                                 }
-                                run_site(c, E, lambda, site0 + i, [&](uint32_t shot, uint4 r) {
+                            }
+                        }
+                        __syncthreads();
+                        const uint32_t njobs = *qn;
+                        if (tid == 0) {
+                            jobn[qpar ^ 1] = 0;  // nobody touches the other counter until the next noise batch
+                        }
+                        qpar ^= 1;
+                        const uint32_t t1 = pw[pc + GH_T1], t2 = pw[pc + GH_T2], t3 = pw[pc + GH_T3];
+                        for (uint32_t jb = tid; jb < njobs; jb += T) {
+                            const uint32_t i = jobq[jb];
+                            const uint32_t w = items[i];
+                            const uint32_t q1 = noframe ? clock_override - 1 : (w & 0xFFFF), q2 = w >> 16;
+                            unsigned long long E = c.clk[q1];
+                            run_site(c, E, lam, inv_lam, group, p.logical_of[q1], [&](uint32_t shot, uint4 r) {
+                                if (!two) {
                                     const uint32_t v = r.y;
                                     const uint32_t sel = v < t1 ? 0u : v < t2 ? 2u : v < t3 ? 4u : 6u;
                                     const uint32_t cat = (aux >> sel) & 3u;
                                     if (cat & 1u) {
-                                        flip_frame(c, c.X, q, shot);
+                                        flip_frame(c, c.X, q1, shot);
                                     }
                                     if (cat & 2u) {
-                                        flip_frame(c, c.Z, q, shot);
+                                        flip_frame(c, c.Z, q1, shot);
                                     }
                                     if (flags & GF_REC) {
                                         flip_rec(c, rec0 + i, shot);
                                     }
-                                });
-                                c.clk[q] = E;
-                            }
-                        }
-                    } break;
-                    case GOP_NOISE2: {
-                        if (c.sub == 0) {
-                            const double lambda = __hiloint2double((int)pw[pc + GH_LAMBDA_HI], (int)pw[pc + GH_LAMBDA_LO]);
-                            const double need = __dmul_rn((double)c.B, lambda);
-                            const uint32_t site0 = pw[pc + GH_SITE0];
-                            const bool table = (flags & GF_TABLE) != 0;
-                            const uint32_t *items = table ? pay + 15 : pay;
-                            for (uint32_t i = c.slot; i < n; i += c.slots) {
-                                const uint32_t w = items[i];
-                                const uint32_t q1 = w & 0xFFFF, q2 = w >> 16;
-                                double E = c.clk[q1];
-                                if (E >= need) {
-                                    c.clk[q1] = __dsub_rn(E, need);
-                                    continue;
-                                }
-                                run_site(c, E, lambda, site0 + i, [&](uint32_t shot, uint4 r) {
+                                } else {
                                     uint32_t fx1, fz1, fx2, fz2;
                                     if (!table) {
                                         // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
@@ -390,21 +414,23 @@ __global__ void __launch_bounds__(1024, 1) gstim_interp_kernel(const InterpParam
                                     if (fz2) {
                                         flip_frame(c, c.Z, q2, shot);
                                     }
-                                });
-                                c.clk[q1] = E;
-                            }
+                                }
+                            });
+                            c.clk[q1] = E;
                         }
+                        __syncthreads();  // events were applied by arbitrary threads
                     } break;
                     case GOP_MEASURE: {
                         const uint32_t basis = aux & 3u, kind = (aux >> 2) & 3u;
-                        const uint32_t csite0 = pw[pc + GH_CSITE0], rec0 = pw[pc + GH_REC0];
+                        const uint32_t mgroup = pw[pc + GH_CSITE0], rec0 = pw[pc + GH_REC0];
                         for (uint32_t i = c.slot; i < n; i += c.slots) {
                             const uint32_t q = pay[i];
+                            const uint32_t lq = p.logical_of[q];
                             uint4 *rrow = c.rec + (uint64_t)((rec0 + i) & c.rec_mask) * c.rec_row_stride;
                             for (uint32_t k = c.sub; k < c.K; k += c.G) {
                                 const size_t o = (size_t)k * c.q_pitch + q;
                                 const uint64_t col = c.col0 + k;
-                                const uint4 rnd = philox4x32_10(csite0 + i, 0, (uint32_t)col, GTAG_COLLAPSE ^ (uint32_t)(col >> 32), c.k0, c.k1);
+                                const uint4 rnd = philox4x32_10(mgroup, lq, (uint32_t)col, GTAG_COLLAPSE ^ (uint32_t)(col >> 32), c.k0, c.k1);
                                 uint4 x = c.X[o], z = c.Z[o];
                                 uint4 m, nx, nz;
                                 const uint4 zero = make_uint4(0, 0, 0, 0);
@@ -499,11 +525,11 @@ __global__ void __launch_bounds__(1024, 1) gstim_interp_kernel(const InterpParam
                                     c.flag[k] = make_uint4(0, 0, 0, 0);
                                 }
                             }
-                            const double lambda = __hiloint2double((int)pw[pc + GH_LAMBDA_HI], (int)pw[pc + GH_LAMBDA_LO]);
-                            if (lambda != 0) {
+                            const unsigned long long lam = ((unsigned long long)pw[pc + GH_LAMBDA_HI] << 32) | pw[pc + GH_LAMBDA_LO];
+                            if (lam != 0) {
                                 const uint32_t cq = pw[pc + GH_EXTRA];
-                                double E = c.clk[cq];
-                                run_site(c, E, lambda, pw[pc + GH_SITE0], [&](uint32_t shot, uint4 r) {
+                                unsigned long long E = c.clk[cq];
+                                run_site(c, E, lam, 1.0f / __ull2float_rn(lam), pw[pc + GH_SITE0], p.logical_of[cq], [&](uint32_t shot, uint4 r) {
                                     uint32_t *fw = (uint32_t *)(c.flag + (shot >> 7)) + ((shot >> 5) & 3);
                                     const uint32_t bit = 1u << (shot & 31);
                                     if (!(*fw & bit)) {

@@ -8,6 +8,7 @@
 namespace gstim {
 
 struct InterpParams {
+    const uint32_t *logical_of; // physical frame row -> logical qubit index (Q+1 entries), addresses the Philox counters
     const uint32_t *prog;      // lowered program in global memory (16-byte aligned, n_chunks*chunk_words words)
     uint32_t n_chunks;
     uint32_t chunk_words;
@@ -17,6 +18,7 @@ struct InterpParams {
     uint32_t G_log2;           // log2(lanes per item)
     uint32_t slots;            // blockDim.x >> G_log2
     uint32_t n_blocks;         // shot blocks in this launch
+    uint32_t max_items;        // largest batch (sizes the event job queue)
     uint64_t col0_base;        // global column index (shot/128) of block 0
     uint32_t seed_lo, seed_hi; // Philox key
     uint4 *rec;                // measurement record rows
@@ -29,7 +31,7 @@ struct InterpParams {
 };
 
 // Shared memory the interpreter needs for (Q, K, chunk_words).
-size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words);
+size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t max_items);
 cudaError_t launch_interp(const InterpParams &p, uint32_t grid, uint32_t threads, size_t smem, cudaStream_t stream);
 cudaError_t interp_set_max_smem(size_t smem);
 

@@ -22,17 +22,23 @@ constexpr uint32_t RES_WRITE = 1u << 31;
 constexpr uint32_t ITEM_X = 1u << 30;  // component flags in OBS_PAULI / FEEDBACK / CORR payload words
 constexpr uint32_t ITEM_Z = 1u << 31;
 
-// Probability -> event rate per shot of the exponential clock. The reference narrows every
-// probability to float before sampling (probability_util.h:47, measure_record_batch.inl:52).
-double rate_of(double p) {
+// Probability -> per-shot event rate of the exponential clock in fixed point (unit 2^-56 nat, DESIGN.md
+// "RNG addressing"). The reference narrows every probability to float before sampling
+// (probability_util.h:47, measure_record_batch.inl:52). p >= 1 saturates: an event at every shot.
+constexpr uint64_t LAM_MAX = 1ull << 62;
+uint64_t rate_of(double p) {
     float f = (float)p;
     if (!(f > 0)) {
-        return 0.0;
+        return 0;
     }
     if (f >= 1) {
-        return std::numeric_limits<double>::infinity();
+        return LAM_MAX;
     }
-    return -std::log1p(-(double)f);
+    double v = std::ldexp(-std::log1p(-(double)f), 56);
+    if (v >= (double)LAM_MAX) {
+        return LAM_MAX;
+    }
+    return (uint64_t)v;
 }
 
 uint32_t thr(double frac) {
@@ -48,7 +54,7 @@ uint32_t thr(double frac) {
 
 struct Key {
     uint32_t op = 0, flags = 0, aux = 0, extra = 0;
-    double lambda = 0;
+    uint64_t lambda = 0;
     uint32_t t1 = 0, t2 = 0, t3 = 0;
     const uint32_t *table = nullptr;  // NOISE2 PAULI_CHANNEL_2 thresholds (15 words) or null
 };
@@ -61,7 +67,7 @@ struct Lowerer {
     uint32_t rec_mask = 0xFFFFFFFFu;
 
     // running counters (the RNG addressing contract)
-    uint32_t site = 0, csite = 0;
+    uint32_t ngroup = 0, mgroup = 0;  // noise / measure group counters
     uint64_t meas = 0;
     uint64_t det = 0;
 
@@ -110,7 +116,7 @@ struct Lowerer {
             cur.t2 != k.t2 || cur.t3 != k.t3) {
             return false;
         }
-        if (memcmp(&cur.lambda, &k.lambda, sizeof(double)) != 0) {
+        if (cur.lambda != k.lambda) {
             return false;
         }
         if (k.table != nullptr && memcmp(cur.payload.data(), k.table, 15 * sizeof(uint32_t)) != 0) {
@@ -120,7 +126,8 @@ struct Lowerer {
     }
 
     // Adds one item. `res` lists resource ids, RES_WRITE-tagged when written.
-    // use_*: whether this op consumes that counter (continuity is then required inside a batch).
+    // use_site / use_csite: the batch is tied to that noise / measure group (all items share it);
+    // use_rec: items record into consecutive rows rec0 + i.
     void add(
         const Key &k,
         const uint32_t *item_words,
@@ -137,7 +144,7 @@ struct Lowerer {
         bool ok = open && !never_merge && same_key(k) && cur.op != GOP_CORR;
         if (ok) {
             uint32_t n = cur.n_items;
-            if ((use_site && cur.site0 + n != site_v) || (use_csite && cur.csite0 + n != csite_v) ||
+            if ((use_site && cur.site0 != site_v) || (use_csite && cur.csite0 != csite_v) ||
                 (use_rec && cur.rec0 + n != rec_v)) {
                 ok = false;
             }
@@ -210,8 +217,36 @@ struct Lowerer {
         uint32_t r[2] = {rec_res(rec_index), q | RES_WRITE};
         add(k, w, 2, r, 2, false, 0, false, 0, false, 0);
     }
-    // basis/kind measurement or reset of one qubit. Allocates csite (+ rec and site when it records).
-    void measure(uint32_t basis, uint32_t kind, uint32_t q) {
+    // Splits a target list into maximal runs without a repeated qubit (each run = one RNG group).
+    template <typename KEYS>
+    static std::vector<std::pair<size_t, size_t>> runs_of(size_t n, KEYS &&keys_of) {
+        std::vector<std::pair<size_t, size_t>> runs;
+        std::vector<uint32_t> seen;
+        size_t start = 0;
+        for (size_t i = 0; i < n; i++) {
+            uint32_t ks[2];
+            int nk = keys_of(i, ks);
+            bool rep = false;
+            for (int j = 0; j < nk; j++) {
+                rep |= std::find(seen.begin(), seen.end(), ks[j]) != seen.end();
+            }
+            if (rep) {
+                runs.push_back({start, i});
+                start = i;
+                seen.clear();
+            }
+            for (int j = 0; j < nk; j++) {
+                seen.push_back(ks[j]);
+            }
+        }
+        if (start < n) {
+            runs.push_back({start, n});
+        }
+        return runs;
+    }
+
+    // basis/kind measurement or reset of one qubit inside measure group `mg`.
+    void measure(uint32_t basis, uint32_t kind, uint32_t q, uint32_t mg) {
         Key k;
         k.op = GOP_MEASURE;
         k.aux = basis | (kind << 2);
@@ -222,45 +257,91 @@ struct Lowerer {
             r[1] = rec_res(meas) | RES_WRITE;
             nr = 2;
         }
-        add(k, &q, 1, r, nr, false, 0, true, csite, records, (uint32_t)meas);
-        csite++;
+        add(k, &q, 1, r, nr, false, 0, true, mg, records, (uint32_t)meas);
         if (records) {
             meas++;
-            site++;
         }
     }
-    // Result-flip noise on record rows [rec_first, rec_first+n) whose sites are [site_first, ...).
-    void rec_noise(double p, const std::vector<uint32_t> &clock_qubits, uint64_t rec_first, uint32_t site_first) {
-        double lam = rate_of(p);
-        if (lam == 0) {
-            return;
+    // One measurement-type instruction on compact qubits qs (may repeat): collapse groups + optional result noise.
+    void measure_list(uint32_t basis, uint32_t kind, const std::vector<uint32_t> &qs, const std::vector<double> &args) {
+        uint64_t rec_first = meas;
+        for (auto run : runs_of(qs.size(), [&](size_t i, uint32_t *ks) { ks[0] = qs[i]; return 1; })) {
+            uint32_t mg = mgroup++;
+            for (size_t i = run.first; i < run.second; i++) {
+                measure(basis, kind, qs[i], mg);
+            }
         }
+        if (kind != GK_R && !args.empty()) {
+            rec_noise(args[0], qs, rec_first);
+        }
+    }
+    // Result-flip noise on record rows rec_first + i with clock qubits clock_qubits[i].
+    void rec_noise(double p, const std::vector<uint32_t> &clock_qubits, uint64_t rec_first) {
+        uint64_t lam = rate_of(p);
         Key k;
         k.op = GOP_NOISE1;
         k.flags = GF_REC;
         k.lambda = lam;
-        for (size_t i = 0; i < clock_qubits.size(); i++) {
-            uint32_t q = clock_qubits[i];
-            uint32_t r[2] = {q | RES_WRITE, rec_res(rec_first + i) | RES_WRITE};
-            add(k, &q, 1, r, 2, true, site_first + (uint32_t)i, false, 0, true, (uint32_t)(rec_first + i));
+        for (auto run : runs_of(clock_qubits.size(), [&](size_t i, uint32_t *ks) { ks[0] = clock_qubits[i]; return 1; })) {
+            uint32_t g = ngroup++;
+            if (lam == 0) {
+                continue;
+            }
+            for (size_t i = run.first; i < run.second; i++) {
+                uint32_t q = clock_qubits[i];
+                uint32_t r[2] = {q | RES_WRITE, rec_res(rec_first + i) | RES_WRITE};
+                add(k, &q, 1, r, 2, true, g, false, 0, true, (uint32_t)(rec_first + i));
+            }
         }
     }
-    void noise1(double lam, uint32_t cats, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t q, uint32_t flags, uint64_t rec_index) {
+    // Single-target Pauli-choice noise over qs (may repeat). rec_first >= 0: every event also flips rec row.
+    void noise1_list(uint64_t lam, uint32_t cats, uint32_t t1, uint32_t t2, uint32_t t3, const std::vector<uint32_t> &qs,
+                     bool herald, uint64_t rec_first) {
         Key k;
         k.op = GOP_NOISE1;
-        k.flags = flags;
+        k.flags = herald ? GF_REC : 0;
         k.aux = cats;
         k.lambda = lam;
         k.t1 = t1;
         k.t2 = t2;
         k.t3 = t3;
-        uint32_t r[2] = {q | RES_WRITE, 0};
-        uint32_t nr = 1;
-        if (flags & GF_REC) {
-            r[1] = rec_res(rec_index) | RES_WRITE;
-            nr = 2;
+        for (auto run : runs_of(qs.size(), [&](size_t i, uint32_t *ks) { ks[0] = qs[i]; return 1; })) {
+            uint32_t g = ngroup++;
+            if (lam == 0) {
+                continue;
+            }
+            for (size_t i = run.first; i < run.second; i++) {
+                uint32_t q = qs[i];
+                uint32_t r[2] = {q | RES_WRITE, 0};
+                uint32_t nr = 1;
+                if (herald) {
+                    r[1] = rec_res(rec_first + i) | RES_WRITE;
+                    nr = 2;
+                }
+                add(k, &q, 1, r, nr, true, g, false, 0, herald, (uint32_t)(rec_first + i));
+            }
         }
-        add(k, &q, 1, r, nr, true, site, false, 0, (flags & GF_REC) != 0, (uint32_t)rec_index);
+    }
+    void noise2_list(uint64_t lam, const std::vector<uint32_t> &flat_pairs, const uint32_t *table, uint32_t last) {
+        Key k;
+        k.op = GOP_NOISE2;
+        k.flags = table ? GF_TABLE : 0;
+        k.aux = table ? last : 0;
+        k.lambda = lam;
+        k.table = table;
+        size_t n = flat_pairs.size() / 2;
+        for (auto run : runs_of(n, [&](size_t i, uint32_t *ks) { ks[0] = flat_pairs[2 * i]; ks[1] = flat_pairs[2 * i + 1]; return 2; })) {
+            uint32_t g = ngroup++;
+            if (lam == 0) {
+                continue;
+            }
+            for (size_t i = run.first; i < run.second; i++) {
+                uint32_t a = flat_pairs[2 * i], b = flat_pairs[2 * i + 1];
+                uint32_t w = a | (b << 16);
+                uint32_t r[2] = {a | RES_WRITE, b | RES_WRITE};
+                add(k, &w, 1, r, 2, true, g, false, 0, false, 0);
+            }
+        }
     }
     void rec_zero(uint64_t rec_index) {
         Key k;
@@ -349,30 +430,26 @@ struct Lowerer {
 
     void do_measure_gate(const Instruction &op) {
         uint32_t basis = op.gate->param & 3, kind = op.gate->param >> 2;
-        uint64_t rec_first = meas;
-        uint32_t site_first = site;
         std::vector<uint32_t> qs;
         for (uint32_t t : op.targets) {
-            uint32_t q = q_of(t);
-            measure(basis, kind, q);
-            qs.push_back(q);
+            qs.push_back(q_of(t));  // '!' is ignored: it lives in the reference sample (frame_simulator.inl:176)
         }
-        if (kind != GK_R && !op.args.empty()) {
-            rec_noise(op.args[0], qs, rec_first, site_first);
-        }
+        measure_list(basis, kind, qs, op.args);
     }
 
-    void do_mpad(const Instruction &op) {
+    void do_mpad(const std::vector<double> &args, size_t n) {
         uint64_t rec_first = meas;
-        uint32_t site_first = site;
-        for (size_t i = 0; i < op.targets.size(); i++) {
+        for (size_t i = 0; i < n; i++) {
             rec_zero(meas);
             meas++;
-            site++;
         }
-        double lam = op.args.empty() ? 0 : rate_of(op.args[0]);
-        if (lam != 0) {
-            for (size_t i = 0; i < op.targets.size(); i++) {
+        if (!args.empty()) {
+            uint64_t lam = rate_of(args[0]);
+            for (size_t i = 0; i < n; i++) {
+                uint32_t g = ngroup++;  // all MPAD results share the global clock: one group each
+                if (lam == 0) {
+                    continue;
+                }
                 Key k;
                 k.op = GOP_NOISE1;
                 k.flags = GF_REC | GF_NOFRAME;
@@ -380,7 +457,7 @@ struct Lowerer {
                 k.extra = Q + 1;  // clock = global clock (index Q)
                 uint32_t r[2] = {res_clock | RES_WRITE, rec_res(rec_first + i) | RES_WRITE};
                 uint32_t dummy = Q;
-                add(k, &dummy, 1, r, 2, true, site_first + (uint32_t)i, false, 0, true, (uint32_t)(rec_first + i));
+                add(k, &dummy, 1, r, 2, true, g, false, 0, true, (uint32_t)(rec_first + i));
             }
         }
     }
@@ -448,8 +525,6 @@ struct Lowerer {
         std::vector<uint32_t> h_xz, h_yz, cx_pairs, ms;
         std::vector<uint8_t> merged(Q, 0);
         const GateInfo *CX = find_gate("CX");
-        uint64_t rec_first = 0;
-        uint32_t site_first = 0;
         auto flush_group = [&]() {
             if (ms.empty()) {
                 return;
@@ -459,14 +534,7 @@ struct Lowerer {
             for (size_t i = 0; i < cx_pairs.size(); i += 2) {
                 cliff2(CX->param, cx_pairs[i], cx_pairs[i + 1]);
             }
-            rec_first = meas;
-            site_first = site;
-            for (uint32_t q : ms) {
-                measure(GB_Z, GK_M, q);
-            }
-            if (!op.args.empty()) {
-                rec_noise(op.args[0], ms, rec_first, site_first);
-            }
+            measure_list(GB_Z, GK_M, ms, op.args);
             for (size_t i = 0; i < cx_pairs.size(); i += 2) {
                 cliff2(CX->param, cx_pairs[i], cx_pairs[i + 1]);
             }
@@ -481,11 +549,7 @@ struct Lowerer {
         for (const Product &p : read_products(op, false)) {
             if (p.terms.empty()) {
                 flush_group();
-                Instruction pad;
-                pad.gate = find_gate("MPAD");
-                pad.args = op.args;
-                pad.targets = {0};
-                do_mpad(pad);
+                do_mpad(op.args, 1);
                 continue;
             }
             bool overlap = false;
@@ -561,16 +625,11 @@ struct Lowerer {
             for (size_t i = 0; i < seg.size(); i += 2) {
                 cliff2(conj->param, seg[i], seg[i + 1]);
             }
-            uint64_t rec_first = meas;
-            uint32_t site_first = site;
             std::vector<uint32_t> ms;
             for (size_t i = 0; i < seg.size(); i += 2) {
-                measure(basis, GK_M, seg[i]);
                 ms.push_back(seg[i]);
             }
-            if (!op.args.empty()) {
-                rec_noise(op.args[0], ms, rec_first, site_first);
-            }
+            measure_list(basis, GK_M, ms, op.args);
             for (size_t i = 0; i < seg.size(); i += 2) {
                 cliff2(conj->param, seg[i], seg[i + 1]);
             }
@@ -589,8 +648,16 @@ struct Lowerer {
         flush_seg();
     }
 
+    std::vector<uint32_t> compact_targets(const Instruction &op) {
+        std::vector<uint32_t> qs;
+        for (uint32_t t : op.targets) {
+            qs.push_back(q_of(t));
+        }
+        return qs;
+    }
+
     void do_noise1_gate(const Instruction &op) {
-        double lam = rate_of(op.args[0]);
+        uint64_t lam = rate_of(op.args[0]);
         uint32_t cats, t1 = 0, t2 = 0, t3 = 0;
         switch (op.gate->param) {
             case 1:
@@ -609,28 +676,11 @@ struct Lowerer {
                 t3 = t2;
                 break;
         }
-        for (uint32_t t : op.targets) {
-            if (lam != 0) {
-                noise1(lam, cats, t1, t2, t3, q_of(t), 0, 0);
-            }
-            site++;
-        }
+        noise1_list(lam, cats, t1, t2, t3, compact_targets(op), false, 0);
     }
 
     void do_depolarize2(const Instruction &op) {
-        double lam = rate_of(op.args[0]);
-        Key k;
-        k.op = GOP_NOISE2;
-        k.lambda = lam;
-        for (size_t i = 0; i < op.targets.size(); i += 2) {
-            if (lam != 0) {
-                uint32_t a = q_of(op.targets[i]), b = q_of(op.targets[i + 1]);
-                uint32_t w = a | (b << 16);
-                uint32_t r[2] = {a | RES_WRITE, b | RES_WRITE};
-                add(k, &w, 1, r, 2, true, site, false, 0, false, 0);
-            }
-            site++;
-        }
+        noise2_list(rate_of(op.args[0]), compact_targets(op), nullptr, 0);
     }
 
     // One site with the channel's total probability, then a category draw: same joint distribution
@@ -638,7 +688,7 @@ struct Lowerer {
     void do_pauli_channel_1(const Instruction &op) {
         double px = op.args[0], py = op.args[1], pz = op.args[2];
         double tot = px + py + pz;
-        double lam = rate_of(std::min(tot, 1.0));
+        uint64_t lam = rate_of(std::min(tot, 1.0));
         uint32_t t1 = 0, t2 = 0, cats = 0;
         if (tot > 0) {
             t1 = thr(px / tot);
@@ -646,12 +696,7 @@ struct Lowerer {
             uint32_t last = pz > 0 ? 2u : py > 0 ? 3u : 1u;
             cats = 1u | (3u << 2) | (last << 4) | (last << 6);
         }
-        for (uint32_t t : op.targets) {
-            if (lam != 0) {
-                noise1(lam, cats, t1, t2, t2, q_of(t), 0, 0);
-            }
-            site++;
-        }
+        noise1_list(lam, cats, t1, t2, t2, compact_targets(op), false, 0);
     }
 
     void do_pauli_channel_2(const Instruction &op) {
@@ -659,7 +704,7 @@ struct Lowerer {
         for (double p : op.args) {
             tot += p;
         }
-        double lam = rate_of(std::min(tot, 1.0));
+        uint64_t lam = rate_of(std::min(tot, 1.0));
         uint32_t table[15];
         uint32_t last = 1;
         double cum = 0;
@@ -670,21 +715,7 @@ struct Lowerer {
                 last = (uint32_t)i + 1;
             }
         }
-        Key k;
-        k.op = GOP_NOISE2;
-        k.flags = GF_TABLE;
-        k.aux = last;
-        k.lambda = lam;
-        k.table = table;
-        for (size_t i = 0; i < op.targets.size(); i += 2) {
-            if (lam != 0) {
-                uint32_t a = q_of(op.targets[i]), b = q_of(op.targets[i + 1]);
-                uint32_t w = a | (b << 16);
-                uint32_t r[2] = {a | RES_WRITE, b | RES_WRITE};
-                add(k, &w, 1, r, 2, true, site, false, 0, false, 0);
-            }
-            site++;
-        }
+        noise2_list(lam, compact_targets(op), table, last);
     }
 
     void do_corr(const Instruction &op) {
@@ -704,16 +735,16 @@ struct Lowerer {
             res.push_back(res_clock | RES_WRITE);
         }
         k.extra = clock;
+        uint32_t g = ngroup++;
         if (k.lambda != 0 || (k.flags & GF_RESET_FLAG)) {
             flush();
             // dedupe resources (a qubit may appear twice in the Pauli list)
             std::sort(res.begin(), res.end());
             res.erase(std::unique(res.begin(), res.end()), res.end());
-            add(k, words.data(), (uint32_t)words.size(), res.data(), (uint32_t)res.size(), true, site, false, 0, false, 0, true);
+            add(k, words.data(), (uint32_t)words.size(), res.data(), (uint32_t)res.size(), true, g, false, 0, false, 0, true);
             cur.n_items = (uint32_t)words.size();
             flush();
         }
-        site++;
     }
 
     void do_heralded(const Instruction &op) {
@@ -732,22 +763,13 @@ struct Lowerer {
             t2 = tot > 0 ? thr((hx + hz) / tot) : 0;
             t3 = tot > 0 ? thr((hx + hz + hy) / tot) : 0;
         }
-        double lam = rate_of(std::min(tot, 1.0));
+        uint64_t lam = rate_of(std::min(tot, 1.0));
         uint64_t rec_first = meas;
-        uint32_t site_first = site;
         for (size_t i = 0; i < op.targets.size(); i++) {
             rec_zero(meas);
             meas++;
-            site++;
         }
-        if (lam != 0) {
-            uint32_t save = site;
-            for (size_t i = 0; i < op.targets.size(); i++) {
-                site = site_first + (uint32_t)i;
-                noise1(lam, cats, t1, t2, t3, q_of(op.targets[i]), GF_REC, rec_first + i);
-            }
-            site = save;
-        }
+        noise1_list(lam, cats, t1, t2, t3, compact_targets(op), true, rec_first);
     }
 
     void do_detector(const Instruction &op) {
@@ -807,7 +829,7 @@ struct Lowerer {
                 do_measure_gate(op);
                 break;
             case GateCat::MPAD:
-                do_mpad(op);
+                do_mpad(op.args, op.targets.size());
                 break;
             case GateCat::MPP:
                 do_mpp(op);
@@ -872,6 +894,204 @@ void mark_used(const Circuit &c, std::vector<uint8_t> &used) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Layout post-pass (performance only; semantics and RNG addressing are unaffected).
+//   1. physical frame rows: qubits are renumbered so that, inside every two-qubit batch, both operand
+//      sets spread evenly over the 8 sixteen-byte bank groups of shared memory (row index mod 8);
+//      lc.logical_of[] keeps the logical (sorted) index that addresses the Philox counters.
+//   2. items of every gate/noise batch are reordered into groups of 8 (one quarter warp) whose rows
+//      are distinct mod 8 for each operand -> conflict-free LDS.128/STS.128. Groups are perfect matchings
+//      of the 8x8 (residue of operand 1, residue of operand 2) multigraph.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+bool is_pair_op(const Batch &b) {
+    return b.op == GOP_CLIFF2 || b.op == GOP_NOISE2;
+}
+bool is_single_op(const Batch &b) {
+    return b.op == GOP_CLIFF1 || (b.op == GOP_NOISE1 && !(b.flags & (GF_REC | GF_NOFRAME)));
+}
+size_t item_skip(const Batch &b) {
+    return (b.op == GOP_NOISE2 && (b.flags & GF_TABLE)) ? 15 : 0;
+}
+
+void assign_physical_rows(LoweredCircuit &lc) {
+    const uint32_t Q = lc.num_qubits;
+    std::vector<uint32_t> phys(Q, UINT32_MAX);
+    uint32_t next = 0;
+    for (const Batch &b : lc.batches) {
+        if (!is_pair_op(b)) {
+            continue;
+        }
+        size_t skip = item_skip(b);
+        for (int role = 0; role < 2; role++) {
+            for (size_t i = skip; i < b.payload.size(); i++) {
+                uint32_t q = role == 0 ? (b.payload[i] & 0xFFFF) : (b.payload[i] >> 16);
+                if (phys[q] == UINT32_MAX) {
+                    phys[q] = next++;
+                }
+            }
+        }
+    }
+    for (uint32_t q = 0; q < Q; q++) {
+        if (phys[q] == UINT32_MAX) {
+            phys[q] = next++;
+        }
+    }
+    lc.logical_of.assign(Q + 1, Q);
+    for (uint32_t q = 0; q < Q; q++) {
+        lc.logical_of[phys[q]] = q;
+    }
+    auto lo24 = [&](uint32_t w) { return (w & 0xFF000000u) | phys[w & 0xFFFFFFu]; };
+    for (Batch &b : lc.batches) {
+        size_t skip = item_skip(b);
+        switch (b.op) {
+            case GOP_CLIFF1:
+            case GOP_MEASURE:
+                for (auto &w : b.payload) {
+                    w = phys[w];
+                }
+                break;
+            case GOP_NOISE1:
+                if (!(b.flags & GF_NOFRAME)) {
+                    for (auto &w : b.payload) {
+                        w = phys[w];
+                    }
+                }
+                break;
+            case GOP_CLIFF2:
+            case GOP_NOISE2:
+                for (size_t i = skip; i < b.payload.size(); i++) {
+                    b.payload[i] = phys[b.payload[i] & 0xFFFF] | (phys[b.payload[i] >> 16] << 16);
+                }
+                break;
+            case GOP_OBS_PAULI:
+            case GOP_FEEDBACK:
+                for (size_t i = 1; i < b.payload.size(); i += 2) {
+                    b.payload[i] = lo24(b.payload[i]);
+                }
+                break;
+            case GOP_CORR:
+                for (auto &w : b.payload) {
+                    w = lo24(w);
+                }
+                if (b.extra < Q) {
+                    b.extra = phys[b.extra];
+                }
+                break;
+            default:
+                break;
+        }
+    }
+}
+
+// Kuhn's augmenting-path matching on the 8x8 residue multigraph.
+bool try_augment(int u, const uint32_t cnt[8][8], int match_v[8], bool seen[8]) {
+    for (int v = 0; v < 8; v++) {
+        if (cnt[u][v] == 0 || seen[v]) {
+            continue;
+        }
+        seen[v] = true;
+        if (match_v[v] < 0 || try_augment(match_v[v], cnt, match_v, seen)) {
+            match_v[v] = u;
+            return true;
+        }
+    }
+    return false;
+}
+
+void spread_banks(Batch &b) {
+    const bool pairs = is_pair_op(b);
+    if (!pairs && !is_single_op(b)) {
+        return;
+    }
+    const size_t skip = item_skip(b);
+    const size_t n = b.payload.size() - skip;
+    if (n < 9 || n != b.res_off.size() - 1) {
+        return;
+    }
+    const uint32_t *items = b.payload.data() + skip;
+    // cell[k1][k2] = stack of item indices (earliest on top)
+    std::vector<uint32_t> cell[8][8];
+    uint32_t cnt[8][8] = {};
+    for (size_t i = n; i-- > 0;) {
+        uint32_t k1 = items[i] & 7, k2 = pairs ? ((items[i] >> 16) & 7) : (uint32_t)(0);
+        if (!pairs) {
+            k2 = k1;  // singles: diagonal cells, a "matching" is just one item per residue
+        }
+        cell[k1][k2].push_back((uint32_t)i);
+        cnt[k1][k2]++;
+    }
+    std::vector<uint32_t> order;
+    order.reserve(n);
+    while (order.size() < n) {
+        int match_v[8];
+        std::fill(match_v, match_v + 8, -1);
+        // visit operand-1 residues with the most remaining items first, so heavy rows are never starved
+        int us[8];
+        uint32_t deg[8];
+        for (int u = 0; u < 8; u++) {
+            us[u] = u;
+            deg[u] = 0;
+            for (int v = 0; v < 8; v++) {
+                deg[u] += cnt[u][v];
+            }
+        }
+        std::sort(us, us + 8, [&](int a, int c) { return deg[a] > deg[c]; });
+        for (int t = 0; t < 8; t++) {
+            if (deg[us[t]] == 0) {
+                continue;
+            }
+            bool seen[8] = {};
+            try_augment(us[t], cnt, match_v, seen);
+        }
+        size_t before = order.size();
+        bool used_u[8] = {};
+        for (int v = 0; v < 8; v++) {
+            if (match_v[v] >= 0) {
+                int u = match_v[v];
+                order.push_back(cell[u][v].back());
+                cell[u][v].pop_back();
+                cnt[u][v]--;
+                used_u[u] = true;
+            }
+        }
+        // fill the rest of the group (unavoidable conflicts) with items from the fullest rows
+        while (order.size() - before < 8 && order.size() < n) {
+            int bu = -1, bv = -1;
+            uint32_t best = 0;
+            for (int u = 0; u < 8; u++) {
+                for (int v = 0; v < 8; v++) {
+                    uint32_t score = cnt[u][v] ? cnt[u][v] + (used_u[u] ? 0 : 1000000u) : 0;
+                    if (score > best) {
+                        best = score;
+                        bu = u;
+                        bv = v;
+                    }
+                }
+            }
+            if (bu < 0) {
+                break;
+            }
+            order.push_back(cell[bu][bv].back());
+            cell[bu][bv].pop_back();
+            cnt[bu][bv]--;
+            used_u[bu] = true;
+        }
+    }
+    std::vector<uint32_t> new_payload(b.payload.begin(), b.payload.begin() + (long)skip), new_res, new_off{0};
+    for (uint32_t it : order) {
+        new_payload.push_back(items[it]);
+        new_res.insert(new_res.end(), b.res.begin() + b.res_off[it], b.res.begin() + b.res_off[it + 1]);
+        new_off.push_back((uint32_t)new_res.size());
+    }
+    b.payload.swap(new_payload);
+    b.res.swap(new_res);
+    b.res_off.swap(new_off);
+}
+
+}  // namespace
+
 LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words) {
     Lowerer lw(max_batch_words);
     LoweredCircuit &lc = lw.lc;
@@ -921,9 +1141,12 @@ LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch
     lw.wr_stamp.assign(lc.num_resources, 0);
 
     // Start of every shot: x <- 0, z <- random for all qubits (frame_simulator.inl:153-163).
-    // Collapse sites 0..Q-1 are reserved for this.
-    for (uint32_t q = 0; q < Q; q++) {
-        lw.measure(GB_Z, GK_R, q);
+    // Measure group 0 is reserved for this.
+    {
+        uint32_t mg = lw.mgroup++;  // measure group 0, also when the circuit has no qubits
+        for (uint32_t q = 0; q < Q; q++) {
+            lw.measure(GB_Z, GK_R, q, mg);
+        }
     }
     // Observable rows start at zero.
     if (mode == 0) {
@@ -935,8 +1158,12 @@ LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch
         lw.do_op(op);
     });
     lw.flush();
-    lc.num_sites = lw.site;
-    lc.num_csites = lw.csite;
+    assign_physical_rows(lc);
+    for (Batch &b : lc.batches) {
+        spread_banks(b);
+    }
+    lc.num_sites = lw.ngroup;
+    lc.num_csites = lw.mgroup;
     return std::move(lw.lc);
 }
 
@@ -954,6 +1181,24 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         out[base + GH_OP] = op;
         out[base + GH_WORDS] = words;
     };
+
+    // physical row -> logical qubit table (read by the host and by oracle/program_emulator.py; the kernel skips it)
+    {
+        const uint32_t per = chunk_words - 2 * GSTIM_HDR_WORDS;
+        for (size_t base0 = 0; base0 < lc.logical_of.size(); base0 += per) {
+            uint32_t cnt = (uint32_t)std::min<size_t>(per, lc.logical_of.size() - base0);
+            uint32_t pos = (uint32_t)(out.size() % chunk_words);
+            if (pos + GSTIM_HDR_WORDS + cnt + GSTIM_HDR_WORDS > chunk_words) {
+                put_header(GOP_NEXT_CHUNK, GSTIM_HDR_WORDS);
+                out.resize((out.size() / chunk_words + 1) * (size_t)chunk_words, 0);
+            }
+            size_t hb = out.size();
+            put_header(GOP_QMAP, GSTIM_HDR_WORDS + cnt);
+            out[hb + GH_N] = cnt;
+            out[hb + GH_EXTRA] = (uint32_t)base0;
+            out.insert(out.end(), lc.logical_of.begin() + (long)base0, lc.logical_of.begin() + (long)(base0 + cnt));
+        }
+    }
 
     for (Batch &b : lc.batches) {
         // ---- hazard analysis: does any item need data last touched by another thread group? ----
@@ -997,6 +1242,10 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             }
         }
 
+        if (b.op == GOP_NOISE1 || b.op == GOP_NOISE2) {
+            epoch++;  // the kernel drains a block-wide event queue and ends these batches with a barrier
+        }
+
         // ---- serialise ----
         uint32_t words = b.words();
         uint32_t pos = (uint32_t)(out.size() % chunk_words);
@@ -1013,8 +1262,7 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         out[base + GH_N] = b.n_items;
         out[base + GH_WORDS] = words;
         out[base + GH_EXTRA] = b.extra;
-        uint64_t lb;
-        memcpy(&lb, &b.lambda, 8);
+        uint64_t lb = b.lambda;
         out[base + GH_LAMBDA_LO] = (uint32_t)lb;
         out[base + GH_LAMBDA_HI] = (uint32_t)(lb >> 32);
         out[base + GH_SITE0] = b.site0;

@@ -21,7 +21,7 @@ namespace gstim {
 
 struct Batch {
     uint32_t op = 0, flags = 0, aux = 0, extra = 0;
-    double lambda = 0;
+    uint64_t lambda = 0;  // event rate per shot, fixed point (2^-56 nat)
     uint32_t site0 = 0, csite0 = 0, rec0 = 0;
     uint32_t t1 = 0, t2 = 0, t3 = 0;
     uint32_t n_items = 0;
@@ -40,7 +40,8 @@ struct LoweredCircuit {
     uint32_t num_qubits = 0;       // compacted
     uint32_t rec_ring = 0;
     uint32_t num_resources = 0;
-    std::vector<uint32_t> qubit_map;  // original index -> compact index or UINT32_MAX
+    std::vector<uint32_t> qubit_map;  // original index -> compact (logical) index or UINT32_MAX
+    std::vector<uint32_t> logical_of; // physical frame row -> logical index (size Q+1; [Q] = Q, the global clock)
     std::vector<Batch> batches;
     uint32_t max_items = 0;
     uint64_t total_items = 0;

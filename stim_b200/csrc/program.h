@@ -34,6 +34,7 @@ enum GstimOp : uint32_t {
     GOP_OBS_PAULI = 9,   // out row ^= frame component. payload per item: dst row, qubit | x<<30 | z<<31
     GOP_FEEDBACK = 10,   // frame ^= record row. payload per item: rec index, qubit | x<<30 | z<<31
     GOP_CORR = 11,       // E / ELSE_CORRELATED_ERROR: one site, payload = Pauli targets qubit | x<<30 | z<<31
+    GOP_QMAP = 12,       // not executed: payload[i] = logical index of physical frame row GH_EXTRA + i
 };
 
 // header word indices
@@ -42,10 +43,10 @@ enum GstimHdr : uint32_t {
     GH_N = 1,        // number of items
     GH_WORDS = 2,    // total words of this batch (header + payload)
     GH_EXTRA = 3,    // op specific (NOISE: clock override qubit+1 or 0; CORR: clock qubit)
-    GH_LAMBDA_LO = 4,  // lambda = -log1p(-p) as IEEE double (lo word)
+    GH_LAMBDA_LO = 4,  // lambda = -log1p(-p) per shot as u64 fixed point, unit 2^-56 nat (lo word)
     GH_LAMBDA_HI = 5,
-    GH_SITE0 = 6,    // noise-site index of item 0 (item i uses site0+i)
-    GH_CSITE0 = 7,   // collapse-site index of item 0
+    GH_SITE0 = 6,    // noise group of the batch (Philox counter word 0 of its event draws)
+    GH_CSITE0 = 7,   // measure group of the batch (Philox counter word 0 of its collapse draws)
     GH_REC0 = 8,     // absolute measurement index of item 0
     GH_T1 = 9,       // NOISE1: category thresholds on a uniform u32
     GH_T2 = 10,
@@ -75,9 +76,9 @@ enum GstimHdr : uint32_t {
 //   v = uniform u32;  v < T1 -> c0;  v < T2 -> c1;  v < T3 -> c2;  else c3.
 
 // Philox counter tags (4th counter word)
-#define GTAG_EVENT 0x45564E54u     // 'EVNT' per noise event:  ctr = (site, k_event, col0, tag)
-#define GTAG_COLLAPSE 0x434F4C4Cu  // 'COLL' per collapse:     ctr = (csite, global column, 0, tag)
-#define GTAG_CLOCK 0x434C4F4Bu     // 'CLOK' clock init:       ctr = (qubit, 0, col0, tag)
+#define GTAG_EVENT 0x45564E54u     // 'EVNT' per noise event:  ctr = (noise group, logical qubit | k_event<<16, col0, tag)
+#define GTAG_COLLAPSE 0x434F4C4Cu  // 'COLL' per collapse:     ctr = (measure group, logical qubit, global column, tag)
+#define GTAG_CLOCK 0x434C4F4Bu     // 'CLOK' clock init:       ctr = (logical qubit, 0, col0, tag)
 
 // Plan: everything the kernel needs besides the program words.
 struct GstimPlan {
