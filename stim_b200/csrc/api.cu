@@ -346,7 +346,8 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
     const uint64_t bytes_per_block = (uint64_t)std::max<uint32_t>(rows, 1) * K * 16;
     uint64_t max_blocks = std::max<uint64_t>(table_budget / bytes_per_block, (uint64_t)s->num_sms);
     max_blocks = std::min(max_blocks, total_blocks);
-    uint32_t grid_cap = (uint32_t)s->num_sms;  // one resident block per SM (shared memory bound)
+    // persistent grid: as many blocks as fit on the device at once (shared memory usually allows one per SM)
+    uint32_t grid_cap = (uint32_t)s->num_sms * (uint32_t)interp_max_blocks_per_sm(s->threads, smem);
     s->d_table.ensure(bytes_per_block * max_blocks);
     if (s->mode == GSTIM_MODE_DETECTORS) {
         s->d_rec.ensure((size_t)grid_cap * s->plan.rec_ring * K * 16);

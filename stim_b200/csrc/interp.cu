@@ -1,0 +1,766 @@
+// interp.cu — the persistent sm_100a interpreter kernel of the Pauli-frame sampler.
+//
+// One thread block owns K*128 shots. The x/z frame bits of every qubit stay resident in shared memory
+// as uint4 (128-shot) columns, the lowered program (program.h) is streamed through a two-stage
+// shared-memory ring by bulk-async (TMA 1D, cp.async.bulk + mbarrier) copies, and every batch of the
+// program is executed by all threads: item i by thread group i % slots, one lane per 128-shot column
+// (or G lanes per item splitting the columns).
+//
+// Replaces FrameSimulator<W>::do_circuit / do_gate and the per-gate row loops
+// (/root/reference/src/stim/simulators/frame_simulator.inl:166-170, 173-912), RareErrorIterator
+// (/root/reference/src/stim/util_bot/probability_util.cc:23-43) and the MeasureRecordBatch window
+// (/root/reference/src/stim/io/measure_record_batch.inl:49-104).
+//
+// Code structure: every opcode is a __noinline__ device function. A monolithic switch let the
+// compiler hoist each case's loop invariants in front of the switch, which made every batch pay a
+// few hundred instructions per warp no matter which opcode it was (profiles/r1 notes).
+#include "kernels.cuh"
+
+#define GSTIM_TABLE_QUAL __device__ const
+#include "log2_table.h"
+
+namespace gstim {
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3").
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory access through 32-bit shared-window addresses
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+
+// mbarrier / bulk-async copy helpers (PTX ISA: mbarrier, cp.async.bulk)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ uint4 xor4(uint4 a, uint4 b) {
+    return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w);
+}
+__device__ __forceinline__ uint4 and4(uint4 a, uint32_t m) {
+    return make_uint4(a.x & m, a.y & m, a.z & m, a.w & m);
+}
+__device__ __forceinline__ uint32_t bitmask(uint32_t aux, int bit) {
+    return (uint32_t)0 - ((aux >> bit) & 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-block context. Lives in shared memory so the opcode functions read what they need with broadcast
+// loads instead of carrying it in registers.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) BlockCtx {
+    uint32_t X_s, Z_s;        // shared-window byte addresses of the frame planes: plane[k][row] as uint4
+    uint32_t flag_s, clk_s;   // correlated-error flag row (K uint4); exponential clocks (u64 per row, + global)
+    uint32_t lt_s, jobq_s;    // log2 table (512 u32); event job queue (u16)
+    uint32_t jobn_s;          // two alternating queue counters
+    uint32_t pitch_b;         // bytes between consecutive columns of a plane (q_pitch * 16)
+    uint32_t K, B, G_log2, slots;
+    uint32_t k0, k1;          // Philox key
+    uint32_t col0_lo, col0_hi;  // global column index of this block's first column
+    uint32_t rec_mask, qpar;
+    uint4 *rec;               // this block's record rows
+    uint4 *out;               // this block's output columns
+    uint64_t rec_row_stride, out_row_stride;  // in uint4
+    const uint32_t *logical_of;
+    uint32_t jobn[2];         // the two queue counters
+};
+
+size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t max_items) {
+    size_t b = 0;
+    b += (size_t)2 * K * q_pitch * 16;            // X, Z
+    b += (size_t)K * 16;                          // correlated-error flag row
+    b += ((size_t)(Q + 1) * 8 + 15) / 16 * 16;    // exponential clocks (u64 fixed point)
+    b += (size_t)2 * chunk_words * 4;             // program ring
+    b += 512 * 4;                                 // log2 table
+    b += ((size_t)max_items * 2 + 15) / 16 * 16;  // event job queue
+    b += 16;                                      // mbarriers
+    b += (sizeof(BlockCtx) + 15) / 16 * 16;
+    return b;
+}
+
+// Exp(1) variate from a uniform u32 in fixed point (unit 2^-56 nat): -ln((r + 1/2) / 2^32) through a
+// 256-entry log2 table with linear interpolation (max error 2e-6 nat). Integer-only, so the oracle
+// (oracle/philox.py: exp_draw_fx) reproduces it bit for bit. lt_s: table in shared memory: base[256], diff[256].
+__device__ __forceinline__ unsigned long long exp_draw_fx(uint32_t r, uint32_t lt_s) {
+    const unsigned long long v = 2ull * r + 1ull;     // odd, < 2^33
+    const int t = 63 - __clzll((long long)v);         // floor(log2 v), 0..32
+    const uint32_t frac = (uint32_t)(v << (32 - t));  // bits below the leading one, left aligned
+    const uint32_t i = frac >> 24, f = frac & 0xFFFFFFu;
+    const unsigned long long log2m = (unsigned long long)lds32(lt_s + 4 * i) + (((unsigned long long)lds32(lt_s + 1024 + 4 * i) * f) >> 24);
+    const unsigned long long lv = ((unsigned long long)t << 32) + log2m;
+    return ((33ull << 32) - lv) * (unsigned long long)GSTIM_LN2_Q24;
+}
+
+__device__ __forceinline__ unsigned long long sat_mul(uint32_t n, unsigned long long lam) {
+    // min(n * lam, 2^63)
+    const unsigned long long lo = (unsigned long long)n * lam, hi = __umul64hi((unsigned long long)n, lam);
+    return (hi != 0 || lo >= (1ull << 63)) ? (1ull << 63) : lo;
+}
+
+__device__ __forceinline__ void flip_plane(const BlockCtx *bc, uint32_t plane_s, uint32_t row, uint32_t shot) {
+    const uint32_t a = plane_s + (shot >> 7) * bc->pitch_b + row * 16 + ((shot >> 5) & 3) * 4;
+    sts32(a, lds32(a) ^ (1u << (shot & 31)));
+}
+__device__ __forceinline__ void flip_rec(const BlockCtx *bc, uint32_t rec_index, uint32_t shot) {
+    uint32_t *w = (uint32_t *)(bc->rec + (uint64_t)(rec_index & bc->rec_mask) * bc->rec_row_stride + (shot >> 7)) + ((shot >> 5) & 3);
+    *w ^= 1u << (shot & 31);
+}
+
+// Walks the events of one noise site over the block's B shots with the exponential clock E (fixed point).
+// on_event(shot, r) is called for every event with the event's Philox draw r (r.x re-arms the clock).
+// Philox counter of the k-th event: (group, logical clock qubit | k << 16, col0 lo, TAG_EVENT ^ col0 hi).
+template <typename F>
+__device__ __forceinline__ void run_site(
+    const BlockCtx *bc, unsigned long long &E, unsigned long long lam, float inv_lam, uint32_t group, uint32_t lcq, F &&on_event) {
+    const uint32_t B = bc->B;
+    uint32_t pos = 0, kev = 0;
+    while (pos < B) {
+        const unsigned long long rem = sat_mul(B - pos, lam);
+        if (E >= rem) {
+            E -= rem;
+            break;
+        }
+        // j = floor(E / lam), clamped to the shots left: float estimate + exact fix-up
+        const uint32_t left = B - pos - 1;
+        const float est = __ull2float_rz(E) * inv_lam;
+        uint32_t j = est >= (float)left ? left : (uint32_t)est;
+        while (j > 0 && (unsigned long long)j * lam > E) {
+            j--;
+        }
+        while (j < left && (unsigned long long)(j + 1) * lam <= E) {
+            j++;
+        }
+        const uint32_t shot = pos + j;
+        const uint4 r = philox4x32_10(group, lcq | (kev << 16), bc->col0_lo, GTAG_EVENT ^ bc->col0_hi, bc->k0, bc->k1);
+        on_event(shot, r);
+        E = exp_draw_fx(r.x, bc->lt_s);
+        pos = shot + 1;
+        kev++;
+    }
+}
+
+#define SLOT_SUB                                      \
+    const uint32_t G_log2 = bc->G_log2;               \
+    const uint32_t sub = threadIdx.x & ((1u << G_log2) - 1); \
+    const uint32_t slot = threadIdx.x >> G_log2;      \
+    const uint32_t slots = bc->slots;                 \
+    const uint32_t K = bc->K;                         \
+    const uint32_t pitch_b = bc->pitch_b;             \
+    const uint32_t kstep = pitch_b << G_log2
+
+// ------------------------------------------------------------------------------------------------
+// opcodes
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void op_cliff1(const BlockCtx *bc, const uint32_t *hdr) {
+    SLOT_SUB;
+    const uint32_t aux = hdr[GH_OP] >> 16, n = hdr[GH_N];
+    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t a = bitmask(aux, 0), b = bitmask(aux, 1), cc = bitmask(aux, 2), d = bitmask(aux, 3);
+    const uint32_t zoff = bc->Z_s - bc->X_s;
+    for (uint32_t i = slot; i < n; i += slots) {
+        uint32_t ax = bc->X_s + pay[i] * 16 + sub * pitch_b;
+        for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
+            const uint4 x = lds128(ax), z = lds128(ax + zoff);
+            sts128(ax, xor4(and4(x, a), and4(z, b)));
+            sts128(ax + zoff, xor4(and4(x, cc), and4(z, d)));
+        }
+    }
+}
+
+__device__ __noinline__ void op_cx(const BlockCtx *bc, const uint32_t *hdr) {
+    // CX: z1 ^= z2 ; x2 ^= x1   (frame_simulator.inl:387-405)
+    SLOT_SUB;
+    const uint32_t n = hdr[GH_N];
+    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t zoff = bc->Z_s - bc->X_s;
+    for (uint32_t i = slot; i < n; i += slots) {
+        const uint32_t w = pay[i];
+        uint32_t a1 = bc->X_s + (w & 0xFFFF) * 16 + sub * pitch_b;
+        uint32_t a2 = bc->X_s + (w >> 16) * 16 + sub * pitch_b;
+        for (uint32_t k = sub; k < K; k += 1u << G_log2, a1 += kstep, a2 += kstep) {
+            const uint4 x1 = lds128(a1), z2 = lds128(a2 + zoff), z1 = lds128(a1 + zoff), x2 = lds128(a2);
+            sts128(a1 + zoff, xor4(z1, z2));
+            sts128(a2, xor4(x2, x1));
+        }
+    }
+}
+
+__device__ __noinline__ void op_cliff2(const BlockCtx *bc, const uint32_t *hdr) {
+    SLOT_SUB;
+    const uint32_t aux = hdr[GH_OP] >> 16, n = hdr[GH_N];
+    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t zoff = bc->Z_s - bc->X_s;
+    uint32_t m[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        m[j] = bitmask(aux, j);
+    }
+    for (uint32_t i = slot; i < n; i += slots) {
+        const uint32_t w = pay[i];
+        uint32_t a1 = bc->X_s + (w & 0xFFFF) * 16 + sub * pitch_b;
+        uint32_t a2 = bc->X_s + (w >> 16) * 16 + sub * pitch_b;
+        for (uint32_t k = sub; k < K; k += 1u << G_log2, a1 += kstep, a2 += kstep) {
+            const uint4 x1 = lds128(a1), z1 = lds128(a1 + zoff), x2 = lds128(a2), z2 = lds128(a2 + zoff);
+            sts128(a1, xor4(xor4(and4(x1, m[0]), and4(z1, m[1])), xor4(and4(x2, m[2]), and4(z2, m[3]))));
+            sts128(a1 + zoff, xor4(xor4(and4(x1, m[4]), and4(z1, m[5])), xor4(and4(x2, m[6]), and4(z2, m[7]))));
+            sts128(a2, xor4(xor4(and4(x1, m[8]), and4(z1, m[9])), xor4(and4(x2, m[10]), and4(z2, m[11]))));
+            sts128(a2 + zoff, xor4(xor4(and4(x1, m[12]), and4(z1, m[13])), xor4(and4(x2, m[14]), and4(z2, m[15]))));
+        }
+    }
+}
+
+// NOISE1 / NOISE2.
+// Pass A (item i -> thread group i % slots): advance each site's clock over the block's B shots; sites
+// whose clock runs out inside the block are pushed on a block-wide queue. Pass B (any thread): drain the
+// queue, so warps are full of event work instead of one busy lane in five. Philox draws are addressed by
+// (group, logical qubit), never by thread, so the result does not depend on who drains what.
+__device__ __noinline__ void op_noise(BlockCtx *bc, const uint32_t *hdr) {
+    const uint32_t h0 = hdr[GH_OP];
+    const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16, n = hdr[GH_N];
+    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const unsigned long long lam = ((unsigned long long)hdr[GH_LAMBDA_HI] << 32) | hdr[GH_LAMBDA_LO];
+    const unsigned long long need = sat_mul(bc->B, lam);
+    const bool two = op == GOP_NOISE2;
+    const bool table = two && (flags & GF_TABLE) != 0;
+    const bool noframe = (flags & GF_NOFRAME) != 0;
+    const uint32_t clock_override = hdr[GH_EXTRA];
+    const uint32_t *items = table ? pay + 15 : pay;
+    const uint32_t qpar = bc->qpar;
+    const uint32_t qn_s = bc->jobn_s + 4 * qpar;
+    const uint32_t clk_s = bc->clk_s, jobq_s = bc->jobq_s;
+    {
+        const uint32_t G_log2 = bc->G_log2;
+        const uint32_t sub = threadIdx.x & ((1u << G_log2) - 1), slot = threadIdx.x >> G_log2, slots = bc->slots;
+        if (sub == 0) {
+            for (uint32_t i = slot; i < n; i += slots) {
+                const uint32_t q = noframe ? clock_override - 1 : (items[i] & 0xFFFF);
+                const unsigned long long E = lds64(clk_s + 8 * q);
+                if (E >= need) {
+                    sts64(clk_s + 8 * q, E - need);
+                } else {
+                    uint32_t at;
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(qn_s) : "memory");
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(jobq_s + 2 * at), "h"((uint16_t)i) : "memory");
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t njobs = lds32(qn_s);
+    if (threadIdx.x == 0) {
+        sts32(bc->jobn_s + 4 * (qpar ^ 1), 0);  // nobody touches the other counter until the next noise batch
+        bc->qpar = qpar ^ 1;
+    }
+    if (njobs != 0) {
+        const float inv_lam = 1.0f / __ull2float_rn(lam);
+        const uint32_t group = hdr[GH_SITE0], rec0 = hdr[GH_REC0];
+        const uint32_t t1 = hdr[GH_T1], t2 = hdr[GH_T2], t3 = hdr[GH_T3];
+        const uint32_t X_s = bc->X_s, Z_s = bc->Z_s;
+        for (uint32_t jb = threadIdx.x; jb < njobs; jb += blockDim.x) {
+            uint16_t i16;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(i16) : "r"(jobq_s + 2 * jb));
+            const uint32_t i = i16;
+            const uint32_t w = items[i];
+            const uint32_t q1 = noframe ? clock_override - 1 : (w & 0xFFFF), q2 = w >> 16;
+            unsigned long long E = lds64(clk_s + 8 * q1);
+            run_site(bc, E, lam, inv_lam, group, bc->logical_of[q1], [&](uint32_t shot, uint4 r) {
+                if (!two) {
+                    const uint32_t v = r.y;
+                    const uint32_t sel = v < t1 ? 0u : v < t2 ? 2u : v < t3 ? 4u : 6u;
+                    const uint32_t cat = (aux >> sel) & 3u;
+                    if (cat & 1u) {
+                        flip_plane(bc, X_s, q1, shot);
+                    }
+                    if (cat & 2u) {
+                        flip_plane(bc, Z_s, q1, shot);
+                    }
+                    if (flags & GF_REC) {
+                        flip_rec(bc, rec0 + i, shot);
+                    }
+                } else {
+                    uint32_t pr;
+                    uint32_t f;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2
+                    if (!table) {
+                        // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
+                        f = 1u + __umulhi(r.y, 15u);
+                    } else {
+                        pr = aux;
+                        for (uint32_t j = 0; j < 15; j++) {
+                            if (r.y < pay[j]) {
+                                pr = j + 1;
+                                break;
+                            }
+                        }
+                        // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
+                        const uint32_t c1 = pr >> 2, c2 = pr & 3u;
+                        f = (((c1 + 1) >> 1) & 1u) | ((c1 >> 1) << 1) | ((((c2 + 1) >> 1) & 1u) << 2) | ((c2 >> 1) << 3);
+                    }
+                    if (f & 1u) {
+                        flip_plane(bc, X_s, q1, shot);
+                    }
+                    if (f & 2u) {
+                        flip_plane(bc, Z_s, q1, shot);
+                    }
+                    if (f & 4u) {
+                        flip_plane(bc, X_s, q2, shot);
+                    }
+                    if (f & 8u) {
+                        flip_plane(bc, Z_s, q2, shot);
+                    }
+                }
+            });
+            sts64(clk_s + 8 * q1, E);
+        }
+    }
+    __syncthreads();  // events were applied by arbitrary threads
+}
+
+__device__ __noinline__ void op_measure(const BlockCtx *bc, const uint32_t *hdr) {
+    SLOT_SUB;
+    const uint32_t aux = hdr[GH_OP] >> 16, n = hdr[GH_N];
+    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t basis = aux & 3u, kind = (aux >> 2) & 3u;
+    const uint32_t mgroup = hdr[GH_CSITE0], rec0 = hdr[GH_REC0];
+    const uint32_t zoff = bc->Z_s - bc->X_s;
+    const uint32_t k0 = bc->k0, k1 = bc->k1;
+    const uint64_t col0 = ((uint64_t)bc->col0_hi << 32) | bc->col0_lo;
+    for (uint32_t i = slot; i < n; i += slots) {
+        const uint32_t q = pay[i];
+        const uint32_t lq = bc->logical_of[q];
+        uint4 *rrow = bc->rec + (uint64_t)((rec0 + i) & bc->rec_mask) * bc->rec_row_stride;
+        uint32_t ax = bc->X_s + q * 16 + sub * pitch_b;
+        for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
+            const uint64_t col = col0 + k;
+            const uint4 rnd = philox4x32_10(mgroup, lq, (uint32_t)col, GTAG_COLLAPSE ^ (uint32_t)(col >> 32), k0, k1);
+            const uint4 zero = make_uint4(0, 0, 0, 0);
+            uint4 m, nx, nz;
+            if (basis == GB_Z) {  // frame_simulator.inl:199-208, 266-274, 306-317
+                const uint4 x = lds128(ax);
+                m = x;
+                nx = kind == GK_M ? x : zero;
+                nz = rnd;
+            } else if (basis == GB_X) {  // :173-182, 211-219, 277-288
+                const uint4 z = lds128(ax + zoff);
+                m = z;
+                nz = kind == GK_M ? z : zero;
+                nx = rnd;
+            } else {  // Y basis :185-196, 255-263, 291-303
+                m = xor4(lds128(ax), lds128(ax + zoff));
+                nz = rnd;
+                nx = kind == GK_M ? xor4(m, rnd) : rnd;
+            }
+            sts128(ax, nx);
+            sts128(ax + zoff, nz);
+            if (kind != GK_R) {
+                rrow[k] = m;
+            }
+        }
+    }
+}
+
+__device__ __noinline__ void op_reczero(const BlockCtx *bc, const uint32_t *hdr) {
+    SLOT_SUB;
+    (void)pitch_b;
+    (void)kstep;
+    const uint32_t n = hdr[GH_N], rec0 = hdr[GH_REC0];
+    for (uint32_t i = slot; i < n; i += slots) {
+        uint4 *rrow = bc->rec + (uint64_t)((rec0 + i) & bc->rec_mask) * bc->rec_row_stride;
+        for (uint32_t k = sub; k < K; k += 1u << G_log2) {
+            rrow[k] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+__device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr) {
+    SLOT_SUB;
+    (void)pitch_b;
+    (void)kstep;
+    const uint32_t flags = (hdr[GH_OP] >> 8) & 0xFF, n = hdr[GH_N];
+    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t *dst = pay, *off = pay + n, *idx = pay + 2 * n + 1;
+    const uint4 *rec = bc->rec;
+    const uint64_t rrs = bc->rec_row_stride;
+    for (uint32_t i = slot; i < n; i += slots) {
+        const uint32_t b0 = off[i], b1 = off[i + 1];
+        uint4 *orow = bc->out + (uint64_t)dst[i] * bc->out_row_stride;
+        for (uint32_t k = sub; k < K; k += 1u << G_log2) {
+            uint4 acc = make_uint4(0, 0, 0, 0);
+            for (uint32_t j = b0; j < b1; j++) {
+                acc = xor4(acc, rec[(uint64_t)idx[j] * rrs + k]);
+            }
+            if (flags & GF_ACCUM) {
+                acc = xor4(acc, orow[k]);
+            }
+            orow[k] = acc;
+        }
+    }
+}
+
+__device__ __noinline__ void op_obs_pauli(const BlockCtx *bc, const uint32_t *hdr) {
+    SLOT_SUB;
+    const uint32_t n = hdr[GH_N];
+    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t zoff = bc->Z_s - bc->X_s;
+    for (uint32_t i = slot; i < n; i += slots) {
+        const uint32_t w = pay[2 * i + 1];
+        uint4 *orow = bc->out + (uint64_t)pay[2 * i] * bc->out_row_stride;
+        uint32_t ax = bc->X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
+        for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
+            uint4 acc = orow[k];
+            if (w & (1u << 30)) {
+                acc = xor4(acc, lds128(ax));
+            }
+            if (w & (1u << 31)) {
+                acc = xor4(acc, lds128(ax + zoff));
+            }
+            orow[k] = acc;
+        }
+    }
+}
+
+__device__ __noinline__ void op_feedback(const BlockCtx *bc, const uint32_t *hdr) {
+    SLOT_SUB;
+    const uint32_t n = hdr[GH_N];
+    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t zoff = bc->Z_s - bc->X_s;
+    for (uint32_t i = slot; i < n; i += slots) {
+        const uint32_t w = pay[2 * i + 1];
+        const uint4 *rrow = bc->rec + (uint64_t)pay[2 * i] * bc->rec_row_stride;
+        uint32_t ax = bc->X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
+        for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
+            const uint4 r = rrow[k];
+            if (w & (1u << 30)) {
+                sts128(ax, xor4(lds128(ax), r));
+            }
+            if (w & (1u << 31)) {
+                sts128(ax + zoff, xor4(lds128(ax + zoff), r));
+            }
+        }
+    }
+}
+
+// E / ELSE_CORRELATED_ERROR (frame_simulator.inl:747-776): one site for the whole Pauli product, masked by
+// (and recorded in) the block's "already occurred" row. Executed by a single thread.
+__device__ __noinline__ void op_corr(const BlockCtx *bc, const uint32_t *hdr) {
+    if (threadIdx.x != 0) {
+        return;
+    }
+    const uint32_t flags = (hdr[GH_OP] >> 8) & 0xFF, n = hdr[GH_N];
+    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t flag_s = bc->flag_s;
+    if (flags & GF_RESET_FLAG) {
+        for (uint32_t k = 0; k < bc->K; k++) {
+            sts128(flag_s + 16 * k, make_uint4(0, 0, 0, 0));
+        }
+    }
+    const unsigned long long lam = ((unsigned long long)hdr[GH_LAMBDA_HI] << 32) | hdr[GH_LAMBDA_LO];
+    if (lam == 0) {
+        return;
+    }
+    const uint32_t cq = hdr[GH_EXTRA];
+    unsigned long long E = lds64(bc->clk_s + 8 * cq);
+    run_site(bc, E, lam, 1.0f / __ull2float_rn(lam), hdr[GH_SITE0], bc->logical_of[cq], [&](uint32_t shot, uint4 r) {
+        const uint32_t fa = flag_s + (shot >> 7) * 16 + ((shot >> 5) & 3) * 4;
+        const uint32_t bit = 1u << (shot & 31);
+        const uint32_t fw = lds32(fa);
+        if (!(fw & bit)) {
+            sts32(fa, fw | bit);
+            for (uint32_t j = 0; j < n; j++) {
+                const uint32_t w = pay[j];
+                if (w & (1u << 30)) {
+                    flip_plane(bc, bc->X_s, w & 0xFFFFFF, shot);
+                }
+                if (w & (1u << 31)) {
+                    flip_plane(bc, bc->Z_s, w & 0xFFFFFF, shot);
+                }
+            }
+        }
+    });
+    sts64(bc->clk_s + 8 * cq, E);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int MAX_THREADS>
+__global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const InterpParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *sp = smem_raw;
+    const uint32_t X_s = smem_u32(sp);
+    sp += (size_t)p.K * p.q_pitch * 16;
+    const uint32_t Z_s = smem_u32(sp);
+    sp += (size_t)p.K * p.q_pitch * 16;
+    const uint32_t flag_s = smem_u32(sp);
+    sp += (size_t)p.K * 16;
+    const uint32_t clk_s = smem_u32(sp);
+    sp += ((size_t)(p.Q + 1) * 8 + 15) / 16 * 16;
+    uint32_t *ring = (uint32_t *)sp;
+    sp += (size_t)2 * p.chunk_words * 4;
+    uint32_t *lt = (uint32_t *)sp;
+    sp += 512 * 4;
+    const uint32_t jobq_s = smem_u32(sp);
+    sp += ((size_t)p.max_items * 2 + 15) / 16 * 16;
+    const uint32_t mbar_s = smem_u32(sp);
+    sp += 16;
+    BlockCtx *bc = (BlockCtx *)sp;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t T = blockDim.x;
+    const uint32_t chunk_bytes = p.chunk_words * 4;
+    const bool multi = p.G_log2 != 0;
+
+    if (tid == 0) {
+        mbar_init(mbar_s, 1);
+        mbar_init(mbar_s + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        bc->jobn[0] = 0;
+        bc->jobn[1] = 0;
+        bc->X_s = X_s;
+        bc->Z_s = Z_s;
+        bc->flag_s = flag_s;
+        bc->clk_s = clk_s;
+        bc->lt_s = smem_u32(lt);
+        bc->jobq_s = jobq_s;
+        bc->jobn_s = smem_u32(&bc->jobn[0]);
+        bc->pitch_b = p.q_pitch * 16;
+        bc->K = p.K;
+        bc->B = p.K * GSTIM_COL_SHOTS;
+        bc->G_log2 = p.G_log2;
+        bc->slots = p.slots;
+        bc->k0 = p.seed_lo;
+        bc->k1 = p.seed_hi;
+        bc->rec_mask = p.rec_mask;
+        bc->qpar = 0;
+        bc->rec_row_stride = p.rec_row_stride;
+        bc->out_row_stride = p.out_row_stride;
+        bc->logical_of = p.logical_of;
+    }
+    for (uint32_t i = tid; i < 256; i += T) {
+        lt[i] = GSTIM_LOG2_BASE[i];
+        lt[256 + i] = GSTIM_LOG2_DIFF[i];
+    }
+    __syncthreads();
+    uint32_t phase0 = 0, phase1 = 0;
+
+    for (uint32_t g = blockIdx.x; g < p.n_blocks; g += gridDim.x) {
+        const uint64_t col0 = p.col0_base + (uint64_t)g * p.K;
+        if (tid == 0) {
+            bc->col0_lo = (uint32_t)col0;
+            bc->col0_hi = (uint32_t)(col0 >> 32);
+            bc->rec = p.rec + (uint64_t)g * p.rec_block_stride + (uint64_t)blockIdx.x * p.rec_cta_stride;
+            bc->out = p.out + (uint64_t)g * p.K;
+            // start streaming the program
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(mbar_s, chunk_bytes);
+            bulk_g2s(smem_u32(ring), p.prog, chunk_bytes, mbar_s);
+            if (p.n_chunks > 1) {
+                mbar_expect_tx(mbar_s + 8, chunk_bytes);
+                bulk_g2s(smem_u32(ring + p.chunk_words), p.prog + p.chunk_words, chunk_bytes, mbar_s + 8);
+            }
+        }
+        // per-qubit exponential clocks (+ the global clock at index Q)
+        for (uint32_t q = tid; q <= p.Q; q += T) {
+            const uint4 r = philox4x32_10(p.logical_of[q], 0, (uint32_t)col0, GTAG_CLOCK ^ (uint32_t)(col0 >> 32), p.seed_lo, p.seed_hi);
+            sts64(clk_s + 8 * q, exp_draw_fx(r.x, smem_u32(lt)));
+        }
+        for (uint32_t k = tid; k < p.K; k += T) {
+            sts128(flag_s + 16 * k, make_uint4(0, 0, 0, 0));
+        }
+        __syncthreads();
+
+        for (uint32_t chunk = 0;; chunk++) {
+            const uint32_t b = chunk & 1;
+            {
+                const uint32_t ph = b ? phase1 : phase0;
+                while (!mbar_try_wait(mbar_s + 8 * b, ph)) {
+                }
+                if (b) {
+                    phase1 ^= 1;
+                } else {
+                    phase0 ^= 1;
+                }
+            }
+            const uint32_t *pw = ring + (size_t)b * p.chunk_words;
+            bool end = false;
+            while (true) {
+                const uint32_t h0 = pw[GH_OP];
+                const uint32_t op = h0 & 0xFF;
+                if (op == GOP_END) {
+                    end = true;
+                    break;
+                }
+                if (op == GOP_NEXT_CHUNK) {
+                    break;
+                }
+                if (h0 & (GF_BARRIER << 8)) {
+                    __syncthreads();
+                } else if (multi) {
+                    __syncwarp();
+                }
+                switch (op) {
+                    case GOP_CLIFF1:
+                        op_cliff1(bc, pw);
+                        break;
+                    case GOP_CLIFF2:
+                        if ((h0 >> 16) == GSTIM_MAT_CX) {
+                            op_cx(bc, pw);
+                        } else {
+                            op_cliff2(bc, pw);
+                        }
+                        break;
+                    case GOP_NOISE1:
+                    case GOP_NOISE2:
+                        op_noise(bc, pw);
+                        break;
+                    case GOP_MEASURE:
+                        op_measure(bc, pw);
+                        break;
+                    case GOP_RECZERO:
+                        op_reczero(bc, pw);
+                        break;
+                    case GOP_XORROWS:
+                        op_xorrows(bc, pw);
+                        break;
+                    case GOP_OBS_PAULI:
+                        op_obs_pauli(bc, pw);
+                        break;
+                    case GOP_FEEDBACK:
+                        op_feedback(bc, pw);
+                        break;
+                    case GOP_CORR:
+                        op_corr(bc, pw);
+                        break;
+                    default:  // GOP_QMAP and unknown words are skipped
+                        break;
+                }
+                pw += pw[GH_WORDS];
+            }
+            __syncthreads();  // everyone is done reading ring[b]
+            if (end) {
+                break;
+            }
+            if (tid == 0 && chunk + 2 < p.n_chunks) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(mbar_s + 8 * b, chunk_bytes);
+                bulk_g2s(smem_u32(ring + (size_t)b * p.chunk_words), p.prog + (size_t)(chunk + 2) * p.chunk_words, chunk_bytes,
+                         mbar_s + 8 * b);
+            }
+        }
+    }
+}
+
+template <int MT>
+static cudaError_t set_attr(size_t smem) {
+    return cudaFuncSetAttribute(gstim_interp_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t interp_set_max_smem(size_t smem) {
+    cudaError_t e;
+    if ((e = set_attr<256>(smem)) != cudaSuccess) {
+        return e;
+    }
+    if ((e = set_attr<512>(smem)) != cudaSuccess) {
+        return e;
+    }
+    if ((e = set_attr<768>(smem)) != cudaSuccess) {
+        return e;
+    }
+    return set_attr<1024>(smem);
+}
+
+cudaError_t launch_interp(const InterpParams &p, uint32_t grid, uint32_t threads, size_t smem, cudaStream_t stream) {
+    // the register budget follows the block size: 255 / 128 / 80 / 64 registers per thread
+    if (threads <= 256) {
+        gstim_interp_kernel<256><<<grid, threads, smem, stream>>>(p);
+    } else if (threads <= 512) {
+        gstim_interp_kernel<512><<<grid, threads, smem, stream>>>(p);
+    } else if (threads <= 768) {
+        gstim_interp_kernel<768><<<grid, threads, smem, stream>>>(p);
+    } else {
+        gstim_interp_kernel<1024><<<grid, threads, smem, stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+int interp_max_blocks_per_sm(uint32_t threads, size_t smem) {
+    int n = 0;
+    cudaError_t e;
+    if (threads <= 256) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gstim_interp_kernel<256>, (int)threads, smem);
+    } else if (threads <= 512) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gstim_interp_kernel<512>, (int)threads, smem);
+    } else if (threads <= 768) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gstim_interp_kernel<768>, (int)threads, smem);
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gstim_interp_kernel<1024>, (int)threads, smem);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    return n < 1 ? 1 : n;
+}
+
+}  // namespace gstim

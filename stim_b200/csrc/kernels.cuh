@@ -34,6 +34,7 @@ struct InterpParams {
 size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t max_items);
 cudaError_t launch_interp(const InterpParams &p, uint32_t grid, uint32_t threads, size_t smem, cudaStream_t stream);
 cudaError_t interp_set_max_smem(size_t smem);
+int interp_max_blocks_per_sm(uint32_t threads, size_t smem);
 
 struct TransposeParams {
     const uint32_t *table;     // bit-major rows: table[row * row_words + shot_word]
