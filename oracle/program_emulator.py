@@ -156,7 +156,7 @@ class Emulator:
             site0, csite0, rec0 = int(w[pc + 6]), int(w[pc + 7]), int(w[pc + 8])
             t1, t2, t3 = int(w[pc + 9]), int(w[pc + 10]), int(w[pc + 11])
             pay = w[pc + HDR: pc + words]
-            if flags & F_BARRIER:
+            if flags & F_BARRIER or op in (OP_NOISE1, OP_NOISE2):  # noise batches are bracketed by block barriers
                 self.writer.clear()
                 self.readers.clear()
             self.batch_w, self.batch_r = set(), set()

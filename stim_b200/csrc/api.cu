@@ -125,7 +125,11 @@ struct gstim_sampler {
 
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    DevBuf d_prog, d_qmap, d_table, d_rec, d_rowmap, d_stage[2], d_counts;
+    DevBuf d_dbg, d_prog, d_qmap, d_table, d_rec, d_rowmap, d_stage[2], d_counts;
+    // noise schedule + per-CTA event scratch (interp.cu noise_prepass)
+    DevBuf d_noise_info, d_rates, d_qlist_off, d_qlist, d_segoff, d_ev_counts, d_ev_buf, d_ev_overflow;
+    uint32_t segoff_K = 0;
+    uint64_t ev_total = 0;
     PinnedBuf h_stage[2];
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
     cudaEvent_t stage_ready[2] = {nullptr, nullptr};
@@ -253,6 +257,21 @@ void configure(gstim_sampler *s) {
     s->words = serialize_program(s->lc, slots, s->chunk_words, &s->plan);
     s->d_prog.ensure(s->words.size() * 4);
     CK(cudaMemcpy(s->d_prog.p, s->words.data(), s->words.size() * 4, cudaMemcpyHostToDevice));
+    {
+        const NoiseSchedule &ns = s->lc.noise;
+        auto up = [&](DevBuf &d, const void *src, size_t bytes) {
+            d.ensure(std::max<size_t>(bytes, 16));
+            if (bytes) {
+                CK(cudaMemcpy(d.p, src, bytes, cudaMemcpyHostToDevice));
+            }
+        };
+        up(s->d_noise_info, ns.info.data(), ns.info.size() * 4);
+        up(s->d_rates, ns.rates.data(), ns.rates.size() * 8);
+        up(s->d_qlist_off, ns.qlist_off.data(), ns.qlist_off.size() * 4);
+        up(s->d_qlist, ns.qlist.data(), ns.qlist.size() * 4);
+        s->d_ev_overflow.ensure(16);
+        CK(cudaMemset(s->d_ev_overflow.p, 0, 16));
+    }
     s->d_qmap.ensure(s->lc.logical_of.size() * 4);
     CK(cudaMemcpy(s->d_qmap.p, s->lc.logical_of.data(), s->lc.logical_of.size() * 4, cudaMemcpyHostToDevice));
     CK(interp_set_max_smem(interp_smem_bytes(q_pitch, Q, K_max, s->chunk_words, s->lc.max_items)));
@@ -353,6 +372,32 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         s->d_rec.ensure((size_t)grid_cap * s->plan.rec_ring * K * 16);
     }
 
+    // event scratch: one segment per noise batch, sized mean + 12 sigma + 64 of its Poisson event count
+    const uint32_t n_noise = (uint32_t)s->lc.noise.n_sites.size();
+    if (s->segoff_K != K) {
+        std::vector<uint32_t> segoff(n_noise + 1, 0);
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n_noise; i++) {
+            const double lam = std::ldexp((double)s->lc.noise.lams[i], -56);
+            const double pr = s->lc.noise.lams[i] >= (1ull << 62) ? 1.0 : -std::expm1(-lam);
+            const double sites = (double)s->lc.noise.n_sites[i] * B;
+            const double mean = sites * pr;
+            const double cap = std::min(sites, std::ceil(mean + 12.0 * std::sqrt(mean) + 64.0));
+            segoff[i] = (uint32_t)total;
+            total += (uint64_t)cap;
+            if (total >= (1ull << 31)) {
+                throw std::invalid_argument("noise event scratch would exceed 2^31 records per block; lower the noise or the block size");
+            }
+        }
+        segoff[n_noise] = (uint32_t)total;
+        s->d_segoff.ensure(segoff.size() * 4);
+        CK(cudaMemcpy(s->d_segoff.p, segoff.data(), segoff.size() * 4, cudaMemcpyHostToDevice));
+        s->segoff_K = K;
+        s->ev_total = total;
+    }
+    s->d_ev_counts.ensure(std::max<size_t>((size_t)grid_cap * n_noise * 4, 16));
+    s->d_ev_buf.ensure(std::max<size_t>((size_t)grid_cap * s->ev_total * 4, 16));
+
     if (!s->call_start) {
         CK(cudaEventCreate(&s->call_start));
         CK(cudaEventCreate(&s->call_end));
@@ -376,6 +421,22 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         p.slots = s->slots;
         p.n_blocks = (uint32_t)nb;
         p.max_items = s->plan.max_items;
+        p.n_noise = n_noise;
+        p.n_rates = (uint32_t)s->lc.noise.rates.size();
+        p.noise_info = (const uint32_t *)s->d_noise_info.p;
+        p.rates = (const unsigned long long *)s->d_rates.p;
+        p.qlist_off = (const uint32_t *)s->d_qlist_off.p;
+        p.qlist = (const uint32_t *)s->d_qlist.p;
+        p.ev_segoff = (const uint32_t *)s->d_segoff.p;
+        p.ev_counts = (uint32_t *)s->d_ev_counts.p;
+        p.ev_buf = (uint32_t *)s->d_ev_buf.p;
+        p.ev_overflow = (uint32_t *)s->d_ev_overflow.p;
+        p.dbg_cycles = nullptr;
+        if (env_u32("GSTIM_DEBUG_CYCLES", 0)) {
+            s->d_dbg.ensure(32 * 8);
+            CK(cudaMemsetAsync(s->d_dbg.p, 0, 32 * 8, s->stream));
+            p.dbg_cycles = (unsigned long long *)s->d_dbg.p;
+        }
         p.col0_base = s->next_col + done_blocks * K;
         p.seed_lo = (uint32_t)s->seed;
         p.seed_hi = (uint32_t)(s->seed >> 32);
@@ -406,6 +467,29 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
     }
     CK(cudaEventRecord(s->call_end, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    if (env_u32("GSTIM_DEBUG_CYCLES", 0) && s->d_dbg.p) {
+        unsigned long long h[32];
+        CK(cudaMemcpy(h, s->d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost));
+        static const char *names[13] = {"END", "CHUNK", "CLIFF1", "CLIFF2", "NOISE1", "NOISE2", "MEASURE", "RECZERO", "XORROWS", "OBS_PAULI", "FEEDBACK", "CORR", "QMAP"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 13; i++) {
+            tot += h[i];
+        }
+        fprintf(stderr, "[gstim cycles, block 0, last launch] total %llu\n", tot);
+        for (int i = 0; i < 13; i++) {
+            if (h[i]) {
+                fprintf(stderr, "  %-9s %10llu cyc (%5.1f%%)  %6llu batches  %8.0f cyc/batch\n", names[i], h[i], 100.0 * h[i] / tot, h[16 + i], h[16 + i] ? (double)h[i] / h[16 + i] : 0.0);
+            }
+        }
+    }
+    {
+        uint32_t overflow = 0;
+        CK(cudaMemcpy(&overflow, s->d_ev_overflow.p, 4, cudaMemcpyDeviceToHost));
+        if (overflow) {
+            CK(cudaMemset(s->d_ev_overflow.p, 0, 16));
+            throw std::runtime_error("internal: noise event scratch overflowed (a > 12 sigma fluctuation); results of this call are invalid");
+        }
+    }
     CK(cudaEventElapsedTime(&s->last_call_ms, s->call_start, s->call_end));
     for (size_t i = 0; i + 3 <= ev; i += 3) {
         float a = 0, b = 0;

@@ -112,30 +112,38 @@ __device__ __forceinline__ uint32_t bitmask(uint32_t aux, int bit) {
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) BlockCtx {
     uint32_t X_s, Z_s;        // shared-window byte addresses of the frame planes: plane[k][row] as uint4
-    uint32_t flag_s, clk_s;   // correlated-error flag row (K uint4); exponential clocks (u64 per row, + global)
-    uint32_t lt_s, jobq_s;    // log2 table (512 u32); event job queue (u16)
-    uint32_t jobn_s;          // two alternating queue counters
+    uint32_t flag_s;          // correlated-error flag row (K uint4)
+    uint32_t lt_s;            // log2 table (512 u32)
+    uint32_t needs_s;         // per rate class: min(B * rate, 2^63) (32 u64)
     uint32_t pitch_b;         // bytes between consecutive columns of a plane (q_pitch * 16)
     uint32_t K, B, G_log2, slots;
     uint32_t k0, k1;          // Philox key
     uint32_t col0_lo, col0_hi;  // global column index of this block's first column
-    uint32_t rec_mask, qpar;
+    uint32_t rec_mask, pad0;
     uint4 *rec;               // this block's record rows
     uint4 *out;               // this block's output columns
     uint64_t rec_row_stride, out_row_stride;  // in uint4
     const uint32_t *logical_of;
-    uint32_t jobn[2];         // the two queue counters
+    const uint32_t *ev_segoff;  // event segment offsets per noise batch
+    uint32_t *ev_counts;        // this CTA's event counters
+    uint32_t *ev_buf;           // this CTA's event records
+    // noise schedule (read by the pre-pass)
+    const uint32_t *qlist_off, *qlist, *noise_info, *prog;
+    const unsigned long long *rates;
+    uint32_t *ev_overflow;
+    uint32_t Q, pad1;
 };
 
 size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t max_items) {
+    (void)Q;
+    (void)max_items;
     size_t b = 0;
-    b += (size_t)2 * K * q_pitch * 16;            // X, Z
-    b += (size_t)K * 16;                          // correlated-error flag row
-    b += ((size_t)(Q + 1) * 8 + 15) / 16 * 16;    // exponential clocks (u64 fixed point)
-    b += (size_t)2 * chunk_words * 4;             // program ring
-    b += 512 * 4;                                 // log2 table
-    b += ((size_t)max_items * 2 + 15) / 16 * 16;  // event job queue
-    b += 16;                                      // mbarriers
+    b += (size_t)2 * K * q_pitch * 16;  // X, Z
+    b += (size_t)K * 16;                // correlated-error flag row
+    b += (size_t)2 * chunk_words * 4;   // program ring
+    b += 512 * 4;                       // log2 table
+    b += 32 * 8;                        // per rate class "need"
+    b += 16;                            // mbarriers
     b += (sizeof(BlockCtx) + 15) / 16 * 16;
     return b;
 }
@@ -168,36 +176,119 @@ __device__ __forceinline__ void flip_rec(const BlockCtx *bc, uint32_t rec_index,
     *w ^= 1u << (shot & 31);
 }
 
-// Walks the events of one noise site over the block's B shots with the exponential clock E (fixed point).
-// on_event(shot, r) is called for every event with the event's Philox draw r (r.x re-arms the clock).
-// Philox counter of the k-th event: (group, logical clock qubit | k << 16, col0 lo, TAG_EVENT ^ col0 hi).
-template <typename F>
-__device__ __forceinline__ void run_site(
-    const BlockCtx *bc, unsigned long long &E, unsigned long long lam, float inv_lam, uint32_t group, uint32_t lcq, F &&on_event) {
-    const uint32_t B = bc->B;
-    uint32_t pos = 0, kev = 0;
-    while (pos < B) {
-        const unsigned long long rem = sat_mul(B - pos, lam);
-        if (E >= rem) {
-            E -= rem;
-            break;
+// ------------------------------------------------------------------------------------------------
+// Noise event pre-pass. Event positions and Pauli choices never depend on the frame, so before a shot block
+// is interpreted every noise site of the whole program is sampled up front: one thread per clock row walks
+// that row's site list (program.h "Noise schedule") with the row's exponential clock in registers and leaves
+// compact event records in this CTA's (L2-resident) scratch, one segment per noise batch. The interpreter
+// then only applies flips. Lanes run a small state machine (skip sites / emit one event) so a warp issues
+// event work for all 32 lanes instead of waiting on the one lane in five that has an event at a given site.
+//
+// Distribution == RareErrorIterator (/root/reference/src/stim/util_bot/probability_util.cc:33-43):
+// gaps are floor(Exp(1)/lambda) = Geometric(p), in exact integer arithmetic (unit 2^-56 nat).
+// Philox counter of the k-th event of a site: (noise group, logical clock row | k << 16, col0 lo, TAG_EVENT ^ col0 hi).
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void noise_prepass(const BlockCtx *bc) {
+    struct {
+        const uint32_t *qlist_off, *qlist, *noise_info, *prog, *logical_of;
+        const unsigned long long *rates;
+        uint32_t *ev_overflow;
+        uint32_t Q;
+    } p = {bc->qlist_off, bc->qlist, bc->noise_info, bc->prog, bc->logical_of, bc->rates, bc->ev_overflow, bc->Q};
+    const uint32_t B = bc->B, lt_s = bc->lt_s, needs_s = bc->needs_s;
+    const uint32_t k0 = bc->k0, k1 = bc->k1, col0_lo = bc->col0_lo, col0_hi = bc->col0_hi;
+    uint32_t *counts = bc->ev_counts;
+    uint32_t *evbuf = bc->ev_buf;
+    for (uint32_t row = threadIdx.x; row <= p.Q; row += blockDim.x) {
+        uint32_t idx = p.qlist_off[row];
+        const uint32_t end = p.qlist_off[row + 1];
+        if (idx == end) {
+            continue;
         }
-        // j = floor(E / lam), clamped to the shots left: float estimate + exact fix-up
-        const uint32_t left = B - pos - 1;
-        const float est = __ull2float_rz(E) * inv_lam;
-        uint32_t j = est >= (float)left ? left : (uint32_t)est;
-        while (j > 0 && (unsigned long long)j * lam > E) {
-            j--;
+        const uint32_t lrow = p.logical_of[row];
+        unsigned long long E;
+        {
+            const uint4 r = philox4x32_10(lrow, 0, col0_lo, GTAG_CLOCK ^ col0_hi, k0, k1);
+            E = exp_draw_fx(r.x, lt_s);
         }
-        while (j < left && (unsigned long long)(j + 1) * lam <= E) {
-            j++;
+        uint32_t pos = 0, kev = 0;
+        while (idx < end) {
+            const uint32_t entry = p.qlist[idx];
+            const uint32_t cls = entry >> 27, nbi = (entry >> 11) & 0xFFFF;
+            const uint32_t *info = p.noise_info + (size_t)nbi * GSTIM_NOISE_INFO_WORDS;
+            if (pos == 0 && cls < 31) {
+                const unsigned long long need = lds64(needs_s + 8 * cls);
+                if (E >= need) {  // no event at this site in this block
+                    E -= need;
+                    idx++;
+                    continue;
+                }
+            }
+            const unsigned long long lam = cls < 31 ? p.rates[cls] : (((unsigned long long)info[GNI_LAM_HI] << 32) | info[GNI_LAM_LO]);
+            const unsigned long long rem = sat_mul(B - pos, lam);
+            if (E >= rem) {
+                E -= rem;
+                idx++;
+                pos = 0;
+                kev = 0;
+                continue;
+            }
+            // j = floor(E / lam), clamped to the shots left: float estimate + exact fix-up
+            const uint32_t left = B - pos - 1;
+            const float est = __ull2float_rz(E) / __ull2float_rn(lam);
+            uint32_t j = est >= (float)left ? left : (uint32_t)est;
+            while (j > 0 && (unsigned long long)j * lam > E) {
+                j--;
+            }
+            while (j < left && (unsigned long long)(j + 1) * lam <= E) {
+                j++;
+            }
+            const uint32_t shot = pos + j;
+            const uint4 r = philox4x32_10(info[GNI_GROUP], lrow | (kev << 16), col0_lo, GTAG_EVENT ^ col0_hi, k0, k1);
+            // which Paulis flip
+            const uint32_t h0 = info[GNI_H0];
+            const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
+            uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
+            if (op == GOP_NOISE1) {
+                const uint32_t v = r.y;
+                const uint32_t sel = v < info[GNI_T1] ? 0u : v < info[GNI_T2] ? 2u : v < info[GNI_T3] ? 4u : 6u;
+                f = (aux >> sel) & 3u;
+                if (flags & GF_REC) {
+                    f |= 16u;
+                }
+            } else if (op == GOP_NOISE2) {
+                if (!(flags & GF_TABLE)) {
+                    f = 1u + __umulhi(r.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
+                } else {
+                    const uint32_t *tab = p.prog + info[GNI_TABLE_OFF];
+                    uint32_t pr = aux;
+                    for (uint32_t t = 0; t < 15; t++) {
+                        if (r.y < tab[t]) {
+                            pr = t + 1;
+                            break;
+                        }
+                    }
+                    // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
+                    const uint32_t c1 = pr >> 2, c2 = pr & 3u;
+                    f = (((c1 + 1) >> 1) & 1u) | ((c1 >> 1) << 1) | ((((c2 + 1) >> 1) & 1u) << 2) | ((c2 >> 1) << 3);
+                }
+            }
+            const uint32_t seg0 = bc->ev_segoff[nbi], cap = bc->ev_segoff[nbi + 1] - seg0;
+            const uint32_t at = atomicAdd(&counts[nbi], 1u);
+            if (at < cap) {
+                evbuf[seg0 + at] = shot | ((entry & GSTIM_EV_ITEM_MASK) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
+            } else {
+                *p.ev_overflow = 1u;
+            }
+            E = exp_draw_fx(r.x, lt_s);
+            pos = shot + 1;
+            kev++;
+            if (pos >= B) {
+                idx++;
+                pos = 0;
+                kev = 0;
+            }
         }
-        const uint32_t shot = pos + j;
-        const uint4 r = philox4x32_10(group, lcq | (kev << 16), bc->col0_lo, GTAG_EVENT ^ bc->col0_hi, bc->k0, bc->k1);
-        on_event(shot, r);
-        E = exp_draw_fx(r.x, bc->lt_s);
-        pos = shot + 1;
-        kev++;
     }
 }
 
@@ -271,111 +362,51 @@ __device__ __noinline__ void op_cliff2(const BlockCtx *bc, const uint32_t *hdr) 
     }
 }
 
-// NOISE1 / NOISE2.
-// Pass A (item i -> thread group i % slots): advance each site's clock over the block's B shots; sites
-// whose clock runs out inside the block are pushed on a block-wide queue. Pass B (any thread): drain the
-// queue, so warps are full of event work instead of one busy lane in five. Philox draws are addressed by
-// (group, logical qubit), never by thread, so the result does not depend on who drains what.
-__device__ __noinline__ void op_noise(BlockCtx *bc, const uint32_t *hdr) {
+// NOISE1 / NOISE2: apply the events the pre-pass left for this batch. Any thread applies any event, so the
+// batch is bracketed by block barriers and flips use shared-memory atomics (two events of one site can hit
+// the same 32-bit word).
+__device__ __forceinline__ void atom_flip_plane(const BlockCtx *bc, uint32_t plane_s, uint32_t row, uint32_t shot) {
+    const uint32_t a = plane_s + (shot >> 7) * bc->pitch_b + row * 16 + ((shot >> 5) & 3) * 4;
+    asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(1u << (shot & 31)) : "memory");
+}
+__device__ __noinline__ void op_noise(const BlockCtx *bc, const uint32_t *hdr) {
+    __syncthreads();
     const uint32_t h0 = hdr[GH_OP];
-    const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16, n = hdr[GH_N];
+    const uint32_t flags = (h0 >> 8) & 0xFF;
     const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
-    const unsigned long long lam = ((unsigned long long)hdr[GH_LAMBDA_HI] << 32) | hdr[GH_LAMBDA_LO];
-    const unsigned long long need = sat_mul(bc->B, lam);
-    const bool two = op == GOP_NOISE2;
-    const bool table = two && (flags & GF_TABLE) != 0;
-    const bool noframe = (flags & GF_NOFRAME) != 0;
-    const uint32_t clock_override = hdr[GH_EXTRA];
-    const uint32_t *items = table ? pay + 15 : pay;
-    const uint32_t qpar = bc->qpar;
-    const uint32_t qn_s = bc->jobn_s + 4 * qpar;
-    const uint32_t clk_s = bc->clk_s, jobq_s = bc->jobq_s;
-    {
-        const uint32_t G_log2 = bc->G_log2;
-        const uint32_t sub = threadIdx.x & ((1u << G_log2) - 1), slot = threadIdx.x >> G_log2, slots = bc->slots;
-        if (sub == 0) {
-            for (uint32_t i = slot; i < n; i += slots) {
-                const uint32_t q = noframe ? clock_override - 1 : (items[i] & 0xFFFF);
-                const unsigned long long E = lds64(clk_s + 8 * q);
-                if (E >= need) {
-                    sts64(clk_s + 8 * q, E - need);
-                } else {
-                    uint32_t at;
-                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(qn_s) : "memory");
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(jobq_s + 2 * at), "h"((uint16_t)i) : "memory");
-                }
-            }
+    const uint32_t *items = ((h0 & 0xFF) == GOP_NOISE2 && (flags & GF_TABLE)) ? pay + 15 : pay;
+    const uint32_t nbi = hdr[GH_CSITE0], rec0 = hdr[GH_REC0];
+    const uint32_t seg0 = bc->ev_segoff[nbi], cap = bc->ev_segoff[nbi + 1] - seg0;
+    const uint32_t cnt = min(bc->ev_counts[nbi], cap);
+    const uint32_t *ev = bc->ev_buf + seg0;
+    const uint32_t X_s = bc->X_s, Z_s = bc->Z_s;
+    for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
+        const uint32_t rec = ev[e];
+        const uint32_t shot = rec & ((1u << GSTIM_EV_SHOT_BITS) - 1);
+        const uint32_t item = (rec >> GSTIM_EV_ITEM_SHIFT) & GSTIM_EV_ITEM_MASK;
+        const uint32_t f = rec >> GSTIM_EV_FLIP_SHIFT;
+        const uint32_t w = (flags & GF_NOFRAME) ? 0u : items[item];
+        const uint32_t q1 = w & 0xFFFF, q2 = w >> 16;
+        if (f & 1u) {
+            atom_flip_plane(bc, X_s, q1, shot);
+        }
+        if (f & 2u) {
+            atom_flip_plane(bc, Z_s, q1, shot);
+        }
+        if (f & 4u) {
+            atom_flip_plane(bc, X_s, q2, shot);
+        }
+        if (f & 8u) {
+            atom_flip_plane(bc, Z_s, q2, shot);
+        }
+        if (f & 16u) {
+            uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)((rec0 + item) & bc->rec_mask) * bc->rec_row_stride + (shot >> 7)) + ((shot >> 5) & 3);
+            atomicXor(rw, 1u << (shot & 31));
         }
     }
     __syncthreads();
-    const uint32_t njobs = lds32(qn_s);
-    if (threadIdx.x == 0) {
-        sts32(bc->jobn_s + 4 * (qpar ^ 1), 0);  // nobody touches the other counter until the next noise batch
-        bc->qpar = qpar ^ 1;
-    }
-    if (njobs != 0) {
-        const float inv_lam = 1.0f / __ull2float_rn(lam);
-        const uint32_t group = hdr[GH_SITE0], rec0 = hdr[GH_REC0];
-        const uint32_t t1 = hdr[GH_T1], t2 = hdr[GH_T2], t3 = hdr[GH_T3];
-        const uint32_t X_s = bc->X_s, Z_s = bc->Z_s;
-        for (uint32_t jb = threadIdx.x; jb < njobs; jb += blockDim.x) {
-            uint16_t i16;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(i16) : "r"(jobq_s + 2 * jb));
-            const uint32_t i = i16;
-            const uint32_t w = items[i];
-            const uint32_t q1 = noframe ? clock_override - 1 : (w & 0xFFFF), q2 = w >> 16;
-            unsigned long long E = lds64(clk_s + 8 * q1);
-            run_site(bc, E, lam, inv_lam, group, bc->logical_of[q1], [&](uint32_t shot, uint4 r) {
-                if (!two) {
-                    const uint32_t v = r.y;
-                    const uint32_t sel = v < t1 ? 0u : v < t2 ? 2u : v < t3 ? 4u : 6u;
-                    const uint32_t cat = (aux >> sel) & 3u;
-                    if (cat & 1u) {
-                        flip_plane(bc, X_s, q1, shot);
-                    }
-                    if (cat & 2u) {
-                        flip_plane(bc, Z_s, q1, shot);
-                    }
-                    if (flags & GF_REC) {
-                        flip_rec(bc, rec0 + i, shot);
-                    }
-                } else {
-                    uint32_t pr;
-                    uint32_t f;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2
-                    if (!table) {
-                        // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
-                        f = 1u + __umulhi(r.y, 15u);
-                    } else {
-                        pr = aux;
-                        for (uint32_t j = 0; j < 15; j++) {
-                            if (r.y < pay[j]) {
-                                pr = j + 1;
-                                break;
-                            }
-                        }
-                        // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
-                        const uint32_t c1 = pr >> 2, c2 = pr & 3u;
-                        f = (((c1 + 1) >> 1) & 1u) | ((c1 >> 1) << 1) | ((((c2 + 1) >> 1) & 1u) << 2) | ((c2 >> 1) << 3);
-                    }
-                    if (f & 1u) {
-                        flip_plane(bc, X_s, q1, shot);
-                    }
-                    if (f & 2u) {
-                        flip_plane(bc, Z_s, q1, shot);
-                    }
-                    if (f & 4u) {
-                        flip_plane(bc, X_s, q2, shot);
-                    }
-                    if (f & 8u) {
-                        flip_plane(bc, Z_s, q2, shot);
-                    }
-                }
-            });
-            sts64(clk_s + 8 * q1, E);
-        }
-    }
-    __syncthreads();  // events were applied by arbitrary threads
 }
+
 
 __device__ __noinline__ void op_measure(const BlockCtx *bc, const uint32_t *hdr) {
     SLOT_SUB;
@@ -502,7 +533,7 @@ __device__ __noinline__ void op_feedback(const BlockCtx *bc, const uint32_t *hdr
 }
 
 // E / ELSE_CORRELATED_ERROR (frame_simulator.inl:747-776): one site for the whole Pauli product, masked by
-// (and recorded in) the block's "already occurred" row. Executed by a single thread.
+// (and recorded in) the block's "already occurred" row. Executed by a single thread from the pre-sampled events.
 __device__ __noinline__ void op_corr(const BlockCtx *bc, const uint32_t *hdr) {
     if (threadIdx.x != 0) {
         return;
@@ -515,13 +546,12 @@ __device__ __noinline__ void op_corr(const BlockCtx *bc, const uint32_t *hdr) {
             sts128(flag_s + 16 * k, make_uint4(0, 0, 0, 0));
         }
     }
-    const unsigned long long lam = ((unsigned long long)hdr[GH_LAMBDA_HI] << 32) | hdr[GH_LAMBDA_LO];
-    if (lam == 0) {
-        return;
-    }
-    const uint32_t cq = hdr[GH_EXTRA];
-    unsigned long long E = lds64(bc->clk_s + 8 * cq);
-    run_site(bc, E, lam, 1.0f / __ull2float_rn(lam), hdr[GH_SITE0], bc->logical_of[cq], [&](uint32_t shot, uint4 r) {
+    const uint32_t nbi = hdr[GH_CSITE0];
+    const uint32_t seg0 = bc->ev_segoff[nbi], cap = bc->ev_segoff[nbi + 1] - seg0;
+    const uint32_t cnt = min(bc->ev_counts[nbi], cap);
+    const uint32_t *ev = bc->ev_buf + seg0;
+    for (uint32_t e = 0; e < cnt; e++) {
+        const uint32_t shot = ev[e] & ((1u << GSTIM_EV_SHOT_BITS) - 1);
         const uint32_t fa = flag_s + (shot >> 7) * 16 + ((shot >> 5) & 3) * 4;
         const uint32_t bit = 1u << (shot & 31);
         const uint32_t fw = lds32(fa);
@@ -537,8 +567,7 @@ __device__ __noinline__ void op_corr(const BlockCtx *bc, const uint32_t *hdr) {
                 }
             }
         }
-    });
-    sts64(bc->clk_s + 8 * cq, E);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -554,14 +583,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     sp += (size_t)p.K * p.q_pitch * 16;
     const uint32_t flag_s = smem_u32(sp);
     sp += (size_t)p.K * 16;
-    const uint32_t clk_s = smem_u32(sp);
-    sp += ((size_t)(p.Q + 1) * 8 + 15) / 16 * 16;
     uint32_t *ring = (uint32_t *)sp;
     sp += (size_t)2 * p.chunk_words * 4;
     uint32_t *lt = (uint32_t *)sp;
     sp += 512 * 4;
-    const uint32_t jobq_s = smem_u32(sp);
-    sp += ((size_t)p.max_items * 2 + 15) / 16 * 16;
+    const uint32_t needs_s = smem_u32(sp);
+    sp += 32 * 8;
     const uint32_t mbar_s = smem_u32(sp);
     sp += 16;
     BlockCtx *bc = (BlockCtx *)sp;
@@ -575,15 +602,21 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         mbar_init(mbar_s, 1);
         mbar_init(mbar_s + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        bc->jobn[0] = 0;
-        bc->jobn[1] = 0;
         bc->X_s = X_s;
         bc->Z_s = Z_s;
         bc->flag_s = flag_s;
-        bc->clk_s = clk_s;
         bc->lt_s = smem_u32(lt);
-        bc->jobq_s = jobq_s;
-        bc->jobn_s = smem_u32(&bc->jobn[0]);
+        bc->needs_s = needs_s;
+        bc->ev_segoff = p.ev_segoff;
+        bc->qlist_off = p.qlist_off;
+        bc->qlist = p.qlist;
+        bc->noise_info = p.noise_info;
+        bc->prog = p.prog;
+        bc->rates = p.rates;
+        bc->ev_overflow = p.ev_overflow;
+        bc->Q = p.Q;
+        bc->ev_counts = p.ev_counts + (size_t)blockIdx.x * p.n_noise;
+        bc->ev_buf = p.ev_buf + (size_t)blockIdx.x * p.ev_segoff[p.n_noise];
         bc->pitch_b = p.q_pitch * 16;
         bc->K = p.K;
         bc->B = p.K * GSTIM_COL_SHOTS;
@@ -592,7 +625,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         bc->k0 = p.seed_lo;
         bc->k1 = p.seed_hi;
         bc->rec_mask = p.rec_mask;
-        bc->qpar = 0;
         bc->rec_row_stride = p.rec_row_stride;
         bc->out_row_stride = p.out_row_stride;
         bc->logical_of = p.logical_of;
@@ -601,8 +633,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         lt[i] = GSTIM_LOG2_BASE[i];
         lt[256 + i] = GSTIM_LOG2_DIFF[i];
     }
+    for (uint32_t i = tid; i < p.n_rates; i += T) {
+        sts64(needs_s + 8 * i, sat_mul(p.K * GSTIM_COL_SHOTS, p.rates[i]));
+    }
     __syncthreads();
     uint32_t phase0 = 0, phase1 = 0;
+    long long dbg_t0 = clock64();
 
     for (uint32_t g = blockIdx.x; g < p.n_blocks; g += gridDim.x) {
         const uint64_t col0 = p.col0_base + (uint64_t)g * p.K;
@@ -620,14 +656,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
                 bulk_g2s(smem_u32(ring + p.chunk_words), p.prog + p.chunk_words, chunk_bytes, mbar_s + 8);
             }
         }
-        // per-qubit exponential clocks (+ the global clock at index Q)
-        for (uint32_t q = tid; q <= p.Q; q += T) {
-            const uint4 r = philox4x32_10(p.logical_of[q], 0, (uint32_t)col0, GTAG_CLOCK ^ (uint32_t)(col0 >> 32), p.seed_lo, p.seed_hi);
-            sts64(clk_s + 8 * q, exp_draw_fx(r.x, smem_u32(lt)));
-        }
         for (uint32_t k = tid; k < p.K; k += T) {
             sts128(flag_s + 16 * k, make_uint4(0, 0, 0, 0));
         }
+        {
+            uint32_t *counts = p.ev_counts + (size_t)blockIdx.x * p.n_noise;
+            for (uint32_t i = tid; i < p.n_noise; i += T) {
+                counts[i] = 0;
+            }
+        }
+        __syncthreads();
+        noise_prepass(bc);
         __syncthreads();
 
         for (uint32_t chunk = 0;; chunk++) {
@@ -644,6 +683,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
             }
             const uint32_t *pw = ring + (size_t)b * p.chunk_words;
             bool end = false;
+            if (p.dbg_cycles != nullptr && tid == 0 && blockIdx.x == 0) {
+                const long long t1 = clock64();
+                p.dbg_cycles[GOP_NEXT_CHUNK] += (unsigned long long)(t1 - dbg_t0);  // chunk hand-over + ring wait
+                dbg_t0 = t1;
+            }
             while (true) {
                 const uint32_t h0 = pw[GH_OP];
                 const uint32_t op = h0 & 0xFF;
@@ -694,6 +738,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
                         break;
                     default:  // GOP_QMAP and unknown words are skipped
                         break;
+                }
+                if (p.dbg_cycles != nullptr && tid == 0 && blockIdx.x == 0) {
+                    const long long t1 = clock64();
+                    p.dbg_cycles[op] += (unsigned long long)(t1 - dbg_t0);
+                    p.dbg_cycles[16 + op] += 1;
+                    dbg_t0 = t1;
                 }
                 pw += pw[GH_WORDS];
             }

@@ -28,6 +28,18 @@ struct InterpParams {
     uint32_t rec_mask;         // ring mask (detector mode) or 0xFFFFFFFF
     uint4 *out;                // detector/observable rows (bit-major); block g owns uint4 columns [g*K,(g+1)*K)
     uint64_t out_row_stride;   // uint4 units
+    unsigned long long *dbg_cycles;  // optional (GSTIM_DEBUG_CYCLES=1): [op] cycles and [16+op] batch counts seen by block 0
+    // noise schedule (program.h) and the per-CTA event scratch the pre-pass fills
+    uint32_t n_noise;                 // noise batches
+    uint32_t n_rates;                 // rate classes (<= 31)
+    const uint32_t *noise_info;       // n_noise * GSTIM_NOISE_INFO_WORDS
+    const unsigned long long *rates;  // n_rates fixed-point rates
+    const uint32_t *qlist_off;        // Q + 2
+    const uint32_t *qlist;
+    const uint32_t *ev_segoff;        // n_noise + 1 : event segment offsets for this launch's block size
+    uint32_t *ev_counts;              // gridDim.x * n_noise
+    uint32_t *ev_buf;                 // gridDim.x * ev_segoff[n_noise]
+    uint32_t *ev_overflow;            // set to 1 if any segment overflowed (host retries with more room)
 };
 
 // Shared memory the interpreter needs for (Q, K, chunk_words).

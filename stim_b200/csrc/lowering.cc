@@ -149,7 +149,7 @@ struct Lowerer {
                 ok = false;
             }
         }
-        if (ok && cur.words() + n_item_words + GSTIM_HDR_WORDS > max_words) {
+        if (ok && (cur.words() + n_item_words + GSTIM_HDR_WORDS > max_words || cur.n_items >= GSTIM_MAX_BATCH_ITEMS)) {
             ok = false;
         }
         if (ok) {
@@ -218,25 +218,28 @@ struct Lowerer {
         add(k, w, 2, r, 2, false, 0, false, 0, false, 0);
     }
     // Splits a target list into maximal runs without a repeated qubit (each run = one RNG group).
+    std::vector<uint32_t> run_stamp;
+    uint32_t run_epoch = 0;
     template <typename KEYS>
-    static std::vector<std::pair<size_t, size_t>> runs_of(size_t n, KEYS &&keys_of) {
+    std::vector<std::pair<size_t, size_t>> runs_of(size_t n, KEYS &&keys_of) {
         std::vector<std::pair<size_t, size_t>> runs;
-        std::vector<uint32_t> seen;
+        run_stamp.resize(Q + 1, 0);
+        run_epoch++;
         size_t start = 0;
         for (size_t i = 0; i < n; i++) {
             uint32_t ks[2];
             int nk = keys_of(i, ks);
             bool rep = false;
             for (int j = 0; j < nk; j++) {
-                rep |= std::find(seen.begin(), seen.end(), ks[j]) != seen.end();
+                rep |= run_stamp[ks[j]] == run_epoch;
             }
             if (rep) {
                 runs.push_back({start, i});
                 start = i;
-                seen.clear();
+                run_epoch++;
             }
             for (int j = 0; j < nk; j++) {
-                seen.push_back(ks[j]);
+                run_stamp[ks[j]] = run_epoch;
             }
         }
         if (start < n) {
@@ -1200,7 +1203,29 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         }
     }
 
+    // Noise schedule (consumed by the kernel's event pre-pass): per noise batch an info record, per
+    // physical clock row the ordered list of its noise sites.
+    NoiseSchedule &ns = lc.noise;
+    ns = NoiseSchedule();
+    std::vector<std::vector<uint32_t>> per_clock(lc.num_qubits + 1);
+    auto rate_class = [&](uint64_t lam) -> uint32_t {
+        for (size_t i = 0; i < ns.rates.size(); i++) {
+            if (ns.rates[i] == lam) {
+                return (uint32_t)i;
+            }
+        }
+        if (ns.rates.size() < 31) {
+            ns.rates.push_back(lam);
+            return (uint32_t)ns.rates.size() - 1;
+        }
+        return 31;  // looked up through the info record
+    };
+
     for (Batch &b : lc.batches) {
+        const bool is_noise = b.op == GOP_NOISE1 || b.op == GOP_NOISE2;
+        if (is_noise) {
+            epoch++;  // noise events are applied by arbitrary threads: the kernel brackets these batches with barriers
+        }
         // ---- hazard analysis: does any item need data last touched by another thread group? ----
         size_t n_haz = b.res_off.size() - 1;
         bool barrier = false;
@@ -1242,8 +1267,8 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             }
         }
 
-        if (b.op == GOP_NOISE1 || b.op == GOP_NOISE2) {
-            epoch++;  // the kernel drains a block-wide event queue and ends these batches with a barrier
+        if (is_noise) {
+            epoch++;
         }
 
         // ---- serialise ----
@@ -1278,6 +1303,45 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         } else {
             out.insert(out.end(), b.payload.begin(), b.payload.end());
         }
+
+        if (is_noise || b.op == GOP_CORR) {
+            const uint32_t nbi = (uint32_t)(ns.info.size() / GSTIM_NOISE_INFO_WORDS);
+            if (nbi >= 65536) {
+                throw std::invalid_argument("Circuits with more than 65536 noise batches are not supported by this build.");
+            }
+            out[base + GH_CSITE0] = nbi;
+            const bool table = b.op == GOP_NOISE2 && (b.flags & GF_TABLE);
+            const uint32_t items_off = (uint32_t)(base + GSTIM_HDR_WORDS + (table ? 15 : 0));
+            uint32_t info[GSTIM_NOISE_INFO_WORDS] = {};
+            info[GNI_H0] = out[base + GH_OP];
+            info[GNI_N] = b.op == GOP_CORR ? 1u : b.n_items;
+            info[GNI_LAM_LO] = (uint32_t)lb;
+            info[GNI_LAM_HI] = (uint32_t)(lb >> 32);
+            info[GNI_GROUP] = b.site0;
+            info[GNI_T1] = b.t1;
+            info[GNI_T2] = b.t2;
+            info[GNI_T3] = b.t3;
+            info[GNI_TABLE_OFF] = table ? (uint32_t)(base + GSTIM_HDR_WORDS) : 0;
+            ns.info.insert(ns.info.end(), info, info + GSTIM_NOISE_INFO_WORDS);
+            ns.n_sites.push_back(info[GNI_N]);
+            ns.lams.push_back(lb);
+            const uint32_t cls = rate_class(lb);
+            if (lb != 0) {
+                if (b.op == GOP_CORR) {
+                    per_clock[b.extra].push_back((cls << 27) | (nbi << 11));
+                } else {
+                    for (uint32_t i = 0; i < b.n_items; i++) {
+                        uint32_t clock = (b.flags & GF_NOFRAME) ? b.extra - 1 : (out[items_off + i] & 0xFFFF);
+                        per_clock[clock].push_back((cls << 27) | (nbi << 11) | i);
+                    }
+                }
+            }
+        }
+    }
+    ns.qlist_off.push_back(0);
+    for (auto &l : per_clock) {
+        ns.qlist.insert(ns.qlist.end(), l.begin(), l.end());
+        ns.qlist_off.push_back((uint32_t)ns.qlist.size());
     }
     put_header(GOP_END, GSTIM_HDR_WORDS);
     out.resize((out.size() + chunk_words - 1) / chunk_words * (size_t)chunk_words, 0);

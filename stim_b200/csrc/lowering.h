@@ -34,6 +34,16 @@ struct Batch {
     uint32_t words() const;
 };
 
+// Filled by serialize_program (see program.h "Noise schedule").
+struct NoiseSchedule {
+    std::vector<uint32_t> info;       // GSTIM_NOISE_INFO_WORDS per noise batch
+    std::vector<uint32_t> n_sites;    // per noise batch
+    std::vector<uint64_t> lams;       // per noise batch (fixed-point rate)
+    std::vector<uint64_t> rates;      // distinct rates (rate classes 0..30)
+    std::vector<uint32_t> qlist_off;  // Q+2 offsets into qlist, indexed by physical clock row (Q = global clock)
+    std::vector<uint32_t> qlist;
+};
+
 struct LoweredCircuit {
     CircuitStats stats;
     uint32_t mode = 0;             // 0 detectors, 1 measurements
@@ -43,6 +53,7 @@ struct LoweredCircuit {
     std::vector<uint32_t> qubit_map;  // original index -> compact (logical) index or UINT32_MAX
     std::vector<uint32_t> logical_of; // physical frame row -> logical index (size Q+1; [Q] = Q, the global clock)
     std::vector<Batch> batches;
+    NoiseSchedule noise;
     uint32_t max_items = 0;
     uint64_t total_items = 0;
     uint64_t num_sites = 0, num_csites = 0;

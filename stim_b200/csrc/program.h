@@ -80,6 +80,29 @@ enum GstimHdr : uint32_t {
 #define GTAG_COLLAPSE 0x434F4C4Cu  // 'COLL' per collapse:     ctr = (measure group, logical qubit, global column, tag)
 #define GTAG_CLOCK 0x434C4F4Bu     // 'CLOK' clock init:       ctr = (logical qubit, 0, col0, tag)
 
+// Noise schedule: one info record per noise batch (NOISE1 / NOISE2 / CORR, numbered in program order; the
+// ordinal is stored in the batch header's GH_CSITE0 word), and per physical clock row the ordered list of
+// its noise sites, entry = rate class << 27 | noise batch ordinal << 11 | item index. The kernel's event
+// pre-pass walks the lists (one thread per clock) and leaves compact event records for the interpreter:
+//   record = shot (bits 0-11) | item (12-22) | flips x1,z1,x2,z2 (23-26) | record flip (27).
+#define GSTIM_NOISE_INFO_WORDS 12u
+enum GstimNoiseInfo : uint32_t {
+    GNI_H0 = 0,         // op | flags<<8 | aux<<16 of the batch
+    GNI_N = 1,          // number of sites
+    GNI_LAM_LO = 2,
+    GNI_LAM_HI = 3,
+    GNI_GROUP = 4,      // noise group (Philox counter word 0)
+    GNI_T1 = 5,
+    GNI_T2 = 6,
+    GNI_T3 = 7,
+    GNI_TABLE_OFF = 8,  // word offset of the 15 PAULI_CHANNEL_2 thresholds in the program (0 = none)
+};
+#define GSTIM_EV_SHOT_BITS 12u
+#define GSTIM_EV_ITEM_SHIFT 12u
+#define GSTIM_EV_ITEM_MASK 0x7FFu
+#define GSTIM_EV_FLIP_SHIFT 23u
+#define GSTIM_MAX_BATCH_ITEMS 2047u
+
 // Plan: everything the kernel needs besides the program words.
 struct GstimPlan {
     uint32_t num_qubits;     // compacted qubit count Q (frame rows)
