@@ -223,12 +223,25 @@ class FrameOracle:
         self.obs = {}
         self.ngroup = 0  # noise group counter   (Philox counter word 0 of event draws)
         self.mgroup = 0  # measure group counter (Philox counter word 0 of collapse draws)
-        # exponential clocks: one per qubit + one global (index Q); DESIGN.md "RNG addressing"
-        q = np.arange(self.Q + 1, dtype=np.uint64)[:, None]
+        # exponential clocks: one per qubit + one global (index Q), re-armed from Philox whenever
+        # noise_group >> CLOCK_SEG_SHIFT changes; DESIGN.md "RNG addressing"
+        self.clk = np.zeros((self.Q + 1, self.nb), dtype=np.uint64)
+        self.clk_seg = [-1] * (self.Q + 1)
+
+    CLOCK_SEG_SHIFT = 5
+
+    def arm_clocks(self, clocks, group):
+        seg = group >> self.CLOCK_SEG_SHIFT
+        stale = [c for c in clocks if self.clk_seg[c] != seg]
+        if not stale:
+            return
+        q = np.asarray(stale, dtype=np.uint64)[:, None]
         c2 = (self.col0 & np.uint64(0xFFFFFFFF))[None, :]
         c3 = (np.uint64(px.TAG_CLOCK) ^ (self.col0 >> np.uint64(32)))[None, :]
-        r = px.philox4x32_10(q, 0, c2, c3, self.k0, self.k1)
-        self.clk = np.array([[px.exp_draw_fx(int(v)) for v in row] for row in r[0]], dtype=np.uint64).reshape(self.Q + 1, self.nb)
+        r = px.philox4x32_10(q, seg, c2, c3, self.k0, self.k1)
+        self.clk[stale, :] = np.array([[px.exp_draw_fx(int(v)) for v in row] for row in r[0]], dtype=np.uint64).reshape(len(stale), self.nb)
+        for c in stale:
+            self.clk_seg[c] = seg
 
     # -- randomness ---------------------------------------------------------------------------
     def collapse_words(self, mgroup, q):
@@ -249,6 +262,7 @@ class FrameOracle:
             return
         B = self.B
         need = min(B * lam, px.REM_SAT)
+        self.arm_clocks(clocks, group)
         E = self.clk[clocks, :]  # [n, nb] copy (uint64)
         hit = E < np.uint64(need)
         E = np.where(hit, E, E - np.uint64(min(need, (1 << 64) - 1)))

@@ -69,9 +69,8 @@ class Emulator:
         self.rec = np.zeros((n_rec, W), dtype=np.uint32)
         self.out = np.zeros((plan["num_det"] + plan["num_obs"], W), dtype=np.uint32)
         self.logical_of = read_qmap(self.w, plan)
-        q = np.asarray(self.logical_of, dtype=np.uint64)
-        r = px.philox4x32_10(q, 0, col0 & 0xFFFFFFFF, px.TAG_CLOCK ^ (col0 >> 32), self.k0, self.k1)
-        self.clk = [px.exp_draw_fx(int(v)) for v in r[0]]
+        self.clk = [0] * (self.Q + 1)       # exponential clocks, (re)armed per clock segment
+        self.clk_seg = [-1] * (self.Q + 1)
         # race detector state: resource -> (slot that wrote, set of slots that read) since the last barrier
         self.writer = {}
         self.readers = {}
@@ -108,6 +107,12 @@ class Emulator:
         arr[shot >> 5] ^= np.uint32(1 << (shot & 31))
 
     def run_site(self, clock, lam, group, on_event):
+        seg = group >> 5  # GSTIM_CLOCK_SEG_SHIFT
+        if self.clk_seg[clock] != seg:
+            r = px.philox4x32_10(self.logical_of[clock], seg, self.col0 & 0xFFFFFFFF, px.TAG_CLOCK ^ (self.col0 >> 32),
+                                 self.k0, self.k1)
+            self.clk[clock] = px.exp_draw_fx(int(r[0]))
+            self.clk_seg[clock] = seg
         E = self.clk[clock]
         pos, kev, B = 0, 0, self.B
         while pos < B:

@@ -129,6 +129,7 @@ struct gstim_sampler {
     // noise schedule + per-CTA event scratch (interp.cu noise_prepass)
     DevBuf d_noise_info, d_rates, d_qlist_off, d_qlist, d_segoff, d_ev_counts, d_ev_buf, d_ev_overflow;
     uint32_t segoff_K = 0;
+    uint32_t n_noise = 0;
     uint64_t ev_total = 0;
     PinnedBuf h_stage[2];
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
@@ -226,7 +227,12 @@ void configure(gstim_sampler *s) {
     // K_max from the shared-memory budget
     uint32_t Q = s->lc.num_qubits;
     uint32_t q_pitch = Q | 1u;
-    size_t fixed = interp_smem_bytes(q_pitch, Q, 0, s->chunk_words, s->lc.max_items);
+    uint32_t n_noise_batches = 0;
+    for (const auto &b : s->lc.batches) {
+        n_noise_batches += b.op == GOP_NOISE1 || b.op == GOP_NOISE2 || b.op == GOP_CORR;
+    }
+    s->n_noise = n_noise_batches;
+    size_t fixed = interp_smem_bytes(q_pitch, Q, 0, s->chunk_words, s->n_noise);
     size_t per_k = (size_t)2 * q_pitch * 16 + 16;
     if (fixed + per_k > s->smem_optin) {
         throw std::invalid_argument(
@@ -267,14 +273,14 @@ void configure(gstim_sampler *s) {
         };
         up(s->d_noise_info, ns.info.data(), ns.info.size() * 4);
         up(s->d_rates, ns.rates.data(), ns.rates.size() * 8);
-        up(s->d_qlist_off, ns.qlist_off.data(), ns.qlist_off.size() * 4);
-        up(s->d_qlist, ns.qlist.data(), ns.qlist.size() * 4);
+        up(s->d_qlist_off, ns.chains.data(), ns.chains.size() * 4);
+        up(s->d_qlist, ns.qlist.data(), ns.qlist.size() * 8);
         s->d_ev_overflow.ensure(16);
         CK(cudaMemset(s->d_ev_overflow.p, 0, 16));
     }
     s->d_qmap.ensure(s->lc.logical_of.size() * 4);
     CK(cudaMemcpy(s->d_qmap.p, s->lc.logical_of.data(), s->lc.logical_of.size() * 4, cudaMemcpyHostToDevice));
-    CK(interp_set_max_smem(interp_smem_bytes(q_pitch, Q, K_max, s->chunk_words, s->lc.max_items)));
+    CK(interp_set_max_smem(interp_smem_bytes(q_pitch, Q, K_max, s->chunk_words, s->n_noise)));
 }
 
 uint32_t choose_K(const gstim_sampler *s, uint64_t shots) {
@@ -356,7 +362,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
     s->last_K = K;
     const uint32_t B = K * GSTIM_COL_SHOTS;
     const uint32_t Q = s->plan.num_qubits, q_pitch = s->plan.q_pitch;
-    const size_t smem = interp_smem_bytes(q_pitch, Q, K, s->chunk_words, s->plan.max_items);
+    const size_t smem = interp_smem_bytes(q_pitch, Q, K, s->chunk_words, s->n_noise);
     const uint32_t rows = n_rows_of(s);
     const uint64_t total_blocks = (shots + B - 1) / B;
 
@@ -425,8 +431,9 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         p.n_rates = (uint32_t)s->lc.noise.rates.size();
         p.noise_info = (const uint32_t *)s->d_noise_info.p;
         p.rates = (const unsigned long long *)s->d_rates.p;
-        p.qlist_off = (const uint32_t *)s->d_qlist_off.p;
-        p.qlist = (const uint32_t *)s->d_qlist.p;
+        p.chains = (const uint32_t *)s->d_qlist_off.p;
+        p.n_chains = (uint32_t)(s->lc.noise.chains.size() / 4);
+        p.qlist = (const uint64_t *)s->d_qlist.p;
         p.ev_segoff = (const uint32_t *)s->d_segoff.p;
         p.ev_counts = (uint32_t *)s->d_ev_counts.p;
         p.ev_buf = (uint32_t *)s->d_ev_buf.p;
@@ -971,7 +978,7 @@ int gstim_get_stats(const gstim_sampler *s, gstim_stats *out) {
         out->slots = s->slots;
         out->max_columns = s->K_max;
         out->chunk_words = s->chunk_words;
-        out->smem_bytes_max = (uint32_t)interp_smem_bytes(s->plan.q_pitch, s->plan.num_qubits, s->K_max, s->chunk_words, s->plan.max_items);
+        out->smem_bytes_max = (uint32_t)interp_smem_bytes(s->plan.q_pitch, s->plan.num_qubits, s->K_max, s->chunk_words, s->n_noise);
     });
 }
 

@@ -114,7 +114,7 @@ struct __align__(16) BlockCtx {
     uint32_t X_s, Z_s;        // shared-window byte addresses of the frame planes: plane[k][row] as uint4
     uint32_t flag_s;          // correlated-error flag row (K uint4)
     uint32_t lt_s;            // log2 table (512 u32)
-    uint32_t needs_s;         // per rate class: min(B * rate, 2^63) (32 u64)
+    uint32_t needs_s;         // per rate class: min(B * rate, 2^63) (32 u64), followed by the 32 rates themselves
     uint32_t pitch_b;         // bytes between consecutive columns of a plane (q_pitch * 16)
     uint32_t K, B, G_log2, slots;
     uint32_t k0, k1;          // Philox key
@@ -128,21 +128,23 @@ struct __align__(16) BlockCtx {
     uint32_t *ev_counts;        // this CTA's event counters
     uint32_t *ev_buf;           // this CTA's event records
     // noise schedule (read by the pre-pass)
-    const uint32_t *qlist_off, *qlist, *noise_info, *prog;
-    const unsigned long long *rates;
+    const uint64_t *qlist;
+    const uint32_t *chains, *noise_info, *prog;
     uint32_t *ev_overflow;
-    uint32_t Q, pad1;
+    uint32_t n_chains, pad1;
 };
 
-size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t max_items) {
+size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t n_noise) {
     (void)Q;
-    (void)max_items;
     size_t b = 0;
     b += (size_t)2 * K * q_pitch * 16;  // X, Z
     b += (size_t)K * 16;                // correlated-error flag row
     b += (size_t)2 * chunk_words * 4;   // program ring
     b += 512 * 4;                       // log2 table
-    b += 32 * 8;                        // per rate class "need"
+    b += 64 * 8;                        // per rate class: need, rate
+    if (n_noise <= GSTIM_EV_SMEM_MAX) {
+        b += ((size_t)(2 * n_noise + 1) * 4 + 15) / 16 * 16;  // event counters + segment offsets
+    }
     b += 16;                            // mbarriers
     b += (sizeof(BlockCtx) + 15) / 16 * 16;
     return b;
@@ -189,105 +191,122 @@ __device__ __forceinline__ void flip_rec(const BlockCtx *bc, uint32_t rec_index,
 // Philox counter of the k-th event of a site: (noise group, logical clock row | k << 16, col0 lo, TAG_EVENT ^ col0 hi).
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ void noise_prepass(const BlockCtx *bc) {
-    struct {
-        const uint32_t *qlist_off, *qlist, *noise_info, *prog, *logical_of;
-        const unsigned long long *rates;
-        uint32_t *ev_overflow;
-        uint32_t Q;
-    } p = {bc->qlist_off, bc->qlist, bc->noise_info, bc->prog, bc->logical_of, bc->rates, bc->ev_overflow, bc->Q};
+    const uint64_t *qlist = bc->qlist;
+    const uint32_t *chains = bc->chains, *noise_info = bc->noise_info, *logical_of = bc->logical_of;
+    const uint32_t n_chains = bc->n_chains;
     const uint32_t B = bc->B, lt_s = bc->lt_s, needs_s = bc->needs_s;
     const uint32_t k0 = bc->k0, k1 = bc->k1, col0_lo = bc->col0_lo, col0_hi = bc->col0_hi;
     uint32_t *counts = bc->ev_counts;
+    const uint32_t *segoff = bc->ev_segoff;
     uint32_t *evbuf = bc->ev_buf;
-    for (uint32_t row = threadIdx.x; row <= p.Q; row += blockDim.x) {
-        uint32_t idx = p.qlist_off[row];
-        const uint32_t end = p.qlist_off[row + 1];
-        if (idx == end) {
-            continue;
-        }
-        const uint32_t lrow = p.logical_of[row];
-        unsigned long long E;
-        {
-            const uint4 r = philox4x32_10(lrow, 0, col0_lo, GTAG_CLOCK ^ col0_hi, k0, k1);
-            E = exp_draw_fx(r.x, lt_s);
-        }
-        uint32_t pos = 0, kev = 0;
-        while (idx < end) {
-            const uint32_t entry = p.qlist[idx];
-            const uint32_t cls = entry >> 27, nbi = (entry >> 11) & 0xFFFF;
-            const uint32_t *info = p.noise_info + (size_t)nbi * GSTIM_NOISE_INFO_WORDS;
-            if (pos == 0 && cls < 31) {
-                const unsigned long long need = lds64(needs_s + 8 * cls);
-                if (E >= need) {  // no event at this site in this block
-                    E -= need;
-                    idx++;
-                    continue;
+
+    uint32_t ci = threadIdx.x;
+    uint32_t idx = 0, end = 0, lrow = 0, pos = 0, kev = 0;
+    unsigned long long E = 0;
+    while (true) {
+        // ---- skip phase: fast-forward over sites (and chains) until this lane has an event pending, so that
+        // when the warp reconverges every live lane has event work
+        unsigned long long entry = 0, lam = 0;
+        bool pending = false;
+        while (true) {
+            if (idx >= end) {
+                if (ci >= n_chains) {
+                    break;
                 }
+                const uint4 ch = *reinterpret_cast<const uint4 *>(chains + 4 * (size_t)ci);  // row, segment, begin, len
+                ci += blockDim.x;
+                idx = ch.z;
+                end = ch.z + ch.w;
+                lrow = logical_of[ch.x];
+                const uint4 r = philox4x32_10(lrow, ch.y, col0_lo, GTAG_CLOCK ^ col0_hi, k0, k1);  // (re)arm the clock
+                E = exp_draw_fx(r.x, lt_s);
+                pos = 0;
+                kev = 0;
+                continue;
             }
-            const unsigned long long lam = cls < 31 ? p.rates[cls] : (((unsigned long long)info[GNI_LAM_HI] << 32) | info[GNI_LAM_LO]);
-            const unsigned long long rem = sat_mul(B - pos, lam);
-            if (E >= rem) {
+            entry = qlist[idx];
+            const uint32_t cls = ((uint32_t)entry >> 27) & 31u;
+            unsigned long long rem;
+            if (cls < 31) {
+                lam = lds64(needs_s + 256 + 8 * cls);
+                rem = pos == 0 ? lds64(needs_s + 8 * cls) : sat_mul(B - pos, lam);
+            } else {
+                const uint32_t *info = noise_info + (size_t)(((uint32_t)entry >> 11) & 0xFFFF) * GSTIM_NOISE_INFO_WORDS;
+                lam = ((unsigned long long)info[GNI_LAM_HI] << 32) | info[GNI_LAM_LO];
+                rem = sat_mul(B - pos, lam);
+            }
+            if (E >= rem) {  // no (further) event at this site in this block
                 E -= rem;
                 idx++;
                 pos = 0;
                 kev = 0;
                 continue;
             }
-            // j = floor(E / lam), clamped to the shots left: float estimate + exact fix-up
-            const uint32_t left = B - pos - 1;
-            const float est = __ull2float_rz(E) / __ull2float_rn(lam);
-            uint32_t j = est >= (float)left ? left : (uint32_t)est;
-            while (j > 0 && (unsigned long long)j * lam > E) {
-                j--;
+            pending = true;
+            break;
+        }
+        if (!pending) {
+            break;
+        }
+        // ---- event phase: exactly one event
+        const uint32_t nbi = ((uint32_t)entry >> 11) & 0xFFFF;
+        const uint32_t *info = noise_info + (size_t)nbi * GSTIM_NOISE_INFO_WORDS;
+        const uint4 i0 = *reinterpret_cast<const uint4 *>(info);      // h0, n, lam lo, lam hi
+        const uint4 i1 = *reinterpret_cast<const uint4 *>(info + 4);  // group, t1, t2, t3
+        // j = floor(E / lam), clamped to the shots left: float estimate + exact fix-up
+        const uint32_t left = B - pos - 1;
+        const float est = __ull2float_rz(E) / __ull2float_rn(lam);
+        uint32_t j = est >= (float)left ? left : (uint32_t)est;
+        while (j > 0 && (unsigned long long)j * lam > E) {
+            j--;
+        }
+        while (j < left && (unsigned long long)(j + 1) * lam <= E) {
+            j++;
+        }
+        const uint32_t shot = pos + j;
+        const uint4 r = philox4x32_10((uint32_t)(entry >> 32), lrow | (kev << 16), col0_lo, GTAG_EVENT ^ col0_hi, k0, k1);
+        // which Paulis flip
+        const uint32_t h0 = i0.x;
+        const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
+        uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
+        if (op == GOP_NOISE1) {
+            const uint32_t v = r.y;
+            const uint32_t sel = v < i1.y ? 0u : v < i1.z ? 2u : v < i1.w ? 4u : 6u;
+            f = (aux >> sel) & 3u;
+            if (flags & GF_REC) {
+                f |= 16u;
             }
-            while (j < left && (unsigned long long)(j + 1) * lam <= E) {
-                j++;
-            }
-            const uint32_t shot = pos + j;
-            const uint4 r = philox4x32_10(info[GNI_GROUP], lrow | (kev << 16), col0_lo, GTAG_EVENT ^ col0_hi, k0, k1);
-            // which Paulis flip
-            const uint32_t h0 = info[GNI_H0];
-            const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
-            uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
-            if (op == GOP_NOISE1) {
-                const uint32_t v = r.y;
-                const uint32_t sel = v < info[GNI_T1] ? 0u : v < info[GNI_T2] ? 2u : v < info[GNI_T3] ? 4u : 6u;
-                f = (aux >> sel) & 3u;
-                if (flags & GF_REC) {
-                    f |= 16u;
-                }
-            } else if (op == GOP_NOISE2) {
-                if (!(flags & GF_TABLE)) {
-                    f = 1u + __umulhi(r.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
-                } else {
-                    const uint32_t *tab = p.prog + info[GNI_TABLE_OFF];
-                    uint32_t pr = aux;
-                    for (uint32_t t = 0; t < 15; t++) {
-                        if (r.y < tab[t]) {
-                            pr = t + 1;
-                            break;
-                        }
-                    }
-                    // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
-                    const uint32_t c1 = pr >> 2, c2 = pr & 3u;
-                    f = (((c1 + 1) >> 1) & 1u) | ((c1 >> 1) << 1) | ((((c2 + 1) >> 1) & 1u) << 2) | ((c2 >> 1) << 3);
-                }
-            }
-            const uint32_t seg0 = bc->ev_segoff[nbi], cap = bc->ev_segoff[nbi + 1] - seg0;
-            const uint32_t at = atomicAdd(&counts[nbi], 1u);
-            if (at < cap) {
-                evbuf[seg0 + at] = shot | ((entry & GSTIM_EV_ITEM_MASK) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
+        } else if (op == GOP_NOISE2) {
+            if (!(flags & GF_TABLE)) {
+                f = 1u + __umulhi(r.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
             } else {
-                *p.ev_overflow = 1u;
+                const uint32_t *tab = bc->prog + info[GNI_TABLE_OFF];
+                uint32_t pr = aux;
+                for (uint32_t t = 0; t < 15; t++) {
+                    if (r.y < tab[t]) {
+                        pr = t + 1;
+                        break;
+                    }
+                }
+                // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
+                const uint32_t c1 = pr >> 2, c2 = pr & 3u;
+                f = (((c1 + 1) >> 1) & 1u) | ((c1 >> 1) << 1) | ((((c2 + 1) >> 1) & 1u) << 2) | ((c2 >> 1) << 3);
             }
-            E = exp_draw_fx(r.x, lt_s);
-            pos = shot + 1;
-            kev++;
-            if (pos >= B) {
-                idx++;
-                pos = 0;
-                kev = 0;
-            }
+        }
+        const uint32_t seg0 = segoff[nbi], cap = segoff[nbi + 1] - seg0;
+        const uint32_t at = atomicAdd(&counts[nbi], 1u);
+        if (at < cap) {
+            evbuf[seg0 + at] = shot | (((uint32_t)entry & GSTIM_EV_ITEM_MASK) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
+        } else {
+            *bc->ev_overflow = 1u;
+        }
+        E = exp_draw_fx(r.x, lt_s);
+        pos = shot + 1;
+        kev++;
+        if (pos >= B) {
+            idx++;
+            pos = 0;
+            kev = 0;
         }
     }
 }
@@ -588,7 +607,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     uint32_t *lt = (uint32_t *)sp;
     sp += 512 * 4;
     const uint32_t needs_s = smem_u32(sp);
-    sp += 32 * 8;
+    sp += 64 * 8;
+    uint32_t *ev_s = (uint32_t *)sp;  // [n_noise] counters, [n_noise + 1] segment offsets (when they fit)
+    const bool ev_in_smem = p.n_noise <= GSTIM_EV_SMEM_MAX;
+    if (ev_in_smem) {
+        sp += ((size_t)(2 * p.n_noise + 1) * 4 + 15) / 16 * 16;
+    }
     const uint32_t mbar_s = smem_u32(sp);
     sp += 16;
     BlockCtx *bc = (BlockCtx *)sp;
@@ -607,15 +631,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         bc->flag_s = flag_s;
         bc->lt_s = smem_u32(lt);
         bc->needs_s = needs_s;
-        bc->ev_segoff = p.ev_segoff;
-        bc->qlist_off = p.qlist_off;
+        bc->ev_segoff = ev_in_smem ? ev_s + p.n_noise : p.ev_segoff;
         bc->qlist = p.qlist;
+        bc->chains = p.chains;
+        bc->n_chains = p.n_chains;
         bc->noise_info = p.noise_info;
         bc->prog = p.prog;
-        bc->rates = p.rates;
         bc->ev_overflow = p.ev_overflow;
-        bc->Q = p.Q;
-        bc->ev_counts = p.ev_counts + (size_t)blockIdx.x * p.n_noise;
+        bc->ev_counts = ev_in_smem ? ev_s : p.ev_counts + (size_t)blockIdx.x * p.n_noise;
         bc->ev_buf = p.ev_buf + (size_t)blockIdx.x * p.ev_segoff[p.n_noise];
         bc->pitch_b = p.q_pitch * 16;
         bc->K = p.K;
@@ -635,6 +658,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     }
     for (uint32_t i = tid; i < p.n_rates; i += T) {
         sts64(needs_s + 8 * i, sat_mul(p.K * GSTIM_COL_SHOTS, p.rates[i]));
+        sts64(needs_s + 256 + 8 * i, p.rates[i]);
+    }
+    if (ev_in_smem) {
+        for (uint32_t i = tid; i <= p.n_noise; i += T) {
+            ev_s[p.n_noise + i] = p.ev_segoff[i];
+        }
     }
     __syncthreads();
     uint32_t phase0 = 0, phase1 = 0;
@@ -660,7 +689,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
             sts128(flag_s + 16 * k, make_uint4(0, 0, 0, 0));
         }
         {
-            uint32_t *counts = p.ev_counts + (size_t)blockIdx.x * p.n_noise;
+            uint32_t *counts = ev_in_smem ? ev_s : p.ev_counts + (size_t)blockIdx.x * p.n_noise;
             for (uint32_t i = tid; i < p.n_noise; i += T) {
                 counts[i] = 0;
             }

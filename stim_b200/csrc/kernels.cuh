@@ -34,8 +34,9 @@ struct InterpParams {
     uint32_t n_rates;                 // rate classes (<= 31)
     const uint32_t *noise_info;       // n_noise * GSTIM_NOISE_INFO_WORDS
     const unsigned long long *rates;  // n_rates fixed-point rates
-    const uint32_t *qlist_off;        // Q + 2
-    const uint32_t *qlist;
+    const uint64_t *qlist;            // site entries (program.h "Noise schedule")
+    const uint32_t *chains;           // 4 words per chain: row, clock segment, first entry, length
+    uint32_t n_chains;
     const uint32_t *ev_segoff;        // n_noise + 1 : event segment offsets for this launch's block size
     uint32_t *ev_counts;              // gridDim.x * n_noise
     uint32_t *ev_buf;                 // gridDim.x * ev_segoff[n_noise]
@@ -43,7 +44,7 @@ struct InterpParams {
 };
 
 // Shared memory the interpreter needs for (Q, K, chunk_words).
-size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t max_items);
+size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t n_noise);
 cudaError_t launch_interp(const InterpParams &p, uint32_t grid, uint32_t threads, size_t smem, cudaStream_t stream);
 cudaError_t interp_set_max_smem(size_t smem);
 int interp_max_blocks_per_sm(uint32_t threads, size_t smem);

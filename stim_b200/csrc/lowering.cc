@@ -1207,7 +1207,7 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
     // physical clock row the ordered list of its noise sites.
     NoiseSchedule &ns = lc.noise;
     ns = NoiseSchedule();
-    std::vector<std::vector<uint32_t>> per_clock(lc.num_qubits + 1);
+    std::vector<std::vector<uint64_t>> per_clock(lc.num_qubits + 1);
     auto rate_class = [&](uint64_t lam) -> uint32_t {
         for (size_t i = 0; i < ns.rates.size(); i++) {
             if (ns.rates[i] == lam) {
@@ -1328,20 +1328,43 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             const uint32_t cls = rate_class(lb);
             if (lb != 0) {
                 if (b.op == GOP_CORR) {
-                    per_clock[b.extra].push_back((cls << 27) | (nbi << 11));
+                    per_clock[b.extra].push_back(((uint64_t)b.site0 << 32) | (cls << 27) | (nbi << 11));
                 } else {
                     for (uint32_t i = 0; i < b.n_items; i++) {
                         uint32_t clock = (b.flags & GF_NOFRAME) ? b.extra - 1 : (out[items_off + i] & 0xFFFF);
-                        per_clock[clock].push_back((cls << 27) | (nbi << 11) | i);
+                        per_clock[clock].push_back(((uint64_t)b.site0 << 32) | (cls << 27) | (nbi << 11) | i);
                     }
                 }
             }
         }
     }
-    ns.qlist_off.push_back(0);
-    for (auto &l : per_clock) {
-        ns.qlist.insert(ns.qlist.end(), l.begin(), l.end());
-        ns.qlist_off.push_back((uint32_t)ns.qlist.size());
+    // Cut every clock row's site list into chains at clock-segment boundaries (a clock is re-armed whenever
+    // noise_group >> GSTIM_CLOCK_SEG_SHIFT changes, DESIGN.md "RNG addressing"); chains are independent, so the
+    // pre-pass deals them to threads longest-first for an even load.
+    struct Chain {
+        uint32_t row, seg, begin, len;
+    };
+    std::vector<Chain> chains;
+    for (uint32_t row = 0; row < per_clock.size(); row++) {
+        const auto &l = per_clock[row];
+        size_t i = 0;
+        while (i < l.size()) {
+            uint32_t seg = (uint32_t)(l[i] >> 32) >> GSTIM_CLOCK_SEG_SHIFT;
+            size_t j = i;
+            while (j < l.size() && ((uint32_t)(l[j] >> 32) >> GSTIM_CLOCK_SEG_SHIFT) == seg) {
+                j++;
+            }
+            chains.push_back({row, seg, (uint32_t)(ns.qlist.size()), (uint32_t)(j - i)});
+            ns.qlist.insert(ns.qlist.end(), l.begin() + (long)i, l.begin() + (long)j);
+            i = j;
+        }
+    }
+    std::stable_sort(chains.begin(), chains.end(), [](const Chain &a, const Chain &c) { return a.len > c.len; });
+    for (const Chain &c : chains) {
+        ns.chains.push_back(c.row);
+        ns.chains.push_back(c.seg);
+        ns.chains.push_back(c.begin);
+        ns.chains.push_back(c.len);
     }
     put_header(GOP_END, GSTIM_HDR_WORDS);
     out.resize((out.size() + chunk_words - 1) / chunk_words * (size_t)chunk_words, 0);

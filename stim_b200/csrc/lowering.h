@@ -40,8 +40,8 @@ struct NoiseSchedule {
     std::vector<uint32_t> n_sites;    // per noise batch
     std::vector<uint64_t> lams;       // per noise batch (fixed-point rate)
     std::vector<uint64_t> rates;      // distinct rates (rate classes 0..30)
-    std::vector<uint32_t> qlist_off;  // Q+2 offsets into qlist, indexed by physical clock row (Q = global clock)
-    std::vector<uint32_t> qlist;
+    std::vector<uint64_t> qlist;      // site entries: noise group << 32 | rate class << 27 | noise batch << 11 | item
+    std::vector<uint32_t> chains;     // 4 words per chain: physical clock row, clock segment, first entry, length (longest first)
 };
 
 struct LoweredCircuit {

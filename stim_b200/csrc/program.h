@@ -78,12 +78,13 @@ enum GstimHdr : uint32_t {
 // Philox counter tags (4th counter word)
 #define GTAG_EVENT 0x45564E54u     // 'EVNT' per noise event:  ctr = (noise group, logical qubit | k_event<<16, col0, tag)
 #define GTAG_COLLAPSE 0x434F4C4Cu  // 'COLL' per collapse:     ctr = (measure group, logical qubit, global column, tag)
-#define GTAG_CLOCK 0x434C4F4Bu     // 'CLOK' clock init:       ctr = (logical qubit, 0, col0, tag)
+#define GTAG_CLOCK 0x434C4F4Bu     // 'CLOK' clock (re)arming: ctr = (logical qubit, clock segment, col0, tag)
 
 // Noise schedule: one info record per noise batch (NOISE1 / NOISE2 / CORR, numbered in program order; the
-// ordinal is stored in the batch header's GH_CSITE0 word), and per physical clock row the ordered list of
-// its noise sites, entry = rate class << 27 | noise batch ordinal << 11 | item index. The kernel's event
-// pre-pass walks the lists (one thread per clock) and leaves compact event records for the interpreter:
+// ordinal is stored in the batch header's GH_CSITE0 word), and per (clock row, clock segment) a chain of
+// its noise sites in program order, entry = noise group << 32 | rate class << 27 | noise batch ordinal << 11
+// | item index. The kernel's event pre-pass walks the chains (dealt to threads longest first) and leaves
+// compact event records for the interpreter:
 //   record = shot (bits 0-11) | item (12-22) | flips x1,z1,x2,z2 (23-26) | record flip (27).
 #define GSTIM_NOISE_INFO_WORDS 12u
 enum GstimNoiseInfo : uint32_t {
@@ -97,11 +98,14 @@ enum GstimNoiseInfo : uint32_t {
     GNI_T3 = 7,
     GNI_TABLE_OFF = 8,  // word offset of the 15 PAULI_CHANNEL_2 thresholds in the program (0 = none)
 };
+// A qubit's exponential clock is re-armed from Philox whenever noise_group >> GSTIM_CLOCK_SEG_SHIFT changes.
+#define GSTIM_CLOCK_SEG_SHIFT 5u
 #define GSTIM_EV_SHOT_BITS 12u
 #define GSTIM_EV_ITEM_SHIFT 12u
 #define GSTIM_EV_ITEM_MASK 0x7FFu
 #define GSTIM_EV_FLIP_SHIFT 23u
 #define GSTIM_MAX_BATCH_ITEMS 2047u
+#define GSTIM_EV_SMEM_MAX 2048u  // event counters / segment offsets live in shared memory up to this many noise batches
 
 // Plan: everything the kernel needs besides the program words.
 struct GstimPlan {
