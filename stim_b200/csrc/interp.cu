@@ -131,6 +131,9 @@ struct __align__(16) BlockCtx {
     const uint64_t *qlist;
     const uint32_t *chains, *noise_info, *prog;
     uint32_t *ev_overflow;
+    const uint32_t *rounds;   // chain index boundaries of the pre-pass rounds (n_rounds + 1)
+    uint32_t n_rounds, info_smem_bytes;
+    uint32_t pre_mbar_s, pre_phase;
     uint32_t n_chains, pad1;
 };
 
@@ -145,7 +148,7 @@ size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chun
     if (n_noise <= GSTIM_EV_SMEM_MAX) {
         b += ((size_t)(2 * n_noise + 1) * 4 + 15) / 16 * 16;  // event counters + segment offsets
     }
-    b += 16;                            // mbarriers
+    b += 32;                            // mbarriers
     b += (sizeof(BlockCtx) + 15) / 16 * 16;
     return b;
 }
@@ -190,124 +193,153 @@ __device__ __forceinline__ void flip_rec(const BlockCtx *bc, uint32_t rec_index,
 // gaps are floor(Exp(1)/lambda) = Geometric(p), in exact integer arithmetic (unit 2^-56 nat).
 // Philox counter of the k-th event of a site: (noise group, logical clock row | k << 16, col0 lo, TAG_EVENT ^ col0 hi).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void noise_prepass(const BlockCtx *bc) {
-    const uint64_t *qlist = bc->qlist;
-    const uint32_t *chains = bc->chains, *noise_info = bc->noise_info, *logical_of = bc->logical_of;
-    const uint32_t n_chains = bc->n_chains;
+__device__ __noinline__ void noise_prepass(BlockCtx *bc) {
+    const uint32_t *chains = bc->chains, *logical_of = bc->logical_of, *rounds = bc->rounds;
+    const uint32_t n_rounds = bc->n_rounds;
     const uint32_t B = bc->B, lt_s = bc->lt_s, needs_s = bc->needs_s;
     const uint32_t k0 = bc->k0, k1 = bc->k1, col0_lo = bc->col0_lo, col0_hi = bc->col0_hi;
     uint32_t *counts = bc->ev_counts;
     const uint32_t *segoff = bc->ev_segoff;
     uint32_t *evbuf = bc->ev_buf;
+    const uint32_t tid = threadIdx.x;
 
-    uint32_t ci = threadIdx.x;
-    uint32_t idx = 0, end = 0, lrow = 0, pos = 0, kev = 0;
-    unsigned long long E = 0;
-    while (true) {
-        // ---- skip phase: fast-forward over sites (and chains) until this lane has an event pending, so that
-        // when the warp reconverges every live lane has event work
-        unsigned long long entry = 0, lam = 0;
-        bool pending = false;
-        while (true) {
-            if (idx >= end) {
-                if (ci >= n_chains) {
+    // The frame planes are not in use yet (the program starts by resetting every qubit), so they serve as
+    // scratch: [noise info records (when they fit)] [site entries of the current round of chains].
+    const uint32_t info_bytes = bc->info_smem_bytes;
+    const uint32_t info_s = bc->X_s, ent_s = bc->X_s + info_bytes;
+    const uint32_t *info_g = bc->noise_info;
+    for (uint32_t i = tid; i < info_bytes / 4; i += blockDim.x) {
+        sts32(info_s + 4 * i, info_g[i]);
+    }
+    const uint32_t bar = bc->pre_mbar_s;
+    uint32_t phase = bc->pre_phase;
+    __syncthreads();
+
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        const uint32_t c0 = rounds[r], c1 = rounds[r + 1];
+        const uint32_t e0 = chains[4 * (size_t)c0 + 2] & ~1u;
+        const uint32_t e1 = chains[4 * (size_t)(c1 - 1) + 2] + chains[4 * (size_t)(c1 - 1) + 3];
+        const uint32_t bytes = ((e1 - e0) * 8 + 15) & ~15u;
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(ent_s, bc->qlist + e0, bytes, bar);
+        }
+        while (!mbar_try_wait(bar, phase)) {
+        }
+        phase ^= 1;
+        if (c0 + tid < c1) {
+            const uint4 ch = *reinterpret_cast<const uint4 *>(chains + 4 * (size_t)(c0 + tid));  // row, segment, begin, len
+            uint32_t ea = ent_s + 8 * (ch.z - e0);
+            const uint32_t ea_end = ea + 8 * ch.w;
+            const uint32_t lrow = logical_of[ch.x];
+            unsigned long long E;
+            {
+                const uint4 rr = philox4x32_10(lrow, ch.y, col0_lo, GTAG_CLOCK ^ col0_hi, k0, k1);  // (re)arm the clock
+                E = exp_draw_fx(rr.x, lt_s);
+            }
+            uint32_t pos = 0, kev = 0;
+            while (true) {
+                // ---- skip phase: fast-forward over sites until this lane has an event pending, so that when the
+                // warp reconverges every live lane has event work
+                unsigned long long entry = 0, lam = 0;
+                bool pending = false;
+                while (ea < ea_end) {
+                    entry = lds64(ea);
+                    const uint32_t cls = ((uint32_t)entry >> 27) & 31u;
+                    unsigned long long rem;
+                    if (cls < 31) {
+                        lam = lds64(needs_s + 256 + 8 * cls);
+                        rem = pos == 0 ? lds64(needs_s + 8 * cls) : sat_mul(B - pos, lam);
+                    } else {
+                        const uint32_t *info = info_g + (size_t)(((uint32_t)entry >> 11) & 0xFFFF) * GSTIM_NOISE_INFO_WORDS;
+                        lam = ((unsigned long long)info[GNI_LAM_HI] << 32) | info[GNI_LAM_LO];
+                        rem = sat_mul(B - pos, lam);
+                    }
+                    if (E >= rem) {  // no (further) event at this site in this block
+                        E -= rem;
+                        ea += 8;
+                        pos = 0;
+                        kev = 0;
+                        continue;
+                    }
+                    pending = true;
                     break;
                 }
-                const uint4 ch = *reinterpret_cast<const uint4 *>(chains + 4 * (size_t)ci);  // row, segment, begin, len
-                ci += blockDim.x;
-                idx = ch.z;
-                end = ch.z + ch.w;
-                lrow = logical_of[ch.x];
-                const uint4 r = philox4x32_10(lrow, ch.y, col0_lo, GTAG_CLOCK ^ col0_hi, k0, k1);  // (re)arm the clock
-                E = exp_draw_fx(r.x, lt_s);
-                pos = 0;
-                kev = 0;
-                continue;
-            }
-            entry = qlist[idx];
-            const uint32_t cls = ((uint32_t)entry >> 27) & 31u;
-            unsigned long long rem;
-            if (cls < 31) {
-                lam = lds64(needs_s + 256 + 8 * cls);
-                rem = pos == 0 ? lds64(needs_s + 8 * cls) : sat_mul(B - pos, lam);
-            } else {
-                const uint32_t *info = noise_info + (size_t)(((uint32_t)entry >> 11) & 0xFFFF) * GSTIM_NOISE_INFO_WORDS;
-                lam = ((unsigned long long)info[GNI_LAM_HI] << 32) | info[GNI_LAM_LO];
-                rem = sat_mul(B - pos, lam);
-            }
-            if (E >= rem) {  // no (further) event at this site in this block
-                E -= rem;
-                idx++;
-                pos = 0;
-                kev = 0;
-                continue;
-            }
-            pending = true;
-            break;
-        }
-        if (!pending) {
-            break;
-        }
-        // ---- event phase: exactly one event
-        const uint32_t nbi = ((uint32_t)entry >> 11) & 0xFFFF;
-        const uint32_t *info = noise_info + (size_t)nbi * GSTIM_NOISE_INFO_WORDS;
-        const uint4 i0 = *reinterpret_cast<const uint4 *>(info);      // h0, n, lam lo, lam hi
-        const uint4 i1 = *reinterpret_cast<const uint4 *>(info + 4);  // group, t1, t2, t3
-        // j = floor(E / lam), clamped to the shots left: float estimate + exact fix-up
-        const uint32_t left = B - pos - 1;
-        const float est = __ull2float_rz(E) / __ull2float_rn(lam);
-        uint32_t j = est >= (float)left ? left : (uint32_t)est;
-        while (j > 0 && (unsigned long long)j * lam > E) {
-            j--;
-        }
-        while (j < left && (unsigned long long)(j + 1) * lam <= E) {
-            j++;
-        }
-        const uint32_t shot = pos + j;
-        const uint4 r = philox4x32_10((uint32_t)(entry >> 32), lrow | (kev << 16), col0_lo, GTAG_EVENT ^ col0_hi, k0, k1);
-        // which Paulis flip
-        const uint32_t h0 = i0.x;
-        const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
-        uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
-        if (op == GOP_NOISE1) {
-            const uint32_t v = r.y;
-            const uint32_t sel = v < i1.y ? 0u : v < i1.z ? 2u : v < i1.w ? 4u : 6u;
-            f = (aux >> sel) & 3u;
-            if (flags & GF_REC) {
-                f |= 16u;
-            }
-        } else if (op == GOP_NOISE2) {
-            if (!(flags & GF_TABLE)) {
-                f = 1u + __umulhi(r.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
-            } else {
-                const uint32_t *tab = bc->prog + info[GNI_TABLE_OFF];
-                uint32_t pr = aux;
-                for (uint32_t t = 0; t < 15; t++) {
-                    if (r.y < tab[t]) {
-                        pr = t + 1;
-                        break;
+                if (!pending) {
+                    break;
+                }
+                // ---- event phase: exactly one event
+                const uint32_t nbi = ((uint32_t)entry >> 11) & 0xFFFF;
+                uint4 i0, i1;  // (h0, n, lam lo, lam hi), (group, t1, t2, t3)
+                if (info_bytes) {
+                    i0 = lds128(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4));
+                    i1 = lds128(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4) + 16);
+                } else {
+                    i0 = *reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS);
+                    i1 = *reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + 4);
+                }
+                // j = floor(E / lam), clamped to the shots left: float estimate + exact fix-up
+                const uint32_t left = B - pos - 1;
+                const float est = __ull2float_rz(E) / __ull2float_rn(lam);
+                uint32_t j = est >= (float)left ? left : (uint32_t)est;
+                while (j > 0 && (unsigned long long)j * lam > E) {
+                    j--;
+                }
+                while (j < left && (unsigned long long)(j + 1) * lam <= E) {
+                    j++;
+                }
+                const uint32_t shot = pos + j;
+                const uint4 rr = philox4x32_10((uint32_t)(entry >> 32), lrow | (kev << 16), col0_lo, GTAG_EVENT ^ col0_hi, k0, k1);
+                // which Paulis flip
+                const uint32_t h0 = i0.x;
+                const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
+                uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
+                if (op == GOP_NOISE1) {
+                    const uint32_t v = rr.y;
+                    const uint32_t sel = v < i1.y ? 0u : v < i1.z ? 2u : v < i1.w ? 4u : 6u;
+                    f = (aux >> sel) & 3u;
+                    if (flags & GF_REC) {
+                        f |= 16u;
+                    }
+                } else if (op == GOP_NOISE2) {
+                    if (!(flags & GF_TABLE)) {
+                        f = 1u + __umulhi(rr.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
+                    } else {
+                        const uint32_t *tab = bc->prog + info_g[(size_t)nbi * GSTIM_NOISE_INFO_WORDS + GNI_TABLE_OFF];
+                        uint32_t pr = aux;
+                        for (uint32_t t = 0; t < 15; t++) {
+                            if (rr.y < tab[t]) {
+                                pr = t + 1;
+                                break;
+                            }
+                        }
+                        // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
+                        const uint32_t c1p = pr >> 2, c2p = pr & 3u;
+                        f = (((c1p + 1) >> 1) & 1u) | ((c1p >> 1) << 1) | ((((c2p + 1) >> 1) & 1u) << 2) | ((c2p >> 1) << 3);
                     }
                 }
-                // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
-                const uint32_t c1 = pr >> 2, c2 = pr & 3u;
-                f = (((c1 + 1) >> 1) & 1u) | ((c1 >> 1) << 1) | ((((c2 + 1) >> 1) & 1u) << 2) | ((c2 >> 1) << 3);
+                const uint32_t seg0 = segoff[nbi], cap = segoff[nbi + 1] - seg0;
+                const uint32_t at = atomicAdd(&counts[nbi], 1u);
+                if (at < cap) {
+                    evbuf[seg0 + at] = shot | (((uint32_t)entry & GSTIM_EV_ITEM_MASK) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
+                } else {
+                    *bc->ev_overflow = 1u;
+                }
+                E = exp_draw_fx(rr.x, lt_s);
+                pos = shot + 1;
+                kev++;
+                if (pos >= B) {
+                    ea += 8;
+                    pos = 0;
+                    kev = 0;
+                }
             }
         }
-        const uint32_t seg0 = segoff[nbi], cap = segoff[nbi + 1] - seg0;
-        const uint32_t at = atomicAdd(&counts[nbi], 1u);
-        if (at < cap) {
-            evbuf[seg0 + at] = shot | (((uint32_t)entry & GSTIM_EV_ITEM_MASK) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
-        } else {
-            *bc->ev_overflow = 1u;
-        }
-        E = exp_draw_fx(r.x, lt_s);
-        pos = shot + 1;
-        kev++;
-        if (pos >= B) {
-            idx++;
-            pos = 0;
-            kev = 0;
-        }
+        __syncthreads();  // the entry scratch is reused by the next round
+    }
+    if (tid == 0) {
+        bc->pre_phase = phase;
     }
 }
 
@@ -614,7 +646,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         sp += ((size_t)(2 * p.n_noise + 1) * 4 + 15) / 16 * 16;
     }
     const uint32_t mbar_s = smem_u32(sp);
-    sp += 16;
+    sp += 32;
     BlockCtx *bc = (BlockCtx *)sp;
 
     const uint32_t tid = threadIdx.x;
@@ -625,6 +657,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     if (tid == 0) {
         mbar_init(mbar_s, 1);
         mbar_init(mbar_s + 8, 1);
+        mbar_init(mbar_s + 16, 1);
+        bc->pre_mbar_s = mbar_s + 16;
+        bc->pre_phase = 0;
+        bc->rounds = p.rounds;
+        bc->n_rounds = p.n_rounds;
+        bc->info_smem_bytes = p.info_smem_bytes;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         bc->X_s = X_s;
         bc->Z_s = Z_s;

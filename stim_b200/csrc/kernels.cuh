@@ -37,6 +37,9 @@ struct InterpParams {
     const uint64_t *qlist;            // site entries (program.h "Noise schedule")
     const uint32_t *chains;           // 4 words per chain: row, clock segment, first entry, length
     uint32_t n_chains;
+    const uint32_t *rounds;           // n_rounds + 1 chain-index boundaries: a round's entries fit the pre-pass scratch
+    uint32_t n_rounds;
+    uint32_t info_smem_bytes;         // n_noise * 48 when the info records are staged in shared memory, else 0
     const uint32_t *ev_segoff;        // n_noise + 1 : event segment offsets for this launch's block size
     uint32_t *ev_counts;              // gridDim.x * n_noise
     uint32_t *ev_buf;                 // gridDim.x * ev_segoff[n_noise]

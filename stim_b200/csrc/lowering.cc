@@ -1360,6 +1360,19 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         }
     }
     std::stable_sort(chains.begin(), chains.end(), [](const Chain &a, const Chain &c) { return a.len > c.len; });
+    // store the entries in chain order, so a round of consecutive chains is one contiguous (bulk-copyable) range
+    {
+        std::vector<uint64_t> ordered;
+        ordered.reserve(ns.qlist.size());
+        for (Chain &c : chains) {
+            uint32_t nb = (uint32_t)ordered.size();
+            ordered.insert(ordered.end(), ns.qlist.begin() + c.begin, ns.qlist.begin() + c.begin + c.len);
+            c.begin = nb;
+        }
+        ns.qlist.swap(ordered);
+        ns.qlist.push_back(0);  // padding so 16-byte bulk copies never read past the end
+        ns.qlist.push_back(0);
+    }
     for (const Chain &c : chains) {
         ns.chains.push_back(c.row);
         ns.chains.push_back(c.seg);
