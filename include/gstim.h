@@ -85,6 +85,11 @@ int gstim_device_count(void);
  * Replaces: Circuit::compute_stats()  src/stim/circuit/circuit.cc:719-725 */
 int gstim_circuit_stats(const char *circuit_text, size_t text_len, gstim_stats *out);
 
+/* Host-only (no GPU): the noiseless reference sample of the circuit, little-endian packed into bits_out
+ * (n_bits = number of measurements). Random measurement outcomes are fixed to 0.
+ * Replaces: TableauSimulator::reference_sample_circuit  src/stim/simulators/tableau_simulator.inl:1435-1438 */
+int gstim_reference_sample(const char *circuit_text, size_t text_len, uint8_t *bits_out, size_t n_bits);
+
 /* Host-only lowering (no GPU needed): circuit text -> the uint32 instruction stream the interpreter
  * kernel executes (format: stim_b200/csrc/program.h), with barrier flags computed for `slots`
  * concurrent thread groups and cut into chunks of `chunk_words` words (0 = library default).
@@ -170,6 +175,22 @@ int gstim_sample_measurements_device(gstim_sampler *s, uint64_t shots, void *out
 int gstim_sample_detectors_to_fd(
     gstim_sampler *s, uint64_t shots, uint32_t flags, int fd, const char *format, int obs_fd, const char *obs_format);
 int gstim_sample_measurements_to_fd(gstim_sampler *s, uint64_t shots, int fd, const char *format);
+
+/* Host-only (no GPU): encode shot-major bit-packed rows (bit k of a shot at rows[shot*row_pitch + k/8] >> k%8)
+ * into any of Stim's result formats. In the "dets" format bits [0, prefix_transition) are printed with prefix1
+ * and the rest with prefix2 ('D'/'L'/'M').
+ * Replaces: write_table_data + MeasureRecordWriterFormat*  src/stim/io/measure_record_writer.h:111-166,
+ *           src/stim/io/measure_record_writer.cc:61-211 */
+int gstim_write_shots_to_fd(
+    const uint8_t *rows,
+    size_t row_pitch,
+    uint64_t shots,
+    uint64_t n_bits,
+    int fd,
+    const char *format,
+    char prefix1,
+    char prefix2,
+    uint64_t prefix_transition);
 
 /* Per-detector and per-observable flip counts over `shots` fresh shots: counts[D+L] (uint64),
  * written to HOST memory; counts_dev (optional, may be NULL) receives the same on the device so a

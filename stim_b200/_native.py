@@ -56,6 +56,7 @@ _SIGNATURES = [
     ("gstim_last_error", ctypes.c_char_p, []),
     ("gstim_device_count", ctypes.c_int, []),
     ("gstim_circuit_stats", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(GstimStats)]),
+    ("gstim_reference_sample", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, _P, ctypes.c_size_t]),
     ("gstim_lower_text", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
                                         _P, ctypes.POINTER(ctypes.c_size_t), _P]),
     ("gstim_create_from_text", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, ctypes.c_int,
@@ -73,6 +74,8 @@ _SIGNATURES = [
     ("gstim_sample_detectors_to_fd", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_char_p,
                                                     ctypes.c_int, ctypes.c_char_p]),
     ("gstim_sample_measurements_to_fd", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p]),
+    ("gstim_write_shots_to_fd", ctypes.c_int, [_P, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int,
+                                               ctypes.c_char_p, ctypes.c_char, ctypes.c_char, ctypes.c_uint64]),
     ("gstim_detector_flip_counts", ctypes.c_int, [_P, ctypes.c_uint64, _P, _P]),
     ("gstim_last_launch_count", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
     ("gstim_last_block_columns", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32)]),

@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgstim.so")
-SOURCES = ["circuit.cc", "lowering.cc", "writers.cc", "interp.cu", "kernels.cu", "api.cu"]
-HEADERS = ["circuit.h", "lowering.h", "writers.h", "kernels.cuh", "program.h", "log2_table.h", "../../include/gstim.h"]
+SOURCES = ["circuit.cc", "lowering.cc", "writers.cc", "tableau_ref.cc", "interp.cu", "kernels.cu", "api.cu"]
+HEADERS = ["circuit.h", "lowering.h", "writers.h", "tableau_ref.h", "kernels.cuh", "program.h", "log2_table.h", "../../include/gstim.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

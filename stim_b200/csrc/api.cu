@@ -23,6 +23,7 @@
 #include "circuit.h"
 #include "kernels.cuh"
 #include "lowering.h"
+#include "tableau_ref.h"
 #include "writers.h"
 
 using namespace gstim;
@@ -512,6 +513,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
             tot += h[i];
         }
         fprintf(stderr, "[gstim cycles, block 0, last launch] total %llu\n", tot);
+        fprintf(stderr, "  prepass(thread 0): bulk wait %llu, own chains %llu, round barrier wait %llu cyc; events %llu, skips %llu, rounds %llu\n", h[24], h[25], h[26], h[27], h[28], h[29]);
         for (int i = 0; i < 13; i++) {
             if (h[i]) {
                 fprintf(stderr, "  %-9s %10llu cyc (%5.1f%%)  %6llu batches  %8.0f cyc/batch\n", names[i], h[i], 100.0 * h[i] / tot, h[16 + i], h[16 + i] ? (double)h[i] / h[16 + i] : 0.0);
@@ -913,6 +915,20 @@ int gstim_circuit_stats(const char *circuit_text, size_t text_len, gstim_stats *
     });
 }
 
+int gstim_reference_sample(const char *circuit_text, size_t text_len, uint8_t *bits_out, size_t n_bits) {
+    return guarded([&] {
+        require(circuit_text != nullptr, "NULL argument.");
+        Circuit c = Circuit::from_text(std::string_view(circuit_text, text_len));
+        std::vector<uint8_t> r = reference_sample(c);
+        require(r.size() == n_bits, "n_bits must equal the circuit's number of measurements.");
+        require(bits_out != nullptr || n_bits == 0, "NULL output.");
+        memset(bits_out, 0, (n_bits + 7) / 8);
+        for (size_t k = 0; k < n_bits; k++) {
+            bits_out[k >> 3] |= (uint8_t)(r[k] << (k & 7));
+        }
+    });
+}
+
 int gstim_lower_text(
     const char *circuit_text,
     size_t text_len,
@@ -1137,6 +1153,47 @@ int gstim_sample_measurements_to_fd(gstim_sampler *s, uint64_t shots, int fd, co
         RowMaps maps = measurement_row_maps(s);
         FdFile out(fd);
         sample_to_file(s, shots, maps.main, out.f, fmt, 'M', 'M', maps.main.size(), nullptr, nullptr, Format::F01);
+    });
+}
+
+int gstim_write_shots_to_fd(
+    const uint8_t *rows,
+    size_t row_pitch,
+    uint64_t shots,
+    uint64_t n_bits,
+    int fd,
+    const char *format,
+    char prefix1,
+    char prefix2,
+    uint64_t prefix_transition) {
+    return guarded([&] {
+        require(rows != nullptr || shots == 0 || n_bits == 0, "NULL rows.");
+        Format fmt = parse_format(format);
+        FdFile out(fd);
+        if (fmt == Format::PTB64) {
+            // shot-major packed rows -> bit-major 32-bit rows, then the ptb64 writer
+            if (shots % 64 != 0) {
+                throw std::invalid_argument("shots must be a multiple of 64 to use ptb64 format.");
+            }
+            const size_t row_words = shots / 32;
+            std::vector<uint32_t> table((size_t)n_bits * row_words, 0), map(n_bits);
+            for (uint64_t sh = 0; sh < shots; sh++) {
+                for (uint64_t b = 0; b < n_bits; b++) {
+                    if ((rows[sh * row_pitch + (b >> 3)] >> (b & 7)) & 1) {
+                        table[b * row_words + (sh >> 5)] |= 1u << (sh & 31);
+                    }
+                }
+            }
+            for (uint64_t b = 0; b < n_bits; b++) {
+                map[b] = (uint32_t)b;
+            }
+            write_ptb64(out.f, table.data(), row_words, map.data(), n_bits, shots);
+        } else {
+            write_shots(out.f, rows, row_pitch, shots, n_bits, fmt, prefix1, prefix2, prefix_transition);
+        }
+        if (fflush(out.f) != 0) {
+            throw IoError("Failed to flush result data.");
+        }
     });
 }
 

@@ -135,6 +135,7 @@ struct __align__(16) BlockCtx {
     uint32_t n_rounds, info_smem_bytes;
     uint32_t pre_mbar_s, pre_phase;
     uint32_t n_chains, pad1;
+    unsigned long long *dbg;  // optional cycle counters (block 0 only)
 };
 
 size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t n_noise) {
@@ -215,6 +216,9 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
     uint32_t phase = bc->pre_phase;
     __syncthreads();
 
+    unsigned long long *dbg = tid == 0 ? bc->dbg : nullptr;
+    long long tA = clock64();
+    unsigned long long n_ev = 0, n_skip = 0;
     for (uint32_t r = 0; r < n_rounds; r++) {
         const uint32_t c0 = rounds[r], c1 = rounds[r + 1];
         const uint32_t e0 = chains[4 * (size_t)c0 + 2] & ~1u;
@@ -228,6 +232,11 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
         while (!mbar_try_wait(bar, phase)) {
         }
         phase ^= 1;
+        if (dbg) {
+            long long t = clock64();
+            dbg[24] += (unsigned long long)(t - tA);  // bulk-copy wait
+            tA = t;
+        }
         if (c0 + tid < c1) {
             const uint4 ch = *reinterpret_cast<const uint4 *>(chains + 4 * (size_t)(c0 + tid));  // row, segment, begin, len
             uint32_t ea = ent_s + 8 * (ch.z - e0);
@@ -257,6 +266,7 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
                         rem = sat_mul(B - pos, lam);
                     }
                     if (E >= rem) {  // no (further) event at this site in this block
+                        n_skip++;
                         E -= rem;
                         ea += 8;
                         pos = 0;
@@ -326,6 +336,7 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
                 } else {
                     *bc->ev_overflow = 1u;
                 }
+                n_ev++;
                 E = exp_draw_fx(rr.x, lt_s);
                 pos = shot + 1;
                 kev++;
@@ -336,7 +347,22 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
                 }
             }
         }
+        if (dbg) {
+            long long t = clock64();
+            dbg[25] += (unsigned long long)(t - tA);  // own chain
+            tA = t;
+        }
         __syncthreads();  // the entry scratch is reused by the next round
+        if (dbg) {
+            long long t = clock64();
+            dbg[26] += (unsigned long long)(t - tA);  // waiting for the slowest chain of the round
+            tA = t;
+        }
+    }
+    if (dbg) {
+        dbg[27] += n_ev;
+        dbg[28] += n_skip;
+        dbg[29] += n_rounds;
     }
     if (tid == 0) {
         bc->pre_phase = phase;
@@ -659,6 +685,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         mbar_init(mbar_s + 8, 1);
         mbar_init(mbar_s + 16, 1);
         bc->pre_mbar_s = mbar_s + 16;
+        bc->dbg = blockIdx.x == 0 ? p.dbg_cycles : nullptr;
         bc->pre_phase = 0;
         bc->rounds = p.rounds;
         bc->n_rounds = p.n_rounds;

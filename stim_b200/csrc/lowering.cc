@@ -1193,7 +1193,7 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             uint32_t pos = (uint32_t)(out.size() % chunk_words);
             if (pos + GSTIM_HDR_WORDS + cnt + GSTIM_HDR_WORDS > chunk_words) {
                 put_header(GOP_NEXT_CHUNK, GSTIM_HDR_WORDS);
-                out.resize((out.size() / chunk_words + 1) * (size_t)chunk_words, 0);
+                out.resize((out.size() + chunk_words - 1) / chunk_words * (size_t)chunk_words, 0);
             }
             size_t hb = out.size();
             put_header(GOP_QMAP, GSTIM_HDR_WORDS + cnt);
@@ -1279,7 +1279,7 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         }
         if (pos + words + GSTIM_HDR_WORDS > chunk_words) {
             put_header(GOP_NEXT_CHUNK, GSTIM_HDR_WORDS);
-            out.resize((out.size() / chunk_words + 1) * (size_t)chunk_words, 0);
+            out.resize((out.size() + chunk_words - 1) / chunk_words * (size_t)chunk_words, 0);
         }
         size_t base = out.size();
         out.resize(base + GSTIM_HDR_WORDS, 0);

@@ -1,0 +1,550 @@
+// tableau_ref.cc — see tableau_ref.h. A from-scratch inverse-tableau stabilizer simulator.
+//
+// State |psi> = T|0..0>. Stored: for every qubit q the Pauli strings T^dag X_q T and T^dag Z_q T (bit-packed
+// rows + sign). A gate U on the state (T <- U T) replaces the rows of its qubits by products of old rows
+// (T^dag U^dag g U T); measuring Z_q is deterministic iff T^dag Z_q T has no X/Y component, in which case the
+// outcome is that row's sign; otherwise the state is collapsed by Clifford operations on the INPUT side of T
+// that fix |0..0>, with the random outcome forced to 0 like the reference's sign_bias = +1
+// (/root/reference/src/stim/simulators/tableau_simulator.inl:1435-1438, :1370).
+// Gate actions are the standard stabilizer generators of each gate (the "flow" table every Stim gate documents).
+#include "tableau_ref.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+
+#include "program.h"
+
+namespace gstim {
+namespace {
+
+// single-qubit Pauli code: bit0 = x, bit1 = z  (0 I, 1 X, 2 Z, 3 Y)
+inline int mul_phase(int a, int b) {
+    // a * b = i^e (a ^ b)
+    static const int8_t E[4][4] = {
+        {0, 0, 0, 0},
+        {0, 0, 3, 1},  // X*Z = -iY, X*Y = iZ
+        {0, 1, 0, 3},  // Z*X = iY,  Z*Y = -iX
+        {0, 3, 1, 0},  // Y*X = -iZ, Y*Z = iX
+    };
+    return E[a][b];
+}
+
+int code_of(char c) {
+    return c == 'X' ? 1 : c == 'Z' ? 2 : c == 'Y' ? 3 : 0;
+}
+
+struct Table1 {
+    uint8_t img[4], sgn[4];
+};
+struct Table2 {
+    uint8_t img[16], sgn[16];  // code = p1 | p2 << 2
+};
+
+// From the generator images "+Y", "-Z" (image of X, image of Z).
+Table1 make1(const char *fx, const char *fz) {
+    Table1 t{};
+    int px = code_of(fx[1]), pz = code_of(fz[1]);
+    int sx = fx[0] == '-', sz = fz[0] == '-';
+    t.img[0] = 0;
+    t.sgn[0] = 0;
+    t.img[1] = (uint8_t)px;
+    t.sgn[1] = (uint8_t)sx;
+    t.img[2] = (uint8_t)pz;
+    t.sgn[2] = (uint8_t)sz;
+    int e = 1 + mul_phase(px, pz) + 2 * (sx + sz);  // Y = i X Z
+    t.img[3] = (uint8_t)(px ^ pz);
+    t.sgn[3] = (uint8_t)((e >> 1) & 1);
+    return t;
+}
+
+struct P2 {
+    int a = 0, b = 0, e = 0;  // i^e * (a (x) b)
+    void mul(const P2 &o) {
+        e = (e + o.e + mul_phase(a, o.a) + mul_phase(b, o.b)) & 3;
+        a ^= o.a;
+        b ^= o.b;
+    }
+};
+
+// From the generator images of X_, Z_, _X, _Z, e.g. "+XX", "+ZI", "+IX", "+ZZ" for CX.
+Table2 make2(const char *f0, const char *f1, const char *f2, const char *f3) {
+    const char *f[4] = {f0, f1, f2, f3};
+    P2 g[4];
+    for (int i = 0; i < 4; i++) {
+        g[i].a = code_of(f[i][1]);
+        g[i].b = code_of(f[i][2]);
+        g[i].e = f[i][0] == '-' ? 2 : 0;
+    }
+    Table2 t{};
+    for (int c = 0; c < 16; c++) {
+        int p1 = c & 3, p2 = c >> 2;
+        P2 acc;
+        acc.e = (p1 == 3) + (p2 == 3);
+        if (p1 & 1) acc.mul(g[0]);
+        if (p1 & 2) acc.mul(g[1]);
+        if (p2 & 1) acc.mul(g[2]);
+        if (p2 & 2) acc.mul(g[3]);
+        // acc = i^e (a (x) b) with Hermitian single-qubit Paulis: e must be even
+        t.img[c] = (uint8_t)(acc.a | (acc.b << 2));
+        t.sgn[c] = (uint8_t)((acc.e >> 1) & 1);
+    }
+    return t;
+}
+
+struct GateDef {
+    const char *name, *inverse;
+    const char *f[4];
+};
+// Forward conjugation U g U^dag of the generators (X, Z) or (X_, Z_, _X, _Z).
+const GateDef DEFS1[] = {
+    {"I", "I", {"+X", "+Z"}},
+    {"X", "X", {"+X", "-Z"}},
+    {"Y", "Y", {"-X", "-Z"}},
+    {"Z", "Z", {"-X", "+Z"}},
+    {"H", "H", {"+Z", "+X"}},
+    {"H_XY", "H_XY", {"+Y", "-Z"}},
+    {"H_YZ", "H_YZ", {"-X", "+Y"}},
+    {"H_NXY", "H_NXY", {"-Y", "-Z"}},
+    {"H_NXZ", "H_NXZ", {"-Z", "-X"}},
+    {"H_NYZ", "H_NYZ", {"-X", "-Y"}},
+    {"C_XYZ", "C_ZYX", {"+Y", "+X"}},
+    {"C_NXYZ", "C_ZYNX", {"-Y", "-X"}},
+    {"C_XNYZ", "C_ZNYX", {"-Y", "+X"}},
+    {"C_XYNZ", "C_NZYX", {"+Y", "-X"}},
+    {"C_ZYX", "C_XYZ", {"+Z", "+Y"}},
+    {"C_ZYNX", "C_NXYZ", {"-Z", "+Y"}},
+    {"C_ZNYX", "C_XNYZ", {"+Z", "-Y"}},
+    {"C_NZYX", "C_XYNZ", {"-Z", "-Y"}},
+    {"SQRT_X", "SQRT_X_DAG", {"+X", "-Y"}},
+    {"SQRT_X_DAG", "SQRT_X", {"+X", "+Y"}},
+    {"SQRT_Y", "SQRT_Y_DAG", {"-Z", "+X"}},
+    {"SQRT_Y_DAG", "SQRT_Y", {"+Z", "-X"}},
+    {"S", "S_DAG", {"+Y", "+Z"}},
+    {"S_DAG", "S", {"-Y", "+Z"}},
+};
+const GateDef DEFS2[] = {
+    {"II", "II", {"+XI", "+ZI", "+IX", "+IZ"}},
+    {"CX", "CX", {"+XX", "+ZI", "+IX", "+ZZ"}},
+    {"CY", "CY", {"+XY", "+ZI", "+ZX", "+ZZ"}},
+    {"CZ", "CZ", {"+XZ", "+ZI", "+ZX", "+IZ"}},
+    {"XCX", "XCX", {"+XI", "+ZX", "+IX", "+XZ"}},
+    {"XCY", "XCY", {"+XI", "+ZY", "+XX", "+XZ"}},
+    {"XCZ", "XCZ", {"+XI", "+ZZ", "+XX", "+IZ"}},
+    {"YCX", "YCX", {"+XX", "+ZX", "+IX", "+YZ"}},
+    {"YCY", "YCY", {"+XY", "+ZY", "+YX", "+YZ"}},
+    {"YCZ", "YCZ", {"+XZ", "+ZZ", "+YX", "+IZ"}},
+    {"SWAP", "SWAP", {"+IX", "+IZ", "+XI", "+ZI"}},
+    {"ISWAP", "ISWAP_DAG", {"+ZY", "+IZ", "+YZ", "+ZI"}},
+    {"ISWAP_DAG", "ISWAP", {"-ZY", "+IZ", "-YZ", "+ZI"}},
+    {"CXSWAP", "SWAPCX", {"+XX", "+IZ", "+XI", "+ZZ"}},
+    {"SWAPCX", "CXSWAP", {"+IX", "+ZZ", "+XX", "+ZI"}},
+    {"CZSWAP", "CZSWAP", {"+ZX", "+IZ", "+XZ", "+ZI"}},
+    {"SQRT_XX", "SQRT_XX_DAG", {"+XI", "-YX", "+IX", "-XY"}},
+    {"SQRT_XX_DAG", "SQRT_XX", {"+XI", "+YX", "+IX", "+XY"}},
+    {"SQRT_YY", "SQRT_YY_DAG", {"-ZY", "+XY", "-YZ", "+YX"}},
+    {"SQRT_YY_DAG", "SQRT_YY", {"+ZY", "-XY", "+YZ", "-YX"}},
+    {"SQRT_ZZ", "SQRT_ZZ_DAG", {"+YZ", "+ZI", "+ZY", "+IZ"}},
+    {"SQRT_ZZ_DAG", "SQRT_ZZ", {"-YZ", "+ZI", "-ZY", "+IZ"}},
+};
+
+struct Tables {
+    std::map<std::string, Table1> fwd1, inv1;  // inv = conjugation by the inverse gate: U^dag P U
+    std::map<std::string, Table2> fwd2, inv2;
+    Tables() {
+        for (const auto &d : DEFS1) {
+            fwd1[d.name] = make1(d.f[0], d.f[1]);
+        }
+        for (const auto &d : DEFS1) {
+            inv1[d.name] = fwd1.at(d.inverse);
+        }
+        for (const auto &d : DEFS2) {
+            fwd2[d.name] = make2(d.f[0], d.f[1], d.f[2], d.f[3]);
+        }
+        for (const auto &d : DEFS2) {
+            inv2[d.name] = fwd2.at(d.inverse);
+        }
+    }
+};
+const Tables &tables() {
+    static const Tables t;
+    return t;
+}
+
+struct Sim {
+    size_t n, nw;
+    std::vector<uint64_t> X, Z;   // rows: 2q = T^dag X_q T, 2q+1 = T^dag Z_q T ; each nw words
+    std::vector<uint8_t> sign;
+    std::vector<uint8_t> record;
+
+    explicit Sim(size_t n) : n(n), nw((n + 63) / 64 + 1), X(2 * n * nw, 0), Z(2 * n * nw, 0), sign(2 * n, 0) {
+        for (size_t q = 0; q < n; q++) {
+            X[(2 * q) * nw + q / 64] |= 1ull << (q % 64);
+            Z[(2 * q + 1) * nw + q / 64] |= 1ull << (q % 64);
+        }
+    }
+    uint64_t *xr(size_t r) { return &X[r * nw]; }
+    uint64_t *zr(size_t r) { return &Z[r * nw]; }
+
+    // acc <- acc * row r ; returns the i-exponent contributed (including the row's sign)
+    int mul_into(uint64_t *ax, uint64_t *az, size_t r) {
+        const uint64_t *bx = xr(r), *bz = zr(r);
+        long plus = 0, minus = 0;
+        for (size_t w = 0; w < nw; w++) {
+            uint64_t xa = ax[w], za = az[w], xb = bx[w], zb = bz[w];
+            uint64_t p = (xa & ~za & xb & zb) | (xa & za & ~xb & zb) | (~xa & za & xb & ~zb);
+            uint64_t m = (xa & za & xb & ~zb) | (~xa & za & xb & zb) | (xa & ~za & ~xb & zb);
+            plus += __builtin_popcountll(p);
+            minus += __builtin_popcountll(m);
+            ax[w] = xa ^ xb;
+            az[w] = za ^ zb;
+        }
+        return (int)(((plus - minus) % 4 + 4 + 2 * sign[r]) & 3);
+    }
+
+    // row for sgn * (Pauli code pa on qubit a) (x) (code pb on qubit b), expressed through the current rows
+    void image_row(int pa, size_t a, int pb, size_t b, int sgn, std::vector<uint64_t> &ox, std::vector<uint64_t> &oz, uint8_t &os) {
+        ox.assign(nw, 0);
+        oz.assign(nw, 0);
+        int e = 2 * sgn + (pa == 3) + (pb == 3);
+        if (pa & 1) e += mul_into(ox.data(), oz.data(), 2 * a);
+        if (pa & 2) e += mul_into(ox.data(), oz.data(), 2 * a + 1);
+        if (pb & 1) e += mul_into(ox.data(), oz.data(), 2 * b);
+        if (pb & 2) e += mul_into(ox.data(), oz.data(), 2 * b + 1);
+        if (e & 1) {
+            throw std::logic_error("internal: non-Hermitian row in the inverse tableau");
+        }
+        os = (uint8_t)((e >> 1) & 1);
+    }
+
+    void gate1(const std::string &name, size_t q) {
+        const Table1 &t = tables().inv1.at(name);
+        std::vector<uint64_t> nx[2], nz[2];
+        uint8_t ns[2];
+        for (int g = 0; g < 2; g++) {
+            int code = g == 0 ? 1 : 2;
+            image_row(t.img[code], q, 0, q, t.sgn[code], nx[g], nz[g], ns[g]);
+        }
+        for (int g = 0; g < 2; g++) {
+            memcpy(xr(2 * q + g), nx[g].data(), nw * 8);
+            memcpy(zr(2 * q + g), nz[g].data(), nw * 8);
+            sign[2 * q + g] = ns[g];
+        }
+    }
+    void gate2(const std::string &name, size_t a, size_t b) {
+        const Table2 &t = tables().inv2.at(name);
+        std::vector<uint64_t> nx[4], nz[4];
+        uint8_t ns[4];
+        const int codes[4] = {1, 2, 4, 8};  // X_, Z_, _X, _Z
+        for (int g = 0; g < 4; g++) {
+            int img = t.img[codes[g]];
+            image_row(img & 3, a, img >> 2, b, t.sgn[codes[g]], nx[g], nz[g], ns[g]);
+        }
+        const size_t rows[4] = {2 * a, 2 * a + 1, 2 * b, 2 * b + 1};
+        for (int g = 0; g < 4; g++) {
+            memcpy(xr(rows[g]), nx[g].data(), nw * 8);
+            memcpy(zr(rows[g]), nz[g].data(), nw * 8);
+            sign[rows[g]] = ns[g];
+        }
+    }
+    void pauli(int code, size_t q) {  // X: 1, Z: 2, Y: 3 applied to the state
+        if (code & 1) sign[2 * q + 1] ^= 1;  // X flips the sign of T^dag Z_q T
+        if (code & 2) sign[2 * q] ^= 1;
+    }
+
+    // ---- input-side column operations: T <- T C, every row R <- C^dag R C -----------------------------------
+    void col1(const Table1 &t, size_t k) {
+        const size_t w = k / 64;
+        const uint64_t bit = 1ull << (k % 64);
+        for (size_t r = 0; r < 2 * n; r++) {
+            uint64_t *x = xr(r), *z = zr(r);
+            int c = ((x[w] & bit) ? 1 : 0) | ((z[w] & bit) ? 2 : 0);
+            if (!c) continue;
+            int d = t.img[c];
+            x[w] = (x[w] & ~bit) | ((d & 1) ? bit : 0);
+            z[w] = (z[w] & ~bit) | ((d & 2) ? bit : 0);
+            sign[r] ^= t.sgn[c];
+        }
+    }
+    void col2(const Table2 &t, size_t k, size_t j) {
+        const size_t wk = k / 64, wj = j / 64;
+        const uint64_t bk = 1ull << (k % 64), bj = 1ull << (j % 64);
+        for (size_t r = 0; r < 2 * n; r++) {
+            uint64_t *x = xr(r), *z = zr(r);
+            int c = ((x[wk] & bk) ? 1 : 0) | ((z[wk] & bk) ? 2 : 0) | ((x[wj] & bj) ? 4 : 0) | ((z[wj] & bj) ? 8 : 0);
+            if (!c) continue;
+            int d = t.img[c];
+            x[wk] = (x[wk] & ~bk) | ((d & 1) ? bk : 0);
+            z[wk] = (z[wk] & ~bk) | ((d & 2) ? bk : 0);
+            x[wj] = (x[wj] & ~bj) | ((d & 4) ? bj : 0);
+            z[wj] = (z[wj] & ~bj) | ((d & 8) ? bj : 0);
+            sign[r] ^= t.sgn[c];
+        }
+    }
+
+    // Z-basis measurement of qubit q; a random outcome is forced to 0.
+    bool measure_z(size_t q) {
+        const size_t r = 2 * q + 1;
+        size_t k = SIZE_MAX;
+        for (size_t w = 0; w < nw && k == SIZE_MAX; w++) {
+            if (xr(r)[w]) {
+                k = w * 64 + (size_t)__builtin_ctzll(xr(r)[w]);
+            }
+        }
+        if (k == SIZE_MAX) {
+            return sign[r] != 0;
+        }
+        const Tables &tb = tables();
+        // fold the X part of the row onto column k (input-side CX with control k fixes |0..0>)
+        for (size_t j = 0; j < n; j++) {
+            if (j != k && (xr(r)[j / 64] >> (j % 64)) & 1) {
+                col2(tb.inv2.at("CX"), k, j);
+            }
+        }
+        // clear the Z part (input-side CZ / S fix |0..0>)
+        for (size_t j = 0; j < n; j++) {
+            if (j != k && (zr(r)[j / 64] >> (j % 64)) & 1) {
+                col2(tb.inv2.at("CZ"), k, j);
+            }
+        }
+        if ((zr(r)[k / 64] >> (k % 64)) & 1) {
+            col1(tb.inv1.at("S"), k);
+        }
+        // row r is now +-X_k: collapse with an input-side H (and X for the sign) so that the outcome is 0
+        col1(tb.inv1.at("H"), k);
+        if (sign[r]) {
+            col1(tb.inv1.at("X"), k);
+        }
+        return false;
+    }
+    void to_z_basis(uint32_t basis, size_t q) {
+        if (basis == GB_X) {
+            gate1("H", q);
+        } else if (basis == GB_Y) {
+            gate1("H_YZ", q);
+        }
+    }
+    bool measure(uint32_t basis, size_t q) {
+        to_z_basis(basis, q);
+        bool m = measure_z(q);
+        to_z_basis(basis, q);
+        return m;
+    }
+    void reset(uint32_t basis, size_t q) {
+        to_z_basis(basis, q);
+        if (measure_z(q)) {
+            pauli(1, q);
+        }
+        to_z_basis(basis, q);
+    }
+};
+
+struct Product {
+    std::vector<std::pair<uint32_t, uint32_t>> terms;  // (qubit, xz code with bit0 = x, bit1 = z)
+    std::vector<uint32_t> bits;
+    bool sign = false;
+};
+
+std::vector<Product> read_products(const Instruction &op) {
+    std::vector<Product> out;
+    const auto &ts = op.targets;
+    size_t k = 0;
+    while (k < ts.size()) {
+        size_t end = k + 1;
+        while (end < ts.size() && ts[end] == T_COMBINER) {
+            end += 2;
+        }
+        Product p;
+        std::map<uint32_t, uint32_t> acc;
+        int e = 0;
+        for (size_t j = k; j < end; j += 2) {
+            uint32_t t = ts[j];
+            if (t & (T_REC | T_SWEEP)) {
+                p.bits.push_back(t);
+                continue;
+            }
+            if (t & T_INVERTED) {
+                p.sign = !p.sign;
+            }
+            uint32_t q = t & T_VALUE_MASK;
+            int c = ((t & T_PAULI_X) ? 1 : 0) | ((t & T_PAULI_Z) ? 2 : 0);
+            e += mul_phase((int)acc[q], c);
+            acc[q] ^= (uint32_t)c;
+        }
+        if (e & 1) {
+            throw std::invalid_argument(std::string("Acted on an anti-Hermitian operator (e.g. X0*Z0 instead of Y0) in ") + op.gate->name + ".");
+        }
+        if ((e >> 1) & 1) {
+            p.sign = !p.sign;
+        }
+        for (auto &kv : acc) {
+            if (kv.second) {
+                p.terms.push_back({kv.first, kv.second});
+            }
+        }
+        out.push_back(std::move(p));
+        k = end;
+    }
+    return out;
+}
+
+}  // namespace
+
+std::vector<uint8_t> reference_sample(const Circuit &circuit) {
+    CircuitStats stats = compute_stats(circuit);
+    Sim sim(std::max<size_t>(stats.num_qubits, 1));
+    auto rec_value = [&](uint32_t t, const char *gate) -> bool {
+        uint64_t k = t & T_VALUE_MASK;
+        if (k == 0 || k > sim.record.size()) {
+            throw std::out_of_range(std::string("Referred to a measurement record before the beginning of time in ") + gate + ".");
+        }
+        return sim.record[sim.record.size() - k] != 0;
+    };
+    circuit.for_each_operation([&](const Instruction &op) {
+        const GateInfo &g = *op.gate;
+        const std::string name = g.name;
+        switch (g.cat) {
+            case GateCat::NOOP:
+                if (name == "X" || name == "Y" || name == "Z") {
+                    int code = name == "X" ? 1 : name == "Z" ? 2 : 3;
+                    for (uint32_t t : op.targets) {
+                        sim.pauli(code, t & T_VALUE_MASK);
+                    }
+                }
+                break;
+            case GateCat::CLIFF1:
+                for (uint32_t t : op.targets) {
+                    sim.gate1(name, t & T_VALUE_MASK);
+                }
+                break;
+            case GateCat::CLIFF2:
+                for (size_t i = 0; i < op.targets.size(); i += 2) {
+                    uint32_t a = op.targets[i], b = op.targets[i + 1];
+                    bool a_bit = (a & (T_REC | T_SWEEP)) != 0, b_bit = (b & (T_REC | T_SWEEP)) != 0;
+                    if (!a_bit && !b_bit) {
+                        sim.gate2(name, a & T_VALUE_MASK, b & T_VALUE_MASK);
+                        continue;
+                    }
+                    // classically controlled Pauli (bit-as-target errors are raised by the lowering)
+                    uint32_t bit, q;
+                    int code;
+                    if (name == "CX" || name == "CY") {
+                        if (b_bit) throw std::invalid_argument("Controlled gate had a bit as its target, instead of its control.");
+                        bit = a, q = b, code = name == "CX" ? 1 : 3;
+                    } else if (name == "XCZ" || name == "YCZ") {
+                        if (a_bit) throw std::invalid_argument("Controlled gate had a bit as its target, instead of its control.");
+                        bit = b, q = a, code = name == "XCZ" ? 1 : 3;
+                    } else {
+                        if (a_bit && b_bit) continue;
+                        bit = a_bit ? a : b, q = a_bit ? b : a, code = 2;
+                    }
+                    if ((bit & T_SWEEP) == 0 && rec_value(bit, g.name)) {
+                        sim.pauli(code, q & T_VALUE_MASK);
+                    }
+                }
+                break;
+            case GateCat::MEASURE: {
+                uint32_t basis = g.param & 3, kind = g.param >> 2;
+                for (uint32_t t : op.targets) {
+                    size_t q = t & T_VALUE_MASK;
+                    if (kind == GK_R) {
+                        sim.reset(basis, q);
+                        continue;
+                    }
+                    bool m = sim.measure(basis, q);
+                    sim.record.push_back((uint8_t)(m ^ ((t & T_INVERTED) != 0)));
+                    if (kind == GK_MR && m) {
+                        // back to the +1 eigenstate of the measured basis
+                        sim.to_z_basis(basis, q);
+                        sim.pauli(1, q);
+                        sim.to_z_basis(basis, q);
+                    }
+                }
+            } break;
+            case GateCat::MPAD:
+                for (uint32_t t : op.targets) {
+                    sim.record.push_back((uint8_t)(t & 1));
+                }
+                break;
+            case GateCat::MPP:
+                for (const Product &p : read_products(op)) {
+                    if (p.terms.empty()) {
+                        sim.record.push_back((uint8_t)p.sign);
+                        continue;
+                    }
+                    size_t first = p.terms[0].first;
+                    for (auto &e : p.terms) {
+                        if (e.second == 1) sim.gate1("H", e.first);
+                        if (e.second == 3) sim.gate1("H_YZ", e.first);
+                    }
+                    for (size_t i = 1; i < p.terms.size(); i++) {
+                        sim.gate2("CX", p.terms[i].first, first);
+                    }
+                    bool m = sim.measure_z(first);
+                    sim.record.push_back((uint8_t)(m ^ p.sign));
+                    for (size_t i = 1; i < p.terms.size(); i++) {
+                        sim.gate2("CX", p.terms[i].first, first);
+                    }
+                    for (auto &e : p.terms) {
+                        if (e.second == 1) sim.gate1("H", e.first);
+                        if (e.second == 3) sim.gate1("H_YZ", e.first);
+                    }
+                }
+                break;
+            case GateCat::SPP:
+                for (const Product &p : read_products(op)) {
+                    if (p.terms.empty()) {
+                        continue;
+                    }
+                    size_t focus = p.terms[0].first;
+                    bool dag = (name == "SPP_DAG") ^ p.sign;
+                    auto conj = [&]() {
+                        for (auto &e : p.terms) {
+                            if (e.second == 1) sim.gate1("H", e.first);
+                            if (e.second == 3) sim.gate1("H_YZ", e.first);
+                        }
+                    };
+                    auto fold = [&]() {
+                        for (size_t i = 1; i < p.terms.size(); i++) {
+                            sim.gate2("CX", p.terms[i].first, focus);
+                        }
+                        for (uint32_t b : p.bits) {
+                            if (!(b & T_SWEEP) && rec_value(b, g.name)) {
+                                sim.pauli(1, focus);
+                            }
+                        }
+                    };
+                    conj();
+                    fold();
+                    sim.gate1(dag ? "S_DAG" : "S", focus);
+                    fold();
+                    conj();
+                }
+                break;
+            case GateCat::MPAIR: {
+                const char *conj = g.param == GB_X ? "CX" : g.param == GB_Y ? "CY" : "XCZ";
+                for (size_t i = 0; i < op.targets.size(); i += 2) {
+                    size_t a = op.targets[i] & T_VALUE_MASK, b = op.targets[i + 1] & T_VALUE_MASK;
+                    bool inv = ((op.targets[i] ^ op.targets[i + 1]) & T_INVERTED) != 0;
+                    sim.gate2(conj, a, b);
+                    bool m = sim.measure(g.param, a);
+                    sim.record.push_back((uint8_t)(m ^ inv));
+                    sim.gate2(conj, a, b);
+                }
+            } break;
+            case GateCat::HERALDED_ERASE:
+            case GateCat::HERALDED_PAULI_CHANNEL_1:
+                for (size_t i = 0; i < op.targets.size(); i++) {
+                    sim.record.push_back(0);
+                }
+                break;
+            default:  // noise, annotations
+                break;
+        }
+    });
+    return sim.record;
+}
+
+}  // namespace gstim

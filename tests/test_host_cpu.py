@@ -1,0 +1,235 @@
+"""CPU tests of the host side: C ABI surface, parser / lowering error behaviour (same exception types as the
+reference), lowering correctness through the program-level emulator, and the multi-rank sharding logic (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import stim_b200
+from conftest import ROOT, gen_circuit
+from oracle import frame_oracle as fo
+from oracle import program_emulator as pe
+from stim_b200 import _native, sharding
+
+
+def lower(text, mode, slots, chunk=0):
+    L = _native.lib()
+    d = text.encode()
+    n = ctypes.c_size_t(0)
+    plan = (ctypes.c_uint32 * 16)()
+    _native.check(L.gstim_lower_text(d, len(d), mode, slots, chunk, None, ctypes.byref(n), plan))
+    w = np.empty(n.value, dtype=np.uint32)
+    _native.check(L.gstim_lower_text(d, len(d), mode, slots, chunk, w.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n), plan))
+    return w, list(plan)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# C ABI
+# ---------------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "gstim.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(gstim_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gstim_sampler", "gstim_stats"}
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/gstim.h but not exported"
+    assert declared == set(_native.exported_symbols()), "ctypes binding and header disagree"
+    assert lib.gstim_version() >= 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device creating a sampler must fail loudly (after validating the circuit)."""
+    if _native.lib().gstim_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(stim_b200.GstimCudaError):
+        stim_b200.Circuit("H 0\nM 0\n").compile_detector_sampler(seed=1)
+    with pytest.raises(stim_b200.GstimCudaError):
+        stim_b200.Circuit("H 0\nM 0\n").compile_sampler(seed=1, skip_reference_sample=True)
+
+
+def test_product_path_does_not_import_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "stim_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cc", ".cu", ".h", ".cuh")):
+                with open(os.path.join(root, fn)) as f:
+                    src = f.read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace(
+                    "oracle/program_emulator.py", "").replace("oracle/philox.py", "").replace("oracle/log2_table.py", ""), fn
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parser / stats / errors (exception types follow the reference: invalid_argument -> ValueError, out_of_range -> IndexError)
+# ---------------------------------------------------------------------------------------------------------
+def test_circuit_stats_match_reference_numbers():
+    # SURVEY Appendix C, computed with the reference
+    c3 = stim_b200.Circuit(gen_circuit("surface_code", "rotated_memory_z", 25, 25, 0.001)) if False else None
+    with open(os.path.join(ROOT, "tests", "golden", "circuits", "c3_surface_z_d25_r25.stim")) as f:
+        c3 = stim_b200.Circuit(f.read())
+    assert (c3.num_qubits, c3.num_measurements, c3.num_detectors, c3.num_observables) == (1324, 16225, 15600, 1)
+    assert c3._stats.max_lookback == 1248 and c3._stats.active_qubits == 1249
+    with open(os.path.join(ROOT, "tests", "golden", "circuits", "c5_surface_x_d51_r51.stim")) as f:
+        c5 = stim_b200.Circuit(f.read())
+    assert (c5.num_measurements, c5.num_detectors, c5._stats.active_qubits) == (135201, 132600, 5201)
+    c = stim_b200.Circuit("MPP X0*Y1 Z2\nMXX 0 1\nMPAD 1\nHERALDED_ERASE(0.1) 3\nOBSERVABLE_INCLUDE(7) rec[-1]\nDETECTOR\n")
+    assert (c.num_measurements, c.num_detectors, c.num_observables, c.num_qubits) == (5, 1, 8, 4)
+
+
+@pytest.mark.parametrize("text", [
+    "NOT_A_GATE 0",
+    "H rec[-1]",
+    "CX 0",
+    "CX 0 0",
+    "X_ERROR(1.5) 0",
+    "X_ERROR 0",
+    "PAULI_CHANNEL_1(0.5, 0.4, 0.3) 0",
+    "M(0.1, 0.2) 0",
+    "DETECTOR 0",
+    "MPP X0*",
+    "MPP X0*Z0",
+    "CX 0 rec[-1]",
+    "M 0\nCY 1 rec[-1]",
+    "REPEAT 0 {\nH 0\n}",
+    "REPEAT 2 {\nH 0\n",
+    "}",
+    "TICK 0",
+    "E(0.1) 5",
+    "OBSERVABLE_INCLUDE(1.5) rec[-1]",
+    "MPAD 2",
+])
+def test_invalid_circuits_raise_value_error(text):
+    with pytest.raises(ValueError):
+        stim_b200.Circuit(text)
+
+
+@pytest.mark.parametrize("text", ["DETECTOR rec[-1]", "M 0\nDETECTOR rec[-2]", "M 0\nCX rec[-3] 1", "OBSERVABLE_INCLUDE(0) rec[-1]"])
+def test_bad_lookback_raises_index_error(text):
+    with pytest.raises(IndexError):  # measure_record_batch.inl:83-94 throws std::out_of_range
+        stim_b200.Circuit(text)
+
+
+def test_parser_accepts_the_documented_syntax():
+    c = stim_b200.Circuit("""
+        # comment
+        h[tag] 0 1   # lower case names, tags
+        CNOT 0 1
+        ZCX 2 3
+        M !0 1
+        MPP !X0*Y1*Z2 X3
+        REPEAT 3 {
+            MR 0
+            DETECTOR(1, 2) rec[-1] rec[-2]
+        }
+        QUBIT_COORDS(1, 2) 5
+        SHIFT_COORDS(0, 0, 1)
+        CX sweep[5] 0
+        OBSERVABLE_INCLUDE(2) rec[-1] X0 Z1
+    """)
+    assert c.num_measurements == 2 + 2 + 3 and c.num_detectors == 3 and c.num_observables == 3
+
+
+# ---------------------------------------------------------------------------------------------------------
+# lowering == reference semantics (program emulator vs circuit-level oracle), incl. the stream's race contract
+# ---------------------------------------------------------------------------------------------------------
+LOWERING_CIRCUITS = [
+    ("repetition_code", "memory", 3, 4, 0.05),
+    ("surface_code", "rotated_memory_z", 3, 3, 0.02),
+    ("surface_code", "unrotated_memory_x", 3, 2, 0.03),
+    ("color_code", "memory_xyz", 3, 3, 0.02),
+]
+
+
+@pytest.mark.parametrize("code,task,d,r,p", LOWERING_CIRCUITS)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_lowered_program_equals_oracle(code, task, d, r, p, mode):
+    text = gen_circuit(code, task, d, r, p)
+    for slots, chunk in ((32, 0), (5, 256)):
+        w, plan = lower(text, mode, slots, chunk)
+        em = pe.emulate(w, plan, seed=7, K=2, n_blocks=2, col0=10)
+        if mode == 0:
+            dd, oo = fo.sample(text, 2 * 2 * 128, 7, 2, "detectors", col0=10)
+            ref = np.concatenate([dd, oo], axis=1)
+        else:
+            ref = fo.sample(text, 2 * 2 * 128, 7, 2, "measurements", col0=10)
+        np.testing.assert_array_equal(em, ref)
+
+
+def test_lowered_program_equals_oracle_on_every_instruction():
+    from test_gpu_parity import ALL_OPS
+
+    for mode in (0, 1):
+        for slots in (32, 3):
+            w, plan = lower(ALL_OPS, mode, slots)
+            em = pe.emulate(w, plan, seed=3, K=1, n_blocks=2, col0=4)
+            if mode == 0:
+                dd, oo = fo.sample(ALL_OPS, 256, 3, 1, "detectors", col0=4)
+                ref = np.concatenate([dd, oo], axis=1)
+            else:
+                ref = fo.sample(ALL_OPS, 256, 3, 1, "measurements", col0=4)
+            np.testing.assert_array_equal(em, ref)
+
+
+def test_batches_are_padded_into_chunks_and_large_circuits_lower_quickly():
+    with open(os.path.join(ROOT, "tests", "golden", "circuits", "c3_surface_z_d25_r25.stim")) as f:
+        text = f.read()
+    w, plan = lower(text, 0, 640)
+    p = pe.plan_dict(plan)
+    assert p["n_words"] == w.size and w.size % p["chunk_words"] == 0
+    assert p["num_qubits"] == 1249 and p["rec_ring"] == 2048 and p["num_det"] == 15600
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-rank path: shots shard with no data-path collective; only the flip-count sum is reduced
+# ---------------------------------------------------------------------------------------------------------
+def test_shard_ranges_partition_the_shot_space():
+    for total in (1 << 20, 1000_003, 128, 64):
+        for world in (1, 2, 4, 8):
+            ranges = [sharding.shard_range(total, r, world) for r in range(world)]
+            assert ranges[0][0] == 0
+            for (a, n), (b, _) in zip(ranges, ranges[1:]):
+                assert a + n == b and a % 128 == 0
+            assert ranges[-1][0] + ranges[-1][1] == total
+
+
+GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, os.environ["REPO_ROOT"])
+import numpy as np
+import torch.distributed as dist
+from oracle import frame_oracle as fo
+from stim_b200 import sharding
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+text = open(os.environ["CIRCUIT"]).read()
+total, K, seed = 2048, 2, 9
+first, count = sharding.shard_range(total, rank, world)
+dets, obs = fo.sample(text, count, seed, K, "detectors", col0=first // 128)   # this rank's shard of the global shot space
+local = np.concatenate([dets, obs], axis=1).sum(axis=0).astype(np.uint64)
+reduced = sharding.allreduce_counts(local)
+if rank == 0:
+    d1, o1 = fo.sample(text, total, seed, K, "detectors", col0=0)             # the same shots in one process
+    want = np.concatenate([d1, o1], axis=1).sum(axis=0).astype(np.uint64)
+    assert np.array_equal(reduced, want), (reduced, want)
+    print("GLOO_OK", int(reduced.sum()))
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_2_gloo_flip_count_allreduce(tmp_path):
+    """Shard-count invariance: 2 ranks sampling disjoint shot ranges + allreduce == 1 rank sampling all of them."""
+    circuit = tmp_path / "c.stim"
+    circuit.write_text(gen_circuit("surface_code", "rotated_memory_z", 3, 3, 0.02))
+    worker = tmp_path / "worker.py"
+    worker.write_text(GLOO_WORKER)
+    env = dict(os.environ, REPO_ROOT=ROOT, CIRCUIT=str(circuit))
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29517", str(worker)],
+        env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_OK" in r.stdout

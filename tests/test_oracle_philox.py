@@ -1,0 +1,54 @@
+"""Pins the oracle's random primitives: Philox4x32-10 against the Random123 known-answer vectors and the
+fixed-point exponential draw against libm."""
+import math
+import random
+
+import numpy as np
+
+from oracle import philox as px
+
+
+def test_philox4x32_10_known_answers():
+    # Random123 kat_vectors: philox4x32 10 rounds (counter words, key words -> output words)
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in kat:
+        got = px.philox4x32_10(*ctr, *key)
+        assert tuple(int(v) for v in got) == want
+
+
+def test_philox_is_vectorised_consistently():
+    c0 = np.arange(7, dtype=np.uint64)
+    a = px.philox4x32_10(c0, 5, 9, 11, 123, 456)
+    for i in range(7):
+        b = px.philox4x32_10(i, 5, 9, 11, 123, 456)
+        assert [int(x[i]) for x in a] == [int(x) for x in b]
+
+
+def test_exp_draw_fx_matches_log():
+    rng = random.Random(5)
+    worst = 0.0
+    for r in [0, 1, 2, 3, 255, 256, 1 << 24, 1 << 31, (1 << 32) - 1] + [rng.getrandbits(32) for _ in range(20000)]:
+        got = px.exp_draw_fx(r) / 2.0**56
+        want = -math.log((r + 0.5) / 2.0**32)
+        worst = max(worst, abs(got - want))
+    assert worst < 3e-6  # table interpolation error bound
+
+
+def test_exp_draw_fx_is_exponential():
+    rng = np.random.default_rng(1)
+    r = rng.integers(0, 1 << 32, size=200000, dtype=np.uint64)
+    e = np.array([px.exp_draw_fx(int(v)) for v in r[:50000]], dtype=np.float64) / 2.0**56
+    assert abs(e.mean() - 1.0) < 0.02
+    assert abs((e > 1.0).mean() - math.exp(-1)) < 0.01
+
+
+def test_lam_fx():
+    assert px.lam_fx(0.0) == 0
+    assert px.lam_fx(1.0) == px.LAM_MAX
+    v = px.lam_fx(1e-3)
+    assert abs(v / 2.0**56 - (-math.log1p(-float(np.float32(1e-3))))) < 1e-15
