@@ -48,7 +48,7 @@ def test_rates_and_pair_correlations_match_reference(name):
         sampler = circ.compile_detector_sampler(seed=20251017)
         draw = lambda n: sampler.sample(n, bit_packed=True, append_observables=True)  # noqa: E731
     else:
-        sampler = circ.compile_sampler(seed=20251017, skip_reference_sample=True)
+        sampler = circ.compile_sampler(seed=20251017)  # default reference sample (e.g. MPAD 1 records a constant 1)
         draw = lambda n: sampler.sample(n, bit_packed=True)  # noqa: E731
     single = np.zeros(n_bits, dtype=np.int64)
     pair = np.zeros(n_bits - 1, dtype=np.int64)
