@@ -469,6 +469,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         p.ev_buf = (uint32_t *)s->d_ev_buf.p;
         p.ev_overflow = (uint32_t *)s->d_ev_overflow.p;
         p.dbg_cycles = nullptr;
+        p.dbg_flags = env_u32("GSTIM_DEBUG_FLAGS", 0);
         if (env_u32("GSTIM_DEBUG_CYCLES", 0)) {
             s->d_dbg.ensure(32 * 8);
             CK(cudaMemsetAsync(s->d_dbg.p, 0, 32 * 8, s->stream));

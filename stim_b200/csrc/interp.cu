@@ -136,6 +136,7 @@ struct __align__(16) BlockCtx {
     uint32_t pre_mbar_s, pre_phase;
     uint32_t n_chains, pad1;
     unsigned long long *dbg;  // optional cycle counters (block 0 only)
+    uint32_t dbg_flags, pad2;
 };
 
 size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t n_noise) {
@@ -145,7 +146,7 @@ size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chun
     b += (size_t)K * 16;                // correlated-error flag row
     b += (size_t)2 * chunk_words * 4;   // program ring
     b += 512 * 4;                       // log2 table
-    b += 64 * 8;                        // per rate class: need, rate
+    b += 128 * 8;                       // per rate class: need, rate, 2^64/need, 2^64/rate
     if (n_noise <= GSTIM_EV_SMEM_MAX) {
         b += ((size_t)(2 * n_noise + 1) * 4 + 15) / 16 * 16;  // event counters + segment offsets
     }
@@ -238,13 +239,16 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
             tA = t;
         }
         if (c0 + tid < c1) {
-            const uint4 ch = *reinterpret_cast<const uint4 *>(chains + 4 * (size_t)(c0 + tid));  // row, segment, begin, len
+            const uint4 ch = *reinterpret_cast<const uint4 *>(chains + 4 * (size_t)(c0 + tid));  // row, segment | flags, begin, len
             uint32_t ea = ent_s + 8 * (ch.z - e0);
             const uint32_t ea_end = ea + 8 * ch.w;
             const uint32_t lrow = logical_of[ch.x];
+            const bool uniform = (ch.y >> 31) != 0;  // every site of the chain has rate class ucls
+            const uint32_t ucls = (ch.y >> 26) & 31u;
+            const uint32_t seg = uniform ? (ch.y & 0x3FFFFFFu) : ch.y;
             unsigned long long E;
             {
-                const uint4 rr = philox4x32_10(lrow, ch.y, col0_lo, GTAG_CLOCK ^ col0_hi, k0, k1);  // (re)arm the clock
+                const uint4 rr = philox4x32_10(lrow, seg, col0_lo, GTAG_CLOCK ^ col0_hi, k0, k1);  // (re)arm the clock
                 E = exp_draw_fx(rr.x, lt_s);
             }
             uint32_t pos = 0, kev = 0;
@@ -252,10 +256,32 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
                 // ---- skip phase: fast-forward over sites until this lane has an event pending, so that when the
                 // warp reconverges every live lane has event work
                 unsigned long long entry = 0, lam = 0;
+                uint32_t cls = 31;
                 bool pending = false;
                 while (ea < ea_end) {
+                    if (pos == 0 && uniform) {
+                        // all sites ahead consume the same amount: jump floor(E / need) of them at once
+                        const unsigned long long need = lds64(needs_s + 8 * ucls);
+                        if (E >= need) {
+                            unsigned long long n = __umul64hi(E, lds64(needs_s + 512 + 8 * ucls));  // ~ E / need (never above)
+                            while ((n + 1) * need <= E) {
+                                n++;
+                            }
+                            const unsigned long long room = (ea_end - ea) >> 3;
+                            n = n < room ? n : room;
+                            n_skip += n;
+                            E -= n * need;
+                            ea += 8 * (uint32_t)n;
+                            continue;
+                        }
+                        entry = lds64(ea);
+                        cls = ucls;
+                        lam = lds64(needs_s + 256 + 8 * cls);
+                        pending = true;
+                        break;
+                    }
                     entry = lds64(ea);
-                    const uint32_t cls = ((uint32_t)entry >> 27) & 31u;
+                    cls = ((uint32_t)entry >> 27) & 31u;
                     unsigned long long rem;
                     if (cls < 31) {
                         lam = lds64(needs_s + 256 + 8 * cls);
@@ -289,15 +315,24 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
                     i0 = *reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS);
                     i1 = *reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + 4);
                 }
-                // j = floor(E / lam), clamped to the shots left: float estimate + exact fix-up
+                // j = floor(E / lam), clamped to the shots left
                 const uint32_t left = B - pos - 1;
-                const float est = __ull2float_rz(E) / __ull2float_rn(lam);
-                uint32_t j = est >= (float)left ? left : (uint32_t)est;
-                while (j > 0 && (unsigned long long)j * lam > E) {
-                    j--;
-                }
-                while (j < left && (unsigned long long)(j + 1) * lam <= E) {
-                    j++;
+                uint32_t j;
+                if (cls < 31) {
+                    unsigned long long q = __umul64hi(E, lds64(needs_s + 768 + 8 * cls));  // reciprocal estimate, never above
+                    while ((q + 1) * lam <= E) {
+                        q++;
+                    }
+                    j = q >= left ? left : (uint32_t)q;
+                } else {
+                    const float est = __ull2float_rz(E) / __ull2float_rn(lam);
+                    j = est >= (float)left ? left : (uint32_t)est;
+                    while (j > 0 && (unsigned long long)j * lam > E) {
+                        j--;
+                    }
+                    while (j < left && (unsigned long long)(j + 1) * lam <= E) {
+                        j++;
+                    }
                 }
                 const uint32_t shot = pos + j;
                 const uint4 rr = philox4x32_10((uint32_t)(entry >> 32), lrow | (kev << 16), col0_lo, GTAG_EVENT ^ col0_hi, k0, k1);
@@ -501,7 +536,7 @@ __device__ __noinline__ void op_measure(const BlockCtx *bc, const uint32_t *hdr)
         uint32_t ax = bc->X_s + q * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
             const uint64_t col = col0 + k;
-            const uint4 rnd = philox4x32_10(mgroup, lq, (uint32_t)col, GTAG_COLLAPSE ^ (uint32_t)(col >> 32), k0, k1);
+            const uint4 rnd = bc->dbg_flags & 2u ? make_uint4(0, 0, 0, 0) : philox4x32_10(mgroup, lq, (uint32_t)col, GTAG_COLLAPSE ^ (uint32_t)(col >> 32), k0, k1);
             const uint4 zero = make_uint4(0, 0, 0, 0);
             uint4 m, nx, nz;
             if (basis == GB_Z) {  // frame_simulator.inl:199-208, 266-274, 306-317
@@ -550,18 +585,53 @@ __device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr)
     const uint32_t *dst = pay, *off = pay + n, *idx = pay + 2 * n + 1;
     const uint4 *rec = bc->rec;
     const uint64_t rrs = bc->rec_row_stride;
+    // Record rows live in global memory (L2): keep up to 4 columns x 2 rows of loads in flight per thread
+    // instead of one dependent load at a time.
+    const uint32_t G = 1u << G_log2;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t b0 = off[i], b1 = off[i + 1];
         uint4 *orow = bc->out + (uint64_t)dst[i] * bc->out_row_stride;
-        for (uint32_t k = sub; k < K; k += 1u << G_log2) {
-            uint4 acc = make_uint4(0, 0, 0, 0);
-            for (uint32_t j = b0; j < b1; j++) {
-                acc = xor4(acc, rec[(uint64_t)idx[j] * rrs + k]);
+        for (uint32_t k0 = sub; k0 < K; k0 += 4 * G) {
+            uint4 acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                acc[u] = make_uint4(0, 0, 0, 0);
             }
-            if (flags & GF_ACCUM) {
-                acc = xor4(acc, orow[k]);
+            uint32_t j = b0;
+            for (; j + 2 <= b1; j += 2) {
+                const uint4 *r0 = rec + (uint64_t)idx[j] * rrs, *r1 = rec + (uint64_t)idx[j + 1] * rrs;
+                uint4 v0[4], v1[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t k = k0 + u * G;
+                    v0[u] = k < K ? r0[k] : make_uint4(0, 0, 0, 0);
+                    v1[u] = k < K ? r1[k] : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    acc[u] = xor4(acc[u], xor4(v0[u], v1[u]));
+                }
             }
-            orow[k] = acc;
+            if (j < b1) {
+                const uint4 *r0 = rec + (uint64_t)idx[j] * rrs;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t k = k0 + u * G;
+                    if (k < K) {
+                        acc[u] = xor4(acc[u], r0[k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t k = k0 + u * G;
+                if (k < K) {
+                    if (flags & GF_ACCUM) {
+                        acc[u] = xor4(acc[u], orow[k]);
+                    }
+                    orow[k] = acc[u];
+                }
+            }
         }
     }
 }
@@ -665,7 +735,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     uint32_t *lt = (uint32_t *)sp;
     sp += 512 * 4;
     const uint32_t needs_s = smem_u32(sp);
-    sp += 64 * 8;
+    sp += 128 * 8;
     uint32_t *ev_s = (uint32_t *)sp;  // [n_noise] counters, [n_noise + 1] segment offsets (when they fit)
     const bool ev_in_smem = p.n_noise <= GSTIM_EV_SMEM_MAX;
     if (ev_in_smem) {
@@ -685,6 +755,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         mbar_init(mbar_s + 8, 1);
         mbar_init(mbar_s + 16, 1);
         bc->pre_mbar_s = mbar_s + 16;
+        bc->dbg_flags = p.dbg_flags;
         bc->dbg = blockIdx.x == 0 ? p.dbg_cycles : nullptr;
         bc->pre_phase = 0;
         bc->rounds = p.rounds;
@@ -724,6 +795,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     for (uint32_t i = tid; i < p.n_rates; i += T) {
         sts64(needs_s + 8 * i, sat_mul(p.K * GSTIM_COL_SHOTS, p.rates[i]));
         sts64(needs_s + 256 + 8 * i, p.rates[i]);
+        {
+            const unsigned long long need = sat_mul(p.K * GSTIM_COL_SHOTS, p.rates[i]);
+            sts64(needs_s + 512 + 8 * i, need ? 0xFFFFFFFFFFFFFFFFull / need : 0ull);
+            sts64(needs_s + 768 + 8 * i, p.rates[i] ? 0xFFFFFFFFFFFFFFFFull / p.rates[i] : 0ull);
+        }
     }
     if (ev_in_smem) {
         for (uint32_t i = tid; i <= p.n_noise; i += T) {
@@ -760,7 +836,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
             }
         }
         __syncthreads();
-        noise_prepass(bc);
+        if (!(p.dbg_flags & 1u)) {
+            noise_prepass(bc);
+        }
         __syncthreads();
 
         for (uint32_t chunk = 0;; chunk++) {
@@ -797,7 +875,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
                 } else if (multi) {
                     __syncwarp();
                 }
-                switch (op) {
+                const uint32_t skipmask = p.dbg_flags >> 8;  // debug: bit (op) set -> skip that opcode
+                switch ((skipmask >> op) & 1u ? (uint32_t)GOP_QMAP : op) {
                     case GOP_CLIFF1:
                         op_cliff1(bc, pw);
                         break;

@@ -28,6 +28,7 @@ struct InterpParams {
     uint32_t rec_mask;         // ring mask (detector mode) or 0xFFFFFFFF
     uint4 *out;                // detector/observable rows (bit-major); block g owns uint4 columns [g*K,(g+1)*K)
     uint64_t out_row_stride;   // uint4 units
+    uint32_t dbg_flags;        // GSTIM_DEBUG_FLAGS: timing experiments only (results become wrong): bit0 no pre-pass, bit1 no collapse RNG, bits 8+op skip opcode
     unsigned long long *dbg_cycles;  // optional (GSTIM_DEBUG_CYCLES=1): [op] cycles and [16+op] batch counts seen by block 0
     // noise schedule (program.h) and the per-CTA event scratch the pre-pass fills
     uint32_t n_noise;                 // noise batches

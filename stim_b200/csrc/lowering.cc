@@ -1375,7 +1375,13 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
     }
     for (const Chain &c : chains) {
         ns.chains.push_back(c.row);
-        ns.chains.push_back(c.seg);
+        // bit 31 of the segment word: every site of the chain has the same (tabulated) rate class, stored in bits 26-30
+        uint32_t cls0 = ((uint32_t)ns.qlist[c.begin] >> 27) & 31u;
+        bool uniform = cls0 < 31 && c.seg < (1u << 26);
+        for (uint32_t i = 1; i < c.len && uniform; i++) {
+            uniform = (((uint32_t)ns.qlist[c.begin + i] >> 27) & 31u) == cls0;
+        }
+        ns.chains.push_back(uniform ? (c.seg | (cls0 << 26) | (1u << 31)) : c.seg);
         ns.chains.push_back(c.begin);
         ns.chains.push_back(c.len);
     }
