@@ -223,25 +223,8 @@ class FrameOracle:
         self.obs = {}
         self.ngroup = 0  # noise group counter   (Philox counter word 0 of event draws)
         self.mgroup = 0  # measure group counter (Philox counter word 0 of collapse draws)
-        # exponential clocks: one per qubit + one global (index Q), re-armed from Philox whenever
-        # noise_group >> CLOCK_SEG_SHIFT changes; DESIGN.md "RNG addressing"
-        self.clk = np.zeros((self.Q + 1, self.nb), dtype=np.uint64)
-        self.clk_seg = [-1] * (self.Q + 1)
 
-    CLOCK_SEG_SHIFT = 5
-
-    def arm_clocks(self, clocks, group):
-        seg = group >> self.CLOCK_SEG_SHIFT
-        stale = [c for c in clocks if self.clk_seg[c] != seg]
-        if not stale:
-            return
-        q = np.asarray(stale, dtype=np.uint64)[:, None]
-        c2 = (self.col0 & np.uint64(0xFFFFFFFF))[None, :]
-        c3 = (np.uint64(px.TAG_CLOCK) ^ (self.col0 >> np.uint64(32)))[None, :]
-        r = px.philox4x32_10(q, seg, c2, c3, self.k0, self.k1)
-        self.clk[stale, :] = np.array([[px.exp_draw_fx(int(v)) for v in row] for row in r[0]], dtype=np.uint64).reshape(len(stale), self.nb)
-        for c in stale:
-            self.clk_seg[c] = seg
+    NOISE_SLICE = 16  # GSTIM_NOISE_SLICE (program.h)
 
     # -- randomness ---------------------------------------------------------------------------
     def collapse_words(self, mgroup, q):
@@ -252,41 +235,37 @@ class FrameOracle:
         return np.stack(r, axis=1).reshape(-1)
 
     def run_sites(self, clocks, lam, group, on_event):
-        """Geometric-skip sampling of len(clocks) independent sites (distinct clock qubits) over all blocks.
+        """Samples the len(clocks) sites of noise group `group` (in target order) over all blocks.
 
-        on_event(i, g, shot, r) with r = 4 uint32 of the event's Philox draw. Event positions follow
-        floor(E/lambda) skipping == RareErrorIterator (probability_util.cc:33-43), in exact integer arithmetic."""
-        clocks = [int(c) for c in clocks]
+        The sites are cut into slices of NOISE_SLICE; a slice x a shot block is one Bernoulli sequence (site-major, then
+        shot) walked with geometric gaps floor(Exp(1)/lambda) == RareErrorIterator (probability_util.cc:33-43), in
+        exact integer arithmetic. Draw d of a slice: Philox counter (group, 0x80000000 | slice, col0 lo, col0 hi | d << 15);
+        word 0 -> gap to the next event, word 1 -> that event's Pauli word. on_event(i, g, shot, r): r[1] = Pauli word."""
         n = len(clocks)
         if n == 0 or lam == 0:
             return
-        B = self.B
-        need = min(B * lam, px.REM_SAT)
-        self.arm_clocks(clocks, group)
-        E = self.clk[clocks, :]  # [n, nb] copy (uint64)
-        hit = E < np.uint64(need)
-        E = np.where(hit, E, E - np.uint64(min(need, (1 << 64) - 1)))
-        for i, g in np.argwhere(hit):
-            i, g = int(i), int(g)
-            e = int(E[i, g])
-            pos = kev = 0
-            c2 = int(self.col0[g]) & 0xFFFFFFFF
-            c3 = px.TAG_EVENT ^ (int(self.col0[g]) >> 32)
-            while pos < B:
-                rem = min((B - pos) * lam, px.REM_SAT)
-                if e >= rem:
-                    e -= rem
-                    break
-                j = min(e // lam, B - pos - 1)
-                shot = pos + j
-                r = px.philox4x32_10(group, clocks[i] | (kev << 16), c2, c3, self.k0, self.k1)
-                r = tuple(int(v) for v in r)
-                on_event(i, g, shot, r)
-                e = px.exp_draw_fx(r[0])
-                pos = shot + 1
-                kev += 1
-            E[i, g] = e
-        self.clk[clocks, :] = E
+        B, S = self.B, self.NOISE_SLICE
+        n_sl = (n + S - 1) // S
+        c2 = (self.col0 & np.uint64(0xFFFFFFFF))[None, :]
+        c3 = (self.col0 >> np.uint64(32))[None, :]
+        assert int(self.col0.max()) < (1 << 47)
+        js = (np.arange(n_sl, dtype=np.uint64) | np.uint64(0x80000000))[:, None]
+        first = px.philox4x32_10(group, js, c2, c3, self.k0, self.k1)
+        for j in range(n_sl):
+            total = min(S, n - j * S) * B
+            for g in range(self.nb):
+                r0, r1 = int(first[0][j, g]), int(first[1][j, g])
+                a, d = 0, 1
+                while True:
+                    G = px.exp_draw_fx(r0) // lam
+                    if G >= total - a:
+                        break
+                    a += G
+                    on_event(j * S + a // B, g, a % B, (0, r1, 0, 0))
+                    a += 1
+                    r = px.philox4x32_10(group, 0x80000000 | j, int(c2[0, g]), int(c3[0, g]) | (d << 15), self.k0, self.k1)
+                    r0, r1 = int(r[0]), int(r[1])
+                    d += 1
 
     def _flip(self, arr, g, shot):
         w = g * self.K * 4 + (shot >> 5)

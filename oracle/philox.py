@@ -20,9 +20,7 @@ W0 = 0x9E3779B9
 W1 = 0xBB67AE85
 MASK32 = np.uint64(0xFFFFFFFF)
 
-TAG_EVENT = 0x45564E54
 TAG_COLLAPSE = 0x434F4C4C
-TAG_CLOCK = 0x434C4F4B
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

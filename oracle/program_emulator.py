@@ -69,8 +69,7 @@ class Emulator:
         self.rec = np.zeros((n_rec, W), dtype=np.uint32)
         self.out = np.zeros((plan["num_det"] + plan["num_obs"], W), dtype=np.uint32)
         self.logical_of = read_qmap(self.w, plan)
-        self.clk = [0] * (self.Q + 1)       # exponential clocks, (re)armed per clock segment
-        self.clk_seg = [-1] * (self.Q + 1)
+        self.group_items = {}  # noise group -> sites of it seen so far (a group may span several batches)
         # race detector state: resource -> (slot that wrote, set of slots that read) since the last barrier
         self.writer = {}
         self.readers = {}
@@ -106,30 +105,28 @@ class Emulator:
     def flip(self, arr, shot):
         arr[shot >> 5] ^= np.uint32(1 << (shot & 31))
 
-    def run_site(self, clock, lam, group, on_event):
-        seg = group >> 5  # GSTIM_CLOCK_SEG_SHIFT
-        if self.clk_seg[clock] != seg:
-            r = px.philox4x32_10(self.logical_of[clock], seg, self.col0 & 0xFFFFFFFF, px.TAG_CLOCK ^ (self.col0 >> 32),
-                                 self.k0, self.k1)
-            self.clk[clock] = px.exp_draw_fx(int(r[0]))
-            self.clk_seg[clock] = seg
-        E = self.clk[clock]
-        pos, kev, B = 0, 0, self.B
-        while pos < B:
-            rem = min((B - pos) * lam, px.REM_SAT)
-            if E >= rem:
-                E -= rem
-                break
-            j = min(E // lam, B - pos - 1)
-            shot = pos + j
-            r = px.philox4x32_10(group, self.logical_of[clock] | (kev << 16), self.col0 & 0xFFFFFFFF, px.TAG_EVENT ^ (self.col0 >> 32),
-                                 self.k0, self.k1)
-            r = tuple(int(v) for v in r)
-            on_event(shot, r)
-            E = px.exp_draw_fx(r[0])
-            pos = shot + 1
-            kev += 1
-        self.clk[clock] = E
+    def run_batch(self, group, lam, evs):
+        """Noise sites of one batch (evs[i](shot, r) = event callback of item i); see frame_oracle.run_sites."""
+        n, S, B = len(evs), 16, self.B  # GSTIM_NOISE_SLICE
+        gfirst = self.group_items.get(group, 0)
+        self.group_items[group] = gfirst + n
+        if lam == 0 or n == 0:
+            return
+        assert gfirst % S == 0, "a noise group was cut inside an RNG slice"
+        c2, hi = self.col0 & 0xFFFFFFFF, self.col0 >> 32
+        for i0 in range(0, n, S):
+            j = (gfirst + i0) // S
+            total = min(S, n - i0) * B
+            a = d = 0
+            while True:
+                r = px.philox4x32_10(group, 0x80000000 | j, c2, hi | (d << 15), self.k0, self.k1)
+                d += 1
+                G = px.exp_draw_fx(int(r[0])) // lam
+                if G >= total - a:
+                    break
+                a += G
+                evs[i0 + a // B](a % B, (0, int(r[1]), 0, 0))
+                a += 1
 
     def collapse(self, mgroup, q):
         cols = np.uint64(self.col0) + np.arange(self.K, dtype=np.uint64)
@@ -185,6 +182,7 @@ class Emulator:
                     o = [(v[0] & m[4 * k]) ^ (v[1] & m[4 * k + 1]) ^ (v[2] & m[4 * k + 2]) ^ (v[3] & m[4 * k + 3]) for k in range(4)]
                     self.x[q1], self.z[q1], self.x[q2], self.z[q2] = o
             elif op == OP_NOISE1:
+                evs = []
                 for i in range(n):
                     q = extra - 1 if flags & F_NOFRAME else int(pay[i])
                     self.touch(i % S, ("clk",) if q == Q else q, True)
@@ -202,10 +200,12 @@ class Emulator:
                         if flags & F_REC:
                             self.flip(self.rec[(rec0 + i) & self.rec_mask], shot)
 
-                    self.run_site(q, lam, site0, ev)
+                    evs.append(ev)
+                self.run_batch(site0, lam, evs)
             elif op == OP_NOISE2:
                 table = [int(v) for v in pay[:15]] if flags & F_TABLE else None
                 items = pay[15:] if flags & F_TABLE else pay
+                evs = []
                 for i in range(n):
                     q1, q2 = int(items[i]) & 0xFFFF, int(items[i]) >> 16
                     self.touch(i % S, q1, True)
@@ -228,7 +228,8 @@ class Emulator:
                             if on:
                                 self.flip(arr, shot)
 
-                    self.run_site(q1, lam, site0, ev)
+                    evs.append(ev)
+                self.run_batch(site0, lam, evs)
             elif op == OP_MEASURE:
                 basis, kind = aux & 3, (aux >> 2) & 3
                 for i in range(n):
@@ -303,8 +304,7 @@ class Emulator:
                             if fz:
                                 self.flip(self.z[q], shot)
 
-                if lam != 0:
-                    self.run_site(extra, lam, site0, ev)
+                self.run_batch(site0, lam, [ev])
             else:
                 raise ValueError(f"bad opcode {op} at word {pc}")
             if op in (OP_NOISE1, OP_NOISE2):

@@ -128,7 +128,7 @@ struct gstim_sampler {
     cudaStream_t copy_stream = nullptr;
     DevBuf d_dbg, d_prog, d_qmap, d_table, d_rec, d_rowmap, d_stage[2], d_counts;
     // noise schedule + per-CTA event scratch (interp.cu noise_prepass)
-    DevBuf d_noise_info, d_rates, d_qlist_off, d_qlist, d_segoff, d_ev_counts, d_ev_buf, d_ev_overflow, d_rounds;
+    DevBuf d_noise_info, d_rates, d_slices, d_segoff, d_ev_counts, d_ev_buf, d_ev_overflow;
     uint32_t n_rounds = 0, info_smem_bytes = 0;
     uint32_t segoff_K = 0;
     uint32_t n_noise = 0;
@@ -275,8 +275,7 @@ void configure(gstim_sampler *s) {
         };
         up(s->d_noise_info, ns.info.data(), ns.info.size() * 4);
         up(s->d_rates, ns.rates.data(), ns.rates.size() * 8);
-        up(s->d_qlist_off, ns.chains.data(), ns.chains.size() * 4);
-        up(s->d_qlist, ns.qlist.data(), ns.qlist.size() * 8);
+        up(s->d_slices, ns.slices.data(), ns.slices.size() * 4);
         s->d_ev_overflow.ensure(16);
         CK(cudaMemset(s->d_ev_overflow.p, 0, 16));
     }
@@ -402,35 +401,17 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         CK(cudaMemcpy(s->d_segoff.p, segoff.data(), segoff.size() * 4, cudaMemcpyHostToDevice));
         s->segoff_K = K;
         s->ev_total = total;
-        // pre-pass rounds: consecutive chains (one per thread) whose site entries fit the frame scratch
-        const NoiseSchedule &ns = s->lc.noise;
         const size_t frame_bytes = (size_t)2 * K * q_pitch * 16;
-        s->info_smem_bytes = (n_noise * GSTIM_NOISE_INFO_WORDS * 4 <= 32768 && n_noise * GSTIM_NOISE_INFO_WORDS * 4 + 4096 <= frame_bytes)
+        s->info_smem_bytes = (n_noise * GSTIM_NOISE_INFO_WORDS * 4 <= 65536 && n_noise * GSTIM_NOISE_INFO_WORDS * 4 <= frame_bytes)
                                  ? n_noise * GSTIM_NOISE_INFO_WORDS * 4
                                  : 0;
-        const size_t cap_entries = (frame_bytes - s->info_smem_bytes) / 8 - 2;
-        std::vector<uint32_t> rounds{0};
-        const uint32_t n_chains = (uint32_t)(ns.chains.size() / 4);
-        uint32_t c = 0;
-        while (c < n_chains) {
-            const uint32_t e0 = ns.chains[4 * c + 2] & ~1u;
-            uint32_t c1 = c;
-            while (c1 < n_chains && c1 - c < s->threads && ns.chains[4 * c1 + 2] + ns.chains[4 * c1 + 3] - e0 <= cap_entries) {
-                c1++;
-            }
-            if (c1 == c) {
-                throw std::invalid_argument("internal: a noise chain does not fit the pre-pass scratch");
-            }
-            rounds.push_back(c1);
-            c = c1;
-        }
-        s->n_rounds = (uint32_t)rounds.size() - 1;
-        s->d_rounds.ensure(rounds.size() * 4);
-        CK(cudaMemcpy(s->d_rounds.p, rounds.data(), rounds.size() * 4, cudaMemcpyHostToDevice));
     }
     s->d_ev_counts.ensure(std::max<size_t>((size_t)grid_cap * n_noise * 4, 16));
     s->d_ev_buf.ensure(std::max<size_t>((size_t)grid_cap * s->ev_total * 4, 16));
 
+    if (s->next_col + total_blocks * K >= (1ull << 47)) {
+        throw std::invalid_argument("shot offset + shots must stay below 2^54");
+    }
     if (!s->call_start) {
         CK(cudaEventCreate(&s->call_start));
         CK(cudaEventCreate(&s->call_end));
@@ -455,15 +436,12 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         p.n_blocks = (uint32_t)nb;
         p.max_items = s->plan.max_items;
         p.n_noise = n_noise;
-        p.n_rates = (uint32_t)s->lc.noise.rates.size();
+        p.n_rates = (uint32_t)(s->lc.noise.rates.size() / 2);
         p.noise_info = (const uint32_t *)s->d_noise_info.p;
-        p.rates = (const unsigned long long *)s->d_rates.p;
-        p.chains = (const uint32_t *)s->d_qlist_off.p;
-        p.n_chains = (uint32_t)(s->lc.noise.chains.size() / 4);
-        p.rounds = (const uint32_t *)s->d_rounds.p;
-        p.n_rounds = s->n_rounds;
+        p.rates = (const ulonglong2 *)s->d_rates.p;
+        p.slices = (const uint4 *)s->d_slices.p;
+        p.n_slices = (uint32_t)(s->lc.noise.slices.size() / 4);
         p.info_smem_bytes = s->info_smem_bytes;
-        p.qlist = (const uint64_t *)s->d_qlist.p;
         p.ev_segoff = (const uint32_t *)s->d_segoff.p;
         p.ev_counts = (uint32_t *)s->d_ev_counts.p;
         p.ev_buf = (uint32_t *)s->d_ev_buf.p;
@@ -514,7 +492,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
             tot += h[i];
         }
         fprintf(stderr, "[gstim cycles, block 0, last launch] total %llu\n", tot);
-        fprintf(stderr, "  prepass(thread 0): bulk wait %llu, own chains %llu, round barrier wait %llu cyc; events %llu, skips %llu, rounds %llu\n", h[24], h[25], h[26], h[27], h[28], h[29]);
+        fprintf(stderr, "  prepass(thread 0): %llu cyc; events %llu, slices %llu, iterations %llu\n", h[25], h[27], h[28], h[29]);
         for (int i = 0; i < 13; i++) {
             if (h[i]) {
                 fprintf(stderr, "  %-9s %10llu cyc (%5.1f%%)  %6llu batches  %8.0f cyc/batch\n", names[i], h[i], 100.0 * h[i] / tot, h[16 + i], h[16 + i] ? (double)h[i] / h[16 + i] : 0.0);

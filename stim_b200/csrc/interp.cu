@@ -128,13 +128,15 @@ struct __align__(16) BlockCtx {
     uint32_t *ev_counts;        // this CTA's event counters
     uint32_t *ev_buf;           // this CTA's event records
     // noise schedule (read by the pre-pass)
-    const uint64_t *qlist;
-    const uint32_t *chains, *noise_info, *prog;
+    const uint4 *slices;
+    const ulonglong2 *rates;
+    const uint32_t *noise_info, *prog;
     uint32_t *ev_overflow;
-    const uint32_t *rounds;   // chain index boundaries of the pre-pass rounds (n_rounds + 1)
-    uint32_t n_rounds, info_smem_bytes;
-    uint32_t pre_mbar_s, pre_phase;
-    uint32_t n_chains, pad1;
+    uint32_t n_slices, info_smem_bytes;
+    uint32_t n_noise, pad3;
+    uint32_t next_s;                   // shared counter the pre-pass threads claim chains from
+    uint32_t ev_counts_s, ev_segoff_s; // shared-window addresses of the event counters / segment offsets (0: global)
+    uint32_t stage_s;                  // 2 x GSTIM_EV_STAGE event records prefetched for the current / next noise batch
     unsigned long long *dbg;  // optional cycle counters (block 0 only)
     uint32_t dbg_flags, pad2;
 };
@@ -146,10 +148,11 @@ size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chun
     b += (size_t)K * 16;                // correlated-error flag row
     b += (size_t)2 * chunk_words * 4;   // program ring
     b += 512 * 4;                       // log2 table
-    b += 128 * 8;                       // per rate class: need, rate, 2^64/need, 2^64/rate
+    b += 128 * 8;                       // the first GSTIM_RATE_SMEM_MAX rates: lam, floor((2^64 - 1) / lam)
     if (n_noise <= GSTIM_EV_SMEM_MAX) {
         b += ((size_t)(2 * n_noise + 1) * 4 + 15) / 16 * 16;  // event counters + segment offsets
     }
+    b += 2 * GSTIM_EV_STAGE * 4;        // staged event records of the current / next noise batch
     b += 32;                            // mbarriers
     b += (sizeof(BlockCtx) + 15) / 16 * 16;
     return b;
@@ -185,222 +188,177 @@ __device__ __forceinline__ void flip_rec(const BlockCtx *bc, uint32_t rec_index,
 
 // ------------------------------------------------------------------------------------------------
 // Noise event pre-pass. Event positions and Pauli choices never depend on the frame, so before a shot block
-// is interpreted every noise site of the whole program is sampled up front: one thread per clock row walks
-// that row's site list (program.h "Noise schedule") with the row's exponential clock in registers and leaves
-// compact event records in this CTA's (L2-resident) scratch, one segment per noise batch. The interpreter
-// then only applies flips. Lanes run a small state machine (skip sites / emit one event) so a warp issues
-// event work for all 32 lanes instead of waiting on the one lane in five that has an event at a given site.
+// is interpreted every noise site of the whole program is sampled up front. The sites of a noise group are
+// cut into slices of GSTIM_NOISE_SLICE sites (program.h "Noise schedule"); a slice x this shot block is one
+// Bernoulli sequence with its own Philox stream. Threads claim slices from a shared counter and walk them with
+// geometric gaps: every loop iteration is one Philox draw -> the gap to the slice's next event and that
+// event's Pauli word, so all lanes of a warp do the same work each iteration and idle only at the very end.
+// Lanes of a warp work on neighbouring slices, i.e. mostly on the same noise batch: they append their events
+// with one counter update per warp and contiguous (coalesced) stores into this CTA's (L2-resident) scratch,
+// one segment per noise batch. The interpreter then only applies flips.
 //
 // Distribution == RareErrorIterator (/root/reference/src/stim/util_bot/probability_util.cc:33-43):
 // gaps are floor(Exp(1)/lambda) = Geometric(p), in exact integer arithmetic (unit 2^-56 nat).
-// Philox counter of the k-th event of a site: (noise group, logical clock row | k << 16, col0 lo, TAG_EVENT ^ col0 hi).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void noise_prepass(BlockCtx *bc) {
-    const uint32_t *chains = bc->chains, *logical_of = bc->logical_of, *rounds = bc->rounds;
-    const uint32_t n_rounds = bc->n_rounds;
-    const uint32_t B = bc->B, lt_s = bc->lt_s, needs_s = bc->needs_s;
-    const uint32_t k0 = bc->k0, k1 = bc->k1, col0_lo = bc->col0_lo, col0_hi = bc->col0_hi;
-    uint32_t *counts = bc->ev_counts;
-    const uint32_t *segoff = bc->ev_segoff;
-    uint32_t *evbuf = bc->ev_buf;
-    const uint32_t tid = threadIdx.x;
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t a, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
 
-    // The frame planes are not in use yet (the program starts by resetting every qubit), so they serve as
-    // scratch: [noise info records (when they fit)] [site entries of the current round of chains].
-    const uint32_t info_bytes = bc->info_smem_bytes;
-    const uint32_t info_s = bc->X_s, ent_s = bc->X_s + info_bytes;
+// floor(E / lam) with inv = floor((2^64 - 1) / lam): the multiply-high estimate is never above and at most one below.
+__device__ __forceinline__ unsigned long long div_by_rate(unsigned long long E, unsigned long long lam, unsigned long long inv) {
+    unsigned long long q = __umul64hi(E, inv);
+    if (E - q * lam >= lam) {
+        q++;
+    }
+    return q;
+}
+
+__device__ __noinline__ void noise_prepass(BlockCtx *bc) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    // The frame planes are not in use yet (the program starts by resetting every qubit), so they hold the
+    // noise info records when those fit.
+    const uint32_t info_bytes = bc->info_smem_bytes, info_s = bc->X_s;
     const uint32_t *info_g = bc->noise_info;
     for (uint32_t i = tid; i < info_bytes / 4; i += blockDim.x) {
         sts32(info_s + 4 * i, info_g[i]);
     }
-    const uint32_t bar = bc->pre_mbar_s;
-    uint32_t phase = bc->pre_phase;
+    const uint32_t next_s = bc->next_s;
+    if (tid == 0) {
+        sts32(next_s, 0);
+    }
     __syncthreads();
 
+    const uint4 *slices = bc->slices;
+    const ulonglong2 *rates_g = bc->rates;
+    const uint32_t n_slices = bc->n_slices;
+    const uint32_t B = bc->B, lt_s = bc->lt_s, rates_s = bc->needs_s;
+    const uint32_t magicB = 0xFFFFFFFFu / B + 1;  // floor(a / B) == umulhi(a, magicB) for a < 2^20 (B <= 4096)
+    const uint32_t k0 = bc->k0, k1 = bc->k1, col0_lo = bc->col0_lo, col0_hi = bc->col0_hi;
+    const uint32_t cnt_s = bc->ev_counts_s, segoff_s = bc->ev_segoff_s;
+    uint32_t *counts = bc->ev_counts;
+    const uint32_t *segoff = bc->ev_segoff;
+    uint32_t *evbuf = bc->ev_buf;
+
     unsigned long long *dbg = tid == 0 ? bc->dbg : nullptr;
-    long long tA = clock64();
-    unsigned long long n_ev = 0, n_skip = 0;
-    for (uint32_t r = 0; r < n_rounds; r++) {
-        const uint32_t c0 = rounds[r], c1 = rounds[r + 1];
-        const uint32_t e0 = chains[4 * (size_t)c0 + 2] & ~1u;
-        const uint32_t e1 = chains[4 * (size_t)(c1 - 1) + 2] + chains[4 * (size_t)(c1 - 1) + 3];
-        const uint32_t bytes = ((e1 - e0) * 8 + 15) & ~15u;
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(ent_s, bc->qlist + e0, bytes, bar);
-        }
-        while (!mbar_try_wait(bar, phase)) {
-        }
-        phase ^= 1;
-        if (dbg) {
-            long long t = clock64();
-            dbg[24] += (unsigned long long)(t - tA);  // bulk-copy wait
-            tA = t;
-        }
-        if (c0 + tid < c1) {
-            const uint4 ch = *reinterpret_cast<const uint4 *>(chains + 4 * (size_t)(c0 + tid));  // row, segment | flags, begin, len
-            uint32_t ea = ent_s + 8 * (ch.z - e0);
-            const uint32_t ea_end = ea + 8 * ch.w;
-            const uint32_t lrow = logical_of[ch.x];
-            const bool uniform = (ch.y >> 31) != 0;  // every site of the chain has rate class ucls
-            const uint32_t ucls = (ch.y >> 26) & 31u;
-            const uint32_t seg = uniform ? (ch.y & 0x3FFFFFFu) : ch.y;
-            unsigned long long E;
-            {
-                const uint4 rr = philox4x32_10(lrow, seg, col0_lo, GTAG_CLOCK ^ col0_hi, k0, k1);  // (re)arm the clock
-                E = exp_draw_fx(rr.x, lt_s);
+    const long long tA = clock64();
+    unsigned long long n_ev = 0, n_iter = 0, n_sl = 0;
+
+    uint32_t grp = 0, sl1 = 0, nbi = 0, item0 = 0, total = 0, a = 0, d = 0;
+    unsigned long long lam = 1, inv = 0;
+    // the next slice is claimed and its descriptor fetched while the current one is walked
+    uint32_t nidx = atom_add_shared(next_s, 1);
+    uint4 nd = make_uint4(0, 0, 0, 0);
+    if (nidx < n_slices) {
+        nd = __ldg(slices + nidx);
+    }
+    bool have = false;
+    while (true) {
+        if (!have) {
+            if (nidx >= n_slices) {
+                break;
             }
-            uint32_t pos = 0, kev = 0;
-            while (true) {
-                // ---- skip phase: fast-forward over sites until this lane has an event pending, so that when the
-                // warp reconverges every live lane has event work
-                unsigned long long entry = 0, lam = 0;
-                uint32_t cls = 31;
-                bool pending = false;
-                while (ea < ea_end) {
-                    if (pos == 0 && uniform) {
-                        // all sites ahead consume the same amount: jump floor(E / need) of them at once
-                        const unsigned long long need = lds64(needs_s + 8 * ucls);
-                        if (E >= need) {
-                            unsigned long long n = __umul64hi(E, lds64(needs_s + 512 + 8 * ucls));  // ~ E / need (never above)
-                            while ((n + 1) * need <= E) {
-                                n++;
-                            }
-                            const unsigned long long room = (ea_end - ea) >> 3;
-                            n = n < room ? n : room;
-                            n_skip += n;
-                            E -= n * need;
-                            ea += 8 * (uint32_t)n;
-                            continue;
-                        }
-                        entry = lds64(ea);
-                        cls = ucls;
-                        lam = lds64(needs_s + 256 + 8 * cls);
-                        pending = true;
+            grp = nd.x;
+            sl1 = nd.y | GSTIM_SLICE_FLAG;
+            nbi = nd.z & 0xFFFFu;
+            item0 = nd.w & 0x7FFu;
+            total = (nd.w >> 11) * B;
+            a = 0;
+            d = 0;
+            const uint32_t ri = nd.z >> 16;
+            if (ri < GSTIM_RATE_SMEM_MAX) {
+                lam = lds64(rates_s + 16 * ri);
+                inv = lds64(rates_s + 16 * ri + 8);
+            } else {
+                const ulonglong2 r = __ldg(rates_g + ri);
+                lam = r.x;
+                inv = r.y;
+            }
+            have = true;
+            n_sl++;
+            nidx = atom_add_shared(next_s, 1);
+            if (nidx < n_slices) {
+                nd = __ldg(slices + nidx);
+            }
+        }
+        n_iter++;
+        const uint4 rr = philox4x32_10(grp, sl1, col0_lo, col0_hi | (d << GSTIM_DRAW_SHIFT), k0, k1);
+        d++;
+        const unsigned long long E = exp_draw_fx(rr.x, lt_s);
+        const unsigned long long G = div_by_rate(E, lam, inv);
+        if (G >= (unsigned long long)(total - a)) {  // no further event in this slice
+            have = false;
+            continue;
+        }
+        // ---- exactly one event, at shot-site a + G of the slice
+        a += (uint32_t)G;
+        const uint32_t site = __umulhi(a, magicB), shot = a - site * B;
+        a++;
+        const uint32_t h0 = info_bytes ? lds32(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4)) : __ldg(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS);
+        const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
+        uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
+        if (op == GOP_NOISE1) {
+            uint4 i1;  // (group, t1, t2, t3)
+            if (info_bytes) {
+                i1 = lds128(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4) + 16);
+            } else {
+                i1 = __ldg(reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + 4));
+            }
+            const uint32_t v = rr.y;
+            const uint32_t sel = v < i1.y ? 0u : v < i1.z ? 2u : v < i1.w ? 4u : 6u;
+            f = (aux >> sel) & 3u;
+            if (flags & GF_REC) {
+                f |= 16u;
+            }
+        } else if (op == GOP_NOISE2) {
+            if (!(flags & GF_TABLE)) {
+                f = 1u + __umulhi(rr.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
+            } else {
+                const uint32_t *tab = bc->prog + __ldg(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + GNI_TABLE_OFF);
+                uint32_t pr = aux;
+                for (uint32_t t = 0; t < 15; t++) {
+                    if (rr.y < __ldg(tab + t)) {
+                        pr = t + 1;
                         break;
                     }
-                    entry = lds64(ea);
-                    cls = ((uint32_t)entry >> 27) & 31u;
-                    unsigned long long rem;
-                    if (cls < 31) {
-                        lam = lds64(needs_s + 256 + 8 * cls);
-                        rem = pos == 0 ? lds64(needs_s + 8 * cls) : sat_mul(B - pos, lam);
-                    } else {
-                        const uint32_t *info = info_g + (size_t)(((uint32_t)entry >> 11) & 0xFFFF) * GSTIM_NOISE_INFO_WORDS;
-                        lam = ((unsigned long long)info[GNI_LAM_HI] << 32) | info[GNI_LAM_LO];
-                        rem = sat_mul(B - pos, lam);
-                    }
-                    if (E >= rem) {  // no (further) event at this site in this block
-                        n_skip++;
-                        E -= rem;
-                        ea += 8;
-                        pos = 0;
-                        kev = 0;
-                        continue;
-                    }
-                    pending = true;
-                    break;
                 }
-                if (!pending) {
-                    break;
-                }
-                // ---- event phase: exactly one event
-                const uint32_t nbi = ((uint32_t)entry >> 11) & 0xFFFF;
-                uint4 i0, i1;  // (h0, n, lam lo, lam hi), (group, t1, t2, t3)
-                if (info_bytes) {
-                    i0 = lds128(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4));
-                    i1 = lds128(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4) + 16);
-                } else {
-                    i0 = *reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS);
-                    i1 = *reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + 4);
-                }
-                // j = floor(E / lam), clamped to the shots left
-                const uint32_t left = B - pos - 1;
-                uint32_t j;
-                if (cls < 31) {
-                    unsigned long long q = __umul64hi(E, lds64(needs_s + 768 + 8 * cls));  // reciprocal estimate, never above
-                    while ((q + 1) * lam <= E) {
-                        q++;
-                    }
-                    j = q >= left ? left : (uint32_t)q;
-                } else {
-                    const float est = __ull2float_rz(E) / __ull2float_rn(lam);
-                    j = est >= (float)left ? left : (uint32_t)est;
-                    while (j > 0 && (unsigned long long)j * lam > E) {
-                        j--;
-                    }
-                    while (j < left && (unsigned long long)(j + 1) * lam <= E) {
-                        j++;
-                    }
-                }
-                const uint32_t shot = pos + j;
-                const uint4 rr = philox4x32_10((uint32_t)(entry >> 32), lrow | (kev << 16), col0_lo, GTAG_EVENT ^ col0_hi, k0, k1);
-                // which Paulis flip
-                const uint32_t h0 = i0.x;
-                const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
-                uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
-                if (op == GOP_NOISE1) {
-                    const uint32_t v = rr.y;
-                    const uint32_t sel = v < i1.y ? 0u : v < i1.z ? 2u : v < i1.w ? 4u : 6u;
-                    f = (aux >> sel) & 3u;
-                    if (flags & GF_REC) {
-                        f |= 16u;
-                    }
-                } else if (op == GOP_NOISE2) {
-                    if (!(flags & GF_TABLE)) {
-                        f = 1u + __umulhi(rr.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
-                    } else {
-                        const uint32_t *tab = bc->prog + info_g[(size_t)nbi * GSTIM_NOISE_INFO_WORDS + GNI_TABLE_OFF];
-                        uint32_t pr = aux;
-                        for (uint32_t t = 0; t < 15; t++) {
-                            if (rr.y < tab[t]) {
-                                pr = t + 1;
-                                break;
-                            }
-                        }
-                        // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
-                        const uint32_t c1p = pr >> 2, c2p = pr & 3u;
-                        f = (((c1p + 1) >> 1) & 1u) | ((c1p >> 1) << 1) | ((((c2p + 1) >> 1) & 1u) << 2) | ((c2p >> 1) << 3);
-                    }
-                }
-                const uint32_t seg0 = segoff[nbi], cap = segoff[nbi + 1] - seg0;
-                const uint32_t at = atomicAdd(&counts[nbi], 1u);
-                if (at < cap) {
-                    evbuf[seg0 + at] = shot | (((uint32_t)entry & GSTIM_EV_ITEM_MASK) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
-                } else {
-                    *bc->ev_overflow = 1u;
-                }
-                n_ev++;
-                E = exp_draw_fx(rr.x, lt_s);
-                pos = shot + 1;
-                kev++;
-                if (pos >= B) {
-                    ea += 8;
-                    pos = 0;
-                    kev = 0;
-                }
+                // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
+                const uint32_t c1p = pr >> 2, c2p = pr & 3u;
+                f = (((c1p + 1) >> 1) & 1u) | ((c1p >> 1) << 1) | ((((c2p + 1) >> 1) & 1u) << 2) | ((c2p >> 1) << 3);
             }
         }
-        if (dbg) {
-            long long t = clock64();
-            dbg[25] += (unsigned long long)(t - tA);  // own chain
-            tA = t;
+        // warp-aggregated append: the lanes that have an event for the same noise batch take consecutive places
+        const unsigned act = __activemask();
+        const unsigned peers = __match_any_sync(act, nbi);
+        const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0, seg0, cap;
+        if (cnt_s) {
+            seg0 = lds32(segoff_s + 4 * nbi);
+            cap = lds32(segoff_s + 4 * nbi + 4) - seg0;
+            if (lane == leader) {
+                base = atom_add_shared(cnt_s + 4 * nbi, __popc(peers));
+            }
+        } else {
+            seg0 = segoff[nbi];
+            cap = segoff[nbi + 1] - seg0;
+            if (lane == leader) {
+                base = atomicAdd(&counts[nbi], __popc(peers));
+            }
         }
-        __syncthreads();  // the entry scratch is reused by the next round
-        if (dbg) {
-            long long t = clock64();
-            dbg[26] += (unsigned long long)(t - tA);  // waiting for the slowest chain of the round
-            tA = t;
+        const uint32_t at = __shfl_sync(peers, base, leader) + rank;
+        if (at < cap) {
+            evbuf[seg0 + at] = shot | ((item0 + site) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
+        } else {
+            *bc->ev_overflow = 1u;
         }
+        n_ev++;
     }
     if (dbg) {
+        dbg[25] += (unsigned long long)(clock64() - tA);
         dbg[27] += n_ev;
-        dbg[28] += n_skip;
-        dbg[29] += n_rounds;
-    }
-    if (tid == 0) {
-        bc->pre_phase = phase;
+        dbg[28] += n_sl;
+        dbg[29] += n_iter;
     }
 }
 
@@ -481,8 +439,22 @@ __device__ __forceinline__ void atom_flip_plane(const BlockCtx *bc, uint32_t pla
     const uint32_t a = plane_s + (shot >> 7) * bc->pitch_b + row * 16 + ((shot >> 5) & 3) * 4;
     asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(1u << (shot & 31)) : "memory");
 }
+// Event records of noise batch `nbi` -> staging buffer (nbi & 1), asynchronously (LDGSTS): thread t copies the
+// records it will apply itself, so no barrier is needed between the copy and the use. One group per call.
+__device__ __forceinline__ void prefetch_events(const BlockCtx *bc, uint32_t nbi) {
+    if (nbi < bc->n_noise) {
+        const uint32_t seg0 = bc->ev_segoff[nbi], cap = bc->ev_segoff[nbi + 1] - seg0;
+        const uint32_t cnt = min(min(bc->ev_counts[nbi], cap), GSTIM_EV_STAGE);
+        const uint32_t *ev = bc->ev_buf + seg0;
+        const uint32_t st = bc->stage_s + (nbi & 1u) * (GSTIM_EV_STAGE * 4);
+        for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(st + 4 * e), "l"(ev + e) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __device__ __noinline__ void op_noise(const BlockCtx *bc, const uint32_t *hdr) {
-    __syncthreads();
     const uint32_t h0 = hdr[GH_OP];
     const uint32_t flags = (h0 >> 8) & 0xFF;
     const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
@@ -492,8 +464,12 @@ __device__ __noinline__ void op_noise(const BlockCtx *bc, const uint32_t *hdr) {
     const uint32_t cnt = min(bc->ev_counts[nbi], cap);
     const uint32_t *ev = bc->ev_buf + seg0;
     const uint32_t X_s = bc->X_s, Z_s = bc->Z_s;
+    const uint32_t st = bc->stage_s + (nbi & 1u) * (GSTIM_EV_STAGE * 4);
+    prefetch_events(bc, nbi + 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's records have landed
+    __syncthreads();
     for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
-        const uint32_t rec = ev[e];
+        const uint32_t rec = e < GSTIM_EV_STAGE ? lds32(st + 4 * e) : ev[e];
         const uint32_t shot = rec & ((1u << GSTIM_EV_SHOT_BITS) - 1);
         const uint32_t item = (rec >> GSTIM_EV_ITEM_SHIFT) & GSTIM_EV_ITEM_MASK;
         const uint32_t f = rec >> GSTIM_EV_FLIP_SHIFT;
@@ -556,7 +532,7 @@ __device__ __noinline__ void op_measure(const BlockCtx *bc, const uint32_t *hdr)
             }
             sts128(ax, nx);
             sts128(ax + zoff, nz);
-            if (kind != GK_R) {
+            if (kind != GK_R && !(bc->dbg_flags & 64u)) {
                 rrow[k] = m;
             }
         }
@@ -588,8 +564,9 @@ __device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr)
     // Record rows live in global memory (L2): keep up to 4 columns x 2 rows of loads in flight per thread
     // instead of one dependent load at a time.
     const uint32_t G = 1u << G_log2;
+    const uint32_t dbgf = bc->dbg_flags;
     for (uint32_t i = slot; i < n; i += slots) {
-        const uint32_t b0 = off[i], b1 = off[i + 1];
+        const uint32_t b0 = off[i], b1 = (dbgf & 16u) ? off[i] : off[i + 1];
         uint4 *orow = bc->out + (uint64_t)dst[i] * bc->out_row_stride;
         for (uint32_t k0 = sub; k0 < K; k0 += 4 * G) {
             uint4 acc[4];
@@ -629,7 +606,9 @@ __device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr)
                     if (flags & GF_ACCUM) {
                         acc[u] = xor4(acc[u], orow[k]);
                     }
-                    orow[k] = acc[u];
+                    if (!(dbgf & 32u)) {
+                        orow[k] = acc[u];
+                    }
                 }
             }
         }
@@ -682,6 +661,7 @@ __device__ __noinline__ void op_feedback(const BlockCtx *bc, const uint32_t *hdr
 // E / ELSE_CORRELATED_ERROR (frame_simulator.inl:747-776): one site for the whole Pauli product, masked by
 // (and recorded in) the block's "already occurred" row. Executed by a single thread from the pre-sampled events.
 __device__ __noinline__ void op_corr(const BlockCtx *bc, const uint32_t *hdr) {
+    prefetch_events(bc, hdr[GH_CSITE0] + 1);  // keeps the staging pipeline of op_noise going (this op reads its records directly)
     if (threadIdx.x != 0) {
         return;
     }
@@ -741,6 +721,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     if (ev_in_smem) {
         sp += ((size_t)(2 * p.n_noise + 1) * 4 + 15) / 16 * 16;
     }
+    const uint32_t stage_s = smem_u32(sp);
+    sp += 2 * GSTIM_EV_STAGE * 4;
     const uint32_t mbar_s = smem_u32(sp);
     sp += 32;
     BlockCtx *bc = (BlockCtx *)sp;
@@ -753,13 +735,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     if (tid == 0) {
         mbar_init(mbar_s, 1);
         mbar_init(mbar_s + 8, 1);
-        mbar_init(mbar_s + 16, 1);
-        bc->pre_mbar_s = mbar_s + 16;
+        bc->next_s = mbar_s + 16;
         bc->dbg_flags = p.dbg_flags;
         bc->dbg = blockIdx.x == 0 ? p.dbg_cycles : nullptr;
-        bc->pre_phase = 0;
-        bc->rounds = p.rounds;
-        bc->n_rounds = p.n_rounds;
         bc->info_smem_bytes = p.info_smem_bytes;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         bc->X_s = X_s;
@@ -768,9 +746,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         bc->lt_s = smem_u32(lt);
         bc->needs_s = needs_s;
         bc->ev_segoff = ev_in_smem ? ev_s + p.n_noise : p.ev_segoff;
-        bc->qlist = p.qlist;
-        bc->chains = p.chains;
-        bc->n_chains = p.n_chains;
+        bc->slices = p.slices;
+        bc->rates = p.rates;
+        bc->ev_counts_s = ev_in_smem ? smem_u32(ev_s) : 0u;
+        bc->ev_segoff_s = ev_in_smem ? smem_u32(ev_s + p.n_noise) : 0u;
+        bc->n_slices = p.n_slices;
+        bc->n_noise = p.n_noise;
+        bc->stage_s = stage_s;
         bc->noise_info = p.noise_info;
         bc->prog = p.prog;
         bc->ev_overflow = p.ev_overflow;
@@ -792,14 +774,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         lt[i] = GSTIM_LOG2_BASE[i];
         lt[256 + i] = GSTIM_LOG2_DIFF[i];
     }
-    for (uint32_t i = tid; i < p.n_rates; i += T) {
-        sts64(needs_s + 8 * i, sat_mul(p.K * GSTIM_COL_SHOTS, p.rates[i]));
-        sts64(needs_s + 256 + 8 * i, p.rates[i]);
-        {
-            const unsigned long long need = sat_mul(p.K * GSTIM_COL_SHOTS, p.rates[i]);
-            sts64(needs_s + 512 + 8 * i, need ? 0xFFFFFFFFFFFFFFFFull / need : 0ull);
-            sts64(needs_s + 768 + 8 * i, p.rates[i] ? 0xFFFFFFFFFFFFFFFFull / p.rates[i] : 0ull);
-        }
+    for (uint32_t i = tid; i < min(p.n_rates, GSTIM_RATE_SMEM_MAX); i += T) {
+        const ulonglong2 r = p.rates[i];
+        sts64(needs_s + 16 * i, r.x);
+        sts64(needs_s + 16 * i + 8, r.y);
     }
     if (ev_in_smem) {
         for (uint32_t i = tid; i <= p.n_noise; i += T) {
@@ -840,6 +818,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
             noise_prepass(bc);
         }
         __syncthreads();
+        prefetch_events(bc, 0);
 
         for (uint32_t chunk = 0;; chunk++) {
             const uint32_t b = chunk & 1;

@@ -32,14 +32,11 @@ struct InterpParams {
     unsigned long long *dbg_cycles;  // optional (GSTIM_DEBUG_CYCLES=1): [op] cycles and [16+op] batch counts seen by block 0
     // noise schedule (program.h) and the per-CTA event scratch the pre-pass fills
     uint32_t n_noise;                 // noise batches
-    uint32_t n_rates;                 // rate classes (<= 31)
+    uint32_t n_rates;                 // distinct rates
     const uint32_t *noise_info;       // n_noise * GSTIM_NOISE_INFO_WORDS
-    const unsigned long long *rates;  // n_rates fixed-point rates
-    const uint64_t *qlist;            // site entries (program.h "Noise schedule")
-    const uint32_t *chains;           // 4 words per chain: row, clock segment, first entry, length
-    uint32_t n_chains;
-    const uint32_t *rounds;           // n_rounds + 1 chain-index boundaries: a round's entries fit the pre-pass scratch
-    uint32_t n_rounds;
+    const ulonglong2 *rates;          // per rate: lam, floor((2^64 - 1) / lam)
+    const uint4 *slices;              // RNG slices (program.h "Noise schedule")
+    uint32_t n_slices;
     uint32_t info_smem_bytes;         // n_noise * 48 when the info records are staged in shared memory, else 0
     const uint32_t *ev_segoff;        // n_noise + 1 : event segment offsets for this launch's block size
     uint32_t *ev_counts;              // gridDim.x * n_noise

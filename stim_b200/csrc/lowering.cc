@@ -79,6 +79,10 @@ struct Lowerer {
     std::vector<uint32_t> rd_stamp, wr_stamp;
 
     explicit Lowerer(uint32_t max_words) : max_words(max_words) {}
+    uint32_t noise_cap() const {
+        const uint32_t room = max_words > 2 * GSTIM_HDR_WORDS + 15 + GSTIM_NOISE_SLICE ? max_words - 2 * GSTIM_HDR_WORDS - 15 : GSTIM_NOISE_SLICE;
+        return std::min<uint32_t>(GSTIM_MAX_BATCH_ITEMS, room) / GSTIM_NOISE_SLICE * GSTIM_NOISE_SLICE;
+    }
 
     uint32_t q_of(uint32_t target) const {
         uint32_t v = target & T_VALUE_MASK;
@@ -151,6 +155,9 @@ struct Lowerer {
         }
         if (ok && (cur.words() + n_item_words + GSTIM_HDR_WORDS > max_words || cur.n_items >= GSTIM_MAX_BATCH_ITEMS)) {
             ok = false;
+        }
+        if (ok && (cur.op == GOP_NOISE1 || cur.op == GOP_NOISE2) && cur.n_items >= noise_cap()) {
+            ok = false;  // a noise group is only ever cut at a multiple of the RNG slice size (program.h)
         }
         if (ok) {
             for (uint32_t i = 0; i < n_res; i++) {
@@ -902,7 +909,7 @@ void mark_used(const Circuit &c, std::vector<uint8_t> &used) {
 //   1. physical frame rows: qubits are renumbered so that, inside every two-qubit batch, both operand
 //      sets spread evenly over the 8 sixteen-byte bank groups of shared memory (row index mod 8);
 //      lc.logical_of[] keeps the logical (sorted) index that addresses the Philox counters.
-//   2. items of every gate/noise batch are reordered into groups of 8 (one quarter warp) whose rows
+//   2. items of every gate batch are reordered into groups of 8 (one quarter warp) whose rows
 //      are distinct mod 8 for each operand -> conflict-free LDS.128/STS.128. Groups are perfect matchings
 //      of the 8x8 (residue of operand 1, residue of operand 2) multigraph.
 // ---------------------------------------------------------------------------------------------
@@ -910,9 +917,6 @@ namespace {
 
 bool is_pair_op(const Batch &b) {
     return b.op == GOP_CLIFF2 || b.op == GOP_NOISE2;
-}
-bool is_single_op(const Batch &b) {
-    return b.op == GOP_CLIFF1 || (b.op == GOP_NOISE1 && !(b.flags & (GF_REC | GF_NOFRAME)));
 }
 size_t item_skip(const Batch &b) {
     return (b.op == GOP_NOISE2 && (b.flags & GF_TABLE)) ? 15 : 0;
@@ -1004,8 +1008,9 @@ bool try_augment(int u, const uint32_t cnt[8][8], int match_v[8], bool seen[8]) 
 }
 
 void spread_banks(Batch &b) {
-    const bool pairs = is_pair_op(b);
-    if (!pairs && !is_single_op(b)) {
+    // gate batches only: the item order of a noise batch is the site order its RNG slices are defined on
+    const bool pairs = b.op == GOP_CLIFF2;
+    if (!pairs && b.op != GOP_CLIFF1) {
         return;
     }
     const size_t skip = item_skip(b);
@@ -1207,18 +1212,19 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
     // physical clock row the ordered list of its noise sites.
     NoiseSchedule &ns = lc.noise;
     ns = NoiseSchedule();
-    std::vector<std::vector<uint64_t>> per_clock(lc.num_qubits + 1);
-    auto rate_class = [&](uint64_t lam) -> uint32_t {
-        for (size_t i = 0; i < ns.rates.size(); i++) {
+    std::vector<uint32_t> group_items(lc.num_sites + 1, 0);  // sites of each noise group serialised so far
+    auto rate_index = [&](uint64_t lam) -> uint32_t {
+        for (size_t i = 0; i < ns.rates.size(); i += 2) {
             if (ns.rates[i] == lam) {
-                return (uint32_t)i;
+                return (uint32_t)(i / 2);
             }
         }
-        if (ns.rates.size() < 31) {
-            ns.rates.push_back(lam);
-            return (uint32_t)ns.rates.size() - 1;
+        if (ns.rates.size() / 2 >= 65536) {
+            throw std::invalid_argument("Circuits with more than 65536 distinct noise probabilities are not supported by this build.");
         }
-        return 31;  // looked up through the info record
+        ns.rates.push_back(lam);
+        ns.rates.push_back(lam ? 0xFFFFFFFFFFFFFFFFull / lam : 0ull);
+        return (uint32_t)(ns.rates.size() / 2) - 1;
     };
 
     for (Batch &b : lc.batches) {
@@ -1325,65 +1331,24 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             ns.info.insert(ns.info.end(), info, info + GSTIM_NOISE_INFO_WORDS);
             ns.n_sites.push_back(info[GNI_N]);
             ns.lams.push_back(lb);
-            const uint32_t cls = rate_class(lb);
+            // RNG slices of this batch (program.h "Noise schedule"): GSTIM_NOISE_SLICE consecutive sites of the group each
+            if (b.site0 >= group_items.size()) {
+                group_items.resize((size_t)b.site0 + 1, 0);
+            }
+            const uint32_t gfirst = group_items[b.site0];
+            group_items[b.site0] += info[GNI_N];
             if (lb != 0) {
-                if (b.op == GOP_CORR) {
-                    per_clock[b.extra].push_back(((uint64_t)b.site0 << 32) | (cls << 27) | (nbi << 11));
-                } else {
-                    for (uint32_t i = 0; i < b.n_items; i++) {
-                        uint32_t clock = (b.flags & GF_NOFRAME) ? b.extra - 1 : (out[items_off + i] & 0xFFFF);
-                        per_clock[clock].push_back(((uint64_t)b.site0 << 32) | (cls << 27) | (nbi << 11) | i);
-                    }
+                const uint32_t rate = rate_index(lb);
+                if (gfirst % GSTIM_NOISE_SLICE != 0) {
+                    throw std::logic_error("internal: a noise group was cut inside an RNG slice");
+                }
+                for (uint32_t i0 = 0; i0 < info[GNI_N]; i0 += GSTIM_NOISE_SLICE) {
+                    const uint32_t cnt = std::min<uint32_t>(GSTIM_NOISE_SLICE, info[GNI_N] - i0);
+                    const uint32_t sl[4] = {b.site0, (gfirst + i0) / GSTIM_NOISE_SLICE, nbi | (rate << 16), i0 | (cnt << 11)};
+                    ns.slices.insert(ns.slices.end(), sl, sl + 4);
                 }
             }
         }
-    }
-    // Cut every clock row's site list into chains at clock-segment boundaries (a clock is re-armed whenever
-    // noise_group >> GSTIM_CLOCK_SEG_SHIFT changes, DESIGN.md "RNG addressing"); chains are independent, so the
-    // pre-pass deals them to threads longest-first for an even load.
-    struct Chain {
-        uint32_t row, seg, begin, len;
-    };
-    std::vector<Chain> chains;
-    for (uint32_t row = 0; row < per_clock.size(); row++) {
-        const auto &l = per_clock[row];
-        size_t i = 0;
-        while (i < l.size()) {
-            uint32_t seg = (uint32_t)(l[i] >> 32) >> GSTIM_CLOCK_SEG_SHIFT;
-            size_t j = i;
-            while (j < l.size() && ((uint32_t)(l[j] >> 32) >> GSTIM_CLOCK_SEG_SHIFT) == seg) {
-                j++;
-            }
-            chains.push_back({row, seg, (uint32_t)(ns.qlist.size()), (uint32_t)(j - i)});
-            ns.qlist.insert(ns.qlist.end(), l.begin() + (long)i, l.begin() + (long)j);
-            i = j;
-        }
-    }
-    std::stable_sort(chains.begin(), chains.end(), [](const Chain &a, const Chain &c) { return a.len > c.len; });
-    // store the entries in chain order, so a round of consecutive chains is one contiguous (bulk-copyable) range
-    {
-        std::vector<uint64_t> ordered;
-        ordered.reserve(ns.qlist.size());
-        for (Chain &c : chains) {
-            uint32_t nb = (uint32_t)ordered.size();
-            ordered.insert(ordered.end(), ns.qlist.begin() + c.begin, ns.qlist.begin() + c.begin + c.len);
-            c.begin = nb;
-        }
-        ns.qlist.swap(ordered);
-        ns.qlist.push_back(0);  // padding so 16-byte bulk copies never read past the end
-        ns.qlist.push_back(0);
-    }
-    for (const Chain &c : chains) {
-        ns.chains.push_back(c.row);
-        // bit 31 of the segment word: every site of the chain has the same (tabulated) rate class, stored in bits 26-30
-        uint32_t cls0 = ((uint32_t)ns.qlist[c.begin] >> 27) & 31u;
-        bool uniform = cls0 < 31 && c.seg < (1u << 26);
-        for (uint32_t i = 1; i < c.len && uniform; i++) {
-            uniform = (((uint32_t)ns.qlist[c.begin + i] >> 27) & 31u) == cls0;
-        }
-        ns.chains.push_back(uniform ? (c.seg | (cls0 << 26) | (1u << 31)) : c.seg);
-        ns.chains.push_back(c.begin);
-        ns.chains.push_back(c.len);
     }
     put_header(GOP_END, GSTIM_HDR_WORDS);
     out.resize((out.size() + chunk_words - 1) / chunk_words * (size_t)chunk_words, 0);

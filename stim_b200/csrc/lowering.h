@@ -39,9 +39,8 @@ struct NoiseSchedule {
     std::vector<uint32_t> info;       // GSTIM_NOISE_INFO_WORDS per noise batch
     std::vector<uint32_t> n_sites;    // per noise batch
     std::vector<uint64_t> lams;       // per noise batch (fixed-point rate)
-    std::vector<uint64_t> rates;      // distinct rates (rate classes 0..30)
-    std::vector<uint64_t> qlist;      // site entries: noise group << 32 | rate class << 27 | noise batch << 11 | item
-    std::vector<uint32_t> chains;     // 4 words per chain: physical clock row, clock segment, first entry, length (longest first)
+    std::vector<uint64_t> rates;      // distinct rates: 2 words each, lam and floor((2^64 - 1) / lam)
+    std::vector<uint32_t> slices;     // 4 words per RNG slice (program.h "Noise schedule"), in program order
 };
 
 struct LoweredCircuit {

@@ -75,17 +75,26 @@ enum GstimHdr : uint32_t {
 // NOISE1 aux: four 2-bit Pauli categories c0..c3 (bit0 = flip x, bit1 = flip z), c_j at bits 2j..2j+1.
 //   v = uniform u32;  v < T1 -> c0;  v < T2 -> c1;  v < T3 -> c2;  else c3.
 
-// Philox counter tags (4th counter word)
-#define GTAG_EVENT 0x45564E54u     // 'EVNT' per noise event:  ctr = (noise group, logical qubit | k_event<<16, col0, tag)
-#define GTAG_COLLAPSE 0x434F4C4Cu  // 'COLL' per collapse:     ctr = (measure group, logical qubit, global column, tag)
-#define GTAG_CLOCK 0x434C4F4Bu     // 'CLOK' clock (re)arming: ctr = (logical qubit, clock segment, col0, tag)
+// Philox counters (key = seed):
+//   collapse of a qubit:    (measure group, logical qubit, global column lo, 'COLL' ^ global column hi)
+//   draw d of a noise slice: (noise group, 0x80000000 | slice index in the group, col0 lo, col0 hi | d << 15)
+// col0 = global column of the shot block's first column (< 2^47).
+#define GTAG_COLLAPSE 0x434F4C4Cu
+#define GSTIM_SLICE_FLAG 0x80000000u
+#define GSTIM_DRAW_SHIFT 15u
 
 // Noise schedule: one info record per noise batch (NOISE1 / NOISE2 / CORR, numbered in program order; the
-// ordinal is stored in the batch header's GH_CSITE0 word), and per (clock row, clock segment) a chain of
-// its noise sites in program order, entry = noise group << 32 | rate class << 27 | noise batch ordinal << 11
-// | item index. The kernel's event pre-pass walks the chains (dealt to threads longest first) and leaves
-// compact event records for the interpreter:
+// ordinal is stored in the batch header's GH_CSITE0 word). The sites of a noise group (in target order) are
+// cut into SLICES of GSTIM_NOISE_SLICE consecutive sites; a slice x a shot block is one Bernoulli sequence
+// (site-major, then shot) walked with geometric gaps drawn from the slice's own Philox stream, like the
+// reference's RareErrorIterator over targets x shots. Lowering never cuts a group into batches inside a slice.
+//   slice (4 words): noise group, slice index in the group, noise batch ordinal | rate index << 16,
+//                    first item of the slice in its batch | number of sites << 11
+//   rate  (2 u64):   lam, floor((2^64 - 1) / lam)
+// The kernel's event pre-pass walks the slices and leaves compact event records for the interpreter:
 //   record = shot (bits 0-11) | item (12-22) | flips x1,z1,x2,z2 (23-26) | record flip (27).
+#define GSTIM_NOISE_SLICE 16u
+#define GSTIM_RATE_SMEM_MAX 64u    // the first 64 rates are mirrored in shared memory
 #define GSTIM_NOISE_INFO_WORDS 12u
 enum GstimNoiseInfo : uint32_t {
     GNI_H0 = 0,         // op | flags<<8 | aux<<16 of the batch
@@ -98,13 +107,12 @@ enum GstimNoiseInfo : uint32_t {
     GNI_T3 = 7,
     GNI_TABLE_OFF = 8,  // word offset of the 15 PAULI_CHANNEL_2 thresholds in the program (0 = none)
 };
-// A qubit's exponential clock is re-armed from Philox whenever noise_group >> GSTIM_CLOCK_SEG_SHIFT changes.
-#define GSTIM_CLOCK_SEG_SHIFT 5u
 #define GSTIM_EV_SHOT_BITS 12u
 #define GSTIM_EV_ITEM_SHIFT 12u
 #define GSTIM_EV_ITEM_MASK 0x7FFu
 #define GSTIM_EV_FLIP_SHIFT 23u
 #define GSTIM_MAX_BATCH_ITEMS 2047u
+#define GSTIM_EV_STAGE 512u      // event records per noise batch prefetched into shared memory
 #define GSTIM_EV_SMEM_MAX 2048u  // event counters / segment offsets live in shared memory up to this many noise batches
 
 // Plan: everything the kernel needs besides the program words.
