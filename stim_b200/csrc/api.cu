@@ -456,20 +456,20 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         p.col0_base = s->next_col + done_blocks * K;
         p.seed_lo = (uint32_t)s->seed;
         p.seed_hi = (uint32_t)(s->seed >> 32);
-        p.out_row_stride = nb * K;
+        p.out_k_stride = std::max<uint32_t>(rows, 1);
         p.rec_mask = s->mode == GSTIM_MODE_DETECTORS ? s->plan.rec_ring - 1 : 0xFFFFFFFFu;
         const uint32_t grid = (uint32_t)std::min<uint64_t>(nb, grid_cap);
         if (s->mode == GSTIM_MODE_DETECTORS) {
             p.out = (uint4 *)s->d_table.p;
             p.rec = (uint4 *)s->d_rec.p;
-            p.rec_row_stride = K;
+            p.rec_k_stride = s->plan.rec_ring;
             p.rec_block_stride = 0;
             p.rec_cta_stride = (uint64_t)s->plan.rec_ring * K;
         } else {
             p.out = nullptr;
             p.rec = (uint4 *)s->d_table.p;
-            p.rec_row_stride = nb * K;
-            p.rec_block_stride = K;
+            p.rec_k_stride = std::max<uint32_t>(rows, 1);
+            p.rec_block_stride = (uint64_t)K * std::max<uint32_t>(rows, 1);
             p.rec_cta_stride = 0;
         }
         cudaEvent_t e0 = get_event(s, ev++), e1 = get_event(s, ev++), e2 = get_event(s, ev++);
@@ -477,7 +477,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         CK(launch_interp(p, grid, s->threads, smem, s->stream));
         CK(cudaEventRecord(e1, s->stream));
         s->last_launches++;
-        sink(first_shot, chunk_shots, (const uint32_t *)s->d_table.p, (uint64_t)nb * K * 4);
+        sink(first_shot, chunk_shots, (const uint32_t *)s->d_table.p, (uint64_t)std::max<uint32_t>(rows, 1));
         CK(cudaEventRecord(e2, s->stream));
         done_blocks += nb;
     }
@@ -528,7 +528,7 @@ void upload_row_map(gstim_sampler *s, const std::vector<uint32_t> &m, size_t off
 void transpose_to(
     gstim_sampler *s,
     const uint32_t *table,
-    uint64_t row_words,
+    uint64_t n_rows,
     const uint32_t *d_map,
     uint32_t n_bits,
     uint64_t n_shots,
@@ -536,7 +536,7 @@ void transpose_to(
     uint64_t pitch) {
     TransposeParams t{};
     t.table = table;
-    t.row_words = row_words;
+    t.n_rows = n_rows;
     t.row_map = d_map;
     t.n_bits = n_bits;
     t.n_shots = n_shots;
@@ -565,12 +565,12 @@ void sample_to_device(
     upload_row_map(s, maps.main, 0);
     upload_row_map(s, maps.obs, nb_main);
     const uint32_t *dm = (const uint32_t *)s->d_rowmap.p;
-    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t row_words) {
+    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
         if (main_out && nb_main) {
-            transpose_to(s, table, row_words, dm, nb_main, n, main_out + first * main_pitch, main_pitch);
+            transpose_to(s, table, n_rows, dm, nb_main, n, main_out + first * main_pitch, main_pitch);
         }
         if (obs_out && nb_obs) {
-            transpose_to(s, table, row_words, dm + nb_main, nb_obs, n, obs_out + first * obs_pitch, obs_pitch);
+            transpose_to(s, table, n_rows, dm + nb_main, nb_obs, n, obs_out + first * obs_pitch, obs_pitch);
         }
     });
 }
@@ -688,16 +688,16 @@ void sample_to_host(
     };
 
     int cur = 0;
-    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t row_words) {
+    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
         drain(cur);  // buffer about to be reused
         s->d_stage[cur].ensure(n * stage_pitch + 16);
         uint8_t *dmain = (uint8_t *)s->d_stage[cur].p;
         uint8_t *dobs = dmain + n * main_bytes;
         if (nb_main) {
-            transpose_to(s, table, row_words, dm, nb_main, n, dmain, main_bytes);
+            transpose_to(s, table, n_rows, dm, nb_main, n, dmain, main_bytes);
         }
         if (nb_obs) {
-            transpose_to(s, table, row_words, dm + nb_main, nb_obs, n, dobs, obs_bytes);
+            transpose_to(s, table, n_rows, dm + nb_main, nb_obs, n, dobs, obs_bytes);
         }
         // copy on the second stream so the next chunk's interpreter overlaps the PCIe drain
         CK(cudaEventRecord(s->stage_ready[cur], s->stream));
@@ -814,7 +814,7 @@ void sample_to_file(
     std::vector<uint8_t> host;
     std::vector<uint32_t> host_table;
     auto emit = [&](const uint32_t *table,
-                    uint64_t row_words,
+                    uint64_t n_rows,
                     uint64_t n,
                     const std::vector<uint32_t> &m,
                     const uint32_t *d_m,
@@ -825,26 +825,25 @@ void sample_to_file(
                     char c2,
                     size_t tr) {
         if (of == Format::PTB64) {
-            uint32_t rows = n_rows_of(s);
-            host_table.resize((size_t)rows * row_words);
+            host_table.resize((size_t)((n + 127) / 128) * n_rows * 4);
             CK(cudaMemcpyAsync(host_table.data(), table, host_table.size() * 4, cudaMemcpyDeviceToHost, s->stream));
             CK(cudaStreamSynchronize(s->stream));
-            write_ptb64(out, host_table.data(), row_words, m.data(), m.size(), n);
+            write_ptb64(out, host_table.data(), n_rows, m.data(), m.size(), n);
         } else {
             s->d_stage[0].ensure(n * bytes + 16);
-            transpose_to(s, table, row_words, d_m, (uint32_t)m.size(), n, (uint8_t *)s->d_stage[0].p, bytes);
+            transpose_to(s, table, n_rows, d_m, (uint32_t)m.size(), n, (uint8_t *)s->d_stage[0].p, bytes);
             host.resize(n * bytes + 1);
             CK(cudaMemcpyAsync(host.data(), s->d_stage[0].p, n * bytes, cudaMemcpyDeviceToHost, s->stream));
             CK(cudaStreamSynchronize(s->stream));
             write_shots(out, host.data(), bytes, n, m.size(), of, c1, c2, tr);
         }
     };
-    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t row_words) {
+    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
         (void)first;
         if (obs_f && obs_map) {
-            emit(table, row_words, n, *obs_map, dm + nb, nbytes_o, obs_f, obs_fmt, 'L', 'L', nbo);
+            emit(table, n_rows, n, *obs_map, dm + nb, nbytes_o, obs_f, obs_fmt, 'L', 'L', nbo);
         }
-        emit(table, row_words, n, map, dm, nbytes, f, fmt, p1, p2, transition);
+        emit(table, n_rows, n, map, dm, nbytes, f, fmt, p1, p2, transition);
     });
     if (fflush(f) != 0 || (obs_f && fflush(obs_f) != 0)) {
         throw IoError("Failed to flush result data.");
@@ -1154,19 +1153,19 @@ int gstim_write_shots_to_fd(
             if (shots % 64 != 0) {
                 throw std::invalid_argument("shots must be a multiple of 64 to use ptb64 format.");
             }
-            const size_t row_words = shots / 32;
-            std::vector<uint32_t> table((size_t)n_bits * row_words, 0), map(n_bits);
+            const size_t n_cols = (shots + 127) / 128;
+            std::vector<uint32_t> table(n_cols * n_bits * 4, 0), map(n_bits);
             for (uint64_t sh = 0; sh < shots; sh++) {
                 for (uint64_t b = 0; b < n_bits; b++) {
                     if ((rows[sh * row_pitch + (b >> 3)] >> (b & 7)) & 1) {
-                        table[b * row_words + (sh >> 5)] |= 1u << (sh & 31);
+                        table[((sh >> 7) * n_bits + b) * 4 + ((sh >> 5) & 3)] |= 1u << (sh & 31);
                     }
                 }
             }
             for (uint64_t b = 0; b < n_bits; b++) {
                 map[b] = (uint32_t)b;
             }
-            write_ptb64(out.f, table.data(), row_words, map.data(), n_bits, shots);
+            write_ptb64(out.f, table.data(), n_bits, map.data(), n_bits, shots);
         } else {
             write_shots(out.f, rows, row_pitch, shots, n_bits, fmt, prefix1, prefix2, prefix_transition);
         }
@@ -1184,9 +1183,9 @@ int gstim_detector_flip_counts(gstim_sampler *s, uint64_t shots, uint64_t *count
         CK(cudaSetDevice(s->device));
         s->d_counts.ensure((size_t)std::max<uint32_t>(rows, 1) * 8);
         CK(cudaMemsetAsync(s->d_counts.p, 0, (size_t)rows * 8, s->stream));
-        run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t row_words) {
+        run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
             (void)first;
-            CK(launch_row_popcount(table, row_words, rows, n, (unsigned long long *)s->d_counts.p, s->stream));
+            CK(launch_row_popcount(table, n_rows, n, (unsigned long long *)s->d_counts.p, s->stream));
             s->last_launches++;
         });
         if (counts_dev) {

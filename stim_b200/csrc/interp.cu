@@ -122,7 +122,7 @@ struct __align__(16) BlockCtx {
     uint32_t rec_mask, pad0;
     uint4 *rec;               // this block's record rows
     uint4 *out;               // this block's output columns
-    uint64_t rec_row_stride, out_row_stride;  // in uint4
+    uint64_t rec_k_stride, out_k_stride;  // uint4 units between the 128-shot columns of a record / output row (rows are contiguous)
     const uint32_t *logical_of;
     const uint32_t *ev_segoff;  // event segment offsets per noise batch
     uint32_t *ev_counts;        // this CTA's event counters
@@ -182,7 +182,7 @@ __device__ __forceinline__ void flip_plane(const BlockCtx *bc, uint32_t plane_s,
     sts32(a, lds32(a) ^ (1u << (shot & 31)));
 }
 __device__ __forceinline__ void flip_rec(const BlockCtx *bc, uint32_t rec_index, uint32_t shot) {
-    uint32_t *w = (uint32_t *)(bc->rec + (uint64_t)(rec_index & bc->rec_mask) * bc->rec_row_stride + (shot >> 7)) + ((shot >> 5) & 3);
+    uint32_t *w = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + (rec_index & bc->rec_mask)) + ((shot >> 5) & 3);
     *w ^= 1u << (shot & 31);
 }
 
@@ -488,7 +488,7 @@ __device__ __noinline__ void op_noise(const BlockCtx *bc, const uint32_t *hdr) {
             atom_flip_plane(bc, Z_s, q2, shot);
         }
         if (f & 16u) {
-            uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)((rec0 + item) & bc->rec_mask) * bc->rec_row_stride + (shot >> 7)) + ((shot >> 5) & 3);
+            uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + ((rec0 + item) & bc->rec_mask)) + ((shot >> 5) & 3);
             atomicXor(rw, 1u << (shot & 31));
         }
     }
@@ -508,7 +508,8 @@ __device__ __noinline__ void op_measure(const BlockCtx *bc, const uint32_t *hdr)
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t q = pay[i];
         const uint32_t lq = bc->logical_of[q];
-        uint4 *rrow = bc->rec + (uint64_t)((rec0 + i) & bc->rec_mask) * bc->rec_row_stride;
+        uint4 *rrow = bc->rec + ((rec0 + i) & bc->rec_mask);
+        const uint64_t rks = bc->rec_k_stride;
         uint32_t ax = bc->X_s + q * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
             const uint64_t col = col0 + k;
@@ -533,7 +534,7 @@ __device__ __noinline__ void op_measure(const BlockCtx *bc, const uint32_t *hdr)
             sts128(ax, nx);
             sts128(ax + zoff, nz);
             if (kind != GK_R && !(bc->dbg_flags & 64u)) {
-                rrow[k] = m;
+                rrow[k * rks] = m;
             }
         }
     }
@@ -545,9 +546,9 @@ __device__ __noinline__ void op_reczero(const BlockCtx *bc, const uint32_t *hdr)
     (void)kstep;
     const uint32_t n = hdr[GH_N], rec0 = hdr[GH_REC0];
     for (uint32_t i = slot; i < n; i += slots) {
-        uint4 *rrow = bc->rec + (uint64_t)((rec0 + i) & bc->rec_mask) * bc->rec_row_stride;
+        uint4 *rrow = bc->rec + ((rec0 + i) & bc->rec_mask);
         for (uint32_t k = sub; k < K; k += 1u << G_log2) {
-            rrow[k] = make_uint4(0, 0, 0, 0);
+            rrow[k * bc->rec_k_stride] = make_uint4(0, 0, 0, 0);
         }
     }
 }
@@ -560,14 +561,14 @@ __device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr)
     const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
     const uint32_t *dst = pay, *off = pay + n, *idx = pay + 2 * n + 1;
     const uint4 *rec = bc->rec;
-    const uint64_t rrs = bc->rec_row_stride;
+    const uint64_t rks = bc->rec_k_stride, oks = bc->out_k_stride;
     // Record rows live in global memory (L2): keep up to 4 columns x 2 rows of loads in flight per thread
     // instead of one dependent load at a time.
     const uint32_t G = 1u << G_log2;
     const uint32_t dbgf = bc->dbg_flags;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t b0 = off[i], b1 = (dbgf & 16u) ? off[i] : off[i + 1];
-        uint4 *orow = bc->out + (uint64_t)dst[i] * bc->out_row_stride;
+        uint4 *orow = bc->out + dst[i];
         for (uint32_t k0 = sub; k0 < K; k0 += 4 * G) {
             uint4 acc[4];
 #pragma unroll
@@ -576,13 +577,13 @@ __device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr)
             }
             uint32_t j = b0;
             for (; j + 2 <= b1; j += 2) {
-                const uint4 *r0 = rec + (uint64_t)idx[j] * rrs, *r1 = rec + (uint64_t)idx[j + 1] * rrs;
+                const uint4 *r0 = rec + idx[j], *r1 = rec + idx[j + 1];
                 uint4 v0[4], v1[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const uint32_t k = k0 + u * G;
-                    v0[u] = k < K ? r0[k] : make_uint4(0, 0, 0, 0);
-                    v1[u] = k < K ? r1[k] : make_uint4(0, 0, 0, 0);
+                    v0[u] = k < K ? r0[k * rks] : make_uint4(0, 0, 0, 0);
+                    v1[u] = k < K ? r1[k * rks] : make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -590,12 +591,12 @@ __device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr)
                 }
             }
             if (j < b1) {
-                const uint4 *r0 = rec + (uint64_t)idx[j] * rrs;
+                const uint4 *r0 = rec + idx[j];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const uint32_t k = k0 + u * G;
                     if (k < K) {
-                        acc[u] = xor4(acc[u], r0[k]);
+                        acc[u] = xor4(acc[u], r0[k * rks]);
                     }
                 }
             }
@@ -604,10 +605,10 @@ __device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr)
                 const uint32_t k = k0 + u * G;
                 if (k < K) {
                     if (flags & GF_ACCUM) {
-                        acc[u] = xor4(acc[u], orow[k]);
+                        acc[u] = xor4(acc[u], orow[k * oks]);
                     }
                     if (!(dbgf & 32u)) {
-                        orow[k] = acc[u];
+                        orow[k * oks] = acc[u];
                     }
                 }
             }
@@ -622,17 +623,18 @@ __device__ __noinline__ void op_obs_pauli(const BlockCtx *bc, const uint32_t *hd
     const uint32_t zoff = bc->Z_s - bc->X_s;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[2 * i + 1];
-        uint4 *orow = bc->out + (uint64_t)pay[2 * i] * bc->out_row_stride;
+        uint4 *orow = bc->out + pay[2 * i];
+        const uint64_t oks = bc->out_k_stride;
         uint32_t ax = bc->X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
-            uint4 acc = orow[k];
+            uint4 acc = orow[k * oks];
             if (w & (1u << 30)) {
                 acc = xor4(acc, lds128(ax));
             }
             if (w & (1u << 31)) {
                 acc = xor4(acc, lds128(ax + zoff));
             }
-            orow[k] = acc;
+            orow[k * oks] = acc;
         }
     }
 }
@@ -644,10 +646,10 @@ __device__ __noinline__ void op_feedback(const BlockCtx *bc, const uint32_t *hdr
     const uint32_t zoff = bc->Z_s - bc->X_s;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[2 * i + 1];
-        const uint4 *rrow = bc->rec + (uint64_t)pay[2 * i] * bc->rec_row_stride;
+        const uint4 *rrow = bc->rec + pay[2 * i];
         uint32_t ax = bc->X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
-            const uint4 r = rrow[k];
+            const uint4 r = rrow[k * bc->rec_k_stride];
             if (w & (1u << 30)) {
                 sts128(ax, xor4(lds128(ax), r));
             }
@@ -766,8 +768,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         bc->k0 = p.seed_lo;
         bc->k1 = p.seed_hi;
         bc->rec_mask = p.rec_mask;
-        bc->rec_row_stride = p.rec_row_stride;
-        bc->out_row_stride = p.out_row_stride;
+        bc->rec_k_stride = p.rec_k_stride;
+        bc->out_k_stride = p.out_k_stride;
         bc->logical_of = p.logical_of;
     }
     for (uint32_t i = tid; i < 256; i += T) {
@@ -794,7 +796,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
             bc->col0_lo = (uint32_t)col0;
             bc->col0_hi = (uint32_t)(col0 >> 32);
             bc->rec = p.rec + (uint64_t)g * p.rec_block_stride + (uint64_t)blockIdx.x * p.rec_cta_stride;
-            bc->out = p.out + (uint64_t)g * p.K;
+            bc->out = p.out + (uint64_t)g * p.K * p.out_k_stride;
             // start streaming the program
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(mbar_s, chunk_bytes);

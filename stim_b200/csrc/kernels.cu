@@ -12,14 +12,18 @@
 namespace gstim {
 
 // ------------------------------------------------------------------------------------------------
-// Output transposer. Tile = 512 shots x 1024 bits. Thread (sw, rg): sw = shot word 0..15 of the tile,
-// rg = group of 32 output bits. Each thread gathers 32 source rows' words (coalesced across sw),
-// transposes the 32x32 bit block in registers, parks it in shared memory, then warps stream whole
-// 128-byte shot segments to the dense (arbitrarily aligned) output rows.
+// Output transposer. Tile = 512 shots (4 columns) x 1024 bits.
+//   1. every thread gathers 8 table entries (2 rows x 4 columns; a warp reads 512 contiguous bytes of a
+//      column) through the row map and parks them in shared memory, one uint4 of padding per 32 rows;
+//   2. thread (col, w, rg) picks up the 32 words (rows rg*32.., shot word w of column col), transposes the
+//      32x32 bit block in registers and parks it in the (aliased) output staging area [shot][40 words];
+//   3. warps stream whole 128-byte shot segments to the dense (arbitrarily aligned) output rows.
 // ------------------------------------------------------------------------------------------------
 constexpr int TP_SHOTS = 512;
+constexpr int TP_COLS = TP_SHOTS / 128;
 constexpr int TP_BITS = 1024;
-constexpr int TP_PITCH = 33;  // words per shot row in shared memory (+1 to spread banks)
+constexpr int TP_PITCH = 40;                       // words per shot row in the output staging (8 mod 32: conflict-free)
+constexpr int TP_IN_COL = TP_BITS + TP_BITS / 32;  // uint4 per column in the input staging (1 pad per 32 rows)
 
 __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
     // After this, a[j] bit i == (input a[i]) bit j.
@@ -38,35 +42,64 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
     }
 }
 
-__global__ void __launch_bounds__(512) gstim_transpose_kernel(const TransposeParams p) {
+__global__ void __launch_bounds__(512, 2) gstim_transpose_kernel(const TransposeParams p) {
     extern __shared__ __align__(16) uint32_t tile[];
+    uint4 *in = reinterpret_cast<uint4 *>(tile);
     const uint32_t tid = threadIdx.x;
-    const uint32_t sw = tid & 15, rg = tid >> 4;
-    const uint64_t shot_word0 = (uint64_t)blockIdx.x * (TP_SHOTS / 32);
+    const uint64_t col0 = (uint64_t)blockIdx.x * TP_COLS;
+    const uint64_t n_cols = (p.n_shots + 127) / 128;
     const uint32_t bit0 = blockIdx.y * TP_BITS;
+    const uint4 *table = reinterpret_cast<const uint4 *>(p.table);
 
+    // ---- 1. gather
+    {
+        uint4 v[2][TP_COLS];
+        uint32_t inv[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint32_t bit = bit0 + tid + 512 * j;
+            const bool ok = bit < p.n_bits;
+            const uint32_t rm = ok ? p.row_map[bit] : 0u;
+            inv[j] = (uint32_t)0 - (rm >> 31);
+#pragma unroll
+            for (int c = 0; c < TP_COLS; c++) {
+                v[j][c] = (ok && col0 + c < n_cols) ? table[(col0 + c) * p.n_rows + (rm & 0x7FFFFFFFu)] : make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint32_t r = tid + 512 * j;
+#pragma unroll
+            for (int c = 0; c < TP_COLS; c++) {
+                uint4 x = v[j][c];
+                x.x ^= inv[j];
+                x.y ^= inv[j];
+                x.z ^= inv[j];
+                x.w ^= inv[j];
+                in[c * TP_IN_COL + r + (r >> 5)] = x;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. 32x32 bit transposes
+    const uint32_t w = tid & 3, rg = (tid >> 2) & 31, col = tid >> 7;
     uint32_t a[32];
-    const uint64_t sword = shot_word0 + sw;
-    const bool in_range = sword < p.row_words;
 #pragma unroll
     for (int i = 0; i < 32; i++) {
-        const uint32_t bit = bit0 + rg * 32 + i;
-        uint32_t v = 0;
-        if (bit < p.n_bits && in_range) {
-            const uint32_t rm = p.row_map[bit];
-            v = p.table[(uint64_t)(rm & 0x7FFFFFFFu) * p.row_words + sword];
-            v ^= (uint32_t)0 - (rm >> 31);
-        }
-        a[i] = v;
+        a[i] = tile[(col * TP_IN_COL + rg * 33 + i) * 4 + w];
     }
     transpose32(a);
-    // shot (sw*32+s) is parked at tile row (s*16+sw): bank = (16 s + sw + rg) % 32
+    __syncthreads();  // the output staging aliases the input staging
+    // shot col*128 + w*32 + s is parked at row s*16 + sw (sw = col*4 + w): bank = (8*(16 s + sw) + rg) % 32
+    const uint32_t sw = col * 4 + w;
 #pragma unroll
     for (int s = 0; s < 32; s++) {
         tile[(s * 16 + sw) * TP_PITCH + rg] = a[s];
     }
     __syncthreads();
 
+    // ---- 3. dense rows out
     const uint32_t nbytes = (p.n_bits + 7) / 8;
     const uint32_t seg0 = blockIdx.y * (TP_BITS / 8);
     const uint32_t seg_len = min((uint32_t)(TP_BITS / 8), nbytes - seg0);
@@ -81,19 +114,19 @@ __global__ void __launch_bounds__(512) gstim_transpose_kernel(const TransposePar
         const uint32_t mis = (uint32_t)((uintptr_t)dst & 3);
         uint8_t *base = dst - mis;  // 4-byte aligned
         // aligned destination word w holds segment bytes [4w - mis, 4w - mis + 4)
-        for (uint32_t w = lane; w * 4 < mis + seg_len; w += 32) {
-            const uint32_t lo = w >= 1 ? S[w - 1] : 0u;
-            const uint32_t hi = w < 32 ? S[w] : 0u;
+        for (uint32_t wd = lane; wd * 4 < mis + seg_len; wd += 32) {
+            const uint32_t lo = wd >= 1 ? S[wd - 1] : 0u;
+            const uint32_t hi = wd < 32 ? S[wd] : 0u;
             const uint32_t val = mis == 0 ? hi : __funnelshift_r(lo, hi, 8 * (4 - mis));
-            const int first = (int)(4 * w) - (int)mis;  // segment byte index of this word's byte 0
+            const int first = (int)(4 * wd) - (int)mis;  // segment byte index of this word's byte 0
             if (first >= 0 && first + 4 <= (int)seg_len) {
-                *(uint32_t *)(base + 4 * w) = val;
+                *(uint32_t *)(base + 4 * wd) = val;
             } else {
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     const int sb = first + b;
                     if (sb >= 0 && sb < (int)seg_len) {
-                        base[4 * w + b] = (uint8_t)(val >> (8 * b));
+                        base[4 * wd + b] = (uint8_t)(val >> (8 * b));
                     }
                 }
             }
@@ -107,7 +140,7 @@ cudaError_t launch_transpose_b8(const TransposeParams &p, cudaStream_t stream) {
     }
     dim3 grid((unsigned)((p.n_shots + TP_SHOTS - 1) / TP_SHOTS), (p.n_bits + TP_BITS - 1) / TP_BITS);
     static bool attr_set = false;
-    const size_t smem = (size_t)TP_SHOTS * TP_PITCH * 4;
+    const size_t smem = std::max((size_t)TP_SHOTS * TP_PITCH * 4, (size_t)TP_COLS * TP_IN_COL * 16);
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gstim_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
@@ -120,43 +153,41 @@ cudaError_t launch_transpose_b8(const TransposeParams &p, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Row popcounts: one warp per (row, slice of shots).
+// Row popcounts of a column-major table: thread = row (coalesced across a column), blockIdx.y = slice of columns.
 // ------------------------------------------------------------------------------------------------
-__global__ void gstim_popcount_kernel(
-    const uint32_t *table, uint64_t row_words, uint32_t n_rows, uint64_t n_shots, unsigned long long *counts) {
-    const uint32_t row = blockIdx.x;
+__global__ void gstim_popcount_kernel(const uint4 *table, uint64_t n_rows, uint64_t n_shots, unsigned long long *counts) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_rows) {
         return;
     }
-    const uint64_t full_words = n_shots / 32;
-    const uint32_t tail_bits = (uint32_t)(n_shots & 31);
-    const uint32_t *r = table + (uint64_t)row * row_words;
+    const uint64_t n_cols = (n_shots + 127) / 128;
     unsigned long long acc = 0;
-    for (uint64_t w = (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; w < full_words; w += (uint64_t)gridDim.y * blockDim.x) {
-        acc += __popc(r[w]);
+    for (uint64_t c = blockIdx.y; c < n_cols; c += gridDim.y) {
+        uint4 v = table[c * n_rows + row];
+        const uint64_t left = n_shots - c * 128;  // shots of this column that count
+        if (left < 128) {
+            uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+            for (uint32_t i = 0; i < 4; i++) {
+                const uint64_t lo = 32ull * i;
+                wds[i] = left <= lo ? 0u : (left - lo >= 32 ? wds[i] : wds[i] & ((1u << (left - lo)) - 1));
+            }
+            v = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        }
+        acc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
     }
-    if (tail_bits && blockIdx.y == 0 && threadIdx.x == 0) {
-        acc += __popc(r[full_words] & ((1u << tail_bits) - 1));
-    }
-    for (int o = 16; o; o >>= 1) {
-        acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
-    }
-    if ((threadIdx.x & 31) == 0 && acc) {
+    if (acc) {
         atomicAdd(&counts[row], acc);
     }
 }
 
 cudaError_t launch_row_popcount(
-    const uint32_t *table, uint64_t row_words, uint32_t n_rows, uint64_t n_shots, unsigned long long *counts, cudaStream_t stream) {
+    const uint32_t *table, uint64_t n_rows, uint64_t n_shots, unsigned long long *counts, cudaStream_t stream) {
     if (n_rows == 0 || n_shots == 0) {
         return cudaSuccess;
     }
-    uint32_t slices = (uint32_t)std::min<uint64_t>(64, (n_shots / 32 + 255) / 256);
-    if (slices == 0) {
-        slices = 1;
-    }
-    dim3 grid(n_rows, slices);
-    gstim_popcount_kernel<<<grid, 256, 0, stream>>>(table, row_words, n_rows, n_shots, counts);
+    const uint64_t n_cols = (n_shots + 127) / 128;
+    dim3 grid((unsigned)((n_rows + 255) / 256), (unsigned)std::min<uint64_t>(n_cols, 1024));
+    gstim_popcount_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(table), n_rows, n_shots, counts);
     return cudaGetLastError();
 }
 

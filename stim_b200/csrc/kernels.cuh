@@ -24,10 +24,10 @@ struct InterpParams {
     uint4 *rec;                // measurement record rows
     uint64_t rec_block_stride; // uint4 units between consecutive shot blocks (measurement mode: rows live in the table)
     uint64_t rec_cta_stride;   // uint4 units between CTAs (detector mode: per-CTA L2-resident ring)
-    uint64_t rec_row_stride;   // uint4 units between consecutive record rows
+    uint64_t rec_k_stride;     // uint4 units between the 128-shot columns of a record row (rows of one column are contiguous)
     uint32_t rec_mask;         // ring mask (detector mode) or 0xFFFFFFFF
-    uint4 *out;                // detector/observable rows (bit-major); block g owns uint4 columns [g*K,(g+1)*K)
-    uint64_t out_row_stride;   // uint4 units
+    uint4 *out;                // detector/observable table, column-major: out[column * out_k_stride + row]; block g owns columns [g*K,(g+1)*K)
+    uint64_t out_k_stride;     // uint4 units between columns (= number of rows)
     uint32_t dbg_flags;        // GSTIM_DEBUG_FLAGS: timing experiments only (results become wrong): bit0 no pre-pass, bit1 no collapse RNG, bits 8+op skip opcode
     unsigned long long *dbg_cycles;  // optional (GSTIM_DEBUG_CYCLES=1): [op] cycles and [16+op] batch counts seen by block 0
     // noise schedule (program.h) and the per-CTA event scratch the pre-pass fills
@@ -51,8 +51,8 @@ cudaError_t interp_set_max_smem(size_t smem);
 int interp_max_blocks_per_sm(uint32_t threads, size_t smem);
 
 struct TransposeParams {
-    const uint32_t *table;     // bit-major rows: table[row * row_words + shot_word]
-    uint64_t row_words;        // uint32 words per row
+    const uint32_t *table;     // column-major bit table: uint4 table[column * n_rows + row], column = 128 shots
+    uint64_t n_rows;           // rows per column
     const uint32_t *row_map;   // n_bits entries: source row | invert<<31
     uint32_t n_bits;           // bits per shot in the output
     uint64_t n_shots;          // shots to emit (may be less than row_words*32)
@@ -61,8 +61,8 @@ struct TransposeParams {
 };
 cudaError_t launch_transpose_b8(const TransposeParams &p, cudaStream_t stream);
 
-// popcount of every row of a bit-major table over the first n_shots shots -> counts[row] (uint64, accumulated)
+// popcount of every row of a column-major bit table over the first n_shots shots -> counts[row] (uint64, accumulated)
 cudaError_t launch_row_popcount(
-    const uint32_t *table, uint64_t row_words, uint32_t n_rows, uint64_t n_shots, unsigned long long *counts, cudaStream_t stream);
+    const uint32_t *table, uint64_t n_rows, uint64_t n_shots, unsigned long long *counts, cudaStream_t stream);
 
 }  // namespace gstim

@@ -139,7 +139,7 @@ void write_shots(
     out.flush();
 }
 
-void write_ptb64(FILE *f, const uint32_t *table, size_t row_words, const uint32_t *row_map, size_t n_bits, size_t n_shots) {
+void write_ptb64(FILE *f, const uint32_t *table, size_t n_rows, const uint32_t *row_map, size_t n_bits, size_t n_shots) {
     if (n_shots % 64 != 0) {
         throw std::invalid_argument("shots must be a multiple of 64 to use ptb64 format.");
     }
@@ -147,7 +147,8 @@ void write_ptb64(FILE *f, const uint32_t *table, size_t row_words, const uint32_
     for (size_t g = 0; g < n_shots / 64; g++) {
         for (size_t m = 0; m < n_bits; m++) {
             uint32_t rm = row_map[m];
-            const uint32_t *r = table + (size_t)(rm & 0x7FFFFFFFu) * row_words + 2 * g;
+            // column-major table: uint4 table[column * n_rows + row], 64-shot group g = half of column g / 2
+            const uint32_t *r = table + ((g >> 1) * n_rows + (size_t)(rm & 0x7FFFFFFFu)) * 4 + 2 * (g & 1);
             uint64_t v = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
             if (rm >> 31) {
                 v = ~v;

@@ -24,6 +24,6 @@ void write_shots(
 
 // ptb64 from bit-major 32-bit rows: for each group of 64 shots, for each output bit, one u64.
 // row_map[bit] = source row | invert<<31. n_shots must be a multiple of 64.
-void write_ptb64(FILE *f, const uint32_t *table, size_t row_words, const uint32_t *row_map, size_t n_bits, size_t n_shots);
+void write_ptb64(FILE *f, const uint32_t *table, size_t n_rows, const uint32_t *row_map, size_t n_bits, size_t n_shots);
 
 }  // namespace gstim
