@@ -449,8 +449,8 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         p.dbg_cycles = nullptr;
         p.dbg_flags = env_u32("GSTIM_DEBUG_FLAGS", 0);
         if (env_u32("GSTIM_DEBUG_CYCLES", 0)) {
-            s->d_dbg.ensure(32 * 8);
-            CK(cudaMemsetAsync(s->d_dbg.p, 0, 32 * 8, s->stream));
+            s->d_dbg.ensure(64 * 8);
+            CK(cudaMemsetAsync(s->d_dbg.p, 0, 64 * 8, s->stream));
             p.dbg_cycles = (unsigned long long *)s->d_dbg.p;
         }
         p.col0_base = s->next_col + done_blocks * K;
@@ -484,7 +484,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
     CK(cudaEventRecord(s->call_end, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     if (env_u32("GSTIM_DEBUG_CYCLES", 0) && s->d_dbg.p) {
-        unsigned long long h[32];
+        unsigned long long h[64];
         CK(cudaMemcpy(h, s->d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost));
         static const char *names[13] = {"END", "CHUNK", "CLIFF1", "CLIFF2", "NOISE1", "NOISE2", "MEASURE", "RECZERO", "XORROWS", "OBS_PAULI", "FEEDBACK", "CORR", "QMAP"};
         unsigned long long tot = 0;
@@ -492,7 +492,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
             tot += h[i];
         }
         fprintf(stderr, "[gstim cycles, block 0, last launch] total %llu\n", tot);
-        fprintf(stderr, "  prepass(thread 0): %llu cyc; events %llu, slices %llu, iterations %llu\n", h[25], h[27], h[28], h[29]);
+        fprintf(stderr, "  prepass(thread 0): %llu cyc; events %llu, slices %llu, iterations %llu\n  noise apply(thread 0): prefetch+wait %llu, entry barrier %llu, flips %llu, exit barrier %llu cyc\n", h[32], h[33], h[34], h[35], h[40], h[41], h[42], h[43]);
         for (int i = 0; i < 13; i++) {
             if (h[i]) {
                 fprintf(stderr, "  %-9s %10llu cyc (%5.1f%%)  %6llu batches  %8.0f cyc/batch\n", names[i], h[i], 100.0 * h[i] / tot, h[16 + i], h[16 + i] ? (double)h[i] / h[16 + i] : 0.0);

@@ -254,111 +254,143 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
         nd = __ldg(slices + nidx);
     }
     bool have = false;
+    // An event record is written one event late: two consecutive events of a slice that flip the same 32-bit
+    // frame words (same item, same 32-shot word) both get GSTIM_EV_CONFLICT, and only those are applied with
+    // shared-memory atomics (2 cycles per lane on the LSU) by the interpreter; everything else is plain.
+    bool pend = false;
+    uint32_t pend_rec = 0;
     while (true) {
+        bool live = true;
         if (!have) {
             if (nidx >= n_slices) {
-                break;
-            }
-            grp = nd.x;
-            sl1 = nd.y | GSTIM_SLICE_FLAG;
-            nbi = nd.z & 0xFFFFu;
-            item0 = nd.w & 0x7FFu;
-            total = (nd.w >> 11) * B;
-            a = 0;
-            d = 0;
-            const uint32_t ri = nd.z >> 16;
-            if (ri < GSTIM_RATE_SMEM_MAX) {
-                lam = lds64(rates_s + 16 * ri);
-                inv = lds64(rates_s + 16 * ri + 8);
+                if (!pend) {
+                    break;
+                }
+                live = false;
             } else {
-                const ulonglong2 r = __ldg(rates_g + ri);
-                lam = r.x;
-                inv = r.y;
-            }
-            have = true;
-            n_sl++;
-            nidx = atom_add_shared(next_s, 1);
-            if (nidx < n_slices) {
-                nd = __ldg(slices + nidx);
+                grp = nd.x;
+                sl1 = nd.y | GSTIM_SLICE_FLAG;
+                nbi = nd.z & 0xFFFFu;
+                item0 = nd.w & 0x7FFu;
+                total = (nd.w >> 11) * B;
+                a = 0;
+                d = 0;
+                const uint32_t ri = nd.z >> 16;
+                if (ri < GSTIM_RATE_SMEM_MAX) {
+                    lam = lds64(rates_s + 16 * ri);
+                    inv = lds64(rates_s + 16 * ri + 8);
+                } else {
+                    const ulonglong2 r = __ldg(rates_g + ri);
+                    lam = r.x;
+                    inv = r.y;
+                }
+                have = true;
+                n_sl++;
+                nidx = atom_add_shared(next_s, 1);
+                if (nidx < n_slices) {
+                    nd = __ldg(slices + nidx);
+                }
             }
         }
-        n_iter++;
-        const uint4 rr = philox4x32_10(grp, sl1, col0_lo, col0_hi | (d << GSTIM_DRAW_SHIFT), k0, k1);
-        d++;
-        const unsigned long long E = exp_draw_fx(rr.x, lt_s);
-        const unsigned long long G = div_by_rate(E, lam, inv);
-        if (G >= (unsigned long long)(total - a)) {  // no further event in this slice
-            have = false;
-            continue;
-        }
-        // ---- exactly one event, at shot-site a + G of the slice
-        a += (uint32_t)G;
-        const uint32_t site = __umulhi(a, magicB), shot = a - site * B;
-        a++;
-        const uint32_t h0 = info_bytes ? lds32(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4)) : __ldg(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS);
-        const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
-        uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
-        if (op == GOP_NOISE1) {
-            uint4 i1;  // (group, t1, t2, t3)
-            if (info_bytes) {
-                i1 = lds128(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4) + 16);
+        bool emit = false;
+        uint32_t emit_rec = 0;
+        const uint32_t emit_nbi = nbi;  // a pending record always belongs to the current slice's batch
+        if (live) {
+            n_iter++;
+            const uint4 rr = philox4x32_10(grp, sl1, col0_lo, col0_hi | (d << GSTIM_DRAW_SHIFT), k0, k1);
+            d++;
+            const unsigned long long E = exp_draw_fx(rr.x, lt_s);
+            const unsigned long long G = div_by_rate(E, lam, inv);
+            if (G >= (unsigned long long)(total - a)) {  // no further event in this slice
+                have = false;
+                emit = pend;
+                emit_rec = pend_rec;
+                pend = false;
             } else {
-                i1 = __ldg(reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + 4));
-            }
-            const uint32_t v = rr.y;
-            const uint32_t sel = v < i1.y ? 0u : v < i1.z ? 2u : v < i1.w ? 4u : 6u;
-            f = (aux >> sel) & 3u;
-            if (flags & GF_REC) {
-                f |= 16u;
-            }
-        } else if (op == GOP_NOISE2) {
-            if (!(flags & GF_TABLE)) {
-                f = 1u + __umulhi(rr.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
-            } else {
-                const uint32_t *tab = bc->prog + __ldg(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + GNI_TABLE_OFF);
-                uint32_t pr = aux;
-                for (uint32_t t = 0; t < 15; t++) {
-                    if (rr.y < __ldg(tab + t)) {
-                        pr = t + 1;
-                        break;
+                // ---- exactly one event, at shot-site a + G of the slice
+                a += (uint32_t)G;
+                const uint32_t site = __umulhi(a, magicB), shot = a - site * B;
+                a++;
+                const uint32_t h0 = info_bytes ? lds32(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4)) : __ldg(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS);
+                const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
+                uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
+                if (op == GOP_NOISE1) {
+                    uint4 i1;  // (group, t1, t2, t3)
+                    if (info_bytes) {
+                        i1 = lds128(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4) + 16);
+                    } else {
+                        i1 = __ldg(reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + 4));
+                    }
+                    const uint32_t v = rr.y;
+                    const uint32_t sel = v < i1.y ? 0u : v < i1.z ? 2u : v < i1.w ? 4u : 6u;
+                    f = (aux >> sel) & 3u;
+                    if (flags & GF_REC) {
+                        f |= 16u;
+                    }
+                } else if (op == GOP_NOISE2) {
+                    if (!(flags & GF_TABLE)) {
+                        f = 1u + __umulhi(rr.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
+                    } else {
+                        const uint32_t *tab = bc->prog + __ldg(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + GNI_TABLE_OFF);
+                        uint32_t pr = aux;
+                        for (uint32_t t = 0; t < 15; t++) {
+                            if (rr.y < __ldg(tab + t)) {
+                                pr = t + 1;
+                                break;
+                            }
+                        }
+                        // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
+                        const uint32_t c1p = pr >> 2, c2p = pr & 3u;
+                        f = (((c1p + 1) >> 1) & 1u) | ((c1p >> 1) << 1) | ((((c2p + 1) >> 1) & 1u) << 2) | ((c2p >> 1) << 3);
                     }
                 }
-                // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
-                const uint32_t c1p = pr >> 2, c2p = pr & 3u;
-                f = (((c1p + 1) >> 1) & 1u) | ((c1p >> 1) << 1) | ((((c2p + 1) >> 1) & 1u) << 2) | ((c2p >> 1) << 3);
-            }
-        }
-        // warp-aggregated append: the lanes that have an event for the same noise batch take consecutive places
-        const unsigned act = __activemask();
-        const unsigned peers = __match_any_sync(act, nbi);
-        const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
-        uint32_t base = 0, seg0, cap;
-        if (cnt_s) {
-            seg0 = lds32(segoff_s + 4 * nbi);
-            cap = lds32(segoff_s + 4 * nbi + 4) - seg0;
-            if (lane == leader) {
-                base = atom_add_shared(cnt_s + 4 * nbi, __popc(peers));
+                uint32_t rec = shot | ((item0 + site) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
+                // same item and same 32-shot word as the previous event of this slice?
+                if (pend && ((rec ^ pend_rec) & ((GSTIM_EV_ITEM_MASK << GSTIM_EV_ITEM_SHIFT) | 0xFE0u)) == 0) {
+                    rec |= GSTIM_EV_CONFLICT;
+                    pend_rec |= GSTIM_EV_CONFLICT;
+                }
+                emit = pend;
+                emit_rec = pend_rec;
+                pend = true;
+                pend_rec = rec;
+                n_ev++;
             }
         } else {
-            seg0 = segoff[nbi];
-            cap = segoff[nbi + 1] - seg0;
-            if (lane == leader) {
-                base = atomicAdd(&counts[nbi], __popc(peers));
+            emit = true;
+            emit_rec = pend_rec;
+            pend = false;
+        }
+        if (emit) {
+            // warp-aggregated append: the lanes that write a record for the same noise batch take consecutive places
+            const unsigned act = __activemask();
+            const unsigned peers = __match_any_sync(act, emit_nbi);
+            const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t base = 0, seg0, cap;
+            if (cnt_s) {
+                seg0 = lds32(segoff_s + 4 * emit_nbi);
+                cap = lds32(segoff_s + 4 * emit_nbi + 4) - seg0;
+                if (lane == leader) {
+                    base = atom_add_shared(cnt_s + 4 * emit_nbi, __popc(peers));
+                }
+            } else {
+                seg0 = segoff[emit_nbi];
+                cap = segoff[emit_nbi + 1] - seg0;
+                if (lane == leader) {
+                    base = atomicAdd(&counts[emit_nbi], __popc(peers));
+                }
+            }
+            const uint32_t at = __shfl_sync(peers, base, leader) + rank;
+            if (at < cap) {  // (an overflowing segment is reported after the pre-pass)
+                evbuf[seg0 + at] = emit_rec;
             }
         }
-        const uint32_t at = __shfl_sync(peers, base, leader) + rank;
-        if (at < cap) {
-            evbuf[seg0 + at] = shot | ((item0 + site) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
-        } else {
-            *bc->ev_overflow = 1u;
-        }
-        n_ev++;
     }
     if (dbg) {
-        dbg[25] += (unsigned long long)(clock64() - tA);
-        dbg[27] += n_ev;
-        dbg[28] += n_sl;
-        dbg[29] += n_iter;
+        dbg[32] += (unsigned long long)(clock64() - tA);
+        dbg[33] += n_ev;
+        dbg[34] += n_sl;
+        dbg[35] += n_iter;
     }
 }
 
@@ -432,19 +464,23 @@ __device__ __noinline__ void op_cliff2(const BlockCtx *bc, const uint32_t *hdr) 
     }
 }
 
-// NOISE1 / NOISE2: apply the events the pre-pass left for this batch. Any thread applies any event, so the
-// batch is bracketed by block barriers and flips use shared-memory atomics (two events of one site can hit
-// the same 32-bit word).
-__device__ __forceinline__ void atom_flip_plane(const BlockCtx *bc, uint32_t plane_s, uint32_t row, uint32_t shot) {
-    const uint32_t a = plane_s + (shot >> 7) * bc->pitch_b + row * 16 + ((shot >> 5) & 3) * 4;
-    asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(1u << (shot & 31)) : "memory");
+// First record and (clamped) record count of noise batch `nbi` in this CTA's event scratch.
+__device__ __forceinline__ void event_segment(const BlockCtx *bc, uint32_t nbi, uint32_t &seg0, uint32_t &cnt) {
+    if (bc->ev_counts_s) {
+        seg0 = lds32(bc->ev_segoff_s + 4 * nbi);
+        cnt = lds32(bc->ev_counts_s + 4 * nbi);
+    } else {
+        seg0 = bc->ev_segoff[nbi];
+        cnt = bc->ev_counts[nbi];
+    }
 }
 // Event records of noise batch `nbi` -> staging buffer (nbi & 1), asynchronously (LDGSTS): thread t copies the
 // records it will apply itself, so no barrier is needed between the copy and the use. One group per call.
 __device__ __forceinline__ void prefetch_events(const BlockCtx *bc, uint32_t nbi) {
     if (nbi < bc->n_noise) {
-        const uint32_t seg0 = bc->ev_segoff[nbi], cap = bc->ev_segoff[nbi + 1] - seg0;
-        const uint32_t cnt = min(min(bc->ev_counts[nbi], cap), GSTIM_EV_STAGE);
+        uint32_t seg0, cnt;
+        event_segment(bc, nbi, seg0, cnt);
+        cnt = min(cnt, GSTIM_EV_STAGE);
         const uint32_t *ev = bc->ev_buf + seg0;
         const uint32_t st = bc->stage_s + (nbi & 1u) * (GSTIM_EV_STAGE * 4);
         for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
@@ -454,42 +490,72 @@ __device__ __forceinline__ void prefetch_events(const BlockCtx *bc, uint32_t nbi
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+__device__ __forceinline__ void flip_plain(uint32_t a, uint32_t bit) {
+    sts32(a, lds32(a) ^ bit);
+}
+__device__ __forceinline__ void flip_atomic(uint32_t a, uint32_t bit) {
+    asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(bit) : "memory");
+}
+
+// NOISE1 / NOISE2: apply the events the pre-pass left for this batch. Any thread applies any event, so the
+// batch is bracketed by block barriers. Two events of one batch touch the same 32-bit frame word only when the
+// pre-pass marked both GSTIM_EV_CONFLICT; only those use shared-memory atomics.
 __device__ __noinline__ void op_noise(const BlockCtx *bc, const uint32_t *hdr) {
-    const uint32_t h0 = hdr[GH_OP];
+    const uint32_t hdr_s = smem_u32(hdr);
+    const uint32_t h0 = lds32(hdr_s + 4 * GH_OP);
     const uint32_t flags = (h0 >> 8) & 0xFF;
-    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
-    const uint32_t *items = ((h0 & 0xFF) == GOP_NOISE2 && (flags & GF_TABLE)) ? pay + 15 : pay;
-    const uint32_t nbi = hdr[GH_CSITE0], rec0 = hdr[GH_REC0];
-    const uint32_t seg0 = bc->ev_segoff[nbi], cap = bc->ev_segoff[nbi + 1] - seg0;
-    const uint32_t cnt = min(bc->ev_counts[nbi], cap);
-    const uint32_t *ev = bc->ev_buf + seg0;
-    const uint32_t X_s = bc->X_s, Z_s = bc->Z_s;
+    const uint32_t items_s = hdr_s + 4 * GSTIM_HDR_WORDS + (((h0 & 0xFF) == GOP_NOISE2 && (flags & GF_TABLE)) ? 60u : 0u);
+    const uint32_t nbi = lds32(hdr_s + 4 * GH_CSITE0), rec0 = lds32(hdr_s + 4 * GH_REC0);
+    uint32_t seg0, cnt;
+    event_segment(bc, nbi, seg0, cnt);
+    const uint32_t X_s = bc->X_s, zoff = bc->Z_s - bc->X_s, pitch_b = bc->pitch_b;
     const uint32_t st = bc->stage_s + (nbi & 1u) * (GSTIM_EV_STAGE * 4);
     prefetch_events(bc, nbi + 1);
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's records have landed
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
-        const uint32_t rec = e < GSTIM_EV_STAGE ? lds32(st + 4 * e) : ev[e];
+        const uint32_t rec = e < GSTIM_EV_STAGE ? lds32(st + 4 * e) : bc->ev_buf[seg0 + e];
         const uint32_t shot = rec & ((1u << GSTIM_EV_SHOT_BITS) - 1);
         const uint32_t item = (rec >> GSTIM_EV_ITEM_SHIFT) & GSTIM_EV_ITEM_MASK;
         const uint32_t f = rec >> GSTIM_EV_FLIP_SHIFT;
-        const uint32_t w = (flags & GF_NOFRAME) ? 0u : items[item];
-        const uint32_t q1 = w & 0xFFFF, q2 = w >> 16;
-        if (f & 1u) {
-            atom_flip_plane(bc, X_s, q1, shot);
-        }
-        if (f & 2u) {
-            atom_flip_plane(bc, Z_s, q1, shot);
-        }
-        if (f & 4u) {
-            atom_flip_plane(bc, X_s, q2, shot);
-        }
-        if (f & 8u) {
-            atom_flip_plane(bc, Z_s, q2, shot);
-        }
-        if (f & 16u) {
-            uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + ((rec0 + item) & bc->rec_mask)) + ((shot >> 5) & 3);
-            atomicXor(rw, 1u << (shot & 31));
+        const uint32_t w = (flags & GF_NOFRAME) ? 0u : lds32(items_s + 4 * item);
+        const uint32_t bit = 1u << (shot & 31);
+        const uint32_t a0 = X_s + (shot >> 7) * pitch_b + ((shot >> 5) & 3) * 4;
+        const uint32_t a1 = a0 + (w & 0xFFFF) * 16, a2 = a0 + (w >> 16) * 16;
+        if (rec & GSTIM_EV_CONFLICT) {
+            if (f & 1u) {
+                flip_atomic(a1, bit);
+            }
+            if (f & 2u) {
+                flip_atomic(a1 + zoff, bit);
+            }
+            if (f & 4u) {
+                flip_atomic(a2, bit);
+            }
+            if (f & 8u) {
+                flip_atomic(a2 + zoff, bit);
+            }
+            if (f & 16u) {
+                uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + ((rec0 + item) & bc->rec_mask)) + ((shot >> 5) & 3);
+                atomicXor(rw, bit);
+            }
+        } else {
+            if (f & 1u) {
+                flip_plain(a1, bit);
+            }
+            if (f & 2u) {
+                flip_plain(a1 + zoff, bit);
+            }
+            if (f & 4u) {
+                flip_plain(a2, bit);
+            }
+            if (f & 8u) {
+                flip_plain(a2 + zoff, bit);
+            }
+            if (f & 16u) {
+                uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + ((rec0 + item) & bc->rec_mask)) + ((shot >> 5) & 3);
+                *rw ^= bit;
+            }
         }
     }
     __syncthreads();
@@ -818,6 +884,19 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         __syncthreads();
         if (!(p.dbg_flags & 1u)) {
             noise_prepass(bc);
+        }
+        __syncthreads();
+        {
+            // clamp the event counts to their segments (an overflow invalidates the call: the host reports it)
+            uint32_t *counts = ev_in_smem ? ev_s : p.ev_counts + (size_t)blockIdx.x * p.n_noise;
+            const uint32_t *so = ev_in_smem ? ev_s + p.n_noise : p.ev_segoff;
+            for (uint32_t i = tid; i < p.n_noise; i += T) {
+                const uint32_t cap = so[i + 1] - so[i];
+                if (counts[i] > cap) {
+                    counts[i] = cap;
+                    *p.ev_overflow = 1u;
+                }
+            }
         }
         __syncthreads();
         prefetch_events(bc, 0);

@@ -12,15 +12,19 @@
 namespace gstim {
 
 // ------------------------------------------------------------------------------------------------
-// Output transposer. Tile = 512 shots (4 columns) x 1024 bits.
-//   1. every thread gathers 8 table entries (2 rows x 4 columns; a warp reads 512 contiguous bytes of a
+// Output transposer. Tile = TP_SHOTS shots (TP_COLS columns) x 1024 bits; small tiles so that several thread
+// blocks per SM overlap their gather / transpose / store phases.
+//   1. every thread gathers TP_RPT rows x TP_COLS columns of table entries (a warp reads 512 contiguous bytes of a
 //      column) through the row map and parks them in shared memory, one uint4 of padding per 32 rows;
 //   2. thread (col, w, rg) picks up the 32 words (rows rg*32.., shot word w of column col), transposes the
 //      32x32 bit block in registers and parks it in the (aliased) output staging area [shot][40 words];
 //   3. warps stream whole 128-byte shot segments to the dense (arbitrarily aligned) output rows.
 // ------------------------------------------------------------------------------------------------
-constexpr int TP_SHOTS = 512;
-constexpr int TP_COLS = TP_SHOTS / 128;
+constexpr int TP_COLS = 2;
+constexpr int TP_SHOTS = TP_COLS * 128;
+constexpr int TP_THREADS = TP_SHOTS;         // one thread per (column, shot word, 32-row group)
+constexpr int TP_WARPS = TP_THREADS / 32;
+constexpr int TP_RPT = 1024 / TP_THREADS;     // rows gathered per thread and column
 constexpr int TP_BITS = 1024;
 constexpr int TP_PITCH = 40;                       // words per shot row in the output staging (8 mod 32: conflict-free)
 constexpr int TP_IN_COL = TP_BITS + TP_BITS / 32;  // uint4 per column in the input staging (1 pad per 32 rows)
@@ -42,22 +46,27 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
     }
 }
 
-__global__ void __launch_bounds__(512, 2) gstim_transpose_kernel(const TransposeParams p) {
+__global__ void __launch_bounds__(TP_THREADS, 4) gstim_transpose_kernel(const TransposeParams p) {
     extern __shared__ __align__(16) uint32_t tile[];
     uint4 *in = reinterpret_cast<uint4 *>(tile);
     const uint32_t tid = threadIdx.x;
-    const uint64_t col0 = (uint64_t)blockIdx.x * TP_COLS;
+    // consecutive blocks take consecutive bit tiles of the same shots, so the 128-byte pieces of an output row are
+    // written at about the same time and reach DRAM as whole rows
+    const uint32_t n_bit_tiles = (p.n_bits + TP_BITS - 1) / TP_BITS;
+    const uint32_t tile_y = blockIdx.x % n_bit_tiles;
+    const uint64_t tile_x = blockIdx.x / n_bit_tiles;
+    const uint64_t col0 = tile_x * TP_COLS;
     const uint64_t n_cols = (p.n_shots + 127) / 128;
-    const uint32_t bit0 = blockIdx.y * TP_BITS;
+    const uint32_t bit0 = tile_y * TP_BITS;
     const uint4 *table = reinterpret_cast<const uint4 *>(p.table);
 
     // ---- 1. gather
     {
-        uint4 v[2][TP_COLS];
-        uint32_t inv[2];
+        uint4 v[TP_RPT][TP_COLS];
+        uint32_t inv[TP_RPT];
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const uint32_t bit = bit0 + tid + 512 * j;
+        for (int j = 0; j < TP_RPT; j++) {
+            const uint32_t bit = bit0 + tid + TP_THREADS * j;
             const bool ok = bit < p.n_bits;
             const uint32_t rm = ok ? p.row_map[bit] : 0u;
             inv[j] = (uint32_t)0 - (rm >> 31);
@@ -67,8 +76,8 @@ __global__ void __launch_bounds__(512, 2) gstim_transpose_kernel(const Transpose
             }
         }
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const uint32_t r = tid + 512 * j;
+        for (int j = 0; j < TP_RPT; j++) {
+            const uint32_t r = tid + TP_THREADS * j;
 #pragma unroll
             for (int c = 0; c < TP_COLS; c++) {
                 uint4 x = v[j][c];
@@ -91,26 +100,54 @@ __global__ void __launch_bounds__(512, 2) gstim_transpose_kernel(const Transpose
     }
     transpose32(a);
     __syncthreads();  // the output staging aliases the input staging
-    // shot col*128 + w*32 + s is parked at row s*16 + sw (sw = col*4 + w): bank = (8*(16 s + sw) + rg) % 32
+    // shot col*128 + w*32 + s is parked at row s*(4 TP_COLS) + sw (sw = col*4 + w): bank = (8*(row) + rg) % 32
     const uint32_t sw = col * 4 + w;
 #pragma unroll
     for (int s = 0; s < 32; s++) {
-        tile[(s * 16 + sw) * TP_PITCH + rg] = a[s];
+        tile[(s * (4 * TP_COLS) + sw) * TP_PITCH + rg] = a[s];
     }
     __syncthreads();
 
-    // ---- 3. dense rows out
+    // ---- 3. dense rows out: warp `warp` streams the 128-byte segments of shots warp, warp + 16, ...
     const uint32_t nbytes = (p.n_bits + 7) / 8;
-    const uint32_t seg0 = blockIdx.y * (TP_BITS / 8);
+    const uint32_t seg0 = tile_y * (TP_BITS / 8);
     const uint32_t seg_len = min((uint32_t)(TP_BITS / 8), nbytes - seg0);
     const uint32_t lane = tid & 31, warp = tid >> 5;
-    for (uint32_t sl = warp; sl < TP_SHOTS; sl += 16) {
-        const uint64_t shot = (uint64_t)blockIdx.x * TP_SHOTS + sl;
-        if (shot >= p.n_shots) {
-            break;
+    const uint64_t shot0 = tile_x * TP_SHOTS;
+    const uint32_t n_valid = (uint32_t)min((uint64_t)TP_SHOTS, p.n_shots - shot0);
+    uint8_t *dst = p.out + (shot0 + warp) * p.out_pitch + seg0;
+    const uint64_t dst_step = TP_WARPS * p.out_pitch;
+    if (seg_len == TP_BITS / 8) {
+        // full segment: aligned word `lane` of the destination holds segment bytes [4 lane - mis, 4 lane - mis + 4).
+        // Lanes 1..31 store whole words; the 4 - mis head bytes and mis tail bytes go out as single predicated
+        // byte stores from lanes 0..3 (no per-byte loops: a loop run by one lane still costs the whole warp).
+        for (uint32_t sl = warp; sl < n_valid; sl += TP_WARPS, dst += dst_step) {
+            const uint32_t *S = &tile[((sl & 31) * (4 * TP_COLS) + (sl >> 5)) * TP_PITCH];
+            const uint32_t mis = (uint32_t)((uintptr_t)dst & 3);
+            const uint32_t hi = S[lane];
+            if (mis == 0) {
+                reinterpret_cast<uint32_t *>(dst)[lane] = hi;
+            } else {
+                const uint32_t sh = 8 * (4 - mis);
+                const uint32_t lo = lane ? S[lane - 1] : 0u;
+                if (lane) {
+                    reinterpret_cast<uint32_t *>(dst - mis)[lane] = __funnelshift_r(lo, hi, sh);
+                }
+                if (lane < 4) {
+                    const uint32_t first = S[0], last = S[31];
+                    if (lane < 4 - mis) {
+                        dst[lane] = (uint8_t)(first >> (8 * lane));  // segment bytes 0 .. 3 - mis
+                    }
+                    if (lane < mis) {
+                        dst[128 - mis + lane] = (uint8_t)(last >> (sh + 8 * lane));  // segment bytes 128 - mis .. 127
+                    }
+                }
+            }
         }
-        const uint32_t *S = &tile[((sl & 31) * 16 + (sl >> 5)) * TP_PITCH];
-        uint8_t *dst = p.out + shot * p.out_pitch + seg0;
+        return;
+    }
+    for (uint32_t sl = warp; sl < n_valid; sl += TP_WARPS, dst += dst_step) {
+        const uint32_t *S = &tile[((sl & 31) * (4 * TP_COLS) + (sl >> 5)) * TP_PITCH];
         const uint32_t mis = (uint32_t)((uintptr_t)dst & 3);
         uint8_t *base = dst - mis;  // 4-byte aligned
         // aligned destination word w holds segment bytes [4w - mis, 4w - mis + 4)
@@ -138,7 +175,11 @@ cudaError_t launch_transpose_b8(const TransposeParams &p, cudaStream_t stream) {
     if (p.n_bits == 0 || p.n_shots == 0) {
         return cudaSuccess;
     }
-    dim3 grid((unsigned)((p.n_shots + TP_SHOTS - 1) / TP_SHOTS), (p.n_bits + TP_BITS - 1) / TP_BITS);
+    const uint64_t n_tiles = ((p.n_shots + TP_SHOTS - 1) / TP_SHOTS) * ((p.n_bits + TP_BITS - 1) / TP_BITS);
+    if (n_tiles >= (1ull << 31)) {
+        return cudaErrorInvalidValue;
+    }
+    dim3 grid((unsigned)n_tiles);
     static bool attr_set = false;
     const size_t smem = std::max((size_t)TP_SHOTS * TP_PITCH * 4, (size_t)TP_COLS * TP_IN_COL * 16);
     if (!attr_set) {
@@ -148,7 +189,7 @@ cudaError_t launch_transpose_b8(const TransposeParams &p, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    gstim_transpose_kernel<<<grid, 512, smem, stream>>>(p);
+    gstim_transpose_kernel<<<grid, TP_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -92,7 +92,7 @@ enum GstimHdr : uint32_t {
 //                    first item of the slice in its batch | number of sites << 11
 //   rate  (2 u64):   lam, floor((2^64 - 1) / lam)
 // The kernel's event pre-pass walks the slices and leaves compact event records for the interpreter:
-//   record = shot (bits 0-11) | item (12-22) | flips x1,z1,x2,z2 (23-26) | record flip (27).
+//   record = shot (bits 0-11) | item (12-22) | flips x1,z1,x2,z2 (23-26) | record flip (27) | conflict (28).
 #define GSTIM_NOISE_SLICE 16u
 #define GSTIM_RATE_SMEM_MAX 64u    // the first 64 rates are mirrored in shared memory
 #define GSTIM_NOISE_INFO_WORDS 12u
@@ -111,6 +111,7 @@ enum GstimNoiseInfo : uint32_t {
 #define GSTIM_EV_ITEM_SHIFT 12u
 #define GSTIM_EV_ITEM_MASK 0x7FFu
 #define GSTIM_EV_FLIP_SHIFT 23u
+#define GSTIM_EV_CONFLICT 0x10000000u  // another record of the batch flips the same 32-bit frame words: apply atomically
 #define GSTIM_MAX_BATCH_ITEMS 2047u
 #define GSTIM_EV_STAGE 512u      // event records per noise batch prefetched into shared memory
 #define GSTIM_EV_SMEM_MAX 2048u  // event counters / segment offsets live in shared memory up to this many noise batches
