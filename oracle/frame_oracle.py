@@ -224,7 +224,7 @@ class FrameOracle:
         self.ngroup = 0  # noise group counter   (Philox counter word 0 of event draws)
         self.mgroup = 0  # measure group counter (Philox counter word 0 of collapse draws)
 
-    NOISE_SLICE = 16  # GSTIM_NOISE_SLICE (program.h)
+    NOISE_SLICE = 32  # GSTIM_NOISE_SLICE (program.h)
 
     # -- randomness ---------------------------------------------------------------------------
     def collapse_words(self, mgroup, q):
@@ -239,8 +239,8 @@ class FrameOracle:
 
         The sites are cut into slices of NOISE_SLICE; a slice x a shot block is one Bernoulli sequence (site-major, then
         shot) walked with geometric gaps floor(Exp(1)/lambda) == RareErrorIterator (probability_util.cc:33-43), in
-        exact integer arithmetic. Draw d of a slice: Philox counter (group, 0x80000000 | slice, col0 lo, col0 hi | d << 15);
-        word 0 -> gap to the next event, word 1 -> that event's Pauli word. on_event(i, g, shot, r): r[1] = Pauli word."""
+        exact integer arithmetic. Call c of a slice: Philox counter (group, 0x80000000 | slice, col0 lo, col0 hi | c << 15)
+        = draws 2c (words 0, 1) and 2c + 1 (words 2, 3); a draw = (gap to the next event, that event's Pauli word). on_event(i, g, shot, r): r[1] = Pauli word."""
         n = len(clocks)
         if n == 0 or lam == 0:
             return
@@ -250,22 +250,24 @@ class FrameOracle:
         c3 = (self.col0 >> np.uint64(32))[None, :]
         assert int(self.col0.max()) < (1 << 47)
         js = (np.arange(n_sl, dtype=np.uint64) | np.uint64(0x80000000))[:, None]
-        first = px.philox4x32_10(group, js, c2, c3, self.k0, self.k1)
+        first = px.philox4x32_10(group, js, c2, c3, self.k0, self.k1)  # call 0 of every (slice, block)
         for j in range(n_sl):
             total = min(S, n - j * S) * B
             for g in range(self.nb):
-                r0, r1 = int(first[0][j, g]), int(first[1][j, g])
-                a, d = 0, 1
+                words = [int(first[k][j, g]) for k in range(4)]  # one Philox call = draws (w0, w1) and (w2, w3)
+                a, d = 0, 0
                 while True:
-                    G = px.exp_draw_fx(r0) // lam
+                    if d and d % 2 == 0:
+                        r = px.philox4x32_10(group, 0x80000000 | j, int(c2[0, g]), int(c3[0, g]) | ((d // 2) << 15), self.k0, self.k1)
+                        words = [int(v) for v in r]
+                    gap_word, pauli_word = words[2 * (d % 2)], words[2 * (d % 2) + 1]
+                    d += 1
+                    G = px.exp_draw_fx(gap_word) // lam
                     if G >= total - a:
                         break
                     a += G
-                    on_event(j * S + a // B, g, a % B, (0, r1, 0, 0))
+                    on_event(j * S + a // B, g, a % B, (0, pauli_word, 0, 0))
                     a += 1
-                    r = px.philox4x32_10(group, 0x80000000 | j, int(c2[0, g]), int(c3[0, g]) | (d << 15), self.k0, self.k1)
-                    r0, r1 = int(r[0]), int(r[1])
-                    d += 1
 
     def _flip(self, arr, g, shot):
         w = g * self.K * 4 + (shot >> 5)

@@ -107,7 +107,7 @@ class Emulator:
 
     def run_batch(self, group, lam, evs):
         """Noise sites of one batch (evs[i](shot, r) = event callback of item i); see frame_oracle.run_sites."""
-        n, S, B = len(evs), 16, self.B  # GSTIM_NOISE_SLICE
+        n, S, B = len(evs), 32, self.B  # GSTIM_NOISE_SLICE
         gfirst = self.group_items.get(group, 0)
         self.group_items[group] = gfirst + n
         if lam == 0 or n == 0:
@@ -118,14 +118,17 @@ class Emulator:
             j = (gfirst + i0) // S
             total = min(S, n - i0) * B
             a = d = 0
+            words = None
             while True:
-                r = px.philox4x32_10(group, 0x80000000 | j, c2, hi | (d << 15), self.k0, self.k1)
+                if d % 2 == 0:  # one Philox call = two draws
+                    words = [int(v) for v in px.philox4x32_10(group, 0x80000000 | j, c2, hi | ((d // 2) << 15), self.k0, self.k1)]
+                gap_word, pauli_word = words[2 * (d % 2)], words[2 * (d % 2) + 1]
                 d += 1
-                G = px.exp_draw_fx(int(r[0])) // lam
+                G = px.exp_draw_fx(gap_word) // lam
                 if G >= total - a:
                     break
                 a += G
-                evs[i0 + a // B](a % B, (0, int(r[1]), 0, 0))
+                evs[i0 + a // B](a % B, (0, pauli_word, 0, 0))
                 a += 1
 
     def collapse(self, mgroup, q):

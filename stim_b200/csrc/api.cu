@@ -120,7 +120,7 @@ struct gstim_sampler {
     std::vector<uint32_t> words;
 
     // launch configuration
-    uint32_t threads = 0, G_log2 = 0, slots = 0, K_max = 0, chunk_words = 0;
+    uint32_t threads = 0, pre_threads = 0, G_log2 = 0, slots = 0, K_max = 0, chunk_words = 0;
     int num_sms = 0;
     size_t smem_optin = 0;
 
@@ -223,7 +223,8 @@ void configure(gstim_sampler *s) {
             break;
         }
     }
-    uint32_t slots = std::min<uint32_t>(1024, std::max<uint32_t>(32, (p95 + 31) / 32 * 32));
+    // (at most 768 interpreter threads: the other warps of the block produce the noise events one shot block ahead)
+    uint32_t slots = std::min<uint32_t>(768, std::max<uint32_t>(32, (p95 + 31) / 32 * 32));
     slots = env_u32("GSTIM_SLOTS", slots);
 
     // K_max from the shared-memory budget
@@ -260,6 +261,18 @@ void configure(gstim_sampler *s) {
     s->K_max = K_max;
     if (s->threads > 1024) {
         throw std::invalid_argument("internal: thread count exceeds 1024");
+    }
+    // noise producer warps (interp.cu): up to 256 threads next to the interpreter's
+    s->pre_threads = 0;
+    if (s->n_noise > 0 && s->threads + 32 <= 1024) {
+        uint32_t want = env_u32("GSTIM_PRE_THREADS", 256) / 32 * 32;
+        s->pre_threads = std::max<uint32_t>(32, std::min<uint32_t>(want, 1024 - s->threads));
+        if (env_u32("GSTIM_PRE_THREADS", 256) == 0) {
+            s->pre_threads = 0;  // timing experiments only: no noise events are produced
+        }
+    }
+    if (s->n_noise > 0 && s->pre_threads == 0 && env_u32("GSTIM_PRE_THREADS", 256) != 0) {
+        throw std::invalid_argument("internal: no room for the noise producer warps");
     }
 
     s->words = serialize_program(s->lc, slots, s->chunk_words, &s->plan);
@@ -373,7 +386,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
     uint64_t max_blocks = std::max<uint64_t>(table_budget / bytes_per_block, (uint64_t)s->num_sms);
     max_blocks = std::min(max_blocks, total_blocks);
     // persistent grid: as many blocks as fit on the device at once (shared memory usually allows one per SM)
-    uint32_t grid_cap = (uint32_t)s->num_sms * (uint32_t)interp_max_blocks_per_sm(s->threads, smem);
+    uint32_t grid_cap = (uint32_t)s->num_sms * (uint32_t)interp_max_blocks_per_sm(s->threads + s->pre_threads, smem);
     s->d_table.ensure(bytes_per_block * max_blocks);
     if (s->mode == GSTIM_MODE_DETECTORS) {
         s->d_rec.ensure((size_t)grid_cap * s->plan.rec_ring * K * 16);
@@ -406,8 +419,8 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
                                  ? n_noise * GSTIM_NOISE_INFO_WORDS * 4
                                  : 0;
     }
-    s->d_ev_counts.ensure(std::max<size_t>((size_t)grid_cap * n_noise * 4, 16));
-    s->d_ev_buf.ensure(std::max<size_t>((size_t)grid_cap * s->ev_total * 4, 16));
+    s->d_ev_counts.ensure(std::max<size_t>((size_t)grid_cap * 2 * n_noise * 4, 16));
+    s->d_ev_buf.ensure(std::max<size_t>((size_t)grid_cap * 2 * s->ev_total * 4, 16));
 
     if (s->next_col + total_blocks * K >= (1ull << 47)) {
         throw std::invalid_argument("shot offset + shots must stay below 2^54");
@@ -433,6 +446,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         p.K = K;
         p.G_log2 = s->G_log2;
         p.slots = s->slots;
+        p.threads_interp = s->threads;
         p.n_blocks = (uint32_t)nb;
         p.max_items = s->plan.max_items;
         p.n_noise = n_noise;
@@ -440,7 +454,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         p.noise_info = (const uint32_t *)s->d_noise_info.p;
         p.rates = (const ulonglong2 *)s->d_rates.p;
         p.slices = (const uint4 *)s->d_slices.p;
-        p.n_slices = (uint32_t)(s->lc.noise.slices.size() / 4);
+        p.n_slices = (uint32_t)(s->lc.noise.slices.size() / GSTIM_SLICE_WORDS);
         p.info_smem_bytes = s->info_smem_bytes;
         p.ev_segoff = (const uint32_t *)s->d_segoff.p;
         p.ev_counts = (uint32_t *)s->d_ev_counts.p;
@@ -474,7 +488,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
         }
         cudaEvent_t e0 = get_event(s, ev++), e1 = get_event(s, ev++), e2 = get_event(s, ev++);
         CK(cudaEventRecord(e0, s->stream));
-        CK(launch_interp(p, grid, s->threads, smem, s->stream));
+        CK(launch_interp(p, grid, s->threads + s->pre_threads, smem, s->stream));
         CK(cudaEventRecord(e1, s->stream));
         s->last_launches++;
         sink(first_shot, chunk_shots, (const uint32_t *)s->d_table.p, (uint64_t)std::max<uint32_t>(rows, 1));

@@ -11,7 +11,8 @@
 // (/root/reference/src/stim/util_bot/probability_util.cc:23-43) and the MeasureRecordBatch window
 // (/root/reference/src/stim/io/measure_record_batch.inl:49-104).
 //
-// Code structure: every opcode is a __noinline__ device function. A monolithic switch let the
+// Code structure: every opcode is a __noinline__ device function that returns the address of the next batch
+// (so the program cursor never has to survive a call in the caller's registers or, worse, in local memory). A monolithic switch let the
 // compiler hoist each case's loop invariants in front of the switch, which made every batch pay a
 // few hundred instructions per warp no matter which opcode it was (profiles/r1 notes).
 #include "kernels.cuh"
@@ -77,10 +78,17 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
+// (the source address is formed inside the asm block: when `base + offset` was left to the compiler, ptxas 12.9 folded it
+// into a 32-bit uniform ULEA with a zeroed high half in one build of this kernel)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *base, uint64_t offset_bytes, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .u64 a;\n"
+        "add.u64 a, %1, %4;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [a], %2, [%3];\n"
+        "}\n" ::"r"(dst),
+        "l"(base), "r"(bytes), "r"(bar), "l"(offset_bytes)
+        : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -94,6 +102,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
+}
+
+// Named barriers. The interpreter warps (threads [0, T_i)) synchronise among themselves on barrier 1; the noise
+// producer warps (threads [T_i, blockDim)) on barrier 6; event buffers are handed over with the arrive/sync pairs
+// FULL(b) = 2 + b (producers arrive, interpreter waits) and FREE(b) = 4 + b (interpreter arrives, producers wait).
+#define GSTIM_BAR_INTERP 1
+#define GSTIM_BAR_FULL 2
+#define GSTIM_BAR_FREE 4
+#define GSTIM_BAR_PRODUCERS 6
+// (barrier ids are immediates: with a register id ptxas reserves all 16 barriers and cannot pick the fast encoding)
+template <int ID>
+__device__ __forceinline__ void bar_sync(uint32_t count) {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void bar_arrive(uint32_t count) {
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void bar_sync2(uint32_t b, uint32_t count) {  // barrier ID + (b & 1)
+    if (b & 1u) {
+        bar_sync<ID + 1>(count);
+    } else {
+        bar_sync<ID>(count);
+    }
+}
+template <int ID>
+__device__ __forceinline__ void bar_arrive2(uint32_t b, uint32_t count) {
+    if (b & 1u) {
+        bar_arrive<ID + 1>(count);
+    } else {
+        bar_arrive<ID>(count);
+    }
 }
 
 __device__ __forceinline__ uint4 xor4(uint4 a, uint4 b) {
@@ -133,12 +174,20 @@ struct __align__(16) BlockCtx {
     const uint32_t *noise_info, *prog;
     uint32_t *ev_overflow;
     uint32_t n_slices, info_smem_bytes;
-    uint32_t n_noise, pad3;
+    uint32_t n_noise, T_i;             // T_i: interpreter threads (the remaining warps of the block produce noise events)
     uint32_t next_s;                   // shared counter the pre-pass threads claim chains from
     uint32_t ev_counts_s, ev_segoff_s; // shared-window addresses of the event counters / segment offsets (0: global)
     uint32_t stage_s;                  // 2 x GSTIM_EV_STAGE event records prefetched for the current / next noise batch
     unsigned long long *dbg;  // optional cycle counters (block 0 only)
     uint32_t dbg_flags, pad2;
+    // launch-wide constants of the two role loops (interp_role / producer_role)
+    uint32_t n_blocks, n_chunks, chunk_words, T_all;
+    uint32_t mbar_s, ev_s, ev_total, pad4;  // ev_s: shared-window address of the event counters (two buffers), 0 if in global memory
+    uint32_t *ring;
+    uint64_t col0_base;
+    uint4 *rec_base, *out_base;
+    uint64_t rec_block_stride, rec_cta_stride;
+    uint32_t *ev_counts_g, *ev_buf_g;
 };
 
 size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t n_noise) {
@@ -150,7 +199,7 @@ size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chun
     b += 512 * 4;                       // log2 table
     b += 128 * 8;                       // the first GSTIM_RATE_SMEM_MAX rates: lam, floor((2^64 - 1) / lam)
     if (n_noise <= GSTIM_EV_SMEM_MAX) {
-        b += ((size_t)(2 * n_noise + 1) * 4 + 15) / 16 * 16;  // event counters + segment offsets
+        b += ((size_t)(3 * n_noise + 1) * 4 + 15) / 16 * 16;  // event counters (two buffers) + segment offsets
     }
     b += 2 * GSTIM_EV_STAGE * 4;        // staged event records of the current / next noise batch
     b += 32;                            // mbarriers
@@ -215,43 +264,53 @@ __device__ __forceinline__ unsigned long long div_by_rate(unsigned long long E, 
     return q;
 }
 
-__device__ __noinline__ void noise_prepass(BlockCtx *bc) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    // The frame planes are not in use yet (the program starts by resetting every qubit), so they hold the
-    // noise info records when those fit.
-    const uint32_t info_bytes = bc->info_smem_bytes, info_s = bc->X_s;
-    const uint32_t *info_g = bc->noise_info;
-    for (uint32_t i = tid; i < info_bytes / 4; i += blockDim.x) {
-        sts32(info_s + 4 * i, info_g[i]);
-    }
+// Per-run arguments of the producers (the interpreter is working on another shot block at the same time).
+struct PrepassRun {
+    uint32_t col0_lo, col0_hi;  // first global column of the shot block
+    uint32_t cnt_s;             // shared-window address of this buffer's event counters (0: use `counts`)
+    uint32_t *counts;
+    uint32_t *evbuf;
+};
+
+__device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun run) {
+    const uint32_t T_p = blockDim.x - bc->T_i;
+    const uint32_t tid = threadIdx.x - bc->T_i, lane = tid & 31u;
     const uint32_t next_s = bc->next_s;
+    const uint32_t n_noise = bc->n_noise;
+    const uint32_t cnt_s = run.cnt_s, segoff_s = bc->ev_segoff_s;
+    uint32_t *evbuf = run.evbuf;
+    // (rarely used pointers are re-read from the BlockCtx where they are needed: registers are what limits this loop)
+    for (uint32_t i = tid; i < n_noise; i += T_p) {
+        if (cnt_s) {
+            sts32(cnt_s + 4 * i, 0);
+        } else {
+            run.counts[i] = 0;
+        }
+    }
     if (tid == 0) {
         sts32(next_s, 0);
     }
-    __syncthreads();
+    bar_sync<GSTIM_BAR_PRODUCERS>(T_p);
 
     const uint4 *slices = bc->slices;
-    const ulonglong2 *rates_g = bc->rates;
-    const uint32_t n_slices = bc->n_slices;
+    const uint32_t n_slices = (bc->dbg_flags & 1u) ? 0u : bc->n_slices;
     const uint32_t B = bc->B, lt_s = bc->lt_s, rates_s = bc->needs_s;
     const uint32_t magicB = 0xFFFFFFFFu / B + 1;  // floor(a / B) == umulhi(a, magicB) for a < 2^20 (B <= 4096)
-    const uint32_t k0 = bc->k0, k1 = bc->k1, col0_lo = bc->col0_lo, col0_hi = bc->col0_hi;
-    const uint32_t cnt_s = bc->ev_counts_s, segoff_s = bc->ev_segoff_s;
-    uint32_t *counts = bc->ev_counts;
-    const uint32_t *segoff = bc->ev_segoff;
-    uint32_t *evbuf = bc->ev_buf;
+    const uint32_t k0 = bc->k0, k1 = bc->k1, col0_lo = run.col0_lo, col0_hi = run.col0_hi;
 
-    unsigned long long *dbg = tid == 0 ? bc->dbg : nullptr;
-    const long long tA = clock64();
-    unsigned long long n_ev = 0, n_iter = 0, n_sl = 0;
+    const bool dbg_on = tid == 0 && !(bc->dbg_flags & 1u) && bc->dbg != nullptr;
+    const uint32_t tA = (uint32_t)clock64();
+    uint32_t n_ev = 0, n_iter = 0, n_sl = 0;
 
     uint32_t grp = 0, sl1 = 0, nbi = 0, item0 = 0, total = 0, a = 0, d = 0;
+    uint4 bh = make_uint4(0, 0, 0, 0);  // of the slice's batch: op | flags << 8 | aux << 16, T1, T2, T3
     unsigned long long lam = 1, inv = 0;
     // the next slice is claimed and its descriptor fetched while the current one is walked
     uint32_t nidx = atom_add_shared(next_s, 1);
-    uint4 nd = make_uint4(0, 0, 0, 0);
+    uint4 nd = make_uint4(0, 0, 0, 0), nh = nd;
     if (nidx < n_slices) {
-        nd = __ldg(slices + nidx);
+        nd = __ldg(slices + 2 * (size_t)nidx);
+        nh = __ldg(slices + 2 * (size_t)nidx + 1);
     }
     bool have = false;
     // An event record is written one event late: two consecutive events of a slice that flip the same 32-bit
@@ -259,6 +318,64 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
     // shared-memory atomics (2 cycles per lane on the LSU) by the interpreter; everything else is plain.
     bool pend = false;
     uint32_t pend_rec = 0;
+    const uint32_t same_word_mask = (GSTIM_EV_ITEM_MASK << GSTIM_EV_ITEM_SHIFT) | 0xFE0u;
+
+    // record of the event at shot-site `at` of the current slice, Pauli word y
+    auto make_rec = [&](uint32_t at, uint32_t y) -> uint32_t {
+        const uint32_t site = __umulhi(at, magicB), shot = at - site * B;
+        const uint32_t h0 = bh.x;
+        const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
+        uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
+        if (op == GOP_NOISE1) {
+            const uint32_t sel = y < bh.y ? 0u : y < bh.z ? 2u : y < bh.w ? 4u : 6u;
+            f = (aux >> sel) & 3u;
+            if (flags & GF_REC) {
+                f |= 16u;
+            }
+        } else if (op == GOP_NOISE2) {
+            if (!(flags & GF_TABLE)) {
+                f = 1u + __umulhi(y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
+            } else {
+                const uint32_t *tab = bc->prog + __ldg(bc->noise_info + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + GNI_TABLE_OFF);
+                uint32_t pr = aux;
+                for (uint32_t t = 0; t < 15; t++) {
+                    if (y < __ldg(tab + t)) {
+                        pr = t + 1;
+                        break;
+                    }
+                }
+                // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
+                const uint32_t c1p = pr >> 2, c2p = pr & 3u;
+                f = (((c1p + 1) >> 1) & 1u) | ((c1p >> 1) << 1) | ((((c2p + 1) >> 1) & 1u) << 2) | ((c2p >> 1) << 3);
+            }
+        }
+        return shot | ((item0 + site) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
+    };
+    // warp-aggregated append: the lanes that write a record for the same noise batch take consecutive places
+    auto emit = [&](uint32_t rec) {
+        const unsigned act = __activemask();
+        const unsigned peers = __match_any_sync(act, nbi);
+        const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0, seg0, cap;
+        if (cnt_s) {
+            seg0 = lds32(segoff_s + 4 * nbi);
+            cap = lds32(segoff_s + 4 * nbi + 4) - seg0;
+            if (lane == leader) {
+                base = atom_add_shared(cnt_s + 4 * nbi, __popc(peers));
+            }
+        } else {
+            seg0 = bc->ev_segoff[nbi];
+            cap = bc->ev_segoff[nbi + 1] - seg0;
+            if (lane == leader) {
+                base = atomicAdd(&run.counts[nbi], __popc(peers));
+            }
+        }
+        const uint32_t at = __shfl_sync(peers, base, leader) + rank;
+        if (at < cap) {  // (an overflowing segment is reported after the pre-pass)
+            evbuf[seg0 + at] = rec;
+        }
+    };
+
     while (true) {
         bool live = true;
         if (!have) {
@@ -273,6 +390,7 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
                 nbi = nd.z & 0xFFFFu;
                 item0 = nd.w & 0x7FFu;
                 total = (nd.w >> 11) * B;
+                bh = nh;
                 a = 0;
                 d = 0;
                 const uint32_t ri = nd.z >> 16;
@@ -280,7 +398,7 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
                     lam = lds64(rates_s + 16 * ri);
                     inv = lds64(rates_s + 16 * ri + 8);
                 } else {
-                    const ulonglong2 r = __ldg(rates_g + ri);
+                    const ulonglong2 r = __ldg(bc->rates + ri);
                     lam = r.x;
                     inv = r.y;
                 }
@@ -288,109 +406,86 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
                 n_sl++;
                 nidx = atom_add_shared(next_s, 1);
                 if (nidx < n_slices) {
-                    nd = __ldg(slices + nidx);
+                    nd = __ldg(slices + 2 * (size_t)nidx);
+                    nh = __ldg(slices + 2 * (size_t)nidx + 1);
                 }
             }
         }
-        bool emit = false;
-        uint32_t emit_rec = 0;
-        const uint32_t emit_nbi = nbi;  // a pending record always belongs to the current slice's batch
+        // records to write this iteration: the pending one and the first of up to two new events
+        bool has0 = false, has1 = false;
+        uint32_t out0 = 0, out1 = 0;
         if (live) {
             n_iter++;
+            // one Philox call = two draws (gap word, Pauli word): their clock arithmetic is independent of the
+            // position in the slice, so both are computed side by side and resolved in order afterwards
             const uint4 rr = philox4x32_10(grp, sl1, col0_lo, col0_hi | (d << GSTIM_DRAW_SHIFT), k0, k1);
             d++;
-            const unsigned long long E = exp_draw_fx(rr.x, lt_s);
-            const unsigned long long G = div_by_rate(E, lam, inv);
-            if (G >= (unsigned long long)(total - a)) {  // no further event in this slice
+            const unsigned long long G0 = div_by_rate(exp_draw_fx(rr.x, lt_s), lam, inv);
+            const unsigned long long G1 = div_by_rate(exp_draw_fx(rr.z, lt_s), lam, inv);
+            has0 = pend;
+            out0 = pend_rec;
+            pend = false;
+            if (G0 >= (unsigned long long)(total - a)) {  // no further event in this slice (the second draw is dropped)
                 have = false;
-                emit = pend;
-                emit_rec = pend_rec;
-                pend = false;
             } else {
-                // ---- exactly one event, at shot-site a + G of the slice
-                a += (uint32_t)G;
-                const uint32_t site = __umulhi(a, magicB), shot = a - site * B;
+                a += (uint32_t)G0;
+                uint32_t r0 = make_rec(a, rr.y);
                 a++;
-                const uint32_t h0 = info_bytes ? lds32(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4)) : __ldg(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS);
-                const uint32_t op = h0 & 0xFF, flags = (h0 >> 8) & 0xFF, aux = h0 >> 16;
-                uint32_t f = 0;  // bit0 x1, bit1 z1, bit2 x2, bit3 z2, bit4 record row
-                if (op == GOP_NOISE1) {
-                    uint4 i1;  // (group, t1, t2, t3)
-                    if (info_bytes) {
-                        i1 = lds128(info_s + nbi * (GSTIM_NOISE_INFO_WORDS * 4) + 16);
-                    } else {
-                        i1 = __ldg(reinterpret_cast<const uint4 *>(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + 4));
-                    }
-                    const uint32_t v = rr.y;
-                    const uint32_t sel = v < i1.y ? 0u : v < i1.z ? 2u : v < i1.w ? 4u : 6u;
-                    f = (aux >> sel) & 3u;
-                    if (flags & GF_REC) {
-                        f |= 16u;
-                    }
-                } else if (op == GOP_NOISE2) {
-                    if (!(flags & GF_TABLE)) {
-                        f = 1u + __umulhi(rr.y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
-                    } else {
-                        const uint32_t *tab = bc->prog + __ldg(info_g + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + GNI_TABLE_OFF);
-                        uint32_t pr = aux;
-                        for (uint32_t t = 0; t < 15; t++) {
-                            if (rr.y < __ldg(tab + t)) {
-                                pr = t + 1;
-                                break;
-                            }
-                        }
-                        // index = 4*P1 + P2 with P: 0=I 1=X 2=Y 3=Z (tableau_simulator.h:307-316)
-                        const uint32_t c1p = pr >> 2, c2p = pr & 3u;
-                        f = (((c1p + 1) >> 1) & 1u) | ((c1p >> 1) << 1) | ((((c2p + 1) >> 1) & 1u) << 2) | ((c2p >> 1) << 3);
-                    }
+                if (has0 && ((r0 ^ out0) & same_word_mask) == 0) {
+                    r0 |= GSTIM_EV_CONFLICT;
+                    out0 |= GSTIM_EV_CONFLICT;
                 }
-                uint32_t rec = shot | ((item0 + site) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
-                // same item and same 32-shot word as the previous event of this slice?
-                if (pend && ((rec ^ pend_rec) & ((GSTIM_EV_ITEM_MASK << GSTIM_EV_ITEM_SHIFT) | 0xFE0u)) == 0) {
-                    rec |= GSTIM_EV_CONFLICT;
-                    pend_rec |= GSTIM_EV_CONFLICT;
-                }
-                emit = pend;
-                emit_rec = pend_rec;
-                pend = true;
-                pend_rec = rec;
                 n_ev++;
+                if (G1 >= (unsigned long long)(total - a)) {
+                    have = false;
+                    has1 = true;
+                    out1 = r0;
+                } else {
+                    a += (uint32_t)G1;
+                    uint32_t r1 = make_rec(a, rr.w);
+                    a++;
+                    if (((r1 ^ r0) & same_word_mask) == 0) {
+                        r1 |= GSTIM_EV_CONFLICT;
+                        r0 |= GSTIM_EV_CONFLICT;
+                    }
+                    n_ev++;
+                    has1 = true;
+                    out1 = r0;
+                    pend = true;
+                    pend_rec = r1;
+                }
             }
         } else {
-            emit = true;
-            emit_rec = pend_rec;
+            has0 = true;
+            out0 = pend_rec;
             pend = false;
         }
-        if (emit) {
-            // warp-aggregated append: the lanes that write a record for the same noise batch take consecutive places
-            const unsigned act = __activemask();
-            const unsigned peers = __match_any_sync(act, emit_nbi);
-            const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t base = 0, seg0, cap;
-            if (cnt_s) {
-                seg0 = lds32(segoff_s + 4 * emit_nbi);
-                cap = lds32(segoff_s + 4 * emit_nbi + 4) - seg0;
-                if (lane == leader) {
-                    base = atom_add_shared(cnt_s + 4 * emit_nbi, __popc(peers));
-                }
-            } else {
-                seg0 = segoff[emit_nbi];
-                cap = segoff[emit_nbi + 1] - seg0;
-                if (lane == leader) {
-                    base = atomicAdd(&counts[emit_nbi], __popc(peers));
-                }
-            }
-            const uint32_t at = __shfl_sync(peers, base, leader) + rank;
-            if (at < cap) {  // (an overflowing segment is reported after the pre-pass)
-                evbuf[seg0 + at] = emit_rec;
-            }
+        if (has0) {
+            emit(out0);
+        }
+        if (has1) {
+            emit(out1);
         }
     }
-    if (dbg) {
-        dbg[32] += (unsigned long long)(clock64() - tA);
-        dbg[33] += n_ev;
-        dbg[34] += n_sl;
-        dbg[35] += n_iter;
+    if (dbg_on) {
+        bc->dbg[32] += (uint32_t)clock64() - tA;
+        bc->dbg[33] += n_ev;
+        bc->dbg[34] += n_sl;
+        bc->dbg[35] += n_iter;
+    }
+    bar_sync<GSTIM_BAR_PRODUCERS>(T_p);
+    // clamp the event counts to their segments (an overflow invalidates the call: the host reports it)
+    for (uint32_t i = tid; i < n_noise; i += T_p) {
+        const uint32_t cap = segoff_s ? lds32(segoff_s + 4 * i + 4) - lds32(segoff_s + 4 * i) : bc->ev_segoff[i + 1] - bc->ev_segoff[i];
+        const uint32_t c = cnt_s ? lds32(cnt_s + 4 * i) : run.counts[i];
+        if (c > cap) {
+            if (cnt_s) {
+                sts32(cnt_s + 4 * i, cap);
+            } else {
+                run.counts[i] = cap;
+            }
+            *bc->ev_overflow = 1u;
+        }
     }
 }
 
@@ -406,7 +501,7 @@ __device__ __noinline__ void noise_prepass(BlockCtx *bc) {
 // ------------------------------------------------------------------------------------------------
 // opcodes
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void op_cliff1(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_cliff1(const BlockCtx *bc, const uint32_t *hdr) {
     SLOT_SUB;
     const uint32_t aux = hdr[GH_OP] >> 16, n = hdr[GH_N];
     const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
@@ -420,9 +515,10 @@ __device__ __noinline__ void op_cliff1(const BlockCtx *bc, const uint32_t *hdr) 
             sts128(ax + zoff, xor4(and4(x, cc), and4(z, d)));
         }
     }
+    return hdr + hdr[GH_WORDS];
 }
 
-__device__ __noinline__ void op_cx(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_cx(const BlockCtx *bc, const uint32_t *hdr) {
     // CX: z1 ^= z2 ; x2 ^= x1   (frame_simulator.inl:387-405)
     SLOT_SUB;
     const uint32_t n = hdr[GH_N];
@@ -438,9 +534,10 @@ __device__ __noinline__ void op_cx(const BlockCtx *bc, const uint32_t *hdr) {
             sts128(a2, xor4(x2, x1));
         }
     }
+    return hdr + hdr[GH_WORDS];
 }
 
-__device__ __noinline__ void op_cliff2(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_cliff2(const BlockCtx *bc, const uint32_t *hdr) {
     SLOT_SUB;
     const uint32_t aux = hdr[GH_OP] >> 16, n = hdr[GH_N];
     const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
@@ -462,6 +559,7 @@ __device__ __noinline__ void op_cliff2(const BlockCtx *bc, const uint32_t *hdr) 
             sts128(a2 + zoff, xor4(xor4(and4(x1, m[12]), and4(z1, m[13])), xor4(and4(x2, m[14]), and4(z2, m[15]))));
         }
     }
+    return hdr + hdr[GH_WORDS];
 }
 
 // First record and (clamped) record count of noise batch `nbi` in this CTA's event scratch.
@@ -483,7 +581,7 @@ __device__ __forceinline__ void prefetch_events(const BlockCtx *bc, uint32_t nbi
         cnt = min(cnt, GSTIM_EV_STAGE);
         const uint32_t *ev = bc->ev_buf + seg0;
         const uint32_t st = bc->stage_s + (nbi & 1u) * (GSTIM_EV_STAGE * 4);
-        for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
+        for (uint32_t e = threadIdx.x; e < cnt; e += bc->T_i) {
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(st + 4 * e), "l"(ev + e) : "memory");
         }
     }
@@ -500,7 +598,7 @@ __device__ __forceinline__ void flip_atomic(uint32_t a, uint32_t bit) {
 // NOISE1 / NOISE2: apply the events the pre-pass left for this batch. Any thread applies any event, so the
 // batch is bracketed by block barriers. Two events of one batch touch the same 32-bit frame word only when the
 // pre-pass marked both GSTIM_EV_CONFLICT; only those use shared-memory atomics.
-__device__ __noinline__ void op_noise(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_noise(const BlockCtx *bc, const uint32_t *hdr) {
     const uint32_t hdr_s = smem_u32(hdr);
     const uint32_t h0 = lds32(hdr_s + 4 * GH_OP);
     const uint32_t flags = (h0 >> 8) & 0xFF;
@@ -511,9 +609,10 @@ __device__ __noinline__ void op_noise(const BlockCtx *bc, const uint32_t *hdr) {
     const uint32_t X_s = bc->X_s, zoff = bc->Z_s - bc->X_s, pitch_b = bc->pitch_b;
     const uint32_t st = bc->stage_s + (nbi & 1u) * (GSTIM_EV_STAGE * 4);
     prefetch_events(bc, nbi + 1);
+    const uint32_t T_i = bc->T_i;
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's records have landed
-    __syncthreads();
-    for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
+    bar_sync<GSTIM_BAR_INTERP>(T_i);
+    for (uint32_t e = threadIdx.x; e < cnt; e += T_i) {
         const uint32_t rec = e < GSTIM_EV_STAGE ? lds32(st + 4 * e) : bc->ev_buf[seg0 + e];
         const uint32_t shot = rec & ((1u << GSTIM_EV_SHOT_BITS) - 1);
         const uint32_t item = (rec >> GSTIM_EV_ITEM_SHIFT) & GSTIM_EV_ITEM_MASK;
@@ -558,11 +657,12 @@ __device__ __noinline__ void op_noise(const BlockCtx *bc, const uint32_t *hdr) {
             }
         }
     }
-    __syncthreads();
+    bar_sync<GSTIM_BAR_INTERP>(T_i);
+    return hdr + hdr[GH_WORDS];
 }
 
 
-__device__ __noinline__ void op_measure(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uint32_t *hdr) {
     SLOT_SUB;
     const uint32_t aux = hdr[GH_OP] >> 16, n = hdr[GH_N];
     const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
@@ -579,7 +679,7 @@ __device__ __noinline__ void op_measure(const BlockCtx *bc, const uint32_t *hdr)
         uint32_t ax = bc->X_s + q * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
             const uint64_t col = col0 + k;
-            const uint4 rnd = bc->dbg_flags & 2u ? make_uint4(0, 0, 0, 0) : philox4x32_10(mgroup, lq, (uint32_t)col, GTAG_COLLAPSE ^ (uint32_t)(col >> 32), k0, k1);
+            const uint4 rnd = philox4x32_10(mgroup, lq, (uint32_t)col, GTAG_COLLAPSE ^ (uint32_t)(col >> 32), k0, k1);
             const uint4 zero = make_uint4(0, 0, 0, 0);
             uint4 m, nx, nz;
             if (basis == GB_Z) {  // frame_simulator.inl:199-208, 266-274, 306-317
@@ -599,14 +699,15 @@ __device__ __noinline__ void op_measure(const BlockCtx *bc, const uint32_t *hdr)
             }
             sts128(ax, nx);
             sts128(ax + zoff, nz);
-            if (kind != GK_R && !(bc->dbg_flags & 64u)) {
+            if (kind != GK_R) {
                 rrow[k * rks] = m;
             }
         }
     }
+    return hdr + hdr[GH_WORDS];
 }
 
-__device__ __noinline__ void op_reczero(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_reczero(const BlockCtx *bc, const uint32_t *hdr) {
     SLOT_SUB;
     (void)pitch_b;
     (void)kstep;
@@ -617,9 +718,10 @@ __device__ __noinline__ void op_reczero(const BlockCtx *bc, const uint32_t *hdr)
             rrow[k * bc->rec_k_stride] = make_uint4(0, 0, 0, 0);
         }
     }
+    return hdr + hdr[GH_WORDS];
 }
 
-__device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uint32_t *hdr) {
     SLOT_SUB;
     (void)pitch_b;
     (void)kstep;
@@ -631,9 +733,8 @@ __device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr)
     // Record rows live in global memory (L2): keep up to 4 columns x 2 rows of loads in flight per thread
     // instead of one dependent load at a time.
     const uint32_t G = 1u << G_log2;
-    const uint32_t dbgf = bc->dbg_flags;
     for (uint32_t i = slot; i < n; i += slots) {
-        const uint32_t b0 = off[i], b1 = (dbgf & 16u) ? off[i] : off[i + 1];
+        const uint32_t b0 = off[i], b1 = off[i + 1];
         uint4 *orow = bc->out + dst[i];
         for (uint32_t k0 = sub; k0 < K; k0 += 4 * G) {
             uint4 acc[4];
@@ -673,16 +774,15 @@ __device__ __noinline__ void op_xorrows(const BlockCtx *bc, const uint32_t *hdr)
                     if (flags & GF_ACCUM) {
                         acc[u] = xor4(acc[u], orow[k * oks]);
                     }
-                    if (!(dbgf & 32u)) {
-                        orow[k * oks] = acc[u];
-                    }
+                    orow[k * oks] = acc[u];
                 }
             }
         }
     }
+    return hdr + hdr[GH_WORDS];
 }
 
-__device__ __noinline__ void op_obs_pauli(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_obs_pauli(const BlockCtx *bc, const uint32_t *hdr) {
     SLOT_SUB;
     const uint32_t n = hdr[GH_N];
     const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
@@ -703,9 +803,10 @@ __device__ __noinline__ void op_obs_pauli(const BlockCtx *bc, const uint32_t *hd
             orow[k * oks] = acc;
         }
     }
+    return hdr + hdr[GH_WORDS];
 }
 
-__device__ __noinline__ void op_feedback(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_feedback(const BlockCtx *bc, const uint32_t *hdr) {
     SLOT_SUB;
     const uint32_t n = hdr[GH_N];
     const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
@@ -724,14 +825,15 @@ __device__ __noinline__ void op_feedback(const BlockCtx *bc, const uint32_t *hdr
             }
         }
     }
+    return hdr + hdr[GH_WORDS];
 }
 
 // E / ELSE_CORRELATED_ERROR (frame_simulator.inl:747-776): one site for the whole Pauli product, masked by
 // (and recorded in) the block's "already occurred" row. Executed by a single thread from the pre-sampled events.
-__device__ __noinline__ void op_corr(const BlockCtx *bc, const uint32_t *hdr) {
+__device__ __noinline__ const uint32_t *op_corr(const BlockCtx *bc, const uint32_t *hdr) {
     prefetch_events(bc, hdr[GH_CSITE0] + 1);  // keeps the staging pipeline of op_noise going (this op reads its records directly)
     if (threadIdx.x != 0) {
-        return;
+        return hdr + hdr[GH_WORDS];
     }
     const uint32_t flags = (hdr[GH_OP] >> 8) & 0xFF, n = hdr[GH_N];
     const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
@@ -742,8 +844,8 @@ __device__ __noinline__ void op_corr(const BlockCtx *bc, const uint32_t *hdr) {
         }
     }
     const uint32_t nbi = hdr[GH_CSITE0];
-    const uint32_t seg0 = bc->ev_segoff[nbi], cap = bc->ev_segoff[nbi + 1] - seg0;
-    const uint32_t cnt = min(bc->ev_counts[nbi], cap);
+    uint32_t seg0, cnt;
+    event_segment(bc, nbi, seg0, cnt);
     const uint32_t *ev = bc->ev_buf + seg0;
     for (uint32_t e = 0; e < cnt; e++) {
         const uint32_t shot = ev[e] & ((1u << GSTIM_EV_SHOT_BITS) - 1);
@@ -762,6 +864,33 @@ __device__ __noinline__ void op_corr(const BlockCtx *bc, const uint32_t *hdr) {
                 }
             }
         }
+    }
+    return hdr + hdr[GH_WORDS];
+}
+
+// ------------------------------------------------------------------------------------------------
+// The two warp roles of a block. Everything they need lives in the BlockCtx, so each role keeps only its
+// own loop state in registers (the opcode functions use the full register budget).
+// ------------------------------------------------------------------------------------------------
+// Producer warps: the noise events of shot block run r go to event buffer r & 1, one run ahead of the interpreter.
+__device__ __noinline__ void producer_role(const BlockCtx *bc) {
+    const uint32_t T_all = bc->T_all, n_noise = bc->n_noise, n_blocks = bc->n_blocks;
+    uint32_t r = 0;
+    for (uint32_t g = blockIdx.x; g < n_blocks; g += gridDim.x, r++) {
+        const uint32_t b = r & 1u;
+        if (r >= 2) {
+            bar_sync2<GSTIM_BAR_FREE>(b, T_all);  // the interpreter is done with run r - 2
+        }
+        const uint64_t col0 = bc->col0_base + (uint64_t)g * bc->K;
+        PrepassRun run;
+        run.col0_lo = (uint32_t)col0;
+        run.col0_hi = (uint32_t)(col0 >> 32);
+        run.cnt_s = bc->ev_s ? bc->ev_s + 4 * b * n_noise : 0u;
+        run.counts = bc->ev_counts_g + ((size_t)blockIdx.x * 2 + b) * n_noise;
+        run.evbuf = bc->ev_buf_g + ((size_t)blockIdx.x * 2 + b) * bc->ev_total;
+        noise_prepass(bc, run);
+        __threadfence_block();
+        bar_arrive2<GSTIM_BAR_FULL>(b, T_all);
     }
 }
 
@@ -784,10 +913,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     sp += 512 * 4;
     const uint32_t needs_s = smem_u32(sp);
     sp += 128 * 8;
-    uint32_t *ev_s = (uint32_t *)sp;  // [n_noise] counters, [n_noise + 1] segment offsets (when they fit)
+    uint32_t *ev_s = (uint32_t *)sp;  // [2][n_noise] counters, [n_noise + 1] segment offsets (when they fit)
     const bool ev_in_smem = p.n_noise <= GSTIM_EV_SMEM_MAX;
     if (ev_in_smem) {
-        sp += ((size_t)(2 * p.n_noise + 1) * 4 + 15) / 16 * 16;
+        sp += ((size_t)(3 * p.n_noise + 1) * 4 + 15) / 16 * 16;
     }
     const uint32_t stage_s = smem_u32(sp);
     sp += 2 * GSTIM_EV_STAGE * 4;
@@ -796,9 +925,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     BlockCtx *bc = (BlockCtx *)sp;
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t T = blockDim.x;
-    const uint32_t chunk_bytes = p.chunk_words * 4;
-    const bool multi = p.G_log2 != 0;
+    const uint32_t T = p.threads_interp;   // interpreter threads; the rest of the block produces noise events
+    const uint32_t T_all = blockDim.x;
 
     if (tid == 0) {
         mbar_init(mbar_s, 1);
@@ -806,26 +934,24 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         bc->next_s = mbar_s + 16;
         bc->dbg_flags = p.dbg_flags;
         bc->dbg = blockIdx.x == 0 ? p.dbg_cycles : nullptr;
-        bc->info_smem_bytes = p.info_smem_bytes;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         bc->X_s = X_s;
         bc->Z_s = Z_s;
         bc->flag_s = flag_s;
         bc->lt_s = smem_u32(lt);
         bc->needs_s = needs_s;
-        bc->ev_segoff = ev_in_smem ? ev_s + p.n_noise : p.ev_segoff;
+        bc->ev_segoff = ev_in_smem ? ev_s + 2 * p.n_noise : p.ev_segoff;
+        bc->T_i = T;
         bc->slices = p.slices;
         bc->rates = p.rates;
-        bc->ev_counts_s = ev_in_smem ? smem_u32(ev_s) : 0u;
-        bc->ev_segoff_s = ev_in_smem ? smem_u32(ev_s + p.n_noise) : 0u;
+        bc->ev_counts_s = 0u;
+        bc->ev_segoff_s = ev_in_smem ? smem_u32(ev_s + 2 * p.n_noise) : 0u;
         bc->n_slices = p.n_slices;
         bc->n_noise = p.n_noise;
         bc->stage_s = stage_s;
         bc->noise_info = p.noise_info;
         bc->prog = p.prog;
         bc->ev_overflow = p.ev_overflow;
-        bc->ev_counts = ev_in_smem ? ev_s : p.ev_counts + (size_t)blockIdx.x * p.n_noise;
-        bc->ev_buf = p.ev_buf + (size_t)blockIdx.x * p.ev_segoff[p.n_noise];
         bc->pitch_b = p.q_pitch * 16;
         bc->K = p.K;
         bc->B = p.K * GSTIM_COL_SHOTS;
@@ -837,68 +963,83 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         bc->rec_k_stride = p.rec_k_stride;
         bc->out_k_stride = p.out_k_stride;
         bc->logical_of = p.logical_of;
+        bc->n_blocks = p.n_blocks;
+        bc->n_chunks = p.n_chunks;
+        bc->chunk_words = p.chunk_words;
+        bc->T_all = T_all;
+        bc->mbar_s = mbar_s;
+        bc->ev_s = ev_in_smem ? smem_u32(ev_s) : 0u;
+        bc->ev_total = p.ev_segoff[p.n_noise];
+        bc->ring = ring;
+        bc->col0_base = p.col0_base;
+        bc->rec_base = p.rec;
+        bc->out_base = p.out;
+        bc->rec_block_stride = p.rec_block_stride;
+        bc->rec_cta_stride = p.rec_cta_stride;
+        bc->ev_counts_g = p.ev_counts;
+        bc->ev_buf_g = p.ev_buf;
     }
-    for (uint32_t i = tid; i < 256; i += T) {
+    for (uint32_t i = tid; i < 256; i += T_all) {
         lt[i] = GSTIM_LOG2_BASE[i];
         lt[256 + i] = GSTIM_LOG2_DIFF[i];
     }
-    for (uint32_t i = tid; i < min(p.n_rates, GSTIM_RATE_SMEM_MAX); i += T) {
+    for (uint32_t i = tid; i < min(p.n_rates, GSTIM_RATE_SMEM_MAX); i += T_all) {
         const ulonglong2 r = p.rates[i];
         sts64(needs_s + 16 * i, r.x);
         sts64(needs_s + 16 * i + 8, r.y);
     }
     if (ev_in_smem) {
-        for (uint32_t i = tid; i <= p.n_noise; i += T) {
-            ev_s[p.n_noise + i] = p.ev_segoff[i];
+        for (uint32_t i = tid; i <= p.n_noise; i += T_all) {
+            ev_s[2 * p.n_noise + i] = p.ev_segoff[i];
         }
     }
     __syncthreads();
-    uint32_t phase0 = 0, phase1 = 0;
+
+    if (tid >= T) {
+        producer_role(bc);
+        return;
+    }
+
+    // Interpreter warps: stream the program through the ring and execute it batch by batch. This loop lives in the kernel:
+    // the state that is live across the opcode calls must stay within the few registers the callees leave alone,
+    // because anything pushed to local memory is reloaded at L2 latency (the frame leaves almost no L1).
+    // (kernel parameters are constant-bank operands: they cost no registers)
+    const uint32_t chunk_words = p.chunk_words, chunk_bytes = chunk_words * 4;
+    const bool multi = p.G_log2 != 0;
+    const uint32_t skipmask = p.dbg_flags >> 8;  // debug: bit (op) set -> skip that opcode
+    uint32_t phase0 = 0, phase1 = 0, run_idx = 0;
     long long dbg_t0 = clock64();
 
-    for (uint32_t g = blockIdx.x; g < p.n_blocks; g += gridDim.x) {
-        const uint64_t col0 = p.col0_base + (uint64_t)g * p.K;
+    for (uint32_t g = blockIdx.x; g < p.n_blocks; g += gridDim.x, run_idx++) {
+        const uint32_t eb = run_idx & 1u;
+        const bool has_producers = blockDim.x > T;
         if (tid == 0) {
+            const uint64_t col0 = p.col0_base + (uint64_t)g * p.K;
+            const uint32_t n_noise = p.n_noise;
             bc->col0_lo = (uint32_t)col0;
             bc->col0_hi = (uint32_t)(col0 >> 32);
+            bc->ev_counts_s = bc->ev_s ? bc->ev_s + 4 * eb * n_noise : 0u;
+            bc->ev_counts = bc->ev_s ? nullptr : p.ev_counts + ((size_t)blockIdx.x * 2 + eb) * n_noise;  // (global fallback)
+            bc->ev_buf = p.ev_buf + ((size_t)blockIdx.x * 2 + eb) * bc->ev_total;
             bc->rec = p.rec + (uint64_t)g * p.rec_block_stride + (uint64_t)blockIdx.x * p.rec_cta_stride;
             bc->out = p.out + (uint64_t)g * p.K * p.out_k_stride;
             // start streaming the program
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(mbar_s, chunk_bytes);
-            bulk_g2s(smem_u32(ring), p.prog, chunk_bytes, mbar_s);
+            bulk_g2s(smem_u32(ring), p.prog, 0, chunk_bytes, mbar_s);
             if (p.n_chunks > 1) {
                 mbar_expect_tx(mbar_s + 8, chunk_bytes);
-                bulk_g2s(smem_u32(ring + p.chunk_words), p.prog + p.chunk_words, chunk_bytes, mbar_s + 8);
+                bulk_g2s(smem_u32(ring + chunk_words), p.prog, chunk_bytes, chunk_bytes, mbar_s + 8);
             }
         }
         for (uint32_t k = tid; k < p.K; k += T) {
-            sts128(flag_s + 16 * k, make_uint4(0, 0, 0, 0));
+            sts128(bc->flag_s + 16 * k, make_uint4(0, 0, 0, 0));
         }
-        {
-            uint32_t *counts = ev_in_smem ? ev_s : p.ev_counts + (size_t)blockIdx.x * p.n_noise;
-            for (uint32_t i = tid; i < p.n_noise; i += T) {
-                counts[i] = 0;
-            }
+        if (has_producers) {
+            bar_sync2<GSTIM_BAR_FULL>(eb, blockDim.x);  // this run's noise events are in place (also orders the bc updates above)
+        } else {
+            bar_sync<GSTIM_BAR_INTERP>(T);
         }
-        __syncthreads();
-        if (!(p.dbg_flags & 1u)) {
-            noise_prepass(bc);
-        }
-        __syncthreads();
-        {
-            // clamp the event counts to their segments (an overflow invalidates the call: the host reports it)
-            uint32_t *counts = ev_in_smem ? ev_s : p.ev_counts + (size_t)blockIdx.x * p.n_noise;
-            const uint32_t *so = ev_in_smem ? ev_s + p.n_noise : p.ev_segoff;
-            for (uint32_t i = tid; i < p.n_noise; i += T) {
-                const uint32_t cap = so[i + 1] - so[i];
-                if (counts[i] > cap) {
-                    counts[i] = cap;
-                    *p.ev_overflow = 1u;
-                }
-            }
-        }
-        __syncthreads();
         prefetch_events(bc, 0);
 
         for (uint32_t chunk = 0;; chunk++) {
@@ -913,8 +1054,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
                     phase0 ^= 1;
                 }
             }
-            const uint32_t *pw = ring + (size_t)b * p.chunk_words;
+            const uint32_t *pw = ring + (size_t)b * chunk_words;
             bool end = false;
+            // (test the constant-bank parameter first: loop state that is only needed for the optional
+            // instrumentation must not sit between the opcode calls)
             if (p.dbg_cycles != nullptr && tid == 0 && blockIdx.x == 0) {
                 const long long t1 = clock64();
                 p.dbg_cycles[GOP_NEXT_CHUNK] += (unsigned long long)(t1 - dbg_t0);  // chunk hand-over + ring wait
@@ -931,45 +1074,45 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
                     break;
                 }
                 if (h0 & (GF_BARRIER << 8)) {
-                    __syncthreads();
+                    bar_sync<GSTIM_BAR_INTERP>(T);
                 } else if (multi) {
                     __syncwarp();
                 }
-                const uint32_t skipmask = p.dbg_flags >> 8;  // debug: bit (op) set -> skip that opcode
                 switch ((skipmask >> op) & 1u ? (uint32_t)GOP_QMAP : op) {
                     case GOP_CLIFF1:
-                        op_cliff1(bc, pw);
+                        pw = op_cliff1(bc, pw);
                         break;
                     case GOP_CLIFF2:
                         if ((h0 >> 16) == GSTIM_MAT_CX) {
-                            op_cx(bc, pw);
+                            pw = op_cx(bc, pw);
                         } else {
-                            op_cliff2(bc, pw);
+                            pw = op_cliff2(bc, pw);
                         }
                         break;
                     case GOP_NOISE1:
                     case GOP_NOISE2:
-                        op_noise(bc, pw);
+                        pw = op_noise(bc, pw);
                         break;
                     case GOP_MEASURE:
-                        op_measure(bc, pw);
+                        pw = op_measure(bc, pw);
                         break;
                     case GOP_RECZERO:
-                        op_reczero(bc, pw);
+                        pw = op_reczero(bc, pw);
                         break;
                     case GOP_XORROWS:
-                        op_xorrows(bc, pw);
+                        pw = op_xorrows(bc, pw);
                         break;
                     case GOP_OBS_PAULI:
-                        op_obs_pauli(bc, pw);
+                        pw = op_obs_pauli(bc, pw);
                         break;
                     case GOP_FEEDBACK:
-                        op_feedback(bc, pw);
+                        pw = op_feedback(bc, pw);
                         break;
                     case GOP_CORR:
-                        op_corr(bc, pw);
+                        pw = op_corr(bc, pw);
                         break;
                     default:  // GOP_QMAP and unknown words are skipped
+                        pw += pw[GH_WORDS];
                         break;
                 }
                 if (p.dbg_cycles != nullptr && tid == 0 && blockIdx.x == 0) {
@@ -978,18 +1121,20 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
                     p.dbg_cycles[16 + op] += 1;
                     dbg_t0 = t1;
                 }
-                pw += pw[GH_WORDS];
             }
-            __syncthreads();  // everyone is done reading ring[b]
+            bar_sync<GSTIM_BAR_INTERP>(T);  // everyone is done reading ring[b]
             if (end) {
                 break;
             }
             if (tid == 0 && chunk + 2 < p.n_chunks) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(mbar_s + 8 * b, chunk_bytes);
-                bulk_g2s(smem_u32(ring + (size_t)b * p.chunk_words), p.prog + (size_t)(chunk + 2) * p.chunk_words, chunk_bytes,
+                bulk_g2s(smem_u32(ring + (size_t)b * chunk_words), p.prog, (uint64_t)(chunk + 2) * chunk_bytes, chunk_bytes,
                          mbar_s + 8 * b);
             }
+        }
+        if (has_producers && (uint64_t)g + 2ull * gridDim.x < bc->n_blocks) {
+            bar_arrive2<GSTIM_BAR_FREE>(eb, blockDim.x);  // event buffer eb may be refilled (for run run_idx + 2)
         }
     }
 }
@@ -1010,17 +1155,22 @@ cudaError_t interp_set_max_smem(size_t smem) {
     if ((e = set_attr<768>(smem)) != cudaSuccess) {
         return e;
     }
+    if ((e = set_attr<896>(smem)) != cudaSuccess) {
+        return e;
+    }
     return set_attr<1024>(smem);
 }
 
 cudaError_t launch_interp(const InterpParams &p, uint32_t grid, uint32_t threads, size_t smem, cudaStream_t stream) {
-    // the register budget follows the block size: 255 / 128 / 80 / 64 registers per thread
+    // the register budget follows the block size: 255 / 128 / 80 / 72 / 64 registers per thread
     if (threads <= 256) {
         gstim_interp_kernel<256><<<grid, threads, smem, stream>>>(p);
     } else if (threads <= 512) {
         gstim_interp_kernel<512><<<grid, threads, smem, stream>>>(p);
     } else if (threads <= 768) {
         gstim_interp_kernel<768><<<grid, threads, smem, stream>>>(p);
+    } else if (threads <= 896) {
+        gstim_interp_kernel<896><<<grid, threads, smem, stream>>>(p);
     } else {
         gstim_interp_kernel<1024><<<grid, threads, smem, stream>>>(p);
     }
@@ -1036,6 +1186,8 @@ int interp_max_blocks_per_sm(uint32_t threads, size_t smem) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gstim_interp_kernel<512>, (int)threads, smem);
     } else if (threads <= 768) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gstim_interp_kernel<768>, (int)threads, smem);
+    } else if (threads <= 896) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gstim_interp_kernel<896>, (int)threads, smem);
     } else {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gstim_interp_kernel<1024>, (int)threads, smem);
     }

@@ -16,7 +16,8 @@ struct InterpParams {
     uint32_t q_pitch;          // shared-memory row pitch (uint4 units), odd
     uint32_t K;                // 128-shot columns per thread block
     uint32_t G_log2;           // log2(lanes per item)
-    uint32_t slots;            // blockDim.x >> G_log2
+    uint32_t slots;            // threads_interp >> G_log2
+    uint32_t threads_interp;   // interpreter threads = the first warps of the block; the remaining warps produce noise events
     uint32_t n_blocks;         // shot blocks in this launch
     uint32_t max_items;        // largest batch (sizes the event job queue)
     uint64_t col0_base;        // global column index (shot/128) of block 0
@@ -28,19 +29,19 @@ struct InterpParams {
     uint32_t rec_mask;         // ring mask (detector mode) or 0xFFFFFFFF
     uint4 *out;                // detector/observable table, column-major: out[column * out_k_stride + row]; block g owns columns [g*K,(g+1)*K)
     uint64_t out_k_stride;     // uint4 units between columns (= number of rows)
-    uint32_t dbg_flags;        // GSTIM_DEBUG_FLAGS: timing experiments only (results become wrong): bit0 no pre-pass, bit1 no collapse RNG, bits 8+op skip opcode
+    uint32_t dbg_flags;        // GSTIM_DEBUG_FLAGS: timing experiments only (results become wrong): bit0 no noise events, bits 8+op skip opcode
     unsigned long long *dbg_cycles;  // optional (GSTIM_DEBUG_CYCLES=1): [op] cycles and [16+op] batch counts seen by block 0
     // noise schedule (program.h) and the per-CTA event scratch the pre-pass fills
     uint32_t n_noise;                 // noise batches
     uint32_t n_rates;                 // distinct rates
     const uint32_t *noise_info;       // n_noise * GSTIM_NOISE_INFO_WORDS
     const ulonglong2 *rates;          // per rate: lam, floor((2^64 - 1) / lam)
-    const uint4 *slices;              // RNG slices (program.h "Noise schedule")
+    const uint4 *slices;              // RNG slices, 2 uint4 each (program.h "Noise schedule")
     uint32_t n_slices;
     uint32_t info_smem_bytes;         // n_noise * 48 when the info records are staged in shared memory, else 0
     const uint32_t *ev_segoff;        // n_noise + 1 : event segment offsets for this launch's block size
-    uint32_t *ev_counts;              // gridDim.x * n_noise
-    uint32_t *ev_buf;                 // gridDim.x * ev_segoff[n_noise]
+    uint32_t *ev_counts;              // gridDim.x * 2 * n_noise (two event buffers per CTA)
+    uint32_t *ev_buf;                 // gridDim.x * 2 * ev_segoff[n_noise]
     uint32_t *ev_overflow;            // set to 1 if any segment overflowed (host retries with more room)
 };
 

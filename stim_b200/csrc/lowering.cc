@@ -1344,8 +1344,9 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
                 }
                 for (uint32_t i0 = 0; i0 < info[GNI_N]; i0 += GSTIM_NOISE_SLICE) {
                     const uint32_t cnt = std::min<uint32_t>(GSTIM_NOISE_SLICE, info[GNI_N] - i0);
-                    const uint32_t sl[4] = {b.site0, (gfirst + i0) / GSTIM_NOISE_SLICE, nbi | (rate << 16), i0 | (cnt << 11)};
-                    ns.slices.insert(ns.slices.end(), sl, sl + 4);
+                    const uint32_t sl[GSTIM_SLICE_WORDS] = {b.site0, (gfirst + i0) / GSTIM_NOISE_SLICE, nbi | (rate << 16), i0 | (cnt << 11),
+                                                            info[GNI_H0], b.t1, b.t2, b.t3};
+                    ns.slices.insert(ns.slices.end(), sl, sl + GSTIM_SLICE_WORDS);
                 }
             }
         }

@@ -40,7 +40,7 @@ struct NoiseSchedule {
     std::vector<uint32_t> n_sites;    // per noise batch
     std::vector<uint64_t> lams;       // per noise batch (fixed-point rate)
     std::vector<uint64_t> rates;      // distinct rates: 2 words each, lam and floor((2^64 - 1) / lam)
-    std::vector<uint32_t> slices;     // 4 words per RNG slice (program.h "Noise schedule"), in program order
+    std::vector<uint32_t> slices;     // GSTIM_SLICE_WORDS per RNG slice (program.h "Noise schedule"), in program order
 };
 
 struct LoweredCircuit {

@@ -77,7 +77,8 @@ enum GstimHdr : uint32_t {
 
 // Philox counters (key = seed):
 //   collapse of a qubit:    (measure group, logical qubit, global column lo, 'COLL' ^ global column hi)
-//   draw d of a noise slice: (noise group, 0x80000000 | slice index in the group, col0 lo, col0 hi | d << 15)
+//   call c of a noise slice: (noise group, 0x80000000 | slice index in the group, col0 lo, col0 hi | c << 15)
+//     -> draws 2c (words 0, 1) and 2c + 1 (words 2, 3); a draw = (gap word, Pauli word of the event the gap leads to)
 // col0 = global column of the shot block's first column (< 2^47).
 #define GTAG_COLLAPSE 0x434F4C4Cu
 #define GSTIM_SLICE_FLAG 0x80000000u
@@ -88,12 +89,14 @@ enum GstimHdr : uint32_t {
 // cut into SLICES of GSTIM_NOISE_SLICE consecutive sites; a slice x a shot block is one Bernoulli sequence
 // (site-major, then shot) walked with geometric gaps drawn from the slice's own Philox stream, like the
 // reference's RareErrorIterator over targets x shots. Lowering never cuts a group into batches inside a slice.
-//   slice (4 words): noise group, slice index in the group, noise batch ordinal | rate index << 16,
-//                    first item of the slice in its batch | number of sites << 11
+//   slice (8 words): noise group, slice index in the group, noise batch ordinal | rate index << 16,
+//                    first item of the slice in its batch | number of sites << 11,
+//                    then what an event needs from its batch header: op | flags << 8 | aux << 16, T1, T2, T3
 //   rate  (2 u64):   lam, floor((2^64 - 1) / lam)
 // The kernel's event pre-pass walks the slices and leaves compact event records for the interpreter:
 //   record = shot (bits 0-11) | item (12-22) | flips x1,z1,x2,z2 (23-26) | record flip (27) | conflict (28).
-#define GSTIM_NOISE_SLICE 16u
+#define GSTIM_NOISE_SLICE 32u
+#define GSTIM_SLICE_WORDS 8u
 #define GSTIM_RATE_SMEM_MAX 64u    // the first 64 rates are mirrored in shared memory
 #define GSTIM_NOISE_INFO_WORDS 12u
 enum GstimNoiseInfo : uint32_t {
