@@ -262,16 +262,16 @@ void configure(gstim_sampler *s) {
     if (s->threads > 1024) {
         throw std::invalid_argument("internal: thread count exceeds 1024");
     }
-    // noise producer warps (interp.cu): up to 256 threads next to the interpreter's
+    // noise producer warps (interp.cu): 128 threads next to the interpreter's keep the block at 768 threads = 80 registers
     s->pre_threads = 0;
     if (s->n_noise > 0 && s->threads + 32 <= 1024) {
-        uint32_t want = env_u32("GSTIM_PRE_THREADS", 256) / 32 * 32;
+        uint32_t want = env_u32("GSTIM_PRE_THREADS", 128) / 32 * 32;
         s->pre_threads = std::max<uint32_t>(32, std::min<uint32_t>(want, 1024 - s->threads));
-        if (env_u32("GSTIM_PRE_THREADS", 256) == 0) {
+        if (env_u32("GSTIM_PRE_THREADS", 128) == 0) {
             s->pre_threads = 0;  // timing experiments only: no noise events are produced
         }
     }
-    if (s->n_noise > 0 && s->pre_threads == 0 && env_u32("GSTIM_PRE_THREADS", 256) != 0) {
+    if (s->n_noise > 0 && s->pre_threads == 0 && env_u32("GSTIM_PRE_THREADS", 128) != 0) {
         throw std::invalid_argument("internal: no room for the noise producer warps");
     }
 

@@ -274,7 +274,7 @@ struct PrepassRun {
 
 __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun run) {
     const uint32_t T_p = blockDim.x - bc->T_i;
-    const uint32_t tid = threadIdx.x - bc->T_i, lane = tid & 31u;
+    const uint32_t tid = threadIdx.x - bc->T_i;
     const uint32_t next_s = bc->next_s;
     const uint32_t n_noise = bc->n_noise;
     const uint32_t cnt_s = run.cnt_s, segoff_s = bc->ev_segoff_s;
@@ -351,26 +351,19 @@ __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun 
         }
         return shot | ((item0 + site) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
     };
-    // warp-aggregated append: the lanes that write a record for the same noise batch take consecutive places
+    // append a record to its noise batch's segment (lanes of a warp work on neighbouring slices, so the places they
+    // get are mostly consecutive and the stores coalesce)
     auto emit = [&](uint32_t rec) {
-        const unsigned act = __activemask();
-        const unsigned peers = __match_any_sync(act, nbi);
-        const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
-        uint32_t base = 0, seg0, cap;
+        uint32_t seg0, cap, at;
         if (cnt_s) {
             seg0 = lds32(segoff_s + 4 * nbi);
             cap = lds32(segoff_s + 4 * nbi + 4) - seg0;
-            if (lane == leader) {
-                base = atom_add_shared(cnt_s + 4 * nbi, __popc(peers));
-            }
+            at = atom_add_shared(cnt_s + 4 * nbi, 1u);
         } else {
             seg0 = bc->ev_segoff[nbi];
             cap = bc->ev_segoff[nbi + 1] - seg0;
-            if (lane == leader) {
-                base = atomicAdd(&run.counts[nbi], __popc(peers));
-            }
+            at = atomicAdd(&run.counts[nbi], 1u);
         }
-        const uint32_t at = __shfl_sync(peers, base, leader) + rank;
         if (at < cap) {  // (an overflowing segment is reported after the pre-pass)
             evbuf[seg0 + at] = rec;
         }
@@ -1008,7 +1001,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     const bool multi = p.G_log2 != 0;
     const uint32_t skipmask = p.dbg_flags >> 8;  // debug: bit (op) set -> skip that opcode
     uint32_t phase0 = 0, phase1 = 0, run_idx = 0;
+#ifdef GSTIM_CYCLE_COUNTERS
+    // per-opcode cycle counters (GSTIM_DEBUG_CYCLES=1): compiled in only on request, because even the test of
+    // `tid == 0` costs a local-memory reload per batch when tid does not survive the opcode calls in a register
     long long dbg_t0 = clock64();
+#endif
 
     for (uint32_t g = blockIdx.x; g < p.n_blocks; g += gridDim.x, run_idx++) {
         const uint32_t eb = run_idx & 1u;
@@ -1056,13 +1053,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
             }
             const uint32_t *pw = ring + (size_t)b * chunk_words;
             bool end = false;
-            // (test the constant-bank parameter first: loop state that is only needed for the optional
-            // instrumentation must not sit between the opcode calls)
+#ifdef GSTIM_CYCLE_COUNTERS
             if (p.dbg_cycles != nullptr && tid == 0 && blockIdx.x == 0) {
                 const long long t1 = clock64();
                 p.dbg_cycles[GOP_NEXT_CHUNK] += (unsigned long long)(t1 - dbg_t0);  // chunk hand-over + ring wait
                 dbg_t0 = t1;
             }
+#endif
             while (true) {
                 const uint32_t h0 = pw[GH_OP];
                 const uint32_t op = h0 & 0xFF;
@@ -1115,12 +1112,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
                         pw += pw[GH_WORDS];
                         break;
                 }
+#ifdef GSTIM_CYCLE_COUNTERS
                 if (p.dbg_cycles != nullptr && tid == 0 && blockIdx.x == 0) {
                     const long long t1 = clock64();
                     p.dbg_cycles[op] += (unsigned long long)(t1 - dbg_t0);
                     p.dbg_cycles[16 + op] += 1;
                     dbg_t0 = t1;
                 }
+#endif
             }
             bar_sync<GSTIM_BAR_INTERP>(T);  // everyone is done reading ring[b]
             if (end) {
