@@ -236,7 +236,8 @@ class Emulator:
             elif op == OP_MEASURE:
                 basis, kind = aux & 3, (aux >> 2) & 3
                 for i in range(n):
-                    q = int(pay[i])
+                    q = int(pay[i]) & 0xFFFF
+                    assert int(pay[i]) >> 16 == self.logical_of[q]
                     self.touch(i % S, q, True)
                     rnd = self.collapse(csite0, q)
                     x, z = self.x[q].copy(), self.z[q].copy()

@@ -664,15 +664,14 @@ __device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uin
     const uint32_t zoff = bc->Z_s - bc->X_s;
     const uint32_t k0 = bc->k0, k1 = bc->k1;
     const uint64_t col0 = ((uint64_t)bc->col0_hi << 32) | bc->col0_lo;
+    const uint64_t rks = bc->rec_k_stride;
+    const uint32_t kinc = 1u << G_log2;
     for (uint32_t i = slot; i < n; i += slots) {
-        const uint32_t q = pay[i];
-        const uint32_t lq = bc->logical_of[q];
+        const uint32_t w = pay[i];
+        const uint32_t q = w & 0xFFFFu, lq = w >> 16;  // physical frame row | logical qubit (addresses the collapse draws)
         uint4 *rrow = bc->rec + ((rec0 + i) & bc->rec_mask);
-        const uint64_t rks = bc->rec_k_stride;
-        uint32_t ax = bc->X_s + q * 16 + sub * pitch_b;
-        for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
-            const uint64_t col = col0 + k;
-            const uint4 rnd = philox4x32_10(mgroup, lq, (uint32_t)col, GTAG_COLLAPSE ^ (uint32_t)(col >> 32), k0, k1);
+        // collapse one column: measurement result m, new frame components
+        auto column = [&](uint32_t k, uint32_t ax, const uint4 rnd) {
             const uint4 zero = make_uint4(0, 0, 0, 0);
             uint4 m, nx, nz;
             if (basis == GB_Z) {  // frame_simulator.inl:199-208, 266-274, 306-317
@@ -694,6 +693,18 @@ __device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uin
             sts128(ax + zoff, nz);
             if (kind != GK_R) {
                 rrow[k * rks] = m;
+            }
+        };
+        uint32_t ax = bc->X_s + q * 16 + sub * pitch_b;
+        // two columns per trip: their Philox chains are independent and overlap in the pipeline
+        for (uint32_t k = sub; k < K; k += 2 * kinc, ax += 2 * kstep) {
+            const uint64_t ca = col0 + k, cb = ca + kinc;
+            const bool two = k + kinc < K;
+            const uint4 ra = philox4x32_10(mgroup, lq, (uint32_t)ca, GTAG_COLLAPSE ^ (uint32_t)(ca >> 32), k0, k1);
+            const uint4 rb = philox4x32_10(mgroup, lq, (uint32_t)cb, GTAG_COLLAPSE ^ (uint32_t)(cb >> 32), k0, k1);
+            column(k, ax, ra);
+            if (two) {
+                column(k + kinc, ax + kstep, rb);
             }
         }
     }

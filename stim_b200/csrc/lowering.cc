@@ -954,9 +954,13 @@ void assign_physical_rows(LoweredCircuit &lc) {
         size_t skip = item_skip(b);
         switch (b.op) {
             case GOP_CLIFF1:
-            case GOP_MEASURE:
                 for (auto &w : b.payload) {
                     w = phys[w];
+                }
+                break;
+            case GOP_MEASURE:  // physical row | logical index << 16 (the logical index addresses the collapse draws)
+                for (auto &w : b.payload) {
+                    w = phys[w] | (w << 16);
                 }
                 break;
             case GOP_NOISE1:

@@ -28,7 +28,7 @@ enum GstimOp : uint32_t {
     GOP_CLIFF2 = 3,      // aux = 4x4 GF(2) matrix over (x1,z1,x2,z2), 4 bits per output. item: q1 | q2<<16
     GOP_NOISE1 = 4,      // single-target Pauli noise site per item. item: qubit (clock + frame target)
     GOP_NOISE2 = 5,      // two-target Pauli noise site per item. item: q1 | q2<<16 (clock = q1)
-    GOP_MEASURE = 6,     // aux = basis | kind<<2. item: qubit
+    GOP_MEASURE = 6,     // aux = basis | kind<<2. item: qubit (physical row) | logical qubit index << 16
     GOP_RECZERO = 7,     // zero record rows rec0 .. rec0+n-1 (no payload)
     GOP_XORROWS = 8,     // out row (^)= XOR of record rows. payload: dst[n], off[n+1], idx[...]
     GOP_OBS_PAULI = 9,   // out row ^= frame component. payload per item: dst row, qubit | x<<30 | z<<31
