@@ -32,6 +32,16 @@ ALG_LOP3_PER_SHOT = 168026 / 32  # XOR word-ops of the frame algorithm per shot 
 LOP3_LANES_PER_CLK_PER_SM = 64   # B300_MICROARCH.md: alu pipe rt_SMSP = 2 -> 16 lanes/clk/SMSP
 
 
+def measured_traffic_bytes_per_shot():
+    """DRAM bytes per shot of the interpreter kernel from the committed `ncu --set full` capture (profiles/r1_interp_full.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_interp_full.json")) as f:
+            d = json.load(f)
+        return (float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])) / float(d["shots"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -228,6 +238,7 @@ def main():
     del host, host_np
 
     peak, peak_src = measured_peak_gbs()
+    traffic_per_shot = measured_traffic_bytes_per_shot()
     interp_s = interp_ms * 1e-3
     achieved = ALG_BYTES_PER_SHOT * shots * args.steps / interp_s / 1e9
     sm_mhz = clk.get("sm_mhz") or 1965.0
@@ -241,7 +252,8 @@ def main():
             "workload": WORKLOAD, "shots_per_gpu_per_step": shots, "output": "b8 dets+obs, 1951 B/shot, resident in HBM",
             "circuit": "tests/golden/circuits/c3_surface_z_d25_r25.stim",
             "l2": "each step writes 32.7 GB of fresh output (>> 126 MB L2); nothing is reused across steps",
-            "threads": int(sampler.stats.threads), "columns_per_block": sampler.last_block_columns(),
+            "threads": int(sampler.stats.threads), "noise_producer_threads": 128,
+            "columns_per_block": sampler.last_block_columns(),
             "detection_fraction_check": frac,
         },
         "gpu_launches": launches,
@@ -253,7 +265,10 @@ def main():
         },
         "roofline": {
             "kernel": "gstim_interp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak,
+            "traffic": (None if traffic_per_shot is None else traffic_per_shot * shots * args.steps / interp_launches),
+            "traffic_source": "dram__bytes_read+write of profiles/r1_interp_full.json scaled to the shots of one launch",
+            "peak_source": peak_src,
             "launches": interp_launches, "avg_launch_ms": interp_ms / interp_launches,
             "alg_bytes_per_launch": ALG_BYTES_PER_SHOT * shots * args.steps / interp_launches,
             "alu_bound": {"lop3_per_shot": ALG_LOP3_PER_SHOT, "achieved_lop3_per_s": per_gpu_rate_interp * ALG_LOP3_PER_SHOT,
