@@ -581,9 +581,6 @@ __device__ __forceinline__ void prefetch_events(const BlockCtx *bc, uint32_t nbi
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__device__ __forceinline__ void flip_plain(uint32_t a, uint32_t bit) {
-    sts32(a, lds32(a) ^ bit);
-}
 __device__ __forceinline__ void flip_atomic(uint32_t a, uint32_t bit) {
     asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(bit) : "memory");
 }
@@ -632,17 +629,31 @@ __device__ __noinline__ const uint32_t *op_noise(const BlockCtx *bc, const uint3
                 atomicXor(rw, bit);
             }
         } else {
+            // all loads first, then the stores: the (up to four) words are independent
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
             if (f & 1u) {
-                flip_plain(a1, bit);
+                w0 = lds32(a1);
             }
             if (f & 2u) {
-                flip_plain(a1 + zoff, bit);
+                w1 = lds32(a1 + zoff);
             }
             if (f & 4u) {
-                flip_plain(a2, bit);
+                w2 = lds32(a2);
             }
             if (f & 8u) {
-                flip_plain(a2 + zoff, bit);
+                w3 = lds32(a2 + zoff);
+            }
+            if (f & 1u) {
+                sts32(a1, w0 ^ bit);
+            }
+            if (f & 2u) {
+                sts32(a1 + zoff, w1 ^ bit);
+            }
+            if (f & 4u) {
+                sts32(a2, w2 ^ bit);
+            }
+            if (f & 8u) {
+                sts32(a2 + zoff, w3 ^ bit);
             }
             if (f & 16u) {
                 uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + ((rec0 + item) & bc->rec_mask)) + ((shot >> 5) & 3);
@@ -734,37 +745,38 @@ __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uin
     const uint32_t *dst = pay, *off = pay + n, *idx = pay + 2 * n + 1;
     const uint4 *rec = bc->rec;
     const uint64_t rks = bc->rec_k_stride, oks = bc->out_k_stride;
-    // Record rows live in global memory (L2): keep up to 4 columns x 2 rows of loads in flight per thread
-    // instead of one dependent load at a time.
+    // Record rows live in global memory (L2): a trip keeps up to XR_COLS columns x 2 rows of loads in flight per
+    // thread instead of one dependent load at a time (6 columns per trip was slower: register pressure).
+    constexpr int XR_COLS = 4;
     const uint32_t G = 1u << G_log2;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t b0 = off[i], b1 = off[i + 1];
         uint4 *orow = bc->out + dst[i];
-        for (uint32_t k0 = sub; k0 < K; k0 += 4 * G) {
-            uint4 acc[4];
+        for (uint32_t k0 = sub; k0 < K; k0 += XR_COLS * G) {
+            uint4 acc[XR_COLS];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < XR_COLS; u++) {
                 acc[u] = make_uint4(0, 0, 0, 0);
             }
             uint32_t j = b0;
             for (; j + 2 <= b1; j += 2) {
                 const uint4 *r0 = rec + idx[j], *r1 = rec + idx[j + 1];
-                uint4 v0[4], v1[4];
+                uint4 v0[XR_COLS], v1[XR_COLS];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < XR_COLS; u++) {
                     const uint32_t k = k0 + u * G;
                     v0[u] = k < K ? r0[k * rks] : make_uint4(0, 0, 0, 0);
                     v1[u] = k < K ? r1[k * rks] : make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < XR_COLS; u++) {
                     acc[u] = xor4(acc[u], xor4(v0[u], v1[u]));
                 }
             }
             if (j < b1) {
                 const uint4 *r0 = rec + idx[j];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < XR_COLS; u++) {
                     const uint32_t k = k0 + u * G;
                     if (k < K) {
                         acc[u] = xor4(acc[u], r0[k * rks]);
@@ -772,7 +784,7 @@ __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uin
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < XR_COLS; u++) {
                 const uint32_t k = k0 + u * G;
                 if (k < K) {
                     if (flags & GF_ACCUM) {
