@@ -55,6 +55,23 @@ def test_generated_detectors_match_oracle(code, task, d, r, p, shots):
     check_detectors(gen_circuit(code, task, d, r, p), shots, seed=1234 + shots)
 
 
+def test_many_noise_batches_use_global_event_counters():
+    """> 2048 noise batches: the event counters / segment offsets no longer fit shared memory (GSTIM_EV_SMEM_MAX)."""
+    text = gen_circuit("repetition_code", "memory", 3, 700, 0.01)
+    s = check_detectors(text, 300, seed=4321)
+    assert s.stats.num_batches > 2048
+
+
+def test_producers_run_ahead_over_many_shot_blocks(monkeypatch):
+    """One column per block -> every CTA executes several shot blocks, so the producer warps reuse both event
+    buffers (FREE / FULL barrier hand-over) while the interpreter is still busy with the previous block."""
+    monkeypatch.setenv("GSTIM_KMAX", "1")
+    monkeypatch.setenv("GSTIM_G_LOG2", "0")  # one lane per item, otherwise K is at least the lanes per item
+    text = gen_circuit("surface_code", "rotated_memory_z", 3, 2, 0.03)
+    s = check_detectors(text, 128 * 148 * 3 + 77, seed=77)
+    assert s.last_block_columns() == 1
+
+
 @pytest.mark.parametrize("code,task,d,r,p", GENERATED[:5])
 def test_generated_measurements_match_oracle(code, task, d, r, p):
     check_measurements(gen_circuit(code, task, d, r, p), 1500, seed=99)
