@@ -105,7 +105,7 @@ class _Sampler:
 
     def __del__(self):
         h = getattr(self, "_handle", None)
-        if h is not None and h.value:
+        if h is not None and h.value and _native is not None:  # (module globals are None during interpreter shutdown)
             _native.lib().gstim_destroy(h)
             self._handle = ctypes.c_void_p()
 

