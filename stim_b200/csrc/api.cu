@@ -363,7 +363,7 @@ RowMaps measurement_row_maps(const gstim_sampler *s) {
 // One pass of the sampler over `shots` shots. For every chunk, `sink(chunk_first_shot, chunk_shots,
 // table, row_words)` is called after the interpreter kernel has been enqueued on s->stream.
 template <typename SINK>
-void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
+void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_mb = 2048) {
     CK(cudaSetDevice(s->device));
     s->last_launches = 0;
     s->last_interp_ms = 0;
@@ -381,12 +381,15 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink) {
     const uint64_t total_blocks = (shots + B - 1) / B;
 
     // chunking: bit-major staging table limited to ~2 GiB
-    const uint64_t table_budget = (uint64_t)env_u32("GSTIM_TABLE_MB", 2048) << 20;
+    // (host delivery passes a smaller budget: it is bound by the PCIe copy, and short chunks fill that pipeline sooner)
+    const uint64_t table_budget = (uint64_t)env_u32("GSTIM_TABLE_MB", table_mb) << 20;
     const uint64_t bytes_per_block = (uint64_t)std::max<uint32_t>(rows, 1) * K * 16;
-    uint64_t max_blocks = std::max<uint64_t>(table_budget / bytes_per_block, (uint64_t)s->num_sms);
-    max_blocks = std::min(max_blocks, total_blocks);
     // persistent grid: as many blocks as fit on the device at once (shared memory usually allows one per SM)
     uint32_t grid_cap = (uint32_t)s->num_sms * (uint32_t)interp_max_blocks_per_sm(s->threads + s->pre_threads, smem);
+    uint64_t max_blocks = std::max<uint64_t>(table_budget / bytes_per_block, (uint64_t)grid_cap);
+    // whole waves only: a chunk of 11.07 waves costs 12 (the CTAs walk their shot blocks in lock step)
+    max_blocks = max_blocks / grid_cap * grid_cap;
+    max_blocks = std::min(max_blocks, total_blocks);
     s->d_table.ensure(bytes_per_block * max_blocks);
     if (s->mode == GSTIM_MODE_DETECTORS) {
         s->d_rec.ensure((size_t)grid_cap * s->plan.rec_ring * K * 16);
@@ -734,7 +737,7 @@ void sample_to_host(
         pending[cur].first = first;
         pending[cur].n = n;
         cur ^= 1;
-    });
+    }, 512);
     drain(cur);
     drain(cur ^ 1);
 }
