@@ -71,6 +71,18 @@ __device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
     asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 
+// A run of 32-bit words in shared memory, read with LDS (a generic pointer into the program ring would be read with
+// generic loads: long-scoreboard latency on the per-batch critical path).
+struct SmemWords {
+    uint32_t s;
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const {
+        return lds32(s + 4 * i);
+    }
+    __device__ __forceinline__ SmemWords operator+(uint32_t n) const {
+        return SmemWords{s + 4 * n};
+    }
+};
+
 // mbarrier / bulk-async copy helpers (PTX ISA: mbarrier, cp.async.bulk)
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -495,9 +507,10 @@ __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun 
 // opcodes
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ const uint32_t *op_cliff1(const BlockCtx *bc, const uint32_t *hdr) {
+    const SmemWords hw{smem_u32(hdr)};
     SLOT_SUB;
-    const uint32_t aux = hdr[GH_OP] >> 16, n = hdr[GH_N];
-    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t aux = hw[GH_OP] >> 16, n = hw[GH_N];
+    const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const uint32_t a = bitmask(aux, 0), b = bitmask(aux, 1), cc = bitmask(aux, 2), d = bitmask(aux, 3);
     const uint32_t zoff = bc->Z_s - bc->X_s;
     for (uint32_t i = slot; i < n; i += slots) {
@@ -508,14 +521,15 @@ __device__ __noinline__ const uint32_t *op_cliff1(const BlockCtx *bc, const uint
             sts128(ax + zoff, xor4(and4(x, cc), and4(z, d)));
         }
     }
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 __device__ __noinline__ const uint32_t *op_cx(const BlockCtx *bc, const uint32_t *hdr) {
+    const SmemWords hw{smem_u32(hdr)};
     // CX: z1 ^= z2 ; x2 ^= x1   (frame_simulator.inl:387-405)
     SLOT_SUB;
-    const uint32_t n = hdr[GH_N];
-    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t n = hw[GH_N];
+    const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const uint32_t zoff = bc->Z_s - bc->X_s;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[i];
@@ -527,13 +541,14 @@ __device__ __noinline__ const uint32_t *op_cx(const BlockCtx *bc, const uint32_t
             sts128(a2, xor4(x2, x1));
         }
     }
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 __device__ __noinline__ const uint32_t *op_cliff2(const BlockCtx *bc, const uint32_t *hdr) {
+    const SmemWords hw{smem_u32(hdr)};
     SLOT_SUB;
-    const uint32_t aux = hdr[GH_OP] >> 16, n = hdr[GH_N];
-    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t aux = hw[GH_OP] >> 16, n = hw[GH_N];
+    const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const uint32_t zoff = bc->Z_s - bc->X_s;
     uint32_t m[16];
 #pragma unroll
@@ -552,7 +567,7 @@ __device__ __noinline__ const uint32_t *op_cliff2(const BlockCtx *bc, const uint
             sts128(a2 + zoff, xor4(xor4(and4(x1, m[12]), and4(z1, m[13])), xor4(and4(x2, m[14]), and4(z2, m[15]))));
         }
     }
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 // First record and (clamped) record count of noise batch `nbi` in this CTA's event scratch.
@@ -589,7 +604,8 @@ __device__ __forceinline__ void flip_atomic(uint32_t a, uint32_t bit) {
 // batch is bracketed by block barriers. Two events of one batch touch the same 32-bit frame word only when the
 // pre-pass marked both GSTIM_EV_CONFLICT; only those use shared-memory atomics.
 __device__ __noinline__ const uint32_t *op_noise(const BlockCtx *bc, const uint32_t *hdr) {
-    const uint32_t hdr_s = smem_u32(hdr);
+    const SmemWords hw{smem_u32(hdr)};
+    const uint32_t hdr_s = hw.s;
     const uint32_t h0 = lds32(hdr_s + 4 * GH_OP);
     const uint32_t flags = (h0 >> 8) & 0xFF;
     const uint32_t items_s = hdr_s + 4 * GSTIM_HDR_WORDS + (((h0 & 0xFF) == GOP_NOISE2 && (flags & GF_TABLE)) ? 60u : 0u);
@@ -662,16 +678,17 @@ __device__ __noinline__ const uint32_t *op_noise(const BlockCtx *bc, const uint3
         }
     }
     bar_sync<GSTIM_BAR_INTERP>(T_i);
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 
 __device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uint32_t *hdr) {
+    const SmemWords hw{smem_u32(hdr)};
     SLOT_SUB;
-    const uint32_t aux = hdr[GH_OP] >> 16, n = hdr[GH_N];
-    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t aux = hw[GH_OP] >> 16, n = hw[GH_N];
+    const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const uint32_t basis = aux & 3u, kind = (aux >> 2) & 3u;
-    const uint32_t mgroup = hdr[GH_CSITE0], rec0 = hdr[GH_REC0];
+    const uint32_t mgroup = hw[GH_CSITE0], rec0 = hw[GH_REC0];
     const uint32_t zoff = bc->Z_s - bc->X_s;
     const uint32_t k0 = bc->k0, k1 = bc->k1;
     const uint64_t col0 = ((uint64_t)bc->col0_hi << 32) | bc->col0_lo;
@@ -719,30 +736,32 @@ __device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uin
             }
         }
     }
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 __device__ __noinline__ const uint32_t *op_reczero(const BlockCtx *bc, const uint32_t *hdr) {
+    const SmemWords hw{smem_u32(hdr)};
     SLOT_SUB;
     (void)pitch_b;
     (void)kstep;
-    const uint32_t n = hdr[GH_N], rec0 = hdr[GH_REC0];
+    const uint32_t n = hw[GH_N], rec0 = hw[GH_REC0];
     for (uint32_t i = slot; i < n; i += slots) {
         uint4 *rrow = bc->rec + ((rec0 + i) & bc->rec_mask);
         for (uint32_t k = sub; k < K; k += 1u << G_log2) {
             rrow[k * bc->rec_k_stride] = make_uint4(0, 0, 0, 0);
         }
     }
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uint32_t *hdr) {
+    const SmemWords hw{smem_u32(hdr)};
     SLOT_SUB;
     (void)pitch_b;
     (void)kstep;
-    const uint32_t flags = (hdr[GH_OP] >> 8) & 0xFF, n = hdr[GH_N];
-    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
-    const uint32_t *dst = pay, *off = pay + n, *idx = pay + 2 * n + 1;
+    const uint32_t flags = (hw[GH_OP] >> 8) & 0xFF, n = hw[GH_N];
+    const SmemWords pay = hw + GSTIM_HDR_WORDS;
+    const SmemWords dst = pay, off = pay + n, idx = pay + 2 * n + 1;
     const uint4 *rec = bc->rec;
     const uint64_t rks = bc->rec_k_stride, oks = bc->out_k_stride;
     // Record rows live in global memory (L2): a trip keeps up to XR_COLS columns x 2 rows of loads in flight per
@@ -795,13 +814,14 @@ __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uin
             }
         }
     }
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 __device__ __noinline__ const uint32_t *op_obs_pauli(const BlockCtx *bc, const uint32_t *hdr) {
+    const SmemWords hw{smem_u32(hdr)};
     SLOT_SUB;
-    const uint32_t n = hdr[GH_N];
-    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t n = hw[GH_N];
+    const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const uint32_t zoff = bc->Z_s - bc->X_s;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[2 * i + 1];
@@ -819,13 +839,14 @@ __device__ __noinline__ const uint32_t *op_obs_pauli(const BlockCtx *bc, const u
             orow[k * oks] = acc;
         }
     }
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 __device__ __noinline__ const uint32_t *op_feedback(const BlockCtx *bc, const uint32_t *hdr) {
+    const SmemWords hw{smem_u32(hdr)};
     SLOT_SUB;
-    const uint32_t n = hdr[GH_N];
-    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t n = hw[GH_N];
+    const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const uint32_t zoff = bc->Z_s - bc->X_s;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[2 * i + 1];
@@ -841,25 +862,26 @@ __device__ __noinline__ const uint32_t *op_feedback(const BlockCtx *bc, const ui
             }
         }
     }
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 // E / ELSE_CORRELATED_ERROR (frame_simulator.inl:747-776): one site for the whole Pauli product, masked by
 // (and recorded in) the block's "already occurred" row. Executed by a single thread from the pre-sampled events.
 __device__ __noinline__ const uint32_t *op_corr(const BlockCtx *bc, const uint32_t *hdr) {
-    prefetch_events(bc, hdr[GH_CSITE0] + 1);  // keeps the staging pipeline of op_noise going (this op reads its records directly)
+    const SmemWords hw{smem_u32(hdr)};
+    prefetch_events(bc, hw[GH_CSITE0] + 1);  // keeps the staging pipeline of op_noise going (this op reads its records directly)
     if (threadIdx.x != 0) {
-        return hdr + hdr[GH_WORDS];
+        return hdr + hw[GH_WORDS];
     }
-    const uint32_t flags = (hdr[GH_OP] >> 8) & 0xFF, n = hdr[GH_N];
-    const uint32_t *pay = hdr + GSTIM_HDR_WORDS;
+    const uint32_t flags = (hw[GH_OP] >> 8) & 0xFF, n = hw[GH_N];
+    const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const uint32_t flag_s = bc->flag_s;
     if (flags & GF_RESET_FLAG) {
         for (uint32_t k = 0; k < bc->K; k++) {
             sts128(flag_s + 16 * k, make_uint4(0, 0, 0, 0));
         }
     }
-    const uint32_t nbi = hdr[GH_CSITE0];
+    const uint32_t nbi = hw[GH_CSITE0];
     uint32_t seg0, cnt;
     event_segment(bc, nbi, seg0, cnt);
     const uint32_t *ev = bc->ev_buf + seg0;
@@ -881,7 +903,7 @@ __device__ __noinline__ const uint32_t *op_corr(const BlockCtx *bc, const uint32
             }
         }
     }
-    return hdr + hdr[GH_WORDS];
+    return hdr + hw[GH_WORDS];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1084,7 +1106,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
             }
 #endif
             while (true) {
-                const uint32_t h0 = pw[GH_OP];
+                const uint32_t h0 = lds32(smem_u32(pw) + 4 * GH_OP);
                 const uint32_t op = h0 & 0xFF;
                 if (op == GOP_END) {
                     end = true;
@@ -1132,7 +1154,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
                         pw = op_corr(bc, pw);
                         break;
                     default:  // GOP_QMAP and unknown words are skipped
-                        pw += pw[GH_WORDS];
+                        pw += lds32(smem_u32(pw) + 4 * GH_WORDS);
                         break;
                 }
 #ifdef GSTIM_CYCLE_COUNTERS
