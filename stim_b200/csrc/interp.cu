@@ -501,6 +501,7 @@ __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun 
     const uint32_t slots = bc->slots;                 \
     const uint32_t K = bc->K;                         \
     const uint32_t pitch_b = bc->pitch_b;             \
+    const uint32_t X_s = bc->X_s;                     \
     const uint32_t kstep = pitch_b << G_log2
 
 // ------------------------------------------------------------------------------------------------
@@ -512,9 +513,9 @@ __device__ __noinline__ const uint32_t *op_cliff1(const BlockCtx *bc, const uint
     const uint32_t aux = hw[GH_OP] >> 16, n = hw[GH_N];
     const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const uint32_t a = bitmask(aux, 0), b = bitmask(aux, 1), cc = bitmask(aux, 2), d = bitmask(aux, 3);
-    const uint32_t zoff = bc->Z_s - bc->X_s;
+    const uint32_t zoff = bc->Z_s - X_s;
     for (uint32_t i = slot; i < n; i += slots) {
-        uint32_t ax = bc->X_s + pay[i] * 16 + sub * pitch_b;
+        uint32_t ax = X_s + pay[i] * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
             const uint4 x = lds128(ax), z = lds128(ax + zoff);
             sts128(ax, xor4(and4(x, a), and4(z, b)));
@@ -530,11 +531,11 @@ __device__ __noinline__ const uint32_t *op_cx(const BlockCtx *bc, const uint32_t
     SLOT_SUB;
     const uint32_t n = hw[GH_N];
     const SmemWords pay = hw + GSTIM_HDR_WORDS;
-    const uint32_t zoff = bc->Z_s - bc->X_s;
+    const uint32_t zoff = bc->Z_s - X_s;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[i];
-        uint32_t a1 = bc->X_s + (w & 0xFFFF) * 16 + sub * pitch_b;
-        uint32_t a2 = bc->X_s + (w >> 16) * 16 + sub * pitch_b;
+        uint32_t a1 = X_s + (w & 0xFFFF) * 16 + sub * pitch_b;
+        uint32_t a2 = X_s + (w >> 16) * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, a1 += kstep, a2 += kstep) {
             const uint4 x1 = lds128(a1), z2 = lds128(a2 + zoff), z1 = lds128(a1 + zoff), x2 = lds128(a2);
             sts128(a1 + zoff, xor4(z1, z2));
@@ -549,7 +550,7 @@ __device__ __noinline__ const uint32_t *op_cliff2(const BlockCtx *bc, const uint
     SLOT_SUB;
     const uint32_t aux = hw[GH_OP] >> 16, n = hw[GH_N];
     const SmemWords pay = hw + GSTIM_HDR_WORDS;
-    const uint32_t zoff = bc->Z_s - bc->X_s;
+    const uint32_t zoff = bc->Z_s - X_s;
     uint32_t m[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
@@ -557,8 +558,8 @@ __device__ __noinline__ const uint32_t *op_cliff2(const BlockCtx *bc, const uint
     }
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[i];
-        uint32_t a1 = bc->X_s + (w & 0xFFFF) * 16 + sub * pitch_b;
-        uint32_t a2 = bc->X_s + (w >> 16) * 16 + sub * pitch_b;
+        uint32_t a1 = X_s + (w & 0xFFFF) * 16 + sub * pitch_b;
+        uint32_t a2 = X_s + (w >> 16) * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, a1 += kstep, a2 += kstep) {
             const uint4 x1 = lds128(a1), z1 = lds128(a1 + zoff), x2 = lds128(a2), z2 = lds128(a2 + zoff);
             sts128(a1, xor4(xor4(and4(x1, m[0]), and4(z1, m[1])), xor4(and4(x2, m[2]), and4(z2, m[3]))));
@@ -682,59 +683,75 @@ __device__ __noinline__ const uint32_t *op_noise(const BlockCtx *bc, const uint3
 }
 
 
-__device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uint32_t *hdr) {
-    const SmemWords hw{smem_u32(hdr)};
+// MEASURE body for one (basis, kind): the per-column code has no data-dependent branches left.
+template <uint32_t BASIS, uint32_t KIND>
+__device__ __forceinline__ void measure_items(const BlockCtx *bc, const SmemWords hw) {
     SLOT_SUB;
-    const uint32_t aux = hw[GH_OP] >> 16, n = hw[GH_N];
+    const uint32_t n = hw[GH_N];
     const SmemWords pay = hw + GSTIM_HDR_WORDS;
-    const uint32_t basis = aux & 3u, kind = (aux >> 2) & 3u;
     const uint32_t mgroup = hw[GH_CSITE0], rec0 = hw[GH_REC0];
-    const uint32_t zoff = bc->Z_s - bc->X_s;
+    const uint32_t zoff = bc->Z_s - X_s;
     const uint32_t k0 = bc->k0, k1 = bc->k1;
-    const uint64_t col0 = ((uint64_t)bc->col0_hi << 32) | bc->col0_lo;
+    const uint32_t col_lo = bc->col0_lo, col_hi = bc->col0_hi, tag_hi = GTAG_COLLAPSE ^ col_hi;
+    uint4 *const rec = bc->rec;
+    const uint32_t rec_mask = bc->rec_mask;
     const uint64_t rks = bc->rec_k_stride;
     const uint32_t kinc = 1u << G_log2;
+    const bool carry_free = col_lo + K >= col_lo;  // the K columns of the block do not cross a 2^32 column boundary
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[i];
         const uint32_t q = w & 0xFFFFu, lq = w >> 16;  // physical frame row | logical qubit (addresses the collapse draws)
-        uint4 *rrow = bc->rec + ((rec0 + i) & bc->rec_mask);
-        // collapse one column: measurement result m, new frame components
-        auto column = [&](uint32_t k, uint32_t ax, const uint4 rnd) {
+        uint4 *rrow = rec + ((rec0 + i) & rec_mask) + (uint64_t)sub * rks;
+        uint32_t ax = X_s + q * 16 + sub * pitch_b;
+        for (uint32_t k = sub; k < K; k += kinc, ax += kstep, rrow += (uint64_t)kinc * rks) {
+            uint32_t c2 = col_lo + k, c3 = tag_hi;
+            if (!carry_free && c2 < col_lo) {
+                c3 = GTAG_COLLAPSE ^ (col_hi + 1);
+            }
+            const uint4 rnd = philox4x32_10(mgroup, lq, c2, c3, k0, k1);
             const uint4 zero = make_uint4(0, 0, 0, 0);
             uint4 m, nx, nz;
-            if (basis == GB_Z) {  // frame_simulator.inl:199-208, 266-274, 306-317
+            if (BASIS == GB_Z) {  // frame_simulator.inl:199-208, 266-274, 306-317
                 const uint4 x = lds128(ax);
                 m = x;
-                nx = kind == GK_M ? x : zero;
+                nx = KIND == GK_M ? x : zero;
                 nz = rnd;
-            } else if (basis == GB_X) {  // :173-182, 211-219, 277-288
+            } else if (BASIS == GB_X) {  // :173-182, 211-219, 277-288
                 const uint4 z = lds128(ax + zoff);
                 m = z;
-                nz = kind == GK_M ? z : zero;
+                nz = KIND == GK_M ? z : zero;
                 nx = rnd;
             } else {  // Y basis :185-196, 255-263, 291-303
                 m = xor4(lds128(ax), lds128(ax + zoff));
                 nz = rnd;
-                nx = kind == GK_M ? xor4(m, rnd) : rnd;
+                nx = KIND == GK_M ? xor4(m, rnd) : rnd;
             }
-            sts128(ax, nx);
-            sts128(ax + zoff, nz);
-            if (kind != GK_R) {
-                rrow[k * rks] = m;
+            if (!(BASIS == GB_Z && KIND == GK_M)) {  // (M in the Z basis leaves x as it is)
+                sts128(ax, nx);
             }
-        };
-        uint32_t ax = bc->X_s + q * 16 + sub * pitch_b;
-        // two columns per trip: their Philox chains are independent and overlap in the pipeline
-        for (uint32_t k = sub; k < K; k += 2 * kinc, ax += 2 * kstep) {
-            const uint64_t ca = col0 + k, cb = ca + kinc;
-            const bool two = k + kinc < K;
-            const uint4 ra = philox4x32_10(mgroup, lq, (uint32_t)ca, GTAG_COLLAPSE ^ (uint32_t)(ca >> 32), k0, k1);
-            const uint4 rb = philox4x32_10(mgroup, lq, (uint32_t)cb, GTAG_COLLAPSE ^ (uint32_t)(cb >> 32), k0, k1);
-            column(k, ax, ra);
-            if (two) {
-                column(k + kinc, ax + kstep, rb);
+            if (!(BASIS == GB_X && KIND == GK_M)) {
+                sts128(ax + zoff, nz);
+            }
+            if (KIND != GK_R) {
+                *rrow = m;
             }
         }
+    }
+}
+
+__device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uint32_t *hdr) {
+    const SmemWords hw{smem_u32(hdr)};
+    const uint32_t aux = hw[GH_OP] >> 16;
+    switch (aux & 15u) {  // basis | kind << 2
+        case GB_X | (GK_M << 2): measure_items<GB_X, GK_M>(bc, hw); break;
+        case GB_Y | (GK_M << 2): measure_items<GB_Y, GK_M>(bc, hw); break;
+        case GB_Z | (GK_M << 2): measure_items<GB_Z, GK_M>(bc, hw); break;
+        case GB_X | (GK_MR << 2): measure_items<GB_X, GK_MR>(bc, hw); break;
+        case GB_Y | (GK_MR << 2): measure_items<GB_Y, GK_MR>(bc, hw); break;
+        case GB_Z | (GK_MR << 2): measure_items<GB_Z, GK_MR>(bc, hw); break;
+        case GB_X | (GK_R << 2): measure_items<GB_X, GK_R>(bc, hw); break;
+        case GB_Y | (GK_R << 2): measure_items<GB_Y, GK_R>(bc, hw); break;
+        default: measure_items<GB_Z, GK_R>(bc, hw); break;
     }
     return hdr + hw[GH_WORDS];
 }
@@ -745,10 +762,13 @@ __device__ __noinline__ const uint32_t *op_reczero(const BlockCtx *bc, const uin
     (void)pitch_b;
     (void)kstep;
     const uint32_t n = hw[GH_N], rec0 = hw[GH_REC0];
+    uint4 *const rec = bc->rec;
+    const uint32_t rec_mask = bc->rec_mask;
+    const uint64_t rks = bc->rec_k_stride;
     for (uint32_t i = slot; i < n; i += slots) {
-        uint4 *rrow = bc->rec + ((rec0 + i) & bc->rec_mask);
+        uint4 *rrow = rec + ((rec0 + i) & rec_mask);
         for (uint32_t k = sub; k < K; k += 1u << G_log2) {
-            rrow[k * bc->rec_k_stride] = make_uint4(0, 0, 0, 0);
+            rrow[k * rks] = make_uint4(0, 0, 0, 0);
         }
     }
     return hdr + hw[GH_WORDS];
@@ -763,6 +783,7 @@ __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uin
     const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const SmemWords dst = pay, off = pay + n, idx = pay + 2 * n + 1;
     const uint4 *rec = bc->rec;
+    uint4 *const out = bc->out;
     const uint64_t rks = bc->rec_k_stride, oks = bc->out_k_stride;
     // Record rows live in global memory (L2): a trip keeps up to XR_COLS columns x 2 rows of loads in flight per
     // thread instead of one dependent load at a time (6 columns per trip was slower: register pressure).
@@ -770,7 +791,7 @@ __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uin
     const uint32_t G = 1u << G_log2;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t b0 = off[i], b1 = off[i + 1];
-        uint4 *orow = bc->out + dst[i];
+        uint4 *orow = out + dst[i];
         for (uint32_t k0 = sub; k0 < K; k0 += XR_COLS * G) {
             uint4 acc[XR_COLS];
 #pragma unroll
@@ -822,12 +843,13 @@ __device__ __noinline__ const uint32_t *op_obs_pauli(const BlockCtx *bc, const u
     SLOT_SUB;
     const uint32_t n = hw[GH_N];
     const SmemWords pay = hw + GSTIM_HDR_WORDS;
-    const uint32_t zoff = bc->Z_s - bc->X_s;
+    const uint32_t zoff = bc->Z_s - X_s;
+    uint4 *const out = bc->out;
+    const uint64_t oks = bc->out_k_stride;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[2 * i + 1];
-        uint4 *orow = bc->out + pay[2 * i];
-        const uint64_t oks = bc->out_k_stride;
-        uint32_t ax = bc->X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
+        uint4 *orow = out + pay[2 * i];
+        uint32_t ax = X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
             uint4 acc = orow[k * oks];
             if (w & (1u << 30)) {
@@ -847,13 +869,15 @@ __device__ __noinline__ const uint32_t *op_feedback(const BlockCtx *bc, const ui
     SLOT_SUB;
     const uint32_t n = hw[GH_N];
     const SmemWords pay = hw + GSTIM_HDR_WORDS;
-    const uint32_t zoff = bc->Z_s - bc->X_s;
+    const uint32_t zoff = bc->Z_s - X_s;
+    const uint4 *const rec = bc->rec;
+    const uint64_t rks = bc->rec_k_stride;
     for (uint32_t i = slot; i < n; i += slots) {
         const uint32_t w = pay[2 * i + 1];
-        const uint4 *rrow = bc->rec + pay[2 * i];
-        uint32_t ax = bc->X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
+        const uint4 *rrow = rec + pay[2 * i];
+        uint32_t ax = X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
-            const uint4 r = rrow[k * bc->rec_k_stride];
+            const uint4 r = rrow[k * rks];
             if (w & (1u << 30)) {
                 sts128(ax, xor4(lds128(ax), r));
             }
