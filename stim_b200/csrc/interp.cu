@@ -71,6 +71,17 @@ __device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
     asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 
+// Explicit global-space accesses for the record ring / output table (a generic ST.E/LD.E takes the slow
+// address-space-resolving path and holds its operand registers for a long scoreboard wait).
+__device__ __forceinline__ void stg128(uint4 *p, uint4 v) {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ldg128(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 // A run of 32-bit words in shared memory, read with LDS (a generic pointer into the program ring would be read with
 // generic loads: long-scoreboard latency on the per-batch critical path).
 struct SmemWords {
@@ -733,7 +744,7 @@ __device__ __forceinline__ void measure_items(const BlockCtx *bc, const SmemWord
                 sts128(ax + zoff, nz);
             }
             if (KIND != GK_R) {
-                *rrow = m;
+                stg128(rrow, m);
             }
         }
     }
@@ -768,7 +779,7 @@ __device__ __noinline__ const uint32_t *op_reczero(const BlockCtx *bc, const uin
     for (uint32_t i = slot; i < n; i += slots) {
         uint4 *rrow = rec + ((rec0 + i) & rec_mask);
         for (uint32_t k = sub; k < K; k += 1u << G_log2) {
-            rrow[k * rks] = make_uint4(0, 0, 0, 0);
+            stg128(rrow + k * rks, make_uint4(0, 0, 0, 0));
         }
     }
     return hdr + hw[GH_WORDS];
@@ -805,8 +816,8 @@ __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uin
 #pragma unroll
                 for (int u = 0; u < XR_COLS; u++) {
                     const uint32_t k = k0 + u * G;
-                    v0[u] = k < K ? r0[k * rks] : make_uint4(0, 0, 0, 0);
-                    v1[u] = k < K ? r1[k * rks] : make_uint4(0, 0, 0, 0);
+                    v0[u] = k < K ? ldg128(r0 + k * rks) : make_uint4(0, 0, 0, 0);
+                    v1[u] = k < K ? ldg128(r1 + k * rks) : make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll
                 for (int u = 0; u < XR_COLS; u++) {
@@ -819,7 +830,7 @@ __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uin
                 for (int u = 0; u < XR_COLS; u++) {
                     const uint32_t k = k0 + u * G;
                     if (k < K) {
-                        acc[u] = xor4(acc[u], r0[k * rks]);
+                        acc[u] = xor4(acc[u], ldg128(r0 + k * rks));
                     }
                 }
             }
@@ -828,9 +839,9 @@ __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uin
                 const uint32_t k = k0 + u * G;
                 if (k < K) {
                     if (flags & GF_ACCUM) {
-                        acc[u] = xor4(acc[u], orow[k * oks]);
+                        acc[u] = xor4(acc[u], ldg128(orow + k * oks));
                     }
-                    orow[k * oks] = acc[u];
+                    stg128(orow + k * oks, acc[u]);
                 }
             }
         }
@@ -851,14 +862,14 @@ __device__ __noinline__ const uint32_t *op_obs_pauli(const BlockCtx *bc, const u
         uint4 *orow = out + pay[2 * i];
         uint32_t ax = X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
-            uint4 acc = orow[k * oks];
+            uint4 acc = ldg128(orow + k * oks);
             if (w & (1u << 30)) {
                 acc = xor4(acc, lds128(ax));
             }
             if (w & (1u << 31)) {
                 acc = xor4(acc, lds128(ax + zoff));
             }
-            orow[k * oks] = acc;
+            stg128(orow + k * oks, acc);
         }
     }
     return hdr + hw[GH_WORDS];
@@ -877,7 +888,7 @@ __device__ __noinline__ const uint32_t *op_feedback(const BlockCtx *bc, const ui
         const uint4 *rrow = rec + pay[2 * i];
         uint32_t ax = X_s + (w & 0xFFFFFF) * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += 1u << G_log2, ax += kstep) {
-            const uint4 r = rrow[k * rks];
+            const uint4 r = ldg128(rrow + k * rks);
             if (w & (1u << 30)) {
                 sts128(ax, xor4(lds128(ax), r));
             }
