@@ -293,11 +293,21 @@ struct PrepassRun {
     uint32_t cnt_s;             // shared-window address of this buffer's event counters (0: use `counts`)
     uint32_t *counts;
     uint32_t *evbuf;
+    uint32_t tid, threads;      // this thread's index among the threads that walk the slices, and how many there are
+    uint32_t whole_block;       // 1: every thread of the block takes part (first shot block of a launch), barrier 0
 };
 
+__device__ __forceinline__ void prepass_sync(const PrepassRun &run) {
+    if (run.whole_block) {
+        __syncthreads();
+    } else {
+        bar_sync<GSTIM_BAR_PRODUCERS>(run.threads);
+    }
+}
+
 __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun run) {
-    const uint32_t T_p = blockDim.x - bc->T_i;
-    const uint32_t tid = threadIdx.x - bc->T_i;
+    const uint32_t T_p = run.threads;
+    const uint32_t tid = run.tid;
     const uint32_t next_s = bc->next_s;
     const uint32_t n_noise = bc->n_noise;
     const uint32_t cnt_s = run.cnt_s, segoff_s = bc->ev_segoff_s;
@@ -313,7 +323,7 @@ __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun 
     if (tid == 0) {
         sts32(next_s, 0);
     }
-    bar_sync<GSTIM_BAR_PRODUCERS>(T_p);
+    prepass_sync(run);
 
     const uint4 *slices = bc->slices;
     const uint32_t n_slices = (bc->dbg_flags & 1u) ? 0u : bc->n_slices;
@@ -489,7 +499,7 @@ __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun 
         bc->dbg[34] += n_sl;
         bc->dbg[35] += n_iter;
     }
-    bar_sync<GSTIM_BAR_PRODUCERS>(T_p);
+    prepass_sync(run);
     // clamp the event counts to their segments (an overflow invalidates the call: the host reports it)
     for (uint32_t i = tid; i < n_noise; i += T_p) {
         const uint32_t cap = segoff_s ? lds32(segoff_s + 4 * i + 4) - lds32(segoff_s + 4 * i) : bc->ev_segoff[i + 1] - bc->ev_segoff[i];
@@ -948,8 +958,9 @@ __device__ __noinline__ const uint32_t *op_corr(const BlockCtx *bc, const uint32
 // Producer warps: the noise events of shot block run r go to event buffer r & 1, one run ahead of the interpreter.
 __device__ __noinline__ void producer_role(const BlockCtx *bc) {
     const uint32_t T_all = bc->T_all, n_noise = bc->n_noise, n_blocks = bc->n_blocks;
-    uint32_t r = 0;
-    for (uint32_t g = blockIdx.x; g < n_blocks; g += gridDim.x, r++) {
+    // (the events of the launch's first shot block were produced by the whole block, see the kernel)
+    uint32_t r = 1;
+    for (uint32_t g = blockIdx.x + gridDim.x; g < n_blocks; g += gridDim.x, r++) {
         const uint32_t b = r & 1u;
         if (r >= 2) {
             bar_sync2<GSTIM_BAR_FREE>(b, T_all);  // the interpreter is done with run r - 2
@@ -961,6 +972,9 @@ __device__ __noinline__ void producer_role(const BlockCtx *bc) {
         run.cnt_s = bc->ev_s ? bc->ev_s + 4 * b * n_noise : 0u;
         run.counts = bc->ev_counts_g + ((size_t)blockIdx.x * 2 + b) * n_noise;
         run.evbuf = bc->ev_buf_g + ((size_t)blockIdx.x * 2 + b) * bc->ev_total;
+        run.tid = threadIdx.x - bc->T_i;
+        run.threads = T_all - bc->T_i;
+        run.whole_block = 0;
         noise_prepass(bc, run);
         __threadfence_block();
         bar_arrive2<GSTIM_BAR_FULL>(b, T_all);
@@ -1068,6 +1082,23 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     }
     __syncthreads();
 
+    const bool has_producers = T_all > T;
+    if (has_producers) {
+        // The first shot block's noise is sampled by the whole block (24 warps instead of 4): the interpreter would
+        // only wait for it anyway. From the second block on the producer warps run ahead on their own.
+        const uint64_t col0 = p.col0_base + (uint64_t)blockIdx.x * p.K;
+        PrepassRun run;
+        run.col0_lo = (uint32_t)col0;
+        run.col0_hi = (uint32_t)(col0 >> 32);
+        run.cnt_s = ev_in_smem ? smem_u32(ev_s) : 0u;
+        run.counts = p.ev_counts + (size_t)blockIdx.x * 2 * p.n_noise;
+        run.evbuf = p.ev_buf + (size_t)blockIdx.x * 2 * p.ev_segoff[p.n_noise];
+        run.tid = tid;
+        run.threads = T_all;
+        run.whole_block = 1;
+        noise_prepass(bc, run);
+        __syncthreads();
+    }
     if (tid >= T) {
         producer_role(bc);
         return;
@@ -1089,7 +1120,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
 
     for (uint32_t g = blockIdx.x; g < p.n_blocks; g += gridDim.x, run_idx++) {
         const uint32_t eb = run_idx & 1u;
-        const bool has_producers = blockDim.x > T;
         if (tid == 0) {
             const uint64_t col0 = p.col0_base + (uint64_t)g * p.K;
             const uint32_t n_noise = p.n_noise;
@@ -1112,7 +1142,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         for (uint32_t k = tid; k < p.K; k += T) {
             sts128(bc->flag_s + 16 * k, make_uint4(0, 0, 0, 0));
         }
-        if (has_producers) {
+        if (has_producers && run_idx > 0) {
             bar_sync2<GSTIM_BAR_FULL>(eb, blockDim.x);  // this run's noise events are in place (also orders the bc updates above)
         } else {
             bar_sync<GSTIM_BAR_INTERP>(T);
