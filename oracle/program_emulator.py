@@ -17,7 +17,7 @@ from . import philox as px
 HDR = 12
 (OP_END, OP_NEXT, OP_CLIFF1, OP_CLIFF2, OP_NOISE1, OP_NOISE2, OP_MEASURE, OP_RECZERO, OP_XORROWS, OP_OBS_PAULI,
  OP_FEEDBACK, OP_CORR, OP_QMAP) = range(13)
-F_BARRIER, F_REC, F_ACCUM, F_RESET, F_TABLE, F_NOFRAME = 1, 2, 4, 8, 16, 32
+F_BARRIER, F_REC, F_ACCUM, F_RESET, F_TABLE, F_NOFRAME, F_DET = 1, 2, 4, 8, 16, 32, 64
 
 PLAN_FIELDS = ["num_qubits", "q_pitch", "num_meas", "num_det", "num_obs", "rec_ring", "n_words", "chunk_words", "n_chunks",
                "slots", "mode", "max_items", "n_batches", "n_barriers"]
@@ -235,9 +235,10 @@ class Emulator:
                 self.run_batch(site0, lam, evs)
             elif op == OP_MEASURE:
                 basis, kind = aux & 3, (aux >> 2) & 3
+                stride = 3 if flags & F_DET else 1  # fused detectors: (qubit word, detector row or NONE, record slot)
                 for i in range(n):
-                    q = int(pay[i]) & 0xFFFF
-                    assert int(pay[i]) >> 16 == self.logical_of[q]
+                    q = int(pay[stride * i]) & 0xFFFF
+                    assert int(pay[stride * i]) >> 16 == self.logical_of[q]
                     self.touch(i % S, q, True)
                     rnd = self.collapse(csite0, q)
                     x, z = self.x[q].copy(), self.z[q].copy()
@@ -253,6 +254,11 @@ class Emulator:
                     if kind != 2:
                         self.touch(i % S, (R_REC, (rec0 + i) & self.rec_mask), True)
                         self.rec[(rec0 + i) & self.rec_mask] = m
+                        if flags & F_DET and int(pay[3 * i + 1]) != 0xFFFFFFFF:
+                            d, other = int(pay[3 * i + 1]), int(pay[3 * i + 2])
+                            self.touch(i % S, ("out", d), True)
+                            self.touch(i % S, (R_REC, other), False)
+                            self.out[d] = m ^ self.rec[other]
             elif op == OP_RECZERO:
                 for i in range(n):
                     self.touch(i % S, (R_REC, (rec0 + i) & self.rec_mask), True)

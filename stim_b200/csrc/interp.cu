@@ -709,6 +709,12 @@ template <uint32_t BASIS, uint32_t KIND>
 __device__ __forceinline__ void measure_items(const BlockCtx *bc, const SmemWords hw) {
     SLOT_SUB;
     const uint32_t n = hw[GH_N];
+    // GF_DET: three payload words per item (qubit word, detector row or NONE, record slot to XOR with): the detector
+    // is written while the fresh result is still in registers (lowering.cc: fuse_detectors)
+    const bool fused = KIND != GK_R && ((hw[GH_OP] >> 8) & GF_DET) != 0;
+    const uint32_t stride = fused ? 3u : 1u;
+    uint4 *const out = bc->out;
+    const uint64_t oks = bc->out_k_stride;
     const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const uint32_t mgroup = hw[GH_CSITE0], rec0 = hw[GH_REC0];
     const uint32_t zoff = bc->Z_s - X_s;
@@ -720,11 +726,18 @@ __device__ __forceinline__ void measure_items(const BlockCtx *bc, const SmemWord
     const uint32_t kinc = 1u << G_log2;
     const bool carry_free = col_lo + K >= col_lo;  // the K columns of the block do not cross a 2^32 column boundary
     for (uint32_t i = slot; i < n; i += slots) {
-        const uint32_t w = pay[i];
+        const uint32_t w = pay[stride * i];
         const uint32_t q = w & 0xFFFFu, lq = w >> 16;  // physical frame row | logical qubit (addresses the collapse draws)
         uint4 *rrow = rec + ((rec0 + i) & rec_mask) + (uint64_t)sub * rks;
+        const uint32_t det = fused ? pay[3 * i + 1] : 0xFFFFFFFFu;
+        const uint4 *orec = rec + (fused ? pay[3 * i + 2] : 0u) + (uint64_t)sub * rks;
+        uint4 *drow = out + (det != 0xFFFFFFFFu ? det : 0u) + (uint64_t)sub * oks;
         uint32_t ax = X_s + q * 16 + sub * pitch_b;
-        for (uint32_t k = sub; k < K; k += kinc, ax += kstep, rrow += (uint64_t)kinc * rks) {
+        for (uint32_t k = sub; k < K; k += kinc, ax += kstep, rrow += (uint64_t)kinc * rks, orec += (uint64_t)kinc * rks, drow += (uint64_t)kinc * oks) {
+            uint4 prev = make_uint4(0, 0, 0, 0);
+            if (det != 0xFFFFFFFFu) {
+                prev = ldg128(orec);  // (issued before the Philox chain so the L2 latency hides behind it)
+            }
             uint32_t c2 = col_lo + k, c3 = tag_hi;
             if (!carry_free && c2 < col_lo) {
                 c3 = GTAG_COLLAPSE ^ (col_hi + 1);
@@ -755,6 +768,9 @@ __device__ __forceinline__ void measure_items(const BlockCtx *bc, const SmemWord
             }
             if (KIND != GK_R) {
                 stg128(rrow, m);
+                if (det != 0xFFFFFFFFu) {
+                    stg128(drow, xor4(m, prev));
+                }
             }
         }
     }

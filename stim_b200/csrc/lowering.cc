@@ -201,6 +201,130 @@ struct Lowerer {
         cur.n_items++;
     }
 
+    // ---- detector fusion ---------------------------------------------------------------------
+    // A detector that is the XOR of one result of a MEASURE batch and one earlier record row (the stabiliser-comparison
+    // detectors of a memory experiment) is computed by the MEASURE item itself while the fresh result is still in
+    // registers: payload of a GF_DET batch = (qubit, detector row or NONE, other record slot) per item. This removes the
+    // store -> L2 -> load round trip of the result and one batch per detector layer. The XORROWS batch moves up to the
+    // MEASURE batch, which is legal when nothing in between writes the record rows it reads or touches its output rows.
+    void fuse_detectors() {
+        if (lc.mode != 0) {
+            return;
+        }
+        auto &B = lc.batches;
+        std::vector<char> dead(B.size(), 0);
+        std::vector<uint32_t> mark(lc.num_resources, 0);  // resources of the XORROWS batch under consideration
+        std::vector<uint32_t> item_of(rec_mask + 1, 0), item_stamp(rec_mask + 1, 0);
+        uint32_t epoch = 0;
+        for (size_t x = 0; x < B.size(); x++) {
+            Batch &X = B[x];
+            if (X.op != GOP_XORROWS || (X.flags & GF_ACCUM) || X.dst.empty()) {
+                continue;
+            }
+            bool pairs = true;
+            for (size_t j = 0; j < X.dst.size() && pairs; j++) {
+                pairs = X.off[j + 1] - X.off[j] == 2;
+            }
+            if (!pairs) {
+                continue;
+            }
+            epoch++;
+            for (uint32_t r : X.res) {
+                mark[r & ~RES_WRITE] = epoch;
+            }
+            for (size_t m = x; m-- > 0;) {
+                Batch &M = B[m];
+                if (dead[m]) {
+                    continue;
+                }
+                const bool candidate = M.op == GOP_MEASURE && ((M.aux >> 2) & 3u) != GK_R;
+                if (candidate && try_fuse(M, X, item_of, item_stamp)) {
+                    dead[x] = 1;
+                    break;
+                }
+                // may the detector batch move above batch m?
+                bool blocked = false;
+                for (uint32_t r : M.res) {
+                    const uint32_t id = r & ~RES_WRITE;
+                    if (mark[id] == epoch && ((r & RES_WRITE) || id >= res_out0)) {
+                        blocked = true;
+                        break;
+                    }
+                }
+                if (blocked) {
+                    break;
+                }
+            }
+        }
+        std::vector<Batch> kept;
+        kept.reserve(B.size());
+        for (size_t i = 0; i < B.size(); i++) {
+            if (!dead[i]) {
+                kept.push_back(std::move(B[i]));
+            }
+        }
+        B.swap(kept);
+        lc.total_items = 0;
+        lc.max_items = 0;
+        for (const Batch &b : B) {
+            lc.total_items += b.res_off.size() - 1;
+            lc.max_items = std::max(lc.max_items, (uint32_t)(b.res_off.size() - 1));
+        }
+    }
+    bool try_fuse(Batch &M, const Batch &X, std::vector<uint32_t> &item_of, std::vector<uint32_t> &item_stamp) {
+        const uint32_t n = M.n_items;
+        const bool fused_before = (M.flags & GF_DET) != 0;  // (a detector layer may arrive as several XORROWS batches)
+        if (GSTIM_HDR_WORDS + 3 * n + GSTIM_HDR_WORDS > max_words || M.payload.size() != (fused_before ? 3 * (size_t)n : (size_t)n)) {
+            return false;
+        }
+        static uint32_t stamp_counter = 0;
+        const uint32_t st = ++stamp_counter;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t slot = (uint32_t)((M.rec0 + i) & rec_mask);
+            item_of[slot] = i;
+            item_stamp[slot] = st;
+        }
+        const uint32_t NONE = 0xFFFFFFFFu;
+        std::vector<uint32_t> det(n, NONE), other(n, 0);
+        if (fused_before) {
+            for (uint32_t i = 0; i < n; i++) {
+                det[i] = M.payload[3 * i + 1];
+                other[i] = M.payload[3 * i + 2];
+            }
+        }
+        const std::vector<uint32_t> det_before = det;
+        for (size_t j = 0; j < X.dst.size(); j++) {
+            const uint32_t a = X.idx[X.off[j]], b = X.idx[X.off[j] + 1];
+            const bool ina = item_stamp[a] == st, inb = item_stamp[b] == st;
+            if (ina == inb) {
+                return false;  // none or both of the two rows come from this batch
+            }
+            const uint32_t i = item_of[ina ? a : b];
+            if (det[i] != NONE) {
+                return false;  // a result that feeds two detectors stays with XORROWS
+            }
+            det[i] = X.dst[j];
+            other[i] = ina ? b : a;
+        }
+        std::vector<uint32_t> payload, res, res_off{0};
+        for (uint32_t i = 0; i < n; i++) {
+            payload.push_back(M.payload[fused_before ? 3 * i : i]);
+            payload.push_back(det[i]);
+            payload.push_back(other[i]);
+            res.insert(res.end(), M.res.begin() + M.res_off[i], M.res.begin() + M.res_off[i + 1]);
+            if (det[i] != NONE && det_before[i] == NONE) {
+                res.push_back((res_out0 + det[i]) | RES_WRITE);
+                res.push_back(res_rec0 + other[i]);
+            }
+            res_off.push_back((uint32_t)res.size());
+        }
+        M.payload.swap(payload);
+        M.res.swap(res);
+        M.res_off.swap(res_off);
+        M.flags |= GF_DET;
+        return true;
+    }
+
     // ---- op emitters -------------------------------------------------------------------------
     void cliff1(uint32_t mat, uint32_t q) {
         Key k;
@@ -958,11 +1082,13 @@ void assign_physical_rows(LoweredCircuit &lc) {
                     w = phys[w];
                 }
                 break;
-            case GOP_MEASURE:  // physical row | logical index << 16 (the logical index addresses the collapse draws)
-                for (auto &w : b.payload) {
-                    w = phys[w] | (w << 16);
+            case GOP_MEASURE: {  // physical row | logical index << 16 (the logical index addresses the collapse draws)
+                const size_t stride = (b.flags & GF_DET) ? 3 : 1;
+                for (size_t i = 0; i < b.payload.size(); i += stride) {
+                    b.payload[i] = phys[b.payload[i]] | (b.payload[i] << 16);
                 }
                 break;
+            }
             case GOP_NOISE1:
                 if (!(b.flags & GF_NOFRAME)) {
                     for (auto &w : b.payload) {
@@ -1170,6 +1296,7 @@ LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch
         lw.do_op(op);
     });
     lw.flush();
+    lw.fuse_detectors();
     assign_physical_rows(lc);
     for (Batch &b : lc.batches) {
         spread_banks(b);

@@ -60,6 +60,8 @@ enum GstimHdr : uint32_t {
 #define GF_RESET_FLAG 0x08u  // CORR: clear the "correlated error occurred" row first (E vs ELSE)
 #define GF_TABLE 0x10u       // NOISE2: 15 cumulative u32 thresholds follow the header (PAULI_CHANNEL_2)
 #define GF_NOFRAME 0x20u     // NOISE1: item is not a frame qubit (MPAD noise); clock = GH_EXTRA-1
+#define GF_DET 0x40u         // MEASURE: 3 payload words per item: qubit word, detector row to write (or 0xFFFFFFFF), record slot
+                             //          to XOR the fresh result with (detector fused into the measurement, lowering.cc)
 
 // CLIFF2 matrix of CX (the interpreter has a dedicated path for it; circuit.cc static_asserts the value)
 #define GSTIM_MAT_CX 0x85A1u

@@ -233,3 +233,30 @@ def test_world_size_2_gloo_flip_count_allreduce(tmp_path):
         env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_OK" in r.stdout
+
+
+def test_stabiliser_comparison_detectors_are_fused_into_the_measurements():
+    """lowering.cc fuse_detectors: a detector = (fresh result) xor (one earlier record row) is computed by the MEASURE
+    item (GF_DET payload); detectors with other shapes stay XORROWS batches. The emulator executes both forms."""
+    text = gen_circuit("surface_code", "rotated_memory_z", 5, 4, 0.01)
+    w, plan = lower(text, 0, 64, 0)
+    pl = pe.plan_dict(plan)
+    pc, chunk, fused_items, xor_items = 0, pl["chunk_words"], 0, 0
+    while True:
+        h = int(w[pc])
+        op = h & 0xFF
+        if op == pe.OP_END:
+            break
+        if op == pe.OP_NEXT:
+            pc = (pc // chunk + 1) * chunk
+            continue
+        n, words = int(w[pc + 1]), int(w[pc + 2])
+        if op == pe.OP_MEASURE and (h >> 8) & pe.F_DET:
+            assert words == pe.HDR + 3 * n
+            fused_items += sum(1 for i in range(n) if int(w[pc + pe.HDR + 3 * i + 1]) != 0xFFFFFFFF)
+        if op == pe.OP_XORROWS:
+            xor_items += n
+        pc += words
+    # d=5 rotated memory: 24 stabilisers; rounds 2..4 compare with the previous round (72 fused detectors); the first
+    # round (12 single-row detectors), the final data-qubit detectors (12) and the observable stay XORROWS items
+    assert fused_items == 72 and xor_items == 12 + 12 + 1 + 1
