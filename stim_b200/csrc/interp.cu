@@ -639,7 +639,9 @@ __device__ __noinline__ const uint32_t *op_noise(const BlockCtx *bc, const uint3
     prefetch_events(bc, nbi + 1);
     const uint32_t T_i = bc->T_i;
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's records have landed
-    bar_sync<GSTIM_BAR_INTERP>(T_i);
+    if (!(flags & GF_NOENTRY)) {
+        bar_sync<GSTIM_BAR_INTERP>(T_i);  // (a directly preceding noise batch ended with this barrier)
+    }
     for (uint32_t e = threadIdx.x; e < cnt; e += T_i) {
         const uint32_t rec = e < GSTIM_EV_STAGE ? lds32(st + 4 * e) : bc->ev_buf[seg0 + e];
         const uint32_t shot = rec & ((1u << GSTIM_EV_SHOT_BITS) - 1);

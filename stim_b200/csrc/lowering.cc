@@ -1358,11 +1358,19 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         return (uint32_t)(ns.rates.size() / 2) - 1;
     };
 
+    bool prev_was_noise = false;
     for (Batch &b : lc.batches) {
         const bool is_noise = b.op == GOP_NOISE1 || b.op == GOP_NOISE2;
         if (is_noise) {
             epoch++;  // noise events are applied by arbitrary threads: the kernel brackets these batches with barriers
+            // ... except that the exit barrier of a directly preceding noise batch already is this batch's entry barrier
+            if (prev_was_noise) {
+                b.flags |= GF_NOENTRY;
+            } else {
+                b.flags &= ~GF_NOENTRY;
+            }
         }
+        prev_was_noise = is_noise;
         // ---- hazard analysis: does any item need data last touched by another thread group? ----
         size_t n_haz = b.res_off.size() - 1;
         bool barrier = false;

@@ -60,6 +60,7 @@ enum GstimHdr : uint32_t {
 #define GF_RESET_FLAG 0x08u  // CORR: clear the "correlated error occurred" row first (E vs ELSE)
 #define GF_TABLE 0x10u       // NOISE2: 15 cumulative u32 thresholds follow the header (PAULI_CHANNEL_2)
 #define GF_NOFRAME 0x20u     // NOISE1: item is not a frame qubit (MPAD noise); clock = GH_EXTRA-1
+#define GF_NOENTRY 0x80u     // NOISE1/NOISE2: the previous batch was a noise batch too: its exit barrier serves as this entry barrier
 #define GF_DET 0x40u         // MEASURE: 3 payload words per item: qubit word, detector row to write (or 0xFFFFFFFF), record slot
                              //          to XOR the fresh result with (detector fused into the measurement, lowering.cc)
 
