@@ -30,11 +30,26 @@ constexpr int TP_PITCH = 40;                       // words per shot row in the 
 constexpr int TP_IN_COL = TP_BITS + TP_BITS / 32;  // uint4 per column in the input staging (1 pad per 32 rows)
 
 __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
-    // After this, a[j] bit i == (input a[i]) bit j.
+    // After this, a[j] bit i == (input a[i]) bit j. The 16- and 8-bit stages are byte permutes (one PRMT per
+    // output word), the 4-, 2- and 1-bit stages masked swaps.
 #pragma unroll
-    for (int st = 0; st < 5; st++) {
+    for (int k = 0; k < 16; k++) {
+        const uint32_t x = a[k], y = a[k + 16];
+        a[k] = __byte_perm(x, y, 0x5410);       // (x.lo16, y.lo16)
+        a[k + 16] = __byte_perm(x, y, 0x7632);  // (x.hi16, y.hi16)
+    }
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        if ((k & 8) == 0) {
+            const uint32_t x = a[k], y = a[k + 8];
+            a[k] = __byte_perm(x, y, 0x6240);      // bytes x0 y0 x2 y2
+            a[k + 8] = __byte_perm(x, y, 0x7351);  // bytes x1 y1 x3 y3
+        }
+    }
+#pragma unroll
+    for (int st = 2; st < 5; st++) {
         const int j = 16 >> st;
-        const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t m = j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
 #pragma unroll
         for (int k = 0; k < 32; k++) {
             if ((k & j) == 0) {
@@ -119,29 +134,24 @@ __global__ void __launch_bounds__(TP_THREADS, 4) gstim_transpose_kernel(const Tr
     const uint64_t dst_step = TP_WARPS * p.out_pitch;
     if (seg_len == TP_BITS / 8) {
         // full segment: aligned word `lane` of the destination holds segment bytes [4 lane - mis, 4 lane - mis + 4).
-        // Lanes 1..31 store whole words; the 4 - mis head bytes and mis tail bytes go out as single predicated
-        // byte stores from lanes 0..3 (no per-byte loops: a loop run by one lane still costs the whole warp).
-        for (uint32_t sl = warp; sl < n_valid; sl += TP_WARPS, dst += dst_step) {
-            const uint32_t *S = &tile[((sl & 31) * (4 * TP_COLS) + (sl >> 5)) * TP_PITCH];
-            const uint32_t mis = (uint32_t)((uintptr_t)dst & 3);
-            const uint32_t hi = S[lane];
-            if (mis == 0) {
-                reinterpret_cast<uint32_t *>(dst)[lane] = hi;
-            } else {
-                const uint32_t sh = 8 * (4 - mis);
-                const uint32_t lo = lane ? S[lane - 1] : 0u;
-                if (lane) {
-                    reinterpret_cast<uint32_t *>(dst - mis)[lane] = __funnelshift_r(lo, hi, sh);
-                }
-                if (lane < 4) {
-                    const uint32_t first = S[0], last = S[31];
-                    if (lane < 4 - mis) {
-                        dst[lane] = (uint8_t)(first >> (8 * lane));  // segment bytes 0 .. 3 - mis
-                    }
-                    if (lane < mis) {
-                        dst[128 - mis + lane] = (uint8_t)(last >> (sh + 8 * lane));  // segment bytes 128 - mis .. 127
-                    }
-                }
+        // Branch-free per row: one (predicated) word store per lane, and the 4 - mis head bytes / mis tail bytes as
+        // single predicated byte stores from lanes 0..2 (a per-byte loop run by one lane still costs the whole warp).
+        const uint32_t mis_step = (uint32_t)(dst_step & 3);
+        uint32_t mis = (uint32_t)((uintptr_t)dst & 3);
+        const uint32_t *S = &tile[(warp * (4 * TP_COLS)) * TP_PITCH];  // row of shot sl = warp + TP_WARPS * t
+#pragma unroll 4
+        for (uint32_t sl = warp; sl < n_valid; sl += TP_WARPS, dst += dst_step, mis = (mis + mis_step) & 3) {
+            const uint32_t *R = S + (((sl - warp) & 31) * (4 * TP_COLS) + (sl >> 5)) * TP_PITCH;
+            const uint32_t sh = 32 - 8 * mis;
+            const uint32_t hi = R[lane], lo = R[(lane + 31) & 31], first = R[0], last = R[31];
+            if (lane != 0 || mis == 0) {
+                reinterpret_cast<uint32_t *>(dst - mis)[lane] = __funnelshift_rc(lo, hi, sh);  // (sh = 32 -> hi)
+            }
+            if (mis != 0 && lane < 4 - mis) {
+                dst[lane] = (uint8_t)(first >> (8 * lane));  // segment bytes 0 .. 3 - mis
+            }
+            if (lane < mis) {
+                dst[128 - mis + lane] = (uint8_t)(last >> (sh + 8 * lane));  // segment bytes 128 - mis .. 127
             }
         }
         return;
