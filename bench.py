@@ -223,8 +223,27 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- end-to-end arm (host buffers, D2H inside the timed region) ----------------------------------
-    e2e_shots = 1 << args.e2e_shots_log2
-    host = torch.empty((e2e_shots, nbytes), dtype=torch.uint8, pin_memory=True)
+    # (per rank: 2^22 shots = 8.2 GB of pinned memory; shrink if the host cannot pin that much - every rank must use the
+    # same size, so the decision is taken together)
+    e2e_log2 = args.e2e_shots_log2
+    host = None
+    while host is None:
+        try:
+            host = torch.empty((1 << e2e_log2, nbytes), dtype=torch.uint8, pin_memory=True)
+            ok = 1.0
+        except RuntimeError:
+            ok = 0.0
+        if world > 1:
+            t = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = float(t.item())
+        if ok == 0.0:
+            host = None
+            torch.cuda.empty_cache()
+            e2e_log2 -= 1
+            if e2e_log2 < 16:
+                raise RuntimeError("cannot allocate a pinned host buffer for the end-to-end arm")
+    e2e_shots = 1 << e2e_log2
     host_np = host.numpy()
     sampler.sample(e2e_shots, bit_packed=True, append_observables=True, dets_out=host_np)  # warm-up (allocations)
     barrier()
