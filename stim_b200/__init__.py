@@ -282,6 +282,24 @@ class CompiledDetectorSampler(_Sampler):
             self._handle, int(shots), flags, ctypes.c_void_p(dets_ptr or None), dets_shot_stride,
             ctypes.c_void_p(obs_ptr or None), obs_shot_stride))
 
+    def sample_torch(self, shots: int, *, separate_observables: bool = True):
+        """Device-resident bit-packed results as torch uint8 CUDA tensors: (dets[shots, ceil(D/8)], obs[shots, ceil(L/8)])
+        or one [shots, ceil((D+L)/8)] tensor with the observables appended. The consumer hook of SURVEY §8(f) rank 1
+        (sinter's sample -> decode loop, glue/sample/src/sinter/_decoding/_stim_then_decode_sampler.py:162-185, without
+        the PCIe drain): a decoder or a reduction that lives on the GPU reads the shots where they were produced."""
+        import torch
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        D, L = int(self.stats.num_detectors), int(self.stats.num_observables)
+        if separate_observables:
+            dets = torch.empty((shots, (D + 7) // 8), dtype=torch.uint8, device=dev)
+            obs = torch.empty((shots, (L + 7) // 8), dtype=torch.uint8, device=dev)
+            self.sample_device(shots, dets.data_ptr() if dets.numel() else 0, obs_ptr=obs.data_ptr() if obs.numel() else 0)
+            return dets, obs
+        out = torch.empty((shots, (D + L + 7) // 8), dtype=torch.uint8, device=dev)
+        self.sample_device(shots, out.data_ptr(), append_observables=True)
+        return out
+
     def flip_counts(self, shots: int, counts_dev_ptr: int = 0) -> np.ndarray:
         """uint64[D+L] flip counts over `shots` fresh shots (device copy optional, for NCCL allreduce)."""
         n = int(self.stats.num_detectors + self.stats.num_observables)

@@ -257,3 +257,23 @@ def test_output_layouts_are_consistent():
         fresh().sample(shots, dets_out=np.zeros((shots, D), dtype=np.uint8))
     with pytest.raises(ValueError):
         fresh().sample(shots, separate_observables=True, append_observables=True)
+
+
+def test_device_resident_torch_results_equal_host_results():
+    """sample_torch (results stay on the GPU) returns the same bits as the host API for the same stream."""
+    import torch
+
+    text = gen_circuit("surface_code", "rotated_memory_z", 5, 5, 0.01)
+    a = stim_b200.Circuit(text).compile_detector_sampler(seed=11)
+    b = stim_b200.Circuit(text).compile_detector_sampler(seed=11)
+    shots = 5000
+    dets_t, obs_t = a.sample_torch(shots)
+    assert dets_t.is_cuda and dets_t.dtype == torch.uint8 and obs_t.shape == (shots, 1)
+    dets_h, obs_h = b.sample(shots, bit_packed=True, separate_observables=True)
+    np.testing.assert_array_equal(dets_t.cpu().numpy(), dets_h)
+    np.testing.assert_array_equal(obs_t.cpu().numpy(), obs_h)
+    both = a.sample_torch(shots, separate_observables=False)
+    ref = b.sample(shots, bit_packed=True, append_observables=True)
+    np.testing.assert_array_equal(both.cpu().numpy(), ref)
+    # a reduction next to the data: shots with at least one detection event
+    assert 0 < int((dets_t != 0).any(dim=1).sum().item()) <= shots
