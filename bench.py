@@ -42,6 +42,30 @@ def measured_traffic_bytes_per_shot():
         return None
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """One process per GPU: run on the CPUs of the GPU's NUMA node, so that the pinned result buffer (first touch) and the
+    PCIe traffic stay on the socket the GPU hangs off. Best effort; returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -164,6 +188,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: stim_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -280,7 +305,7 @@ def main():
         "clocks": clk,
         "e2e": {
             "value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": e2e_shots * nbytes,
-            "shots_per_step": e2e_shots, "steps": e2e_steps, "host_buffer": "pinned",
+            "shots_per_step": e2e_shots, "steps": e2e_steps, "host_buffer": "pinned", "numa_node": numa,
         },
         "roofline": {
             "kernel": "gstim_interp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
