@@ -207,6 +207,28 @@ void configure(gstim_sampler *s) {
 
     s->lc = lower_circuit(s->circuit, (uint32_t)s->mode, s->chunk_words - GSTIM_HDR_WORDS);
 
+    // Every chunk hand-over of the program ring costs ~1400 cycles per shot block (barrier + ring turn-around,
+    // profiles/r1_notes.md), so the shared memory that the frame columns leave unused goes into larger chunks
+    // (c3: 5.9 KB spare -> 2688-word chunks, 104 instead of 155 chunks). The circuit is lowered again for that size.
+    if (env_u32("GSTIM_CHUNK_WORDS", 0) == 0) {
+        const uint32_t Q0 = s->lc.num_qubits, pitch0 = Q0 | 1u;
+        uint32_t n_noise0 = 0;
+        for (const auto &b : s->lc.batches) {
+            n_noise0 += b.op == GOP_NOISE1 || b.op == GOP_NOISE2 || b.op == GOP_CORR;
+        }
+        const size_t fixed0 = interp_smem_bytes(pitch0, Q0, 0, s->chunk_words, n_noise0);
+        const size_t per_k0 = (size_t)2 * pitch0 * 16 + 16;
+        if (fixed0 + per_k0 <= s->smem_optin) {
+            const size_t k0 = std::min<size_t>((s->smem_optin - fixed0) / per_k0, 32);
+            const size_t spare = s->smem_optin - fixed0 - k0 * per_k0;
+            const uint32_t grown = std::min<uint32_t>(8192, s->chunk_words + (uint32_t)(spare / 8) / 128 * 128);
+            if (grown >= s->chunk_words + 256) {
+                s->chunk_words = grown;
+                s->lc = lower_circuit(s->circuit, (uint32_t)s->mode, s->chunk_words - GSTIM_HDR_WORDS);
+            }
+        }
+    }
+
     // slots: cover the batch size below which 95% of all items live
     std::vector<std::pair<uint32_t, uint64_t>> sizes;
     for (const auto &b : s->lc.batches) {
