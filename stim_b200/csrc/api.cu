@@ -126,10 +126,9 @@ struct gstim_sampler {
 
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    DevBuf d_dbg, d_prog, d_qmap, d_table, d_rec, d_rowmap, d_stage[2], d_counts;
+    DevBuf d_dbg, d_prog, d_table, d_rec, d_rowmap, d_stage[2], d_counts;
     // noise schedule + per-CTA event scratch (interp.cu noise_prepass)
     DevBuf d_noise_info, d_rates, d_slices, d_segoff, d_ev_counts, d_ev_buf, d_ev_overflow;
-    uint32_t n_rounds = 0, info_smem_bytes = 0;
     uint32_t segoff_K = 0;
     uint32_t n_noise = 0;
     uint64_t ev_total = 0;
@@ -314,8 +313,6 @@ void configure(gstim_sampler *s) {
         s->d_ev_overflow.ensure(16);
         CK(cudaMemset(s->d_ev_overflow.p, 0, 16));
     }
-    s->d_qmap.ensure(s->lc.logical_of.size() * 4);
-    CK(cudaMemcpy(s->d_qmap.p, s->lc.logical_of.data(), s->lc.logical_of.size() * 4, cudaMemcpyHostToDevice));
     CK(interp_set_max_smem(interp_smem_bytes(q_pitch, Q, K_max, s->chunk_words, s->n_noise)));
 }
 
@@ -439,10 +436,6 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
         CK(cudaMemcpy(s->d_segoff.p, segoff.data(), segoff.size() * 4, cudaMemcpyHostToDevice));
         s->segoff_K = K;
         s->ev_total = total;
-        const size_t frame_bytes = (size_t)2 * K * q_pitch * 16;
-        s->info_smem_bytes = (n_noise * GSTIM_NOISE_INFO_WORDS * 4 <= 65536 && n_noise * GSTIM_NOISE_INFO_WORDS * 4 <= frame_bytes)
-                                 ? n_noise * GSTIM_NOISE_INFO_WORDS * 4
-                                 : 0;
     }
     s->d_ev_counts.ensure(std::max<size_t>((size_t)grid_cap * 2 * n_noise * 4, 16));
     s->d_ev_buf.ensure(std::max<size_t>((size_t)grid_cap * 2 * s->ev_total * 4, 16));
@@ -463,7 +456,6 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
         const uint64_t chunk_shots = std::min<uint64_t>(nb * B, shots - first_shot);
         InterpParams p{};
         p.prog = (const uint32_t *)s->d_prog.p;
-        p.logical_of = (const uint32_t *)s->d_qmap.p;
         p.n_chunks = s->plan.n_chunks;
         p.chunk_words = s->chunk_words;
         p.Q = Q;
@@ -473,14 +465,12 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
         p.slots = s->slots;
         p.threads_interp = s->threads;
         p.n_blocks = (uint32_t)nb;
-        p.max_items = s->plan.max_items;
         p.n_noise = n_noise;
         p.n_rates = (uint32_t)(s->lc.noise.rates.size() / 2);
         p.noise_info = (const uint32_t *)s->d_noise_info.p;
         p.rates = (const ulonglong2 *)s->d_rates.p;
         p.slices = (const uint4 *)s->d_slices.p;
         p.n_slices = (uint32_t)(s->lc.noise.slices.size() / GSTIM_SLICE_WORDS);
-        p.info_smem_bytes = s->info_smem_bytes;
         p.ev_segoff = (const uint32_t *)s->d_segoff.p;
         p.ev_counts = (uint32_t *)s->d_ev_counts.p;
         p.ev_buf = (uint32_t *)s->d_ev_buf.p;

@@ -187,7 +187,6 @@ struct __align__(16) BlockCtx {
     uint4 *rec;               // this block's record rows
     uint4 *out;               // this block's output columns
     uint64_t rec_k_stride, out_k_stride;  // uint4 units between the 128-shot columns of a record / output row (rows are contiguous)
-    const uint32_t *logical_of;
     const uint32_t *ev_segoff;  // event segment offsets per noise batch
     uint32_t *ev_counts;        // this CTA's event counters
     uint32_t *ev_buf;           // this CTA's event records
@@ -196,7 +195,7 @@ struct __align__(16) BlockCtx {
     const ulonglong2 *rates;
     const uint32_t *noise_info, *prog;
     uint32_t *ev_overflow;
-    uint32_t n_slices, info_smem_bytes;
+    uint32_t n_slices, pad5;
     uint32_t n_noise, T_i;             // T_i: interpreter threads (the remaining warps of the block produce noise events)
     uint32_t next_s;                   // shared counter the pre-pass threads claim chains from
     uint32_t ev_counts_s, ev_segoff_s; // shared-window addresses of the event counters / segment offsets (0: global)
@@ -1067,7 +1066,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         bc->rec_mask = p.rec_mask;
         bc->rec_k_stride = p.rec_k_stride;
         bc->out_k_stride = p.out_k_stride;
-        bc->logical_of = p.logical_of;
         bc->n_blocks = p.n_blocks;
         bc->n_chunks = p.n_chunks;
         bc->chunk_words = p.chunk_words;

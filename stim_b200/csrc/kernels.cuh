@@ -8,7 +8,6 @@
 namespace gstim {
 
 struct InterpParams {
-    const uint32_t *logical_of; // physical frame row -> logical qubit index (Q+1 entries), addresses the Philox counters
     const uint32_t *prog;      // lowered program in global memory (16-byte aligned, n_chunks*chunk_words words)
     uint32_t n_chunks;
     uint32_t chunk_words;
@@ -19,7 +18,6 @@ struct InterpParams {
     uint32_t slots;            // threads_interp >> G_log2
     uint32_t threads_interp;   // interpreter threads = the first warps of the block; the remaining warps produce noise events
     uint32_t n_blocks;         // shot blocks in this launch
-    uint32_t max_items;        // largest batch (sizes the event job queue)
     uint64_t col0_base;        // global column index (shot/128) of block 0
     uint32_t seed_lo, seed_hi; // Philox key
     uint4 *rec;                // measurement record rows
@@ -38,7 +36,6 @@ struct InterpParams {
     const ulonglong2 *rates;          // per rate: lam, floor((2^64 - 1) / lam)
     const uint4 *slices;              // RNG slices, 2 uint4 each (program.h "Noise schedule")
     uint32_t n_slices;
-    uint32_t info_smem_bytes;         // n_noise * 48 when the info records are staged in shared memory, else 0
     const uint32_t *ev_segoff;        // n_noise + 1 : event segment offsets for this launch's block size
     uint32_t *ev_counts;              // gridDim.x * 2 * n_noise (two event buffers per CTA)
     uint32_t *ev_buf;                 // gridDim.x * 2 * ev_segoff[n_noise]
