@@ -260,3 +260,27 @@ def test_stabiliser_comparison_detectors_are_fused_into_the_measurements():
     # d=5 rotated memory: 24 stabilisers; rounds 2..4 compare with the previous round (72 fused detectors); the first
     # round (12 single-row detectors), the final data-qubit detectors (12) and the observable stay XORROWS items
     assert fused_items == 72 and xor_items == 12 + 12 + 1 + 1
+
+
+def _golden_detect_cases():
+    from golden_util import load_cases
+
+    return [c for c in load_cases() if c["mode"] == "detect"]
+
+
+@pytest.mark.parametrize("case", _golden_detect_cases(), ids=lambda c: c["name"])
+def test_lowered_golden_circuits_reproduce_the_reference_on_the_emulator(case):
+    """The lowered instruction stream (detector fusion, batching, barriers) of every deterministic reference test circuit,
+    executed by the program emulator with its race detector on, gives the reference CLI's detection events."""
+    from golden_util import arrange, expected_bits
+
+    shots = next(iter(case["outputs"].values()))["shots"]
+    K = 1
+    n_blocks = (shots + 127) // 128
+    for slots in (3,):  # few thread groups: many cross-group hazards, i.e. the barrier analysis is exercised hardest
+        w, plan = lower(case["circuit"], 0, slots, 0)
+        pl = pe.plan_dict(plan)
+        out = pe.emulate(w, plan, seed=9, K=K, n_blocks=n_blocks, col0=0)[:shots]
+        dets, obs = out[:, : pl["num_det"]], out[:, pl["num_det"]:]
+        got = arrange(dets, obs, case["flags"])
+        np.testing.assert_array_equal(got, expected_bits(case, got.shape[1])[:shots])
