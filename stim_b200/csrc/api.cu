@@ -244,8 +244,9 @@ void configure(gstim_sampler *s) {
             break;
         }
     }
-    // (at most 768 interpreter threads: the other warps of the block produce the noise events one shot block ahead)
-    uint32_t slots = std::min<uint32_t>(768, std::max<uint32_t>(32, (p95 + 31) / 32 * 32));
+    // (at most 640 interpreter threads: with the 128 noise producer threads the block stays at 768 threads = 80 registers
+    // per thread; at 896 threads = 72 registers the opcode functions spill - c5: 7 % slower)
+    uint32_t slots = std::min<uint32_t>(640, std::max<uint32_t>(32, (p95 + 31) / 32 * 32));
     slots = env_u32("GSTIM_SLOTS", slots);
 
     // K_max from the shared-memory budget
