@@ -10,6 +10,7 @@
 #include "tableau_ref.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -205,49 +206,101 @@ struct Sim {
     }
 
     // row for sgn * (Pauli code pa on qubit a) (x) (code pb on qubit b), expressed through the current rows
-    void image_row(int pa, size_t a, int pb, size_t b, int sgn, std::vector<uint64_t> &ox, std::vector<uint64_t> &oz, uint8_t &os) {
-        ox.assign(nw, 0);
-        oz.assign(nw, 0);
+    void image_row(int pa, size_t a, int pb, size_t b, int sgn, uint64_t *ox, uint64_t *oz, uint8_t &os) {
+        memset(ox, 0, nw * 8);
+        memset(oz, 0, nw * 8);
         int e = 2 * sgn + (pa == 3) + (pb == 3);
-        if (pa & 1) e += mul_into(ox.data(), oz.data(), 2 * a);
-        if (pa & 2) e += mul_into(ox.data(), oz.data(), 2 * a + 1);
-        if (pb & 1) e += mul_into(ox.data(), oz.data(), 2 * b);
-        if (pb & 2) e += mul_into(ox.data(), oz.data(), 2 * b + 1);
+        if (pa & 1) e += mul_into(ox, oz, 2 * a);
+        if (pa & 2) e += mul_into(ox, oz, 2 * a + 1);
+        if (pb & 1) e += mul_into(ox, oz, 2 * b);
+        if (pb & 2) e += mul_into(ox, oz, 2 * b + 1);
         if (e & 1) {
             throw std::logic_error("internal: non-Hermitian row in the inverse tableau");
         }
         os = (uint8_t)((e >> 1) & 1);
     }
 
-    void gate1(const std::string &name, size_t q) {
-        const Table1 &t = tables().inv1.at(name);
-        std::vector<uint64_t> nx[2], nz[2];
+    // Scratch rows for the generator images of one gate (no allocation per gate: a d=51 memory experiment applies
+    // 6.6e5 gates). Generators that the gate maps to themselves are skipped (CX: Z of the control, X of the target).
+    std::vector<uint64_t> scratch;
+    uint64_t *sx(int g) { return &scratch[(size_t)(2 * g) * nw]; }
+    uint64_t *sz(int g) { return &scratch[(size_t)(2 * g + 1) * nw]; }
+
+    void gate1(const Table1 &t, size_t q) {
+        scratch.resize(8 * nw);
         uint8_t ns[2];
+        bool changed[2];
         for (int g = 0; g < 2; g++) {
             int code = g == 0 ? 1 : 2;
-            image_row(t.img[code], q, 0, q, t.sgn[code], nx[g], nz[g], ns[g]);
+            changed[g] = !(t.img[code] == code && t.sgn[code] == 0);
+            if (changed[g]) {
+                image_row(t.img[code], q, 0, q, t.sgn[code], sx(g), sz(g), ns[g]);
+            }
         }
         for (int g = 0; g < 2; g++) {
-            memcpy(xr(2 * q + g), nx[g].data(), nw * 8);
-            memcpy(zr(2 * q + g), nz[g].data(), nw * 8);
-            sign[2 * q + g] = ns[g];
+            if (changed[g]) {
+                memcpy(xr(2 * q + g), sx(g), nw * 8);
+                memcpy(zr(2 * q + g), sz(g), nw * 8);
+                sign[2 * q + g] = ns[g];
+            }
         }
     }
-    void gate2(const std::string &name, size_t a, size_t b) {
-        const Table2 &t = tables().inv2.at(name);
-        std::vector<uint64_t> nx[4], nz[4];
+    void gate2(const Table2 &t, size_t a, size_t b) {
+        scratch.resize(8 * nw);
         uint8_t ns[4];
+        bool changed[4];
         const int codes[4] = {1, 2, 4, 8};  // X_, Z_, _X, _Z
+        const size_t rows_of[4] = {2 * a, 2 * a + 1, 2 * b, 2 * b + 1};
         for (int g = 0; g < 4; g++) {
             int img = t.img[codes[g]];
-            image_row(img & 3, a, img >> 2, b, t.sgn[codes[g]], nx[g], nz[g], ns[g]);
+            changed[g] = !(img == codes[g] && t.sgn[codes[g]] == 0);
+        }
+        // In-place fast path (CX, CZ, ...): a generator whose image is itself times ONE generator of the other qubit
+        // that the gate leaves alone. The two rows commute (they are images of commuting generators), so the order of
+        // the product does not matter and row(g) *= row(h) needs no scratch copy.
+        if (!slow_column_ops) {
+            for (int g = 0; g < 4; g++) {
+                if (!changed[g] || t.sgn[codes[g]] != 0) {
+                    continue;
+                }
+                const int other = t.img[codes[g]] ^ codes[g];  // the image without g itself
+                int h = -1;
+                for (int k = 0; k < 4; k++) {
+                    if (other == codes[k]) {
+                        h = k;
+                    }
+                }
+                if ((t.img[codes[g]] & codes[g]) != codes[g] || h < 0 || (h >> 1) == (g >> 1) || changed[h]) {
+                    continue;
+                }
+                const int e = 2 * sign[rows_of[g]] + mul_into(xr(rows_of[g]), zr(rows_of[g]), rows_of[h]);
+                if (e & 1) {
+                    throw std::logic_error("internal: non-Hermitian row in the inverse tableau");
+                }
+                sign[rows_of[g]] = (uint8_t)((e >> 1) & 1);
+                changed[g] = false;
+            }
+        }
+        for (int g = 0; g < 4; g++) {
+            int img = t.img[codes[g]];
+            if (changed[g]) {
+                image_row(img & 3, a, img >> 2, b, t.sgn[codes[g]], sx(g), sz(g), ns[g]);
+            }
         }
         const size_t rows[4] = {2 * a, 2 * a + 1, 2 * b, 2 * b + 1};
         for (int g = 0; g < 4; g++) {
-            memcpy(xr(rows[g]), nx[g].data(), nw * 8);
-            memcpy(zr(rows[g]), nz[g].data(), nw * 8);
-            sign[rows[g]] = ns[g];
+            if (changed[g]) {
+                memcpy(xr(rows[g]), sx(g), nw * 8);
+                memcpy(zr(rows[g]), sz(g), nw * 8);
+                sign[rows[g]] = ns[g];
+            }
         }
+    }
+    void gate1(const std::string &name, size_t q) {
+        gate1(tables().inv1.at(name), q);
+    }
+    void gate2(const std::string &name, size_t a, size_t b) {
+        gate2(tables().inv2.at(name), a, b);
     }
     void pauli(int code, size_t q) {  // X: 1, Z: 2, Y: 3 applied to the state
         if (code & 1) sign[2 * q + 1] ^= 1;  // X flips the sign of T^dag Z_q T
@@ -297,6 +350,10 @@ struct Sim {
             return sign[r] != 0;
         }
         const Tables &tb = tables();
+        if (!slow_column_ops) {
+            collapse_fused(r, k);
+            return false;
+        }
         // fold the X part of the row onto column k (input-side CX with control k fixes |0..0>)
         for (size_t j = 0; j < n; j++) {
             if (j != k && (xr(r)[j / 64] >> (j % 64)) & 1) {
@@ -319,6 +376,109 @@ struct Sim {
         }
         return false;
     }
+    // The same column operations as the loop in measure_z, applied in ONE pass over the rows: the list of
+    // (gate, column) steps is fixed by row r before anything changes, every step acts on the pivot column k and at most
+    // one other column, and a row's bits in those columns are all that the steps read or write. Each full pass over the
+    // 2n rows of a d=51 circuit moves 2.7 MB, and a random measurement needs half a dozen of them when done one by one.
+    bool slow_column_ops = false;
+    struct Step {
+        const Table2 *t2;
+        const Table1 *t1;
+        size_t j;
+    };
+    std::vector<Step> steps;
+    void collapse_fused(size_t r, size_t k) {
+        const Tables &tb = tables();
+        steps.clear();
+        const Table2 *cx = &tb.inv2.at("CX"), *cz = &tb.inv2.at("CZ");
+        for (size_t j = 0; j < n; j++) {
+            if (j != k && (xr(r)[j / 64] >> (j % 64)) & 1) {
+                steps.push_back({cx, nullptr, j});
+            }
+        }
+        // the CX steps do not change the Z part of row r outside column k (CX(k, j): z_k ^= z_j), so the CZ list can be
+        // read off the row as it is now; whether S is needed depends on the updated z_k, which the pass tracks on row r
+        for (size_t j = 0; j < n; j++) {
+            if (j != k && (zr(r)[j / 64] >> (j % 64)) & 1) {
+                steps.push_back({cz, nullptr, j});
+            }
+        }
+        // simulate the steps on row r alone to decide the trailing single-qubit steps
+        auto run = [&](size_t row, size_t upto, int &ck, uint8_t &sg) {
+            const size_t wk = k / 64;
+            const uint64_t bk = 1ull << (k % 64);
+            uint64_t *x = xr(row), *z = zr(row);
+            ck = ((x[wk] & bk) ? 1 : 0) | ((z[wk] & bk) ? 2 : 0);
+            for (size_t s = 0; s < upto; s++) {
+                const Step &st = steps[s];
+                if (st.t2 != nullptr) {
+                    const size_t wj = st.j / 64;
+                    const uint64_t bj = 1ull << (st.j % 64);
+                    const int cj = ((x[wj] & bj) ? 1 : 0) | ((z[wj] & bj) ? 2 : 0);
+                    const int c = ck | (cj << 2);
+                    if (c) {
+                        const int d = st.t2->img[c];
+                        sg ^= st.t2->sgn[c];
+                        ck = d & 3;
+                        const int dj = d >> 2;
+                        x[wj] = (x[wj] & ~bj) | ((dj & 1) ? bj : 0);
+                        z[wj] = (z[wj] & ~bj) | ((dj & 2) ? bj : 0);
+                    }
+                } else if (ck) {
+                    sg ^= st.t1->sgn[ck];
+                    ck = st.t1->img[ck];
+                }
+            }
+            x[wk] = (x[wk] & ~bk) | ((ck & 1) ? bk : 0);
+            z[wk] = (z[wk] & ~bk) | ((ck & 2) ? bk : 0);
+        };
+        // row r first (it decides S and X), then every other row with the complete list
+        const size_t n2 = steps.size();
+        int ck;
+        run(r, n2, ck, sign[r]);
+        size_t first_tail = steps.size();
+        if (ck & 2) {  // z_k still set: S
+            steps.push_back({nullptr, &tb.inv1.at("S"), k});
+        }
+        steps.push_back({nullptr, &tb.inv1.at("H"), k});
+        {
+            // continue row r through the tail to learn its sign before the optional X
+            const size_t wk = k / 64;
+            const uint64_t bk = 1ull << (k % 64);
+            int c = ((xr(r)[wk] & bk) ? 1 : 0) | ((zr(r)[wk] & bk) ? 2 : 0);
+            uint8_t sg = sign[r];
+            for (size_t s = first_tail; s < steps.size(); s++) {
+                if (c) {
+                    sg ^= steps[s].t1->sgn[c];
+                    c = steps[s].t1->img[c];
+                }
+            }
+            if (sg) {
+                steps.push_back({nullptr, &tb.inv1.at("X"), k});
+            }
+        }
+        // row r: only the tail is left; all other rows: everything
+        {
+            const size_t wk = k / 64;
+            const uint64_t bk = 1ull << (k % 64);
+            int c = ((xr(r)[wk] & bk) ? 1 : 0) | ((zr(r)[wk] & bk) ? 2 : 0);
+            for (size_t s = first_tail; s < steps.size(); s++) {
+                if (c) {
+                    sign[r] ^= steps[s].t1->sgn[c];
+                    c = steps[s].t1->img[c];
+                }
+            }
+            xr(r)[wk] = (xr(r)[wk] & ~bk) | ((c & 1) ? bk : 0);
+            zr(r)[wk] = (zr(r)[wk] & ~bk) | ((c & 2) ? bk : 0);
+        }
+        for (size_t row = 0; row < 2 * n; row++) {
+            if (row != r) {
+                int c;
+                run(row, steps.size(), c, sign[row]);
+            }
+        }
+    }
+
     void to_z_basis(uint32_t basis, size_t q) {
         if (basis == GB_X) {
             gate1("H", q);
@@ -395,6 +555,10 @@ std::vector<Product> read_products(const Instruction &op) {
 std::vector<uint8_t> reference_sample(const Circuit &circuit) {
     CircuitStats stats = compute_stats(circuit);
     Sim sim(std::max<size_t>(stats.num_qubits, 1));
+    {
+        const char *e = getenv("GSTIM_TABLEAU_SLOW");  // differential testing of the fused column pass
+        sim.slow_column_ops = e != nullptr && e[0] == '1';
+    }
     auto rec_value = [&](uint32_t t, const char *gate) -> bool {
         uint64_t k = t & T_VALUE_MASK;
         if (k == 0 || k > sim.record.size()) {
@@ -414,17 +578,19 @@ std::vector<uint8_t> reference_sample(const Circuit &circuit) {
                     }
                 }
                 break;
-            case GateCat::CLIFF1:
+            case GateCat::CLIFF1: {
+                const Table1 &tb = tables().inv1.at(name);
                 for (uint32_t t : op.targets) {
-                    sim.gate1(name, t & T_VALUE_MASK);
+                    sim.gate1(tb, t & T_VALUE_MASK);
                 }
-                break;
-            case GateCat::CLIFF2:
+            } break;
+            case GateCat::CLIFF2: {
+                const Table2 &tb = tables().inv2.at(name);
                 for (size_t i = 0; i < op.targets.size(); i += 2) {
                     uint32_t a = op.targets[i], b = op.targets[i + 1];
                     bool a_bit = (a & (T_REC | T_SWEEP)) != 0, b_bit = (b & (T_REC | T_SWEEP)) != 0;
                     if (!a_bit && !b_bit) {
-                        sim.gate2(name, a & T_VALUE_MASK, b & T_VALUE_MASK);
+                        sim.gate2(tb, a & T_VALUE_MASK, b & T_VALUE_MASK);
                         continue;
                     }
                     // classically controlled Pauli (bit-as-target errors are raised by the lowering)
@@ -444,7 +610,7 @@ std::vector<uint8_t> reference_sample(const Circuit &circuit) {
                         sim.pauli(code, q & T_VALUE_MASK);
                     }
                 }
-                break;
+            } break;
             case GateCat::MEASURE: {
                 uint32_t basis = g.param & 3, kind = g.param >> 2;
                 for (uint32_t t : op.targets) {

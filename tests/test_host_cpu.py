@@ -284,3 +284,48 @@ def test_lowered_golden_circuits_reproduce_the_reference_on_the_emulator(case):
         dets, obs = out[:, : pl["num_det"]], out[:, pl["num_det"]:]
         got = arrange(dets, obs, case["flags"])
         np.testing.assert_array_equal(got, expected_bits(case, got.shape[1])[:shots])
+
+
+def test_reference_sample_matches_the_reference_and_its_own_slow_path(monkeypatch):
+    """gstim_reference_sample (host inverse-tableau simulator, replaces TableauSimulator::reference_sample_circuit):
+    equals the reference's sample on the golden circuits, and its fast paths (fused column pass for random measurements,
+    in-place row products) equal the step-by-step path on random Clifford circuits."""
+    import random
+
+    from golden_util import load_cases
+    from stim_b200 import _reference_sample as rs
+
+    for case in load_cases():
+        if case["mode"] != "sample":
+            continue
+        ref = np.array([int(ch) for ch in case["reference_sample"]], dtype=np.uint8)
+        got = np.unpackbits(rs.reference_sample_bits(case["circuit"], ref.size), bitorder="little")[: ref.size]
+        np.testing.assert_array_equal(got, ref, err_msg=case["name"])
+
+    g1 = ["H", "S", "S_DAG", "SQRT_X", "SQRT_X_DAG", "SQRT_Y", "SQRT_Y_DAG", "H_XY", "H_YZ", "C_XYZ", "C_ZYX", "X", "Y", "Z"]
+    g2 = ["CX", "CY", "CZ", "SWAP", "ISWAP", "ISWAP_DAG", "SQRT_XX", "SQRT_YY", "SQRT_ZZ", "XCX", "XCY", "XCZ", "YCX", "YCY", "YCZ",
+          "CXSWAP", "SWAPCX", "CZSWAP"]
+    ms = ["M", "MX", "MY", "MR", "MRX", "MRY", "R", "RX", "RY"]
+    rng = random.Random(5)
+    for _ in range(300):
+        n = rng.choice([2, 3, 5, 9, 17, 70, 130])
+        lines = []
+        for _ in range(rng.choice([10, 40, 150])):
+            r = rng.random()
+            if r < 0.4:
+                lines.append(f"{rng.choice(g1)} {rng.randrange(n)}")
+            elif r < 0.8:
+                a, b = rng.sample(range(n), 2)
+                lines.append(f"{rng.choice(g2)} {a} {b}")
+            elif r < 0.95:
+                lines.append(f"{rng.choice(ms)} {rng.randrange(n)}")
+            else:
+                lines.append("MPP " + "*".join(rng.choice("XYZ") + str(q) for q in rng.sample(range(n), min(n, 3))))
+        lines.append("M " + " ".join(map(str, range(n))))
+        text = "\n".join(lines)
+        m = stim_b200.Circuit(text).num_measurements
+        monkeypatch.setenv("GSTIM_TABLEAU_SLOW", "1")
+        slow = rs.reference_sample_bits(text, m)
+        monkeypatch.setenv("GSTIM_TABLEAU_SLOW", "0")
+        fast = rs.reference_sample_bits(text, m)
+        np.testing.assert_array_equal(fast, slow)
