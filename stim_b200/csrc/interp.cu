@@ -262,11 +262,12 @@ __device__ __forceinline__ void flip_rec(const BlockCtx *bc, uint32_t rec_index,
 // is interpreted every noise site of the whole program is sampled up front. The sites of a noise group are
 // cut into slices of GSTIM_NOISE_SLICE sites (program.h "Noise schedule"); a slice x this shot block is one
 // Bernoulli sequence with its own Philox stream. Threads claim slices from a shared counter and walk them with
-// geometric gaps: every loop iteration is one Philox draw -> the gap to the slice's next event and that
-// event's Pauli word, so all lanes of a warp do the same work each iteration and idle only at the very end.
-// Lanes of a warp work on neighbouring slices, i.e. mostly on the same noise batch: they append their events
-// with one counter update per warp and contiguous (coalesced) stores into this CTA's (L2-resident) scratch,
-// one segment per noise batch. The interpreter then only applies flips.
+// geometric gaps: every loop iteration is one Philox call -> two draws (gap to the slice's next event, that
+// event's Pauli word), so all lanes of a warp do the same work each iteration and idle only at the very end.
+// Lanes of a warp work on neighbouring slices, i.e. mostly on the same noise batch: a record takes its place
+// with one shared-memory atomic on the batch's counter, and the places of neighbouring lanes are mostly
+// consecutive, so the stores into this CTA's (L2-resident) scratch coalesce; one segment per noise batch.
+// The interpreter then only applies flips.
 //
 // Distribution == RareErrorIterator (/root/reference/src/stim/util_bot/probability_util.cc:33-43):
 // gaps are floor(Exp(1)/lambda) = Geometric(p), in exact integer arithmetic (unit 2^-56 nat).
