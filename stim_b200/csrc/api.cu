@@ -504,6 +504,8 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
         }
         cudaEvent_t e0 = get_event(s, ev++), e1 = get_event(s, ev++), e2 = get_event(s, ev++);
         CK(cudaEventRecord(e0, s->stream));
+        // (the attribute is per kernel and device, not per sampler: another sampler may have lowered it since)
+        CK(interp_set_max_smem(smem));
         CK(launch_interp(p, grid, s->threads + s->pre_threads, smem, s->stream));
         CK(cudaEventRecord(e1, s->stream));
         s->last_launches++;
@@ -718,6 +720,7 @@ void sample_to_host(
     };
 
     int cur = 0;
+    try {
     run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
         drain(cur);  // buffer about to be reused
         s->d_stage[cur].ensure(n * stage_pitch + 16);
@@ -751,6 +754,12 @@ void sample_to_host(
         pending[cur].n = n;
         cur ^= 1;
     }, 512);
+    } catch (...) {
+        // no copy may still be writing into the caller's buffer (or the staging buffers) once the error is reported
+        cudaStreamSynchronize(s->copy_stream);
+        pending[0].active = pending[1].active = false;
+        throw;
+    }
     drain(cur);
     drain(cur ^ 1);
 }
@@ -908,18 +917,28 @@ int gstim_circuit_stats(const char *circuit_text, size_t text_len, gstim_stats *
     return guarded([&] {
         require(circuit_text != nullptr && out != nullptr, "NULL argument.");
         Circuit c = Circuit::from_text(std::string_view(circuit_text, text_len));
-        // lowering validates what the parser cannot (record lookbacks, bit targets) without touching a GPU
-        LoweredCircuit lc = lower_circuit(c, GSTIM_MODE_DETECTORS, 2048 - GSTIM_HDR_WORDS);
+        // (parse + count only: like the reference, a bad rec[-k] lookback surfaces when a sampler is compiled, not here)
+        const CircuitStats st = compute_stats(c);
+        std::vector<uint8_t> used(st.num_qubits, 0);
+        uint64_t active = 0;
+        c.for_each_instruction_once([&](const Instruction &op) {
+            if (op.gate->cat == GateCat::MPAD || op.gate->targets == TR_NONE || std::string(op.gate->name) == "QUBIT_COORDS") {
+                return;
+            }
+            for (uint32_t t : op.targets) {
+                if (t != T_COMBINER && !(t & (T_REC | T_SWEEP)) && !used[t & T_VALUE_MASK]) {
+                    used[t & T_VALUE_MASK] = 1;
+                    active++;
+                }
+            }
+        });
         memset(out, 0, sizeof(*out));
-        out->num_qubits = lc.stats.num_qubits;
-        out->num_measurements = lc.stats.num_measurements;
-        out->num_detectors = lc.stats.num_detectors;
-        out->num_observables = lc.stats.num_observables;
-        out->max_lookback = lc.stats.max_lookback;
-        out->active_qubits = lc.num_qubits;
-        out->num_batches = lc.batches.size();
-        out->num_noise_sites = lc.num_sites;
-        out->num_collapse_sites = lc.num_csites;
+        out->num_qubits = st.num_qubits;
+        out->num_measurements = st.num_measurements;
+        out->num_detectors = st.num_detectors;
+        out->num_observables = st.num_observables;
+        out->max_lookback = st.max_lookback;
+        out->active_qubits = active;
     });
 }
 

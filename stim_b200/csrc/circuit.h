@@ -108,6 +108,17 @@ struct Circuit {
             }
         }
     }
+    // Visits every non-REPEAT instruction of the text once (REPEAT bodies are not unrolled).
+    template <typename F>
+    void for_each_instruction_once(F &&f) const {
+        for (const auto &op : ops) {
+            if (op.gate->cat == GateCat::REPEAT) {
+                blocks[op.block_index].for_each_instruction_once(f);
+            } else {
+                f(op);
+            }
+        }
+    }
 };
 
 // Aggregate sizes, mirroring stim::CircuitStats (/root/reference/src/stim/circuit/circuit_instruction.h:30-50).

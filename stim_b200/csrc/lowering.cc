@@ -1258,8 +1258,28 @@ LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch
     // record addressing
     uint64_t rec_slots;
     if (mode == 0) {
+        // The ring must also hold every result of one instruction at once: a noisy measurement / heralded channel with
+        // more targets than ring slots would alias two of its record rows (and cut its RNG group inside a slice).
+        uint64_t most_results = 0;
+        c.for_each_instruction_once([&](const Instruction &op) {
+            switch (op.gate->cat) {
+                case GateCat::MEASURE:
+                case GateCat::MPAD:
+                case GateCat::MPP:
+                case GateCat::MPAIR:
+                case GateCat::HERALDED_ERASE:
+                case GateCat::HERALDED_PAULI_CHANNEL_1:
+                    most_results = std::max<uint64_t>(most_results, op.targets.size());  // (an upper bound for MPP / MPAIR)
+                    break;
+                default:
+                    break;
+            }
+        });
+        if (lc.stats.max_lookback + most_results >= (1ull << 31)) {
+            throw std::invalid_argument("Measurement record window too large for this build.");
+        }
         uint32_t ring = 1;
-        while (ring < lc.stats.max_lookback) {
+        while (ring < lc.stats.max_lookback + most_results) {
             ring <<= 1;
         }
         lc.rec_ring = ring;

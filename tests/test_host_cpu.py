@@ -90,9 +90,6 @@ def test_circuit_stats_match_reference_numbers():
     "M(0.1, 0.2) 0",
     "DETECTOR 0",
     "MPP X0*",
-    "MPP X0*Z0",
-    "CX 0 rec[-1]",
-    "M 0\nCY 1 rec[-1]",
     "REPEAT 0 {\nH 0\n}",
     "REPEAT 2 {\nH 0\n",
     "}",
@@ -106,10 +103,36 @@ def test_invalid_circuits_raise_value_error(text):
         stim_b200.Circuit(text)
 
 
+@pytest.mark.parametrize("text", ["MPP X0*Z0", "CX 0 rec[-1]", "M 0\nCY 1 rec[-1]"])
+def test_errors_the_reference_raises_when_the_circuit_is_run(text):
+    """Anti-Hermitian products (gate_decomposition.cc) and bit-as-target (frame_simulator.inl:399-402, 421-424) parse
+    fine in the reference and throw std::invalid_argument when simulated: here, when a sampler is compiled."""
+    c = stim_b200.Circuit(text)
+    with pytest.raises(ValueError):
+        c.compile_detector_sampler(seed=1)
+    with pytest.raises(ValueError):
+        c.compile_sampler(seed=1, skip_reference_sample=True)
+
+
 @pytest.mark.parametrize("text", ["DETECTOR rec[-1]", "M 0\nDETECTOR rec[-2]", "M 0\nCX rec[-3] 1", "OBSERVABLE_INCLUDE(0) rec[-1]"])
 def test_bad_lookback_raises_index_error(text):
+    c = stim_b200.Circuit(text)  # parses, like the reference
     with pytest.raises(IndexError):  # measure_record_batch.inl:83-94 throws std::out_of_range
-        stim_b200.Circuit(text)
+        c.compile_detector_sampler(seed=1)
+
+
+@pytest.mark.parametrize("text", [
+    "M(0.01) 0 1 2 3\nDETECTOR rec[-1]",
+    "HERALDED_PAULI_CHANNEL_1(0.01, 0.02, 0.03, 0.04) 1 0",
+    "MPP(0.1) X0*X1 Z0*Z1 Y2 Z3 X4\nDETECTOR rec[-2]",
+    "MPAD(0.25) 0 1 1 0 1",
+])
+def test_noisy_results_with_more_targets_than_the_lookback_window(text):
+    """The record ring of detector mode must hold every result of one instruction (round-1 bug: it was sized from the
+    maximum lookback alone, two record rows of one noisy instruction aliased and lowering threw)."""
+    for mode in (0, 1):
+        w, plan = lower(text, mode, 32)  # (used to throw "a noise group was cut inside an RNG slice")
+        assert w.size > 0
 
 
 def test_parser_accepts_the_documented_syntax():
