@@ -29,7 +29,8 @@ WORKLOAD = "surface_code:rotated_memory_z d=25 rounds=25 p=1e-3 (all four noise 
 METRIC = "detector shots/s, rotated surface code d=25 r=25 p=1e-3"
 ALG_BYTES_PER_SHOT = 1951       # ceil((15600 detectors + 1 observable) / 8): result bytes written once
 ALG_LOP3_PER_SHOT = 168026 / 32  # XOR word-ops of the frame algorithm per shot
-LOP3_LANES_PER_CLK_PER_SM = 64   # B300_MICROARCH.md: alu pipe rt_SMSP = 2 -> 16 lanes/clk/SMSP
+LOP3_LANES_PER_CLK_PER_SM = 64   # fallback only (B300_MICROARCH.md: alu pipe rt_SMSP = 2 -> 16 lanes/clk/SMSP); bench measures it
+C4_CIRCUIT = os.path.join(ROOT, "tests", "golden", "circuits", "c4_color_d15_r15.stim")
 
 
 def measured_traffic_bytes_per_shot():
@@ -139,7 +140,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     nproc = os.cpu_count() or 1
-    shots_per_proc = 1 << 15
+    shots_per_proc = 1 << 17  # >= 2^17 shots per process, so process start + circuit parsing (< 30 ms) are amortised
     if not os.path.exists(REF_STIM):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/stim is not built (run make -C oracle ref)"}))
         return
@@ -323,7 +324,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_STIM):
         nproc = os.cpu_count() or 1
-        sp = 1 << 16
+        sp = 1 << 17
         t1 = run_reference(sp, 1, 777)
         tn = run_reference(sp, nproc, 888)
         line["cpu_baseline"] = {

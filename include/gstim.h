@@ -197,6 +197,26 @@ int gstim_write_shots_to_fd(
  * multi-GPU caller can allreduce it (NCCL sum over uint64[D+L]) without a host round trip. */
 int gstim_detector_flip_counts(gstim_sampler *s, uint64_t shots, uint64_t *counts_host, void *counts_dev);
 
+/* Flip counts of every output bit over `shots` fresh shots, computed on the device from the bit-major table (no
+ * transposition, no result transfer): single[n] and pair[n - 1] (count of shots where bits j and j + 1 are both set),
+ * n = D + L in detector mode (detectors then observables) or M in measurement mode (reference sample applied).
+ * Any of the four outputs may be NULL; the *_dev pointers are device memory (uint64), e.g. for an NCCL allreduce.
+ * This is the statistic of the reference's own sampling tests (src/stim/cmd/command_sample.test.cc:39-71), and what
+ * sinter's collection loop reduces shots to (glue/sample/src/sinter/_decoding/_stim_then_decode_sampler.py:162-185). */
+int gstim_bit_counts(gstim_sampler *s, uint64_t shots, uint64_t *single_host, uint64_t *pair_host, void *single_dev, void *pair_dev);
+
+/* Pins the number of 128-shot columns per thread block (0 = choose per call from the shot count, the default). The
+ * random stream is a function of (seed, shot offset, columns per block): callers that split one global shot range over
+ * several handles / GPUs and need the union to equal a single-handle run pin the same value everywhere and keep every
+ * shard a multiple of columns * 128 shots. `columns` must be a multiple of lanes_per_item and <= max_columns
+ * (gstim_get_stats). */
+int gstim_set_block_columns(gstim_sampler *s, uint32_t columns);
+
+/* Integer-ALU roofline probe: runs a LOP3 microbenchmark on `device` and reports 32-bit logic lane-operations per clock
+ * per SM, per second for the whole chip, and the SM clock during the probe (MHz). Measurement aid for bench.py
+ * (SURVEY.md 8d); not on the sampling path. */
+int gstim_measure_lop3_peak(int device, double *lane_ops_per_clk_per_sm, double *lane_ops_per_sec, double *sm_mhz);
+
 /* Kernel launches issued by the most recent sampling call (for bench accounting). */
 int gstim_last_launch_count(const gstim_sampler *s, uint64_t *launches);
 

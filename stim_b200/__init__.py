@@ -20,7 +20,14 @@ import numpy as np
 from . import _native
 from ._native import GstimCudaError, GstimStats
 
-__all__ = ["Circuit", "CompiledDetectorSampler", "CompiledMeasurementSampler", "GstimCudaError"]
+__all__ = ["Circuit", "CompiledDetectorSampler", "CompiledMeasurementSampler", "GstimCudaError", "measure_lop3_peak"]
+
+
+def measure_lop3_peak(device: int = 0) -> dict:
+    """LOP3 microbenchmark (gstim_measure_lop3_peak): the measured integer-ALU roofline of `device`."""
+    a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+    _native.check(_native.lib().gstim_measure_lop3_peak(int(device), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return {"lane_ops_per_clk_per_sm": a.value, "lane_ops_per_sec": b.value, "sm_mhz": c.value}
 
 
 def _seed_to_u64(seed) -> int:
@@ -127,6 +134,10 @@ class _Sampler:
     def shot_offset(self, value: int):
         _native.check(_native.lib().gstim_set_shot_offset(self._handle, ctypes.c_uint64(int(value))))
 
+    def set_block_columns(self, columns: int) -> None:
+        """Pins K (128-shot columns per thread block); 0 = automatic. See gstim_set_block_columns."""
+        _native.check(_native.lib().gstim_set_block_columns(self._handle, int(columns)))
+
     def last_launch_count(self) -> int:
         v = ctypes.c_uint64(0)
         _native.check(_native.lib().gstim_last_launch_count(self._handle, ctypes.byref(v)))
@@ -146,6 +157,23 @@ class _Sampler:
         a, b = ctypes.c_float(0), ctypes.c_float(0)
         _native.check(_native.lib().gstim_last_kernel_ms(self._handle, ctypes.byref(a), ctypes.byref(b)))
         return float(a.value), float(b.value)
+
+
+def _bit_counts(self, shots: int, pairs: bool = True, single_dev_ptr: int = 0, pair_dev_ptr: int = 0):
+    """(single[n], pair[n - 1]) uint64 flip counts of every output bit and of adjacent bit pairs over `shots` fresh
+    shots, reduced on the device (gstim_bit_counts); optional device copies for an NCCL allreduce."""
+    n = int(self.stats.num_detectors + self.stats.num_observables) if isinstance(self, CompiledDetectorSampler) else int(
+        self.stats.num_measurements)
+    single = np.zeros(n, dtype=np.uint64)
+    pair = np.zeros(max(n - 1, 0), dtype=np.uint64)
+    _native.check(_native.lib().gstim_bit_counts(
+        self._handle, int(shots), single.ctypes.data_as(ctypes.c_void_p),
+        pair.ctypes.data_as(ctypes.c_void_p) if pairs and pair.size else None,
+        ctypes.c_void_p(single_dev_ptr or None), ctypes.c_void_p(pair_dev_ptr or None)))
+    return single, pair
+
+
+_Sampler.bit_counts = _bit_counts
 
 
 def _prepare_out(buf, shots: int, n_bits: int, bit_packed: bool):
@@ -298,6 +326,21 @@ class CompiledDetectorSampler(_Sampler):
             return dets, obs
         out = torch.empty((shots, (D + L + 7) // 8), dtype=torch.uint8, device=dev)
         self.sample_device(shots, out.data_ptr(), append_observables=True)
+        return out
+
+    def sample_pinned(self, shots: int, *, separate_observables: bool = True):
+        """Bit-packed results in page-locked host memory (numpy views of pinned torch tensors): the library DMAs straight
+        into them (no staging copy), and a consumer can feed them to further async H2D copies."""
+        import torch
+
+        D, L = int(self.stats.num_detectors), int(self.stats.num_observables)
+        if separate_observables:
+            dets = torch.empty((shots, (D + 7) // 8), dtype=torch.uint8, pin_memory=True).numpy()
+            obs = torch.empty((shots, (L + 7) // 8), dtype=torch.uint8, pin_memory=True).numpy()
+            self.sample(shots, bit_packed=True, dets_out=dets, obs_out=obs)
+            return dets, obs
+        out = torch.empty((shots, (D + L + 7) // 8), dtype=torch.uint8, pin_memory=True).numpy()
+        self.sample(shots, bit_packed=True, append_observables=True, dets_out=out)
         return out
 
     def flip_counts(self, shots: int, counts_dev_ptr: int = 0) -> np.ndarray:

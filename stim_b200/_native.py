@@ -77,6 +77,10 @@ _SIGNATURES = [
     ("gstim_write_shots_to_fd", ctypes.c_int, [_P, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int,
                                                ctypes.c_char_p, ctypes.c_char, ctypes.c_char, ctypes.c_uint64]),
     ("gstim_detector_flip_counts", ctypes.c_int, [_P, ctypes.c_uint64, _P, _P]),
+    ("gstim_bit_counts", ctypes.c_int, [_P, ctypes.c_uint64, _P, _P, _P, _P]),
+    ("gstim_set_block_columns", ctypes.c_int, [_P, ctypes.c_uint32]),
+    ("gstim_measure_lop3_peak", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                               ctypes.POINTER(ctypes.c_double)]),
     ("gstim_last_launch_count", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
     ("gstim_last_block_columns", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32)]),
     ("gstim_last_call_ms", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),

@@ -140,6 +140,7 @@ struct gstim_sampler {
 
     uint64_t last_launches = 0;
     uint32_t last_K = 0;
+    uint32_t K_fixed = 0;  // gstim_set_block_columns: 0 = chosen per call from the shot count
     float last_interp_ms = 0, last_transpose_ms = 0, last_call_ms = 0;
     cudaEvent_t call_start = nullptr, call_end = nullptr;
 
@@ -318,6 +319,9 @@ void configure(gstim_sampler *s) {
 }
 
 uint32_t choose_K(const gstim_sampler *s, uint64_t shots) {
+    if (s->K_fixed) {
+        return s->K_fixed;
+    }
     uint32_t G = 1u << s->G_log2;
     uint64_t cols = (shots + GSTIM_COL_SHOTS - 1) / GSTIM_COL_SHOTS;
     // aim for at least two blocks per SM before growing the block
@@ -1224,26 +1228,63 @@ int gstim_write_shots_to_fd(
     });
 }
 
-int gstim_detector_flip_counts(gstim_sampler *s, uint64_t shots, uint64_t *counts_host, void *counts_dev) {
+int gstim_bit_counts(gstim_sampler *s, uint64_t shots, uint64_t *single_host, uint64_t *pair_host, void *single_dev, void *pair_dev) {
     return guarded([&] {
         require(s != nullptr, "NULL sampler.");
-        require(s->mode == GSTIM_MODE_DETECTORS, "Not a detector sampler.");
-        const uint32_t rows = n_rows_of(s);
+        const bool want_pairs = pair_host != nullptr || pair_dev != nullptr;
+        RowMaps maps = s->mode == GSTIM_MODE_DETECTORS ? detector_row_maps(s, GSTIM_APPEND_OBS) : measurement_row_maps(s);
+        const uint32_t n_bits = (uint32_t)maps.main.size();
         CK(cudaSetDevice(s->device));
-        s->d_counts.ensure((size_t)std::max<uint32_t>(rows, 1) * 8);
-        CK(cudaMemsetAsync(s->d_counts.p, 0, (size_t)rows * 8, s->stream));
+        s->d_rowmap.ensure((size_t)(n_bits + 1) * 4);
+        upload_row_map(s, maps.main, 0);
+        s->d_counts.ensure((size_t)std::max<uint32_t>(n_bits, 1) * 16);
+        CK(cudaMemsetAsync(s->d_counts.p, 0, (size_t)std::max<uint32_t>(n_bits, 1) * 16, s->stream));
+        unsigned long long *d_single = (unsigned long long *)s->d_counts.p, *d_pair = d_single + n_bits;
         run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
             (void)first;
-            CK(launch_row_popcount(table, n_rows, n, (unsigned long long *)s->d_counts.p, s->stream));
+            CK(launch_bit_counts(table, n_rows, n, (const uint32_t *)s->d_rowmap.p, n_bits, d_single, want_pairs ? d_pair : nullptr, s->stream));
             s->last_launches++;
         });
-        if (counts_dev) {
-            CK(cudaMemcpyAsync(counts_dev, s->d_counts.p, (size_t)rows * 8, cudaMemcpyDeviceToDevice, s->stream));
+        const size_t nb1 = (size_t)n_bits * 8, nb2 = n_bits ? (size_t)(n_bits - 1) * 8 : 0;
+        if (single_dev) {
+            CK(cudaMemcpyAsync(single_dev, d_single, nb1, cudaMemcpyDeviceToDevice, s->stream));
         }
-        if (counts_host) {
-            CK(cudaMemcpyAsync(counts_host, s->d_counts.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (pair_dev && nb2) {
+            CK(cudaMemcpyAsync(pair_dev, d_pair, nb2, cudaMemcpyDeviceToDevice, s->stream));
+        }
+        if (single_host) {
+            CK(cudaMemcpyAsync(single_host, d_single, nb1, cudaMemcpyDeviceToHost, s->stream));
+        }
+        if (pair_host && nb2) {
+            CK(cudaMemcpyAsync(pair_host, d_pair, nb2, cudaMemcpyDeviceToHost, s->stream));
         }
         CK(cudaStreamSynchronize(s->stream));
+    });
+}
+
+int gstim_detector_flip_counts(gstim_sampler *s, uint64_t shots, uint64_t *counts_host, void *counts_dev) {
+    if (s != nullptr && s->mode != GSTIM_MODE_DETECTORS) {
+        return guarded([&] { require(false, "Not a detector sampler."); });
+    }
+    return gstim_bit_counts(s, shots, counts_host, nullptr, counts_dev, nullptr);
+}
+
+int gstim_measure_lop3_peak(int device, double *lane_ops_per_clk_per_sm, double *lane_ops_per_sec, double *sm_mhz) {
+    return guarded([&] {
+        require(lane_ops_per_clk_per_sm && lane_ops_per_sec && sm_mhz, "NULL argument.");
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        CK(measure_lop3_peak(prop.multiProcessorCount, lane_ops_per_clk_per_sm, lane_ops_per_sec, sm_mhz));
+    });
+}
+
+int gstim_set_block_columns(gstim_sampler *s, uint32_t columns) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        const uint32_t G = 1u << s->G_log2;
+        require(columns == 0 || (columns % G == 0 && columns <= s->K_max), "columns must be 0 (automatic) or a multiple of lanes_per_item up to max_columns.");
+        s->K_fixed = columns;
     });
 }
 

@@ -4,10 +4,11 @@
 //   gstim_transpose_kernel  bit-major rows -> dense shot-major b8 bytes.
 //                         Replaces simd_bit_table::transposed + write_table_data
 //                         (/root/reference/src/stim/io/measure_record_writer.h:101-166).
-//   gstim_popcount_kernel per-row flip counts (feeds the optional multi-GPU allreduce).
+//   gstim_bitcount_kernel per-bit flip counts and adjacent-pair counts (feed the optional multi-GPU allreduce).
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <vector>
 
 namespace gstim {
 
@@ -204,42 +205,155 @@ cudaError_t launch_transpose_b8(const TransposeParams &p, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Row popcounts of a column-major table: thread = row (coalesced across a column), blockIdx.y = slice of columns.
+// Flip counts of the output bits of a column-major table: single[j] = popcount of output bit j over the first n_shots
+// shots, pair[j] = popcount of (bit j AND bit j + 1) (the adjacent-pair correlations of the statistical parity tests).
+// Output bit j = table row (row_map[j] & 0x7FFFFFFF), inverted when bit 31 of the map entry is set (reference sample).
+// thread = output bit (a warp reads 512 contiguous bytes of a column when the map is the identity), blockIdx.y = slice
+// of columns. `pair` may be null.
 // ------------------------------------------------------------------------------------------------
-__global__ void gstim_popcount_kernel(const uint4 *table, uint64_t n_rows, uint64_t n_shots, unsigned long long *counts) {
-    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) {
+__device__ __forceinline__ uint4 masked_row(const uint4 *table, uint64_t c, uint64_t n_rows, uint32_t rm, uint64_t n_shots) {
+    uint4 v = table[c * n_rows + (rm & 0x7FFFFFFFu)];
+    const uint32_t inv = (uint32_t)0 - (rm >> 31);
+    uint32_t wds[4] = {v.x ^ inv, v.y ^ inv, v.z ^ inv, v.w ^ inv};
+    const uint64_t left = n_shots - c * 128;  // shots of this column that count
+    if (left < 128) {
+        for (uint32_t i = 0; i < 4; i++) {
+            const uint64_t lo = 32ull * i;
+            wds[i] = left <= lo ? 0u : (left - lo >= 32 ? wds[i] : wds[i] & ((1u << (left - lo)) - 1));
+        }
+    }
+    return make_uint4(wds[0], wds[1], wds[2], wds[3]);
+}
+
+__global__ void gstim_bitcount_kernel(const uint4 *table, uint64_t n_rows, uint64_t n_shots, const uint32_t *row_map, uint32_t n_bits,
+                                      unsigned long long *single, unsigned long long *pair) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_bits) {
         return;
     }
+    const uint32_t rm0 = row_map ? row_map[j] : (uint32_t)j;
+    const bool has_next = pair != nullptr && j + 1 < n_bits;
+    const uint32_t rm1 = has_next ? (row_map ? row_map[j + 1] : (uint32_t)(j + 1)) : rm0;
     const uint64_t n_cols = (n_shots + 127) / 128;
-    unsigned long long acc = 0;
+    unsigned long long a1 = 0, a2 = 0;
     for (uint64_t c = blockIdx.y; c < n_cols; c += gridDim.y) {
-        uint4 v = table[c * n_rows + row];
-        const uint64_t left = n_shots - c * 128;  // shots of this column that count
-        if (left < 128) {
-            uint32_t wds[4] = {v.x, v.y, v.z, v.w};
-            for (uint32_t i = 0; i < 4; i++) {
-                const uint64_t lo = 32ull * i;
-                wds[i] = left <= lo ? 0u : (left - lo >= 32 ? wds[i] : wds[i] & ((1u << (left - lo)) - 1));
-            }
-            v = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        const uint4 v = masked_row(table, c, n_rows, rm0, n_shots);
+        a1 += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        if (has_next) {
+            const uint4 w = masked_row(table, c, n_rows, rm1, n_shots);
+            a2 += __popc(v.x & w.x) + __popc(v.y & w.y) + __popc(v.z & w.z) + __popc(v.w & w.w);
         }
-        acc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
     }
-    if (acc) {
-        atomicAdd(&counts[row], acc);
+    if (a1) {
+        atomicAdd(&single[j], a1);
+    }
+    if (a2) {
+        atomicAdd(&pair[j], a2);
     }
 }
 
-cudaError_t launch_row_popcount(
-    const uint32_t *table, uint64_t n_rows, uint64_t n_shots, unsigned long long *counts, cudaStream_t stream) {
-    if (n_rows == 0 || n_shots == 0) {
+cudaError_t launch_bit_counts(const uint32_t *table, uint64_t n_rows, uint64_t n_shots, const uint32_t *row_map, uint32_t n_bits,
+                              unsigned long long *single, unsigned long long *pair, cudaStream_t stream) {
+    if (n_bits == 0 || n_shots == 0) {
         return cudaSuccess;
     }
     const uint64_t n_cols = (n_shots + 127) / 128;
-    dim3 grid((unsigned)((n_rows + 255) / 256), (unsigned)std::min<uint64_t>(n_cols, 1024));
-    gstim_popcount_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(table), n_rows, n_shots, counts);
+    dim3 grid((unsigned)((n_bits + 255) / 256), (unsigned)std::min<uint64_t>(n_cols, 1024));
+    gstim_bitcount_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(table), n_rows, n_shots, row_map, n_bits, single, pair);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer-ALU roofline probe ("lanes/clk/SM for 32-bit logic must be measured with a LOP3
+// microbenchmark on the box"). Every thread runs 8 independent chains of three-input LOP3 (xor3), fully unrolled;
+// blocks report their own clock64 span, the host divides the lane-operations of an SM by the longest span.
+// ------------------------------------------------------------------------------------------------
+constexpr int LOP3_CHAINS = 8, LOP3_UNROLL = 32;
+__global__ void __launch_bounds__(1024, 2) gstim_lop3_probe_kernel(uint32_t iters, uint32_t seed, uint32_t *sink, long long *spans) {
+    uint32_t v[LOP3_CHAINS];
+#pragma unroll
+    for (int c = 0; c < LOP3_CHAINS; c++) {
+        v[c] = seed * (threadIdx.x + 1u) + c;
+    }
+    const uint32_t a = seed ^ 0x9E3779B9u, b = seed + blockIdx.x;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < LOP3_UNROLL; u++) {
+#pragma unroll
+            for (int c = 0; c < LOP3_CHAINS; c++) {
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[c]) : "r"(a), "r"(b + u));
+            }
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < LOP3_CHAINS; c++) {
+        acc ^= v[c];
+    }
+    if (acc == 0x12345u) {
+        sink[0] = acc;  // keeps the chains alive
+    }
+    if (threadIdx.x == 0) {
+        spans[2 * blockIdx.x] = t0;
+        spans[2 * blockIdx.x + 1] = t1;
+    }
+}
+
+cudaError_t measure_lop3_peak(int num_sms, double *lane_ops_per_clk_per_sm, double *lane_ops_per_sec, double *sm_mhz) {
+    const uint32_t iters = 4096, grid = (uint32_t)num_sms * 2;
+    uint32_t *sink = nullptr;
+    long long *spans = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&sink, 16)) != cudaSuccess) {
+        return e;
+    }
+    if ((e = cudaMalloc(&spans, (size_t)grid * 16)) != cudaSuccess) {
+        cudaFree(sink);
+        return e;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best_per_clk = 0, best_per_sec = 0, mhz = 0;
+    std::vector<long long> h((size_t)grid * 2);
+    for (int rep = 0; rep < 5 && e == cudaSuccess; rep++) {
+        cudaEventRecord(e0);
+        gstim_lop3_probe_kernel<<<grid, 1024>>>(iters, 12345u + rep, sink, spans);
+        cudaEventRecord(e1);
+        if ((e = cudaEventSynchronize(e1)) != cudaSuccess) {
+            break;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaMemcpy(h.data(), spans, (size_t)grid * 16, cudaMemcpyDeviceToHost);
+        long long longest = 1;
+        for (uint32_t b = 0; b < grid; b++) {
+            longest = std::max(longest, h[2 * b + 1] - h[2 * b]);
+        }
+        // two 1024-thread blocks share an SM for (almost) the same span
+        const double ops_per_sm = 2.0 * 1024.0 * iters * LOP3_UNROLL * LOP3_CHAINS;
+        const double per_clk = ops_per_sm / (double)longest;
+        const double per_sec = ops_per_sm * num_sms / (ms * 1e-3);
+        if (rep > 0 && per_sec > best_per_sec) {  // (rep 0 = warm-up)
+            best_per_sec = per_sec;
+            best_per_clk = per_clk;
+            mhz = (double)longest / (ms * 1e-3) * 1e-6;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(spans);
+    if (e == cudaSuccess) {
+        e = cudaGetLastError();
+    }
+    *lane_ops_per_clk_per_sm = best_per_clk;
+    *lane_ops_per_sec = best_per_sec;
+    *sm_mhz = mhz;
+    return e;
 }
 
 }  // namespace gstim

@@ -59,8 +59,13 @@ struct TransposeParams {
 };
 cudaError_t launch_transpose_b8(const TransposeParams &p, cudaStream_t stream);
 
-// popcount of every row of a column-major bit table over the first n_shots shots -> counts[row] (uint64, accumulated)
-cudaError_t launch_row_popcount(
-    const uint32_t *table, uint64_t n_rows, uint64_t n_shots, unsigned long long *counts, cudaStream_t stream);
+// flip counts of the output bits (rows through row_map, bit 31 = invert; null = identity) over the first n_shots shots:
+// single[n_bits] and (optional) pair[n_bits - 1] = counts of bit j AND bit j + 1; both uint64, accumulated
+cudaError_t launch_bit_counts(const uint32_t *table, uint64_t n_rows, uint64_t n_shots, const uint32_t *row_map, uint32_t n_bits,
+                              unsigned long long *single, unsigned long long *pair, cudaStream_t stream);
+
+// LOP3 microbenchmark on the current device: 32-bit three-input logic lane-operations per clock per SM, per second
+// (whole chip) and the SM clock the probe ran at (MHz, from clock64 span / event time).
+cudaError_t measure_lop3_peak(int num_sms, double *lane_ops_per_clk_per_sm, double *lane_ops_per_sec, double *sm_mhz);
 
 }  // namespace gstim

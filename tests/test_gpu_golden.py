@@ -88,6 +88,47 @@ def _c3_variant(knob):
     return "\n".join(out)
 
 
+def _c5_variant(knob):
+    """BASELINE.json configs[4] (d=51 r=51, REPEAT kept) made deterministic: DEPOLARIZE off, one family of flips at p = 1:
+    "measure" = the X_ERROR / Z_ERROR directly in front of a measurement, "reset" = the ones behind a reset."""
+    import re
+
+    with open(os.path.join(ROOT, "tests", "golden", "circuits", "c5_surface_x_d51_r51.stim")) as f:
+        text = f.read()
+    text = re.sub(r"DEPOLARIZE([12])\(0\.001\)", r"DEPOLARIZE\1(0)", text)
+    lines = text.split("\n")
+    out = []
+    for i, ln in enumerate(lines):
+        m = re.match(r"\s*([XZ])_ERROR\(0\.001\)", ln)
+        if m:
+            nxt = next((l.strip() for l in lines[i + 1:] if l.strip()), "")
+            before_measure = nxt.startswith("M")
+            on = (knob == "measure") == before_measure
+            ln = ln.replace("_ERROR(0.001)", "_ERROR(1)" if on else "_ERROR(0)")
+        out.append(ln)
+    return "\n".join(out)
+
+
+def test_d51_deterministic_noise_rows_equal_reference():
+    """c5 (5201 qubits, 132 600 detectors, lookback 5201, REPEAT 50): every shot must equal the row the reference
+    produces (tests/golden/c5_det_rows.json, tools/gen_c3_rows.py); a noiseless run gives all-zero detectors."""
+    import json
+    import re
+
+    with open(os.path.join(ROOT, "tests", "golden", "c5_det_rows.json")) as f:
+        rows = json.load(f)
+    for knob in ("measure", "reset"):
+        want = np.frombuffer(bytes.fromhex(rows[knob]), dtype=np.uint8)
+        got = stim_b200.Circuit(_c5_variant(knob)).compile_detector_sampler(seed=2).sample(
+            1024 + 77, bit_packed=True, append_observables=True)
+        assert got.shape[1] == want.size == 16576
+        assert (got == want[None, :]).all(), knob
+    with open(os.path.join(ROOT, "tests", "golden", "circuits", "c5_surface_x_d51_r51.stim")) as f:
+        noiseless = re.sub(r"\((0\.001)\)", "(0)", f.read())
+    a = stim_b200.Circuit(noiseless).compile_detector_sampler(seed=1).sample(2048, bit_packed=True, append_observables=True)
+    assert a.shape == (2048, 16576) and not a.any()
+
+
 def test_full_size_noiseless_and_deterministic_noise():
     """BASELINE.json configs[2] size: a noiseless run gives all-zero detectors; with probability-1 flips every shot
     must equal the row the reference produces (fixture c3_det_rows.json)."""

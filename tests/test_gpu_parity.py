@@ -259,21 +259,52 @@ def test_output_layouts_are_consistent():
         fresh().sample(shots, separate_observables=True, append_observables=True)
 
 
-def test_device_resident_torch_results_equal_host_results():
-    """sample_torch (results stay on the GPU) returns the same bits as the host API for the same stream."""
+def test_device_resident_consumer_hook_matches_oracle():
+    """the sinter-shaped consumer (glue/sample/src/sinter/_decoding/_stim_then_decode_sampler.py:162-185:
+    sample bit-packed dets + separate observables, decode, count shots whose prediction differs) with the shots staying on
+    the GPU (sample_torch), and with page-locked host arrays (sample_pinned). Bits are checked against the ORACLE."""
     import torch
 
     text = gen_circuit("surface_code", "rotated_memory_z", 5, 5, 0.01)
-    a = stim_b200.Circuit(text).compile_detector_sampler(seed=11)
-    b = stim_b200.Circuit(text).compile_detector_sampler(seed=11)
-    shots = 5000
+    seed, shots = 11, 5000
+    a = stim_b200.Circuit(text).compile_detector_sampler(seed=seed)
     dets_t, obs_t = a.sample_torch(shots)
     assert dets_t.is_cuda and dets_t.dtype == torch.uint8 and obs_t.shape == (shots, 1)
-    dets_h, obs_h = b.sample(shots, bit_packed=True, separate_observables=True)
-    np.testing.assert_array_equal(dets_t.cpu().numpy(), dets_h)
-    np.testing.assert_array_equal(obs_t.cpu().numpy(), obs_h)
+    want_d, want_o = fo.sample(text, shots, seed, a.last_block_columns(), "detectors")
+    D = want_d.shape[1]
+    np.testing.assert_array_equal(np.unpackbits(dets_t.cpu().numpy(), axis=1, bitorder="little")[:, :D], want_d)
+    np.testing.assert_array_equal(obs_t.cpu().numpy() & 1, want_o)
+    # "decoder" that always predicts no logical flip, evaluated next to the data: errors = shots with a flipped observable
+    predictions = torch.zeros_like(obs_t)
+    num_errors = int((predictions != obs_t).any(dim=1).sum().item())
+    assert num_errors == int(want_o.any(axis=1).sum()) and 0 < num_errors < shots
+    # detection-event weight histogram on the device (what a GPU decoder's front end consumes)
+    lut = torch.tensor([bin(v).count("1") for v in range(256)], dtype=torch.int32, device=dets_t.device)
+    weights = lut[dets_t.long()].sum(dim=1)
+    np.testing.assert_array_equal(weights.cpu().numpy(), want_d.sum(axis=1))
+    # appended form continues the stream: compare with the oracle at the advanced offset
+    off = a.shot_offset
     both = a.sample_torch(shots, separate_observables=False)
-    ref = b.sample(shots, bit_packed=True, append_observables=True)
-    np.testing.assert_array_equal(both.cpu().numpy(), ref)
-    # a reduction next to the data: shots with at least one detection event
-    assert 0 < int((dets_t != 0).any(dim=1).sum().item()) <= shots
+    d2, o2 = fo.sample(text, shots, seed, a.last_block_columns(), "detectors", col0=off // 128)
+    np.testing.assert_array_equal(np.unpackbits(both.cpu().numpy(), axis=1, bitorder="little")[:, : D + 1], np.concatenate([d2, o2], axis=1))
+    # page-locked host arrays (DMA target of the direct copy path)
+    b = stim_b200.Circuit(text).compile_detector_sampler(seed=seed)
+    dp, op = b.sample_pinned(shots)
+    assert dp.dtype == np.uint8 and dp.shape == (shots, (D + 7) // 8)
+    np.testing.assert_array_equal(np.unpackbits(dp, axis=1, bitorder="little")[:, :D], want_d)
+    np.testing.assert_array_equal(op & 1, want_o)
+
+
+def test_samplers_of_different_sizes_interleave():
+    """The dynamic shared-memory attribute is per kernel and device, not per sampler (round-1 advisor finding): a small
+    sampler created after a large one must not break the large one's next launch."""
+    big_text = gen_circuit("surface_code", "rotated_memory_z", 5, 5, 0.01)
+    small_text = gen_circuit("repetition_code", "memory", 3, 10, 0.02)
+    big = stim_b200.Circuit(big_text).compile_detector_sampler(seed=5)
+    n_big = 128 * 148 * int(big.stats.max_columns)
+    first = big.sample(n_big, bit_packed=True)
+    small = stim_b200.Circuit(small_text).compile_detector_sampler(seed=6)
+    small.sample(100)
+    big.shot_offset = 0
+    again = big.sample(n_big, bit_packed=True)
+    np.testing.assert_array_equal(first, again)

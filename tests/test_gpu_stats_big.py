@@ -1,0 +1,156 @@
+"""Statistical parity on the full-size BASELINE.json configs (north_star: "per-detector and per-observable flip rates and
+adjacent detector-pair correlations must match the reference within 5 sigma binomial over >= 10^7 shots").
+
+Reference side: tests/golden/stats_big/<name>.npz = counts over 2^24 shots of the unmodified reference
+(tools/gen_stats_big.py: oracle/_ref/stim detect / sample, ptb64 popcounts).
+CUDA side: 2^24 shots reduced on the device by gstim_bit_counts (single + adjacent-pair AND counts of the bit-major
+table), i.e. the noisy headline circuit runs in exactly the launch configuration the bench uses.
+
+Test statistic: two-sample binomial z per bit and per adjacent pair (the two-sample form of
+/root/reference/src/stim/cmd/command_sample.test.cc:59-66). Every |z| must stay below 5; because c5 makes 2.6e5
+comparisons at once (a 5 sigma excursion somewhere is then a 14 % event by chance alone) the bound is widened to the
+family-wise 1 % quantile when that is above 5 (5.9 for c5, 5.4 for c3). The z-scores must also look standard normal as a
+whole (RMS within a few percent of 1), which is the sensitive check against a systematic rate error."""
+import math
+import os
+from statistics import NormalDist
+
+import numpy as np
+import pytest
+
+import stim_b200
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+SDIR = os.path.join(ROOT, "tests", "golden", "stats_big")
+CDIR = os.path.join(ROOT, "tests", "golden", "circuits")
+N_GPU = 1 << 24
+NAMES = ["c3_surface_z_d25_r25", "c4_color_d15_r15", "c4v_color_d15_r15_mpp_dense", "c5_surface_x_d51_r51",
+         "c5f_surface_x_d51_r51_feedback"]
+
+
+def circuit_text(name):
+    if name.startswith("c5f_"):
+        import sys
+
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import gen_variants
+
+        return gen_variants.c5_feedback()
+    with open(os.path.join(CDIR, name + ".stim")) as f:
+        return f.read()
+
+
+def z_scores(k_gpu, n_gpu, k_ref, n_ref):
+    k_gpu, k_ref = np.asarray(k_gpu, dtype=np.float64), np.asarray(k_ref, dtype=np.float64)
+    p = (k_gpu + k_ref) / (n_gpu + n_ref)
+    sigma = np.sqrt(np.maximum(p * (1 - p), 1e-300) * (1.0 / n_gpu + 1.0 / n_ref))
+    z = (k_gpu / n_gpu - k_ref / n_ref) / sigma
+    return np.where(k_gpu + k_ref == 0, 0.0, z)
+
+
+def check(k_gpu, n_gpu, k_ref, n_ref, what):
+    k_gpu, k_ref = np.asarray(k_gpu, dtype=np.int64), np.asarray(k_ref, dtype=np.int64)
+    z = z_scores(k_gpu, n_gpu, k_ref, n_ref)
+    # columns with a handful of events are not Gaussian: bound their count difference directly
+    rare = (k_gpu + k_ref) < 60
+    assert np.all(np.abs(k_gpu[rare] * (n_ref / n_gpu) - k_ref[rare]) <= 40), what + ": rare columns differ"
+    zz = z[~rare]
+    bound = max(5.0, -NormalDist().inv_cdf(0.005 / max(zz.size, 1)))
+    worst = int(np.argmax(np.abs(np.where(rare, 0.0, z))))
+    assert np.all(np.abs(zz) <= bound), (
+        f"{what}: column {worst} deviates {z[worst]:.2f} sigma ({k_gpu[worst]} of {n_gpu} vs {k_ref[worst]} of {n_ref}), bound {bound:.2f}")
+    rms = float(np.sqrt(np.mean(zz**2))) if zz.size else 1.0
+    tol = 0.05 + 4.0 / math.sqrt(2 * max(zz.size, 1))
+    assert abs(rms - 1.0) < tol, f"{what}: z-score RMS {rms:.3f} (expected 1 +- {tol:.3f})"
+    return rms, float(np.abs(zz).max()) if zz.size else 0.0
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_full_size_configs_match_reference_statistics(name):
+    ref = np.load(os.path.join(SDIR, name + ".npz"))
+    mode, n_ref, n_bits = str(ref["mode"]), int(ref["n_ref"]), int(ref["n_bits"])
+    circ = stim_b200.Circuit(circuit_text(name))
+    sampler = circ.compile_detector_sampler(seed=20261017) if mode == "detect" else circ.compile_sampler(seed=20261017)
+    single, pair = sampler.bit_counts(N_GPU)
+    assert single.size == n_bits and pair.size == n_bits - 1
+    r1 = check(single, N_GPU, ref["single"], n_ref, name + " rates")
+    r2 = check(pair, N_GPU, ref["pair"], n_ref, name + " adjacent-pair correlations")
+    print(f"{name}: {n_bits} bits, K={sampler.last_block_columns()}, rates z rms/max {r1[0]:.3f}/{r1[1]:.2f}, "
+          f"pairs z rms/max {r2[0]:.3f}/{r2[1]:.2f}")
+
+
+def test_bit_counts_equal_counts_of_sampled_bits():
+    """gstim_bit_counts (single + pair, both modes) == popcounts of the bits the sampler returns for the same stream."""
+    with open(os.path.join(CDIR, "c2_surface_x_d5_r5.stim")) as f:
+        text = f.read()
+    circ = stim_b200.Circuit(text)
+    shots = 100_000
+    for make, draw in (
+        (lambda: circ.compile_detector_sampler(seed=77), lambda s: s.sample(shots, bit_packed=True, append_observables=True)),
+        (lambda: circ.compile_sampler(seed=78), lambda s: s.sample(shots, bit_packed=True)),
+    ):
+        single, pair = make().bit_counts(shots)
+        bits = np.unpackbits(draw(make()), axis=1, bitorder="little")[:, : single.size]
+        np.testing.assert_array_equal(single.astype(np.int64), bits.sum(axis=0, dtype=np.int64))
+        np.testing.assert_array_equal(pair.astype(np.int64), (bits[:, :-1] & bits[:, 1:]).sum(axis=0, dtype=np.int64))
+
+
+def test_shard_count_invariance_with_pinned_block_columns():
+    """shots shard over GPUs as disjoint ranges of one global shot index space. With the block size pinned
+    (gstim_set_block_columns) the union of the shards IS the single-sampler stream, so flip counts summed over shards
+    (what the NCCL allreduce of bench.py / sharding.allreduce_counts produces) equal the one-sampler counts exactly."""
+    with open(os.path.join(CDIR, "c4_color_d15_r15.stim")) as f:
+        circ = stim_b200.Circuit(f.read())
+    whole = circ.compile_detector_sampler(seed=99)
+    K = 2 * int(whole.stats.lanes_per_item)
+    assert K <= int(whole.stats.max_columns)
+    shard = 64 * K * 128
+    world = 4
+    whole.set_block_columns(K)
+    want_s, want_p = whole.bit_counts(world * shard)
+    got_s = np.zeros_like(want_s)
+    got_p = np.zeros_like(want_p)
+    for rank in range(world):
+        s = circ.compile_detector_sampler(seed=99)
+        s.set_block_columns(K)
+        s.shot_offset = rank * shard
+        a, b = s.bit_counts(shard)
+        got_s += a
+        got_p += b
+    np.testing.assert_array_equal(got_s, want_s)
+    np.testing.assert_array_equal(got_p, want_p)
+    assert want_s.sum() > 0
+    with pytest.raises(ValueError):
+        whole.set_block_columns(int(whole.stats.max_columns) + 1)
+
+
+def test_nccl_allreduce_of_flip_counts_on_two_gpus(tmp_path):
+    """The path's one collective on hardware: 2 ranks, each samples its shard of c4 and the device-resident uint64 counts
+    are summed with NCCL (stim_b200.sharding.allreduce_counts); rank 0 compares with a single-sampler run."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "allreduce.py"
+    script.write_text(f"""
+import os, sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np, torch, torch.distributed as dist
+import stim_b200
+from stim_b200 import sharding
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+circ = stim_b200.Circuit(open({os.path.join(CDIR, "c4_color_d15_r15.stim")!r}).read())
+ok = sharding.check_shard_invariance(circ, seed=5, shots_per_rank=1 << 16, device=rank)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+""")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29511", str(script)], capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]

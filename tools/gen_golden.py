@@ -259,6 +259,12 @@ for code, task, d, r in [("repetition_code", "memory", 3, 4), ("repetition_code"
 detect_case("surface_d5_all_formats", gen("surface_code", "rotated_memory_x", 5, 4, before_measure_flip_probability=1),
             formats=ALL_FORMATS + ("ptb64",), shots=128)
 
+# --- BASELINE.json config 4, MPP variant with deterministic noise (tools/gen_variants.py): b8 and ptb64 bytes -------------
+with open(os.path.join(ROOT, "tests", "golden", "circuits", "c4v_color_d15_r15_mpp_det.stim")) as _f:
+    detect_case("c4v_color_d15_r15_mpp_deterministic", _f.read(),
+                src="generated color_code:memory_xyz d=15 r=15 with the ancilla cycle replaced by MPP (tools/gen_variants.py)",
+                formats=("b8", "ptb64"), shots=128)
+
 # --- random reversible-classical circuits -------------------------------------------------------------------------
 _rng = random.Random(20240601)
 for basis in "ZXY":
@@ -267,6 +273,65 @@ for basis in "ZXY":
 for i in range(3):
     c = classical_circuit(_rng, 8, 80, "Z")
     sample_case(f"classical_sample_{i}", c, formats=("b8", "01"), shots=65)
+
+
+# --- every Clifford gate against the reference (restates frame_simulator.test.cc:58-104 through the CLI) -----------
+# G^60 is the identity for every named Clifford, so "prepare in basis B, apply G 59 times, flip with a probability-1
+# Pauli P, apply G once more, measure in basis B" has deterministic detectors that spell out whether G P G^-1 anticommutes
+# with B on each target: over B in {X, Y, Z} and P in {X, Y, Z} on each target this pins the whole frame action of G.
+CLIFFORD_1Q = ["I", "X", "Y", "Z", "H", "H_XY", "H_YZ", "H_NXY", "H_NXZ", "H_NYZ", "S", "S_DAG", "SQRT_X", "SQRT_X_DAG", "SQRT_Y",
+               "SQRT_Y_DAG", "C_XYZ", "C_ZYX", "C_NXYZ", "C_XNYZ", "C_XYNZ", "C_NZYX", "C_ZNYX", "C_ZYNX"]
+CLIFFORD_2Q = ["CX", "CY", "CZ", "XCX", "XCY", "XCZ", "YCX", "YCY", "YCZ", "SWAP", "ISWAP", "ISWAP_DAG", "CXSWAP", "SWAPCX", "CZSWAP",
+               "SQRT_XX", "SQRT_XX_DAG", "SQRT_YY", "SQRT_YY_DAG", "SQRT_ZZ", "SQRT_ZZ_DAG", "II"]
+SPP_PRODUCTS = ["X0", "Y0", "Z0", "X0*X1", "Z0*Z1", "Y0*Y1", "X0*Z1", "X0*Y1*Z2", "Z0*Y1*X2"]
+
+
+def clifford_probe(apply_line, n_targets):
+    """apply_line(q0) -> instruction text acting on qubits q0 .. q0 + n_targets - 1."""
+    prep = {"Z": ("R", "M"), "X": ("RX", "MX"), "Y": ("RY", "MY")}
+    lines, q = [], 0
+    for basis in "ZXY":
+        for victim in range(n_targets):
+            for pauli in "XYZ":
+                qs = " ".join(str(q + t) for t in range(n_targets))
+                lines.append(f"{prep[basis][0]} {qs}")
+                lines.append("REPEAT 59 {\n    " + apply_line(q) + "\n}")
+                lines.append(f"{pauli}_ERROR(1) {q + victim}")
+                lines.append(apply_line(q))
+                lines.append(f"{prep[basis][1]} {qs}")
+                for t in range(n_targets):
+                    lines.append(f"DETECTOR rec[-{n_targets - t}]")
+                q += n_targets
+    return "\n".join(lines) + "\n"
+
+
+def _reference_knows(line):
+    try:
+        run("detect", "--shots", "1", stdin=line + "\n")
+        return True
+    except RuntimeError:
+        return False
+
+
+if os.path.exists(STIM):
+    for g in CLIFFORD_1Q:
+        if _reference_knows(f"{g} 0"):
+            detect_case(f"clifford_probe_{g}", clifford_probe(lambda q, g=g: f"{g} {q}", 1),
+                        src="src/stim/simulators/frame_simulator.test.cc:58-104 (gate action vs tableau), as CLI probes", shots=5)
+    for g in CLIFFORD_2Q:
+        if _reference_knows(f"{g} 0 1"):
+            detect_case(f"clifford_probe_{g}", clifford_probe(lambda q, g=g: f"{g} {q} {q + 1}", 2),
+                        src="src/stim/simulators/frame_simulator.test.cc:58-104 (gate action vs tableau), as CLI probes", shots=5)
+    for name in ("SPP", "SPP_DAG"):
+        for prod in SPP_PRODUCTS:
+            n = prod.count("*") + 1
+
+            def line(q, prod=prod, name=name):
+                import re as _re
+                return name + " " + _re.sub(r"([XYZ])(\d)", lambda m: m.group(1) + str(q + int(m.group(2))), prod)
+
+            detect_case(f"clifford_probe_{name}_{prod.replace('*', '')}", clifford_probe(line, n),
+                        src="src/stim/simulators/frame_simulator.inl:705-716 + gate_decomposition.cc:163-243, as CLI probes", shots=5)
 
 
 def noiseless(circuit):
