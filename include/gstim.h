@@ -92,14 +92,18 @@ int gstim_reference_sample(const char *circuit_text, size_t text_len, uint8_t *b
 
 /* Host-only lowering (no GPU needed): circuit text -> the uint32 instruction stream the interpreter
  * kernel executes (format: stim_b200/csrc/program.h), with barrier flags computed for `slots`
- * concurrent thread groups and cut into chunks of `chunk_words` words (0 = library default).
- * plan_out receives the 14 uint32 fields of GstimPlan (program.h). Call with words == NULL to get
- * the required length in *n_words. No reference analogue (new subsystem: the lowering). */
+ * concurrent thread groups of 2^lanes_log2 lanes each (a warp executes 32 >> lanes_log2 consecutive items; slots must
+ * be a multiple of that) and cut into chunks of `chunk_words` words (0 = library default). The program
+ * (plan.n_words words) is followed by a copy of the noise schedule: 'NSCH', n_slices, n_rates, n_table_words, the
+ * slice descriptors, rates and PAULI_CHANNEL_2 tables. plan_out receives the 16 uint32 fields of GstimPlan
+ * (program.h). Call with words == NULL to get the required length in *n_words. No reference analogue (new
+ * subsystem: the lowering). */
 int gstim_lower_text(
     const char *circuit_text,
     size_t text_len,
     int mode,
     uint32_t slots,
+    uint32_t lanes_log2,
     uint32_t chunk_words,
     uint32_t *words,
     size_t *n_words,

@@ -5,8 +5,9 @@ numpy restatement of the two random primitives the device noise generator is spe
 
   * Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
     Pinned against the Random123 known-answer vectors in tests/test_oracle_philox.py.
-  * exp_draw: Exp(1) variate from a uniform u32 using only IEEE-754 double + - * / in a fixed order,
-    so the CUDA kernel (stim_b200/csrc/kernels.cu: exp_draw) reproduces it bit for bit.
+  * exp_draw_q26 / gap_of: Exp(1) variate from a uniform u32 and the geometric gap it gives, integer arithmetic only,
+    so the CUDA kernel (stim_b200/csrc/interp.cu) reproduces them bit for bit. (exp_draw is the round-1 double
+    precision form, kept as the accuracy reference for tests/test_oracle_philox.py.)
 
 These replace, in distribution, the reference's std::mt19937_64 + std::geometric_distribution
 (/root/reference/src/stim/util_bot/probability_util.cc:23-43): floor(Exp(1)/lambda) with
@@ -73,35 +74,40 @@ def exp_draw(r):
 
 
 # ---------------------------------------------------------------------------------------------
-# Fixed-point exponential clock (spec v2, DESIGN.md "RNG addressing"): all integer arithmetic, so the
-# device (stim_b200/csrc/kernels.cu: exp_draw_fx) and this oracle agree bit for bit by construction.
-# Unit = 2**-56 nat.
+# Gap arithmetic, spec v6 (stim_b200/csrc/program.h "Gap arithmetic"): all integer, so the device
+# (stim_b200/csrc/interp.cu: exp_draw_q26 / the producer loop) and this oracle agree bit for bit by construction.
 # ---------------------------------------------------------------------------------------------
-from .log2_table import LN2_Q24, LOG2_T  # noqa: E402
-
-FX_SHIFT = 56
-LAM_MAX = 1 << 62
-REM_SAT = 1 << 63
+from .log2_table import LN2_Q32, LOG2_T26  # noqa: E402
 
 
-def exp_draw_fx(r: int) -> int:
-    """-ln((r + 1/2) / 2**32) in units of 2**-56, via a 256-entry log2 table with linear interpolation."""
-    v = 2 * int(r) + 1
+def exp_draw_q26(r: int) -> int:
+    """-ln(v / 2**32), v = r | 1, in units of 2**-26 nat: 256-entry log2 table (Q26), 13-bit linear interpolation,
+    multiply-high by ln 2 (Q32)."""
+    v = int(r) | 1
     t = v.bit_length() - 1
-    vn = v << (32 - t)
-    frac = vn & 0xFFFFFFFF
-    i, f = frac >> 24, frac & 0xFFFFFF
-    log2m = LOG2_T[i] + (((LOG2_T[i + 1] - LOG2_T[i]) * f) >> 24)
-    return ((33 << 32) - ((t << 32) + log2m)) * LN2_Q24
+    frac = (v << (32 - t)) & 0xFFFFFFFF  # bits below the leading one, left aligned
+    i, f = frac >> 24, (frac >> 11) & 0x1FFF
+    log2v = (t << 26) + LOG2_T26[i] + (((LOG2_T26[i + 1] - LOG2_T26[i]) * f) >> 13)
+    return (((1 << 31) - log2v) * LN2_Q32) >> 32
 
 
-def lam_fx(p: float) -> int:
-    """Per-shot event rate of probability p (narrowed to float32 like the reference) in clock units."""
+def rate_of(p: float):
+    """Probability (narrowed to float32 like the reference) -> (INV, SH) of the gap arithmetic, or None if it never fires."""
     import math
 
     f = float(np.float32(p))
     if not f > 0:
-        return 0
+        return None
     if f >= 1:
-        return LAM_MAX
-    return min(int(math.ldexp(-math.log1p(-f), FX_SHIFT)), LAM_MAX)
+        return (0, 0)
+    lam = -math.log1p(-f)
+    m, e = math.frexp(1.0 / lam)
+    sh = 58 - e
+    if sh < 0:
+        return None
+    return (int(math.floor(math.ldexp(m, 32))), sh)
+
+
+def gap_of(gap_word: int, rate) -> int:
+    """floor(Exp(1) / lambda) in the fixed-point arithmetic of the device."""
+    return (exp_draw_q26(gap_word) * rate[0]) >> rate[1]

@@ -58,7 +58,7 @@ _SIGNATURES = [
     ("gstim_circuit_stats", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(GstimStats)]),
     ("gstim_reference_sample", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, _P, ctypes.c_size_t]),
     ("gstim_lower_text", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
-                                        _P, ctypes.POINTER(ctypes.c_size_t), _P]),
+                                        ctypes.c_uint32, _P, ctypes.POINTER(ctypes.c_size_t), _P]),
     ("gstim_create_from_text", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, ctypes.c_int,
                                               ctypes.POINTER(_P)]),
     ("gstim_destroy", None, [_P]),
