@@ -475,6 +475,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
         p.ev_overflow = (uint32_t *)s->d_ev_overflow.p;
         p.dbg_cycles = nullptr;
         p.dbg_flags = env_u32("GSTIM_DEBUG_FLAGS", 0);
+        p.phased = env_u32("GSTIM_PHASED", 0);  // (measured on c3: overlapped producers 30.1 ms, phased 33.1 ms per 2^22 shots)
         if (env_u32("GSTIM_DEBUG_CYCLES", 0)) {
             s->d_dbg.ensure(64 * 8);
             CK(cudaMemsetAsync(s->d_dbg.p, 0, 64 * 8, s->stream));

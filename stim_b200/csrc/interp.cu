@@ -737,7 +737,7 @@ __device__ __forceinline__ void measure_items(const BlockCtx *bc, const SmemWord
         uint32_t ax = X_s + q * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += kinc, ax += kstep, rrow += (uint64_t)kinc * rks, orec += (uint64_t)kinc * rks, drow += (uint64_t)kinc * oks) {
             uint4 prev = make_uint4(0, 0, 0, 0);
-            if (det != 0xFFFFFFFFu) {
+            if (det != 0xFFFFFFFFu && !(bc->dbg_flags & 2u)) {  // (flag 2: timing experiment without the previous round's row)
                 prev = ldg128(orec);  // (issued before the Philox chain so the L2 latency hides behind it)
             }
             uint32_t c2 = col_lo + k, c3 = tag_hi;
@@ -1091,7 +1091,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     }
     __syncthreads();
 
-    const bool has_producers = T_all > T;
+    // Two ways to get a shot block's noise events (p.phased):
+    //   overlapped (default): the last warps of the block are dedicated producers that sample block r + 1 while block r is
+    //     interpreted (double-buffered events, FULL / FREE hand-over barriers);
+    //   phased: at the start of every shot block ALL warps of the block sample its events together, then the interpreter
+    //     warps run (no overlap, but 24 warps hide the latency of the dependent Philox / gap chains better than 4).
+    // c3, per 2^22 shots: overlapped 30.1 ms, phased 33.1 ms (profiles/r2_notes.md).
+    const bool phased = p.phased != 0;
+    const bool has_producers = T_all > T && !phased;
     if (has_producers) {
         // The first shot block's noise is sampled by the whole block (24 warps instead of 4): the interpreter would
         // only wait for it anyway. From the second block on the producer warps run ahead on their own.
@@ -1106,7 +1113,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         noise_prepass(bc, run);
         __syncthreads();
     }
-    if (tid >= T) {
+    if (tid >= T && !phased) {
         producer_role(bc);
         return;
     }
@@ -1125,7 +1132,21 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
 #endif
 
     for (uint32_t g = blockIdx.x; g < p.n_blocks; g += gridDim.x, run_idx++) {
-        const uint32_t eb = run_idx & 1u;
+        const uint32_t eb = phased ? 0u : (run_idx & 1u);
+        if (phased && p.n_slices != 0) {
+            const uint64_t col0 = p.col0_base + (uint64_t)g * p.K;
+            PrepassRun run;
+            run.col0_lo = (uint32_t)col0;
+            run.col0_hi = (uint32_t)(col0 >> 32);
+            run.evbuf = p.ev_buf + (size_t)blockIdx.x * 2 * p.ev_total;
+            run.tid = tid;
+            run.threads = T_all;
+            run.whole_block = 1;
+            noise_prepass(bc, run);  // (starts and ends with a barrier of the whole block)
+        }
+        if (tid >= T) {
+            continue;  // helper warps only take part in the sampling phase
+        }
         if (tid == 0) {
             const uint64_t col0 = p.col0_base + (uint64_t)g * p.K;
             bc->col0_lo = (uint32_t)col0;

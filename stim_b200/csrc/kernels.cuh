@@ -27,6 +27,7 @@ struct InterpParams {
     uint32_t rec_mask;         // ring mask (detector mode) or 0xFFFFFFFF
     uint4 *out;                // detector/observable table, column-major: out[column * out_k_stride + row]; block g owns columns [g*K,(g+1)*K)
     uint64_t out_k_stride;     // uint4 units between columns (= number of rows)
+    uint32_t phased;           // 1: every shot block starts with all warps sampling its noise events; 0: dedicated producer warps run one block ahead
     uint32_t dbg_flags;        // GSTIM_DEBUG_FLAGS: timing experiments only (results become wrong): bit0 no noise events, bits 8+op skip opcode
     unsigned long long *dbg_cycles;  // optional (GSTIM_DEBUG_CYCLES=1): [op] cycles and [16+op] batch counts seen by block 0
     // noise schedule (program.h) and the per-CTA event buffers the producer warps fill
