@@ -8,9 +8,15 @@ code memory-Z circuit (BASELINE.json configs[2], fixture tests/golden/circuits/c
 producing bit-packed (b8) detection events + observables.
 
   value  device-resident throughput: results land in a preallocated HBM buffer (no PCIe in the timed region)
-  e2e    same metric through the public API with (pinned) HOST output buffers, D2H inside the timed region
+  e2e    same metric through the public API with HOST output buffers, D2H inside the timed region: the headline number is
+         the page-locked caller buffer (direct DMA); the default pageable numpy path (sample(bit_packed=True)) and the
+         bare D2H copy ceiling of the same bytes are reported beside it
   --impl reference   the unmodified reference CLI (oracle/_ref/stim detect, built from /root/reference by
-                     oracle/Makefile) timed on the host cores, one process per core.
+                     oracle/Makefile) timed on the host cores, one process per core, 2^17 shots per process and step.
+
+On N > 1 GPUs every rank samples its own shot range (no data-path collective); after the timed region the path's one
+collective is exercised on hardware: per-detector flip counts of BASELINE config 4 are summed with NCCL and compared with a
+single-sampler run of the same global shot range (stim_b200.sharding.check_shard_invariance).
 """
 import argparse
 import json
@@ -34,13 +40,16 @@ C4_CIRCUIT = os.path.join(ROOT, "tests", "golden", "circuits", "c4_color_d15_r15
 
 
 def measured_traffic_bytes_per_shot():
-    """DRAM bytes per shot of the interpreter kernel from the committed `ncu --set full` capture (profiles/r1_interp_full.json)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_interp_full.json")) as f:
-            d = json.load(f)
-        return (float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])) / float(d["shots"])
-    except Exception:
-        return None
+    """DRAM bytes per shot of the interpreter kernel from the committed `ncu --set full` capture (profiles/r2_interp_full.json,
+    else the round-1 one). Returns (bytes per shot, file name)."""
+    for name in ("r2_interp_full.json", "r1_interp_full.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            return (float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])) / float(d["shots"]), name
+        except Exception:
+            continue
+    return None, None
 
 
 def bind_to_gpu_numa_node(torch, index):
@@ -169,7 +178,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shots-log2", type=int, default=24)
-    ap.add_argument("--e2e-shots-log2", type=int, default=22)
+    ap.add_argument("--e2e-shots-log2", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -249,9 +259,9 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- end-to-end arm (host buffers, D2H inside the timed region) ----------------------------------
-    # (per rank: 2^22 shots = 8.2 GB of pinned memory; shrink if the host cannot pin that much - every rank must use the
-    # same size, so the decision is taken together)
-    e2e_log2 = args.e2e_shots_log2
+    # Headline: the caller's page-locked buffer at the same 2^24 shots per step when the host can pin 32.7 GB per rank
+    # (else the largest power of two it can; every rank uses the same size, so the decision is taken together).
+    e2e_log2 = min(args.e2e_shots_log2, args.shots_log2)
     host = None
     while host is None:
         try:
@@ -272,22 +282,59 @@ def main():
     e2e_shots = 1 << e2e_log2
     host_np = host.numpy()
     sampler.sample(e2e_shots, bit_packed=True, append_observables=True, dets_out=host_np)  # warm-up (allocations)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
         sampler.sample(e2e_shots, bit_packed=True, append_observables=True, dets_out=host_np)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * e2e_shots * e2e_steps / e2e_s
+    # the bare D2H copy of the same bytes into the same buffer: the ceiling the end-to-end number can reach
+    dev_src = torch.empty((min(e2e_shots, 1 << 22), nbytes), dtype=torch.uint8, device="cuda")
+    n_cp = dev_src.shape[0]
+    host[:n_cp].copy_(dev_src, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        host[:n_cp].copy_(dev_src, non_blocking=True)
+    barrier()
+    d2h_s = max_over_ranks(time.perf_counter() - t0)
+    d2h_gbs = world * 3 * n_cp * nbytes / d2h_s / 1e9
+    del dev_src
+    # the default API path: sample(bit_packed=True) returns a fresh pageable numpy array (pinned staging + threaded copy)
+    page_shots = min(e2e_shots, 1 << 22)
+    sampler.sample(page_shots, bit_packed=True, append_observables=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        sampler.sample(page_shots, bit_packed=True, append_observables=True)
+    barrier()
+    page_s = max_over_ranks(time.perf_counter() - t0)
+    page_value = world * page_shots * 2 / page_s
     del host, host_np
 
+    # ---- the path's one collective, on hardware (N > 1): NCCL sum of per-detector flip counts, shard invariance --------
+    collective = None
+    if dist is not None:
+        from stim_b200 import sharding
+
+        with open(C4_CIRCUIT) as f:
+            c4 = stim_b200.Circuit(f.read())
+        ok = sharding.check_shard_invariance(c4, seed=2026, shots_per_rank=1 << 18, device=local_rank)
+        collective = {"op": "all_reduce(SUM) of uint64[D+L] flip counts and adjacent-pair counts, NCCL", "ranks": world,
+                      "circuit": "tests/golden/circuits/c4_color_d15_r15.stim", "shots_per_rank": 1 << 18,
+                      "sum_over_ranks_equals_single_sampler": bool(ok)}
+
+    lop3 = stim_b200.measure_lop3_peak(local_rank)
+
     peak, peak_src = measured_peak_gbs()
-    traffic_per_shot = measured_traffic_bytes_per_shot()
+    traffic_per_shot, traffic_file = measured_traffic_bytes_per_shot()
     interp_s = interp_ms * 1e-3
     achieved = ALG_BYTES_PER_SHOT * shots * args.steps / interp_s / 1e9
     sm_mhz = clk.get("sm_mhz") or 1965.0
-    lop3_peak = 148 * LOP3_LANES_PER_CLK_PER_SM * sm_mhz * 1e6
+    lanes = lop3["lane_ops_per_clk_per_sm"] or LOP3_LANES_PER_CLK_PER_SM
+    lop3_peak = 148 * lanes * sm_mhz * 1e6
     per_gpu_rate_interp = shots * args.steps / interp_s
     line = {
         "metric": METRIC, "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -306,19 +353,29 @@ def main():
         "clocks": clk,
         "e2e": {
             "value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": e2e_shots * nbytes,
-            "shots_per_step": e2e_shots, "steps": e2e_steps, "host_buffer": "pinned", "numa_node": numa,
+            "shots_per_step": e2e_shots, "steps": e2e_steps, "host_buffer": "pinned (caller's page-locked array, direct DMA)",
+            "numa_node": numa, "result_gbs": e2e_value * nbytes / 1e9,
+            "d2h_copy_ceiling_gbs": d2h_gbs,
+            "d2h_copy_ceiling_note": "bare cudaMemcpyAsync of the same bytes into the same pinned buffer on every rank at once: "
+                                     "what PCIe / host DRAM allow with no sampling at all",
+            "pageable": {"value": page_value, "unit": "shots/s", "shots_per_step": page_shots,
+                         "note": "default sample(bit_packed=True): fresh pageable numpy array (pinned staging + threaded copy)"},
         },
+        "collective": collective,
         "roofline": {
             "kernel": "gstim_interp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak,
             "traffic": (None if traffic_per_shot is None else traffic_per_shot * shots * args.steps / interp_launches),
-            "traffic_source": "dram__bytes_read+write of profiles/r1_interp_full.json scaled to the shots of one launch",
+            "traffic_source": f"dram__bytes_read+write of profiles/{traffic_file} scaled to the shots of one launch",
             "peak_source": peak_src,
             "launches": interp_launches, "avg_launch_ms": interp_ms / interp_launches,
             "alg_bytes_per_launch": ALG_BYTES_PER_SHOT * shots * args.steps / interp_launches,
             "alu_bound": {"lop3_per_shot": ALG_LOP3_PER_SHOT, "achieved_lop3_per_s": per_gpu_rate_interp * ALG_LOP3_PER_SHOT,
                           "peak_lop3_per_s": lop3_peak, "frac": per_gpu_rate_interp * ALG_LOP3_PER_SHOT / lop3_peak,
-                          "peak_basis": f"148 SMs x {LOP3_LANES_PER_CLK_PER_SM} lanes/clk x {sm_mhz:.0f} MHz (sampled)"},
+                          "peak_basis": f"measured: LOP3 microbenchmark in this run = {lanes:.2f} lanes/clk/SM "
+                                        f"({lop3['lane_ops_per_sec'] / 1e12:.2f} T lane-ops/s at {lop3['sm_mhz']:.0f} MHz) x 148 SMs x "
+                                        f"{sm_mhz:.0f} MHz sampled during the timed region",
+                          "lop3_probe": lop3},
         },
     }
 

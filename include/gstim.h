@@ -209,6 +209,28 @@ int gstim_detector_flip_counts(gstim_sampler *s, uint64_t shots, uint64_t *count
  * sinter's collection loop reduces shots to (glue/sample/src/sinter/_decoding/_stim_then_decode_sampler.py:162-185). */
 int gstim_bit_counts(gstim_sampler *s, uint64_t shots, uint64_t *single_host, uint64_t *pair_host, void *single_dev, void *pair_dev);
 
+/* ---- detector error model sampling --------------------------------------------------------
+ * Replaces: DemSampler<W>::resample / sample_write          src/stim/simulators/dem_sampler.inl:52-130
+ *           stim sample_dem                                  src/stim/cmd/command_sample_dem.cc:25-93
+ *           stim.CompiledDemSampler.sample / sample_write    src/stim/simulators/dem_sampler.pybind.cc
+ * dem_text is a detector error model in Stim's .dem format (error / detector / logical_observable / shift_detectors /
+ * repeat). Every `error(p)` is an independent Bernoulli(p) row XORed into its targets' rows; parse errors are
+ * GSTIM_ERR_INVALID_ARGUMENT. Successive calls continue the random stream. */
+typedef struct gstim_dem_sampler gstim_dem_sampler;
+int gstim_dem_counts(const char *dem_text, size_t text_len, uint64_t *num_detectors, uint64_t *num_observables, uint64_t *num_errors);
+int gstim_dem_create_from_text(const char *dem_text, size_t text_len, uint64_t seed, int device, gstim_dem_sampler **out);
+void gstim_dem_destroy(gstim_dem_sampler *s);
+int gstim_dem_set_shot_offset(gstim_dem_sampler *s, uint64_t offset);
+/* Host outputs, shot-major: dets [shots, D], obs [shots, L], errs [shots, E] (any may be NULL), one byte per bit or
+ * bit-packed little-endian with GSTIM_BIT_PACKED; strides in bytes (0 = dense). errs = which error mechanisms fired
+ * (the reference's return_errors / --err_out). Replaying recorded errors (--replay_err_in) is not supported. */
+int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void *dets_out, int64_t dets_stride, void *obs_out,
+                     int64_t obs_stride, void *errs_out, int64_t errs_stride);
+/* Streams to files in any result format; a negative fd skips that output. The outputs of one chunk are written in the
+ * reference's order (errors, observables, detectors). */
+int gstim_dem_sample_to_fd(gstim_dem_sampler *s, uint64_t shots, int det_fd, const char *det_format, int obs_fd, const char *obs_format,
+                           int err_fd, const char *err_format);
+
 /* Pins the number of 128-shot columns per thread block (0 = choose per call from the shot count, the default). The
  * random stream is a function of (seed, shot offset, columns per block): callers that split one global shot range over
  * several handles / GPUs and need the union to equal a single-handle run pin the same value everywhere and keep every

@@ -91,21 +91,32 @@ def exp_draw_q26(r: int) -> int:
     return (((1 << 31) - log2v) * LN2_Q32) >> 32
 
 
+def slice_width_log2(f: float) -> int:
+    """log2 of the sites per RNG slice for probability f (program.h gstim_slice_width_log2): 5 below 2**-6, one less for
+    every doubling, 0 from 1/4."""
+    w, t = 5, 1.0 / 64
+    while w > 0 and f >= t:
+        w -= 1
+        t *= 2
+    return w
+
+
 def rate_of(p: float):
-    """Probability (narrowed to float32 like the reference) -> (INV, SH) of the gap arithmetic, or None if it never fires."""
+    """Probability (narrowed to float32 like the reference) -> (INV, SH, slice width log2) of the gap arithmetic, or None
+    if it never fires."""
     import math
 
     f = float(np.float32(p))
     if not f > 0:
         return None
     if f >= 1:
-        return (0, 0)
+        return (0, 0, 0)
     lam = -math.log1p(-f)
     m, e = math.frexp(1.0 / lam)
     sh = 58 - e
     if sh < 0:
         return None
-    return (int(math.floor(math.ldexp(m, 32))), sh)
+    return (int(math.floor(math.ldexp(m, 32))), sh, slice_width_log2(f))
 
 
 def gap_of(gap_word: int, rate) -> int:

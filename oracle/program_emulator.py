@@ -21,7 +21,7 @@ HDR = 12
 (OP_END, OP_NEXT, OP_CLIFF1, OP_CLIFF2, OP_NOISE1, OP_NOISE2, OP_MEASURE, OP_RECZERO, OP_XORROWS, OP_OBS_PAULI,
  OP_FEEDBACK, OP_CORR, OP_QMAP) = range(13)
 F_BARRIER, F_REC, F_ACCUM, F_RESET, F_TABLE, F_NOFRAME, F_DET = 1, 2, 4, 8, 16, 32, 64
-(GH_OP, GH_N, GH_WORDS, GH_EXTRA, GH_CSITE0, GH_REC0, GH_PRE, GH_PRE_NEXT, GH_POST, GH_POST_NEXT, GH_PERM, GH_SPARE) = range(12)
+(GH_OP, GH_N, GH_WORDS, GH_EXTRA, GH_CSITE0, GH_REC0, GH_PRE, GH_PRE_NEXT, GH_POST, GH_POST_NEXT, GH_PERM, GH_WIDTHS) = range(12)
 NO_NOISE = 0xFFFFFFFF
 SLICE_WORDS = 8
 
@@ -93,7 +93,10 @@ class Emulator:
         self.slices, self.rates, self.tables = read_schedule(self.w, plan)
         self.group_slices = {}  # noise group -> slices of it seen so far (must arrive in order, without gaps)
         self.n_applications = 0
-        self.expect_next = 0 if self.slices else NO_NOISE  # first slice the chain promises for the next application
+        # what the chain promises for the next application: its first slice | log2(slices per 32 items) << 28
+        self.expect_next = NO_NOISE
+        if self.slices:
+            self.expect_next = None  # (the first application's width is not promised by anyone: the kernel stages slice 0)
         # race detector state: resource -> (warp that wrote, set of warps that read) since the last barrier
         self.writer = {}
         self.readers = {}
@@ -134,24 +137,29 @@ class Emulator:
     def flip(self, arr, shot):
         arr[shot >> 5] ^= np.uint32(1 << (shot & 31))
 
-    def apply_noise(self, att, nxt, n, item_of, rec0, corr=None):
+    def apply_noise(self, att, nxt, n, item_of, rec0, w, corr=None):
         """One noise application: walks its ceil(n / 32) slices exactly like the kernel's producers and applies every event
         to the item it hits. item_of(it) = (row1, row2) of item `it` (noise target order); corr: E / ELSE handler."""
         assert att != NO_NOISE
         slice0, parity = att & 0x7FFFFFFF, att >> 31
         assert parity == self.n_applications & 1, "noise application parity out of step"
-        assert slice0 == self.expect_next, "noise chain broken: the previous application promised another slice"
+        if self.expect_next is None:
+            assert slice0 == 0
+        else:
+            assert slice0 | ((5 - w) << 28) == self.expect_next, "noise chain broken: the previous application promised another slice"
         self.n_applications += 1
         self.expect_next = nxt
+        S = 1 << w
         B = self.B
         c2, hi = self.col0 & 0xFFFFFFFF, self.col0 >> 32
-        for sl_rel in range((n + 31) // 32):
+        for sl_rel in range((n + S - 1) // S):
             group, j, rs, h0, t1, t2, t3, _ = self.slices[slice0 + sl_rel]
             assert self.group_slices.get(group, 0) == j, "slices of a noise group out of order"
             self.group_slices[group] = j + 1
             rate = self.rates[rs & 0xFFFF]
             sites = rs >> 16
-            assert sites == min(32, n - 32 * sl_rel)
+            assert sites == min(S, n - S * sl_rel)
+            assert abs(w - px.slice_width_log2(self._prob_of(rate))) <= 1  # (exact up to the rounding of INV at a boundary)
             op, flags, aux = h0 & 0xFF, (h0 >> 8) & 0xFF, h0 >> 16
             total = sites * B
             a = d = 0
@@ -165,7 +173,7 @@ class Emulator:
                 if G >= total - a:
                     break
                 a += G
-                it, shot = 32 * sl_rel + a // B, a % B
+                it, shot = S * sl_rel + a // B, a % B
                 a += 1
                 if corr is not None:
                     corr(shot)
@@ -194,6 +202,15 @@ class Emulator:
                 for on, arr in zip(f, (self.x[q1], self.z[q1], self.x[q2], self.z[q2])):
                     if on:
                         self.flip(arr, shot)
+
+    @staticmethod
+    def _prob_of(rate):
+        """probability back from (INV, SH): 1 / lambda = INV * 2^(26 - SH)."""
+        import math
+
+        if rate[0] == 0:
+            return 1.0  # p >= 1: INV = 0
+        return -math.expm1(-1.0 / (rate[0] * 2.0 ** (26 - rate[1])))
 
     def noise_flags(self, att):
         """flags of the noise of application att (from its first slice)."""
@@ -229,6 +246,7 @@ class Emulator:
             pre, pre_next = int(w[pc + GH_PRE]), int(w[pc + GH_PRE_NEXT])
             post, post_next = int(w[pc + GH_POST]), int(w[pc + GH_POST_NEXT])
             perm_off = int(w[pc + GH_PERM])
+            w_pre, w_post = int(w[pc + GH_WIDTHS]) & 15, (int(w[pc + GH_WIDTHS]) >> 4) & 15
             pay = w[pc + HDR: pc + words]
             perm = None
             if perm_off:
@@ -252,7 +270,7 @@ class Emulator:
                     self.x[q] = (x & np.uint32(a)) ^ (z & np.uint32(b))
                     self.z[q] = (x & np.uint32(c)) ^ (z & np.uint32(d))
                 if post != NO_NOISE:
-                    self.apply_noise(post, post_next, n, lambda it: (int(pay[pos_of(it)]), 0), rec0)
+                    self.apply_noise(post, post_next, n, lambda it: (int(pay[pos_of(it)]), 0), rec0, w_post)
             elif op == OP_CLIFF2:
                 m = [np.uint32(0xFFFFFFFF if (aux >> i) & 1 else 0) for i in range(16)]
                 for i in range(n):
@@ -263,7 +281,7 @@ class Emulator:
                     o = [(v[0] & m[4 * k]) ^ (v[1] & m[4 * k + 1]) ^ (v[2] & m[4 * k + 2]) ^ (v[3] & m[4 * k + 3]) for k in range(4)]
                     self.x[q1], self.z[q1], self.x[q2], self.z[q2] = o
                 if post != NO_NOISE:
-                    self.apply_noise(post, post_next, n, lambda it: (int(pay[pos_of(it)]) & 0xFFFF, int(pay[pos_of(it)]) >> 16), rec0)
+                    self.apply_noise(post, post_next, n, lambda it: (int(pay[pos_of(it)]) & 0xFFFF, int(pay[pos_of(it)]) >> 16), rec0, w_post)
             elif op == OP_NOISE1:
                 for i in range(n):
                     if not flags & F_NOFRAME:
@@ -272,20 +290,20 @@ class Emulator:
                         self.touch(S(i), (R_REC, (rec0 + i) & self.rec_mask), True)
                 if post != NO_NOISE:
                     assert flags & ~F_BARRIER == self.noise_flags(post)
-                    self.apply_noise(post, post_next, n, lambda it: (int(pay[it]) & 0xFFFF, 0), rec0)
+                    self.apply_noise(post, post_next, n, lambda it: (int(pay[it]) & 0xFFFF, 0), rec0, w_post)
             elif op == OP_NOISE2:
                 for i in range(n):
                     self.touch(S(i), int(pay[i]) & 0xFFFF, True)
                     self.touch(S(i), int(pay[i]) >> 16, True)
                 if post != NO_NOISE:
-                    self.apply_noise(post, post_next, n, lambda it: (int(pay[it]) & 0xFFFF, int(pay[it]) >> 16), rec0)
+                    self.apply_noise(post, post_next, n, lambda it: (int(pay[it]) & 0xFFFF, int(pay[it]) >> 16), rec0, w_post)
             elif op == OP_MEASURE:
                 basis, kind = aux & 3, (aux >> 2) & 3
                 stride = 3 if flags & F_DET else 1  # fused detectors: (qubit word, detector row or NONE, record slot)
                 item = lambda it: (int(pay[stride * it]) & 0xFFFF, 0)  # noqa: E731
                 if pre != NO_NOISE:
                     assert not self.noise_flags(pre) & F_REC
-                    self.apply_noise(pre, pre_next, n, item, rec0)
+                    self.apply_noise(pre, pre_next, n, item, rec0, w_pre)
                 for i in range(n):
                     q = int(pay[stride * i]) & 0xFFFF
                     assert int(pay[stride * i]) >> 16 == self.logical_of[q]
@@ -311,7 +329,7 @@ class Emulator:
                             self.out[d] = m ^ self.rec[other]
                 if post != NO_NOISE:
                     assert kind != 2 or not self.noise_flags(post) & F_REC
-                    self.apply_noise(post, post_next, n, item, rec0)
+                    self.apply_noise(post, post_next, n, item, rec0, w_post)
             elif op == OP_RECZERO:
                 for i in range(n):
                     self.touch(S(i), (R_REC, (rec0 + i) & self.rec_mask), True)
@@ -368,7 +386,7 @@ class Emulator:
                                 self.flip(self.z[q], shot)
 
                 if post != NO_NOISE:
-                    self.apply_noise(post, post_next, 1, None, rec0, corr=lambda shot: ev(shot, None))
+                    self.apply_noise(post, post_next, 1, None, rec0, w_post, corr=lambda shot: ev(shot, None))
             else:
                 raise ValueError(f"bad opcode {op} at word {pc}")
             pc += words

@@ -78,6 +78,14 @@ _SIGNATURES = [
                                                ctypes.c_char_p, ctypes.c_char, ctypes.c_char, ctypes.c_uint64]),
     ("gstim_detector_flip_counts", ctypes.c_int, [_P, ctypes.c_uint64, _P, _P]),
     ("gstim_bit_counts", ctypes.c_int, [_P, ctypes.c_uint64, _P, _P, _P, _P]),
+    ("gstim_dem_counts", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
+                                        ctypes.POINTER(ctypes.c_uint64)]),
+    ("gstim_dem_create_from_text", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(_P)]),
+    ("gstim_dem_destroy", None, [_P]),
+    ("gstim_dem_set_shot_offset", ctypes.c_int, [_P, ctypes.c_uint64]),
+    ("gstim_dem_sample", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_uint32, _P, ctypes.c_int64, _P, ctypes.c_int64, _P, ctypes.c_int64]),
+    ("gstim_dem_sample_to_fd", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p,
+                                              ctypes.c_int, ctypes.c_char_p]),
     ("gstim_set_block_columns", ctypes.c_int, [_P, ctypes.c_uint32]),
     ("gstim_measure_lop3_peak", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                                ctypes.POINTER(ctypes.c_double)]),

@@ -468,6 +468,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
         p.rates = (const uint2 *)s->d_rates.p;
         p.slices = (const uint4 *)s->d_slices.p;
         p.n_slices = n_slices;
+        p.first_lpg = n_slices ? 5 - gstim_slice_width_log2(s->lc.noise.slice_prob[0]) : 0;
         p.tables = (const uint32_t *)s->d_tables.p;
         p.ev_ovf_off = (const uint32_t *)s->d_ovf_off.p;
         p.ev_total = s->ev_total;
@@ -888,6 +889,11 @@ void sample_to_file(
 }
 
 }  // namespace
+
+// (used by dem.cu: one error channel for the whole library)
+void gstim_set_last_error(const char *msg) {
+    g_last_error = msg ? msg : "";
+}
 
 // =================================================================================================
 // C ABI

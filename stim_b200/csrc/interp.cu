@@ -523,14 +523,15 @@ __device__ __forceinline__ void noise_chain_step(const BlockCtx *bc, uint32_t at
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (next != GSTIM_NO_NOISE) {
-        stage_line(bc, next + (warp_first_item(bc) >> 5), (att >> 31) ^ 1u);
+        // (first slice of the 32-item group this warp's first items belong to: next = first slice | log2(slices per group) << 28)
+        stage_line(bc, (next & 0x0FFFFFFFu) + ((warp_first_item(bc) >> 5) << (next >> 28)), (att >> 31) ^ 1u);
     }
 }
 
-// Applies the events of application `att` to the n items at items_s (stride words per item; word = row1 | row2 << 16),
-// perm_s: byte table site -> position inside the 32-item group (0: identity), rec0: record row of item 0.
+// Applies the events of application `att` (slices of 2^w sites) to the n items at items_s (stride words per item; word =
+// row1 | row2 << 16), perm_s: byte table site -> position inside the 32-item group (0: identity), rec0: record row of item 0.
 __device__ __forceinline__ void noise_apply(const BlockCtx *bc, uint32_t att, uint32_t next, uint32_t n, uint32_t items_s, uint32_t stride,
-                                            uint32_t perm_s, uint32_t rec0) {
+                                            uint32_t perm_s, uint32_t rec0, uint32_t w) {
     noise_chain_step(bc, att, next);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ipw_log2 = 5 - bc->G_log2, ipw = 1u << ipw_log2;
@@ -538,10 +539,16 @@ __device__ __forceinline__ void noise_apply(const BlockCtx *bc, uint32_t att, ui
     const uint32_t st = bc->stage_s + ((threadIdx.x >> 5) * 2 + (att >> 31)) * (GSTIM_EV_LINE_WORDS * 4);
     const uint32_t X_s = bc->X_s, zoff = bc->Z_s - bc->X_s, pitch_b = bc->pitch_b, slots = bc->slots;
     uint32_t trip = 0;
+    const uint32_t lpg = 5 - w;  // log2(slices per group of 32 items)
     for (uint32_t base = warp_first_item(bc); base < n; base += slots, trip++) {
-        const uint32_t sl_rel = base >> 5, sub_lo = base & 31u;
+      const uint32_t grp = base >> 5, sub_lo = base & 31u;
+      // the slices that can hold events for this warp's positions base .. base + ipw - 1: those of its own item indices, or
+      // (when a permutation maps sites to positions) every slice of the 32-item group
+      const uint32_t j_lo = perm_s ? 0u : (sub_lo >> w), j_hi = perm_s ? ((32u >> w) - 1) : ((sub_lo + ipw - 1) >> w);
+      for (uint32_t j = j_lo; j <= j_hi && grp * 32 + (j << w) < n; j++) {
+        const uint32_t sl_rel = (grp << lpg) + j, it0 = grp * 32 + (j << w);
         const uint32_t *line = bc->ev_buf + (size_t)GSTIM_EV_LINE_WORDS * (slice0 + sl_rel);
-        const bool staged = trip == 0;
+        const bool staged = trip == 0 && j == 0;  // (the chain staged the first slice of the warp's group)
         const uint32_t cnt = staged ? lds32(st) : ldcg32(line);
         for (uint32_t idx = 1 + lane; idx <= cnt; idx += 32) {
             uint32_t rec;
@@ -551,21 +558,21 @@ __device__ __forceinline__ void noise_apply(const BlockCtx *bc, uint32_t att, ui
                 rec = ldcg32(bc->ev_buf + (size_t)GSTIM_EV_LINE_WORDS * bc->n_slices + __ldg(bc->ev_ovf_off + slice0 + sl_rel) + (idx - GSTIM_EV_LINE_WORDS));
             }
             const uint32_t site = (rec >> GSTIM_EV_SITE_SHIFT) & 31u;
-            const uint32_t it = sl_rel * 32 + site;
+            const uint32_t it = it0 + site;
             // position of the hit item in the batch: the warp that EXECUTES that position applies the event (with several
             // lanes per item the slice is shared with neighbouring warps, and a bank-spreading permutation may have moved
             // the item to another warp of the 32-item group)
-            const uint32_t pos_in_group = perm_s ? lds8(perm_s + it) : site;
+            const uint32_t pos_in_group = perm_s ? lds8(perm_s + it) : (it & 31u);
             if (pos_in_group - sub_lo >= ipw) {
                 continue;
             }
             const uint32_t shot = rec & ((1u << GSTIM_EV_SHOT_BITS) - 1);
             const uint32_t f = (rec >> GSTIM_EV_FLIP_SHIFT) & 31u;
-            const uint32_t pos = sl_rel * 32 + pos_in_group;
-            const uint32_t w = lds32(items_s + 4 * stride * pos);
+            const uint32_t pos = grp * 32 + pos_in_group;
+            const uint32_t iw = lds32(items_s + 4 * stride * pos);
             const uint32_t bit = 1u << (shot & 31);
             const uint32_t a0 = X_s + (shot >> 7) * pitch_b + ((shot >> 5) & 3) * 4;
-            const uint32_t a1 = a0 + (w & 0xFFFF) * 16, a2 = a0 + (w >> 16) * 16;
+            const uint32_t a1 = a0 + (iw & 0xFFFF) * 16, a2 = a0 + (iw >> 16) * 16;
             if (rec & GSTIM_EV_CONFLICT) {
                 if (f & 1u) {
                     flip_atomic(a1, bit);
@@ -616,6 +623,7 @@ __device__ __forceinline__ void noise_apply(const BlockCtx *bc, uint32_t att, ui
                 }
             }
         }
+      }
     }
     __syncwarp();
 }
@@ -628,7 +636,7 @@ __device__ __noinline__ const uint32_t *noise_post(const BlockCtx *bc, const uin
     if (att != GSTIM_NO_NOISE) {
         __syncwarp();
         const uint32_t perm = hw[GH_PERM];
-        noise_apply(bc, att, hw[GH_POST_NEXT], hw[GH_N], items_s, stride, perm ? hw.s + 4 * perm : 0u, hw[GH_REC0]);
+        noise_apply(bc, att, hw[GH_POST_NEXT], hw[GH_N], items_s, stride, perm ? hw.s + 4 * perm : 0u, hw[GH_REC0], (hw[GH_WIDTHS] >> 4) & 15u);
     }
     return hdr + hw[GH_WORDS];
 }
@@ -783,7 +791,7 @@ __device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uin
     const uint32_t aux = hw[GH_OP] >> 16;
     const uint32_t item_stride = (((aux >> 2) & 3u) != GK_R && ((hw[GH_OP] >> 8) & GF_DET)) ? 3u : 1u;
     if (hw[GH_PRE] != GSTIM_NO_NOISE) {  // flips in front of the measurement (X_ERROR before MR ...)
-        noise_apply(bc, hw[GH_PRE], hw[GH_PRE_NEXT], hw[GH_N], hw.s + 4 * GSTIM_HDR_WORDS, item_stride, 0u, hw[GH_REC0]);
+        noise_apply(bc, hw[GH_PRE], hw[GH_PRE_NEXT], hw[GH_N], hw.s + 4 * GSTIM_HDR_WORDS, item_stride, 0u, hw[GH_REC0], hw[GH_WIDTHS] & 15u);
     }
     switch (aux & 15u) {  // basis | kind << 2
         case GB_X | (GK_M << 2): measure_items<GB_X, GK_M>(bc, hw); break;
@@ -1172,7 +1180,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
             bar_sync<GSTIM_BAR_INTERP>(T);
         }
         // the first noise application of a shot block starts at slice 0 with parity 0
-        stage_line(bc, warp_first_item(bc) >> 5, 0u);
+        stage_line(bc, (warp_first_item(bc) >> 5) << p.first_lpg, 0u);
 
         for (uint32_t chunk = 0;; chunk++) {
             const uint32_t b = chunk & 1;

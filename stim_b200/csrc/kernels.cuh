@@ -35,6 +35,7 @@ struct InterpParams {
     const uint2 *rates;               // per rate: INV, SH (program.h "Gap arithmetic")
     const uint4 *slices;              // RNG slices, 2 uint4 each (program.h "Noise schedule")
     uint32_t n_slices;
+    uint32_t first_lpg;               // log2(slices per 32 items) of the first noise application of the program
     const uint32_t *tables;           // PAULI_CHANNEL_2 threshold tables
     const uint32_t *ev_ovf_off;       // n_slices + 1 : overflow segment offsets (words) for this launch's block size
     uint64_t ev_total;                // words per event buffer: 32 * n_slices + ev_ovf_off[n_slices] (+ padding)

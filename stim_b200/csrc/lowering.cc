@@ -18,23 +18,16 @@ uint32_t Batch::words() const {
     return GSTIM_HDR_WORDS + (uint32_t)payload.size() + perm_words;
 }
 
-namespace {
-
-constexpr uint32_t RES_WRITE = 1u << 31;
-constexpr uint32_t ITEM_X = 1u << 30;  // component flags in OBS_PAULI / FEEDBACK / CORR payload words
-constexpr uint32_t ITEM_Z = 1u << 31;
-
 // Probability -> rate key of the geometric gap arithmetic (program.h "Gap arithmetic"): bit 63 = valid, INV << 8 | SH.
 // 0 = the noise never fires. The reference narrows every probability to float before sampling
 // (probability_util.h:47, measure_record_batch.inl:52). p >= 1 saturates: INV = 0, an event at every shot.
-constexpr uint64_t RATE_VALID = 1ull << 63;
-uint64_t rate_of(double p) {
+uint64_t gstim_rate_key(double p) {
     float f = (float)p;
     if (!(f > 0)) {
         return 0;
     }
     if (f >= 1) {
-        return RATE_VALID;
+        return 1ull << 63;
     }
     const double lam = -std::log1p(-(double)f);
     int e = 0;
@@ -44,7 +37,18 @@ uint64_t rate_of(double p) {
         return 0;  // p < 2^-58: not a single event in any feasible number of shots
     }
     const uint64_t inv = (uint64_t)std::floor(std::ldexp(m, 32));
-    return RATE_VALID | (inv << 8) | (uint64_t)sh;
+    return (1ull << 63) | (inv << 8) | (uint64_t)sh;
+}
+
+namespace {
+
+constexpr uint32_t RES_WRITE = 1u << 31;
+constexpr uint32_t ITEM_X = 1u << 30;  // component flags in OBS_PAULI / FEEDBACK / CORR payload words
+constexpr uint32_t ITEM_Z = 1u << 31;
+
+constexpr uint64_t RATE_VALID = 1ull << 63;
+uint64_t rate_of(double p) {
+    return gstim_rate_key(p);
 }
 double prob_of(double p) {
     float f = (float)p;
@@ -1598,7 +1602,9 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
     };
     size_t prev_next_field = SIZE_MAX;  // where the previous noise application wants the first slice of this one
     // Emits the slices of one application of `spec` over n sites; returns the header word (first slice | parity << 31).
-    auto emit_application = [&](const NoiseSpec &spec, uint32_t n_sites, size_t next_field) -> uint32_t {
+    auto emit_application = [&](const NoiseSpec &spec, uint32_t n_sites, size_t next_field, uint32_t *width_log2) -> uint32_t {
+        const uint32_t w = gstim_slice_width_log2(spec.prob), S = 1u << w;
+        *width_log2 = w;
         if (spec.group >= group_items.size()) {
             group_items.resize((size_t)spec.group + 1, 0);
         }
@@ -1608,8 +1614,8 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             throw std::logic_error("internal: a noise group was cut inside an RNG slice");
         }
         const uint32_t slice0 = (uint32_t)(ns.slices.size() / GSTIM_SLICE_WORDS);
-        if (slice0 + (n_sites + GSTIM_NOISE_SLICE - 1) / GSTIM_NOISE_SLICE >= (1u << 31)) {
-            throw std::invalid_argument("Circuits with more than 2^31 noise slices are not supported by this build.");
+        if (slice0 + (uint64_t)(n_sites + S - 1) / S >= (1u << 28)) {
+            throw std::invalid_argument("Circuits with more than 2^28 noise slices are not supported by this build.");
         }
         const uint32_t rate = rate_index(spec.rate);
         uint32_t t1 = spec.t1;
@@ -1617,11 +1623,11 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             t1 = (uint32_t)ns.tables.size();
             ns.tables.insert(ns.tables.end(), spec.table, spec.table + 15);
         }
-        for (uint32_t i0 = 0; i0 < n_sites; i0 += GSTIM_NOISE_SLICE) {
-            const uint32_t cnt = std::min<uint32_t>(GSTIM_NOISE_SLICE, n_sites - i0);
+        for (uint32_t i0 = 0; i0 < n_sites; i0 += S) {
+            const uint32_t cnt = std::min<uint32_t>(S, n_sites - i0);
             uint32_t sl[GSTIM_SLICE_WORDS] = {};
             sl[GSL_GROUP] = spec.group;
-            sl[GSL_INDEX] = (gfirst + i0) / GSTIM_NOISE_SLICE;
+            sl[GSL_INDEX] = (gfirst + i0) / S;
             sl[GSL_RATE_SITES] = rate | (cnt << 16);
             sl[GSL_H0] = spec.op | (spec.flags << 8) | (spec.aux << 16);
             sl[GSL_T1] = t1;
@@ -1632,7 +1638,7 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             ns.slice_sites.push_back(cnt);
         }
         if (prev_next_field != SIZE_MAX) {
-            out[prev_next_field] = slice0;
+            out[prev_next_field] = slice0 | ((5 - w) << 28);
         }
         prev_next_field = next_field;
         const uint32_t parity = ns.n_applications & 1u;
@@ -1725,12 +1731,14 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             }
         }
         const uint32_t n_sites = b.op == GOP_CORR ? 1u : b.n_items;
+        uint32_t w_pre = 5, w_post = 5;
         if (b.pre.present && b.pre.rate != 0) {
-            out[base + GH_PRE] = emit_application(b.pre, n_sites, base + GH_PRE_NEXT);
+            out[base + GH_PRE] = emit_application(b.pre, n_sites, base + GH_PRE_NEXT, &w_pre);
         }
         if (b.post.present && b.post.rate != 0) {
-            out[base + GH_POST] = emit_application(b.post, n_sites, base + GH_POST_NEXT);
+            out[base + GH_POST] = emit_application(b.post, n_sites, base + GH_POST_NEXT, &w_post);
         }
+        out[base + GH_WIDTHS] = w_pre | (w_post << 4);
     }
     put_header(GOP_END, GSTIM_HDR_WORDS);
     out.resize((out.size() + chunk_words - 1) / chunk_words * (size_t)chunk_words, 0);

@@ -73,6 +73,9 @@ struct LoweredCircuit {
     uint64_t num_sites = 0, num_csites = 0;
 };
 
+// Probability -> rate key of the gap arithmetic: bit 63 = valid, (INV << 8) | SH below it; 0 = never fires.
+uint64_t gstim_rate_key(double p);
+
 // Pass 1: semantics. Throws std::invalid_argument / std::out_of_range like the reference would.
 LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words);
 

@@ -55,12 +55,13 @@ enum GstimHdr : uint32_t {
     GH_CSITE0 = 4,    // measure group of the batch (Philox counter word 0 of its collapse draws)
     GH_REC0 = 5,      // absolute measurement index of item 0 (MEASURE / RECZERO / record-flipping noise)
     GH_PRE = 6,       // pre-noise application: first RNG slice | parity << 31, or GSTIM_NO_NOISE (MEASURE only)
-    GH_PRE_NEXT = 7,  // first slice of the noise application that follows it in program order, or GSTIM_NO_NOISE
+    GH_PRE_NEXT = 7,  // the noise application that follows it in program order: first slice | log2(slices per 32 items) << 28,
+                      // or GSTIM_NO_NOISE
     GH_POST = 8,      // post-noise application (for GOP_NOISE1 / GOP_NOISE2 / GOP_CORR: the batch's own noise)
     GH_POST_NEXT = 9,
     GH_PERM = 10,     // word offset (from the header) of the byte table site -> item position inside its 32-item group,
                       // 0 = identity (gate batches whose items were reordered for bank spreading)
-    GH_SPARE = 11,
+    GH_WIDTHS = 11,   // log2(sites per slice) of the pre-noise (bits 0-3) and of the post-noise (bits 4-7)
 };
 #define GSTIM_NO_NOISE 0xFFFFFFFFu
 
@@ -106,10 +107,13 @@ enum GstimHdr : uint32_t {
 #define GSTIM_LN2_Q32 2977044472u
 
 // Noise schedule. The sites of a noise group (one noise instruction, or one run of it without a repeated qubit), in
-// target order, are cut into SLICES of GSTIM_NOISE_SLICE consecutive sites; a slice x a shot block is one Bernoulli
-// sequence (site-major, then shot) walked with geometric gaps drawn from the slice's own Philox stream, like the
-// reference's RareErrorIterator over targets x shots. Slices are numbered in program order; a noise application (the
-// pre- / post-noise of a batch, or a stand-alone noise batch) owns ceil(n / 32) consecutive slices.
+// target order, are cut into SLICES of 2^w consecutive sites; a slice x a shot block is one Bernoulli sequence
+// (site-major, then shot) walked with geometric gaps drawn from the slice's own Philox stream, like the reference's
+// RareErrorIterator over targets x shots. The slice width follows the probability, so that a slice holds a bounded
+// number of events however dense the noise: w = 5 (GSTIM_NOISE_SLICE = 32 sites) for p < 2^-6, one less for every
+// doubling of p, w = 0 (one site per slice) from p >= 1/4 (gstim_slice_width_log2). Slices are numbered in program
+// order; a noise application (the pre- / post-noise of a batch, or a stand-alone noise batch) over n items owns
+// ceil(n / 2^w) consecutive slices, 32 >> w of them per group of 32 items.
 //   slice descriptor (8 words): noise group, slice index in the group, rate index | number of sites << 16,
 //                    op | flags << 8 | aux << 16 of the noise, T1, T2, T3 (NOISE1 thresholds; NOISE2 + GF_TABLE: T1 = word
 //                    offset of the 15 PAULI_CHANNEL_2 thresholds in the schedule's table area), spare
@@ -120,6 +124,16 @@ enum GstimHdr : uint32_t {
 //   record = shot (bits 0-11) | site in the slice (12-16) | flips x1,z1,x2,z2 (17-20) | record flip (21) | conflict (22).
 #define GSTIM_NOISE_SLICE 32u
 #define GSTIM_SLICE_WORDS 8u
+#ifdef __cplusplus
+// log2 of the sites per slice for event probability p (already narrowed to float): 2^-6 > p -> 5, ..., p >= 2^-2 -> 0.
+static inline uint32_t gstim_slice_width_log2(double p) {
+    uint32_t w = 5;
+    for (double t = 1.0 / 64; w > 0 && p >= t; t *= 2) {
+        w--;
+    }
+    return w;
+}
+#endif
 enum GstimSliceWord : uint32_t {
     GSL_GROUP = 0,
     GSL_INDEX = 1,

@@ -50,17 +50,18 @@ def test_exp_draw_q26_is_exponential():
 
 def test_rate_and_gap_arithmetic():
     assert px.rate_of(0.0) is None and px.rate_of(-1.0) is None and px.rate_of(1e-30) is None
-    assert px.rate_of(1.0) == (0, 0) and px.gap_of(12345, (0, 0)) == 0  # p = 1: an event at every shot
+    assert px.rate_of(1.0) == (0, 0, 0) and px.gap_of(12345, (0, 0, 0)) == 0  # p = 1: an event at every shot
+    assert [px.slice_width_log2(f) for f in (1e-3, 0.0156, 0.015625, 0.03, 0.0625, 0.2, 0.25, 0.9)] == [5, 5, 4, 4, 2, 1, 0, 0]
     rng = random.Random(7)
     for p in (1e-9, 1e-6, 1e-3, 0.02, 0.3, 0.5, 0.999, float(np.float32(1) - np.float32(2.0**-24))):
-        inv, sh = px.rate_of(p)
+        inv, sh, _ = px.rate_of(p)
         assert (1 << 31) <= inv < (1 << 32) and 0 <= sh <= 62
         lam = -math.log1p(-float(np.float32(p)))
         assert abs(inv / 2.0 ** (sh - 26) * lam - 1.0) < 1e-9  # INV * 2^(26 - SH) = 1 / lambda
         for _ in range(2000):
             w = rng.getrandbits(32)
             exact = px.exp_draw_q26(w) / 2.0**26 / lam
-            assert abs(px.gap_of(w, (inv, sh)) - exact) <= 1.0 + 1e-6 * exact
+            assert abs(px.gap_of(w, (inv, sh, 5)) - exact) <= 1.0 + 1e-6 * exact
 
 
 def test_gaps_are_geometric():
