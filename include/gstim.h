@@ -92,18 +92,14 @@ int gstim_reference_sample(const char *circuit_text, size_t text_len, uint8_t *b
 
 /* Host-only lowering (no GPU needed): circuit text -> the uint32 instruction stream the interpreter
  * kernel executes (format: stim_b200/csrc/program.h), with barrier flags computed for `slots`
- * concurrent thread groups of 2^lanes_log2 lanes each (a warp executes 32 >> lanes_log2 consecutive items; slots must
- * be a multiple of that) and cut into chunks of `chunk_words` words (0 = library default). The program
- * (plan.n_words words) is followed by a copy of the noise schedule: 'NSCH', n_slices, n_rates, n_table_words, the
- * slice descriptors, rates and PAULI_CHANNEL_2 tables. plan_out receives the 16 uint32 fields of GstimPlan
- * (program.h). Call with words == NULL to get the required length in *n_words. No reference analogue (new
- * subsystem: the lowering). */
+ * concurrent thread groups and cut into chunks of `chunk_words` words (0 = library default).
+ * plan_out receives the 14 uint32 fields of GstimPlan (program.h). Call with words == NULL to get
+ * the required length in *n_words. No reference analogue (new subsystem: the lowering). */
 int gstim_lower_text(
     const char *circuit_text,
     size_t text_len,
     int mode,
     uint32_t slots,
-    uint32_t lanes_log2,
     uint32_t chunk_words,
     uint32_t *words,
     size_t *n_words,
@@ -226,6 +222,9 @@ int gstim_dem_set_shot_offset(gstim_dem_sampler *s, uint64_t offset);
  * (the reference's return_errors / --err_out). Replaying recorded errors (--replay_err_in) is not supported. */
 int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void *dets_out, int64_t dets_stride, void *obs_out,
                      int64_t obs_stride, void *errs_out, int64_t errs_stride);
+/* Flip counts of the D + L output bits (detectors, then observables) and of adjacent pairs over `shots` fresh shots,
+ * reduced on the device (the statistic of the parity tests; see gstim_bit_counts). pair_host may be NULL. */
+int gstim_dem_bit_counts(gstim_dem_sampler *s, uint64_t shots, uint64_t *single_host, uint64_t *pair_host);
 /* Streams to files in any result format; a negative fd skips that output. The outputs of one chunk are written in the
  * reference's order (errors, observables, detectors). */
 int gstim_dem_sample_to_fd(gstim_dem_sampler *s, uint64_t shots, int det_fd, const char *det_format, int obs_fd, const char *obs_format,

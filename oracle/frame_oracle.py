@@ -178,7 +178,7 @@ TWO_QUBIT = {
 }
 
 
-rate_of = px.rate_of  # probability -> (INV, SH) of the fixed-point gap arithmetic, None = never fires
+rate_of = px.lam_fx  # probability -> per-shot event rate in fixed-point clock units (2**-56 nat)
 
 
 def thr(frac):
@@ -237,14 +237,14 @@ class FrameOracle:
     def run_sites(self, clocks, lam, group, on_event):
         """Samples the len(clocks) sites of noise group `group` (in target order) over all blocks.
 
-        The sites are cut into slices of 2^w sites (w from the probability); a slice x a shot block is one Bernoulli sequence (site-major, then
+        The sites are cut into slices of NOISE_SLICE; a slice x a shot block is one Bernoulli sequence (site-major, then
         shot) walked with geometric gaps floor(Exp(1)/lambda) == RareErrorIterator (probability_util.cc:33-43), in
         exact integer arithmetic. Call c of a slice: Philox counter (group, 0x80000000 | slice, col0 lo, col0 hi | c << 15)
         = draws 2c (words 0, 1) and 2c + 1 (words 2, 3); a draw = (gap to the next event, that event's Pauli word). on_event(i, g, shot, r): r[1] = Pauli word."""
         n = len(clocks)
-        if n == 0 or lam is None:
+        if n == 0 or lam == 0:
             return
-        B, S = self.B, 1 << lam[2]  # sites per slice follow the probability (program.h "Noise schedule")
+        B, S = self.B, self.NOISE_SLICE
         n_sl = (n + S - 1) // S
         c2 = (self.col0 & np.uint64(0xFFFFFFFF))[None, :]
         c3 = (self.col0 >> np.uint64(32))[None, :]
@@ -262,7 +262,7 @@ class FrameOracle:
                         words = [int(v) for v in r]
                     gap_word, pauli_word = words[2 * (d % 2)], words[2 * (d % 2) + 1]
                     d += 1
-                    G = px.gap_of(gap_word, lam)
+                    G = px.exp_draw_fx(gap_word) // lam
                     if G >= total - a:
                         break
                     a += G

@@ -5,9 +5,8 @@ numpy restatement of the two random primitives the device noise generator is spe
 
   * Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
     Pinned against the Random123 known-answer vectors in tests/test_oracle_philox.py.
-  * exp_draw_q26 / gap_of: Exp(1) variate from a uniform u32 and the geometric gap it gives, integer arithmetic only,
-    so the CUDA kernel (stim_b200/csrc/interp.cu) reproduces them bit for bit. (exp_draw is the round-1 double
-    precision form, kept as the accuracy reference for tests/test_oracle_philox.py.)
+  * exp_draw: Exp(1) variate from a uniform u32 using only IEEE-754 double + - * / in a fixed order,
+    so the CUDA kernel (stim_b200/csrc/kernels.cu: exp_draw) reproduces it bit for bit.
 
 These replace, in distribution, the reference's std::mt19937_64 + std::geometric_distribution
 (/root/reference/src/stim/util_bot/probability_util.cc:23-43): floor(Exp(1)/lambda) with
@@ -74,8 +73,43 @@ def exp_draw(r):
 
 
 # ---------------------------------------------------------------------------------------------
-# Gap arithmetic, spec v6 (stim_b200/csrc/program.h "Gap arithmetic"): all integer, so the device
-# (stim_b200/csrc/interp.cu: exp_draw_q26 / the producer loop) and this oracle agree bit for bit by construction.
+# Fixed-point exponential clock (spec v2, DESIGN.md "RNG addressing"): all integer arithmetic, so the
+# device (stim_b200/csrc/kernels.cu: exp_draw_fx) and this oracle agree bit for bit by construction.
+# Unit = 2**-56 nat.
+# ---------------------------------------------------------------------------------------------
+from .log2_table import LN2_Q24, LOG2_T  # noqa: E402
+
+FX_SHIFT = 56
+LAM_MAX = 1 << 62
+REM_SAT = 1 << 63
+
+
+def exp_draw_fx(r: int) -> int:
+    """-ln((r + 1/2) / 2**32) in units of 2**-56, via a 256-entry log2 table with linear interpolation."""
+    v = 2 * int(r) + 1
+    t = v.bit_length() - 1
+    vn = v << (32 - t)
+    frac = vn & 0xFFFFFFFF
+    i, f = frac >> 24, frac & 0xFFFFFF
+    log2m = LOG2_T[i] + (((LOG2_T[i + 1] - LOG2_T[i]) * f) >> 24)
+    return ((33 << 32) - ((t << 32) + log2m)) * LN2_Q24
+
+
+def lam_fx(p: float) -> int:
+    """Per-shot event rate of probability p (narrowed to float32 like the reference) in clock units."""
+    import math
+
+    f = float(np.float32(p))
+    if not f > 0:
+        return 0
+    if f >= 1:
+        return LAM_MAX
+    return min(int(math.ldexp(-math.log1p(-f), FX_SHIFT)), LAM_MAX)
+
+
+# ---------------------------------------------------------------------------------------------
+# 32-bit gap arithmetic of the detector-error-model sampler (stim_b200/csrc/dem.cu, header comment): all integer, so the
+# device and this restatement agree bit for bit by construction.
 # ---------------------------------------------------------------------------------------------
 from .log2_table import LN2_Q32, LOG2_T26  # noqa: E402
 
@@ -91,32 +125,21 @@ def exp_draw_q26(r: int) -> int:
     return (((1 << 31) - log2v) * LN2_Q32) >> 32
 
 
-def slice_width_log2(f: float) -> int:
-    """log2 of the sites per RNG slice for probability f (program.h gstim_slice_width_log2): 5 below 2**-6, one less for
-    every doubling, 0 from 1/4."""
-    w, t = 5, 1.0 / 64
-    while w > 0 and f >= t:
-        w -= 1
-        t *= 2
-    return w
-
-
 def rate_of(p: float):
-    """Probability (narrowed to float32 like the reference) -> (INV, SH, slice width log2) of the gap arithmetic, or None
-    if it never fires."""
+    """Probability (narrowed to float32 like the reference) -> (INV, SH) of the gap arithmetic, or None if it never fires."""
     import math
 
     f = float(np.float32(p))
     if not f > 0:
         return None
     if f >= 1:
-        return (0, 0, 0)
+        return (0, 0)
     lam = -math.log1p(-f)
     m, e = math.frexp(1.0 / lam)
     sh = 58 - e
     if sh < 0:
         return None
-    return (int(math.floor(math.ldexp(m, 32))), sh, slice_width_log2(f))
+    return (int(math.floor(math.ldexp(m, 32))), sh)
 
 
 def gap_of(gap_word: int, rate) -> int:

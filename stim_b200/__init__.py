@@ -20,7 +20,10 @@ import numpy as np
 from . import _native
 from ._native import GstimCudaError, GstimStats
 
-__all__ = ["Circuit", "CompiledDetectorSampler", "CompiledMeasurementSampler", "GstimCudaError", "measure_lop3_peak"]
+from .dem import CompiledDemSampler, DetectorErrorModel  # noqa: E402,F401
+
+__all__ = ["Circuit", "CompiledDetectorSampler", "CompiledMeasurementSampler", "GstimCudaError", "measure_lop3_peak",
+           "DetectorErrorModel", "CompiledDemSampler"]
 
 
 def measure_lop3_peak(device: int = 0) -> dict:

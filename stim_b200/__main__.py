@@ -1,11 +1,14 @@
-"""Command-line mirror of the two reference sub-commands that sit on the replaced path:
+"""Command-line mirror of the reference sub-commands that sit on the replaced path:
 
     python -m stim_b200 detect --shots N [--in FILE] [--out FILE] [--out_format F] [--seed S]
                                [--append_observables | --prepend_observables] [--obs_out FILE] [--obs_out_format F]
     python -m stim_b200 sample --shots N [--in FILE] [--out FILE] [--out_format F] [--seed S] [--skip_reference_sample]
+    python -m stim_b200 sample_dem --shots N [--in FILE] [--out FILE] [--out_format F] [--obs_out FILE] [--obs_out_format F]
+                               [--err_out FILE] [--err_out_format F] [--seed S]
 
-Same flags, defaults and output bytes as `stim detect` / `stim sample`
-(/root/reference/src/stim/cmd/command_detect.cc:23-79, command_sample.cc:25-71, doc/usage_command_line.md); the sampling itself
+Same flags, defaults and output bytes as `stim detect` / `stim sample` / `stim sample_dem`
+(/root/reference/src/stim/cmd/command_detect.cc:23-79, command_sample.cc:25-71, command_sample_dem.cc:25-93,
+doc/usage_command_line.md); the sampling itself
 runs on the GPU through the C ABI (there is no CPU fallback). Errors print to stderr and exit with status 1 like
 /root/reference/src/stim/main_namespaced.cc:113-122."""
 import argparse
@@ -33,6 +36,13 @@ def _parser():
             q.add_argument("--obs_out_format", default="01", choices=FORMATS)
         else:
             q.add_argument("--skip_reference_sample", action="store_true")
+    q = sub.add_parser("sample_dem", allow_abbrev=False)
+    q.add_argument("--shots", type=int, default=1)
+    q.add_argument("--in", dest="inp", default=None)
+    q.add_argument("--seed", type=int, default=None)
+    for flag in ("out", "obs_out", "err_out"):
+        q.add_argument("--" + flag, default=None)
+        q.add_argument("--" + flag + "_format", default="01", choices=FORMATS)
     return p
 
 
@@ -40,6 +50,15 @@ def main(argv=None) -> int:
     args = _parser().parse_args(argv)
     try:
         text = sys.stdin.read() if args.inp is None else open(args.inp).read()
+        if args.command == "sample_dem":
+            sampler = stim_b200.DetectorErrorModel(text).compile_sampler(seed=args.seed)
+            sys.stdout.flush()
+            if args.shots > 0:
+                sampler.sample_write(
+                    args.shots, det_out_file=args.out if args.out is not None else "/dev/stdout", det_out_format=args.out_format,
+                    obs_out_file=args.obs_out, obs_out_format=args.obs_out_format, err_out_file=args.err_out,
+                    err_out_format=args.err_out_format)
+            return 0
         circuit = stim_b200.Circuit(text)
         out_path = args.out if args.out is not None else "/dev/stdout"
         sys.stdout.flush()

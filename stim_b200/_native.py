@@ -58,7 +58,7 @@ _SIGNATURES = [
     ("gstim_circuit_stats", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(GstimStats)]),
     ("gstim_reference_sample", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, _P, ctypes.c_size_t]),
     ("gstim_lower_text", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
-                                        ctypes.c_uint32, _P, ctypes.POINTER(ctypes.c_size_t), _P]),
+                                        _P, ctypes.POINTER(ctypes.c_size_t), _P]),
     ("gstim_create_from_text", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, ctypes.c_int,
                                               ctypes.POINTER(_P)]),
     ("gstim_destroy", None, [_P]),
@@ -84,6 +84,7 @@ _SIGNATURES = [
     ("gstim_dem_destroy", None, [_P]),
     ("gstim_dem_set_shot_offset", ctypes.c_int, [_P, ctypes.c_uint64]),
     ("gstim_dem_sample", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_uint32, _P, ctypes.c_int64, _P, ctypes.c_int64, _P, ctypes.c_int64]),
+    ("gstim_dem_bit_counts", ctypes.c_int, [_P, ctypes.c_uint64, _P, _P]),
     ("gstim_dem_sample_to_fd", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p,
                                               ctypes.c_int, ctypes.c_char_p]),
     ("gstim_set_block_columns", ctypes.c_int, [_P, ctypes.c_uint32]),

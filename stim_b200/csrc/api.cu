@@ -127,11 +127,11 @@ struct gstim_sampler {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     DevBuf d_dbg, d_prog, d_table, d_rec, d_rowmap, d_stage[2], d_counts;
-    // noise schedule + per-CTA event buffers (interp.cu noise_prepass)
-    DevBuf d_rates, d_slices, d_tables, d_ovf_off, d_ev_buf, d_ev_overflow;
-    uint32_t ovf_K = 0;      // block size the overflow offsets were computed for
-    uint32_t n_slices = 0;
-    uint64_t ev_total = 0;   // words per event buffer
+    // noise schedule + per-CTA event scratch (interp.cu noise_prepass)
+    DevBuf d_noise_info, d_rates, d_slices, d_segoff, d_ev_counts, d_ev_buf, d_ev_overflow;
+    uint32_t segoff_K = 0;
+    uint32_t n_noise = 0;
+    uint64_t ev_total = 0;
     PinnedBuf h_stage[2];
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
     cudaEvent_t stage_ready[2] = {nullptr, nullptr};
@@ -208,11 +208,15 @@ void configure(gstim_sampler *s) {
     s->lc = lower_circuit(s->circuit, (uint32_t)s->mode, s->chunk_words - GSTIM_HDR_WORDS);
 
     // Every chunk hand-over of the program ring costs ~1400 cycles per shot block (barrier + ring turn-around,
-    // profiles/r1_notes.md), so the shared memory that the frame columns leave unused goes into larger chunks.
-    // The circuit is lowered again for that size.
+    // profiles/r1_notes.md), so the shared memory that the frame columns leave unused goes into larger chunks
+    // (c3: 5.9 KB spare -> 2688-word chunks, 104 instead of 155 chunks). The circuit is lowered again for that size.
     if (env_u32("GSTIM_CHUNK_WORDS", 0) == 0) {
         const uint32_t Q0 = s->lc.num_qubits, pitch0 = Q0 | 1u;
-        const size_t fixed0 = interp_smem_bytes(pitch0, 0, s->chunk_words, 640);
+        uint32_t n_noise0 = 0;
+        for (const auto &b : s->lc.batches) {
+            n_noise0 += b.op == GOP_NOISE1 || b.op == GOP_NOISE2 || b.op == GOP_CORR;
+        }
+        const size_t fixed0 = interp_smem_bytes(pitch0, Q0, 0, s->chunk_words, n_noise0);
         const size_t per_k0 = (size_t)2 * pitch0 * 16 + 16;
         if (fixed0 + per_k0 <= s->smem_optin) {
             const size_t k0 = std::min<size_t>((s->smem_optin - fixed0) / per_k0, 32);
@@ -249,11 +253,12 @@ void configure(gstim_sampler *s) {
     // K_max from the shared-memory budget
     uint32_t Q = s->lc.num_qubits;
     uint32_t q_pitch = Q | 1u;
-    bool any_noise = false;
+    uint32_t n_noise_batches = 0;
     for (const auto &b : s->lc.batches) {
-        any_noise |= (b.pre.present && b.pre.rate != 0) || (b.post.present && b.post.rate != 0);
+        n_noise_batches += b.op == GOP_NOISE1 || b.op == GOP_NOISE2 || b.op == GOP_CORR;
     }
-    size_t fixed = interp_smem_bytes(q_pitch, 0, s->chunk_words, 640);
+    s->n_noise = n_noise_batches;
+    size_t fixed = interp_smem_bytes(q_pitch, Q, 0, s->chunk_words, s->n_noise);
     size_t per_k = (size_t)2 * q_pitch * 16 + 16;
     if (fixed + per_k > s->smem_optin) {
         throw std::invalid_argument(
@@ -282,18 +287,20 @@ void configure(gstim_sampler *s) {
     }
     // noise producer warps (interp.cu): 128 threads next to the interpreter's keep the block at 768 threads = 80 registers
     s->pre_threads = 0;
-    if (any_noise && s->threads + 32 <= 1024) {
+    if (s->n_noise > 0 && s->threads + 32 <= 1024) {
         uint32_t want = env_u32("GSTIM_PRE_THREADS", 128) / 32 * 32;
         s->pre_threads = std::max<uint32_t>(32, std::min<uint32_t>(want, 1024 - s->threads));
+        if (env_u32("GSTIM_PRE_THREADS", 128) == 0) {
+            s->pre_threads = 0;  // timing experiments only: no noise events are produced
+        }
     }
-    if (any_noise && s->pre_threads == 0) {
+    if (s->n_noise > 0 && s->pre_threads == 0 && env_u32("GSTIM_PRE_THREADS", 128) != 0) {
         throw std::invalid_argument("internal: no room for the noise producer warps");
     }
 
-    s->words = serialize_program(s->lc, slots, G_log2, s->chunk_words, &s->plan);
-    s->n_slices = s->plan.n_slices;
-    s->d_prog.ensure((size_t)s->plan.n_words * 4);
-    CK(cudaMemcpy(s->d_prog.p, s->words.data(), (size_t)s->plan.n_words * 4, cudaMemcpyHostToDevice));
+    s->words = serialize_program(s->lc, slots, s->chunk_words, &s->plan);
+    s->d_prog.ensure(s->words.size() * 4);
+    CK(cudaMemcpy(s->d_prog.p, s->words.data(), s->words.size() * 4, cudaMemcpyHostToDevice));
     {
         const NoiseSchedule &ns = s->lc.noise;
         auto up = [&](DevBuf &d, const void *src, size_t bytes) {
@@ -302,12 +309,13 @@ void configure(gstim_sampler *s) {
                 CK(cudaMemcpy(d.p, src, bytes, cudaMemcpyHostToDevice));
             }
         };
-        up(s->d_rates, ns.rates.data(), ns.rates.size() * 4);
+        up(s->d_noise_info, ns.info.data(), ns.info.size() * 4);
+        up(s->d_rates, ns.rates.data(), ns.rates.size() * 8);
         up(s->d_slices, ns.slices.data(), ns.slices.size() * 4);
-        up(s->d_tables, ns.tables.data(), ns.tables.size() * 4);
         s->d_ev_overflow.ensure(16);
         CK(cudaMemset(s->d_ev_overflow.p, 0, 16));
     }
+    CK(interp_set_max_smem(interp_smem_bytes(q_pitch, Q, K_max, s->chunk_words, s->n_noise)));
 }
 
 uint32_t choose_K(const gstim_sampler *s, uint64_t shots) {
@@ -392,7 +400,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
     s->last_K = K;
     const uint32_t B = K * GSTIM_COL_SHOTS;
     const uint32_t Q = s->plan.num_qubits, q_pitch = s->plan.q_pitch;
-    const size_t smem = interp_smem_bytes(q_pitch, K, s->chunk_words, s->threads);
+    const size_t smem = interp_smem_bytes(q_pitch, Q, K, s->chunk_words, s->n_noise);
     const uint32_t rows = n_rows_of(s);
     const uint64_t total_blocks = (shots + B - 1) / B;
 
@@ -402,7 +410,6 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
     const uint64_t bytes_per_block = (uint64_t)std::max<uint32_t>(rows, 1) * K * 16;
     // persistent grid: as many blocks as fit on the device at once (shared memory usually allows one per SM)
     uint32_t grid_cap = (uint32_t)s->num_sms * (uint32_t)interp_max_blocks_per_sm(s->threads + s->pre_threads, smem);
-    grid_cap = std::max<uint32_t>(1, std::min(grid_cap, env_u32("GSTIM_GRID_CAP", grid_cap)));  // (debugging: fewer CTAs, more shot blocks each)
     uint64_t max_blocks = std::max<uint64_t>(table_budget / bytes_per_block, (uint64_t)grid_cap);
     // whole waves only: a chunk of 11.07 waves costs 12 (the CTAs walk their shot blocks in lock step)
     max_blocks = max_blocks / grid_cap * grid_cap;
@@ -412,31 +419,30 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
         s->d_rec.ensure((size_t)grid_cap * s->plan.rec_ring * K * 16);
     }
 
-    // event buffers: one 128-byte line per RNG slice (count + 31 records) and, behind the lines, an overflow segment per
-    // slice sized so that line + overflow hold mean + 12 sigma + 8 of the slice's binomial event count
-    const uint32_t n_slices = s->n_slices;
-    if (s->ovf_K != K) {
-        const NoiseSchedule &ns = s->lc.noise;
-        std::vector<uint32_t> ovf(n_slices + 1, 0);
+    // event scratch: one segment per noise batch, sized mean + 12 sigma + 64 of its Poisson event count
+    const uint32_t n_noise = (uint32_t)s->lc.noise.n_sites.size();
+    if (s->segoff_K != K) {
+        std::vector<uint32_t> segoff(n_noise + 1, 0);
         uint64_t total = 0;
-        for (uint32_t i = 0; i < n_slices; i++) {
-            const double pr = ns.slice_prob[i];
-            const double sites = (double)ns.slice_sites[i] * B;
+        for (uint32_t i = 0; i < n_noise; i++) {
+            const double lam = std::ldexp((double)s->lc.noise.lams[i], -56);
+            const double pr = s->lc.noise.lams[i] >= (1ull << 62) ? 1.0 : -std::expm1(-lam);
+            const double sites = (double)s->lc.noise.n_sites[i] * B;
             const double mean = sites * pr;
-            const double cap = std::min(sites, std::ceil(mean + 12.0 * std::sqrt(mean * (1.0 - pr)) + 8.0));
-            ovf[i] = (uint32_t)total;
-            total += cap > GSTIM_EV_LINE_WORDS - 1 ? (uint64_t)cap - (GSTIM_EV_LINE_WORDS - 1) : 0;
+            const double cap = std::min(sites, std::ceil(mean + 12.0 * std::sqrt(mean) + 64.0));
+            segoff[i] = (uint32_t)total;
+            total += (uint64_t)cap;
             if (total >= (1ull << 31)) {
-                throw std::invalid_argument("noise event buffers would exceed 2^31 records per block; lower the noise or the block size");
+                throw std::invalid_argument("noise event scratch would exceed 2^31 records per block; lower the noise or the block size");
             }
         }
-        ovf[n_slices] = (uint32_t)total;
-        s->d_ovf_off.ensure(ovf.size() * 4);
-        CK(cudaMemcpy(s->d_ovf_off.p, ovf.data(), ovf.size() * 4, cudaMemcpyHostToDevice));
-        s->ovf_K = K;
-        // (+ 32 lines: a warp without items in an application may stage a line past the application's last slice)
-        s->ev_total = ((uint64_t)GSTIM_EV_LINE_WORDS * n_slices + total + 31) / 32 * 32 + 32 * GSTIM_EV_LINE_WORDS;
+        segoff[n_noise] = (uint32_t)total;
+        s->d_segoff.ensure(segoff.size() * 4);
+        CK(cudaMemcpy(s->d_segoff.p, segoff.data(), segoff.size() * 4, cudaMemcpyHostToDevice));
+        s->segoff_K = K;
+        s->ev_total = total;
     }
+    s->d_ev_counts.ensure(std::max<size_t>((size_t)grid_cap * 2 * n_noise * 4, 16));
     s->d_ev_buf.ensure(std::max<size_t>((size_t)grid_cap * 2 * s->ev_total * 4, 16));
 
     if (s->next_col + total_blocks * K >= (1ull << 47)) {
@@ -464,19 +470,18 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
         p.slots = s->slots;
         p.threads_interp = s->threads;
         p.n_blocks = (uint32_t)nb;
+        p.n_noise = n_noise;
         p.n_rates = (uint32_t)(s->lc.noise.rates.size() / 2);
-        p.rates = (const uint2 *)s->d_rates.p;
+        p.noise_info = (const uint32_t *)s->d_noise_info.p;
+        p.rates = (const ulonglong2 *)s->d_rates.p;
         p.slices = (const uint4 *)s->d_slices.p;
-        p.n_slices = n_slices;
-        p.first_lpg = n_slices ? 5 - gstim_slice_width_log2(s->lc.noise.slice_prob[0]) : 0;
-        p.tables = (const uint32_t *)s->d_tables.p;
-        p.ev_ovf_off = (const uint32_t *)s->d_ovf_off.p;
-        p.ev_total = s->ev_total;
+        p.n_slices = (uint32_t)(s->lc.noise.slices.size() / GSTIM_SLICE_WORDS);
+        p.ev_segoff = (const uint32_t *)s->d_segoff.p;
+        p.ev_counts = (uint32_t *)s->d_ev_counts.p;
         p.ev_buf = (uint32_t *)s->d_ev_buf.p;
         p.ev_overflow = (uint32_t *)s->d_ev_overflow.p;
         p.dbg_cycles = nullptr;
         p.dbg_flags = env_u32("GSTIM_DEBUG_FLAGS", 0);
-        p.phased = env_u32("GSTIM_PHASED", 0);  // (measured on c3: overlapped producers 30.1 ms, phased 33.1 ms per 2^22 shots)
         if (env_u32("GSTIM_DEBUG_CYCLES", 0)) {
             s->d_dbg.ensure(64 * 8);
             CK(cudaMemsetAsync(s->d_dbg.p, 0, 64 * 8, s->stream));
@@ -523,7 +528,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
             tot += h[i];
         }
         fprintf(stderr, "[gstim cycles, block 0, last launch] total %llu\n", tot);
-        fprintf(stderr, "  producers(thread 0): %llu cyc; events %llu, slices %llu, iterations %llu\n", h[32], h[33], h[34], h[35]);
+        fprintf(stderr, "  prepass(thread 0): %llu cyc; events %llu, slices %llu, iterations %llu\n  noise apply(thread 0): prefetch+wait %llu, entry barrier %llu, flips %llu, exit barrier %llu cyc\n", h[32], h[33], h[34], h[35], h[40], h[41], h[42], h[43]);
         for (int i = 0; i < 13; i++) {
             if (h[i]) {
                 fprintf(stderr, "  %-9s %10llu cyc (%5.1f%%)  %6llu batches  %8.0f cyc/batch\n", names[i], h[i], 100.0 * h[i] / tot, h[16 + i], h[16 + i] ? (double)h[i] / h[16 + i] : 0.0);
@@ -965,7 +970,6 @@ int gstim_lower_text(
     size_t text_len,
     int mode,
     uint32_t slots,
-    uint32_t lanes_log2,
     uint32_t chunk_words,
     uint32_t *words,
     size_t *n_words,
@@ -984,7 +988,7 @@ int gstim_lower_text(
         }
         LoweredCircuit lc = lower_circuit(c, (uint32_t)mode, chunk_words - GSTIM_HDR_WORDS);
         GstimPlan plan;
-        std::vector<uint32_t> w = serialize_program(lc, slots, lanes_log2, chunk_words, &plan);
+        std::vector<uint32_t> w = serialize_program(lc, slots, chunk_words, &plan);
         if (plan_out != nullptr) {
             memset(plan_out, 0, 16 * sizeof(uint32_t));
             memcpy(plan_out, &plan, sizeof(plan));
@@ -1055,7 +1059,7 @@ int gstim_get_stats(const gstim_sampler *s, gstim_stats *out) {
         out->slots = s->slots;
         out->max_columns = s->K_max;
         out->chunk_words = s->chunk_words;
-        out->smem_bytes_max = (uint32_t)interp_smem_bytes(s->plan.q_pitch, s->K_max, s->chunk_words, s->threads);
+        out->smem_bytes_max = (uint32_t)interp_smem_bytes(s->plan.q_pitch, s->plan.num_qubits, s->K_max, s->chunk_words, s->n_noise);
     });
 }
 

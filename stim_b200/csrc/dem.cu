@@ -7,12 +7,18 @@
 // Bernoulli(p) row over the shots; its targets' rows (detectors, observables) are XORed with it.
 //
 // Device side: one thread walks one error mechanism over the K * 128 shots of a shot block with geometric gaps (the
-// gap arithmetic of the circuit sampler, program.h "Gap arithmetic": floor(Exp(1) / lambda) == Geometric(p), the
-// reference's RareErrorIterator, probability_util.cc:33-43) and flips the bits of the mechanism's target rows in the
+// 32-bit gap arithmetic below: floor(Exp(1) / lambda) == Geometric(p), the reference's RareErrorIterator,
+// probability_util.cc:33-43) and flips the bits of the mechanism's target rows in the
 // block's columns of a column-major bit table with red.global.xor (the table stays L2-resident). The table then goes
 // through the same transposer / counters / writers as the circuit sampler's.
-//   Philox counter of call c of error e in the shot block whose first column is col0:
+//   Shot blocks are 32 columns (4096 shots) wide, whatever the request. Philox counter of call c of error e in the shot
+//   block whose first column is col0:
 //       (e, 'DEMS', col0 lo, col0 hi | c << 15)  ->  four gap words (draws 4c .. 4c + 3).
+//   Gap arithmetic (all integer, restated bit for bit by oracle/philox.py: exp_draw_q26 / gap_of):
+//       E   = -ln(v / 2^32), v = word | 1, in units of 2^-26 nat: 256-entry log2 table (Q26 base + forward difference),
+//             13-bit linear interpolation, one multiply-high by ln 2 (Q32)
+//       gap = (E * INV) >> SH as a 64-bit product, INV = floor(2^32 m), SH = 58 - e for 1 / lambda = m 2^e, lambda = -log1p(-p)
+//       p >= 1: INV = 0 (an event at every shot); p below 2^-58 is treated as 0.
 #include <cuda_runtime.h>
 #include <unistd.h>
 
@@ -32,11 +38,12 @@
 #include "writers.h"
 
 #define GSTIM_TABLE_QUAL __device__ const
-#include "log2_table.h"
+#include "log2_q26_table.h"
 
 namespace gstim {
 
 #define GTAG_DEM 0x44454D53u
+#define GSTIM_DEM_BLOCK_COLS 32u
 
 // ------------------------------------------------------------------------------------------------
 // host: the model
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(256, 4) gstim_dem_kernel(const DemParams p) {
                     if (done) {
                         break;
                     }
-                    // exp_draw_q26 (program.h "Gap arithmetic"; interp.cu has the shared-memory twin)
+                    // exp_draw_q26 (header comment)
                     const uint32_t v = words[j] | 1u;
                     const uint32_t t = 31u - (uint32_t)__clz((int)v);
                     const uint32_t frac = (v << (31u - t)) << 1;
@@ -467,8 +474,8 @@ void dem_run(gstim_dem_sampler *s, uint64_t shots, bool record_errors, SINK &&si
     }
     const uint32_t rows = (uint32_t)rows64;
     const uint64_t cols = (shots + GSTIM_COL_SHOTS - 1) / GSTIM_COL_SHOTS;
-    // columns per block: enough blocks to fill the device a few times over, at most 32 columns (4096 shots)
-    uint32_t K = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, cols / ((uint64_t)8 * s->num_sms)));
+    // A shot block is always 32 columns (4096 shots): the random stream then depends on (seed, shot offset) only.
+    const uint32_t K = GSTIM_DEM_BLOCK_COLS;
     const uint64_t bytes_per_block = (uint64_t)rows * K * 16;
     const uint64_t total_blocks = (cols + K - 1) / K;
     const uint64_t budget = 1ull << 30;
@@ -645,6 +652,30 @@ int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void 
                 }
             }
         });
+    });
+}
+
+int gstim_dem_bit_counts(gstim_dem_sampler *s, uint64_t shots, uint64_t *single_host, uint64_t *pair_host) {
+    return dem_guarded([&] {
+        if (s == nullptr) {
+            throw std::invalid_argument("NULL sampler.");
+        }
+        const uint32_t n = (uint32_t)(s->model.num_detectors + s->model.num_observables);
+        ck(cudaSetDevice(s->device), "cudaSetDevice");
+        DevMem counts;
+        counts.ensure((size_t)std::max<uint32_t>(n, 1) * 16);
+        ck(cudaMemsetAsync(counts.p, 0, (size_t)std::max<uint32_t>(n, 1) * 16, s->stream), "memset");
+        unsigned long long *d_single = (unsigned long long *)counts.p, *d_pair = d_single + n;
+        dem_run(s, shots, false, [&](uint64_t first, uint64_t cnt, const uint32_t *table, uint64_t n_rows) {
+            (void)first;
+            ck(launch_bit_counts(table, n_rows, cnt, nullptr, n, d_single, pair_host ? d_pair : nullptr, s->stream), "bit counts");
+        });
+        if (single_host && n) {
+            ck(cudaMemcpy(single_host, d_single, (size_t)n * 8, cudaMemcpyDeviceToHost), "D2H");
+        }
+        if (pair_host && n > 1) {
+            ck(cudaMemcpy(pair_host, d_pair, (size_t)(n - 1) * 8, cudaMemcpyDeviceToHost), "D2H");
+        }
     });
 }
 

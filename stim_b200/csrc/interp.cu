@@ -4,9 +4,7 @@
 // as uint4 (128-shot) columns, the lowered program (program.h) is streamed through a two-stage
 // shared-memory ring by bulk-async (TMA 1D, cp.async.bulk + mbarrier) copies, and every batch of the
 // program is executed by all threads: item i by thread group i % slots, one lane per 128-shot column
-// (or G lanes per item splitting the columns). Pauli noise is pre-sampled by the block's producer warps (one shot
-// block ahead) into one event line per RNG slice, and applied by the warp that owns the slice's 32 items right
-// before / after it executes them (program.h: attached noise) - no block barrier, no second item list.
+// (or G lanes per item splitting the columns).
 //
 // Replaces FrameSimulator<W>::do_circuit / do_gate and the per-gate row loops
 // (/root/reference/src/stim/simulators/frame_simulator.inl:166-170, 173-912), RareErrorIterator
@@ -179,95 +177,122 @@ __device__ __forceinline__ uint32_t bitmask(uint32_t aux, int bit) {
 struct __align__(16) BlockCtx {
     uint32_t X_s, Z_s;        // shared-window byte addresses of the frame planes: plane[k][row] as uint4
     uint32_t flag_s;          // correlated-error flag row (K uint4)
-    uint32_t lt_s;            // log2 table: 256 x (base, diff) in Q26
-    uint32_t rates_s;         // the first GSTIM_RATE_SMEM_MAX rates: (INV, SH)
+    uint32_t lt_s;            // log2 table (512 u32)
+    uint32_t needs_s;         // per rate class: min(B * rate, 2^63) (32 u64), followed by the 32 rates themselves
     uint32_t pitch_b;         // bytes between consecutive columns of a plane (q_pitch * 16)
     uint32_t K, B, G_log2, slots;
     uint32_t k0, k1;          // Philox key
     uint32_t col0_lo, col0_hi;  // global column index of this block's first column
-    uint32_t rec_mask, stage_s;  // stage_s: per interpreter warp 2 x 128 bytes, the staged event line of the current / next noise application
+    uint32_t rec_mask, pad0;
     uint4 *rec;               // this block's record rows
     uint4 *out;               // this block's output columns
     uint64_t rec_k_stride, out_k_stride;  // uint4 units between the 128-shot columns of a record / output row (rows are contiguous)
-    const uint32_t *ev_buf;     // this shot block's event buffer: n_slices lines of 32 words, then the overflow segments
-    const uint32_t *ev_ovf_off; // n_slices + 1: overflow segment offsets (words, relative to the end of the lines)
-    // noise schedule (read by the producers)
+    const uint32_t *ev_segoff;  // event segment offsets per noise batch
+    uint32_t *ev_counts;        // this CTA's event counters
+    uint32_t *ev_buf;           // this CTA's event records
+    // noise schedule (read by the pre-pass)
     const uint4 *slices;
-    const uint2 *rates;
-    const uint32_t *tables;
+    const ulonglong2 *rates;
+    const uint32_t *noise_info, *prog;
     uint32_t *ev_overflow;
-    uint32_t n_slices, T_i;            // T_i: interpreter threads (the remaining warps of the block produce noise events)
-    uint32_t next_s, pad0;             // shared counter the producer threads claim slices from
+    uint32_t n_slices, pad5;
+    uint32_t n_noise, T_i;             // T_i: interpreter threads (the remaining warps of the block produce noise events)
+    uint32_t next_s;                   // shared counter the pre-pass threads claim chains from
+    uint32_t ev_counts_s, ev_segoff_s; // shared-window addresses of the event counters / segment offsets (0: global)
+    uint32_t stage_s;                  // 2 x GSTIM_EV_STAGE event records prefetched for the current / next noise batch
     unsigned long long *dbg;  // optional cycle counters (block 0 only)
     uint32_t dbg_flags, pad2;
-    // launch-wide constants of the two role loops
+    // launch-wide constants of the two role loops (interp_role / producer_role)
     uint32_t n_blocks, n_chunks, chunk_words, T_all;
-    uint32_t mbar_s, pad3;
-    uint64_t ev_total;        // words per event buffer
+    uint32_t mbar_s, ev_s, ev_total, pad4;  // ev_s: shared-window address of the event counters (two buffers), 0 if in global memory
     uint32_t *ring;
     uint64_t col0_base;
     uint4 *rec_base, *out_base;
     uint64_t rec_block_stride, rec_cta_stride;
-    uint32_t *ev_buf_g;       // this CTA's two event buffers
+    uint32_t *ev_counts_g, *ev_buf_g;
 };
 
-size_t interp_smem_bytes(uint32_t q_pitch, uint32_t K, uint32_t chunk_words, uint32_t interp_threads) {
+size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t n_noise) {
+    (void)Q;
     size_t b = 0;
     b += (size_t)2 * K * q_pitch * 16;  // X, Z
     b += (size_t)K * 16;                // correlated-error flag row
     b += (size_t)2 * chunk_words * 4;   // program ring
     b += 512 * 4;                       // log2 table
-    b += GSTIM_RATE_SMEM_MAX * 8;       // the first rates: INV, SH
-    b += (size_t)((interp_threads + 31) / 32) * 2 * GSTIM_EV_LINE_WORDS * 4;  // staged event lines, two per interpreter warp
+    b += 128 * 8;                       // the first GSTIM_RATE_SMEM_MAX rates: lam, floor((2^64 - 1) / lam)
+    if (n_noise <= GSTIM_EV_SMEM_MAX) {
+        b += ((size_t)(3 * n_noise + 1) * 4 + 15) / 16 * 16;  // event counters (two buffers) + segment offsets
+    }
+    b += 2 * GSTIM_EV_STAGE * 4;        // staged event records of the current / next noise batch
     b += 32;                            // mbarriers
     b += (sizeof(BlockCtx) + 15) / 16 * 16;
     return b;
 }
 
-// Exp(1) variate from a uniform u32 in fixed point (unit 2^-26 nat): -ln(v / 2^32), v = r | 1, through a 256-entry log2
-// table with 13-bit linear interpolation (max error 2e-6 nat) and one multiply-high by ln 2. Integer-only, so the oracle
-// (oracle/philox.py: exp_draw_q26) reproduces it bit for bit. lt_s: table in shared memory, entry i = (base, diff).
-__device__ __forceinline__ uint32_t exp_draw_q26(uint32_t r, uint32_t lt_s) {
-    const uint32_t v = r | 1u;
-    const uint32_t t = 31u - (uint32_t)__clz((int)v);  // floor(log2 v), 0..31
-    const uint32_t frac = (v << (31u - t)) << 1;       // bits below the leading one, left aligned
-    const unsigned long long e = lds64(lt_s + 8u * (frac >> 24));
-    const uint32_t log2v = (t << 26) + (uint32_t)e + (((uint32_t)(e >> 32) * ((frac >> 11) & 0x1FFFu)) >> 13);
-    return __umulhi(0x80000000u - log2v, GSTIM_LN2_Q32);
+// Exp(1) variate from a uniform u32 in fixed point (unit 2^-56 nat): -ln((r + 1/2) / 2^32) through a
+// 256-entry log2 table with linear interpolation (max error 2e-6 nat). Integer-only, so the oracle
+// (oracle/philox.py: exp_draw_fx) reproduces it bit for bit. lt_s: table in shared memory: base[256], diff[256].
+__device__ __forceinline__ unsigned long long exp_draw_fx(uint32_t r, uint32_t lt_s) {
+    const unsigned long long v = 2ull * r + 1ull;     // odd, < 2^33
+    const int t = 63 - __clzll((long long)v);         // floor(log2 v), 0..32
+    const uint32_t frac = (uint32_t)(v << (32 - t));  // bits below the leading one, left aligned
+    const uint32_t i = frac >> 24, f = frac & 0xFFFFFFu;
+    const unsigned long long log2m = (unsigned long long)lds32(lt_s + 4 * i) + (((unsigned long long)lds32(lt_s + 1024 + 4 * i) * f) >> 24);
+    const unsigned long long lv = ((unsigned long long)t << 32) + log2m;
+    return ((33ull << 32) - lv) * (unsigned long long)GSTIM_LN2_Q24;
+}
+
+__device__ __forceinline__ unsigned long long sat_mul(uint32_t n, unsigned long long lam) {
+    // min(n * lam, 2^63)
+    const unsigned long long lo = (unsigned long long)n * lam, hi = __umul64hi((unsigned long long)n, lam);
+    return (hi != 0 || lo >= (1ull << 63)) ? (1ull << 63) : lo;
+}
+
+__device__ __forceinline__ void flip_plane(const BlockCtx *bc, uint32_t plane_s, uint32_t row, uint32_t shot) {
+    const uint32_t a = plane_s + (shot >> 7) * bc->pitch_b + row * 16 + ((shot >> 5) & 3) * 4;
+    sts32(a, lds32(a) ^ (1u << (shot & 31)));
+}
+__device__ __forceinline__ void flip_rec(const BlockCtx *bc, uint32_t rec_index, uint32_t shot) {
+    uint32_t *w = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + (rec_index & bc->rec_mask)) + ((shot >> 5) & 3);
+    *w ^= 1u << (shot & 31);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Noise producers. Event positions and Pauli choices never depend on the frame, so the noise of a whole shot block is
-// sampled ahead of its interpretation. The sites of a noise group are cut into slices of GSTIM_NOISE_SLICE sites
-// (program.h "Noise schedule"); a slice x this shot block is one Bernoulli sequence with its own Philox stream. Threads
-// claim slices from a shared counter and walk them with geometric gaps: every loop iteration is one Philox call -> two
-// draws (gap to the slice's next event, that event's Pauli word), so all lanes of a warp do the same work each
-// iteration and idle only at the very end. A slice's records go to the slice's own 128-byte line of this CTA's
-// (L2-resident) event buffer - count in word 0, records behind it, the rare 32nd+ record in the slice's overflow
-// segment - where the one interpreter warp that owns the slice's items picks them up.
+// Noise event pre-pass. Event positions and Pauli choices never depend on the frame, so before a shot block
+// is interpreted every noise site of the whole program is sampled up front. The sites of a noise group are
+// cut into slices of GSTIM_NOISE_SLICE sites (program.h "Noise schedule"); a slice x this shot block is one
+// Bernoulli sequence with its own Philox stream. Threads claim slices from a shared counter and walk them with
+// geometric gaps: every loop iteration is one Philox call -> two draws (gap to the slice's next event, that
+// event's Pauli word), so all lanes of a warp do the same work each iteration and idle only at the very end.
+// Lanes of a warp work on neighbouring slices, i.e. mostly on the same noise batch: a record takes its place
+// with one shared-memory atomic on the batch's counter, and the places of neighbouring lanes are mostly
+// consecutive, so the stores into this CTA's (L2-resident) scratch coalesce; one segment per noise batch.
+// The interpreter then only applies flips.
 //
 // Distribution == RareErrorIterator (/root/reference/src/stim/util_bot/probability_util.cc:33-43):
-// gaps are floor(Exp(1)/lambda) = Geometric(p), in integer arithmetic (program.h "Gap arithmetic").
+// gaps are floor(Exp(1)/lambda) = Geometric(p), in exact integer arithmetic (unit 2^-56 nat).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t atom_add_shared(uint32_t a, uint32_t v) {
     uint32_t old;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
     return old;
 }
-__device__ __forceinline__ void stg32(uint32_t *p, uint32_t v) {
-    asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// L2-coherent loads of the event buffers (they are rewritten every other shot block: never through L1)
-__device__ __forceinline__ uint32_t ldcg32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
+
+// floor(E / lam) with inv = floor((2^64 - 1) / lam): the multiply-high estimate is never above and at most one below.
+__device__ __forceinline__ unsigned long long div_by_rate(unsigned long long E, unsigned long long lam, unsigned long long inv) {
+    unsigned long long q = __umul64hi(E, inv);
+    if (E - q * lam >= lam) {
+        q++;
+    }
+    return q;
 }
 
 // Per-run arguments of the producers (the interpreter is working on another shot block at the same time).
 struct PrepassRun {
     uint32_t col0_lo, col0_hi;  // first global column of the shot block
-    uint32_t *evbuf;            // the event buffer to fill
+    uint32_t cnt_s;             // shared-window address of this buffer's event counters (0: use `counts`)
+    uint32_t *counts;
+    uint32_t *evbuf;
     uint32_t tid, threads;      // this thread's index among the threads that walk the slices, and how many there are
     uint32_t whole_block;       // 1: every thread of the block takes part (first shot block of a launch), barrier 0
 };
@@ -281,54 +306,52 @@ __device__ __forceinline__ void prepass_sync(const PrepassRun &run) {
 }
 
 __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun run) {
+    const uint32_t T_p = run.threads;
     const uint32_t tid = run.tid;
     const uint32_t next_s = bc->next_s;
-    uint32_t *const evbuf = run.evbuf;
+    const uint32_t n_noise = bc->n_noise;
+    const uint32_t cnt_s = run.cnt_s, segoff_s = bc->ev_segoff_s;
+    uint32_t *evbuf = run.evbuf;
+    // (rarely used pointers are re-read from the BlockCtx where they are needed: registers are what limits this loop)
+    for (uint32_t i = tid; i < n_noise; i += T_p) {
+        if (cnt_s) {
+            sts32(cnt_s + 4 * i, 0);
+        } else {
+            run.counts[i] = 0;
+        }
+    }
     if (tid == 0) {
         sts32(next_s, 0);
     }
     prepass_sync(run);
 
     const uint4 *slices = bc->slices;
-    const uint32_t n_slices = bc->n_slices;
-    const uint32_t *ovf_off = bc->ev_ovf_off;
-    uint32_t *const ovf_base = evbuf + (size_t)GSTIM_EV_LINE_WORDS * n_slices;
-    if (bc->dbg_flags & 1u) {  // timing experiments: no events at all
-        for (uint32_t sl = tid; sl < n_slices; sl += run.threads) {
-            stg32(evbuf + (size_t)GSTIM_EV_LINE_WORDS * sl, 0u);
-        }
-        __threadfence();
-        prepass_sync(run);
-        return;
-    }
-    const uint32_t B = bc->B, lt_s = bc->lt_s, rates_s = bc->rates_s;
+    const uint32_t n_slices = (bc->dbg_flags & 1u) ? 0u : bc->n_slices;
+    const uint32_t B = bc->B, lt_s = bc->lt_s, rates_s = bc->needs_s;
     const uint32_t magicB = 0xFFFFFFFFu / B + 1;  // floor(a / B) == umulhi(a, magicB) for a < 2^20 (B <= 4096)
     const uint32_t k0 = bc->k0, k1 = bc->k1, col0_lo = run.col0_lo, col0_hi = run.col0_hi;
 
-    const bool dbg_on = tid == 0 && bc->dbg != nullptr;
+    const bool dbg_on = tid == 0 && !(bc->dbg_flags & 1u) && bc->dbg != nullptr;
     const uint32_t tA = (uint32_t)clock64();
     uint32_t n_ev = 0, n_iter = 0, n_sl = 0;
 
-    uint32_t grp = 0, sl1 = 0, total = 0, a = 0, d = 0, n = 0, ovf_cap = 0, inv = 0, sh = 0;
-    uint32_t *line = evbuf, *ovf = evbuf;
-    uint4 bh = make_uint4(0, 0, 0, 0);  // of the slice's noise: op | flags << 8 | aux << 16, T1, T2, T3
+    uint32_t grp = 0, sl1 = 0, nbi = 0, item0 = 0, total = 0, a = 0, d = 0;
+    uint4 bh = make_uint4(0, 0, 0, 0);  // of the slice's batch: op | flags << 8 | aux << 16, T1, T2, T3
+    unsigned long long lam = 1, inv = 0;
     // the next slice is claimed and its descriptor fetched while the current one is walked
     uint32_t nidx = atom_add_shared(next_s, 1);
     uint4 nd = make_uint4(0, 0, 0, 0), nh = nd;
-    uint32_t no0 = 0, no1 = 0;
     if (nidx < n_slices) {
         nd = __ldg(slices + 2 * (size_t)nidx);
         nh = __ldg(slices + 2 * (size_t)nidx + 1);
-        no0 = __ldg(ovf_off + nidx);
-        no1 = __ldg(ovf_off + nidx + 1);
     }
     bool have = false;
     // An event record is written one event late: two consecutive events of a slice that flip the same 32-bit
-    // frame words (same site, same 32-shot word) both get GSTIM_EV_CONFLICT, and only those are applied with
+    // frame words (same item, same 32-shot word) both get GSTIM_EV_CONFLICT, and only those are applied with
     // shared-memory atomics (2 cycles per lane on the LSU) by the interpreter; everything else is plain.
     bool pend = false;
     uint32_t pend_rec = 0;
-    const uint32_t same_word_mask = (31u << GSTIM_EV_SITE_SHIFT) | 0xFE0u;
+    const uint32_t same_word_mask = (GSTIM_EV_ITEM_MASK << GSTIM_EV_ITEM_SHIFT) | 0xFE0u;
 
     // record of the event at shot-site `at` of the current slice, Pauli word y
     auto make_rec = [&](uint32_t at, uint32_t y) -> uint32_t {
@@ -346,7 +369,7 @@ __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun 
             if (!(flags & GF_TABLE)) {
                 f = 1u + __umulhi(y, 15u);  // uniform over the 15 non-identity pairs (frame_simulator.inl:651-659)
             } else {
-                const uint32_t *tab = bc->tables + bh.y;
+                const uint32_t *tab = bc->prog + __ldg(bc->noise_info + (size_t)nbi * GSTIM_NOISE_INFO_WORDS + GNI_TABLE_OFF);
                 uint32_t pr = aux;
                 for (uint32_t t = 0; t < 15; t++) {
                     if (y < __ldg(tab + t)) {
@@ -359,101 +382,115 @@ __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun 
                 f = (((c1p + 1) >> 1) & 1u) | ((c1p >> 1) << 1) | ((((c2p + 1) >> 1) & 1u) << 2) | ((c2p >> 1) << 3);
             }
         }
-        return shot | (site << GSTIM_EV_SITE_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
+        return shot | ((item0 + site) << GSTIM_EV_ITEM_SHIFT) | (f << GSTIM_EV_FLIP_SHIFT);
     };
-    // append a record to the current slice
+    // append a record to its noise batch's segment (lanes of a warp work on neighbouring slices, so the places they
+    // get are mostly consecutive and the stores coalesce)
     auto emit = [&](uint32_t rec) {
-        const uint32_t idx = n++;
-        if (idx < GSTIM_EV_LINE_WORDS - 1) {
-            stg32(line + 1 + idx, rec);
-        } else if (idx - (GSTIM_EV_LINE_WORDS - 1) < ovf_cap) {
-            stg32(ovf + (idx - (GSTIM_EV_LINE_WORDS - 1)), rec);
-        }  // (an overflowing slice is reported when its count is written)
+        uint32_t seg0, cap, at;
+        if (cnt_s) {
+            seg0 = lds32(segoff_s + 4 * nbi);
+            cap = lds32(segoff_s + 4 * nbi + 4) - seg0;
+            at = atom_add_shared(cnt_s + 4 * nbi, 1u);
+        } else {
+            seg0 = bc->ev_segoff[nbi];
+            cap = bc->ev_segoff[nbi + 1] - seg0;
+            at = atomicAdd(&run.counts[nbi], 1u);
+        }
+        if (at < cap) {  // (an overflowing segment is reported after the pre-pass)
+            evbuf[seg0 + at] = rec;
+        }
     };
 
     while (true) {
+        bool live = true;
         if (!have) {
             if (nidx >= n_slices) {
-                break;
-            }
-            grp = nd.x;
-            sl1 = nd.y | GSTIM_SLICE_FLAG;
-            total = (nd.z >> 16) * B;
-            bh = make_uint4(nd.w, nh.x, nh.y, nh.z);
-            line = evbuf + (size_t)GSTIM_EV_LINE_WORDS * nidx;
-            ovf = ovf_base + no0;
-            ovf_cap = no1 - no0;
-            a = 0;
-            d = 0;
-            n = 0;
-            const uint32_t ri = nd.z & 0xFFFFu;
-            if (ri < GSTIM_RATE_SMEM_MAX) {
-                const unsigned long long r = lds64(rates_s + 8 * ri);
-                inv = (uint32_t)r;
-                sh = (uint32_t)(r >> 32);
+                if (!pend) {
+                    break;
+                }
+                live = false;
             } else {
-                const uint2 r = __ldg(bc->rates + ri);
-                inv = r.x;
-                sh = r.y;
-            }
-            have = true;
-            n_sl++;
-            nidx = atom_add_shared(next_s, 1);
-            if (nidx < n_slices) {
-                nd = __ldg(slices + 2 * (size_t)nidx);
-                nh = __ldg(slices + 2 * (size_t)nidx + 1);
-                no0 = __ldg(ovf_off + nidx);
-                no1 = __ldg(ovf_off + nidx + 1);
+                grp = nd.x;
+                sl1 = nd.y | GSTIM_SLICE_FLAG;
+                nbi = nd.z & 0xFFFFu;
+                item0 = nd.w & 0x7FFu;
+                total = (nd.w >> 11) * B;
+                bh = nh;
+                a = 0;
+                d = 0;
+                const uint32_t ri = nd.z >> 16;
+                if (ri < GSTIM_RATE_SMEM_MAX) {
+                    lam = lds64(rates_s + 16 * ri);
+                    inv = lds64(rates_s + 16 * ri + 8);
+                } else {
+                    const ulonglong2 r = __ldg(bc->rates + ri);
+                    lam = r.x;
+                    inv = r.y;
+                }
+                have = true;
+                n_sl++;
+                nidx = atom_add_shared(next_s, 1);
+                if (nidx < n_slices) {
+                    nd = __ldg(slices + 2 * (size_t)nidx);
+                    nh = __ldg(slices + 2 * (size_t)nidx + 1);
+                }
             }
         }
-        n_iter++;
-        // one Philox call = two draws (gap word, Pauli word): their gap arithmetic is independent of the
-        // position in the slice, so both are computed side by side and resolved in order afterwards
-        const uint4 rr = philox4x32_10(grp, sl1, col0_lo, col0_hi | (d << GSTIM_DRAW_SHIFT), k0, k1);
-        d++;
-        const unsigned long long G0 = ((unsigned long long)exp_draw_q26(rr.x, lt_s) * inv) >> sh;
-        const unsigned long long G1 = ((unsigned long long)exp_draw_q26(rr.z, lt_s) * inv) >> sh;
-        bool end = true;
-        if (G0 < (unsigned long long)(total - a)) {  // (else: no further event in this slice, the second draw is dropped)
-            a += (uint32_t)G0;
-            uint32_t r0 = make_rec(a, rr.y);
-            a++;
-            n_ev++;
-            if (pend) {
-                if (((r0 ^ pend_rec) & same_word_mask) == 0) {
-                    r0 |= GSTIM_EV_CONFLICT;
-                    pend_rec |= GSTIM_EV_CONFLICT;
-                }
-                emit(pend_rec);
-            }
-            pend = true;
-            pend_rec = r0;
-            if (G1 < (unsigned long long)(total - a)) {
-                a += (uint32_t)G1;
-                uint32_t r1 = make_rec(a, rr.w);
+        // records to write this iteration: the pending one and the first of up to two new events
+        bool has0 = false, has1 = false;
+        uint32_t out0 = 0, out1 = 0;
+        if (live) {
+            n_iter++;
+            // one Philox call = two draws (gap word, Pauli word): their clock arithmetic is independent of the
+            // position in the slice, so both are computed side by side and resolved in order afterwards
+            const uint4 rr = philox4x32_10(grp, sl1, col0_lo, col0_hi | (d << GSTIM_DRAW_SHIFT), k0, k1);
+            d++;
+            const unsigned long long G0 = div_by_rate(exp_draw_fx(rr.x, lt_s), lam, inv);
+            const unsigned long long G1 = div_by_rate(exp_draw_fx(rr.z, lt_s), lam, inv);
+            has0 = pend;
+            out0 = pend_rec;
+            pend = false;
+            if (G0 >= (unsigned long long)(total - a)) {  // no further event in this slice (the second draw is dropped)
+                have = false;
+            } else {
+                a += (uint32_t)G0;
+                uint32_t r0 = make_rec(a, rr.y);
                 a++;
-                n_ev++;
-                if (((r1 ^ pend_rec) & same_word_mask) == 0) {
-                    r1 |= GSTIM_EV_CONFLICT;
-                    pend_rec |= GSTIM_EV_CONFLICT;
+                if (has0 && ((r0 ^ out0) & same_word_mask) == 0) {
+                    r0 |= GSTIM_EV_CONFLICT;
+                    out0 |= GSTIM_EV_CONFLICT;
                 }
-                emit(pend_rec);
-                pend_rec = r1;
-                end = false;
+                n_ev++;
+                if (G1 >= (unsigned long long)(total - a)) {
+                    have = false;
+                    has1 = true;
+                    out1 = r0;
+                } else {
+                    a += (uint32_t)G1;
+                    uint32_t r1 = make_rec(a, rr.w);
+                    a++;
+                    if (((r1 ^ r0) & same_word_mask) == 0) {
+                        r1 |= GSTIM_EV_CONFLICT;
+                        r0 |= GSTIM_EV_CONFLICT;
+                    }
+                    n_ev++;
+                    has1 = true;
+                    out1 = r0;
+                    pend = true;
+                    pend_rec = r1;
+                }
             }
+        } else {
+            has0 = true;
+            out0 = pend_rec;
+            pend = false;
         }
-        if (end) {
-            if (pend) {
-                emit(pend_rec);
-                pend = false;
-            }
-            const uint32_t cap = GSTIM_EV_LINE_WORDS - 1 + ovf_cap;
-            if (n > cap) {
-                n = cap;
-                *bc->ev_overflow = 1u;  // invalidates the call: the host reports it
-            }
-            stg32(line, n);
-            have = false;
+        if (has0) {
+            emit(out0);
+        }
+        if (has1) {
+            emit(out1);
         }
     }
     if (dbg_on) {
@@ -462,11 +499,20 @@ __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun 
         bc->dbg[34] += n_sl;
         bc->dbg[35] += n_iter;
     }
-    // The interpreter warps read the lines past L1 (cp.async.cg / ld.global.cg: a buffer is rewritten every other shot
-    // block, L1 may hold its previous contents), so the records must have reached L2 before the hand-over barrier:
-    // a gpu-scope fence, not a cta-scope one.
-    __threadfence();
     prepass_sync(run);
+    // clamp the event counts to their segments (an overflow invalidates the call: the host reports it)
+    for (uint32_t i = tid; i < n_noise; i += T_p) {
+        const uint32_t cap = segoff_s ? lds32(segoff_s + 4 * i + 4) - lds32(segoff_s + 4 * i) : bc->ev_segoff[i + 1] - bc->ev_segoff[i];
+        const uint32_t c = cnt_s ? lds32(cnt_s + 4 * i) : run.counts[i];
+        if (c > cap) {
+            if (cnt_s) {
+                sts32(cnt_s + 4 * i, cap);
+            } else {
+                run.counts[i] = cap;
+            }
+            *bc->ev_overflow = 1u;
+        }
+    }
 }
 
 #define SLOT_SUB                                      \
@@ -478,168 +524,6 @@ __device__ __noinline__ void noise_prepass(const BlockCtx *bc, const PrepassRun 
     const uint32_t pitch_b = bc->pitch_b;             \
     const uint32_t X_s = bc->X_s;                     \
     const uint32_t kstep = pitch_b << G_log2
-
-// ------------------------------------------------------------------------------------------------
-// Noise application (warp-local). A noise application = ceil(n / 32) consecutive RNG slices over the n items of a batch;
-// the warp that executes items base .. base + ipw - 1 (ipw = 32 >> G_log2 items per warp; they never straddle a slice)
-// applies the events of the slice that holds them, in the same program position as its own items: only the warp has to
-// re-converge (__syncwarp orders its shared / global accesses), never the block. The event line of a warp's first trip
-// is copied into the warp's staging buffer (cp.async, LDGSTS) one application ahead, so no L2 latency sits in the way:
-// every application names the first slice of the next one (GH_*_NEXT); staging buffer = parity of the application.
-// Two events of one slice touch the same 32-bit frame word only when the producer marked both GSTIM_EV_CONFLICT; only
-// those use shared-memory atomics.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void flip_atomic(uint32_t a, uint32_t bit) {
-    asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(bit) : "memory");
-}
-__device__ __forceinline__ void flip_plane(const BlockCtx *bc, uint32_t plane_s, uint32_t row, uint32_t shot) {
-    const uint32_t a = plane_s + (shot >> 7) * bc->pitch_b + row * 16 + ((shot >> 5) & 3) * 4;
-    sts32(a, lds32(a) ^ (1u << (shot & 31)));
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-
-// Starts the copy of event line `slice` into this warp's staging buffer `parity` (lanes 0-7 move 16 bytes each).
-__device__ __forceinline__ void stage_line(const BlockCtx *bc, uint32_t slice, uint32_t parity) {
-    const uint32_t lane = threadIdx.x & 31u;
-    if (lane < 8 && slice < bc->n_slices) {
-        const uint32_t st = bc->stage_s + ((threadIdx.x >> 5) * 2 + parity) * (GSTIM_EV_LINE_WORDS * 4) + 16 * lane;
-        const uint32_t *src = bc->ev_buf + (size_t)GSTIM_EV_LINE_WORDS * slice + 4 * lane;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-// First item this warp executes in trip 0 of a batch.
-__device__ __forceinline__ uint32_t warp_first_item(const BlockCtx *bc) {
-    return (threadIdx.x >> 5) << (5 - bc->G_log2);
-}
-
-// Every warp, at every noise application: the line staged for it has landed; start staging the next application's.
-__device__ __forceinline__ void noise_chain_step(const BlockCtx *bc, uint32_t att, uint32_t next) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    if (next != GSTIM_NO_NOISE) {
-        // (first slice of the 32-item group this warp's first items belong to: next = first slice | log2(slices per group) << 28)
-        stage_line(bc, (next & 0x0FFFFFFFu) + ((warp_first_item(bc) >> 5) << (next >> 28)), (att >> 31) ^ 1u);
-    }
-}
-
-// Applies the events of application `att` (slices of 2^w sites) to the n items at items_s (stride words per item; word =
-// row1 | row2 << 16), perm_s: byte table site -> position inside the 32-item group (0: identity), rec0: record row of item 0.
-__device__ __forceinline__ void noise_apply(const BlockCtx *bc, uint32_t att, uint32_t next, uint32_t n, uint32_t items_s, uint32_t stride,
-                                            uint32_t perm_s, uint32_t rec0, uint32_t w) {
-    noise_chain_step(bc, att, next);
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t ipw_log2 = 5 - bc->G_log2, ipw = 1u << ipw_log2;
-    const uint32_t slice0 = att & 0x7FFFFFFFu;
-    const uint32_t st = bc->stage_s + ((threadIdx.x >> 5) * 2 + (att >> 31)) * (GSTIM_EV_LINE_WORDS * 4);
-    const uint32_t X_s = bc->X_s, zoff = bc->Z_s - bc->X_s, pitch_b = bc->pitch_b, slots = bc->slots;
-    uint32_t trip = 0;
-    const uint32_t lpg = 5 - w;  // log2(slices per group of 32 items)
-    for (uint32_t base = warp_first_item(bc); base < n; base += slots, trip++) {
-      const uint32_t grp = base >> 5, sub_lo = base & 31u;
-      // the slices that can hold events for this warp's positions base .. base + ipw - 1: those of its own item indices, or
-      // (when a permutation maps sites to positions) every slice of the 32-item group
-      const uint32_t j_lo = perm_s ? 0u : (sub_lo >> w), j_hi = perm_s ? ((32u >> w) - 1) : ((sub_lo + ipw - 1) >> w);
-      for (uint32_t j = j_lo; j <= j_hi && grp * 32 + (j << w) < n; j++) {
-        const uint32_t sl_rel = (grp << lpg) + j, it0 = grp * 32 + (j << w);
-        const uint32_t *line = bc->ev_buf + (size_t)GSTIM_EV_LINE_WORDS * (slice0 + sl_rel);
-        const bool staged = trip == 0 && j == 0;  // (the chain staged the first slice of the warp's group)
-        const uint32_t cnt = staged ? lds32(st) : ldcg32(line);
-        for (uint32_t idx = 1 + lane; idx <= cnt; idx += 32) {
-            uint32_t rec;
-            if (idx < GSTIM_EV_LINE_WORDS) {
-                rec = staged ? lds32(st + 4 * idx) : ldcg32(line + idx);
-            } else {
-                rec = ldcg32(bc->ev_buf + (size_t)GSTIM_EV_LINE_WORDS * bc->n_slices + __ldg(bc->ev_ovf_off + slice0 + sl_rel) + (idx - GSTIM_EV_LINE_WORDS));
-            }
-            const uint32_t site = (rec >> GSTIM_EV_SITE_SHIFT) & 31u;
-            const uint32_t it = it0 + site;
-            // position of the hit item in the batch: the warp that EXECUTES that position applies the event (with several
-            // lanes per item the slice is shared with neighbouring warps, and a bank-spreading permutation may have moved
-            // the item to another warp of the 32-item group)
-            const uint32_t pos_in_group = perm_s ? lds8(perm_s + it) : (it & 31u);
-            if (pos_in_group - sub_lo >= ipw) {
-                continue;
-            }
-            const uint32_t shot = rec & ((1u << GSTIM_EV_SHOT_BITS) - 1);
-            const uint32_t f = (rec >> GSTIM_EV_FLIP_SHIFT) & 31u;
-            const uint32_t pos = grp * 32 + pos_in_group;
-            const uint32_t iw = lds32(items_s + 4 * stride * pos);
-            const uint32_t bit = 1u << (shot & 31);
-            const uint32_t a0 = X_s + (shot >> 7) * pitch_b + ((shot >> 5) & 3) * 4;
-            const uint32_t a1 = a0 + (iw & 0xFFFF) * 16, a2 = a0 + (iw >> 16) * 16;
-            if (rec & GSTIM_EV_CONFLICT) {
-                if (f & 1u) {
-                    flip_atomic(a1, bit);
-                }
-                if (f & 2u) {
-                    flip_atomic(a1 + zoff, bit);
-                }
-                if (f & 4u) {
-                    flip_atomic(a2, bit);
-                }
-                if (f & 8u) {
-                    flip_atomic(a2 + zoff, bit);
-                }
-                if (f & 16u) {
-                    uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + ((rec0 + it) & bc->rec_mask)) + ((shot >> 5) & 3);
-                    atomicXor(rw, bit);
-                }
-            } else {
-                // all loads first, then the stores: the (up to four) words are independent
-                uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-                if (f & 1u) {
-                    w0 = lds32(a1);
-                }
-                if (f & 2u) {
-                    w1 = lds32(a1 + zoff);
-                }
-                if (f & 4u) {
-                    w2 = lds32(a2);
-                }
-                if (f & 8u) {
-                    w3 = lds32(a2 + zoff);
-                }
-                if (f & 1u) {
-                    sts32(a1, w0 ^ bit);
-                }
-                if (f & 2u) {
-                    sts32(a1 + zoff, w1 ^ bit);
-                }
-                if (f & 4u) {
-                    sts32(a2, w2 ^ bit);
-                }
-                if (f & 8u) {
-                    sts32(a2 + zoff, w3 ^ bit);
-                }
-                if (f & 16u) {
-                    uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + ((rec0 + it) & bc->rec_mask)) + ((shot >> 5) & 3);
-                    *rw ^= bit;
-                }
-            }
-        }
-      }
-    }
-    __syncwarp();
-}
-
-// Tail of every batch that can carry post-noise: applies it (after the warp's own items are done) and returns the
-// address of the next batch. A real call in tail position: nothing of the caller stays live across it.
-__device__ __noinline__ const uint32_t *noise_post(const BlockCtx *bc, const uint32_t *hdr, uint32_t items_s, uint32_t stride) {
-    const SmemWords hw{smem_u32(hdr)};
-    const uint32_t att = hw[GH_POST];
-    if (att != GSTIM_NO_NOISE) {
-        __syncwarp();
-        const uint32_t perm = hw[GH_PERM];
-        noise_apply(bc, att, hw[GH_POST_NEXT], hw[GH_N], items_s, stride, perm ? hw.s + 4 * perm : 0u, hw[GH_REC0], (hw[GH_WIDTHS] >> 4) & 15u);
-    }
-    return hdr + hw[GH_WORDS];
-}
 
 // ------------------------------------------------------------------------------------------------
 // opcodes
@@ -659,7 +543,7 @@ __device__ __noinline__ const uint32_t *op_cliff1(const BlockCtx *bc, const uint
             sts128(ax + zoff, xor4(and4(x, cc), and4(z, d)));
         }
     }
-    return noise_post(bc, hdr, pay.s, 1);
+    return hdr + hw[GH_WORDS];
 }
 
 __device__ __noinline__ const uint32_t *op_cx(const BlockCtx *bc, const uint32_t *hdr) {
@@ -679,7 +563,7 @@ __device__ __noinline__ const uint32_t *op_cx(const BlockCtx *bc, const uint32_t
             sts128(a2, xor4(x2, x1));
         }
     }
-    return noise_post(bc, hdr, pay.s, 1);
+    return hdr + hw[GH_WORDS];
 }
 
 __device__ __noinline__ const uint32_t *op_cliff2(const BlockCtx *bc, const uint32_t *hdr) {
@@ -705,12 +589,120 @@ __device__ __noinline__ const uint32_t *op_cliff2(const BlockCtx *bc, const uint
             sts128(a2 + zoff, xor4(xor4(and4(x1, m[12]), and4(z1, m[13])), xor4(and4(x2, m[14]), and4(z2, m[15]))));
         }
     }
-    return noise_post(bc, hdr, pay.s, 1);
+    return hdr + hw[GH_WORDS];
 }
 
-// Stand-alone noise batch: its own item list, applied like attached noise.
+// First record and (clamped) record count of noise batch `nbi` in this CTA's event scratch.
+__device__ __forceinline__ void event_segment(const BlockCtx *bc, uint32_t nbi, uint32_t &seg0, uint32_t &cnt) {
+    if (bc->ev_counts_s) {
+        seg0 = lds32(bc->ev_segoff_s + 4 * nbi);
+        cnt = lds32(bc->ev_counts_s + 4 * nbi);
+    } else {
+        seg0 = bc->ev_segoff[nbi];
+        cnt = bc->ev_counts[nbi];
+    }
+}
+// Event records of noise batch `nbi` -> staging buffer (nbi & 1), asynchronously (LDGSTS): thread t copies the
+// records it will apply itself, so no barrier is needed between the copy and the use. One group per call.
+__device__ __forceinline__ void prefetch_events(const BlockCtx *bc, uint32_t nbi) {
+    if (nbi < bc->n_noise) {
+        uint32_t seg0, cnt;
+        event_segment(bc, nbi, seg0, cnt);
+        cnt = min(cnt, GSTIM_EV_STAGE);
+        const uint32_t *ev = bc->ev_buf + seg0;
+        const uint32_t st = bc->stage_s + (nbi & 1u) * (GSTIM_EV_STAGE * 4);
+        for (uint32_t e = threadIdx.x; e < cnt; e += bc->T_i) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(st + 4 * e), "l"(ev + e) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void flip_atomic(uint32_t a, uint32_t bit) {
+    asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(bit) : "memory");
+}
+
+// NOISE1 / NOISE2: apply the events the pre-pass left for this batch. Any thread applies any event, so the
+// batch is bracketed by block barriers. Two events of one batch touch the same 32-bit frame word only when the
+// pre-pass marked both GSTIM_EV_CONFLICT; only those use shared-memory atomics.
 __device__ __noinline__ const uint32_t *op_noise(const BlockCtx *bc, const uint32_t *hdr) {
-    return noise_post(bc, hdr, smem_u32(hdr) + 4 * GSTIM_HDR_WORDS, 1);
+    const SmemWords hw{smem_u32(hdr)};
+    const uint32_t hdr_s = hw.s;
+    const uint32_t h0 = lds32(hdr_s + 4 * GH_OP);
+    const uint32_t flags = (h0 >> 8) & 0xFF;
+    const uint32_t items_s = hdr_s + 4 * GSTIM_HDR_WORDS + (((h0 & 0xFF) == GOP_NOISE2 && (flags & GF_TABLE)) ? 60u : 0u);
+    const uint32_t nbi = lds32(hdr_s + 4 * GH_CSITE0), rec0 = lds32(hdr_s + 4 * GH_REC0);
+    uint32_t seg0, cnt;
+    event_segment(bc, nbi, seg0, cnt);
+    const uint32_t X_s = bc->X_s, zoff = bc->Z_s - bc->X_s, pitch_b = bc->pitch_b;
+    const uint32_t st = bc->stage_s + (nbi & 1u) * (GSTIM_EV_STAGE * 4);
+    prefetch_events(bc, nbi + 1);
+    const uint32_t T_i = bc->T_i;
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's records have landed
+    if (!(flags & GF_NOENTRY)) {
+        bar_sync<GSTIM_BAR_INTERP>(T_i);  // (a directly preceding noise batch ended with this barrier)
+    }
+    for (uint32_t e = threadIdx.x; e < cnt; e += T_i) {
+        const uint32_t rec = e < GSTIM_EV_STAGE ? lds32(st + 4 * e) : bc->ev_buf[seg0 + e];
+        const uint32_t shot = rec & ((1u << GSTIM_EV_SHOT_BITS) - 1);
+        const uint32_t item = (rec >> GSTIM_EV_ITEM_SHIFT) & GSTIM_EV_ITEM_MASK;
+        const uint32_t f = rec >> GSTIM_EV_FLIP_SHIFT;
+        const uint32_t w = (flags & GF_NOFRAME) ? 0u : lds32(items_s + 4 * item);
+        const uint32_t bit = 1u << (shot & 31);
+        const uint32_t a0 = X_s + (shot >> 7) * pitch_b + ((shot >> 5) & 3) * 4;
+        const uint32_t a1 = a0 + (w & 0xFFFF) * 16, a2 = a0 + (w >> 16) * 16;
+        if (rec & GSTIM_EV_CONFLICT) {
+            if (f & 1u) {
+                flip_atomic(a1, bit);
+            }
+            if (f & 2u) {
+                flip_atomic(a1 + zoff, bit);
+            }
+            if (f & 4u) {
+                flip_atomic(a2, bit);
+            }
+            if (f & 8u) {
+                flip_atomic(a2 + zoff, bit);
+            }
+            if (f & 16u) {
+                uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + ((rec0 + item) & bc->rec_mask)) + ((shot >> 5) & 3);
+                atomicXor(rw, bit);
+            }
+        } else {
+            // all loads first, then the stores: the (up to four) words are independent
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            if (f & 1u) {
+                w0 = lds32(a1);
+            }
+            if (f & 2u) {
+                w1 = lds32(a1 + zoff);
+            }
+            if (f & 4u) {
+                w2 = lds32(a2);
+            }
+            if (f & 8u) {
+                w3 = lds32(a2 + zoff);
+            }
+            if (f & 1u) {
+                sts32(a1, w0 ^ bit);
+            }
+            if (f & 2u) {
+                sts32(a1 + zoff, w1 ^ bit);
+            }
+            if (f & 4u) {
+                sts32(a2, w2 ^ bit);
+            }
+            if (f & 8u) {
+                sts32(a2 + zoff, w3 ^ bit);
+            }
+            if (f & 16u) {
+                uint32_t *rw = (uint32_t *)(bc->rec + (uint64_t)(shot >> 7) * bc->rec_k_stride + ((rec0 + item) & bc->rec_mask)) + ((shot >> 5) & 3);
+                *rw ^= bit;
+            }
+        }
+    }
+    bar_sync<GSTIM_BAR_INTERP>(T_i);
+    return hdr + hw[GH_WORDS];
 }
 
 
@@ -745,7 +737,7 @@ __device__ __forceinline__ void measure_items(const BlockCtx *bc, const SmemWord
         uint32_t ax = X_s + q * 16 + sub * pitch_b;
         for (uint32_t k = sub; k < K; k += kinc, ax += kstep, rrow += (uint64_t)kinc * rks, orec += (uint64_t)kinc * rks, drow += (uint64_t)kinc * oks) {
             uint4 prev = make_uint4(0, 0, 0, 0);
-            if (det != 0xFFFFFFFFu && !(bc->dbg_flags & 2u)) {  // (flag 2: timing experiment without the previous round's row)
+            if (det != 0xFFFFFFFFu) {
                 prev = ldg128(orec);  // (issued before the Philox chain so the L2 latency hides behind it)
             }
             uint32_t c2 = col_lo + k, c3 = tag_hi;
@@ -789,10 +781,6 @@ __device__ __forceinline__ void measure_items(const BlockCtx *bc, const SmemWord
 __device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uint32_t *hdr) {
     const SmemWords hw{smem_u32(hdr)};
     const uint32_t aux = hw[GH_OP] >> 16;
-    const uint32_t item_stride = (((aux >> 2) & 3u) != GK_R && ((hw[GH_OP] >> 8) & GF_DET)) ? 3u : 1u;
-    if (hw[GH_PRE] != GSTIM_NO_NOISE) {  // flips in front of the measurement (X_ERROR before MR ...)
-        noise_apply(bc, hw[GH_PRE], hw[GH_PRE_NEXT], hw[GH_N], hw.s + 4 * GSTIM_HDR_WORDS, item_stride, 0u, hw[GH_REC0], hw[GH_WIDTHS] & 15u);
-    }
     switch (aux & 15u) {  // basis | kind << 2
         case GB_X | (GK_M << 2): measure_items<GB_X, GK_M>(bc, hw); break;
         case GB_Y | (GK_M << 2): measure_items<GB_Y, GK_M>(bc, hw); break;
@@ -804,7 +792,7 @@ __device__ __noinline__ const uint32_t *op_measure(const BlockCtx *bc, const uin
         case GB_Y | (GK_R << 2): measure_items<GB_Y, GK_R>(bc, hw); break;
         default: measure_items<GB_Z, GK_R>(bc, hw); break;
     }
-    return noise_post(bc, hdr, hw.s + 4 * GSTIM_HDR_WORDS, item_stride);
+    return hdr + hw[GH_WORDS];
 }
 
 __device__ __noinline__ const uint32_t *op_reczero(const BlockCtx *bc, const uint32_t *hdr) {
@@ -944,10 +932,7 @@ __device__ __noinline__ const uint32_t *op_feedback(const BlockCtx *bc, const ui
 // (and recorded in) the block's "already occurred" row. Executed by a single thread from the pre-sampled events.
 __device__ __noinline__ const uint32_t *op_corr(const BlockCtx *bc, const uint32_t *hdr) {
     const SmemWords hw{smem_u32(hdr)};
-    const uint32_t att = hw[GH_POST];
-    if (att != GSTIM_NO_NOISE) {
-        noise_chain_step(bc, att, hw[GH_POST_NEXT]);  // (every warp keeps the staging pipeline going)
-    }
+    prefetch_events(bc, hw[GH_CSITE0] + 1);  // keeps the staging pipeline of op_noise going (this op reads its records directly)
     if (threadIdx.x != 0) {
         return hdr + hw[GH_WORDS];
     }
@@ -959,17 +944,12 @@ __device__ __noinline__ const uint32_t *op_corr(const BlockCtx *bc, const uint32
             sts128(flag_s + 16 * k, make_uint4(0, 0, 0, 0));
         }
     }
-    if (att == GSTIM_NO_NOISE) {
-        return hdr + hw[GH_WORDS];
-    }
-    // the single slice of this site: thread 0 belongs to warp 0, whose staged line it is
-    const uint32_t slice = att & 0x7FFFFFFFu;
-    const uint32_t st = bc->stage_s + (att >> 31) * (GSTIM_EV_LINE_WORDS * 4);
-    const uint32_t cnt = lds32(st);
-    const uint32_t *ovf = bc->ev_buf + (size_t)GSTIM_EV_LINE_WORDS * bc->n_slices + __ldg(bc->ev_ovf_off + slice);
-    for (uint32_t idx = 1; idx <= cnt; idx++) {
-        const uint32_t rec = idx < GSTIM_EV_LINE_WORDS ? lds32(st + 4 * idx) : ldcg32(ovf + (idx - GSTIM_EV_LINE_WORDS));
-        const uint32_t shot = rec & ((1u << GSTIM_EV_SHOT_BITS) - 1);
+    const uint32_t nbi = hw[GH_CSITE0];
+    uint32_t seg0, cnt;
+    event_segment(bc, nbi, seg0, cnt);
+    const uint32_t *ev = bc->ev_buf + seg0;
+    for (uint32_t e = 0; e < cnt; e++) {
+        const uint32_t shot = ev[e] & ((1u << GSTIM_EV_SHOT_BITS) - 1);
         const uint32_t fa = flag_s + (shot >> 7) * 16 + ((shot >> 5) & 3) * 4;
         const uint32_t bit = 1u << (shot & 31);
         const uint32_t fw = lds32(fa);
@@ -995,7 +975,7 @@ __device__ __noinline__ const uint32_t *op_corr(const BlockCtx *bc, const uint32
 // ------------------------------------------------------------------------------------------------
 // Producer warps: the noise events of shot block run r go to event buffer r & 1, one run ahead of the interpreter.
 __device__ __noinline__ void producer_role(const BlockCtx *bc) {
-    const uint32_t T_all = bc->T_all, n_blocks = bc->n_blocks;
+    const uint32_t T_all = bc->T_all, n_noise = bc->n_noise, n_blocks = bc->n_blocks;
     // (the events of the launch's first shot block were produced by the whole block, see the kernel)
     uint32_t r = 1;
     for (uint32_t g = blockIdx.x + gridDim.x; g < n_blocks; g += gridDim.x, r++) {
@@ -1007,11 +987,14 @@ __device__ __noinline__ void producer_role(const BlockCtx *bc) {
         PrepassRun run;
         run.col0_lo = (uint32_t)col0;
         run.col0_hi = (uint32_t)(col0 >> 32);
-        run.evbuf = bc->ev_buf_g + (size_t)b * bc->ev_total;
+        run.cnt_s = bc->ev_s ? bc->ev_s + 4 * b * n_noise : 0u;
+        run.counts = bc->ev_counts_g + ((size_t)blockIdx.x * 2 + b) * n_noise;
+        run.evbuf = bc->ev_buf_g + ((size_t)blockIdx.x * 2 + b) * bc->ev_total;
         run.tid = threadIdx.x - bc->T_i;
         run.threads = T_all - bc->T_i;
         run.whole_block = 0;
-        noise_prepass(bc, run);  // (ends with a gpu-scope fence)
+        noise_prepass(bc, run);
+        __threadfence_block();
         bar_arrive2<GSTIM_BAR_FULL>(b, T_all);
     }
 }
@@ -1033,10 +1016,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     sp += (size_t)2 * p.chunk_words * 4;
     uint32_t *lt = (uint32_t *)sp;
     sp += 512 * 4;
-    const uint32_t rates_s = smem_u32(sp);
-    sp += GSTIM_RATE_SMEM_MAX * 8;
+    const uint32_t needs_s = smem_u32(sp);
+    sp += 128 * 8;
+    uint32_t *ev_s = (uint32_t *)sp;  // [2][n_noise] counters, [n_noise + 1] segment offsets (when they fit)
+    const bool ev_in_smem = p.n_noise <= GSTIM_EV_SMEM_MAX;
+    if (ev_in_smem) {
+        sp += ((size_t)(3 * p.n_noise + 1) * 4 + 15) / 16 * 16;
+    }
     const uint32_t stage_s = smem_u32(sp);
-    sp += (size_t)((p.threads_interp + 31) / 32) * 2 * GSTIM_EV_LINE_WORDS * 4;
+    sp += 2 * GSTIM_EV_STAGE * 4;
     const uint32_t mbar_s = smem_u32(sp);
     sp += 32;
     BlockCtx *bc = (BlockCtx *)sp;
@@ -1056,14 +1044,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         bc->Z_s = Z_s;
         bc->flag_s = flag_s;
         bc->lt_s = smem_u32(lt);
-        bc->rates_s = rates_s;
+        bc->needs_s = needs_s;
+        bc->ev_segoff = ev_in_smem ? ev_s + 2 * p.n_noise : p.ev_segoff;
         bc->T_i = T;
         bc->slices = p.slices;
         bc->rates = p.rates;
-        bc->tables = p.tables;
+        bc->ev_counts_s = 0u;
+        bc->ev_segoff_s = ev_in_smem ? smem_u32(ev_s + 2 * p.n_noise) : 0u;
         bc->n_slices = p.n_slices;
+        bc->n_noise = p.n_noise;
         bc->stage_s = stage_s;
-        bc->ev_ovf_off = p.ev_ovf_off;
+        bc->noise_info = p.noise_info;
+        bc->prog = p.prog;
         bc->ev_overflow = p.ev_overflow;
         bc->pitch_b = p.q_pitch * 16;
         bc->K = p.K;
@@ -1080,33 +1072,34 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         bc->chunk_words = p.chunk_words;
         bc->T_all = T_all;
         bc->mbar_s = mbar_s;
-        bc->ev_total = p.ev_total;
+        bc->ev_s = ev_in_smem ? smem_u32(ev_s) : 0u;
+        bc->ev_total = p.ev_segoff[p.n_noise];
         bc->ring = ring;
         bc->col0_base = p.col0_base;
         bc->rec_base = p.rec;
         bc->out_base = p.out;
         bc->rec_block_stride = p.rec_block_stride;
         bc->rec_cta_stride = p.rec_cta_stride;
-        bc->ev_buf_g = p.ev_buf + (size_t)blockIdx.x * 2 * p.ev_total;
-        bc->ev_buf = bc->ev_buf_g;
+        bc->ev_counts_g = p.ev_counts;
+        bc->ev_buf_g = p.ev_buf;
     }
-    for (uint32_t i = tid; i < 512; i += T_all) {
-        lt[i] = GSTIM_LOG2_Q26[i];
+    for (uint32_t i = tid; i < 256; i += T_all) {
+        lt[i] = GSTIM_LOG2_BASE[i];
+        lt[256 + i] = GSTIM_LOG2_DIFF[i];
     }
     for (uint32_t i = tid; i < min(p.n_rates, GSTIM_RATE_SMEM_MAX); i += T_all) {
-        const uint2 r = p.rates[i];
-        sts64(rates_s + 8 * i, (unsigned long long)r.x | ((unsigned long long)r.y << 32));
+        const ulonglong2 r = p.rates[i];
+        sts64(needs_s + 16 * i, r.x);
+        sts64(needs_s + 16 * i + 8, r.y);
+    }
+    if (ev_in_smem) {
+        for (uint32_t i = tid; i <= p.n_noise; i += T_all) {
+            ev_s[2 * p.n_noise + i] = p.ev_segoff[i];
+        }
     }
     __syncthreads();
 
-    // Two ways to get a shot block's noise events (p.phased):
-    //   overlapped (default): the last warps of the block are dedicated producers that sample block r + 1 while block r is
-    //     interpreted (double-buffered events, FULL / FREE hand-over barriers);
-    //   phased: at the start of every shot block ALL warps of the block sample its events together, then the interpreter
-    //     warps run (no overlap, but 24 warps hide the latency of the dependent Philox / gap chains better than 4).
-    // c3, per 2^22 shots: overlapped 30.1 ms, phased 33.1 ms (profiles/r2_notes.md).
-    const bool phased = p.phased != 0;
-    const bool has_producers = T_all > T && !phased;
+    const bool has_producers = T_all > T;
     if (has_producers) {
         // The first shot block's noise is sampled by the whole block (24 warps instead of 4): the interpreter would
         // only wait for it anyway. From the second block on the producer warps run ahead on their own.
@@ -1114,14 +1107,16 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         PrepassRun run;
         run.col0_lo = (uint32_t)col0;
         run.col0_hi = (uint32_t)(col0 >> 32);
-        run.evbuf = p.ev_buf + (size_t)blockIdx.x * 2 * p.ev_total;
+        run.cnt_s = ev_in_smem ? smem_u32(ev_s) : 0u;
+        run.counts = p.ev_counts + (size_t)blockIdx.x * 2 * p.n_noise;
+        run.evbuf = p.ev_buf + (size_t)blockIdx.x * 2 * p.ev_segoff[p.n_noise];
         run.tid = tid;
         run.threads = T_all;
         run.whole_block = 1;
         noise_prepass(bc, run);
         __syncthreads();
     }
-    if (tid >= T && !phased) {
+    if (tid >= T) {
         producer_role(bc);
         return;
     }
@@ -1131,6 +1126,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
     // because anything pushed to local memory is reloaded at L2 latency (the frame leaves almost no L1).
     // (kernel parameters are constant-bank operands: they cost no registers)
     const uint32_t chunk_words = p.chunk_words, chunk_bytes = chunk_words * 4;
+    const bool multi = p.G_log2 != 0;
     const uint32_t skipmask = p.dbg_flags >> 8;  // debug: bit (op) set -> skip that opcode
     uint32_t phase0 = 0, phase1 = 0, run_idx = 0;
 #ifdef GSTIM_CYCLE_COUNTERS
@@ -1140,26 +1136,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
 #endif
 
     for (uint32_t g = blockIdx.x; g < p.n_blocks; g += gridDim.x, run_idx++) {
-        const uint32_t eb = phased ? 0u : (run_idx & 1u);
-        if (phased && p.n_slices != 0) {
-            const uint64_t col0 = p.col0_base + (uint64_t)g * p.K;
-            PrepassRun run;
-            run.col0_lo = (uint32_t)col0;
-            run.col0_hi = (uint32_t)(col0 >> 32);
-            run.evbuf = p.ev_buf + (size_t)blockIdx.x * 2 * p.ev_total;
-            run.tid = tid;
-            run.threads = T_all;
-            run.whole_block = 1;
-            noise_prepass(bc, run);  // (starts and ends with a barrier of the whole block)
-        }
-        if (tid >= T) {
-            continue;  // helper warps only take part in the sampling phase
-        }
+        const uint32_t eb = run_idx & 1u;
         if (tid == 0) {
             const uint64_t col0 = p.col0_base + (uint64_t)g * p.K;
+            const uint32_t n_noise = p.n_noise;
             bc->col0_lo = (uint32_t)col0;
             bc->col0_hi = (uint32_t)(col0 >> 32);
-            bc->ev_buf = p.ev_buf + ((size_t)blockIdx.x * 2 + eb) * p.ev_total;
+            bc->ev_counts_s = bc->ev_s ? bc->ev_s + 4 * eb * n_noise : 0u;
+            bc->ev_counts = bc->ev_s ? nullptr : p.ev_counts + ((size_t)blockIdx.x * 2 + eb) * n_noise;  // (global fallback)
+            bc->ev_buf = p.ev_buf + ((size_t)blockIdx.x * 2 + eb) * bc->ev_total;
             bc->rec = p.rec + (uint64_t)g * p.rec_block_stride + (uint64_t)blockIdx.x * p.rec_cta_stride;
             bc->out = p.out + (uint64_t)g * p.K * p.out_k_stride;
             // start streaming the program
@@ -1179,8 +1164,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
         } else {
             bar_sync<GSTIM_BAR_INTERP>(T);
         }
-        // the first noise application of a shot block starts at slice 0 with parity 0
-        stage_line(bc, (warp_first_item(bc) >> 5) << p.first_lpg, 0u);
+        prefetch_events(bc, 0);
 
         for (uint32_t chunk = 0;; chunk++) {
             const uint32_t b = chunk & 1;
@@ -1215,8 +1199,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gstim_interp_kernel(const Inte
                 }
                 if (h0 & (GF_BARRIER << 8)) {
                     bar_sync<GSTIM_BAR_INTERP>(T);
-                } else {
-                    __syncwarp();  // hazards are tracked per warp (lowering.cc): the warp re-converges and orders its accesses
+                } else if (multi) {
+                    __syncwarp();
                 }
                 switch ((skipmask >> op) & 1u ? (uint32_t)GOP_QMAP : op) {
                     case GOP_CLIFF1:

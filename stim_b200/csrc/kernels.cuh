@@ -27,24 +27,23 @@ struct InterpParams {
     uint32_t rec_mask;         // ring mask (detector mode) or 0xFFFFFFFF
     uint4 *out;                // detector/observable table, column-major: out[column * out_k_stride + row]; block g owns columns [g*K,(g+1)*K)
     uint64_t out_k_stride;     // uint4 units between columns (= number of rows)
-    uint32_t phased;           // 1: every shot block starts with all warps sampling its noise events; 0: dedicated producer warps run one block ahead
     uint32_t dbg_flags;        // GSTIM_DEBUG_FLAGS: timing experiments only (results become wrong): bit0 no noise events, bits 8+op skip opcode
     unsigned long long *dbg_cycles;  // optional (GSTIM_DEBUG_CYCLES=1): [op] cycles and [16+op] batch counts seen by block 0
-    // noise schedule (program.h) and the per-CTA event buffers the producer warps fill
+    // noise schedule (program.h) and the per-CTA event scratch the pre-pass fills
+    uint32_t n_noise;                 // noise batches
     uint32_t n_rates;                 // distinct rates
-    const uint2 *rates;               // per rate: INV, SH (program.h "Gap arithmetic")
+    const uint32_t *noise_info;       // n_noise * GSTIM_NOISE_INFO_WORDS
+    const ulonglong2 *rates;          // per rate: lam, floor((2^64 - 1) / lam)
     const uint4 *slices;              // RNG slices, 2 uint4 each (program.h "Noise schedule")
     uint32_t n_slices;
-    uint32_t first_lpg;               // log2(slices per 32 items) of the first noise application of the program
-    const uint32_t *tables;           // PAULI_CHANNEL_2 threshold tables
-    const uint32_t *ev_ovf_off;       // n_slices + 1 : overflow segment offsets (words) for this launch's block size
-    uint64_t ev_total;                // words per event buffer: 32 * n_slices + ev_ovf_off[n_slices] (+ padding)
-    uint32_t *ev_buf;                 // gridDim.x * 2 * ev_total (two event buffers per CTA)
-    uint32_t *ev_overflow;            // set to 1 if any slice overflowed (the host reports it)
+    const uint32_t *ev_segoff;        // n_noise + 1 : event segment offsets for this launch's block size
+    uint32_t *ev_counts;              // gridDim.x * 2 * n_noise (two event buffers per CTA)
+    uint32_t *ev_buf;                 // gridDim.x * 2 * ev_segoff[n_noise]
+    uint32_t *ev_overflow;            // set to 1 if any segment overflowed (host retries with more room)
 };
 
 // Shared memory the interpreter needs for (Q, K, chunk_words).
-size_t interp_smem_bytes(uint32_t q_pitch, uint32_t K, uint32_t chunk_words, uint32_t interp_threads);
+size_t interp_smem_bytes(uint32_t q_pitch, uint32_t Q, uint32_t K, uint32_t chunk_words, uint32_t n_noise);
 cudaError_t launch_interp(const InterpParams &p, uint32_t grid, uint32_t threads, size_t smem, cudaStream_t stream);
 cudaError_t interp_set_max_smem(size_t smem);
 int interp_max_blocks_per_sm(uint32_t threads, size_t smem);

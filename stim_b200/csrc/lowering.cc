@@ -13,14 +13,11 @@ uint32_t Batch::words() const {
     if (op == GOP_XORROWS) {
         return GSTIM_HDR_WORDS + (uint32_t)dst.size() + (uint32_t)off.size() + (uint32_t)idx.size();
     }
-    // (gate batches keep room for the byte table of a bank-spreading permutation, see spread_banks)
-    const uint32_t perm_words = (op == GOP_CLIFF1 || op == GOP_CLIFF2) ? (n_items + 3) / 4 + 1 : 0;
-    return GSTIM_HDR_WORDS + (uint32_t)payload.size() + perm_words;
+    return GSTIM_HDR_WORDS + (uint32_t)payload.size();
 }
 
-// Probability -> rate key of the geometric gap arithmetic (program.h "Gap arithmetic"): bit 63 = valid, INV << 8 | SH.
-// 0 = the noise never fires. The reference narrows every probability to float before sampling
-// (probability_util.h:47, measure_record_batch.inl:52). p >= 1 saturates: INV = 0, an event at every shot.
+// Probability -> rate key of the 32-bit gap arithmetic of the detector-error-model sampler (dem.cu): bit 63 = valid,
+// INV << 8 | SH with INV = floor(2^32 m), SH = 58 - e for 1 / lambda = m 2^e; 0 = never fires; p >= 1: INV = 0.
 uint64_t gstim_rate_key(double p) {
     float f = (float)p;
     if (!(f > 0)) {
@@ -46,21 +43,23 @@ constexpr uint32_t RES_WRITE = 1u << 31;
 constexpr uint32_t ITEM_X = 1u << 30;  // component flags in OBS_PAULI / FEEDBACK / CORR payload words
 constexpr uint32_t ITEM_Z = 1u << 31;
 
-constexpr uint64_t RATE_VALID = 1ull << 63;
+// Probability -> per-shot event rate of the exponential clock in fixed point (unit 2^-56 nat, DESIGN.md
+// "RNG addressing"). The reference narrows every probability to float before sampling
+// (probability_util.h:47, measure_record_batch.inl:52). p >= 1 saturates: an event at every shot.
+constexpr uint64_t LAM_MAX = 1ull << 62;
 uint64_t rate_of(double p) {
-    return gstim_rate_key(p);
-}
-double prob_of(double p) {
     float f = (float)p;
-    return !(f > 0) ? 0.0 : f >= 1 ? 1.0 : (double)f;
-}
-struct Rate {
-    uint64_t key;
-    double prob;
-};
-Rate rate_pair(double p) {
-    const uint64_t k = rate_of(p);
-    return Rate{k, k ? prob_of(p) : 0.0};
+    if (!(f > 0)) {
+        return 0;
+    }
+    if (f >= 1) {
+        return LAM_MAX;
+    }
+    double v = std::ldexp(-std::log1p(-(double)f), 56);
+    if (v >= (double)LAM_MAX) {
+        return LAM_MAX;
+    }
+    return (uint64_t)v;
 }
 
 uint32_t thr(double frac) {
@@ -76,8 +75,7 @@ uint32_t thr(double frac) {
 
 struct Key {
     uint32_t op = 0, flags = 0, aux = 0, extra = 0;
-    uint64_t lambda = 0;  // rate key (rate_of)
-    double prob = 0;
+    uint64_t lambda = 0;
     uint32_t t1 = 0, t2 = 0, t3 = 0;
     const uint32_t *table = nullptr;  // NOISE2 PAULI_CHANNEL_2 thresholds (15 words) or null
 };
@@ -102,12 +100,9 @@ struct Lowerer {
     std::vector<uint32_t> rd_stamp, wr_stamp;
 
     explicit Lowerer(uint32_t max_words) : max_words(max_words) {}
-    // Largest number of items in a batch: a multiple of the RNG slice size, and small enough that a gate batch with its
-    // bank-spreading byte table (one word per item + n / 4) fits a chunk - gate, measurement and noise batches of long
-    // instructions are all cut here, so they stay item for item aligned (attach_noise).
     uint32_t noise_cap() const {
-        const uint32_t room = max_words > 2 * GSTIM_HDR_WORDS + 16 + 2 * GSTIM_NOISE_SLICE ? (max_words - 2 * GSTIM_HDR_WORDS - 16) / 5 * 4 : GSTIM_NOISE_SLICE;
-        return std::max<uint32_t>(std::min<uint32_t>(GSTIM_MAX_BATCH_ITEMS, room) / GSTIM_NOISE_SLICE * GSTIM_NOISE_SLICE, GSTIM_NOISE_SLICE);
+        const uint32_t room = max_words > 2 * GSTIM_HDR_WORDS + 15 + GSTIM_NOISE_SLICE ? max_words - 2 * GSTIM_HDR_WORDS - 15 : GSTIM_NOISE_SLICE;
+        return std::min<uint32_t>(GSTIM_MAX_BATCH_ITEMS, room) / GSTIM_NOISE_SLICE * GSTIM_NOISE_SLICE;
     }
 
     uint32_t q_of(uint32_t target) const {
@@ -142,14 +137,14 @@ struct Lowerer {
     }
 
     bool same_key(const Key &k) const {
-        if (cur.op != k.op || cur.flags != k.flags || cur.aux != k.aux || cur.extra != k.extra) {
+        if (cur.op != k.op || cur.flags != k.flags || cur.aux != k.aux || cur.extra != k.extra || cur.t1 != k.t1 ||
+            cur.t2 != k.t2 || cur.t3 != k.t3) {
             return false;
         }
-        const NoiseSpec &ns = cur.post;
-        if (ns.rate != k.lambda || ns.t1 != k.t1 || ns.t2 != k.t2 || ns.t3 != k.t3) {
+        if (cur.lambda != k.lambda) {
             return false;
         }
-        if ((k.table != nullptr) != ns.has_table || (k.table != nullptr && memcmp(ns.table, k.table, 15 * sizeof(uint32_t)) != 0)) {
+        if (k.table != nullptr && memcmp(cur.payload.data(), k.table, 15 * sizeof(uint32_t)) != 0) {
             return false;
         }
         return true;
@@ -174,7 +169,7 @@ struct Lowerer {
         bool ok = open && !never_merge && same_key(k) && cur.op != GOP_CORR;
         if (ok) {
             uint32_t n = cur.n_items;
-            if ((use_site && cur.post.group != site_v) || (use_csite && cur.csite0 != csite_v) ||
+            if ((use_site && cur.site0 != site_v) || (use_csite && cur.csite0 != csite_v) ||
                 (use_rec && cur.rec0 + n != rec_v)) {
                 ok = false;
             }
@@ -182,10 +177,8 @@ struct Lowerer {
         if (ok && (cur.words() + n_item_words + GSTIM_HDR_WORDS > max_words || cur.n_items >= GSTIM_MAX_BATCH_ITEMS)) {
             ok = false;
         }
-        if (ok && cur.n_items >= noise_cap()) {
-            // a noise group is only ever cut at a multiple of the RNG slice size (program.h); gate and measurement batches
-            // are cut at the same place so that a long instruction and the noise that follows it stay item for item aligned
-            ok = false;
+        if (ok && (cur.op == GOP_NOISE1 || cur.op == GOP_NOISE2) && cur.n_items >= noise_cap()) {
+            ok = false;  // a noise group is only ever cut at a multiple of the RNG slice size (program.h)
         }
         if (ok) {
             for (uint32_t i = 0; i < n_res; i++) {
@@ -203,25 +196,16 @@ struct Lowerer {
             cur.flags = k.flags;
             cur.aux = k.aux;
             cur.extra = k.extra;
+            cur.lambda = k.lambda;
+            cur.t1 = k.t1;
+            cur.t2 = k.t2;
+            cur.t3 = k.t3;
+            cur.site0 = site_v;
             cur.csite0 = csite_v;
             cur.rec0 = rec_v;
             cur.res_off.push_back(0);
-            if (k.op == GOP_NOISE1 || k.op == GOP_NOISE2 || k.op == GOP_CORR) {
-                NoiseSpec &ns = cur.post;
-                ns.present = true;
-                ns.op = k.op;
-                ns.flags = k.flags;
-                ns.aux = k.aux;
-                ns.rate = k.lambda;
-                ns.prob = k.prob;
-                ns.t1 = k.t1;
-                ns.t2 = k.t2;
-                ns.t3 = k.t3;
-                ns.group = site_v;
-                ns.has_table = k.table != nullptr;
-                if (k.table != nullptr) {
-                    memcpy(ns.table, k.table, sizeof(ns.table));
-                }
+            if (k.table != nullptr) {
+                cur.payload.assign(k.table, k.table + 15);
             }
         }
         cur.payload.insert(cur.payload.end(), item_words, item_words + n_item_words);
@@ -448,13 +432,11 @@ struct Lowerer {
     }
     // Result-flip noise on record rows rec_first + i with clock qubits clock_qubits[i].
     void rec_noise(double p, const std::vector<uint32_t> &clock_qubits, uint64_t rec_first) {
-        const Rate rt = rate_pair(p);
-        const uint64_t lam = rt.key;
+        uint64_t lam = rate_of(p);
         Key k;
         k.op = GOP_NOISE1;
         k.flags = GF_REC;
         k.lambda = lam;
-        k.prob = rt.prob;
         for (auto run : runs_of(clock_qubits.size(), [&](size_t i, uint32_t *ks) { ks[0] = clock_qubits[i]; return 1; })) {
             uint32_t g = ngroup++;
             if (lam == 0) {
@@ -468,15 +450,13 @@ struct Lowerer {
         }
     }
     // Single-target Pauli-choice noise over qs (may repeat). rec_first >= 0: every event also flips rec row.
-    void noise1_list(Rate rt, uint32_t cats, uint32_t t1, uint32_t t2, uint32_t t3, const std::vector<uint32_t> &qs,
+    void noise1_list(uint64_t lam, uint32_t cats, uint32_t t1, uint32_t t2, uint32_t t3, const std::vector<uint32_t> &qs,
                      bool herald, uint64_t rec_first) {
         Key k;
         k.op = GOP_NOISE1;
         k.flags = herald ? GF_REC : 0;
         k.aux = cats;
-        const uint64_t lam = rt.key;
         k.lambda = lam;
-        k.prob = rt.prob;
         k.t1 = t1;
         k.t2 = t2;
         k.t3 = t3;
@@ -497,14 +477,12 @@ struct Lowerer {
             }
         }
     }
-    void noise2_list(Rate rt, const std::vector<uint32_t> &flat_pairs, const uint32_t *table, uint32_t last) {
+    void noise2_list(uint64_t lam, const std::vector<uint32_t> &flat_pairs, const uint32_t *table, uint32_t last) {
         Key k;
         k.op = GOP_NOISE2;
         k.flags = table ? GF_TABLE : 0;
         k.aux = table ? last : 0;
-        const uint64_t lam = rt.key;
         k.lambda = lam;
-        k.prob = rt.prob;
         k.table = table;
         size_t n = flat_pairs.size() / 2;
         for (auto run : runs_of(n, [&](size_t i, uint32_t *ks) { ks[0] = flat_pairs[2 * i]; ks[1] = flat_pairs[2 * i + 1]; return 2; })) {
@@ -621,8 +599,7 @@ struct Lowerer {
             meas++;
         }
         if (!args.empty()) {
-            const Rate rt = rate_pair(args[0]);
-            const uint64_t lam = rt.key;
+            uint64_t lam = rate_of(args[0]);
             for (size_t i = 0; i < n; i++) {
                 uint32_t g = ngroup++;  // all MPAD results share the global clock: one group each
                 if (lam == 0) {
@@ -632,7 +609,6 @@ struct Lowerer {
                 k.op = GOP_NOISE1;
                 k.flags = GF_REC | GF_NOFRAME;
                 k.lambda = lam;
-                k.prob = rt.prob;
                 k.extra = Q + 1;  // clock = global clock (index Q)
                 uint32_t r[2] = {res_clock | RES_WRITE, rec_res(rec_first + i) | RES_WRITE};
                 uint32_t dummy = Q;
@@ -855,7 +831,7 @@ struct Lowerer {
     }
 
     void do_noise1_gate(const Instruction &op) {
-        const Rate lam = rate_pair(op.args[0]);
+        uint64_t lam = rate_of(op.args[0]);
         uint32_t cats, t1 = 0, t2 = 0, t3 = 0;
         switch (op.gate->param) {
             case 1:
@@ -878,7 +854,7 @@ struct Lowerer {
     }
 
     void do_depolarize2(const Instruction &op) {
-        noise2_list(rate_pair(op.args[0]), compact_targets(op), nullptr, 0);
+        noise2_list(rate_of(op.args[0]), compact_targets(op), nullptr, 0);
     }
 
     // One site with the channel's total probability, then a category draw: same joint distribution
@@ -886,7 +862,7 @@ struct Lowerer {
     void do_pauli_channel_1(const Instruction &op) {
         double px = op.args[0], py = op.args[1], pz = op.args[2];
         double tot = px + py + pz;
-        const Rate lam = rate_pair(std::min(tot, 1.0));
+        uint64_t lam = rate_of(std::min(tot, 1.0));
         uint32_t t1 = 0, t2 = 0, cats = 0;
         if (tot > 0) {
             t1 = thr(px / tot);
@@ -902,7 +878,7 @@ struct Lowerer {
         for (double p : op.args) {
             tot += p;
         }
-        const Rate lam = rate_pair(std::min(tot, 1.0));
+        uint64_t lam = rate_of(std::min(tot, 1.0));
         uint32_t table[15];
         uint32_t last = 1;
         double cum = 0;
@@ -921,7 +897,6 @@ struct Lowerer {
         k.op = GOP_CORR;
         k.flags = op.gate->param ? GF_RESET_FLAG : 0;
         k.lambda = rate_of(op.args[0]);
-        k.prob = k.lambda ? prob_of(op.args[0]) : 0.0;
         std::vector<uint32_t> words, res;
         res.push_back(res_flag | RES_WRITE);
         for (uint32_t t : op.targets) {
@@ -962,7 +937,7 @@ struct Lowerer {
             t2 = tot > 0 ? thr((hx + hz) / tot) : 0;
             t3 = tot > 0 ? thr((hx + hz + hy) / tot) : 0;
         }
-        const Rate lam = rate_pair(std::min(tot, 1.0));
+        uint64_t lam = rate_of(std::min(tot, 1.0));
         uint64_t rec_first = meas;
         for (size_t i = 0; i < op.targets.size(); i++) {
             rec_zero(meas);
@@ -1107,131 +1082,8 @@ namespace {
 bool is_pair_op(const Batch &b) {
     return b.op == GOP_CLIFF2 || b.op == GOP_NOISE2;
 }
-size_t item_skip(const Batch &) {
-    return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Noise attachment (performance only; semantics and RNG addressing are unaffected): a noise batch whose item list equals
-// that of the gate / measurement batch directly before it becomes that batch's post-noise, one directly in front of a
-// measurement batch its pre-noise (program.h). Per item the order "gate, then noise" is unchanged; the events are applied
-// by the warp that executes the item, so neither a block barrier nor a second item list is needed.
-// ---------------------------------------------------------------------------------------------
-bool same_items(const Batch &host, const Batch &noise) {
-    if (host.n_items != noise.n_items || noise.payload.size() != noise.n_items) {
-        return false;
-    }
-    const size_t stride = host.op == GOP_MEASURE && (host.flags & GF_DET) ? 3 : 1;
-    if (host.payload.size() != stride * (size_t)host.n_items) {
-        return false;
-    }
-    for (uint32_t i = 0; i < host.n_items; i++) {
-        if (host.payload[stride * i] != noise.payload[i]) {
-            return false;
-        }
-    }
-    return true;
-}
-
-void merge_resources(Batch &host, const Batch &noise) {
-    // (the noise touches the host items' qubits, plus the items' own record rows when it flips results)
-    std::vector<uint32_t> res, res_off{0};
-    for (uint32_t i = 0; i < host.n_items; i++) {
-        res.insert(res.end(), host.res.begin() + host.res_off[i], host.res.begin() + host.res_off[i + 1]);
-        for (uint32_t j = noise.res_off[i]; j < noise.res_off[i + 1]; j++) {
-            const uint32_t r = noise.res[j];
-            bool have = false;
-            for (uint32_t k = host.res_off[i]; k < host.res_off[i + 1]; k++) {
-                have |= (host.res[k] & ~RES_WRITE) == (r & ~RES_WRITE) && (host.res[k] & RES_WRITE) >= (r & RES_WRITE);
-            }
-            if (!have) {
-                res.push_back(r);
-            }
-        }
-        res_off.push_back((uint32_t)res.size());
-    }
-    host.res.swap(res);
-    host.res_off.swap(res_off);
-}
-
-void attach_noise(LoweredCircuit &lc) {
-    std::vector<Batch> kept;
-    kept.reserve(lc.batches.size());
-    auto &B = lc.batches;
-    // A noise batch may hop over batches that share no resource with it (the other cuts of a long instruction: CX a, CX b,
-    // DEPOLARIZE2 a, DEPOLARIZE2 b) to reach the batch whose items it acts on.
-    std::vector<uint32_t> mark(lc.num_resources, 0);
-    uint32_t epoch = 0;
-    auto touches_marked = [&](const Batch &x) {
-        for (uint32_t r : x.res) {
-            if (mark[r & ~RES_WRITE] == epoch) {
-                return true;
-            }
-        }
-        return false;
-    };
-    constexpr int MAX_HOPS = 16;
-    std::vector<char> taken(B.size(), 0);  // noise batches that became the pre-noise of a later measurement batch
-    for (size_t i = 0; i < B.size(); i++) {
-        if (taken[i]) {
-            continue;
-        }
-        Batch &n = B[i];
-        const bool is_noise = (n.op == GOP_NOISE1 || n.op == GOP_NOISE2) && !(n.flags & GF_NOFRAME);
-        if (!is_noise) {
-            kept.push_back(std::move(n));
-            continue;
-        }
-        epoch++;
-        for (uint32_t r : n.res) {
-            mark[r & ~RES_WRITE] = epoch;
-        }
-        bool attached = false;
-        int hops = 0;
-        for (size_t k = kept.size(); k-- > 0 && hops < MAX_HOPS; hops++) {
-            Batch &h = kept[k];
-            const bool fits = n.op == GOP_NOISE1 ? (h.op == GOP_CLIFF1 || h.op == GOP_MEASURE) : h.op == GOP_CLIFF2;
-            // (record-flipping noise may only follow the measurement that produced exactly these rows)
-            const bool rec_ok = !(n.flags & GF_REC) || (h.op == GOP_MEASURE && ((h.aux >> 2) & 3u) != GK_R && h.rec0 == n.rec0);
-            if (fits && rec_ok && !h.post.present && same_items(h, n)) {
-                h.post = n.post;
-                merge_resources(h, n);
-                attached = true;
-                break;
-            }
-            if (touches_marked(h)) {
-                break;
-            }
-        }
-        if (!attached && n.op == GOP_NOISE1 && !(n.flags & GF_REC)) {
-            hops = 0;
-            for (size_t j = i + 1; j < B.size() && hops < MAX_HOPS; j++, hops++) {
-                Batch &h = B[j];
-                if (taken[j]) {
-                    continue;
-                }
-                if (h.op == GOP_MEASURE && !h.pre.present && same_items(h, n)) {
-                    h.pre = n.post;
-                    merge_resources(h, n);
-                    attached = true;
-                    break;
-                }
-                if (touches_marked(h)) {
-                    break;
-                }
-            }
-        }
-        if (!attached) {
-            kept.push_back(std::move(n));
-        }
-    }
-    B.swap(kept);
-    lc.total_items = 0;
-    lc.max_items = 0;
-    for (const Batch &b : B) {
-        lc.total_items += b.res_off.size() - 1;
-        lc.max_items = std::max(lc.max_items, (uint32_t)(b.res_off.size() - 1));
-    }
+size_t item_skip(const Batch &b) {
+    return (b.op == GOP_NOISE2 && (b.flags & GF_TABLE)) ? 15 : 0;
 }
 
 void assign_physical_rows(LoweredCircuit &lc) {
@@ -1325,9 +1177,18 @@ bool try_augment(int u, const uint32_t cnt[8][8], int match_v[8], bool seen[8]) 
     return false;
 }
 
-// Orders items[first, first + n) into groups of 8 that are perfect matchings of the residue multigraph (as far as possible).
-// Returns the new order as indices into the range.
-std::vector<uint32_t> matching_order(const uint32_t *items, size_t n, bool pairs) {
+void spread_banks(Batch &b) {
+    // gate batches only: the item order of a noise batch is the site order its RNG slices are defined on
+    const bool pairs = b.op == GOP_CLIFF2;
+    if (!pairs && b.op != GOP_CLIFF1) {
+        return;
+    }
+    const size_t skip = item_skip(b);
+    const size_t n = b.payload.size() - skip;
+    if (n < 9 || n != b.res_off.size() - 1) {
+        return;
+    }
+    const uint32_t *items = b.payload.data() + skip;
     // cell[k1][k2] = stack of item indices (earliest on top)
     std::vector<uint32_t> cell[8][8];
     uint32_t cnt[8][8] = {};
@@ -1396,42 +1257,7 @@ std::vector<uint32_t> matching_order(const uint32_t *items, size_t n, bool pairs
             used_u[bu] = true;
         }
     }
-    return order;
-}
-
-void spread_banks(Batch &b) {
-    // gate batches only: the item order of a stand-alone noise batch is the site order its RNG slices are defined on
-    const bool pairs = b.op == GOP_CLIFF2;
-    if (!pairs && b.op != GOP_CLIFF1) {
-        return;
-    }
-    const size_t n = b.payload.size();
-    if (n < 9 || n != b.res_off.size() - 1) {
-        return;
-    }
-    const uint32_t *items = b.payload.data();
-    std::vector<uint32_t> order;
-    if (!b.post.present && !b.pre.present) {
-        order = matching_order(items, n, pairs);
-    } else {
-        // attached noise addresses items by (slice, site): reorder only inside the 32-item groups and keep the
-        // site -> position table (GH_PERM) for the event application
-        b.perm.assign(n, 0);
-        bool identity = true;
-        for (size_t g0 = 0; g0 < n; g0 += 32) {
-            const size_t cnt = std::min<size_t>(32, n - g0);
-            std::vector<uint32_t> o = matching_order(items + g0, cnt, pairs);
-            for (size_t pos = 0; pos < cnt; pos++) {
-                order.push_back((uint32_t)(g0 + o[pos]));
-                b.perm[g0 + o[pos]] = (uint8_t)pos;
-                identity &= o[pos] == pos;
-            }
-        }
-        if (identity) {
-            b.perm.clear();
-        }
-    }
-    std::vector<uint32_t> new_payload, new_res, new_off{0};
+    std::vector<uint32_t> new_payload(b.payload.begin(), b.payload.begin() + (long)skip), new_res, new_off{0};
     for (uint32_t it : order) {
         new_payload.push_back(items[it]);
         new_res.insert(new_res.end(), b.res.begin() + b.res_off[it], b.res.begin() + b.res_off[it + 1]);
@@ -1531,7 +1357,6 @@ LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch
     });
     lw.flush();
     lw.fuse_detectors();
-    attach_noise(lc);
     assign_physical_rows(lc);
     for (Batch &b : lc.batches) {
         spread_banks(b);
@@ -1541,21 +1366,13 @@ LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch
     return std::move(lw.lc);
 }
 
-std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint32_t lanes_log2, uint32_t chunk_words, GstimPlan *plan) {
+std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint32_t chunk_words, GstimPlan *plan) {
     std::vector<uint32_t> out;
     const uint32_t NONE = 0xFFFFFFFFu, MULTI = 0xFFFFFFFEu;
     std::vector<uint32_t> w_epoch(lc.num_resources, 0), w_slot(lc.num_resources, NONE);
     std::vector<uint32_t> r_epoch(lc.num_resources, 0), r_slot(lc.num_resources, NONE);
     uint32_t epoch = 1;
     uint32_t n_barriers = 0;
-    if (lanes_log2 > 5 || slots == 0 || slots % (32u >> lanes_log2) != 0) {
-        // (a warp executes 32 >> lanes_log2 consecutive items; they must not straddle an RNG slice of 32 sites)
-        throw std::invalid_argument("slots must be a multiple of the items a warp executes (32 >> lanes_log2)");
-    }
-    // Hazards are tracked per WARP: item i is executed by thread group i % slots, i.e. by warp (i % slots) >> warp_shift;
-    // the interpreter re-converges every warp (__syncwarp, which also orders its memory accesses) at the start of each
-    // batch and around the noise a batch applies, so data only needs a block barrier when it changes warps.
-    const uint32_t warp_shift = 5 - lanes_log2;
 
     auto put_header = [&](uint32_t op, uint32_t words) {
         size_t base = out.size();
@@ -1582,76 +1399,43 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         }
     }
 
-    // Noise schedule (consumed by the kernel's producer warps): the RNG slices of every noise application in program order.
+    // Noise schedule (consumed by the kernel's event pre-pass): per noise batch an info record, per
+    // physical clock row the ordered list of its noise sites.
     NoiseSchedule &ns = lc.noise;
     ns = NoiseSchedule();
     std::vector<uint32_t> group_items(lc.num_sites + 1, 0);  // sites of each noise group serialised so far
-    auto rate_index = [&](uint64_t key) -> uint32_t {
-        const uint32_t inv = (uint32_t)(key >> 8), sh = (uint32_t)(key & 0xFF);
+    auto rate_index = [&](uint64_t lam) -> uint32_t {
         for (size_t i = 0; i < ns.rates.size(); i += 2) {
-            if (ns.rates[i] == inv && ns.rates[i + 1] == sh) {
+            if (ns.rates[i] == lam) {
                 return (uint32_t)(i / 2);
             }
         }
         if (ns.rates.size() / 2 >= 65536) {
             throw std::invalid_argument("Circuits with more than 65536 distinct noise probabilities are not supported by this build.");
         }
-        ns.rates.push_back(inv);
-        ns.rates.push_back(sh);
+        ns.rates.push_back(lam);
+        ns.rates.push_back(lam ? 0xFFFFFFFFFFFFFFFFull / lam : 0ull);
         return (uint32_t)(ns.rates.size() / 2) - 1;
     };
-    size_t prev_next_field = SIZE_MAX;  // where the previous noise application wants the first slice of this one
-    // Emits the slices of one application of `spec` over n sites; returns the header word (first slice | parity << 31).
-    auto emit_application = [&](const NoiseSpec &spec, uint32_t n_sites, size_t next_field, uint32_t *width_log2) -> uint32_t {
-        const uint32_t w = gstim_slice_width_log2(spec.prob), S = 1u << w;
-        *width_log2 = w;
-        if (spec.group >= group_items.size()) {
-            group_items.resize((size_t)spec.group + 1, 0);
-        }
-        const uint32_t gfirst = group_items[spec.group];
-        group_items[spec.group] += n_sites;
-        if (gfirst % GSTIM_NOISE_SLICE != 0) {
-            throw std::logic_error("internal: a noise group was cut inside an RNG slice");
-        }
-        const uint32_t slice0 = (uint32_t)(ns.slices.size() / GSTIM_SLICE_WORDS);
-        if (slice0 + (uint64_t)(n_sites + S - 1) / S >= (1u << 28)) {
-            throw std::invalid_argument("Circuits with more than 2^28 noise slices are not supported by this build.");
-        }
-        const uint32_t rate = rate_index(spec.rate);
-        uint32_t t1 = spec.t1;
-        if (spec.has_table) {
-            t1 = (uint32_t)ns.tables.size();
-            ns.tables.insert(ns.tables.end(), spec.table, spec.table + 15);
-        }
-        for (uint32_t i0 = 0; i0 < n_sites; i0 += S) {
-            const uint32_t cnt = std::min<uint32_t>(S, n_sites - i0);
-            uint32_t sl[GSTIM_SLICE_WORDS] = {};
-            sl[GSL_GROUP] = spec.group;
-            sl[GSL_INDEX] = (gfirst + i0) / S;
-            sl[GSL_RATE_SITES] = rate | (cnt << 16);
-            sl[GSL_H0] = spec.op | (spec.flags << 8) | (spec.aux << 16);
-            sl[GSL_T1] = t1;
-            sl[GSL_T2] = spec.t2;
-            sl[GSL_T3] = spec.t3;
-            ns.slices.insert(ns.slices.end(), sl, sl + GSTIM_SLICE_WORDS);
-            ns.slice_prob.push_back(spec.prob);
-            ns.slice_sites.push_back(cnt);
-        }
-        if (prev_next_field != SIZE_MAX) {
-            out[prev_next_field] = slice0 | ((5 - w) << 28);
-        }
-        prev_next_field = next_field;
-        const uint32_t parity = ns.n_applications & 1u;
-        ns.n_applications++;
-        return slice0 | (parity << 31);
-    };
 
+    bool prev_was_noise = false;
     for (Batch &b : lc.batches) {
-        // ---- hazard analysis: does any item need data last touched by another warp? ----
+        const bool is_noise = b.op == GOP_NOISE1 || b.op == GOP_NOISE2;
+        if (is_noise) {
+            epoch++;  // noise events are applied by arbitrary threads: the kernel brackets these batches with barriers
+            // ... except that the exit barrier of a directly preceding noise batch already is this batch's entry barrier
+            if (prev_was_noise) {
+                b.flags |= GF_NOENTRY;
+            } else {
+                b.flags &= ~GF_NOENTRY;
+            }
+        }
+        prev_was_noise = is_noise;
+        // ---- hazard analysis: does any item need data last touched by another thread group? ----
         size_t n_haz = b.res_off.size() - 1;
         bool barrier = false;
         for (size_t i = 0; i < n_haz && !barrier; i++) {
-            uint32_t slot = (uint32_t)(i % slots) >> warp_shift;
+            uint32_t slot = (uint32_t)(i % slots);
             for (uint32_t j = b.res_off[i]; j < b.res_off[i + 1]; j++) {
                 uint32_t r = b.res[j] & ~RES_WRITE;
                 bool wr = (b.res[j] & RES_WRITE) != 0;
@@ -1673,7 +1457,7 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             b.flags &= ~GF_BARRIER;
         }
         for (size_t i = 0; i < n_haz; i++) {
-            uint32_t slot = (uint32_t)(i % slots) >> warp_shift;
+            uint32_t slot = (uint32_t)(i % slots);
             for (uint32_t j = b.res_off[i]; j < b.res_off[i + 1]; j++) {
                 uint32_t r = b.res[j] & ~RES_WRITE;
                 if (b.res[j] & RES_WRITE) {
@@ -1688,11 +1472,12 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             }
         }
 
+        if (is_noise) {
+            epoch++;
+        }
+
         // ---- serialise ----
-        const bool has_perm = !b.perm.empty();
-        const uint32_t perm_words = has_perm ? (uint32_t)(b.perm.size() + 3) / 4 : 0;
-        const uint32_t body = b.op == GOP_XORROWS ? (uint32_t)(b.dst.size() + b.off.size() + b.idx.size()) : (uint32_t)b.payload.size();
-        const uint32_t words = GSTIM_HDR_WORDS + body + perm_words;
+        uint32_t words = b.words();
         uint32_t pos = (uint32_t)(out.size() % chunk_words);
         if (words + GSTIM_HDR_WORDS > chunk_words) {
             throw std::logic_error("internal: batch larger than a program chunk");
@@ -1707,13 +1492,15 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         out[base + GH_N] = b.n_items;
         out[base + GH_WORDS] = words;
         out[base + GH_EXTRA] = b.extra;
+        uint64_t lb = b.lambda;
+        out[base + GH_LAMBDA_LO] = (uint32_t)lb;
+        out[base + GH_LAMBDA_HI] = (uint32_t)(lb >> 32);
+        out[base + GH_SITE0] = b.site0;
         out[base + GH_CSITE0] = b.csite0;
         out[base + GH_REC0] = b.rec0;
-        out[base + GH_PRE] = GSTIM_NO_NOISE;
-        out[base + GH_PRE_NEXT] = GSTIM_NO_NOISE;
-        out[base + GH_POST] = GSTIM_NO_NOISE;
-        out[base + GH_POST_NEXT] = GSTIM_NO_NOISE;
-        out[base + GH_PERM] = has_perm ? GSTIM_HDR_WORDS + body : 0;
+        out[base + GH_T1] = b.t1;
+        out[base + GH_T2] = b.t2;
+        out[base + GH_T3] = b.t3;
         if (b.op == GOP_XORROWS) {
             out.insert(out.end(), b.dst.begin(), b.dst.end());
             out.insert(out.end(), b.off.begin(), b.off.end());
@@ -1721,37 +1508,50 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         } else {
             out.insert(out.end(), b.payload.begin(), b.payload.end());
         }
-        if (has_perm) {
-            for (uint32_t w = 0; w < perm_words; w++) {
-                uint32_t v = 0;
-                for (uint32_t k = 0; k < 4 && 4 * w + k < b.perm.size(); k++) {
-                    v |= (uint32_t)b.perm[4 * w + k] << (8 * k);
+
+        if (is_noise || b.op == GOP_CORR) {
+            const uint32_t nbi = (uint32_t)(ns.info.size() / GSTIM_NOISE_INFO_WORDS);
+            if (nbi >= 65536) {
+                throw std::invalid_argument("Circuits with more than 65536 noise batches are not supported by this build.");
+            }
+            out[base + GH_CSITE0] = nbi;
+            const bool table = b.op == GOP_NOISE2 && (b.flags & GF_TABLE);
+            const uint32_t items_off = (uint32_t)(base + GSTIM_HDR_WORDS + (table ? 15 : 0));
+            uint32_t info[GSTIM_NOISE_INFO_WORDS] = {};
+            info[GNI_H0] = out[base + GH_OP];
+            info[GNI_N] = b.op == GOP_CORR ? 1u : b.n_items;
+            info[GNI_LAM_LO] = (uint32_t)lb;
+            info[GNI_LAM_HI] = (uint32_t)(lb >> 32);
+            info[GNI_GROUP] = b.site0;
+            info[GNI_T1] = b.t1;
+            info[GNI_T2] = b.t2;
+            info[GNI_T3] = b.t3;
+            info[GNI_TABLE_OFF] = table ? (uint32_t)(base + GSTIM_HDR_WORDS) : 0;
+            ns.info.insert(ns.info.end(), info, info + GSTIM_NOISE_INFO_WORDS);
+            ns.n_sites.push_back(info[GNI_N]);
+            ns.lams.push_back(lb);
+            // RNG slices of this batch (program.h "Noise schedule"): GSTIM_NOISE_SLICE consecutive sites of the group each
+            if (b.site0 >= group_items.size()) {
+                group_items.resize((size_t)b.site0 + 1, 0);
+            }
+            const uint32_t gfirst = group_items[b.site0];
+            group_items[b.site0] += info[GNI_N];
+            if (lb != 0) {
+                const uint32_t rate = rate_index(lb);
+                if (gfirst % GSTIM_NOISE_SLICE != 0) {
+                    throw std::logic_error("internal: a noise group was cut inside an RNG slice");
                 }
-                out.push_back(v);
+                for (uint32_t i0 = 0; i0 < info[GNI_N]; i0 += GSTIM_NOISE_SLICE) {
+                    const uint32_t cnt = std::min<uint32_t>(GSTIM_NOISE_SLICE, info[GNI_N] - i0);
+                    const uint32_t sl[GSTIM_SLICE_WORDS] = {b.site0, (gfirst + i0) / GSTIM_NOISE_SLICE, nbi | (rate << 16), i0 | (cnt << 11),
+                                                            info[GNI_H0], b.t1, b.t2, b.t3};
+                    ns.slices.insert(ns.slices.end(), sl, sl + GSTIM_SLICE_WORDS);
+                }
             }
         }
-        const uint32_t n_sites = b.op == GOP_CORR ? 1u : b.n_items;
-        uint32_t w_pre = 5, w_post = 5;
-        if (b.pre.present && b.pre.rate != 0) {
-            out[base + GH_PRE] = emit_application(b.pre, n_sites, base + GH_PRE_NEXT, &w_pre);
-        }
-        if (b.post.present && b.post.rate != 0) {
-            out[base + GH_POST] = emit_application(b.post, n_sites, base + GH_POST_NEXT, &w_post);
-        }
-        out[base + GH_WIDTHS] = w_pre | (w_post << 4);
     }
     put_header(GOP_END, GSTIM_HDR_WORDS);
     out.resize((out.size() + chunk_words - 1) / chunk_words * (size_t)chunk_words, 0);
-    const size_t n_prog_words = out.size();
-
-    // copy of the noise schedule behind the program (not streamed by the kernel)
-    out.push_back(0x4843534Eu);  // 'NSCH'
-    out.push_back((uint32_t)(ns.slices.size() / GSTIM_SLICE_WORDS));
-    out.push_back((uint32_t)(ns.rates.size() / 2));
-    out.push_back((uint32_t)ns.tables.size());
-    out.insert(out.end(), ns.slices.begin(), ns.slices.end());
-    out.insert(out.end(), ns.rates.begin(), ns.rates.end());
-    out.insert(out.end(), ns.tables.begin(), ns.tables.end());
 
     if (plan != nullptr) {
         memset(plan, 0, sizeof(*plan));
@@ -1761,12 +1561,10 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
         plan->num_det = (uint32_t)lc.stats.num_detectors;
         plan->num_obs = (uint32_t)lc.stats.num_observables;
         plan->rec_ring = lc.rec_ring;
-        plan->n_words = (uint32_t)n_prog_words;
+        plan->n_words = (uint32_t)out.size();
         plan->chunk_words = chunk_words;
-        plan->n_chunks = (uint32_t)(n_prog_words / chunk_words);
+        plan->n_chunks = (uint32_t)(out.size() / chunk_words);
         plan->slots = slots;
-        plan->lanes_log2 = lanes_log2;
-        plan->n_slices = (uint32_t)(ns.slices.size() / GSTIM_SLICE_WORDS);
         plan->mode = lc.mode;
         plan->max_items = lc.max_items;
         plan->n_batches = (uint32_t)lc.batches.size();

@@ -19,21 +19,11 @@
 
 namespace gstim {
 
-// A Pauli-noise instruction (or the part of it that lies in one batch), as the producer warps need it.
-struct NoiseSpec {
-    bool present = false;
-    uint32_t op = 0, flags = 0, aux = 0;  // GOP_NOISE1 / GOP_NOISE2 / GOP_CORR, GF_REC | GF_TABLE | GF_NOFRAME, NOISE1 categories / PC2 fallback
-    uint64_t rate = 0;                     // rate key (lowering.cc rate_of): valid bit | INV << 8 | SH
-    double prob = 0;                       // the probability (narrowed to float), for sizing the event buffers
-    uint32_t t1 = 0, t2 = 0, t3 = 0;
-    bool has_table = false;
-    uint32_t table[15] = {};
-    uint32_t group = 0;                    // noise group (Philox counter word 0)
-};
-
 struct Batch {
     uint32_t op = 0, flags = 0, aux = 0, extra = 0;
-    uint32_t csite0 = 0, rec0 = 0;
+    uint64_t lambda = 0;  // event rate per shot, fixed point (2^-56 nat)
+    uint32_t site0 = 0, csite0 = 0, rec0 = 0;
+    uint32_t t1 = 0, t2 = 0, t3 = 0;
     uint32_t n_items = 0;
     std::vector<uint32_t> payload;  // op specific (see program.h)
     // XORROWS is assembled from these three at serialisation time:
@@ -41,21 +31,16 @@ struct Batch {
     // resources (for the hazard pass): per item, [begin,end) into res; bit31 of an entry = write.
     std::vector<uint32_t> res_off;
     std::vector<uint32_t> res;
-    // noise applied by the warps that own the items: before (MEASURE only) / after the items themselves.
-    // A stand-alone noise batch (GOP_NOISE1 / GOP_NOISE2 / GOP_CORR) describes itself in `post`.
-    NoiseSpec pre, post;
-    std::vector<uint8_t> perm;      // site -> position of the item inside its 32-item group (empty = identity)
     uint32_t words() const;
 };
 
 // Filled by serialize_program (see program.h "Noise schedule").
 struct NoiseSchedule {
-    std::vector<uint32_t> slices;     // GSTIM_SLICE_WORDS per RNG slice, in program order
-    std::vector<uint32_t> rates;      // distinct rates: INV, SH
-    std::vector<uint32_t> tables;     // PAULI_CHANNEL_2 threshold tables, 15 words each
-    std::vector<double> slice_prob;   // per slice: event probability per (site, shot)
-    std::vector<uint32_t> slice_sites;  // per slice: number of sites
-    uint32_t n_applications = 0;      // noise applications (pre / post / stand-alone) per shot block
+    std::vector<uint32_t> info;       // GSTIM_NOISE_INFO_WORDS per noise batch
+    std::vector<uint32_t> n_sites;    // per noise batch
+    std::vector<uint64_t> lams;       // per noise batch (fixed-point rate)
+    std::vector<uint64_t> rates;      // distinct rates: 2 words each, lam and floor((2^64 - 1) / lam)
+    std::vector<uint32_t> slices;     // GSTIM_SLICE_WORDS per RNG slice (program.h "Noise schedule"), in program order
 };
 
 struct LoweredCircuit {
@@ -73,16 +58,13 @@ struct LoweredCircuit {
     uint64_t num_sites = 0, num_csites = 0;
 };
 
-// Probability -> rate key of the gap arithmetic: bit 63 = valid, (INV << 8) | SH below it; 0 = never fires.
+// Probability -> rate key of the detector-error-model sampler's gap arithmetic (dem.cu): bit 63 = valid, (INV << 8) | SH.
 uint64_t gstim_rate_key(double p);
 
 // Pass 1: semantics. Throws std::invalid_argument / std::out_of_range like the reference would.
 LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words);
 
 // Pass 2: hazard analysis for `slots` concurrent thread groups + serialisation into chunks.
-// The returned words are the program (plan->n_words words, streamed by the kernel) followed by a copy of the noise
-// schedule for host-side consumers of the stream (oracle/program_emulator.py): 'NSCH', n_slices, n_rates, n_table_words,
-// then the slices, rates and tables.
-std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint32_t lanes_log2, uint32_t chunk_words, GstimPlan *plan);
+std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint32_t chunk_words, GstimPlan *plan);
 
 }  // namespace gstim

@@ -1,0 +1,119 @@
+"""Detector-error-model sampling: host-side mirror of stim.DetectorErrorModel.compile_sampler() /
+stim.CompiledDemSampler (/root/reference/src/stim/simulators/dem_sampler.pybind.cc) over the C ABI
+(include/gstim.h: gstim_dem_*). Sampling runs in stim_b200/csrc/dem.cu on the GPU; there is no CPU fallback."""
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native
+
+
+def _seed_to_u64(seed) -> int:
+    if seed is None:
+        return int.from_bytes(os.urandom(8), "little")
+    if not isinstance(seed, (int, np.integer)) or isinstance(seed, bool) or not 0 <= int(seed) < 1 << 64:
+        raise ValueError("Expected seed to be None or a 64 bit unsigned integer.")
+    return int(seed)
+
+
+class DetectorErrorModel:
+    """A detector error model in Stim's .dem text format. Only what the sampling path needs is mirrored."""
+
+    def __init__(self, detector_error_model_text: str = ""):
+        if not isinstance(detector_error_model_text, str):
+            raise TypeError("detector_error_model_text must be a str")
+        self._text = detector_error_model_text
+        d, l, e = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        data = self._text.encode("utf-8")
+        _native.check(_native.lib().gstim_dem_counts(data, len(data), ctypes.byref(d), ctypes.byref(l), ctypes.byref(e)))
+        self.num_detectors, self.num_observables, self.num_errors = int(d.value), int(l.value), int(e.value)
+
+    @staticmethod
+    def from_file(file) -> "DetectorErrorModel":
+        if hasattr(file, "read"):
+            return DetectorErrorModel(file.read())
+        with open(os.fspath(file), "r") as f:
+            return DetectorErrorModel(f.read())
+
+    def __str__(self) -> str:
+        return self._text
+
+    def compile_sampler(self, *, seed=None, device: int = 0) -> "CompiledDemSampler":
+        return CompiledDemSampler(self, seed=seed, device=device)
+
+
+class CompiledDemSampler:
+    """Mirror of stim.CompiledDemSampler: sample() returns (detection events, observable flips, errors or None)."""
+
+    def __init__(self, dem: DetectorErrorModel, *, seed=None, device: int = 0):
+        if isinstance(dem, str):
+            dem = DetectorErrorModel(dem)
+        self._dem = dem
+        self._handle = ctypes.c_void_p()
+        data = str(dem).encode("utf-8")
+        _native.check(_native.lib().gstim_dem_create_from_text(
+            data, len(data), ctypes.c_uint64(_seed_to_u64(seed)), int(device), ctypes.byref(self._handle)))
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value and _native is not None:
+            _native.lib().gstim_dem_destroy(h)
+            self._handle = ctypes.c_void_p()
+
+    def set_shot_offset(self, offset: int) -> None:
+        _native.check(_native.lib().gstim_dem_set_shot_offset(self._handle, ctypes.c_uint64(int(offset))))
+
+    def sample(self, shots: int, *, bit_packed: bool = False, return_errors: bool = False,
+               recorded_errors_to_replay=None) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]:
+        if recorded_errors_to_replay is not None:
+            raise ValueError("recorded_errors_to_replay is not supported by this sampler")
+        shots = int(shots)
+        if shots < 0:
+            raise ValueError("shots must be non-negative")
+        dt = np.uint8 if bit_packed else np.bool_
+
+        def alloc(n_bits):
+            return np.zeros((shots, (n_bits + 7) // 8 if bit_packed else n_bits), dtype=dt)
+
+        dets, obs = alloc(self._dem.num_detectors), alloc(self._dem.num_observables)
+        errs = alloc(self._dem.num_errors) if return_errors else None
+
+        def ptr(a):
+            return None if a is None or a.size == 0 else a.ctypes.data_as(ctypes.c_void_p)
+
+        _native.check(_native.lib().gstim_dem_sample(
+            self._handle, shots, _native.BIT_PACKED if bit_packed else 0, ptr(dets), 0, ptr(obs), 0, ptr(errs), 0))
+        return dets, obs, errs
+
+    def bit_counts(self, shots: int):
+        """(single[D + L], pair[D + L - 1]) uint64 flip counts over `shots` fresh shots, reduced on the device."""
+        n = self._dem.num_detectors + self._dem.num_observables
+        single = np.zeros(n, dtype=np.uint64)
+        pair = np.zeros(max(n - 1, 0), dtype=np.uint64)
+        _native.check(_native.lib().gstim_dem_bit_counts(
+            self._handle, int(shots), single.ctypes.data_as(ctypes.c_void_p), pair.ctypes.data_as(ctypes.c_void_p) if pair.size else None))
+        return single, pair
+
+    def sample_write(self, shots: int, *, det_out_file=None, det_out_format: str = "01", obs_out_file=None,
+                     obs_out_format: str = "01", err_out_file=None, err_out_format: str = "01",
+                     replay_err_in_file=None, replay_err_in_format: str = "01") -> None:
+        if replay_err_in_file is not None:
+            raise ValueError("replay_err_in_file is not supported by this sampler")
+        files = []
+        try:
+            fds = []
+            for path in (det_out_file, obs_out_file, err_out_file):
+                if path is None:
+                    fds.append(-1)
+                else:
+                    f = open(os.fspath(path), "wb")
+                    files.append(f)
+                    fds.append(f.fileno())
+            _native.check(_native.lib().gstim_dem_sample_to_fd(
+                self._handle, int(shots), fds[0], det_out_format.encode(), fds[1], obs_out_format.encode(), fds[2],
+                err_out_format.encode()))
+        finally:
+            for f in files:
+                f.close()

@@ -16,19 +16,14 @@ from oracle import program_emulator as pe
 from stim_b200 import _native, sharding
 
 
-def lower(text, mode, slots, chunk=0, lanes_log2=None):
-    """Lowered program + plan. By default a warp executes 32 items (one lane per item) when `slots` allows it, else one
-    item (32 lanes per item): the latter makes every thread group a warp of its own, i.e. the hardest case for the
-    barrier analysis."""
-    if lanes_log2 is None:
-        lanes_log2 = 0 if slots % 32 == 0 else 5
+def lower(text, mode, slots, chunk=0):
     L = _native.lib()
     d = text.encode()
     n = ctypes.c_size_t(0)
     plan = (ctypes.c_uint32 * 16)()
-    _native.check(L.gstim_lower_text(d, len(d), mode, slots, lanes_log2, chunk, None, ctypes.byref(n), plan))
+    _native.check(L.gstim_lower_text(d, len(d), mode, slots, chunk, None, ctypes.byref(n), plan))
     w = np.empty(n.value, dtype=np.uint32)
-    _native.check(L.gstim_lower_text(d, len(d), mode, slots, lanes_log2, chunk, w.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n), plan))
+    _native.check(L.gstim_lower_text(d, len(d), mode, slots, chunk, w.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n), plan))
     return w, list(plan)
 
 
@@ -206,7 +201,7 @@ def test_batches_are_padded_into_chunks_and_large_circuits_lower_quickly():
         text = f.read()
     w, plan = lower(text, 0, 640)
     p = pe.plan_dict(plan)
-    assert p["n_words"] % p["chunk_words"] == 0 and int(w[p["n_words"]]) == 0x4843534E  # program, then the schedule copy
+    assert p["n_words"] == w.size and w.size % p["chunk_words"] == 0
     assert p["num_qubits"] == 1249 and p["rec_ring"] == 2048 and p["num_det"] == 15600
 
 

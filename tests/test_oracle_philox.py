@@ -29,6 +29,31 @@ def test_philox_is_vectorised_consistently():
         assert [int(x[i]) for x in a] == [int(x) for x in b]
 
 
+def test_exp_draw_fx_matches_log():
+    rng = random.Random(5)
+    worst = 0.0
+    for r in [0, 1, 2, 3, 255, 256, 1 << 24, 1 << 31, (1 << 32) - 1] + [rng.getrandbits(32) for _ in range(20000)]:
+        got = px.exp_draw_fx(r) / 2.0**56
+        want = -math.log((r + 0.5) / 2.0**32)
+        worst = max(worst, abs(got - want))
+    assert worst < 3e-6  # table interpolation error bound (DESIGN.md)
+
+
+def test_exp_draw_fx_is_exponential():
+    rng = np.random.default_rng(1)
+    r = rng.integers(0, 1 << 32, size=200000, dtype=np.uint64)
+    e = np.array([px.exp_draw_fx(int(v)) for v in r[:50000]], dtype=np.float64) / 2.0**56
+    assert abs(e.mean() - 1.0) < 0.02
+    assert abs((e > 1.0).mean() - math.exp(-1)) < 0.01
+
+
+def test_lam_fx():
+    assert px.lam_fx(0.0) == 0
+    assert px.lam_fx(1.0) == px.LAM_MAX
+    v = px.lam_fx(1e-3)
+    assert abs(v / 2.0**56 - (-math.log1p(-float(np.float32(1e-3))))) < 1e-15
+
+
 def test_exp_draw_q26_matches_log():
     rng = random.Random(5)
     worst = 0.0
@@ -37,34 +62,25 @@ def test_exp_draw_q26_matches_log():
         want = -math.log((r | 1) / 2.0**32)
         worst = max(worst, abs(got - want))
         assert 0 <= px.exp_draw_q26(r) < 1 << 31
-    assert worst < 3e-6  # table interpolation error bound (DESIGN.md)
+    assert worst < 3e-6  # table interpolation error bound
 
 
-def test_exp_draw_q26_is_exponential():
-    rng = np.random.default_rng(1)
-    r = rng.integers(0, 1 << 32, size=200000, dtype=np.uint64)
-    e = np.array([px.exp_draw_q26(int(v)) for v in r[:50000]], dtype=np.float64) / 2.0**26
-    assert abs(e.mean() - 1.0) < 0.02
-    assert abs((e > 1.0).mean() - math.exp(-1)) < 0.01
-
-
-def test_rate_and_gap_arithmetic():
+def test_rate_and_gap_arithmetic_of_the_dem_sampler():
     assert px.rate_of(0.0) is None and px.rate_of(-1.0) is None and px.rate_of(1e-30) is None
-    assert px.rate_of(1.0) == (0, 0, 0) and px.gap_of(12345, (0, 0, 0)) == 0  # p = 1: an event at every shot
-    assert [px.slice_width_log2(f) for f in (1e-3, 0.0156, 0.015625, 0.03, 0.0625, 0.2, 0.25, 0.9)] == [5, 5, 4, 4, 2, 1, 0, 0]
+    assert px.rate_of(1.0) == (0, 0) and px.gap_of(12345, (0, 0)) == 0  # p = 1: an event at every shot
     rng = random.Random(7)
     for p in (1e-9, 1e-6, 1e-3, 0.02, 0.3, 0.5, 0.999, float(np.float32(1) - np.float32(2.0**-24))):
-        inv, sh, _ = px.rate_of(p)
+        inv, sh = px.rate_of(p)
         assert (1 << 31) <= inv < (1 << 32) and 0 <= sh <= 62
         lam = -math.log1p(-float(np.float32(p)))
         assert abs(inv / 2.0 ** (sh - 26) * lam - 1.0) < 1e-9  # INV * 2^(26 - SH) = 1 / lambda
         for _ in range(2000):
             w = rng.getrandbits(32)
             exact = px.exp_draw_q26(w) / 2.0**26 / lam
-            assert abs(px.gap_of(w, (inv, sh, 5)) - exact) <= 1.0 + 1e-6 * exact
+            assert abs(px.gap_of(w, (inv, sh)) - exact) <= 1.0 + 1e-6 * exact
 
 
-def test_gaps_are_geometric():
+def test_q26_gaps_are_geometric():
     """floor(Exp(1) / lambda) with lambda = -log1p(-p) is Geometric(p): P(gap = k) = p (1 - p)^k."""
     p = 0.1
     rate = px.rate_of(p)
