@@ -230,6 +230,60 @@ int gstim_dem_bit_counts(gstim_dem_sampler *s, uint64_t shots, uint64_t *single_
 int gstim_dem_sample_to_fd(gstim_dem_sampler *s, uint64_t shots, int det_fd, const char *det_format, int obs_fd, const char *obs_format,
                            int err_fd, const char *err_format);
 
+/* ---- sampling engines ------------------------------------------------------------------------------------------
+ * The library has two implementations of the path, chosen per sampler:
+ *   GSTIM_ENGINE_INTERPRETER  the frame interpreter (interp.cu): x/z frame words pushed through every lowered
+ *                             instruction, like FrameSimulator::do_circuit (src/stim/simulators/frame_simulator.inl:166-170).
+ *   GSTIM_ENGINE_EVENTS       the event-driven engine (sparse.cu): the frame simulation is GF(2)-linear in its random
+ *                             bits, so every (noise site, Pauli) has a fixed response - the set of output bits it
+ *                             flips - computed once per circuit by propagating sensitivities backwards through the
+ *                             lowered program (response.cc). A shot is the XOR of the responses of the events that fired,
+ *                             sampled with geometric skipping over (site x shot) like RareErrorIterator
+ *                             (src/stim/util_bot/probability_util.cc:23-43). Same distribution as the reference for
+ *                             every eligible circuit; bit-exact on deterministic circuits (p in {0, 1}).
+ * A circuit is eligible for the event engine unless it contains an ELSE_CORRELATED_ERROR chain or its table would be
+ * too large; collapse randomisation that reaches an output (non-deterministic detectors, measurement sampling) becomes
+ * p = 1/2 sites. GSTIM_ENGINE_AUTO (default; env GSTIM_ENGINE=auto|interp|events overrides) picks the event engine when
+ * the circuit is eligible and its cost model (expected events per shot vs lowered items) favours it.
+ * The two engines draw different random streams: with GSTIM_ENGINE_EVENTS the stream is a function of
+ * (seed, shot offset) only, and shot offsets must be multiples of the tile height (gstim_engine_info). */
+#define GSTIM_ENGINE_AUTO 0
+#define GSTIM_ENGINE_INTERPRETER 1
+#define GSTIM_ENGINE_EVENTS 2
+typedef struct gstim_engine_info {
+    int32_t eligible;          /* 1 when the event engine can sample this circuit */
+    int32_t favoured;          /* 1 when GSTIM_ENGINE_AUTO picks it */
+    int32_t last_engine;       /* engine of the most recent sampling call */
+    uint32_t tile_shots;       /* shots per thread-block tile (power of two <= 128) */
+    uint32_t blocks_per_sm;
+    uint32_t num_classes;      /* site classes (probability + outcome chooser) */
+    uint32_t num_slices;       /* RNG slices per tile */
+    uint32_t max_response;     /* most output bits flipped by one (site, outcome) */
+    uint64_t num_sites;        /* noise + live collapse sites */
+    uint64_t num_entries;      /* (site, outcome) table entries of 16 bytes */
+    uint64_t overflow_words;
+    double events_per_shot;    /* expected events per shot */
+    double flips_per_shot;     /* expected bit flips per shot */
+    char why_not[96];          /* reason when not eligible */
+} gstim_engine_info;
+int gstim_set_engine(gstim_sampler *s, int engine);
+int gstim_get_engine_info(const gstim_sampler *s, gstim_engine_info *out);
+/* Copies one array of the response table (tests / the oracle re-derive the responses by forward injection and restate
+ * the sampling from it). what: 0 classes (23 words each: lam lo, lam hi, inv, sh, kind, n_out, thr[15], n_sites, entry0),
+ * 1 entries (4 words each: output ids - detector d, observable D + l, measurement m - 0xFFFFFFFF = empty, a 4th word with
+ * bit 31 = offset into the overflow array), 2 overflow (count, ids...), 3 site noise group (bit 31: collapse site of that
+ * measure group), 4 site index in its group (collapse sites: logical qubit), 5 representative chooser word per class
+ * outcome, 6 slices (4 words each: class, trials = sites * tile_shots, first entry, 0).
+ * Call with words == NULL to get the length in *n_words. */
+int gstim_get_response_table(const gstim_sampler *s, int what, uint32_t *words, size_t *n_words);
+/* Host-only (no GPU needed): lowers the circuit and builds its response table; `what` selectors 0-5 as above.
+ * gstim_response_table_info fills the table statistics of gstim_engine_info (eligible, why_not, sites, entries, ...). */
+typedef struct gstim_response_table gstim_response_table;
+int gstim_response_table_create(const char *circuit_text, size_t text_len, int mode, gstim_response_table **out);
+void gstim_response_table_destroy(gstim_response_table *t);
+int gstim_response_table_info(const gstim_response_table *t, gstim_engine_info *out);
+int gstim_response_table_get(const gstim_response_table *t, int what, uint32_t *words, size_t *n_words);
+
 /* Pins the number of 128-shot columns per thread block (0 = choose per call from the shot count, the default). The
  * random stream is a function of (seed, shot offset, columns per block): callers that split one global shot range over
  * several handles / GPUs and need the union to equal a single-handle run pin the same value everywhere and keep every

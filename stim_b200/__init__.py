@@ -22,7 +22,7 @@ from ._native import GstimCudaError, GstimStats
 
 from .dem import CompiledDemSampler, DetectorErrorModel  # noqa: E402,F401
 
-__all__ = ["Circuit", "CompiledDetectorSampler", "CompiledMeasurementSampler", "GstimCudaError", "measure_lop3_peak",
+__all__ = ["Circuit", "CompiledDetectorSampler", "CompiledMeasurementSampler", "GstimCudaError", "measure_lop3_peak", "response_table",
            "DetectorErrorModel", "CompiledDemSampler"]
 
 
@@ -91,17 +91,59 @@ class Circuit:
     def num_observables(self) -> int:
         return int(self._stats.num_observables)
 
-    def compile_detector_sampler(self, *, seed=None, device: int = 0) -> "CompiledDetectorSampler":
-        return CompiledDetectorSampler(self, seed=seed, device=device)
+    def compile_detector_sampler(self, *, seed=None, device: int = 0, engine: str = "auto") -> "CompiledDetectorSampler":
+        """`engine` (not in the reference): "auto" | "interp" | "events" — include/gstim.h "sampling engines"."""
+        return CompiledDetectorSampler(self, seed=seed, device=device, engine=engine)
 
     def compile_sampler(self, *, skip_reference_sample: bool = False, seed=None, reference_sample=None,
-                        device: int = 0) -> "CompiledMeasurementSampler":
+                        device: int = 0, engine: str = "auto") -> "CompiledMeasurementSampler":
         return CompiledMeasurementSampler(
-            self, skip_reference_sample=skip_reference_sample, seed=seed, reference_sample=reference_sample, device=device)
+            self, skip_reference_sample=skip_reference_sample, seed=seed, reference_sample=reference_sample, device=device,
+            engine=engine)
+
+
+_TABLE_ARRAYS = ["classes", "entries", "overflow", "site_group", "site_index", "outcome_word", "slices"]
+
+
+def _shape_table(out: dict) -> dict:
+    out["classes"] = out["classes"].reshape(-1, 23)
+    out["entries"] = out["entries"].reshape(-1, 4)
+    if "slices" in out:
+        out["slices"] = out["slices"].reshape(-1, 4)
+    return out
+
+
+def response_table(circuit, mode: str = "detectors") -> dict:
+    """Host-only (no GPU): the event engine's response table of a circuit (gstim_response_table_create) as numpy
+    arrays plus an "info" dict; info["eligible"] == 0 means the circuit has none (info["why_not"])."""
+    text = str(circuit).encode("utf-8")
+    h = ctypes.c_void_p()
+    m = _native.MODE_DETECTORS if mode == "detectors" else _native.MODE_MEASUREMENTS
+    _native.check(_native.lib().gstim_response_table_create(text, len(text), m, ctypes.byref(h)))
+    try:
+        info = _native.GstimEngineInfo()
+        _native.check(_native.lib().gstim_response_table_info(h, ctypes.byref(info)))
+        d = {k: getattr(info, k) for k, _ in info._fields_}
+        d["why_not"] = info.why_not.decode()
+        out = {"info": d}
+        if not info.eligible:
+            return out
+        for what, name in enumerate(_TABLE_ARRAYS[:6]):
+            n = ctypes.c_size_t(0)
+            _native.check(_native.lib().gstim_response_table_get(h, what, None, ctypes.byref(n)))
+            a = np.zeros(n.value, dtype=np.uint32)
+            if n.value:
+                _native.check(_native.lib().gstim_response_table_get(h, what, a.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n)))
+            out[name] = a
+        return _shape_table(out)
+    finally:
+        _native.lib().gstim_response_table_destroy(h)
 
 
 class _Sampler:
-    def __init__(self, circuit: Circuit, mode: int, seed, device: int):
+    def __init__(self, circuit: Circuit, mode: int, seed, device: int, engine: str = "auto"):
+        if engine not in _native.ENGINE_NAMES:
+            raise ValueError("engine must be 'auto', 'interp' or 'events'")
         if isinstance(circuit, str):
             circuit = Circuit(circuit)
         self._circuit = circuit
@@ -112,6 +154,8 @@ class _Sampler:
         st = GstimStats()
         _native.check(_native.lib().gstim_get_stats(self._handle, ctypes.byref(st)))
         self.stats = st
+        if engine != "auto":
+            self.set_engine(engine)
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -136,6 +180,30 @@ class _Sampler:
     @shot_offset.setter
     def shot_offset(self, value: int):
         _native.check(_native.lib().gstim_set_shot_offset(self._handle, ctypes.c_uint64(int(value))))
+
+    def set_engine(self, engine: str) -> None:
+        """"auto" | "interp" | "events" (gstim_set_engine); "events" raises ValueError when the circuit is not eligible."""
+        _native.check(_native.lib().gstim_set_engine(self._handle, _native.ENGINE_NAMES[engine]))
+
+    def engine_info(self) -> dict:
+        info = _native.GstimEngineInfo()
+        _native.check(_native.lib().gstim_get_engine_info(self._handle, ctypes.byref(info)))
+        d = {k: getattr(info, k) for k, _ in info._fields_}
+        d["why_not"] = info.why_not.decode()
+        d["last_engine"] = {0: "auto", 1: "interp", 2: "events"}[info.last_engine]
+        return d
+
+    def response_table(self) -> dict:
+        """Arrays of the event engine's response table (gstim_get_response_table), for tests and the oracle."""
+        out = {}
+        for what, name in enumerate(_TABLE_ARRAYS):
+            n = ctypes.c_size_t(0)
+            _native.check(_native.lib().gstim_get_response_table(self._handle, what, None, ctypes.byref(n)))
+            a = np.zeros(n.value, dtype=np.uint32)
+            if n.value:
+                _native.check(_native.lib().gstim_get_response_table(self._handle, what, a.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n)))
+            out[name] = a
+        return _shape_table(out)
 
     def set_block_columns(self, columns: int) -> None:
         """Pins K (128-shot columns per thread block); 0 = automatic. See gstim_set_block_columns."""
@@ -212,8 +280,8 @@ def _stride(a: Optional[np.ndarray]) -> int:
 class CompiledDetectorSampler(_Sampler):
     """Mirror of stim.CompiledDetectorSampler (compiled_detector_sampler.pybind.cc:151-421)."""
 
-    def __init__(self, circuit: Circuit, *, seed=None, device: int = 0):
-        super().__init__(circuit, _native.MODE_DETECTORS, seed, device)
+    def __init__(self, circuit: Circuit, *, seed=None, device: int = 0, engine: str = "auto"):
+        super().__init__(circuit, _native.MODE_DETECTORS, seed, device, engine)
 
     def sample(
         self,
@@ -362,10 +430,10 @@ class CompiledMeasurementSampler(_Sampler):
     """Mirror of stim.CompiledMeasurementSampler (compiled_measurement_sampler.pybind.cc:26-290)."""
 
     def __init__(self, circuit: Circuit, *, skip_reference_sample: bool = False, seed=None, reference_sample=None,
-                 device: int = 0):
+                 device: int = 0, engine: str = "auto"):
         if reference_sample is not None and skip_reference_sample:
             raise ValueError("reference_sample is specified but skip_reference_sample=True")
-        super().__init__(circuit, _native.MODE_MEASUREMENTS, seed, device)
+        super().__init__(circuit, _native.MODE_MEASUREMENTS, seed, device, engine)
         M = int(self.stats.num_measurements)
         if reference_sample is not None:
             ref = np.asarray(reference_sample)

@@ -45,6 +45,29 @@ class GstimStats(ctypes.Structure):
     ]
 
 
+ENGINE_AUTO, ENGINE_INTERPRETER, ENGINE_EVENTS = 0, 1, 2
+ENGINE_NAMES = {"auto": ENGINE_AUTO, "interp": ENGINE_INTERPRETER, "interpreter": ENGINE_INTERPRETER, "events": ENGINE_EVENTS}
+
+
+class GstimEngineInfo(ctypes.Structure):
+    _fields_ = [
+        ("eligible", ctypes.c_int32),
+        ("favoured", ctypes.c_int32),
+        ("last_engine", ctypes.c_int32),
+        ("tile_shots", ctypes.c_uint32),
+        ("blocks_per_sm", ctypes.c_uint32),
+        ("num_classes", ctypes.c_uint32),
+        ("num_slices", ctypes.c_uint32),
+        ("max_response", ctypes.c_uint32),
+        ("num_sites", ctypes.c_uint64),
+        ("num_entries", ctypes.c_uint64),
+        ("overflow_words", ctypes.c_uint64),
+        ("events_per_shot", ctypes.c_double),
+        ("flips_per_shot", ctypes.c_double),
+        ("why_not", ctypes.c_char * 96),
+    ]
+
+
 class GstimCudaError(RuntimeError):
     """CUDA failure or no usable device (the library has no CPU fallback)."""
 
@@ -87,6 +110,13 @@ _SIGNATURES = [
     ("gstim_dem_bit_counts", ctypes.c_int, [_P, ctypes.c_uint64, _P, _P]),
     ("gstim_dem_sample_to_fd", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p,
                                               ctypes.c_int, ctypes.c_char_p]),
+    ("gstim_set_engine", ctypes.c_int, [_P, ctypes.c_int]),
+    ("gstim_get_engine_info", ctypes.c_int, [_P, ctypes.POINTER(GstimEngineInfo)]),
+    ("gstim_get_response_table", ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_size_t)]),
+    ("gstim_response_table_create", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(_P)]),
+    ("gstim_response_table_destroy", None, [_P]),
+    ("gstim_response_table_info", ctypes.c_int, [_P, ctypes.POINTER(GstimEngineInfo)]),
+    ("gstim_response_table_get", ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_size_t)]),
     ("gstim_set_block_columns", ctypes.c_int, [_P, ctypes.c_uint32]),
     ("gstim_measure_lop3_peak", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                                ctypes.POINTER(ctypes.c_double)]),

@@ -23,6 +23,7 @@
 #include "circuit.h"
 #include "kernels.cuh"
 #include "lowering.h"
+#include "sparse.cuh"
 #include "tableau_ref.h"
 #include "writers.h"
 
@@ -137,6 +138,13 @@ struct gstim_sampler {
     cudaEvent_t stage_ready[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> events;
     std::vector<uint8_t> ref_bits;  // one byte per measurement (0/1)
+
+    // event-driven engine (sparse.cu): present when the circuit's response table exists (response.h)
+    std::unique_ptr<SparseEngine> sparse;
+    std::string sparse_why;     // why the circuit is not eligible ("" when it is)
+    int engine_pref = GSTIM_ENGINE_AUTO;
+    int last_engine = GSTIM_ENGINE_INTERPRETER;
+    bool sparse_favoured = false;  // the cost model's choice for GSTIM_ENGINE_AUTO
 
     uint64_t last_launches = 0;
     uint32_t last_K = 0;
@@ -318,6 +326,56 @@ void configure(gstim_sampler *s) {
     CK(interp_set_max_smem(interp_smem_bytes(q_pitch, Q, K_max, s->chunk_words, s->n_noise)));
 }
 
+int engine_from_env() {
+    const char *v = getenv("GSTIM_ENGINE");
+    if (v == nullptr || *v == '\0' || strcmp(v, "auto") == 0) {
+        return GSTIM_ENGINE_AUTO;
+    }
+    if (strcmp(v, "interp") == 0 || strcmp(v, "interpreter") == 0) {
+        return GSTIM_ENGINE_INTERPRETER;
+    }
+    if (strcmp(v, "events") == 0 || strcmp(v, "sparse") == 0) {
+        return GSTIM_ENGINE_EVENTS;
+    }
+    throw std::invalid_argument("GSTIM_ENGINE must be auto, interp or events.");
+}
+
+// Builds the response table (response.cc) and, when the circuit is eligible, the event-driven engine (sparse.cu).
+void configure_event_engine(gstim_sampler *s) {
+    s->engine_pref = engine_from_env();
+    s->sparse.reset();
+    s->sparse_favoured = false;
+    if (env_u32("GSTIM_NO_EVENT_ENGINE", 0)) {
+        s->sparse_why = "disabled by GSTIM_NO_EVENT_ENGINE";
+        return;
+    }
+    ResponseTable rt = build_response_table(s->lc);
+    if (!rt.eligible) {
+        s->sparse_why = rt.why_not;
+        return;
+    }
+    // Cost model (profiles/r2_notes.md): an event costs ~2.2 SM-cycles plus ~0.3 per flipped bit; the interpreter
+    // costs ~0.009 SM-cycles per lowered item and shot.
+    const double ev_cost = rt.events_per_shot * 2.2 + rt.flips_per_shot * 0.3;
+    const double interp_cost = (double)s->lc.total_items * 0.009;
+    const bool favoured = ev_cost < interp_cost;
+    try {
+        s->sparse = std::make_unique<SparseEngine>(
+            std::move(rt), (uint32_t)s->mode, s->plan.num_det, s->plan.num_obs, s->plan.num_meas, s->device, env_u32("GSTIM_SLICE_EVENTS", 4));
+        s->sparse_favoured = favoured;
+        s->sparse_why.clear();
+    } catch (const std::invalid_argument &e) {
+        s->sparse_why = e.what();
+    }
+}
+
+bool use_events(const gstim_sampler *s) {
+    if (!s->sparse || s->engine_pref == GSTIM_ENGINE_INTERPRETER) {
+        return false;
+    }
+    return s->engine_pref == GSTIM_ENGINE_EVENTS || s->sparse_favoured;
+}
+
 uint32_t choose_K(const gstim_sampler *s, uint64_t shots) {
     if (s->K_fixed) {
         return s->K_fixed;
@@ -343,6 +401,69 @@ cudaEvent_t get_event(gstim_sampler *s, size_t i) {
         s->events.push_back(e);
     }
     return s->events[i];
+}
+
+// One pass of the event engine over `shots` shots in chunks of at most `chunk_shots` (a multiple of 128): for every
+// chunk, `place(first, n, &main, &main_pitch, &obs, &obs_pitch)` names the dense device rows to fill and
+// `after(first, n)` runs once the kernel is enqueued on s->stream.
+template <typename PLACE, typename AFTER>
+void run_events(gstim_sampler *s, uint64_t shots, uint32_t layout_flags, uint64_t chunk_shots, PLACE &&place, AFTER &&after) {
+    CK(cudaSetDevice(s->device));
+    s->last_launches = 0;
+    s->last_interp_ms = 0;
+    s->last_transpose_ms = 0;
+    s->last_call_ms = 0;
+    s->last_engine = GSTIM_ENGINE_EVENTS;
+    s->last_K = 0;
+    if (shots == 0) {
+        return;
+    }
+    SparseEngine &E = *s->sparse;
+    const uint64_t cols = (shots + GSTIM_COL_SHOTS - 1) / GSTIM_COL_SHOTS;
+    if (s->next_col + cols >= (1ull << 47)) {
+        throw std::invalid_argument("shot offset + shots must stay below 2^54");
+    }
+    E.set_layout(layout_flags, s->stream);
+    if (s->mode == GSTIM_MODE_MEASUREMENTS) {
+        std::vector<uint8_t> packed((s->plan.num_meas + 7) / 8, 0);
+        for (size_t k = 0; k < s->ref_bits.size(); k++) {
+            packed[k >> 3] |= (uint8_t)(s->ref_bits[k] << (k & 7));
+        }
+        E.set_reference_row(s->ref_bits.empty() ? nullptr : packed.data(), packed.size());
+    }
+    if (!s->call_start) {
+        CK(cudaEventCreate(&s->call_start));
+        CK(cudaEventCreate(&s->call_end));
+    }
+    chunk_shots = std::max<uint64_t>(chunk_shots / GSTIM_COL_SHOTS, 1) * GSTIM_COL_SHOTS;
+    const uint64_t base = s->next_col * GSTIM_COL_SHOTS;
+    CK(cudaEventRecord(s->call_start, s->stream));
+    size_t ev = 0;
+    for (uint64_t first = 0; first < shots; first += chunk_shots) {
+        const uint64_t n = std::min(chunk_shots, shots - first);
+        uint8_t *main = nullptr, *obs = nullptr;
+        uint64_t main_pitch = 0, obs_pitch = 0;
+        place(first, n, &main, &main_pitch, &obs, &obs_pitch);
+        cudaEvent_t e0 = get_event(s, ev++), e1 = get_event(s, ev++);
+        CK(cudaEventRecord(e0, s->stream));
+        try {
+            E.launch(base + first, n, main, main_pitch, obs, obs_pitch, s->seed, s->stream);
+        } catch (const std::runtime_error &e) {
+            throw CudaError(e.what());
+        }
+        CK(cudaEventRecord(e1, s->stream));
+        s->last_launches++;
+        after(first, n);
+    }
+    CK(cudaEventRecord(s->call_end, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaEventElapsedTime(&s->last_call_ms, s->call_start, s->call_end));
+    for (size_t i = 0; i + 2 <= ev; i += 2) {
+        float a = 0;
+        CK(cudaEventElapsedTime(&a, s->events[i], s->events[i + 1]));
+        s->last_interp_ms += a;
+    }
+    s->next_col += cols;
 }
 
 struct RowMaps {
@@ -393,6 +514,7 @@ void run_sampler(gstim_sampler *s, uint64_t shots, SINK &&sink, uint32_t table_m
     s->last_interp_ms = 0;
     s->last_transpose_ms = 0;
     s->last_call_ms = 0;
+    s->last_engine = GSTIM_ENGINE_INTERPRETER;
     if (shots == 0) {
         return;
     }
@@ -589,6 +711,7 @@ void sample_to_device(
     gstim_sampler *s,
     uint64_t shots,
     const RowMaps &maps,
+    uint32_t layout_flags,
     uint8_t *main_out,
     int64_t main_stride,
     uint8_t *obs_out,
@@ -597,6 +720,19 @@ void sample_to_device(
     const uint64_t main_pitch = main_stride ? (uint64_t)main_stride : (nb_main + 7) / 8;
     const uint64_t obs_pitch = obs_stride ? (uint64_t)obs_stride : (nb_obs + 7) / 8;
     CK(cudaSetDevice(s->device));
+    if (use_events(s)) {
+        // the engine writes the caller's rows directly: the output bytes are the only HBM traffic
+        run_events(
+            s, shots, layout_flags, 1ull << 30,
+            [&](uint64_t first, uint64_t, uint8_t **m, uint64_t *mp, uint8_t **o, uint64_t *op) {
+                *m = main_out && nb_main ? main_out + first * main_pitch : nullptr;
+                *mp = main_pitch;
+                *o = obs_out && nb_obs ? obs_out + first * obs_pitch : nullptr;
+                *op = obs_pitch;
+            },
+            [](uint64_t, uint64_t) {});
+        return;
+    }
     s->d_rowmap.ensure((size_t)(nb_main + nb_obs + 1) * 4);
     upload_row_map(s, maps.main, 0);
     upload_row_map(s, maps.obs, nb_main);
@@ -638,6 +774,7 @@ void sample_to_host(
     gstim_sampler *s,
     uint64_t shots,
     const RowMaps &maps,
+    uint32_t layout_flags,
     bool bit_packed,
     uint8_t *main_out,
     int64_t main_stride,
@@ -724,19 +861,17 @@ void sample_to_host(
     };
 
     int cur = 0;
-    try {
-    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
+    uint8_t *dmain = nullptr, *dobs = nullptr;
+    // claims the staging buffer of the next chunk
+    auto begin = [&](uint64_t n) {
         drain(cur);  // buffer about to be reused
         s->d_stage[cur].ensure(n * stage_pitch + 16);
-        uint8_t *dmain = (uint8_t *)s->d_stage[cur].p;
-        uint8_t *dobs = dmain + n * main_bytes;
-        if (nb_main) {
-            transpose_to(s, table, n_rows, dm, nb_main, n, dmain, main_bytes);
-        }
-        if (nb_obs) {
-            transpose_to(s, table, n_rows, dm + nb_main, nb_obs, n, dobs, obs_bytes);
-        }
-        // copy on the second stream so the next chunk's interpreter overlaps the PCIe drain
+        dmain = (uint8_t *)s->d_stage[cur].p;
+        dobs = dmain + n * main_bytes;
+    };
+    // the chunk's rows are enqueued on s->stream: copy them out on the second stream so the next chunk's kernels
+    // overlap the PCIe drain
+    auto finish = [&](uint64_t first, uint64_t n) {
         CK(cudaEventRecord(s->stage_ready[cur], s->stream));
         CK(cudaStreamWaitEvent(s->copy_stream, s->stage_ready[cur], 0));
         if (direct) {
@@ -757,7 +892,32 @@ void sample_to_host(
         pending[cur].first = first;
         pending[cur].n = n;
         cur ^= 1;
+    };
+    try {
+    if (use_events(s)) {
+        const uint64_t chunk = std::max<uint64_t>(((uint64_t)env_u32("GSTIM_STAGE_MB", 256) << 20) / std::max<uint64_t>(stage_pitch, 1), 128);
+        run_events(
+            s, shots, layout_flags, chunk,
+            [&](uint64_t, uint64_t n, uint8_t **m, uint64_t *mp, uint8_t **o, uint64_t *op) {
+                begin(n);
+                *m = nb_main ? dmain : nullptr;
+                *mp = main_bytes;
+                *o = nb_obs ? dobs : nullptr;
+                *op = obs_bytes;
+            },
+            finish);
+    } else {
+    run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
+        begin(n);
+        if (nb_main) {
+            transpose_to(s, table, n_rows, dm, nb_main, n, dmain, main_bytes);
+        }
+        if (nb_obs) {
+            transpose_to(s, table, n_rows, dm + nb_main, nb_obs, n, dobs, obs_bytes);
+        }
+        finish(first, n);
     }, 512);
+    }
     } catch (...) {
         // no copy may still be writing into the caller's buffer (or the staging buffers) once the error is reported
         cudaStreamSynchronize(s->copy_stream);
@@ -827,10 +987,28 @@ struct FdFile {
     }
 };
 
+// shot-major packed rows -> bit-major 32-bit rows, then the ptb64 writer (shots % 64 == 0 is checked by the callers)
+void write_ptb64_rows(FILE *out, const uint8_t *rows, size_t row_pitch, uint64_t shots, uint64_t n_bits) {
+    const size_t n_cols = (shots + 127) / 128;
+    std::vector<uint32_t> table(n_cols * n_bits * 4, 0), map(n_bits);
+    for (uint64_t sh = 0; sh < shots; sh++) {
+        for (uint64_t b = 0; b < n_bits; b++) {
+            if ((rows[sh * row_pitch + (b >> 3)] >> (b & 7)) & 1) {
+                table[((sh >> 7) * n_bits + b) * 4 + ((sh >> 5) & 3)] |= 1u << (sh & 31);
+            }
+        }
+    }
+    for (uint64_t b = 0; b < n_bits; b++) {
+        map[b] = (uint32_t)b;
+    }
+    write_ptb64(out, table.data(), n_bits, map.data(), n_bits, shots);
+}
+
 // Streams shots to a file in any format; chunked through the host sampler.
 void sample_to_file(
     gstim_sampler *s,
     uint64_t shots,
+    uint32_t layout_flags,
     const std::vector<uint32_t> &map,
     FILE *f,
     Format fmt,
@@ -847,6 +1025,45 @@ void sample_to_file(
     }
     // Host-side encoders work on b8 rows, or on the bit-major rows for ptb64.
     CK(cudaSetDevice(s->device));
+    if (use_events(s)) {
+        const uint64_t nbytes = (nb + 7) / 8, nbytes_o = (nbo + 7) / 8;
+        // (ptb64 chunks must hold whole groups of 64 shots; 128-shot multiples do)
+        const uint64_t chunk = std::max<uint64_t>((64ull << 20) / std::max<uint64_t>(nbytes + nbytes_o, 1), 128);
+        std::vector<uint8_t> host;
+        uint8_t *dmain = nullptr, *dobs = nullptr;
+        run_events(
+            s, shots, layout_flags, chunk,
+            [&](uint64_t, uint64_t n, uint8_t **m, uint64_t *mp, uint8_t **o, uint64_t *op) {
+                s->d_stage[0].ensure(n * (nbytes + nbytes_o) + 16);
+                dmain = (uint8_t *)s->d_stage[0].p;
+                dobs = dmain + n * nbytes;
+                *m = nb ? dmain : nullptr;
+                *mp = nbytes;
+                *o = nbo ? dobs : nullptr;
+                *op = nbytes_o;
+            },
+            [&](uint64_t, uint64_t n) {
+                host.resize(n * (nbytes + nbytes_o) + 1);
+                CK(cudaMemcpyAsync(host.data(), dmain, n * (nbytes + nbytes_o), cudaMemcpyDeviceToHost, s->stream));
+                CK(cudaStreamSynchronize(s->stream));
+                if (obs_f && obs_map) {
+                    if (obs_fmt == Format::PTB64) {
+                        write_ptb64_rows(obs_f, host.data() + n * nbytes, nbytes_o, n, nbo);
+                    } else {
+                        write_shots(obs_f, host.data() + n * nbytes, nbytes_o, n, nbo, obs_fmt, 'L', 'L', nbo);
+                    }
+                }
+                if (fmt == Format::PTB64) {
+                    write_ptb64_rows(f, host.data(), nbytes, n, nb);
+                } else {
+                    write_shots(f, host.data(), nbytes, n, nb, fmt, p1, p2, transition);
+                }
+            });
+        if (fflush(f) != 0 || (obs_f && fflush(obs_f) != 0)) {
+            throw IoError("Failed to flush result data.");
+        }
+        return;
+    }
     s->d_rowmap.ensure((size_t)(nb + nbo + 1) * 4);
     upload_row_map(s, map, 0);
     if (obs_map) {
@@ -891,6 +1108,69 @@ void sample_to_file(
     if (fflush(f) != 0 || (obs_f && fflush(obs_f) != 0)) {
         throw IoError("Failed to flush result data.");
     }
+}
+
+void fill_table_info(const ResponseTable &rt, gstim_engine_info *out) {
+    out->eligible = rt.eligible ? 1 : 0;
+    out->num_classes = (uint32_t)rt.classes.size();
+    out->max_response = rt.max_response;
+    out->num_sites = rt.n_sites;
+    out->num_entries = rt.n_entries;
+    out->overflow_words = rt.overflow.size();
+    out->events_per_shot = rt.events_per_shot;
+    out->flips_per_shot = rt.flips_per_shot;
+}
+
+void export_table_array(const ResponseTable &rt, const std::vector<uint32_t> *slices, int what, uint32_t *words, size_t *n_words) {
+    std::vector<uint32_t> tmp;
+    const std::vector<uint32_t> *src = &tmp;
+    switch (what) {
+        case 0:
+            for (const RespClass &c : rt.classes) {
+                tmp.push_back((uint32_t)c.lam);
+                tmp.push_back((uint32_t)(c.lam >> 32));
+                tmp.push_back(c.inv);
+                tmp.push_back(c.sh);
+                tmp.push_back(c.kind);
+                tmp.push_back(c.n_out);
+                tmp.insert(tmp.end(), c.thr, c.thr + 15);
+                tmp.push_back(c.n_sites);
+                tmp.push_back(c.entry0);
+            }
+            break;
+        case 1:
+            src = &rt.entries;
+            break;
+        case 2:
+            src = &rt.overflow;
+            break;
+        case 3:
+            src = &rt.site_group;
+            break;
+        case 4:
+            src = &rt.site_index;
+            break;
+        case 5:
+            src = &rt.outcome_word;
+            break;
+        case 6:
+            if (slices == nullptr) {
+                throw std::invalid_argument("slices belong to a sampler (they depend on the tile height).");
+            }
+            src = slices;
+            break;
+        default:
+            throw std::invalid_argument("bad table selector.");
+    }
+    if (words == nullptr) {
+        *n_words = src->size();
+        return;
+    }
+    require(*n_words >= src->size(), "buffer too small.");
+    if (!src->empty()) {
+        memcpy(words, src->data(), src->size() * 4);
+    }
+    *n_words = src->size();
 }
 
 }  // namespace
@@ -1028,6 +1308,7 @@ int gstim_create_from_text(const char *circuit_text, size_t text_len, int mode, 
         CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
         configure(s.get());
+        configure_event_engine(s.get());
         *out = s.release();
     });
 }
@@ -1116,7 +1397,7 @@ int gstim_sample_detectors(
         check_flag_combo(flags);
         RowMaps maps = detector_row_maps(s, flags);
         sample_to_host(
-            s, shots, maps, (flags & GSTIM_BIT_PACKED) != 0, (uint8_t *)dets_out, dets_shot_stride, (uint8_t *)obs_out, obs_shot_stride);
+            s, shots, maps, flags, (flags & GSTIM_BIT_PACKED) != 0, (uint8_t *)dets_out, dets_shot_stride, (uint8_t *)obs_out, obs_shot_stride);
     });
 }
 
@@ -1126,7 +1407,7 @@ int gstim_sample_measurements(gstim_sampler *s, uint64_t shots, uint32_t flags, 
         require(s->mode == GSTIM_MODE_MEASUREMENTS, "Not a measurement sampler.");
         require(shot_stride >= 0, "negative strides are not supported.");
         RowMaps maps = measurement_row_maps(s);
-        sample_to_host(s, shots, maps, (flags & GSTIM_BIT_PACKED) != 0, (uint8_t *)out, shot_stride, nullptr, 0);
+        sample_to_host(s, shots, maps, 0, (flags & GSTIM_BIT_PACKED) != 0, (uint8_t *)out, shot_stride, nullptr, 0);
     });
 }
 
@@ -1138,7 +1419,7 @@ int gstim_sample_detectors_device(
         require(dets_shot_stride >= 0 && obs_shot_stride >= 0, "negative strides are not supported.");
         check_flag_combo(flags);
         RowMaps maps = detector_row_maps(s, flags);
-        sample_to_device(s, shots, maps, (uint8_t *)dets_out_dev, dets_shot_stride, (uint8_t *)obs_out_dev, obs_shot_stride);
+        sample_to_device(s, shots, maps, flags, (uint8_t *)dets_out_dev, dets_shot_stride, (uint8_t *)obs_out_dev, obs_shot_stride);
     });
 }
 
@@ -1148,7 +1429,7 @@ int gstim_sample_measurements_device(gstim_sampler *s, uint64_t shots, void *out
         require(s->mode == GSTIM_MODE_MEASUREMENTS, "Not a measurement sampler.");
         require(shot_stride >= 0, "negative strides are not supported.");
         RowMaps maps = measurement_row_maps(s);
-        sample_to_device(s, shots, maps, (uint8_t *)out_dev, shot_stride, nullptr, 0);
+        sample_to_device(s, shots, maps, 0, (uint8_t *)out_dev, shot_stride, nullptr, 0);
     });
 }
 
@@ -1177,7 +1458,7 @@ int gstim_sample_detectors_to_fd(
             c2 = 'D';
             tr = s->plan.num_obs;
         }
-        sample_to_file(s, shots, maps.main, out.f, fmt, c1, c2, tr, obs ? &maps.obs : nullptr, obs ? obs->f : nullptr, ofmt);
+        sample_to_file(s, shots, f, maps.main, out.f, fmt, c1, c2, tr, obs ? &maps.obs : nullptr, obs ? obs->f : nullptr, ofmt);
     });
 }
 
@@ -1188,7 +1469,7 @@ int gstim_sample_measurements_to_fd(gstim_sampler *s, uint64_t shots, int fd, co
         Format fmt = parse_format(format);
         RowMaps maps = measurement_row_maps(s);
         FdFile out(fd);
-        sample_to_file(s, shots, maps.main, out.f, fmt, 'M', 'M', maps.main.size(), nullptr, nullptr, Format::F01);
+        sample_to_file(s, shots, 0, maps.main, out.f, fmt, 'M', 'M', maps.main.size(), nullptr, nullptr, Format::F01);
     });
 }
 
@@ -1211,19 +1492,7 @@ int gstim_write_shots_to_fd(
             if (shots % 64 != 0) {
                 throw std::invalid_argument("shots must be a multiple of 64 to use ptb64 format.");
             }
-            const size_t n_cols = (shots + 127) / 128;
-            std::vector<uint32_t> table(n_cols * n_bits * 4, 0), map(n_bits);
-            for (uint64_t sh = 0; sh < shots; sh++) {
-                for (uint64_t b = 0; b < n_bits; b++) {
-                    if ((rows[sh * row_pitch + (b >> 3)] >> (b & 7)) & 1) {
-                        table[((sh >> 7) * n_bits + b) * 4 + ((sh >> 5) & 3)] |= 1u << (sh & 31);
-                    }
-                }
-            }
-            for (uint64_t b = 0; b < n_bits; b++) {
-                map[b] = (uint32_t)b;
-            }
-            write_ptb64(out.f, table.data(), n_bits, map.data(), n_bits, shots);
+            write_ptb64_rows(out.f, rows, row_pitch, shots, n_bits);
         } else {
             write_shots(out.f, rows, row_pitch, shots, n_bits, fmt, prefix1, prefix2, prefix_transition);
         }
@@ -1245,11 +1514,32 @@ int gstim_bit_counts(gstim_sampler *s, uint64_t shots, uint64_t *single_host, ui
         s->d_counts.ensure((size_t)std::max<uint32_t>(n_bits, 1) * 16);
         CK(cudaMemsetAsync(s->d_counts.p, 0, (size_t)std::max<uint32_t>(n_bits, 1) * 16, s->stream));
         unsigned long long *d_single = (unsigned long long *)s->d_counts.p, *d_pair = d_single + n_bits;
+        if (use_events(s)) {
+            // rows of one chunk stay in device staging and are reduced there
+            const uint64_t nbytes = (n_bits + 7) / 8;
+            const uint64_t chunk = std::max<uint64_t>((512ull << 20) / std::max<uint64_t>(nbytes, 1), 128);
+            uint8_t *rows = nullptr;
+            run_events(
+                s, shots, s->mode == GSTIM_MODE_DETECTORS ? GSTIM_APPEND_OBS : 0u, chunk,
+                [&](uint64_t, uint64_t n, uint8_t **m, uint64_t *mp, uint8_t **o, uint64_t *op) {
+                    s->d_stage[0].ensure(n * nbytes + 16);
+                    rows = (uint8_t *)s->d_stage[0].p;
+                    *m = rows;
+                    *mp = nbytes;
+                    *o = nullptr;
+                    *op = 0;
+                },
+                [&](uint64_t, uint64_t n) {
+                    CK(launch_count_b8(rows, nbytes, n, n_bits, d_single, want_pairs ? d_pair : nullptr, s->stream));
+                    s->last_launches++;
+                });
+        } else {
         run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
             (void)first;
             CK(launch_bit_counts(table, n_rows, n, (const uint32_t *)s->d_rowmap.p, n_bits, d_single, want_pairs ? d_pair : nullptr, s->stream));
             s->last_launches++;
         });
+        }
         const size_t nb1 = (size_t)n_bits * 8, nb2 = n_bits ? (size_t)(n_bits - 1) * 8 : 0;
         if (single_dev) {
             CK(cudaMemcpyAsync(single_dev, d_single, nb1, cudaMemcpyDeviceToDevice, s->stream));
@@ -1281,6 +1571,82 @@ int gstim_measure_lop3_peak(int device, double *lane_ops_per_clk_per_sm, double 
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         CK(measure_lop3_peak(prop.multiProcessorCount, lane_ops_per_clk_per_sm, lane_ops_per_sec, sm_mhz));
+    });
+}
+
+int gstim_set_engine(gstim_sampler *s, int engine) {
+    return guarded([&] {
+        require(s != nullptr, "NULL sampler.");
+        require(engine == GSTIM_ENGINE_AUTO || engine == GSTIM_ENGINE_INTERPRETER || engine == GSTIM_ENGINE_EVENTS, "bad engine.");
+        if (engine == GSTIM_ENGINE_EVENTS && !s->sparse) {
+            throw std::invalid_argument("The event engine cannot sample this circuit: " + s->sparse_why + ".");
+        }
+        s->engine_pref = engine;
+    });
+}
+
+int gstim_get_engine_info(const gstim_sampler *s, gstim_engine_info *out) {
+    return guarded([&] {
+        require(s && out, "NULL argument.");
+        memset(out, 0, sizeof(*out));
+        out->last_engine = s->last_engine;
+        if (!s->sparse) {
+            snprintf(out->why_not, sizeof(out->why_not), "%s", s->sparse_why.c_str());
+            return;
+        }
+        fill_table_info(s->sparse->table(), out);
+        out->favoured = s->sparse_favoured ? 1 : 0;
+        out->tile_shots = s->sparse->tile_shots();
+        out->blocks_per_sm = s->sparse->blocks_per_sm();
+        out->num_slices = (uint32_t)(s->sparse->slices().size() / 4);
+    });
+}
+
+int gstim_get_response_table(const gstim_sampler *s, int what, uint32_t *words, size_t *n_words) {
+    return guarded([&] {
+        require(s && n_words, "NULL argument.");
+        require(s->sparse != nullptr, "The circuit has no response table.");
+        export_table_array(s->sparse->table(), &s->sparse->slices(), what, words, n_words);
+    });
+}
+
+struct gstim_response_table {
+    ResponseTable rt;
+};
+
+int gstim_response_table_create(const char *circuit_text, size_t text_len, int mode, gstim_response_table **out) {
+    return guarded([&] {
+        require(circuit_text != nullptr && out != nullptr, "NULL argument.");
+        require(mode == GSTIM_MODE_DETECTORS || mode == GSTIM_MODE_MEASUREMENTS, "bad mode.");
+        *out = nullptr;
+        Circuit c = Circuit::from_text(std::string_view(circuit_text, text_len));
+        LoweredCircuit lc = lower_circuit(c, (uint32_t)mode, 2048 - GSTIM_HDR_WORDS);
+        auto t = std::make_unique<gstim_response_table>();
+        t->rt = build_response_table(lc);
+        *out = t.release();
+    });
+}
+
+void gstim_response_table_destroy(gstim_response_table *t) {
+    delete t;
+}
+
+int gstim_response_table_info(const gstim_response_table *t, gstim_engine_info *out) {
+    return guarded([&] {
+        require(t && out, "NULL argument.");
+        memset(out, 0, sizeof(*out));
+        fill_table_info(t->rt, out);
+        if (!t->rt.eligible) {
+            snprintf(out->why_not, sizeof(out->why_not), "%s", t->rt.why_not.c_str());
+        }
+    });
+}
+
+int gstim_response_table_get(const gstim_response_table *t, int what, uint32_t *words, size_t *n_words) {
+    return guarded([&] {
+        require(t && n_words, "NULL argument.");
+        require(t->rt.eligible, "The circuit has no response table.");
+        export_table_array(t->rt, nullptr, what, words, n_words);
     });
 }
 

@@ -1,0 +1,528 @@
+// response.cc — see response.h.
+#include "response.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+
+namespace gstim {
+
+namespace {
+
+constexpr uint32_t ITEM_X = 1u << 30;  // component flags in OBS_PAULI / FEEDBACK / CORR payload words (lowering.cc)
+constexpr uint32_t ITEM_Z = 1u << 31;
+constexpr uint64_t LAM_MAX = 1ull << 62;
+constexpr uint64_t LAM_HALF = 49946518145322872ull;  // floor(ln 2 * 2^56): the rate of a fair coin (collapse bits)
+
+using Set = std::vector<uint32_t>;  // sorted output ids
+
+// a ^= b (symmetric difference of sorted sets)
+void xor_into(Set &a, const Set &b, Set &tmp) {
+    if (b.empty()) {
+        return;
+    }
+    if (a.empty()) {
+        a = b;
+        return;
+    }
+    tmp.clear();
+    tmp.reserve(a.size() + b.size());
+    size_t i = 0, j = 0;
+    while (i < a.size() && j < b.size()) {
+        if (a[i] < b[j]) {
+            tmp.push_back(a[i++]);
+        } else if (b[j] < a[i]) {
+            tmp.push_back(b[j++]);
+        } else {
+            i++;
+            j++;
+        }
+    }
+    tmp.insert(tmp.end(), a.begin() + i, a.end());
+    tmp.insert(tmp.end(), b.begin() + j, b.end());
+    a.swap(tmp);
+}
+
+void xor_one(Set &a, uint32_t v) {
+    auto it = std::lower_bound(a.begin(), a.end(), v);
+    if (it != a.end() && *it == v) {
+        a.erase(it);
+    } else {
+        a.insert(it, v);
+    }
+}
+
+struct ClassKey {
+    uint64_t lam;
+    uint32_t kind, n_out;
+    uint32_t thr[15];
+    bool operator<(const ClassKey &o) const {
+        if (lam != o.lam) {
+            return lam < o.lam;
+        }
+        if (kind != o.kind) {
+            return kind < o.kind;
+        }
+        if (n_out != o.n_out) {
+            return n_out < o.n_out;
+        }
+        return memcmp(thr, o.thr, sizeof(thr)) < 0;
+    }
+};
+
+// Sites are discovered in reverse program order; every class collects its own entry words and is reversed at the end.
+struct ClassAcc {
+    ClassKey key;
+    std::vector<uint32_t> rep_word;   // outcome -> representative chooser word
+    std::vector<Set> responses;       // n_out per site, in discovery (reverse) order
+    std::vector<uint32_t> group, index;
+};
+
+// 1 / lambda = m 2^e with m in [0.5, 1): INV = floor(2^32 m), SH = 58 - e (dem.cu's gap arithmetic).
+bool gap_params(uint64_t lam, uint32_t *inv, uint32_t *sh) {
+    if (lam == 0) {
+        return false;
+    }
+    if (lam >= LAM_MAX) {
+        *inv = 0;
+        *sh = 0;
+        return true;
+    }
+    int e = 0;
+    const double m = std::frexp(std::ldexp(1.0, 56) / (double)lam, &e);
+    const int s = 58 - e;
+    if (s < 0 || s > 63) {
+        return false;
+    }
+    *inv = (uint32_t)std::min<double>(std::floor(std::ldexp(m, 32)), 4294967295.0);
+    *sh = (uint32_t)s;
+    return true;
+}
+
+}  // namespace
+
+ResponseTable build_response_table(const LoweredCircuit &lc) {
+    ResponseTable rt;
+    const uint32_t D = (uint32_t)lc.stats.num_detectors, L = (uint32_t)lc.stats.num_observables;
+    const uint32_t M = (uint32_t)lc.stats.num_measurements;
+    const bool det_mode = lc.mode == 0;
+    rt.n_outputs = det_mode ? D + L : M;
+    const uint32_t Q = lc.num_qubits;
+    const uint32_t rec_mask = det_mode ? lc.rec_ring - 1 : 0xFFFFFFFFu;
+    const size_t n_rec = det_mode ? lc.rec_ring : std::max<uint32_t>(M, 1);
+
+    auto fail = [&](const std::string &why) {
+        rt.eligible = false;
+        rt.why_not = why;
+        rt.classes.clear();
+        rt.entries.clear();
+        rt.overflow.clear();
+        return rt;
+    };
+
+    // ELSE_CORRELATED_ERROR makes sites dependent on each other (the "already occurred" row); not representable here.
+    // Forward pass: index of every noise batch's first site inside its noise group.
+    std::vector<uint32_t> gfirst(lc.batches.size(), 0);
+    {
+        std::map<uint32_t, uint32_t> seen;
+        for (size_t b = 0; b < lc.batches.size(); b++) {
+            const Batch &B = lc.batches[b];
+            if (B.op == GOP_CORR && !(B.flags & GF_RESET_FLAG) && B.lambda != 0) {
+                return fail("ELSE_CORRELATED_ERROR chain");
+            }
+            if (B.op == GOP_NOISE1 || B.op == GOP_NOISE2) {
+                uint32_t &n = seen[B.site0];
+                gfirst[b] = n;
+                n += B.n_items;
+            }
+        }
+    }
+
+    std::vector<Set> SX(Q + 1), SZ(Q + 1), SR(n_rec);
+    std::vector<uint8_t> out_dead(rt.n_outputs + 1, 0);
+    if (!det_mode) {
+        for (uint32_t m = 0; m < M; m++) {
+            SR[m] = {m};
+        }
+    }
+    Set tmp, acc, comp[4];
+    std::map<ClassKey, size_t> class_of;
+    std::vector<ClassAcc> accs;
+    uint64_t total_ids = 0;
+    const uint64_t MAX_IDS = 1ull << 28;
+
+    auto get_class = [&](const ClassKey &k, const uint32_t *rep) -> ClassAcc & {
+        auto it = class_of.find(k);
+        if (it == class_of.end()) {
+            it = class_of.emplace(k, accs.size()).first;
+            accs.emplace_back();
+            accs.back().key = k;
+            accs.back().rep_word.assign(rep, rep + k.n_out);
+        }
+        return accs[it->second];
+    };
+
+    for (size_t bi = lc.batches.size(); bi-- > 0;) {
+        const Batch &B = lc.batches[bi];
+        const uint32_t n = B.n_items;
+        switch (B.op) {
+            case GOP_CLIFF1: {
+                const uint32_t a = B.aux & 1, b = (B.aux >> 1) & 1, c = (B.aux >> 2) & 1, d = (B.aux >> 3) & 1;
+                if (a && !b && !c && d) {
+                    break;
+                }
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t q = B.payload[i];
+                    // x' = a x ^ b z, z' = c x ^ d z  =>  SX_before = a SX' ^ c SZ', SZ_before = b SX' ^ d SZ'
+                    Set nx, nz;
+                    if (a) {
+                        xor_into(nx, SX[q], tmp);
+                    }
+                    if (c) {
+                        xor_into(nx, SZ[q], tmp);
+                    }
+                    if (b) {
+                        xor_into(nz, SX[q], tmp);
+                    }
+                    if (d) {
+                        xor_into(nz, SZ[q], tmp);
+                    }
+                    SX[q].swap(nx);
+                    SZ[q].swap(nz);
+                }
+                break;
+            }
+            case GOP_CLIFF2: {
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t q1 = B.payload[i] & 0xFFFF, q2 = B.payload[i] >> 16;
+                    Set *after[4] = {&SX[q1], &SZ[q1], &SX[q2], &SZ[q2]};
+                    if (B.aux == GSTIM_MAT_CX) {
+                        // x2 ^= x1, z1 ^= z2  =>  SX1 ^= SX2', SZ2 ^= SZ1'
+                        xor_into(SX[q1], SX[q2], tmp);
+                        xor_into(SZ[q2], SZ[q1], tmp);
+                        continue;
+                    }
+                    Set before[4];
+                    for (int j = 0; j < 4; j++) {
+                        for (int k = 0; k < 4; k++) {
+                            if ((B.aux >> (4 * k + j)) & 1) {  // output k reads input j
+                                xor_into(before[j], *after[k], tmp);
+                            }
+                        }
+                    }
+                    for (int j = 0; j < 4; j++) {
+                        after[j]->swap(before[j]);
+                    }
+                }
+                break;
+            }
+            case GOP_MEASURE: {
+                const uint32_t basis = B.aux & 3, kind = (B.aux >> 2) & 3;
+                const uint32_t stride = (B.flags & GF_DET) ? 3 : 1;
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t q = B.payload[stride * i] & 0xFFFF, lq = B.payload[stride * i] >> 16;
+                    Set sm;
+                    if (kind != GK_R) {
+                        const uint32_t slot = (B.rec0 + i) & rec_mask;
+                        if ((B.flags & GF_DET) && B.payload[3 * i + 1] != 0xFFFFFFFFu) {
+                            const uint32_t d = B.payload[3 * i + 1], other = B.payload[3 * i + 2];
+                            if (!out_dead[d]) {
+                                xor_one(sm, d);
+                                xor_one(SR[other], d);
+                            }
+                            out_dead[d] = 1;
+                        }
+                        xor_into(sm, SR[slot], tmp);
+                        SR[slot].clear();
+                    }
+                    Set rr;  // response of the collapse randomisation bit
+                    if (basis == GB_Z) {
+                        rr.swap(SZ[q]);
+                        if (kind != GK_M) {
+                            SX[q].clear();
+                        }
+                        xor_into(SX[q], sm, tmp);
+                    } else if (basis == GB_X) {
+                        rr.swap(SX[q]);
+                        if (kind != GK_M) {
+                            SZ[q].clear();
+                        }
+                        xor_into(SZ[q], sm, tmp);
+                    } else {
+                        rr = SX[q];
+                        xor_into(rr, SZ[q], tmp);
+                        if (kind != GK_M) {
+                            SX[q].clear();
+                        }
+                        xor_into(SX[q], sm, tmp);
+                        SZ[q] = SX[q];
+                    }
+                    if (!rr.empty()) {
+                        ClassKey k{};
+                        k.lam = LAM_HALF;
+                        k.kind = RK_SINGLE;
+                        k.n_out = 1;
+                        const uint32_t rep = 0;
+                        ClassAcc &c = get_class(k, &rep);
+                        total_ids += rr.size();
+                        c.responses.push_back(std::move(rr));
+                        c.group.push_back(0x80000000u | B.csite0);
+                        c.index.push_back(lq);
+                    }
+                }
+                break;
+            }
+            case GOP_RECZERO:
+                for (uint32_t i = 0; i < n; i++) {
+                    SR[(B.rec0 + i) & rec_mask].clear();
+                }
+                break;
+            case GOP_XORROWS: {
+                for (size_t i = 0; i < B.dst.size(); i++) {
+                    const uint32_t d = B.dst[i];
+                    if (!out_dead[d]) {
+                        for (uint32_t j = B.off[i]; j < B.off[i + 1]; j++) {
+                            xor_one(SR[B.idx[j]], d);
+                        }
+                    }
+                    if (!(B.flags & GF_ACCUM)) {
+                        out_dead[d] = 1;
+                    }
+                }
+                break;
+            }
+            case GOP_OBS_PAULI:
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t d = B.payload[2 * i], wq = B.payload[2 * i + 1], q = wq & 0xFFFFFF;
+                    if (out_dead[d]) {
+                        continue;
+                    }
+                    if (wq & ITEM_X) {
+                        xor_one(SX[q], d);
+                    }
+                    if (wq & ITEM_Z) {
+                        xor_one(SZ[q], d);
+                    }
+                }
+                break;
+            case GOP_FEEDBACK:
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t ri = B.payload[2 * i], wq = B.payload[2 * i + 1], q = wq & 0xFFFFFF;
+                    if (wq & ITEM_X) {
+                        xor_into(SR[ri], SX[q], tmp);
+                    }
+                    if (wq & ITEM_Z) {
+                        xor_into(SR[ri], SZ[q], tmp);
+                    }
+                }
+                break;
+            case GOP_NOISE1: {
+                if (B.lambda == 0) {
+                    break;
+                }
+                // outcomes = non-empty ranges of the chooser (program.h "NOISE1 aux")
+                const uint64_t upper[4] = {B.t1, B.t2, B.t3, 1ull << 32};
+                ClassKey k{};
+                k.lam = B.lambda;
+                uint32_t cats[4], rep[4], no = 0;
+                uint64_t lo = 0;
+                for (int j = 0; j < 4; j++) {
+                    if (upper[j] > lo) {  // v in [lo, upper[j]) selects category j
+                        cats[no] = (B.aux >> (2 * j)) & 3u;
+                        rep[no] = (uint32_t)lo;
+                        if (no > 0) {
+                            k.thr[no - 1] = (uint32_t)lo;
+                        }
+                        no++;
+                        lo = upper[j];
+                    }
+                }
+                k.n_out = no;
+                k.kind = no == 1 ? RK_SINGLE : RK_THRESH;
+                ClassAcc &c = get_class(k, rep);
+                for (uint32_t ii = n; ii-- > 0;) {
+                    const uint32_t q = (B.flags & GF_NOFRAME) ? Q : B.payload[ii];
+                    // (reverse discovery order: the outcomes of a site are pushed last-to-first and the whole list is reversed)
+                    for (uint32_t o = no; o-- > 0;) {
+                        acc.clear();
+                        if (!(B.flags & GF_NOFRAME)) {
+                            if (cats[o] & 1) {
+                                xor_into(acc, SX[q], tmp);
+                            }
+                            if (cats[o] & 2) {
+                                xor_into(acc, SZ[q], tmp);
+                            }
+                        }
+                        if (B.flags & GF_REC) {
+                            xor_into(acc, SR[(B.rec0 + ii) & rec_mask], tmp);
+                        }
+                        total_ids += acc.size();
+                        c.responses.push_back(acc);
+                    }
+                    c.group.push_back(B.site0);
+                    c.index.push_back(gfirst[bi] + ii);
+                }
+                break;
+            }
+            case GOP_NOISE2: {
+                if (B.lambda == 0) {
+                    break;
+                }
+                const bool table = (B.flags & GF_TABLE) != 0;
+                const uint32_t *items = B.payload.data() + (table ? 15 : 0);
+                ClassKey k{};
+                k.lam = B.lambda;
+                uint32_t masks[16], rep[16], no = 0;
+                if (!table) {
+                    k.kind = RK_UNIFORM;
+                    k.n_out = no = 15;
+                    for (uint32_t o = 0; o < 15; o++) {
+                        masks[o] = o + 1;  // Pauli pr = o + 1: bits x1, z1, x2, z2
+                        rep[o] = (uint32_t)((((uint64_t)o << 32) + 14) / 15);  // smallest v with mulhi(v, 15) == o
+                    }
+                } else {
+                    uint64_t lo = 0;
+                    for (int j = 0; j < 16; j++) {
+                        const uint64_t hi = j < 15 ? (uint64_t)B.payload[j] : (1ull << 32);
+                        if (hi > lo) {
+                            const uint32_t pr = j < 15 ? (uint32_t)j + 1 : B.aux;
+                            const uint32_t c1 = pr >> 2, c2 = pr & 3;
+                            masks[no] = (((c1 + 1) >> 1) & 1) | ((c1 >> 1) << 1) | ((((c2 + 1) >> 1) & 1) << 2) | ((c2 >> 1) << 3);
+                            rep[no] = (uint32_t)lo;
+                            if (no > 0) {
+                                k.thr[no - 1] = (uint32_t)lo;
+                            }
+                            no++;
+                            lo = hi;
+                        }
+                    }
+                    k.n_out = no;
+                    k.kind = no == 1 ? RK_SINGLE : RK_THRESH;
+                }
+                ClassAcc &c = get_class(k, rep);
+                for (uint32_t ii = n; ii-- > 0;) {
+                    const uint32_t q1 = items[ii] & 0xFFFF, q2 = items[ii] >> 16;
+                    const Set *cs[4] = {&SX[q1], &SZ[q1], &SX[q2], &SZ[q2]};
+                    for (uint32_t o = no; o-- > 0;) {
+                        acc.clear();
+                        for (int j = 0; j < 4; j++) {
+                            if ((masks[o] >> j) & 1) {
+                                xor_into(acc, *cs[j], tmp);
+                            }
+                        }
+                        total_ids += acc.size();
+                        c.responses.push_back(acc);
+                    }
+                    c.group.push_back(B.site0);
+                    c.index.push_back(gfirst[bi] + ii);
+                }
+                break;
+            }
+            case GOP_CORR: {
+                if (B.lambda == 0) {
+                    break;
+                }
+                ClassKey k{};
+                k.lam = B.lambda;
+                k.kind = RK_SINGLE;
+                k.n_out = 1;
+                const uint32_t rep = 0;
+                ClassAcc &c = get_class(k, &rep);
+                acc.clear();
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t w = B.payload[i], q = w & 0xFFFFFF;
+                    if (w & ITEM_X) {
+                        xor_into(acc, SX[q], tmp);
+                    }
+                    if (w & ITEM_Z) {
+                        xor_into(acc, SZ[q], tmp);
+                    }
+                }
+                total_ids += acc.size();
+                c.responses.push_back(acc);
+                c.group.push_back(B.site0);
+                c.index.push_back(0);
+                break;
+            }
+            default:
+                break;
+        }
+        if (total_ids > MAX_IDS) {
+            return fail("response table too large");
+        }
+    }
+
+    // assemble: classes in a deterministic order (rate, then chooser), sites in program order
+    std::vector<size_t> order(accs.size());
+    for (size_t i = 0; i < order.size(); i++) {
+        order[i] = i;
+    }
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return accs[a].key < accs[b].key; });
+    uint64_t n_entries = 0;
+    for (size_t ci : order) {
+        n_entries += accs[ci].responses.size();
+    }
+    if (n_entries >= (1ull << 31) / 4) {
+        return fail("response table too large");
+    }
+    rt.entries.reserve(n_entries * 4);
+    for (size_t ci : order) {
+        ClassAcc &a = accs[ci];
+        RespClass rc;
+        rc.lam = a.key.lam;
+        if (!gap_params(a.key.lam, &rc.inv, &rc.sh)) {
+            continue;  // a rate too small to ever fire
+        }
+        rc.kind = a.key.kind;
+        rc.n_out = a.key.n_out;
+        memcpy(rc.thr, a.key.thr, sizeof(rc.thr));
+        rc.n_sites = (uint32_t)a.group.size();
+        rc.entry0 = (uint32_t)(rt.entries.size() / 4);
+        const double lam = std::ldexp((double)a.key.lam, -56);
+        const double p = a.key.lam >= LAM_MAX ? 1.0 : -std::expm1(-lam);
+        rt.events_per_shot += p * rc.n_sites;
+        uint64_t class_ids = 0;
+        for (const Set &s : a.responses) {
+            class_ids += s.size();
+        }
+        rt.flips_per_shot += p * (double)class_ids / rc.n_out;
+        for (size_t r = a.responses.size(); r-- > 0;) {  // reverse discovery order = program order, outcomes ascending
+            const Set &s = a.responses[r];
+            rt.max_response = std::max<uint32_t>(rt.max_response, (uint32_t)s.size());
+            uint32_t w[4] = {RESP_NONE, RESP_NONE, RESP_NONE, RESP_NONE};
+            if (s.size() <= 4) {
+                for (size_t j = 0; j < s.size(); j++) {
+                    w[j] = s[j];
+                }
+            } else {
+                for (size_t j = 0; j < 3; j++) {
+                    w[j] = s[j];
+                }
+                if (rt.overflow.size() + s.size() >= (1ull << 30)) {
+                    return fail("response table too large");
+                }
+                w[3] = RESP_OVERFLOW | (uint32_t)rt.overflow.size();
+                rt.overflow.push_back((uint32_t)(s.size() - 3));
+                rt.overflow.insert(rt.overflow.end(), s.begin() + 3, s.end());
+            }
+            rt.entries.insert(rt.entries.end(), w, w + 4);
+        }
+        for (size_t r = a.group.size(); r-- > 0;) {
+            rt.site_group.push_back(a.group[r]);
+            rt.site_index.push_back(a.index[r]);
+        }
+        rt.outcome_word.insert(rt.outcome_word.end(), a.rep_word.begin(), a.rep_word.end());
+        rt.n_sites += rc.n_sites;
+        rt.classes.push_back(rc);
+    }
+    rt.n_entries = rt.entries.size() / 4;
+    if (rt.n_outputs >= (1u << 30)) {
+        return fail("too many output bits");
+    }
+    rt.eligible = true;
+    return rt;
+}
+
+}  // namespace gstim

@@ -1,0 +1,72 @@
+// response.h — the propagated-response table of a lowered circuit (host side of the event-driven engine, sparse.cu).
+//
+// A Pauli-frame simulation is linear over GF(2): every output bit (detector, observable, or measurement flip) is the
+// XOR of the contributions of the random bits the run drew — which noise site fired with which Pauli, which collapse
+// randomisation bit was set (/root/reference/src/stim/simulators/frame_simulator.inl:173-317 only ever XORs frame rows
+// into frame rows, record rows and outputs). The reference evaluates that linear map once per shot by pushing dense
+// frame words through every gate. For rare noise almost all of those words are zero, so this engine evaluates the map
+// the other way round: the response of every (noise site, outcome) — the set of output bits it flips — is computed once
+// per circuit by propagating sensitivities BACKWARDS through the lowered program, and a shot is the XOR of the responses
+// of the events that fired in it (same sampling distribution as the reference: every site is an independent
+// Bernoulli(p) with the channel's own outcome distribution, exactly like RareErrorIterator over targets x shots,
+// /root/reference/src/stim/util_bot/probability_util.cc:23-43).
+//
+// The backward pass keeps, per frame row, the sets SX[q] / SZ[q] of output bits that an X / Z flip of q at the current
+// point of the program would flip, and per record slot the set SR[m]; it walks lc.batches in reverse:
+//   gate with GF(2) matrix A      S_before = A^T S_after
+//   MEASURE (m = x, z <- random)  SX ^= SR[slot] (^ fused detector), SZ <- {} ; the random bit's own response is SZ_after
+//   XORROWS / OBS_PAULI / FEEDBACK add the destination's sensitivity to their sources
+//   NOISE / CORR                  snapshot: response(outcome) = XOR of the flipped components' sets
+// A circuit is ELIGIBLE when every collapse randomisation bit has an empty response (deterministic detectors: the usual
+// case for QEC circuits), it has no ELSE_CORRELATED_ERROR chain, and the table stays within bounds; otherwise the
+// interpreter (interp.cu) samples it.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "lowering.h"
+
+namespace gstim {
+
+constexpr uint32_t RESP_NONE = 0xFFFFFFFFu;      // empty slot of a table entry
+constexpr uint32_t RESP_OVERFLOW = 0x80000000u;  // last slot: 0x80000000 | offset into `overflow` (count, then ids)
+
+enum RespKind : uint32_t {
+    RK_SINGLE = 0,   // one outcome
+    RK_UNIFORM = 1,  // outcome = mulhi(v, n_out)            (DEPOLARIZE2: frame_simulator.inl:651-659)
+    RK_THRESH = 2,   // outcome = number of thresholds <= v  (PAULI_CHANNEL_*, DEPOLARIZE1, HERALDED_*)
+};
+
+struct RespClass {
+    uint64_t lam = 0;            // event rate of the class, fixed point (lowering.cc rate_of)
+    uint32_t inv = 0, sh = 0;    // gap arithmetic: gap = (E * inv) >> sh  (E = Exp(1) in units of 2^-26 nat); inv = 0: always fires
+    uint32_t kind = RK_SINGLE;
+    uint32_t n_out = 1;          // outcomes per site (<= 16)
+    uint32_t thr[15] = {0};      // RK_THRESH: ascending upper bounds of outcomes 0 .. n_out - 2 on a uniform u32
+    uint32_t n_sites = 0;
+    uint32_t entry0 = 0;         // table entry of (site s, outcome o) = entry0 + s * n_out + o
+};
+
+struct ResponseTable {
+    bool eligible = false;
+    std::string why_not;             // reason when not eligible
+    uint32_t n_outputs = 0;          // D + L (detector mode) or M (measurement mode)
+    std::vector<RespClass> classes;
+    std::vector<uint32_t> entries;   // 4 words per entry: output ids ascending, RESP_NONE padded; > 4 ids: 3 ids + overflow link
+    std::vector<uint32_t> overflow;  // [count, id, id, ...] blocks
+    // provenance of every site, in class-major table order (tests re-derive the responses by forward injection):
+    std::vector<uint32_t> site_group;  // noise group (Philox word 0 of the interpreter's stream for it)
+    std::vector<uint32_t> site_index;  // index of the site inside its group
+    // outcome -> representative Pauli word v of the interpreter's chooser, per class (n_out values each), for the same tests
+    std::vector<uint32_t> outcome_word;
+    uint64_t n_sites = 0, n_entries = 0;
+    uint32_t max_response = 0;       // largest number of output bits of one entry
+    double events_per_shot = 0;      // expected number of events per shot
+    double flips_per_shot = 0;       // expected number of output bit flips per shot (before cancellation)
+};
+
+// Builds the table from the lowered batches (before or after serialisation; only lc.batches / lc.mode / lc.rec_ring are read).
+ResponseTable build_response_table(const LoweredCircuit &lc);
+
+}  // namespace gstim

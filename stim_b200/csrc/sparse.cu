@@ -1,0 +1,619 @@
+// sparse.cu — the event-driven engine: samples detection events from the propagated-response table (response.h).
+//
+// Replaces the same reference path as the interpreter (FrameSimulator::do_circuit over a batch of shots,
+// /root/reference/src/stim/simulators/frame_simulator.inl:166-170, with the transposing writer behind it,
+// /root/reference/src/stim/io/measure_record_writer.h:101-166) for circuits whose response table exists (response.h
+// "ELIGIBLE"). Nothing is simulated per gate: a shot's output row is the XOR of the responses of the noise events that
+// fired in it, so the work per shot is O(events), not O(gates).
+//
+//   * A thread block owns a TILE of S = 2^k consecutive shots and keeps the tile's output image — S dense shot-major
+//     rows, byte for byte what the caller's b8 array holds for those shots — in shared memory.
+//   * The (site x shot) Bernoulli trials of a tile are cut into SLICES (one class, a run of consecutive sites, all S shots;
+//     site-major like the reference's RareErrorIterator over targets x shots, probability_util.cc:33-43). Threads claim
+//     slices from a shared counter and walk them with geometric gaps: gap = floor(Exp(1) / lambda) in the 32-bit fixed
+//     point of dem.cu (exactly Geometric(p) up to the 2^-26 nat resolution of the exponential).
+//   * An event picks its outcome (the channel's Pauli) from the second word of its draw, loads the 16-byte table entry of
+//     (site, outcome) — up to four output bit positions, more through an overflow list — and flips those bits of its
+//     shot's row with red.shared.xor.
+//   * When the slice pool is dry the block stores the image to global memory with 16-byte coalesced stores (the image is
+//     kept at the same 16-byte phase as its destination, so rows of odd length — c3: 1951 B — need no shuffling) and
+//     moves to its next tile. There is no bit-major table and no transposer pass: HBM sees the output bytes once.
+//
+// RNG addressing (restated bit for bit by oracle/sparse_oracle.py): Philox4x32-10, key = seed,
+//     counter = (slice index, call, tile lo, 'SP' << 20 | tile hi),  tile = global shot index / S,
+// call c of a slice -> draws 2c (words 0, 1) and 2c + 1 (words 2, 3); a draw = (gap word, outcome word). The draw
+// that overshoots the slice ends it; a slice also ends when its last trial fired.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "sparse.cuh"
+
+#define GSTIM_TABLE_QUAL __device__ const
+#include "log2_q26_table.h"
+
+namespace gstim {
+
+namespace {
+
+constexpr uint32_t SPARSE_TAG = 0x53500000u;  // 'SP' << 20
+constexpr uint32_t SMEM_CLASSES = 24;         // classes mirrored in shared memory (more: read from global memory)
+
+struct SparseParams {
+    const uint4 *slices;  // x = class, y = trials (sites << log_s), z = table entry of the slice's first site, w = unused
+    uint32_t n_slices;
+    const SparseClassDev *classes;
+    uint32_t n_classes;
+    const uint4 *entries;
+    const uint32_t *overflow;
+    const uint8_t *init_row;  // measurement mode: reference sample (main_bytes bytes) every row starts from, or null
+    uint32_t log_s;
+    uint32_t n_tiles;
+    uint64_t tile0;    // global index of tile 0 of this launch
+    uint64_t n_shots;  // valid shots of this launch
+    uint8_t *main_out;
+    uint64_t main_pitch;
+    uint32_t main_bytes;
+    uint8_t *obs_out;
+    uint64_t obs_pitch;
+    uint32_t obs_bytes;
+    uint32_t obs_img_off;  // byte offset of the observable image inside the tile's shared memory (multiple of 16)
+    uint32_t img_bytes;    // bytes of both images (multiple of 16)
+    uint32_t seed_lo, seed_hi;
+};
+
+__device__ __forceinline__ uint4 sp_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ void flip_bit(uint32_t img_saddr, uint32_t bit) {
+    asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(img_saddr + ((bit >> 5) << 2)), "r"(1u << (bit & 31u)) : "memory");
+}
+
+// Copies `nbytes` bytes from shared memory (image coordinate `phase`) to dst, where (dst & 15) == phase.
+__device__ __forceinline__ void store_span(const uint8_t *img, uint32_t phase, uint8_t *dst, uint64_t nbytes) {
+    const uint64_t end = phase + nbytes;
+    uint8_t *const g0 = dst - phase;  // 16-byte aligned
+    for (uint64_t c = (uint64_t)threadIdx.x * 16; c < end; c += (uint64_t)blockDim.x * 16) {
+        if (c >= phase && c + 16 <= end) {
+            *reinterpret_cast<uint4 *>(g0 + c) = *reinterpret_cast<const uint4 *>(img + c);
+        } else {
+            for (uint64_t b = c < phase ? phase : c; b < c + 16 && b < end; b++) {
+                g0[b] = img[b];
+            }
+        }
+    }
+}
+
+template <bool SEPARATE>
+__global__ void __launch_bounds__(384, 3) gstim_sparse_kernel(const SparseParams p) {
+    extern __shared__ uint4 smem4[];
+    uint2 *const lt = reinterpret_cast<uint2 *>(smem4);                                 // 256 x (base, diff): 2 KiB
+    SparseClassDev *const scls = reinterpret_cast<SparseClassDev *>(lt + 256);            // SMEM_CLASSES x 80 B
+    uint32_t *const ctl = reinterpret_cast<uint32_t *>(scls + SMEM_CLASSES);              // [0] = next slice
+    uint8_t *const img = reinterpret_cast<uint8_t *>(ctl + 4);                            // 16-byte aligned
+    const uint32_t img_saddr = (uint32_t)__cvta_generic_to_shared(img);
+
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        lt[i] = make_uint2(GSTIM_LOG2_Q26[2 * i], GSTIM_LOG2_Q26[2 * i + 1]);
+    }
+    const bool cls_in_smem = p.n_classes <= SMEM_CLASSES;
+    if (cls_in_smem) {
+        const uint32_t words = p.n_classes * (uint32_t)(sizeof(SparseClassDev) / 4);
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) {
+            reinterpret_cast<uint32_t *>(scls)[i] = reinterpret_cast<const uint32_t *>(p.classes)[i];
+        }
+    }
+    const SparseClassDev *const cls = cls_in_smem ? scls : p.classes;
+    const uint32_t S = 1u << p.log_s, smask = S - 1u;
+    const uint32_t main_bits = p.main_bytes * 8u, obs_bits = p.obs_bytes * 8u;
+    const bool main_dense = p.main_pitch == p.main_bytes, obs_dense = p.obs_pitch == p.obs_bytes;
+
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const uint64_t shot0 = (uint64_t)tile << p.log_s;
+        const uint32_t n_valid = (uint32_t)min((uint64_t)S, p.n_shots - shot0);
+        // the image sits at the 16-byte phase of its destination
+        uint32_t phase_m = 0, phase_o = 0;
+        if (p.main_out != nullptr && main_dense) {
+            phase_m = (uint32_t)((reinterpret_cast<uintptr_t>(p.main_out) + shot0 * p.main_bytes) & 15u);
+        }
+        if (SEPARATE && p.obs_out != nullptr && obs_dense) {
+            phase_o = (uint32_t)((reinterpret_cast<uintptr_t>(p.obs_out) + shot0 * p.obs_bytes) & 15u);
+        }
+        __syncthreads();  // the previous tile's stores have read the image (also covers the table loads above)
+        for (uint32_t i = threadIdx.x; i < p.img_bytes / 16; i += blockDim.x) {
+            reinterpret_cast<uint4 *>(img)[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (threadIdx.x == 0) {
+            ctl[0] = 0;
+        }
+        __syncthreads();
+        if (p.init_row != nullptr) {
+            for (uint32_t i = threadIdx.x; i < S * p.main_bytes; i += blockDim.x) {
+                img[phase_m + i] = p.init_row[i % p.main_bytes];
+            }
+            __syncthreads();
+        }
+        const uint32_t base_m = phase_m * 8u, base_o = (p.obs_img_off + phase_o) * 8u;
+        const uint64_t gt = p.tile0 + tile;
+        const uint32_t c2 = (uint32_t)gt, c3 = SPARSE_TAG | (uint32_t)(gt >> 32);
+
+        auto flip = [&](uint32_t shot, uint32_t v) {
+            if (SEPARATE && (v & 0x40000000u)) {
+                flip_bit(img_saddr, base_o + shot * obs_bits + (v & 0x3FFFFFFFu));
+            } else {
+                flip_bit(img_saddr, base_m + shot * main_bits + v);
+            }
+        };
+
+        bool active = false;
+        uint32_t sl = 0, a = 0, total = 0, call = 0, inv = 0, sh = 0, ebase = 0, n_out = 1, kind = 0;
+        const SparseClassDev *cl = cls;
+        while (true) {
+            if (!active) {
+                sl = atomicAdd(&ctl[0], 1u);
+                if (sl >= p.n_slices) {
+                    break;
+                }
+                const uint4 d = __ldg(p.slices + sl);
+                cl = cls + d.x;
+                inv = cl->inv;
+                sh = cl->sh;
+                kind = cl->kind;
+                n_out = cl->n_out;
+                total = d.y;
+                ebase = d.z;
+                a = 0;
+                call = 0;
+                active = true;
+            }
+            const uint4 r = sp_philox(sl, call, c2, c3, p.seed_lo, p.seed_hi);
+            call++;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (!active) {
+                    continue;
+                }
+                const uint32_t gw = h ? r.z : r.x, pw = h ? r.w : r.y;
+                // E = -ln(v / 2^32) in units of 2^-26 nat (dem.cu header)
+                const uint32_t v = gw | 1u;
+                const uint32_t t = 31u - (uint32_t)__clz((int)v);
+                const uint32_t frac = (v << (31u - t)) << 1;
+                const uint2 en = lt[frac >> 24];
+                const uint32_t log2v = (t << 26) + en.x + ((en.y * ((frac >> 11) & 0x1FFFu)) >> 13);
+                const uint32_t E = __umulhi(0x80000000u - log2v, GSTIM_LN2_Q32);
+                const unsigned long long G = ((unsigned long long)E * inv) >> sh;
+                if (G >= (unsigned long long)(total - a)) {
+                    active = false;
+                    continue;
+                }
+                a += (uint32_t)G;
+                const uint32_t site = a >> p.log_s, shot = a & smask;
+                a++;
+                if (a >= total) {
+                    active = false;
+                }
+                uint32_t o = 0;
+                if (kind == RK_UNIFORM) {
+                    o = __umulhi(pw, n_out);
+                } else if (kind == RK_THRESH) {
+                    for (uint32_t j = 0; j + 1 < n_out; j++) {
+                        o += pw >= cl->thr[j] ? 1u : 0u;
+                    }
+                }
+                const uint4 e = __ldg(p.entries + (ebase + site * n_out + o));
+                if (e.x == RESP_NONE) {
+                    continue;
+                }
+                flip(shot, e.x);
+                if (e.y == RESP_NONE) {
+                    continue;
+                }
+                flip(shot, e.y);
+                if (e.z == RESP_NONE) {
+                    continue;
+                }
+                flip(shot, e.z);
+                if (e.w == RESP_NONE) {
+                    continue;
+                }
+                if (e.w & RESP_OVERFLOW) {
+                    const uint32_t *ov = p.overflow + (e.w & 0x7FFFFFFFu);
+                    const uint32_t cnt = __ldg(ov);
+                    for (uint32_t j = 1; j <= cnt; j++) {
+                        flip(shot, __ldg(ov + j));
+                    }
+                } else {
+                    flip(shot, e.w);
+                }
+            }
+        }
+        __syncthreads();
+        // store the image
+        if (p.main_out != nullptr && p.main_bytes) {
+            if (main_dense) {
+                store_span(img, phase_m, p.main_out + shot0 * p.main_bytes, (uint64_t)n_valid * p.main_bytes);
+            } else {
+                for (uint32_t i = threadIdx.x; i < n_valid * p.main_bytes; i += blockDim.x) {
+                    const uint32_t row = i / p.main_bytes, col = i - row * p.main_bytes;
+                    p.main_out[(shot0 + row) * p.main_pitch + col] = img[i];
+                }
+            }
+        }
+        if (SEPARATE && p.obs_out != nullptr && p.obs_bytes) {
+            const uint8_t *oimg = img + p.obs_img_off;
+            if (obs_dense) {
+                store_span(oimg, phase_o, p.obs_out + shot0 * p.obs_bytes, (uint64_t)n_valid * p.obs_bytes);
+            } else {
+                for (uint32_t i = threadIdx.x; i < n_valid * p.obs_bytes; i += blockDim.x) {
+                    const uint32_t row = i / p.obs_bytes, col = i - row * p.obs_bytes;
+                    p.obs_out[(shot0 + row) * p.obs_pitch + col] = oimg[i];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flip counts of dense b8 rows: single[b] += popcount over shots of bit b, pair[b] += bit b AND bit b + 1
+// (the statistics the 5-sigma tests and the per-detector count allreduce use; the reference has no such kernel — it is
+// what a caller computes from the b8 array).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gstim_count_b8_kernel(const uint8_t *rows, uint64_t pitch, uint64_t n_shots, uint32_t n_bits,
+                                                            unsigned long long *single, unsigned long long *pair) {
+    const uint32_t n_bytes = (n_bits + 7) / 8;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_bytes) {
+        return;
+    }
+    const uint64_t per = (n_shots + gridDim.y - 1) / gridDim.y;
+    const uint64_t s0 = (uint64_t)blockIdx.y * per, s1 = min(n_shots, s0 + per);
+    uint32_t c1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool has_next = j + 1 < n_bytes;
+    for (uint64_t s = s0; s < s1; s++) {
+        const uint8_t *row = rows + s * pitch;
+        const uint32_t b = row[j] | (has_next ? (uint32_t)row[j + 1] << 8 : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            c1[k] += (b >> k) & 1u;
+            c2[k] += (b >> k) & (b >> (k + 1)) & 1u;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t bit = j * 8 + k;
+        if (bit < n_bits && c1[k]) {
+            atomicAdd(single + bit, (unsigned long long)c1[k]);
+        }
+        if (pair != nullptr && bit + 1 < n_bits && c2[k]) {
+            atomicAdd(pair + bit, (unsigned long long)c2[k]);
+        }
+    }
+}
+
+void ck(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) {
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+        }
+        throw std::runtime_error(std::string("CUDA error '") + cudaGetErrorString(e) + "' in " + what);
+    }
+}
+
+uint32_t align16(uint32_t v) {
+    return (v + 15u) & ~15u;
+}
+
+constexpr uint32_t SPARSE_THREADS = 384;
+constexpr size_t FIXED_SMEM = 256 * 8 + SMEM_CLASSES * sizeof(SparseClassDev) + 16;
+
+}  // namespace
+
+cudaError_t launch_count_b8(const uint8_t *rows, uint64_t pitch, uint64_t n_shots, uint32_t n_bits, unsigned long long *single,
+                            unsigned long long *pair, cudaStream_t stream) {
+    if (n_bits == 0 || n_shots == 0) {
+        return cudaSuccess;
+    }
+    const uint32_t n_bytes = (n_bits + 7) / 8;
+    dim3 grid((n_bytes + 127) / 128, (unsigned)std::min<uint64_t>((n_shots + 255) / 256, 4096));
+    gstim_count_b8_kernel<<<grid, 128, 0, stream>>>(rows, pitch, n_shots, n_bits, single, pair);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// SparseEngine
+// ------------------------------------------------------------------------------------------------
+struct SparseEngine::Impl {
+    int device = 0;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    uint32_t D = 0, L = 0, M = 0, mode = 0;
+    ResponseTable rt;
+    uint32_t log_s = 0;
+    uint32_t blocks_per_sm = 1;
+    uint32_t layout_flags = 0xFFFFFFFFu;  // layout the device table is encoded for
+    uint32_t main_bits = 0, obs_bits = 0;
+    void *d_slices = nullptr, *d_classes = nullptr, *d_entries = nullptr, *d_overflow = nullptr, *d_init = nullptr;
+    uint32_t n_slices = 0;
+    std::vector<uint32_t> slices_host;  // 4 words per slice (tests / oracle)
+    ~Impl() {
+        for (void *p : {d_slices, d_classes, d_entries, d_overflow, d_init}) {
+            if (p) {
+                cudaFree(p);
+            }
+        }
+    }
+};
+
+SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32_t L, uint32_t M, int device, uint32_t slice_events)
+    : impl(new Impl()) {
+    Impl &I = *impl;
+    I.rt = std::move(rt);
+    I.device = device;
+    I.mode = mode;
+    I.D = D;
+    I.L = L;
+    I.M = M;
+    cudaDeviceProp prop;
+    ck(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    I.num_sms = prop.multiProcessorCount;
+    I.smem_optin = prop.sharedMemPerBlockOptin;
+
+    // Tile height: the largest power of two <= 128 whose image lets three blocks share an SM (then two, then one).
+    // It depends on the circuit only (not on the output layout), so the random stream does too.
+    const uint32_t row_all = mode == 0 ? (D + 7) / 8 + (L + 7) / 8 + 1 : (M + 7) / 8 + 1;
+    const size_t per_sm = (size_t)prop.sharedMemPerMultiprocessor;
+    bool ok = false;
+    for (uint32_t blocks = 3; blocks >= 1 && !ok; blocks--) {
+        const size_t budget = std::min<size_t>(I.smem_optin, per_sm / blocks - 1024) - FIXED_SMEM - 64;
+        for (int ls = 7; ls >= (blocks == 1 ? 0 : 2); ls--) {
+            if (((size_t)row_all << ls) <= budget) {
+                I.log_s = (uint32_t)ls;
+                I.blocks_per_sm = blocks;
+                ok = true;
+                break;
+            }
+        }
+    }
+    if (!ok) {
+        throw std::invalid_argument("output row does not fit in shared memory");
+    }
+    const uint32_t S = 1u << I.log_s;
+
+    // slices: runs of sites with about `slice_events` expected events per tile
+    std::vector<SparseClassDev> cls;
+    for (const RespClass &c : I.rt.classes) {
+        SparseClassDev d{};
+        d.inv = c.inv;
+        d.sh = c.sh;
+        d.kind = c.kind;
+        d.n_out = c.n_out;
+        memcpy(d.thr, c.thr, sizeof(c.thr));
+        cls.push_back(d);
+        const double lam = std::ldexp((double)c.lam, -56);
+        const double pr = c.inv == 0 ? 1.0 : -std::expm1(-lam);
+        double want = (double)slice_events / (pr * S);
+        uint32_t per = (uint32_t)std::max(1.0, std::min(want, (double)((1u << 30) >> I.log_s)));
+        for (uint32_t s0 = 0; s0 < c.n_sites; s0 += per) {
+            const uint32_t ns = std::min(per, c.n_sites - s0);
+            I.slices_host.push_back((uint32_t)(cls.size() - 1));
+            I.slices_host.push_back(ns << I.log_s);
+            I.slices_host.push_back(c.entry0 + s0 * c.n_out);
+            I.slices_host.push_back(0);
+        }
+    }
+    I.n_slices = (uint32_t)(I.slices_host.size() / 4);
+    ck(cudaSetDevice(device), "cudaSetDevice");
+    auto up = [&](void **d, const void *src, size_t bytes) {
+        ck(cudaMalloc(d, std::max<size_t>(bytes, 16)), "cudaMalloc (response table)");
+        if (bytes && src) {
+            ck(cudaMemcpy(*d, src, bytes, cudaMemcpyHostToDevice), "upload (response table)");
+        }
+    };
+    up(&I.d_slices, I.slices_host.data(), I.slices_host.size() * 4);
+    up(&I.d_classes, cls.data(), cls.size() * sizeof(SparseClassDev));
+    up(&I.d_overflow, nullptr, I.rt.overflow.size() * 4);
+    up(&I.d_entries, nullptr, I.rt.entries.size() * 4);
+    ck(cudaFuncSetAttribute(gstim_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_optin), "smem attribute");
+    ck(cudaFuncSetAttribute(gstim_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_optin), "smem attribute");
+}
+
+SparseEngine::~SparseEngine() {
+    delete impl;
+}
+
+const ResponseTable &SparseEngine::table() const {
+    return impl->rt;
+}
+uint32_t SparseEngine::tile_shots() const {
+    return 1u << impl->log_s;
+}
+uint32_t SparseEngine::blocks_per_sm() const {
+    return impl->blocks_per_sm;
+}
+const std::vector<uint32_t> &SparseEngine::slices() const {
+    return impl->slices_host;
+}
+
+void SparseEngine::set_reference_row(const uint8_t *packed, size_t n_bytes) {
+    Impl &I = *impl;
+    ck(cudaSetDevice(I.device), "cudaSetDevice");
+    if (I.d_init) {
+        cudaFree(I.d_init);
+        I.d_init = nullptr;
+    }
+    bool any = false;
+    for (size_t i = 0; packed != nullptr && i < n_bytes; i++) {
+        any |= packed[i] != 0;
+    }
+    if (!any) {
+        return;
+    }
+    ck(cudaMalloc(&I.d_init, n_bytes), "cudaMalloc");
+    ck(cudaMemcpy(I.d_init, packed, n_bytes, cudaMemcpyHostToDevice), "upload reference row");
+}
+
+// Output ids -> bit positions of the requested layout (flags: GSTIM_PREPEND_OBS / GSTIM_APPEND_OBS / GSTIM_SEPARATE_OBS of gstim.h).
+void SparseEngine::set_layout(uint32_t flags, cudaStream_t stream) {
+    Impl &I = *impl;
+    if (flags == I.layout_flags) {
+        return;
+    }
+    const uint32_t D = I.D, L = I.L;
+    const bool prepend = flags & 0x02u, append = flags & 0x04u, separate = flags & 0x08u;
+    if (I.mode != 0) {
+        I.main_bits = I.M;
+        I.obs_bits = 0;
+    } else {
+        I.main_bits = D + ((prepend || append) ? L : 0);
+        I.obs_bits = separate ? L : 0;
+    }
+    auto map = [&](uint32_t id) -> uint32_t {
+        if (I.mode != 0) {
+            return id;
+        }
+        if (id < D) {
+            return prepend ? id + L : id;
+        }
+        const uint32_t l = id - D;
+        if (prepend) {
+            return l;
+        }
+        if (append) {
+            return D + l;
+        }
+        if (separate) {
+            return 0x40000000u | l;
+        }
+        return RESP_NONE;  // observables are not part of this output
+    };
+    // re-encode entries: dropped ids are squeezed out (slots stay ascending-then-NONE)
+    std::vector<uint32_t> ent(I.rt.entries.size()), ovf(I.rt.overflow.size());
+    std::vector<uint32_t> ids;
+    for (size_t e = 0; e < I.rt.entries.size(); e += 4) {
+        ids.clear();
+        const uint32_t *w = &I.rt.entries[e];
+        for (int j = 0; j < 4; j++) {
+            if (w[j] == RESP_NONE) {
+                break;
+            }
+            if (j == 3 && (w[j] & RESP_OVERFLOW)) {
+                const uint32_t off = w[j] & 0x7FFFFFFFu, cnt = I.rt.overflow[off];
+                for (uint32_t k = 1; k <= cnt; k++) {
+                    ids.push_back(I.rt.overflow[off + k]);
+                }
+                break;
+            }
+            ids.push_back(w[j]);
+        }
+        size_t n = 0;
+        for (uint32_t id : ids) {
+            const uint32_t v = map(id);
+            if (v != RESP_NONE) {
+                ids[n++] = v;
+            }
+        }
+        ids.resize(n);
+        uint32_t o[4] = {RESP_NONE, RESP_NONE, RESP_NONE, RESP_NONE};
+        if (n <= 4) {
+            for (size_t j = 0; j < n; j++) {
+                o[j] = ids[j];
+            }
+        } else {
+            // reuse the entry's own overflow block (the mapped list is never longer than the original)
+            const uint32_t off = w[3] & 0x7FFFFFFFu;
+            for (size_t j = 0; j < 3; j++) {
+                o[j] = ids[j];
+            }
+            o[3] = RESP_OVERFLOW | off;
+            ovf[off] = (uint32_t)(n - 3);
+            for (size_t j = 3; j < n; j++) {
+                ovf[off + 1 + (j - 3)] = ids[j];
+            }
+        }
+        memcpy(&ent[e], o, 16);
+    }
+    ck(cudaSetDevice(I.device), "cudaSetDevice");
+    ck(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    if (!ent.empty()) {
+        ck(cudaMemcpy(I.d_entries, ent.data(), ent.size() * 4, cudaMemcpyHostToDevice), "upload entries");
+    }
+    if (!ovf.empty()) {
+        ck(cudaMemcpy(I.d_overflow, ovf.data(), ovf.size() * 4, cudaMemcpyHostToDevice), "upload overflow");
+    }
+    I.layout_flags = flags;
+}
+
+uint32_t SparseEngine::main_bits() const {
+    return impl->main_bits;
+}
+uint32_t SparseEngine::obs_bits() const {
+    return impl->obs_bits;
+}
+
+void SparseEngine::launch(uint64_t first_shot, uint64_t n_shots, uint8_t *main_out, uint64_t main_pitch, uint8_t *obs_out,
+                          uint64_t obs_pitch, uint64_t seed, cudaStream_t stream) {
+    Impl &I = *impl;
+    if (n_shots == 0) {
+        return;
+    }
+    const uint32_t S = 1u << I.log_s;
+    if (first_shot % S != 0) {
+        throw std::invalid_argument("shot offset must be a multiple of the engine's tile height (" + std::to_string(S) + " shots)");
+    }
+    SparseParams p{};
+    p.slices = (const uint4 *)I.d_slices;
+    p.n_slices = I.n_slices;
+    p.classes = (const SparseClassDev *)I.d_classes;
+    p.n_classes = (uint32_t)I.rt.classes.size();
+    p.entries = (const uint4 *)I.d_entries;
+    p.overflow = (const uint32_t *)I.d_overflow;
+    p.init_row = (const uint8_t *)I.d_init;
+    p.log_s = I.log_s;
+    const uint64_t n_tiles = (n_shots + S - 1) / S;
+    if (n_tiles >= (1ull << 31)) {
+        throw std::invalid_argument("too many shots in one launch");
+    }
+    p.n_tiles = (uint32_t)n_tiles;
+    p.tile0 = first_shot >> I.log_s;
+    p.n_shots = n_shots;
+    p.main_bytes = (I.main_bits + 7) / 8;
+    p.obs_bytes = (I.obs_bits + 7) / 8;
+    p.main_out = main_out;
+    p.main_pitch = main_pitch ? main_pitch : p.main_bytes;
+    p.obs_out = obs_out;
+    p.obs_pitch = obs_pitch ? obs_pitch : p.obs_bytes;
+    p.obs_img_off = align16(p.main_bytes * S + 16);
+    p.img_bytes = p.obs_img_off + align16(p.obs_bytes * S + 16);
+    p.seed_lo = (uint32_t)seed;
+    p.seed_hi = (uint32_t)(seed >> 32);
+    const size_t smem = FIXED_SMEM + p.img_bytes;
+    if (smem > I.smem_optin) {
+        throw std::invalid_argument("internal: tile image exceeds shared memory");
+    }
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)I.num_sms * I.blocks_per_sm);
+    if (I.obs_bits) {
+        gstim_sparse_kernel<true><<<grid, SPARSE_THREADS, smem, stream>>>(p);
+    } else {
+        gstim_sparse_kernel<false><<<grid, SPARSE_THREADS, smem, stream>>>(p);
+    }
+    ck(cudaGetLastError(), "gstim_sparse_kernel launch");
+}
+
+}  // namespace gstim

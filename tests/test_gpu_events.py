@@ -1,0 +1,156 @@
+"""GPU parity of the event-driven engine (stim_b200/csrc/sparse.cu): bit for bit against oracle/sparse_oracle.sample
+(the restatement of its sampling on the exported response table) for the same (seed, shot offset); the table itself is
+checked against forward injection on the frame oracle in tests/test_response_table.py (CPU), and the engine as a whole
+against the reference CLI's deterministic outputs (test_gpu_golden.py runs under both engines) and 2^24-shot reference
+statistics (test_gpu_stats_big.py)."""
+import numpy as np
+import pytest
+
+import stim_b200
+from conftest import gen_circuit
+from oracle import sparse_oracle as so
+from test_gpu_parity import ALL_OPS
+
+pytestmark = pytest.mark.gpu
+
+ALL_OPS_NO_ELSE = "\n".join(l for l in ALL_OPS.split("\n") if not l.startswith("ELSE_CORRELATED_ERROR"))
+
+
+def oracle_rows(s, seed, first_shot, shots, n_outputs):
+    t = s.response_table()
+    return so.sample(t, t["slices"], s.engine_info()["tile_shots"], seed, first_shot, shots, n_outputs)
+
+
+def check_detectors(text, shots, seed, **kw):
+    s = stim_b200.Circuit(text).compile_detector_sampler(seed=seed, engine="events")
+    D, L = int(s.stats.num_detectors), int(s.stats.num_observables)
+    off = s.shot_offset
+    dets, obs = s.sample(shots, separate_observables=True, **kw)
+    assert s.engine_info()["last_engine"] == "events"
+    want = oracle_rows(s, seed, off, shots, D + L)
+    np.testing.assert_array_equal(dets.astype(np.uint8), want[:, :D])
+    np.testing.assert_array_equal(obs.astype(np.uint8), want[:, D:])
+    return s, want
+
+
+GENERATED = [
+    ("repetition_code", "memory", 3, 10, 0.02),
+    ("surface_code", "rotated_memory_z", 3, 3, 0.02),
+    ("surface_code", "rotated_memory_x", 5, 5, 0.01),
+    ("color_code", "memory_xyz", 3, 3, 0.02),
+    ("color_code", "memory_xyz", 5, 2, 0.01),
+]
+
+
+@pytest.mark.parametrize("code,task,d,r,p", GENERATED)
+@pytest.mark.parametrize("shots", [1, 200, 1500])
+def test_generated_detectors_match_oracle(code, task, d, r, p, shots):
+    check_detectors(gen_circuit(code, task, d, r, p), shots, seed=4321 + shots)
+
+
+def test_every_instruction_detectors_match_oracle():
+    s, _ = check_detectors(ALL_OPS_NO_ELSE, 700, seed=2025)
+    info = s.engine_info()
+    assert info["eligible"] == 1 and info["max_response"] >= 5 and info["overflow_words"] > 0
+
+
+def test_every_instruction_measurements_match_oracle():
+    seed = 31
+    s = stim_b200.Circuit(ALL_OPS_NO_ELSE).compile_sampler(seed=seed, skip_reference_sample=True, engine="events")
+    M = int(s.stats.num_measurements)
+    m = s.sample(600)
+    assert s.engine_info()["last_engine"] == "events"
+    np.testing.assert_array_equal(m.astype(np.uint8), oracle_rows(s, seed, 0, 600, M))
+    # the reference sample is XORed in (rows start from it)
+    ref = np.zeros(M, dtype=np.bool_)
+    ref[::3] = True
+    s2 = stim_b200.Circuit(ALL_OPS_NO_ELSE).compile_sampler(seed=seed, reference_sample=ref, engine="events")
+    np.testing.assert_array_equal(s2.sample(600), m ^ ref[None, :])
+
+
+def test_else_chain_is_not_eligible():
+    s = stim_b200.Circuit(ALL_OPS).compile_detector_sampler(seed=1)
+    info = s.engine_info()
+    assert info["eligible"] == 0 and "ELSE" in info["why_not"]
+    with pytest.raises(ValueError):
+        s.set_engine("events")
+    s.sample(10)
+    assert s.engine_info()["last_engine"] == "interp"
+
+
+def test_layouts_strides_and_stream_continuation():
+    text = gen_circuit("surface_code", "rotated_memory_x", 5, 5, 0.01)
+    seed = 77
+    s = stim_b200.Circuit(text).compile_detector_sampler(seed=seed, engine="events")
+    D, L = int(s.stats.num_detectors), int(s.stats.num_observables)
+    S = s.engine_info()["tile_shots"]
+    a = s.sample(333, append_observables=True)
+    off1 = s.shot_offset
+    assert off1 % 128 == 0 and off1 >= 333
+    b = s.sample(130, prepend_observables=True, bit_packed=True)
+    off2 = s.shot_offset
+    buf = np.zeros((257, 40), dtype=np.uint8)  # strided rows
+    c = s.sample(257, bit_packed=True, dets_out=buf[:, 3:3 + (D + 7) // 8])
+    wa = oracle_rows(s, seed, 0, 333, D + L)
+    wb = oracle_rows(s, seed, off1, 130, D + L)
+    wc = oracle_rows(s, seed, off2, 257, D + L)
+    np.testing.assert_array_equal(a.astype(np.uint8), wa)
+    np.testing.assert_array_equal(np.unpackbits(b, axis=1, bitorder="little")[:, :D + L], np.concatenate([wb[:, D:], wb[:, :D]], axis=1))
+    np.testing.assert_array_equal(np.unpackbits(c, axis=1, bitorder="little")[:, :D], wc[:, :D])
+    assert not buf[:, :3].any() and not buf[:, 3 + (D + 7) // 8:].any()
+    assert S & (S - 1) == 0
+
+
+def test_device_results_counts_and_files_agree(tmp_path):
+    import torch
+
+    text = gen_circuit("color_code", "memory_xyz", 5, 2, 0.01)
+    seed = 9
+    mk = lambda: stim_b200.Circuit(text).compile_detector_sampler(seed=seed, engine="events")
+    shots = 1000
+    s = mk()
+    D, L = int(s.stats.num_detectors), int(s.stats.num_observables)
+    host = s.sample(shots, append_observables=True, bit_packed=True)
+    dets, obs = mk().sample_torch(shots)
+    both = mk().sample_torch(shots, separate_observables=False)
+    np.testing.assert_array_equal(both.cpu().numpy(), host)
+    bits = np.unpackbits(host, axis=1, bitorder="little")[:, :D + L]
+    np.testing.assert_array_equal(np.unpackbits(dets.cpu().numpy(), axis=1, bitorder="little")[:, :D], bits[:, :D])
+    np.testing.assert_array_equal(np.unpackbits(obs.cpu().numpy(), axis=1, bitorder="little")[:, :L], bits[:, D:])
+    single, pair = mk().bit_counts(shots)
+    np.testing.assert_array_equal(single, bits.sum(axis=0).astype(np.uint64))
+    np.testing.assert_array_equal(pair, (bits[:, :-1] & bits[:, 1:]).sum(axis=0).astype(np.uint64))
+    # files: every format describes the same shots (1024 shots: ptb64 needs a multiple of 64)
+    host2 = mk().sample(1024, append_observables=True, bit_packed=True)
+    for fmt in ["b8", "01", "ptb64"]:
+        p = tmp_path / f"x.{fmt}"
+        mk().sample_write(1024, filepath=str(p), format=fmt, append_observables=True)
+        raw = p.read_bytes()
+        if fmt == "b8":
+            assert raw == host2.tobytes()
+        elif fmt == "01":
+            want = "".join("".join(map(str, r)) + "\n" for r in np.unpackbits(host2, axis=1, bitorder="little")[:, :D + L])
+            assert raw.decode() == want
+        else:
+            b2 = np.unpackbits(host2, axis=1, bitorder="little")[:, :D + L]
+            got = np.frombuffer(raw, dtype=np.uint8).reshape(1024 // 64, D + L, 8)
+            gb = np.unpackbits(got, axis=2, bitorder="little")  # [group, bit, shot in group]
+            np.testing.assert_array_equal(gb.transpose(0, 2, 1).reshape(1024, D + L), b2)
+    del torch
+
+
+def test_large_rows_use_small_tiles():
+    """d = 51 (16.6 KB per shot): four shots per tile; deterministic variant checked against the all-zero expectation
+    plus one injected p = 1 flip."""
+    import os
+    import re
+
+    from conftest import ROOT
+
+    with open(os.path.join(ROOT, "tests", "golden", "circuits", "c5_surface_x_d51_r51.stim")) as f:
+        text = f.read()
+    text = re.sub(r"\(0\.001\)", "(0)", text)
+    s = stim_b200.Circuit(text).compile_detector_sampler(seed=3, engine="events")
+    assert s.engine_info()["eligible"] == 1
+    out = s.sample(300, bit_packed=True, append_observables=True)
+    assert not out.any()
