@@ -42,17 +42,37 @@ namespace gstim {
 namespace {
 
 constexpr uint32_t SPARSE_TAG = 0x53500000u;  // 'SP' << 20
-constexpr uint32_t SMEM_CLASSES = 24;         // classes mirrored in shared memory (more: read from global memory)
+constexpr uint32_t MAX_CLASSES = 64;          // classes are mirrored in shared memory
+constexpr uint32_t MAX_BUFFERS = 8;           // tile images per block
+constexpr uint32_t SPARSE_THREADS = 1024;     // 31 producer warps + 1 writer warp
+constexpr uint32_t CTL_WORDS = 8;             // per buffer: next slice, lanes that left, full seq, ready seq, phase main, phase obs
+
+enum : uint32_t { DK_SINGLE = 0, DK_UNIFORM = 1, DK_THRESH3 = 2, DK_THRESH_N = 3 };
+
+struct EvClass {  // 64 bytes, shared memory
+    uint32_t slice_end;  // cumulative slice count up to and including this class
+    uint32_t slice0;     // first slice of the class
+    uint32_t per;        // sites per slice
+    uint32_t n_sites;
+    uint32_t entry0;
+    uint32_t inv, sh;
+    uint32_t kind;       // DK_*
+    uint32_t n_out;
+    uint32_t thr[3];     // DK_THRESH3: thresholds (unused ones 0xFFFFFFFF with n_out guarding them)
+    uint32_t thr_off;    // DK_THRESH_N: word offset of the 15 thresholds in `thr_all`
+    uint32_t pad[3];
+};
 
 struct SparseParams {
-    const uint4 *slices;  // x = class, y = trials (sites << log_s), z = table entry of the slice's first site, w = unused
-    uint32_t n_slices;
-    const SparseClassDev *classes;
+    const EvClass *classes;
     uint32_t n_classes;
+    uint32_t n_slices;
+    const uint32_t *thr_all;  // 15 thresholds per class (general chooser)
     const uint4 *entries;
     const uint32_t *overflow;
     const uint8_t *init_row;  // measurement mode: reference sample (main_bytes bytes) every row starts from, or null
     uint32_t log_s;
+    uint32_t n_buffers;
     uint32_t n_tiles;
     uint64_t tile0;    // global index of tile 0 of this launch
     uint64_t n_shots;  // valid shots of this launch
@@ -62,22 +82,20 @@ struct SparseParams {
     uint8_t *obs_out;
     uint64_t obs_pitch;
     uint32_t obs_bytes;
-    uint32_t obs_img_off;  // byte offset of the observable image inside the tile's shared memory (multiple of 16)
-    uint32_t img_bytes;    // bytes of both images (multiple of 16)
-    uint32_t seed_lo, seed_hi;
+    uint32_t obs_img_off;  // byte offset of the observable image inside a tile image (multiple of 16)
+    uint32_t img_bytes;    // bytes of one tile image, both parts (multiple of 16)
+    uint32_t rk[20];       // Philox round keys: (k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85), r = 0..9
 };
 
-__device__ __forceinline__ uint4 sp_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+__device__ __forceinline__ uint4 sp_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20]) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0;
+        c0 = hi1 ^ c1 ^ rk[2 * r];
         c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
+        c2 = hi0 ^ c3 ^ rk[2 * r + 1];
         c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -86,185 +104,316 @@ __device__ __forceinline__ void flip_bit(uint32_t img_saddr, uint32_t bit) {
     asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(img_saddr + ((bit >> 5) << 2)), "r"(1u << (bit & 31u)) : "memory");
 }
 
-// Copies `nbytes` bytes from shared memory (image coordinate `phase`) to dst, where (dst & 15) == phase.
-__device__ __forceinline__ void store_span(const uint8_t *img, uint32_t phase, uint8_t *dst, uint64_t nbytes) {
-    const uint64_t end = phase + nbytes;
-    uint8_t *const g0 = dst - phase;  // 16-byte aligned
-    for (uint64_t c = (uint64_t)threadIdx.x * 16; c < end; c += (uint64_t)blockDim.x * 16) {
-        if (c >= phase && c + 16 <= end) {
-            *reinterpret_cast<uint4 *>(g0 + c) = *reinterpret_cast<const uint4 *>(img + c);
-        } else {
-            for (uint64_t b = c < phase ? phase : c; b < c + 16 && b < end; b++) {
-                g0[b] = img[b];
-            }
-        }
-    }
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
+    return *reinterpret_cast<const volatile uint32_t *>(p);
+}
+__device__ __forceinline__ void st_volatile_shared(uint32_t *p, uint32_t v) {
+    *reinterpret_cast<volatile uint32_t *>(p) = v;
 }
 
-template <bool SEPARATE>
-__global__ void __launch_bounds__(384, 3) gstim_sparse_kernel(const SparseParams p) {
-    extern __shared__ uint4 smem4[];
-    uint2 *const lt = reinterpret_cast<uint2 *>(smem4);                                 // 256 x (base, diff): 2 KiB
-    SparseClassDev *const scls = reinterpret_cast<SparseClassDev *>(lt + 256);            // SMEM_CLASSES x 80 B
-    uint32_t *const ctl = reinterpret_cast<uint32_t *>(scls + SMEM_CLASSES);              // [0] = next slice
-    uint8_t *const img = reinterpret_cast<uint8_t *>(ctl + 4);                            // 16-byte aligned
-    const uint32_t img_saddr = (uint32_t)__cvta_generic_to_shared(img);
+// Copies `nbytes` bytes from shared memory (image coordinate `phase`) to dst, where (dst & 15) == phase; one warp.
+// The 16-byte aligned middle goes out as ONE bulk-async copy (TMA 1-D, cp.async.bulk shared -> global) issued by lane 0:
+// the warp spends a handful of instructions per tile instead of a load/store loop; the <= 15 edge bytes on either side
+// are byte stores. Returns after the bulk copy has finished READING shared memory (the image may be cleared).
+__device__ __forceinline__ void store_span(const uint8_t *img, uint32_t img_saddr, uint32_t phase, uint8_t *dst, uint64_t nbytes, uint32_t lane) {
+    const uint64_t end = phase + nbytes;
+    uint8_t *const g0 = dst - phase;  // 16-byte aligned
+    const uint64_t mid0 = phase ? 16 : 0, mid1 = end & ~15ull;
+    if (mid1 > mid0) {
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g0 + mid0), "r"(img_saddr + (uint32_t)mid0),
+                         "r"((uint32_t)(mid1 - mid0))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        for (uint64_t b = phase + lane; b < mid0 && b < end; b += 32) {
+            g0[b] = img[b];
+        }
+        for (uint64_t b = mid1 + lane; b < end; b += 32) {
+            g0[b] = img[b];
+        }
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else {
+        for (uint64_t b = phase + lane; b < end; b += 32) {
+            g0[b] = img[b];
+        }
+    }
+    __syncwarp();
+}
 
+// One persistent block per SM. The block keeps n_buffers tile images in shared memory; tile sequence q of the block
+// (global tile blockIdx.x + q * gridDim.x) lives in buffer q % n_buffers.
+//   producer lanes (all warps but the last) walk the sequences in order: claim slices of sequence q until its pool is
+//     dry, then LEAVE it (count themselves out) and go on to q + 1 without waiting for anybody — so a lane never idles
+//     at a tile boundary; it only waits when buffer (q + 1) % n_buffers has not been recycled yet;
+//   the writer warp waits until every producer lane has left sequence q, stores the image to global memory, clears it
+//     and hands the buffer to sequence q + n_buffers.
+template <bool SEPARATE>
+__global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const __grid_constant__ SparseParams p) {
+    extern __shared__ uint4 smem4[];
+    uint2 *const lt = reinterpret_cast<uint2 *>(smem4);                        // 256 x (base, diff): 2 KiB
+    EvClass *const cls = reinterpret_cast<EvClass *>(lt + 256);                 // MAX_CLASSES x 64 B
+    uint32_t *const ctl = reinterpret_cast<uint32_t *>(cls + MAX_CLASSES);      // MAX_BUFFERS x CTL_WORDS
+    uint8_t *const img0 = reinterpret_cast<uint8_t *>(ctl + MAX_BUFFERS * CTL_WORDS);  // 16-byte aligned
+    const uint32_t img0_saddr = (uint32_t)__cvta_generic_to_shared(img0);
+
+    const uint32_t S = 1u << p.log_s, smask = S - 1u, NB = p.n_buffers;
+    const uint32_t main_bits = p.main_bytes * 8u, obs_bits = p.obs_bytes * 8u;
+    const bool main_dense = p.main_pitch == p.main_bytes, obs_dense = p.obs_pitch == p.obs_bytes;
+    const uint32_t n_seq = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles of this block
+    const uint32_t n_prod = blockDim.x - 32;
+
+    auto phases_of = [&](uint32_t q, uint32_t *pm, uint32_t *po) {
+        const uint64_t shot0 = ((uint64_t)blockIdx.x + (uint64_t)q * gridDim.x) << p.log_s;
+        *pm = (p.main_out != nullptr && main_dense) ? (uint32_t)((reinterpret_cast<uintptr_t>(p.main_out) + shot0 * p.main_bytes) & 15u) : 0u;
+        *po = (SEPARATE && p.obs_out != nullptr && obs_dense) ? (uint32_t)((reinterpret_cast<uintptr_t>(p.obs_out) + shot0 * p.obs_bytes) & 15u) : 0u;
+    };
+    auto fill_init = [&](uint8_t *img, uint32_t pm, uint32_t tid, uint32_t nt) {
+        for (uint32_t i = tid; i < S * p.main_bytes; i += nt) {
+            img[pm + i] = p.init_row[i % p.main_bytes];
+        }
+    };
+
+    // ---- set-up by the whole block -------------------------------------------------------------------------
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
         lt[i] = make_uint2(GSTIM_LOG2_Q26[2 * i], GSTIM_LOG2_Q26[2 * i + 1]);
     }
-    const bool cls_in_smem = p.n_classes <= SMEM_CLASSES;
-    if (cls_in_smem) {
-        const uint32_t words = p.n_classes * (uint32_t)(sizeof(SparseClassDev) / 4);
-        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) {
-            reinterpret_cast<uint32_t *>(scls)[i] = reinterpret_cast<const uint32_t *>(p.classes)[i];
-        }
+    for (uint32_t i = threadIdx.x; i < p.n_classes * (uint32_t)(sizeof(EvClass) / 4); i += blockDim.x) {
+        reinterpret_cast<uint32_t *>(cls)[i] = reinterpret_cast<const uint32_t *>(p.classes)[i];
     }
-    const SparseClassDev *const cls = cls_in_smem ? scls : p.classes;
-    const uint32_t S = 1u << p.log_s, smask = S - 1u;
-    const uint32_t main_bits = p.main_bytes * 8u, obs_bits = p.obs_bytes * 8u;
-    const bool main_dense = p.main_pitch == p.main_bytes, obs_dense = p.obs_pitch == p.obs_bytes;
-
-    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const uint64_t shot0 = (uint64_t)tile << p.log_s;
-        const uint32_t n_valid = (uint32_t)min((uint64_t)S, p.n_shots - shot0);
-        // the image sits at the 16-byte phase of its destination
-        uint32_t phase_m = 0, phase_o = 0;
-        if (p.main_out != nullptr && main_dense) {
-            phase_m = (uint32_t)((reinterpret_cast<uintptr_t>(p.main_out) + shot0 * p.main_bytes) & 15u);
-        }
-        if (SEPARATE && p.obs_out != nullptr && obs_dense) {
-            phase_o = (uint32_t)((reinterpret_cast<uintptr_t>(p.obs_out) + shot0 * p.obs_bytes) & 15u);
-        }
-        __syncthreads();  // the previous tile's stores have read the image (also covers the table loads above)
-        for (uint32_t i = threadIdx.x; i < p.img_bytes / 16; i += blockDim.x) {
-            reinterpret_cast<uint4 *>(img)[i] = make_uint4(0, 0, 0, 0);
-        }
-        if (threadIdx.x == 0) {
-            ctl[0] = 0;
+    for (uint32_t i = threadIdx.x; i < NB * (p.img_bytes / 16); i += blockDim.x) {
+        reinterpret_cast<uint4 *>(img0)[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (threadIdx.x < NB) {
+        uint32_t *c = ctl + threadIdx.x * CTL_WORDS;
+        uint32_t pm, po;
+        phases_of(threadIdx.x, &pm, &po);
+        c[0] = 0;                                   // next slice
+        c[1] = 0;                                   // producer lanes that left the sequence
+        c[2] = 0;                                   // full: sequence + 1 whose events are all applied
+        c[3] = threadIdx.x < n_seq ? threadIdx.x + 1 : 0;  // ready: sequence + 1 the buffer is cleared for
+        c[4] = pm;
+        c[5] = po;
+    }
+    __syncthreads();
+    if (p.init_row != nullptr) {
+        for (uint32_t b = 0; b < NB && b < n_seq; b++) {
+            fill_init(img0 + b * p.img_bytes, ctl[b * CTL_WORDS + 4], threadIdx.x, blockDim.x);
         }
         __syncthreads();
-        if (p.init_row != nullptr) {
-            for (uint32_t i = threadIdx.x; i < S * p.main_bytes; i += blockDim.x) {
-                img[phase_m + i] = p.init_row[i % p.main_bytes];
+    }
+
+    if (threadIdx.x >= n_prod) {
+        // ---- writer warp -------------------------------------------------------------------------------------
+        const uint32_t lane = threadIdx.x & 31u;
+        for (uint32_t q = 0; q < n_seq; q++) {
+            const uint32_t b = q % NB;
+            uint32_t *c = ctl + b * CTL_WORDS;
+            uint8_t *img = img0 + b * p.img_bytes;
+            while (ld_volatile_shared(c + 2) != q + 1) {
+                __nanosleep(64);
             }
-            __syncthreads();
+            __threadfence_block();
+            const uint64_t shot0 = ((uint64_t)blockIdx.x + (uint64_t)q * gridDim.x) << p.log_s;
+            const uint32_t n_valid = (uint32_t)min((uint64_t)S, p.n_shots - shot0);
+            const uint32_t pm = c[4], po = c[5];
+            if (p.main_out != nullptr && p.main_bytes) {
+                if (main_dense) {
+                    store_span(img, img0_saddr + b * p.img_bytes, pm, p.main_out + shot0 * p.main_bytes, (uint64_t)n_valid * p.main_bytes, lane);
+                } else {
+                    for (uint32_t i = lane; i < n_valid * p.main_bytes; i += 32) {
+                        const uint32_t row = i / p.main_bytes, col = i - row * p.main_bytes;
+                        p.main_out[(shot0 + row) * p.main_pitch + col] = img[i];
+                    }
+                }
+            }
+            if (SEPARATE && p.obs_out != nullptr && p.obs_bytes) {
+                const uint8_t *oimg = img + p.obs_img_off;
+                if (obs_dense) {
+                    store_span(oimg, img0_saddr + b * p.img_bytes + p.obs_img_off, po, p.obs_out + shot0 * p.obs_bytes, (uint64_t)n_valid * p.obs_bytes, lane);
+                } else {
+                    for (uint32_t i = lane; i < n_valid * p.obs_bytes; i += 32) {
+                        const uint32_t row = i / p.obs_bytes, col = i - row * p.obs_bytes;
+                        p.obs_out[(shot0 + row) * p.obs_pitch + col] = oimg[i];
+                    }
+                }
+            }
+            if (q + NB < n_seq) {  // recycle the buffer for sequence q + NB
+                __syncwarp();
+#pragma unroll 8
+                for (uint32_t i = lane; i < p.img_bytes / 16; i += 32) {
+                    reinterpret_cast<uint4 *>(img)[i] = make_uint4(0, 0, 0, 0);
+                }
+                uint32_t npm, npo;
+                phases_of(q + NB, &npm, &npo);
+                if (p.init_row != nullptr) {
+                    __syncwarp();
+                    fill_init(img, npm, lane, 32);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    c[0] = 0;
+                    c[1] = 0;
+                    c[4] = npm;
+                    c[5] = npo;
+                    __threadfence_block();
+                    st_volatile_shared(c + 3, q + NB + 1);
+                }
+                __syncwarp();
+            }
         }
-        const uint32_t base_m = phase_m * 8u, base_o = (p.obs_img_off + phase_o) * 8u;
-        const uint64_t gt = p.tile0 + tile;
-        const uint32_t c2 = (uint32_t)gt, c3 = SPARSE_TAG | (uint32_t)(gt >> 32);
+        return;
+    }
 
-        auto flip = [&](uint32_t shot, uint32_t v) {
-            if (SEPARATE && (v & 0x40000000u)) {
-                flip_bit(img_saddr, base_o + shot * obs_bits + (v & 0x3FFFFFFFu));
-            } else {
-                flip_bit(img_saddr, base_m + shot * main_bits + v);
+    // ---- producer lanes -------------------------------------------------------------------------------------
+    uint32_t q = 0, b = 0;              // sequence this lane works on, its buffer
+    bool entered = false;               // tile constants below are valid for q
+    uint32_t rowbase_m = 0, rowbase_o = 0, c2 = 0, c3 = 0;
+    uint32_t *c = ctl;
+    bool active = false;
+    uint32_t sl = 0, a = 0, total = 0, call = 0, inv = 0, sh = 0, ebase = 0, n_out = 1, kind = 0, t0 = 0, t1 = 0, t2 = 0, thr_off = 0;
+    // the flips of an event are applied one event later, so its table entry has time to arrive
+    uint4 pend = make_uint4(RESP_NONE, RESP_NONE, RESP_NONE, RESP_NONE);
+    uint32_t pend_m = 0, pend_o = 0;
+
+    auto flip = [&](uint32_t row_m, uint32_t row_o, uint32_t v) {
+        if (SEPARATE && (v & 0x40000000u)) {
+            flip_bit(img0_saddr, row_o + (v & 0x3FFFFFFFu));
+        } else {
+            flip_bit(img0_saddr, row_m + v);
+        }
+    };
+    auto apply_pending = [&]() {
+        if (pend.x != RESP_NONE) {
+            flip(pend_m, pend_o, pend.x);
+            if (pend.y != RESP_NONE) {
+                flip(pend_m, pend_o, pend.y);
+                if (pend.z != RESP_NONE) {
+                    flip(pend_m, pend_o, pend.z);
+                    if (pend.w != RESP_NONE) {
+                        if (pend.w & RESP_OVERFLOW) {
+                            const uint32_t *ov = p.overflow + (pend.w & 0x7FFFFFFFu);
+                            const uint32_t cnt = __ldg(ov);
+                            for (uint32_t j = 1; j <= cnt; j++) {
+                                flip(pend_m, pend_o, __ldg(ov + j));
+                            }
+                        } else {
+                            flip(pend_m, pend_o, pend.w);
+                        }
+                    }
+                }
             }
-        };
+        }
+    };
 
-        bool active = false;
-        uint32_t sl = 0, a = 0, total = 0, call = 0, inv = 0, sh = 0, ebase = 0, n_out = 1, kind = 0;
-        const SparseClassDev *cl = cls;
-        while (true) {
-            if (!active) {
-                sl = atomicAdd(&ctl[0], 1u);
-                if (sl >= p.n_slices) {
+    while (true) {
+        if (!active) {
+#pragma unroll 1
+            for (int attempt = 0; attempt < 2 && !active; attempt++) {
+                if (q >= n_seq) {
                     break;
                 }
-                const uint4 d = __ldg(p.slices + sl);
-                cl = cls + d.x;
-                inv = cl->inv;
-                sh = cl->sh;
-                kind = cl->kind;
-                n_out = cl->n_out;
-                total = d.y;
-                ebase = d.z;
-                a = 0;
-                call = 0;
-                active = true;
-            }
-            const uint4 r = sp_philox(sl, call, c2, c3, p.seed_lo, p.seed_hi);
-            call++;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                if (!active) {
-                    continue;
-                }
-                const uint32_t gw = h ? r.z : r.x, pw = h ? r.w : r.y;
-                // E = -ln(v / 2^32) in units of 2^-26 nat (dem.cu header)
-                const uint32_t v = gw | 1u;
-                const uint32_t t = 31u - (uint32_t)__clz((int)v);
-                const uint32_t frac = (v << (31u - t)) << 1;
-                const uint2 en = lt[frac >> 24];
-                const uint32_t log2v = (t << 26) + en.x + ((en.y * ((frac >> 11) & 0x1FFFu)) >> 13);
-                const uint32_t E = __umulhi(0x80000000u - log2v, GSTIM_LN2_Q32);
-                const unsigned long long G = ((unsigned long long)E * inv) >> sh;
-                if (G >= (unsigned long long)(total - a)) {
-                    active = false;
-                    continue;
-                }
-                a += (uint32_t)G;
-                const uint32_t site = a >> p.log_s, shot = a & smask;
-                a++;
-                if (a >= total) {
-                    active = false;
-                }
-                uint32_t o = 0;
-                if (kind == RK_UNIFORM) {
-                    o = __umulhi(pw, n_out);
-                } else if (kind == RK_THRESH) {
-                    for (uint32_t j = 0; j + 1 < n_out; j++) {
-                        o += pw >= cl->thr[j] ? 1u : 0u;
+                if (!entered) {
+                    if (ld_volatile_shared(c + 3) != q + 1) {
+                        __nanosleep(32);  // the buffer still belongs to sequence q - NB
+                        break;
                     }
+                    __threadfence_block();
+                    const uint64_t gt = p.tile0 + blockIdx.x + (uint64_t)q * gridDim.x;
+                    c2 = (uint32_t)gt;
+                    c3 = SPARSE_TAG | (uint32_t)(gt >> 32);
+                    rowbase_m = (b * p.img_bytes + c[4]) * 8u;
+                    rowbase_o = (b * p.img_bytes + p.obs_img_off + c[5]) * 8u;
+                    entered = true;
                 }
-                const uint4 e = __ldg(p.entries + (ebase + site * n_out + o));
-                if (e.x == RESP_NONE) {
-                    continue;
-                }
-                flip(shot, e.x);
-                if (e.y == RESP_NONE) {
-                    continue;
-                }
-                flip(shot, e.y);
-                if (e.z == RESP_NONE) {
-                    continue;
-                }
-                flip(shot, e.z);
-                if (e.w == RESP_NONE) {
-                    continue;
-                }
-                if (e.w & RESP_OVERFLOW) {
-                    const uint32_t *ov = p.overflow + (e.w & 0x7FFFFFFFu);
-                    const uint32_t cnt = __ldg(ov);
-                    for (uint32_t j = 1; j <= cnt; j++) {
-                        flip(shot, __ldg(ov + j));
+                sl = atomicAdd(c, 1u);
+                if (sl < p.n_slices) {
+                    uint32_t k = 0;
+                    while (sl >= cls[k].slice_end) {
+                        k++;
                     }
+                    const EvClass &cl = cls[k];
+                    const uint32_t s0 = (sl - cl.slice0) * cl.per;
+                    total = min(cl.per, cl.n_sites - s0) << p.log_s;
+                    n_out = cl.n_out;
+                    ebase = cl.entry0 + s0 * n_out;
+                    inv = cl.inv;
+                    sh = cl.sh;
+                    kind = cl.kind;
+                    t0 = cl.thr[0];
+                    t1 = cl.thr[1];
+                    t2 = cl.thr[2];
+                    thr_off = cl.thr_off;
+                    a = 0;
+                    call = 0;
+                    active = true;
                 } else {
-                    flip(shot, e.w);
+                    // the pool of sequence q is dry: apply what is pending, count this lane out, move on
+                    apply_pending();
+                    pend.x = RESP_NONE;
+                    __threadfence_block();
+                    if (atomicAdd(c + 1, 1u) + 1 == n_prod) {
+                        __threadfence_block();
+                        st_volatile_shared(c + 2, q + 1);
+                    }
+                    q++;
+                    b = b + 1 == NB ? 0 : b + 1;
+                    c = ctl + b * CTL_WORDS;
+                    entered = false;
                 }
             }
-        }
-        __syncthreads();
-        // store the image
-        if (p.main_out != nullptr && p.main_bytes) {
-            if (main_dense) {
-                store_span(img, phase_m, p.main_out + shot0 * p.main_bytes, (uint64_t)n_valid * p.main_bytes);
-            } else {
-                for (uint32_t i = threadIdx.x; i < n_valid * p.main_bytes; i += blockDim.x) {
-                    const uint32_t row = i / p.main_bytes, col = i - row * p.main_bytes;
-                    p.main_out[(shot0 + row) * p.main_pitch + col] = img[i];
-                }
+            if (q >= n_seq) {
+                break;
             }
         }
-        if (SEPARATE && p.obs_out != nullptr && p.obs_bytes) {
-            const uint8_t *oimg = img + p.obs_img_off;
-            if (obs_dense) {
-                store_span(oimg, phase_o, p.obs_out + shot0 * p.obs_bytes, (uint64_t)n_valid * p.obs_bytes);
-            } else {
-                for (uint32_t i = threadIdx.x; i < n_valid * p.obs_bytes; i += blockDim.x) {
-                    const uint32_t row = i / p.obs_bytes, col = i - row * p.obs_bytes;
-                    p.obs_out[(shot0 + row) * p.obs_pitch + col] = oimg[i];
+        if (!active) {
+            continue;
+        }
+        const uint4 r = sp_philox(sl, call, c2, c3, p.rk);
+        call++;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (!active) {
+                continue;
+            }
+            const uint32_t gw = h ? r.z : r.x, pw = h ? r.w : r.y;
+            // E = -ln(v / 2^32) in units of 2^-26 nat (dem.cu header)
+            const uint32_t v = gw | 1u;
+            const uint32_t t = 31u - (uint32_t)__clz((int)v);
+            const uint32_t frac = (v << (31u - t)) << 1;
+            const uint2 en = lt[frac >> 24];
+            const uint32_t log2v = (t << 26) + en.x + ((en.y * ((frac >> 11) & 0x1FFFu)) >> 13);
+            const uint32_t E = __umulhi(0x80000000u - log2v, GSTIM_LN2_Q32);
+            const unsigned long long G = ((unsigned long long)E * inv) >> sh;
+            if (G >= (unsigned long long)(total - a)) {
+                active = false;
+                continue;
+            }
+            a += (uint32_t)G;
+            const uint32_t site = a >> p.log_s, shot = a & smask;
+            a++;
+            if (a >= total) {
+                active = false;
+            }
+            uint32_t o = 0;
+            if (kind == DK_UNIFORM) {
+                o = __umulhi(pw, n_out);
+            } else if (kind == DK_THRESH3) {
+                o = (pw >= t0 ? 1u : 0u) + ((pw >= t1 && n_out > 2) ? 1u : 0u) + ((pw >= t2 && n_out > 3) ? 1u : 0u);
+            } else if (kind == DK_THRESH_N) {
+                for (uint32_t j = 0; j + 1 < n_out; j++) {
+                    o += pw >= __ldg(p.thr_all + thr_off + j) ? 1u : 0u;
                 }
+            }
+            const uint4 e = __ldg(p.entries + (ebase + site * n_out + o));
+            apply_pending();
+            pend = e;
+            pend_m = rowbase_m + shot * main_bits;
+            if (SEPARATE) {
+                pend_o = rowbase_o + shot * obs_bits;
             }
         }
     }
@@ -320,8 +469,8 @@ uint32_t align16(uint32_t v) {
     return (v + 15u) & ~15u;
 }
 
-constexpr uint32_t SPARSE_THREADS = 384;
-constexpr size_t FIXED_SMEM = 256 * 8 + SMEM_CLASSES * sizeof(SparseClassDev) + 16;
+constexpr size_t FIXED_SMEM = 256 * 8 + MAX_CLASSES * sizeof(EvClass) + MAX_BUFFERS * CTL_WORDS * 4;
+static_assert(sizeof(EvClass) == 64 && FIXED_SMEM % 16 == 0, "shared memory layout");
 
 }  // namespace
 
@@ -346,14 +495,14 @@ struct SparseEngine::Impl {
     uint32_t D = 0, L = 0, M = 0, mode = 0;
     ResponseTable rt;
     uint32_t log_s = 0;
-    uint32_t blocks_per_sm = 1;
+    uint32_t row_all = 0;                 // upper bound of the bytes per shot over all layouts
     uint32_t layout_flags = 0xFFFFFFFFu;  // layout the device table is encoded for
     uint32_t main_bits = 0, obs_bits = 0;
-    void *d_slices = nullptr, *d_classes = nullptr, *d_entries = nullptr, *d_overflow = nullptr, *d_init = nullptr;
+    void *d_thr = nullptr, *d_classes = nullptr, *d_entries = nullptr, *d_overflow = nullptr, *d_init = nullptr;
     uint32_t n_slices = 0;
     std::vector<uint32_t> slices_host;  // 4 words per slice (tests / oracle)
     ~Impl() {
-        for (void *p : {d_slices, d_classes, d_entries, d_overflow, d_init}) {
+        for (void *p : {d_thr, d_classes, d_entries, d_overflow, d_init}) {
             if (p) {
                 cudaFree(p);
             }
@@ -375,17 +524,18 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
     I.num_sms = prop.multiProcessorCount;
     I.smem_optin = prop.sharedMemPerBlockOptin;
 
-    // Tile height: the largest power of two <= 128 whose image lets three blocks share an SM (then two, then one).
-    // It depends on the circuit only (not on the output layout), so the random stream does too.
-    const uint32_t row_all = mode == 0 ? (D + 7) / 8 + (L + 7) / 8 + 1 : (M + 7) / 8 + 1;
-    const size_t per_sm = (size_t)prop.sharedMemPerMultiprocessor;
+    // Tile height: the largest power of two <= 128 for which three tile images fit in shared memory (then two, then
+    // one). It depends on the circuit only (not on the output layout or the device), so the random stream does too.
+    I.row_all = mode == 0 ? (D + 7) / 8 + (L + 7) / 8 + 1 : (M + 7) / 8 + 1;
+    const size_t budget = (size_t)227 * 1024 - FIXED_SMEM;
+    if (I.smem_optin < (size_t)227 * 1024) {
+        throw std::invalid_argument("device has less than 227 KiB of shared memory per block");
+    }
     bool ok = false;
-    for (uint32_t blocks = 3; blocks >= 1 && !ok; blocks--) {
-        const size_t budget = std::min<size_t>(I.smem_optin, per_sm / blocks - 1024) - FIXED_SMEM - 64;
-        for (int ls = 7; ls >= (blocks == 1 ? 0 : 2); ls--) {
-            if (((size_t)row_all << ls) <= budget) {
+    for (uint32_t bufs = 3; bufs >= 1 && !ok; bufs--) {
+        for (int ls = 7; ls >= 0; ls--) {
+            if (((((size_t)I.row_all << ls) + 64) * bufs) <= budget) {
                 I.log_s = (uint32_t)ls;
-                I.blocks_per_sm = blocks;
                 ok = true;
                 break;
             }
@@ -394,29 +544,42 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
     if (!ok) {
         throw std::invalid_argument("output row does not fit in shared memory");
     }
+    if (I.rt.classes.size() > MAX_CLASSES) {
+        throw std::invalid_argument("more than 64 distinct site classes");
+    }
     const uint32_t S = 1u << I.log_s;
 
     // slices: runs of sites with about `slice_events` expected events per tile
-    std::vector<SparseClassDev> cls;
+    std::vector<EvClass> cls;
+    std::vector<uint32_t> thr_all;
     for (const RespClass &c : I.rt.classes) {
-        SparseClassDev d{};
-        d.inv = c.inv;
-        d.sh = c.sh;
-        d.kind = c.kind;
-        d.n_out = c.n_out;
-        memcpy(d.thr, c.thr, sizeof(c.thr));
-        cls.push_back(d);
         const double lam = std::ldexp((double)c.lam, -56);
         const double pr = c.inv == 0 ? 1.0 : -std::expm1(-lam);
-        double want = (double)slice_events / (pr * S);
-        uint32_t per = (uint32_t)std::max(1.0, std::min(want, (double)((1u << 30) >> I.log_s)));
+        const double want = (double)slice_events / (pr * S);
+        const uint32_t per = (uint32_t)std::max(1.0, std::min(want, (double)((1u << 30) >> I.log_s)));
+        EvClass d{};
+        d.slice0 = (uint32_t)(I.slices_host.size() / 4);
+        d.per = per;
+        d.n_sites = c.n_sites;
+        d.entry0 = c.entry0;
+        d.inv = c.inv;
+        d.sh = c.sh;
+        d.n_out = c.n_out;
+        d.kind = c.kind == RK_SINGLE ? DK_SINGLE : c.kind == RK_UNIFORM ? DK_UNIFORM : c.n_out <= 4 ? DK_THRESH3 : DK_THRESH_N;
+        for (int j = 0; j < 3; j++) {
+            d.thr[j] = c.thr[j];
+        }
+        d.thr_off = (uint32_t)thr_all.size();
+        thr_all.insert(thr_all.end(), c.thr, c.thr + 15);
         for (uint32_t s0 = 0; s0 < c.n_sites; s0 += per) {
             const uint32_t ns = std::min(per, c.n_sites - s0);
-            I.slices_host.push_back((uint32_t)(cls.size() - 1));
+            I.slices_host.push_back((uint32_t)cls.size());
             I.slices_host.push_back(ns << I.log_s);
             I.slices_host.push_back(c.entry0 + s0 * c.n_out);
             I.slices_host.push_back(0);
         }
+        d.slice_end = (uint32_t)(I.slices_host.size() / 4);
+        cls.push_back(d);
     }
     I.n_slices = (uint32_t)(I.slices_host.size() / 4);
     ck(cudaSetDevice(device), "cudaSetDevice");
@@ -426,8 +589,8 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
             ck(cudaMemcpy(*d, src, bytes, cudaMemcpyHostToDevice), "upload (response table)");
         }
     };
-    up(&I.d_slices, I.slices_host.data(), I.slices_host.size() * 4);
-    up(&I.d_classes, cls.data(), cls.size() * sizeof(SparseClassDev));
+    up(&I.d_thr, thr_all.data(), thr_all.size() * 4);
+    up(&I.d_classes, cls.data(), cls.size() * sizeof(EvClass));
     up(&I.d_overflow, nullptr, I.rt.overflow.size() * 4);
     up(&I.d_entries, nullptr, I.rt.entries.size() * 4);
     ck(cudaFuncSetAttribute(gstim_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_optin), "smem attribute");
@@ -445,7 +608,7 @@ uint32_t SparseEngine::tile_shots() const {
     return 1u << impl->log_s;
 }
 uint32_t SparseEngine::blocks_per_sm() const {
-    return impl->blocks_per_sm;
+    return 1;
 }
 const std::vector<uint32_t> &SparseEngine::slices() const {
     return impl->slices_host;
@@ -578,10 +741,10 @@ void SparseEngine::launch(uint64_t first_shot, uint64_t n_shots, uint8_t *main_o
         throw std::invalid_argument("shot offset must be a multiple of the engine's tile height (" + std::to_string(S) + " shots)");
     }
     SparseParams p{};
-    p.slices = (const uint4 *)I.d_slices;
-    p.n_slices = I.n_slices;
-    p.classes = (const SparseClassDev *)I.d_classes;
+    p.classes = (const EvClass *)I.d_classes;
     p.n_classes = (uint32_t)I.rt.classes.size();
+    p.n_slices = I.n_slices;
+    p.thr_all = (const uint32_t *)I.d_thr;
     p.entries = (const uint4 *)I.d_entries;
     p.overflow = (const uint32_t *)I.d_overflow;
     p.init_row = (const uint8_t *)I.d_init;
@@ -601,13 +764,16 @@ void SparseEngine::launch(uint64_t first_shot, uint64_t n_shots, uint8_t *main_o
     p.obs_pitch = obs_pitch ? obs_pitch : p.obs_bytes;
     p.obs_img_off = align16(p.main_bytes * S + 16);
     p.img_bytes = p.obs_img_off + align16(p.obs_bytes * S + 16);
-    p.seed_lo = (uint32_t)seed;
-    p.seed_hi = (uint32_t)(seed >> 32);
-    const size_t smem = FIXED_SMEM + p.img_bytes;
-    if (smem > I.smem_optin) {
+    for (uint32_t r = 0; r < 10; r++) {
+        p.rk[2 * r] = (uint32_t)seed + r * 0x9E3779B9u;
+        p.rk[2 * r + 1] = (uint32_t)(seed >> 32) + r * 0xBB67AE85u;
+    }
+    p.n_buffers = (uint32_t)std::min<size_t>(MAX_BUFFERS, ((size_t)227 * 1024 - FIXED_SMEM) / p.img_bytes);
+    if (p.n_buffers == 0) {
         throw std::invalid_argument("internal: tile image exceeds shared memory");
     }
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)I.num_sms * I.blocks_per_sm);
+    const size_t smem = FIXED_SMEM + (size_t)p.n_buffers * p.img_bytes;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)I.num_sms);
     if (I.obs_bits) {
         gstim_sparse_kernel<true><<<grid, SPARSE_THREADS, smem, stream>>>(p);
     } else {
