@@ -58,7 +58,7 @@ struct EvClass {  // 64 bytes, shared memory
     uint32_t inv, sh;
     uint32_t kind;       // DK_*
     uint32_t n_out;
-    uint32_t thr[3];     // DK_THRESH3: thresholds (unused ones 0xFFFFFFFF with n_out guarding them)
+    uint32_t thr[3];     // DK_THRESH3: thresholds - 1 (outcome = number of thr[j] < word); unused ones 0xFFFFFFFF
     uint32_t thr_off;    // DK_THRESH_N: word offset of the 15 thresholds in `thr_all`
     uint32_t pad[3];
 };
@@ -98,10 +98,6 @@ __device__ __forceinline__ uint4 sp_philox(uint32_t c0, uint32_t c1, uint32_t c2
         c3 = lo0;
     }
     return make_uint4(c0, c1, c2, c3);
-}
-
-__device__ __forceinline__ void flip_bit(uint32_t img_saddr, uint32_t bit) {
-    asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(img_saddr + ((bit >> 5) << 2)), "r"(1u << (bit & 31u)) : "memory");
 }
 
 __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
@@ -164,7 +160,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
     const uint32_t main_bits = p.main_bytes * 8u, obs_bits = p.obs_bytes * 8u;
     const bool main_dense = p.main_pitch == p.main_bytes, obs_dense = p.obs_pitch == p.obs_bytes;
     const uint32_t n_seq = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles of this block
-    const uint32_t n_prod = blockDim.x - 32;
+    const uint32_t n_prod = blockDim.x - 32, n_prod_warps = n_prod / 32;
 
     auto phases_of = [&](uint32_t q, uint32_t *pm, uint32_t *po) {
         const uint64_t shot0 = ((uint64_t)blockIdx.x + (uint64_t)q * gridDim.x) << p.log_s;
@@ -268,155 +264,186 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         return;
     }
 
-    // ---- producer lanes -------------------------------------------------------------------------------------
-    uint32_t q = 0, b = 0;              // sequence this lane works on, its buffer
-    bool entered = false;               // tile constants below are valid for q
-    uint32_t rowbase_m = 0, rowbase_o = 0, c2 = 0, c3 = 0;
+    // ---- producer warps -------------------------------------------------------------------------------------
+    // A warp walks ONE slice at a time, 64 draws per step: lane l computes Philox call (step * 32 + l) of the slice =
+    // draws 2l and 2l + 1 of the step, turns their gap words into gaps, and a warp prefix sum over (gap + 1) gives
+    // every draw its position in the slice - the same positions the sequential walk visits, since draw d's event sits
+    // at sum_{j <= d} (gap_j + 1) - 1. Draws whose position falls beyond the slice are dropped; the first of them ends
+    // the slice. All 32 lanes execute the same instructions (no divergence), valid draws only differ in predicates.
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t q = 0, b = 0;  // sequence this warp works on, its buffer (warp-uniform)
     uint32_t *c = ctl;
-    bool active = false;
-    uint32_t sl = 0, a = 0, total = 0, call = 0, inv = 0, sh = 0, ebase = 0, n_out = 1, kind = 0, t0 = 0, t1 = 0, t2 = 0, thr_off = 0;
-    // the flips of an event are applied one event later, so its table entry has time to arrive
-    uint4 pend = make_uint4(RESP_NONE, RESP_NONE, RESP_NONE, RESP_NONE);
-    uint32_t pend_m = 0, pend_o = 0;
+    bool entered = false;
+    uint32_t rowbase_m = 0, rowbase_o = 0, c2 = 0, c3 = 0;
+    const uint32_t e0 = p.n_classes > 0 ? cls[0].slice_end : 0xFFFFFFFFu, e1 = p.n_classes > 1 ? cls[1].slice_end : 0xFFFFFFFFu,
+                   e2 = p.n_classes > 2 ? cls[2].slice_end : 0xFFFFFFFFu;
+    // the flips of a step's events are applied one step later, so their table entries have time to arrive
+    uint4 pend0 = make_uint4(RESP_NONE, RESP_NONE, RESP_NONE, RESP_NONE), pend1 = pend0;
+    uint32_t pm0 = 0, po0 = 0, pm1 = 0, po1 = 0;
 
+    // flips output bit v of a row unless v is an empty slot / overflow link (bit 31 set): predicated, no branch
     auto flip = [&](uint32_t row_m, uint32_t row_o, uint32_t v) {
-        if (SEPARATE && (v & 0x40000000u)) {
-            flip_bit(img0_saddr, row_o + (v & 0x3FFFFFFFu));
+        uint32_t bit;
+        if (SEPARATE) {
+            bit = ((v & 0x40000000u) ? row_o : row_m) + (v & 0x3FFFFFFFu);
         } else {
-            flip_bit(img0_saddr, row_m + v);
+            bit = row_m + v;
         }
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.lt.u32 p, %2, 0x80000000;\n"
+            "@p red.shared.xor.b32 [%0], %1;\n"
+            "}" ::"r"(img0_saddr + ((bit >> 5) << 2)),
+            "r"(1u << (bit & 31u)), "r"(v)
+            : "memory");
     };
-    auto apply_pending = [&]() {
-        if (pend.x != RESP_NONE) {
-            flip(pend_m, pend_o, pend.x);
-            if (pend.y != RESP_NONE) {
-                flip(pend_m, pend_o, pend.y);
-                if (pend.z != RESP_NONE) {
-                    flip(pend_m, pend_o, pend.z);
-                    if (pend.w != RESP_NONE) {
-                        if (pend.w & RESP_OVERFLOW) {
-                            const uint32_t *ov = p.overflow + (pend.w & 0x7FFFFFFFu);
-                            const uint32_t cnt = __ldg(ov);
-                            for (uint32_t j = 1; j <= cnt; j++) {
-                                flip(pend_m, pend_o, __ldg(ov + j));
-                            }
-                        } else {
-                            flip(pend_m, pend_o, pend.w);
-                        }
-                    }
-                }
+    auto apply = [&](const uint4 &e, uint32_t row_m, uint32_t row_o) {
+        flip(row_m, row_o, e.x);
+        flip(row_m, row_o, e.y);
+        flip(row_m, row_o, e.z);
+        flip(row_m, row_o, e.w);
+        if (e.w != RESP_NONE && (e.w & RESP_OVERFLOW)) {
+            const uint32_t *ov = p.overflow + (e.w & 0x7FFFFFFFu);
+            const uint32_t cnt = __ldg(ov);
+            for (uint32_t j = 1; j <= cnt; j++) {
+                flip(row_m, row_o, __ldg(ov + j));
             }
         }
     };
 
-    while (true) {
-        if (!active) {
-#pragma unroll 1
-            for (int attempt = 0; attempt < 2 && !active; attempt++) {
-                if (q >= n_seq) {
-                    break;
-                }
-                if (!entered) {
-                    if (ld_volatile_shared(c + 3) != q + 1) {
-                        __nanosleep(32);  // the buffer still belongs to sequence q - NB
-                        break;
-                    }
+    while (q < n_seq) {
+        if (!entered) {
+            // wait until the buffer has been recycled for sequence q
+            while (ld_volatile_shared(c + 3) != q + 1) {
+                __nanosleep(32);
+            }
+            __threadfence_block();
+            const uint64_t gt = p.tile0 + blockIdx.x + (uint64_t)q * gridDim.x;
+            c2 = (uint32_t)gt;
+            c3 = SPARSE_TAG | (uint32_t)(gt >> 32);
+            rowbase_m = (b * p.img_bytes + c[4]) * 8u;
+            rowbase_o = (b * p.img_bytes + p.obs_img_off + c[5]) * 8u;
+            entered = true;
+        }
+        uint32_t sl = 0;
+        if (lane == 0) {
+            sl = atomicAdd(c, 1u);
+        }
+        sl = __shfl_sync(0xFFFFFFFFu, sl, 0);
+        if (sl >= p.n_slices) {
+            // the pool of sequence q is dry: apply what is pending, count this warp out, move on
+            apply(pend0, pm0, po0);
+            apply(pend1, pm1, po1);
+            pend0.x = pend0.y = pend0.z = pend0.w = RESP_NONE;
+            pend1 = pend0;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) {
+                if (atomicAdd(c + 1, 1u) + 1 == n_prod_warps) {
                     __threadfence_block();
-                    const uint64_t gt = p.tile0 + blockIdx.x + (uint64_t)q * gridDim.x;
-                    c2 = (uint32_t)gt;
-                    c3 = SPARSE_TAG | (uint32_t)(gt >> 32);
-                    rowbase_m = (b * p.img_bytes + c[4]) * 8u;
-                    rowbase_o = (b * p.img_bytes + p.obs_img_off + c[5]) * 8u;
-                    entered = true;
-                }
-                sl = atomicAdd(c, 1u);
-                if (sl < p.n_slices) {
-                    uint32_t k = 0;
-                    while (sl >= cls[k].slice_end) {
-                        k++;
-                    }
-                    const EvClass &cl = cls[k];
-                    const uint32_t s0 = (sl - cl.slice0) * cl.per;
-                    total = min(cl.per, cl.n_sites - s0) << p.log_s;
-                    n_out = cl.n_out;
-                    ebase = cl.entry0 + s0 * n_out;
-                    inv = cl.inv;
-                    sh = cl.sh;
-                    kind = cl.kind;
-                    t0 = cl.thr[0];
-                    t1 = cl.thr[1];
-                    t2 = cl.thr[2];
-                    thr_off = cl.thr_off;
-                    a = 0;
-                    call = 0;
-                    active = true;
-                } else {
-                    // the pool of sequence q is dry: apply what is pending, count this lane out, move on
-                    apply_pending();
-                    pend.x = RESP_NONE;
-                    __threadfence_block();
-                    if (atomicAdd(c + 1, 1u) + 1 == n_prod) {
-                        __threadfence_block();
-                        st_volatile_shared(c + 2, q + 1);
-                    }
-                    q++;
-                    b = b + 1 == NB ? 0 : b + 1;
-                    c = ctl + b * CTL_WORDS;
-                    entered = false;
+                    st_volatile_shared(c + 2, q + 1);
                 }
             }
-            if (q >= n_seq) {
+            q++;
+            b = b + 1 == NB ? 0 : b + 1;
+            c = ctl + b * CTL_WORDS;
+            entered = false;
+            continue;
+        }
+        uint32_t k = (sl >= e0 ? 1u : 0u) + (sl >= e1 ? 1u : 0u) + (sl >= e2 ? 1u : 0u);
+        if (k == 3) {
+            while (sl >= cls[k].slice_end) {
+                k++;
+            }
+        }
+        const uint4 *cw = reinterpret_cast<const uint4 *>(cls + k);
+        const uint4 w0 = cw[0], w1 = cw[1], w2 = cw[2];  // (slice_end, slice0, per, n_sites) (entry0, inv, sh, kind) (n_out, thr)
+        const uint32_t s0 = (sl - w0.y) * w0.z;
+        const uint32_t total = min(w0.z, w0.w - s0) << p.log_s;  // trials of the slice (<= 2^30)
+        const uint32_t n_out = w2.x, ebase = w1.x + s0 * n_out, inv = w1.y, sh = w1.z, kind = w1.w;
+        const uint32_t t0 = w2.y, t1 = w2.z, t2 = w2.w, thr_off = cls[k].thr_off;
+
+        uint32_t a0 = 0;  // trials consumed by the previous steps
+        for (uint32_t call0 = 0;; call0 += 32) {
+            const uint4 r = sp_philox(sl, call0 + lane, c2, c3, p.rk);
+            const uint32_t rem = total - a0;  // > 0
+            // gaps of the lane's two draws, clamped to rem (a clamped gap is an overshoot)
+            uint32_t G[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t v = (h ? r.z : r.x) | 1u;
+                const uint32_t t = 31u - (uint32_t)__clz((int)v);
+                const uint32_t frac = (v << (31u - t)) << 1;
+                const uint2 en = lt[frac >> 24];
+                const uint32_t log2v = (t << 26) + en.x + ((en.y * ((frac >> 11) & 0x1FFFu)) >> 13);
+                const uint32_t E = __umulhi(0x80000000u - log2v, GSTIM_LN2_Q32);
+                const unsigned long long g = ((unsigned long long)E * inv) >> sh;
+                G[h] = (uint32_t)min(g, (unsigned long long)rem);
+            }
+            // saturating prefix sum of (gap + 1) over the 64 draws of the step (saturation at rem keeps 32 bits exact for
+            // every draw that is still inside the slice)
+            const uint32_t s_a = min(G[0] + 1u, rem), s_ab = min(s_a + G[1] + 1u, rem);
+            uint32_t incl = s_ab;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (uint32_t)d) {
+                    incl = min(incl + up, rem);
+                }
+            }
+            uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+            if (lane == 0) {
+                excl = 0;
+            }
+            const uint32_t consumed = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            // event of draw h sits at trial a0 + (trials before the draw) + gap; it exists iff that is < total
+            const uint32_t off0 = excl + G[0], off1 = excl + s_a + G[1];
+            const bool ok0 = off0 < rem, ok1 = ok0 && off1 < rem;
+            // last step's events first (their entries have arrived by now), then this step's loads take their place
+            apply(pend0, pm0, po0);
+            apply(pend1, pm1, po1);
+            pend0.x = pend0.y = pend0.z = pend0.w = RESP_NONE;
+            pend1 = pend0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const bool ok = h ? ok1 : ok0;
+                const uint32_t pos = a0 + (h ? off1 : off0), pw = h ? r.w : r.y;
+                const uint32_t site = pos >> p.log_s, shot = pos & smask;
+                // outcome: uniform (mulhi) or the number of thresholds <= pw (t_j hold threshold - 1; unused ones 0xFFFFFFFF)
+                uint32_t o = (pw > t0 ? 1u : 0u) + (pw > t1 ? 1u : 0u) + (pw > t2 ? 1u : 0u);
+                if (kind == DK_UNIFORM) {
+                    o = __umulhi(pw, n_out);
+                }
+                if (kind == DK_THRESH_N) {
+                    o = 0;
+                    for (uint32_t j = 0; j + 1 < n_out; j++) {
+                        o += pw >= __ldg(p.thr_all + thr_off + j) ? 1u : 0u;
+                    }
+                }
+                if (ok) {
+                    const uint4 e = __ldg(p.entries + (ebase + site * n_out + o));
+                    if (h) {
+                        pend1 = e;
+                    } else {
+                        pend0 = e;
+                    }
+                }
+                if (h) {
+                    pm1 = rowbase_m + shot * main_bits;
+                    po1 = rowbase_o + shot * obs_bits;
+                } else {
+                    pm0 = rowbase_m + shot * main_bits;
+                    po0 = rowbase_o + shot * obs_bits;
+                }
+            }
+            a0 += consumed;
+            if (a0 >= total) {  // (warp-uniform) some draw of this step overshot, or the last trial fired
                 break;
             }
         }
-        if (!active) {
-            continue;
-        }
-        const uint4 r = sp_philox(sl, call, c2, c3, p.rk);
-        call++;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            if (!active) {
-                continue;
-            }
-            const uint32_t gw = h ? r.z : r.x, pw = h ? r.w : r.y;
-            // E = -ln(v / 2^32) in units of 2^-26 nat (dem.cu header)
-            const uint32_t v = gw | 1u;
-            const uint32_t t = 31u - (uint32_t)__clz((int)v);
-            const uint32_t frac = (v << (31u - t)) << 1;
-            const uint2 en = lt[frac >> 24];
-            const uint32_t log2v = (t << 26) + en.x + ((en.y * ((frac >> 11) & 0x1FFFu)) >> 13);
-            const uint32_t E = __umulhi(0x80000000u - log2v, GSTIM_LN2_Q32);
-            const unsigned long long G = ((unsigned long long)E * inv) >> sh;
-            if (G >= (unsigned long long)(total - a)) {
-                active = false;
-                continue;
-            }
-            a += (uint32_t)G;
-            const uint32_t site = a >> p.log_s, shot = a & smask;
-            a++;
-            if (a >= total) {
-                active = false;
-            }
-            uint32_t o = 0;
-            if (kind == DK_UNIFORM) {
-                o = __umulhi(pw, n_out);
-            } else if (kind == DK_THRESH3) {
-                o = (pw >= t0 ? 1u : 0u) + ((pw >= t1 && n_out > 2) ? 1u : 0u) + ((pw >= t2 && n_out > 3) ? 1u : 0u);
-            } else if (kind == DK_THRESH_N) {
-                for (uint32_t j = 0; j + 1 < n_out; j++) {
-                    o += pw >= __ldg(p.thr_all + thr_off + j) ? 1u : 0u;
-                }
-            }
-            const uint4 e = __ldg(p.entries + (ebase + site * n_out + o));
-            apply_pending();
-            pend = e;
-            pend_m = rowbase_m + shot * main_bits;
-            if (SEPARATE) {
-                pend_o = rowbase_o + shot * obs_bits;
-            }
-        }
     }
+    // (q == n_seq: every sequence has been left with nothing pending)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -549,7 +576,13 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
     }
     const uint32_t S = 1u << I.log_s;
 
-    // slices: runs of sites with about `slice_events` expected events per tile
+    // slices: runs of sites with about `slice_events` expected events per tile. A producer warp walks a slice 64 draws at
+    // a time, so ~48 events per slice keep most draws of a step useful; circuits with few events per tile get smaller
+    // slices so that there is work for every warp (0 = this automatic choice; it is part of the stream's definition).
+    if (slice_events == 0) {
+        const double per_tile = I.rt.events_per_shot * S;
+        slice_events = (uint32_t)std::max(4.0, std::min(48.0, per_tile / 62.0));
+    }
     std::vector<EvClass> cls;
     std::vector<uint32_t> thr_all;
     for (const RespClass &c : I.rt.classes) {
@@ -566,8 +599,8 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
         d.sh = c.sh;
         d.n_out = c.n_out;
         d.kind = c.kind == RK_SINGLE ? DK_SINGLE : c.kind == RK_UNIFORM ? DK_UNIFORM : c.n_out <= 4 ? DK_THRESH3 : DK_THRESH_N;
-        for (int j = 0; j < 3; j++) {
-            d.thr[j] = c.thr[j];
+        for (uint32_t j = 0; j < 3; j++) {  // registers of the chooser: threshold - 1 (pw > t <=> pw >= threshold), unused: never
+            d.thr[j] = (d.kind == DK_THRESH3 && j + 1 < c.n_out) ? c.thr[j] - 1u : 0xFFFFFFFFu;
         }
         d.thr_off = (uint32_t)thr_all.size();
         thr_all.insert(thr_all.end(), c.thr, c.thr + 15);

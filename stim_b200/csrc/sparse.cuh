@@ -18,7 +18,7 @@ struct SparseClassDev {  // 80 bytes
 // Owns the device copy of a response table and launches the sampling kernel. Not thread-safe (like the sampler handle).
 class SparseEngine {
   public:
-    // slice_events: expected events per slice and tile (part of the random stream's definition; default 4)
+    // slice_events: expected events per slice and tile (part of the random stream's definition; 0 = automatic)
     SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32_t L, uint32_t M, int device, uint32_t slice_events);
     ~SparseEngine();
     SparseEngine(const SparseEngine &) = delete;
