@@ -39,14 +39,14 @@ LOP3_LANES_PER_CLK_PER_SM = 64   # fallback only (B300_MICROARCH.md: alu pipe rt
 C4_CIRCUIT = os.path.join(ROOT, "tests", "golden", "circuits", "c4_color_d15_r15.stim")
 
 
-def measured_traffic_bytes_per_shot():
-    """DRAM bytes per shot of the interpreter kernel from the committed `ncu --set full` capture (profiles/r2_interp_full.json,
-    else the round-1 one). Returns (bytes per shot, file name)."""
-    for name in ("r2_interp_full.json", "r1_interp_full.json"):
+def ncu_capture(engine):
+    """The committed `ncu --set full` summary of the dominant kernel of `engine` (profiles/r2_events_full.json for the event
+    engine, the interpreter's otherwise). Returns (dict or None, file name)."""
+    names = ("r2_events_full.json",) if engine == "events" else ("r2_interp_full.json", "r1_interp_full.json")
+    for name in names:
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
-                d = json.load(f)
-            return (float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])) / float(d["shots"]), name
+                return json.load(f), name
         except Exception:
             continue
     return None, None
@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--e2e-shots-log2", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="auto", choices=["auto", "interp", "events"],
+                    help="sampling engine (include/gstim.h); auto = the library's own choice (the event engine for this circuit)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -222,7 +224,7 @@ def main():
     with open(CIRCUIT) as f:
         text = f.read()
     circuit = stim_b200.Circuit(text)
-    sampler = circuit.compile_detector_sampler(seed=12345, device=local_rank)
+    sampler = circuit.compile_detector_sampler(seed=12345, device=local_rank, engine=args.engine)
     sampler.shot_offset = rank << 44  # disjoint Philox counter ranges per GPU; no inter-GPU traffic
     D, L = circuit.num_detectors, circuit.num_observables
     nbytes = (D + L + 7) // 8
@@ -249,7 +251,10 @@ def main():
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     clk = clocks.stop()
-    interp_launches = launches // 2 if launches else 1  # one interpreter + one transposer launch per chunk
+    info = sampler.engine_info()
+    engine = info["last_engine"]
+    # interpreter: one interpreter + one transposer launch per chunk; event engine: one launch per call
+    interp_launches = (launches // 2 if engine == "interp" else launches) or 1
     ms_per_step = max_over_ranks(dev_ms / args.steps)
     wall_ms_per_step = max_over_ranks(wall_ms / args.steps)
     value = world * shots / (ms_per_step * 1e-3)
@@ -326,10 +331,27 @@ def main():
                       "circuit": "tests/golden/circuits/c4_color_d15_r15.stim", "shots_per_rank": 1 << 18,
                       "sum_over_ranks_equals_single_sampler": bool(ok)}
 
+    # the other engine on the same workload, 2^22 shots (kept beside the headline for continuity with round 1)
+    other = None
+    try:
+        other_engine = "interp" if engine == "events" else "events"
+        s2 = circuit.compile_detector_sampler(seed=999, device=local_rank, engine=other_engine)
+        n2 = min(shots, 1 << 22)
+        out2 = torch.empty((n2, nbytes), dtype=torch.uint8, device="cuda")
+        best = None
+        for _ in range(3):
+            s2.sample_device(n2, out2.data_ptr(), append_observables=True)
+            best = s2.last_call_ms() if best is None else min(best, s2.last_call_ms())
+        other = {"engine": other_engine, "value": n2 / (best * 1e-3), "unit": "shots/s (one GPU, device-resident)", "shots": n2}
+        del out2, s2
+    except ValueError:
+        pass
+
     lop3 = stim_b200.measure_lop3_peak(local_rank)
 
     peak, peak_src = measured_peak_gbs()
-    traffic_per_shot, traffic_file = measured_traffic_bytes_per_shot()
+    cap, traffic_file = ncu_capture(engine)
+    traffic_per_shot = None if cap is None else (float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])) / float(cap["shots"])
     interp_s = interp_ms * 1e-3
     achieved = ALG_BYTES_PER_SHOT * shots * args.steps / interp_s / 1e9
     sm_mhz = clk.get("sm_mhz") or 1965.0
@@ -339,17 +361,21 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 (bitwise frame words; f64 only in the noise clocks)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u32 (bitwise XOR of output words; integer fixed point in the noise gaps)", "data": "synthetic",
         "config": {
             "workload": WORKLOAD, "shots_per_gpu_per_step": shots, "output": "b8 dets+obs, 1951 B/shot, resident in HBM",
             "circuit": "tests/golden/circuits/c3_surface_z_d25_r25.stim",
             "l2": "each step writes 32.7 GB of fresh output (>> 126 MB L2); nothing is reused across steps",
-            "threads": int(sampler.stats.threads), "noise_producer_threads": 128,
+            "engine": engine,
+            "engine_info": {k: info[k] for k in ("tile_shots", "num_sites", "num_entries", "num_slices", "events_per_shot", "flips_per_shot")},
+            "threads": 1024 if engine == "events" else int(sampler.stats.threads),
             "columns_per_block": sampler.last_block_columns(),
-            "detection_fraction_check": frac,
+            "nonzero_byte_fraction_check": frac,
         },
         "gpu_launches": launches,
-        "kernel_ms_per_step": {"interp": interp_ms / args.steps, "transpose": transpose_ms / args.steps},
+        "kernel_ms_per_step": ({"events": interp_ms / args.steps} if engine == "events" else
+                               {"interp": interp_ms / args.steps, "transpose": transpose_ms / args.steps}),
+        "other_engine": other,
         "clocks": clk,
         "e2e": {
             "value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": e2e_shots * nbytes,
@@ -363,7 +389,8 @@ def main():
         },
         "collective": collective,
         "roofline": {
-            "kernel": "gstim_interp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "kernel": "gstim_sparse_kernel" if engine == "events" else "gstim_interp_kernel", "bound": "hbm", "achieved": achieved,
+            "peak": peak, "unit": "GB/s",
             "frac": achieved / peak,
             "traffic": (None if traffic_per_shot is None else traffic_per_shot * shots * args.steps / interp_launches),
             "traffic_source": f"dram__bytes_read+write of profiles/{traffic_file} scaled to the shots of one launch",
@@ -372,10 +399,19 @@ def main():
             "alg_bytes_per_launch": ALG_BYTES_PER_SHOT * shots * args.steps / interp_launches,
             "alu_bound": {"lop3_per_shot": ALG_LOP3_PER_SHOT, "achieved_lop3_per_s": per_gpu_rate_interp * ALG_LOP3_PER_SHOT,
                           "peak_lop3_per_s": lop3_peak, "frac": per_gpu_rate_interp * ALG_LOP3_PER_SHOT / lop3_peak,
+                          "note": "word-ops of the reference's frame algorithm; the event engine does not execute them (it is "
+                                  "bound by instruction issue, see issue_bound)" if engine == "events" else "",
                           "peak_basis": f"measured: LOP3 microbenchmark in this run = {lanes:.2f} lanes/clk/SM "
                                         f"({lop3['lane_ops_per_sec'] / 1e12:.2f} T lane-ops/s at {lop3['sm_mhz']:.0f} MHz) x 148 SMs x "
                                         f"{sm_mhz:.0f} MHz sampled during the timed region",
                           "lop3_probe": lop3},
+            # what binds the event engine: warp instructions per shot (ncu capture) against 4 issue slots per clock and SM
+            "issue_bound": (None if cap is None or engine != "events" else {
+                "warp_instructions_per_shot": float(cap["warp_instructions"]) / float(cap["shots"]),
+                "achieved_warp_inst_per_s": per_gpu_rate_interp * float(cap["warp_instructions"]) / float(cap["shots"]),
+                "peak_warp_inst_per_s": 148 * 4 * sm_mhz * 1e6,
+                "frac": per_gpu_rate_interp * float(cap["warp_instructions"]) / float(cap["shots"]) / (148 * 4 * sm_mhz * 1e6),
+                "source": f"smsp__inst_executed.sum of profiles/{traffic_file}"}),
         },
     }
 

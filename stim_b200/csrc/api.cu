@@ -361,7 +361,8 @@ void configure_event_engine(gstim_sampler *s) {
     const bool favoured = ev_cost < interp_cost;
     try {
         s->sparse = std::make_unique<SparseEngine>(
-            std::move(rt), (uint32_t)s->mode, s->plan.num_det, s->plan.num_obs, s->plan.num_meas, s->device, env_u32("GSTIM_SLICE_EVENTS", 0));
+            std::move(rt), (uint32_t)s->mode, s->plan.num_det, s->plan.num_obs, s->plan.num_meas, s->device, env_u32("GSTIM_SLICE_EVENTS", 0),
+            env_u32("GSTIM_TILE_BUFFERS", 0));
         s->sparse_favoured = favoured;
         s->sparse_why.clear();
     } catch (const std::invalid_argument &e) {

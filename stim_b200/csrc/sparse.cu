@@ -537,7 +537,8 @@ struct SparseEngine::Impl {
     }
 };
 
-SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32_t L, uint32_t M, int device, uint32_t slice_events)
+SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32_t L, uint32_t M, int device, uint32_t slice_events,
+                           uint32_t tile_buffers)
     : impl(new Impl()) {
     Impl &I = *impl;
     I.rt = std::move(rt);
@@ -559,10 +560,13 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
         throw std::invalid_argument("device has less than 227 KiB of shared memory per block");
     }
     bool ok = false;
-    for (uint32_t bufs = 3; bufs >= 1 && !ok; bufs--) {
+    uint32_t n_buffers_hint = 1;
+    const uint32_t want_bufs = tile_buffers ? tile_buffers : 3;
+    for (uint32_t bufs = want_bufs; bufs >= 1 && !ok; bufs--) {
         for (int ls = 7; ls >= 0; ls--) {
             if (((((size_t)I.row_all << ls) + 64) * bufs) <= budget) {
                 I.log_s = (uint32_t)ls;
+                n_buffers_hint = (uint32_t)std::min<size_t>(MAX_BUFFERS, budget / (((size_t)I.row_all << ls) + 64));
                 ok = true;
                 break;
             }
@@ -580,8 +584,19 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
     // a time, so ~48 events per slice keep most draws of a step useful; circuits with few events per tile get smaller
     // slices so that there is work for every warp (0 = this automatic choice; it is part of the stream's definition).
     if (slice_events == 0) {
-        const double per_tile = I.rt.events_per_shot * S;
-        slice_events = (uint32_t)std::max(4.0, std::min(48.0, per_tile / 62.0));
+        // k steps of 64 draws hold a slice of mu events when mu + 1 + 1.5 sigma <= 64 k; take the largest k <= 3 that still
+        // leaves two slices per producer warp among the tiles a block has in flight
+        const double in_flight = I.rt.events_per_shot * S * n_buffers_hint;
+        slice_events = 4;
+        for (int k = 1; k <= 3; k++) {
+            const double mu = 64.0 * k - 1.5 * std::sqrt(64.0 * k) - 1.0;
+            if (in_flight / mu >= 2.0 * 31) {
+                slice_events = (uint32_t)mu;
+            }
+        }
+        if (slice_events == 4) {
+            slice_events = (uint32_t)std::max(4.0, std::min(51.0, in_flight / 62.0));
+        }
     }
     std::vector<EvClass> cls;
     std::vector<uint32_t> thr_all;

@@ -19,7 +19,9 @@ struct SparseClassDev {  // 80 bytes
 class SparseEngine {
   public:
     // slice_events: expected events per slice and tile (part of the random stream's definition; 0 = automatic)
-    SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32_t L, uint32_t M, int device, uint32_t slice_events);
+    // tile_buffers: tile images a block should be able to hold (decides the tile height; 0 = default 3)
+    SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32_t L, uint32_t M, int device, uint32_t slice_events,
+                 uint32_t tile_buffers);
     ~SparseEngine();
     SparseEngine(const SparseEngine &) = delete;
     SparseEngine &operator=(const SparseEngine &) = delete;

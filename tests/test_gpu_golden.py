@@ -12,6 +12,14 @@ from golden_util import arrange, case_ids, expected_bits, load_cases, output_byt
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["interp", "events"])
+def engine(request, monkeypatch):
+    """Every golden case runs under both engines: the reference's deterministic outputs do not depend on how the shots
+    are sampled ("events" = the event engine wherever the circuit is eligible for it)."""
+    monkeypatch.setenv("GSTIM_ENGINE", request.param)
+    return request.param
+
 CASES = load_cases()
 DETECT = [c for c in CASES if c["mode"] == "detect"]
 SAMPLE = [c for c in CASES if c["mode"] == "sample"]

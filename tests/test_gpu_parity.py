@@ -10,6 +10,13 @@ from oracle import frame_oracle as fo
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _interpreter_engine(monkeypatch):
+    """These tests compare with the frame oracle's random stream, which is the interpreter's (the event engine draws a
+    different stream and has its own bit-exact tests in test_gpu_events.py)."""
+    monkeypatch.setenv("GSTIM_ENGINE", "interp")
+
+
 def oracle_for(sampler, text, shots, seed, mode, offset_before):
     K = sampler.last_block_columns()
     assert K >= 1

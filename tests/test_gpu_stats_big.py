@@ -67,17 +67,22 @@ def check(k_gpu, n_gpu, k_ref, n_ref, what):
     return rms, float(np.abs(zz).max()) if zz.size else 0.0
 
 
+@pytest.mark.parametrize("engine", ["interp", "events"])
 @pytest.mark.parametrize("name", NAMES)
-def test_full_size_configs_match_reference_statistics(name):
+def test_full_size_configs_match_reference_statistics(name, engine):
     ref = np.load(os.path.join(SDIR, name + ".npz"))
     mode, n_ref, n_bits = str(ref["mode"]), int(ref["n_ref"]), int(ref["n_bits"])
     circ = stim_b200.Circuit(circuit_text(name))
     sampler = circ.compile_detector_sampler(seed=20261017) if mode == "detect" else circ.compile_sampler(seed=20261017)
+    if engine == "events" and not sampler.engine_info()["eligible"]:
+        pytest.skip("not eligible for the event engine: " + sampler.engine_info()["why_not"])
+    sampler.set_engine(engine)
     single, pair = sampler.bit_counts(N_GPU)
+    assert sampler.engine_info()["last_engine"] == engine
     assert single.size == n_bits and pair.size == n_bits - 1
     r1 = check(single, N_GPU, ref["single"], n_ref, name + " rates")
     r2 = check(pair, N_GPU, ref["pair"], n_ref, name + " adjacent-pair correlations")
-    print(f"{name}: {n_bits} bits, K={sampler.last_block_columns()}, rates z rms/max {r1[0]:.3f}/{r1[1]:.2f}, "
+    print(f"{name} [{engine}]: {n_bits} bits, K={sampler.last_block_columns()}, rates z rms/max {r1[0]:.3f}/{r1[1]:.2f}, "
           f"pairs z rms/max {r2[0]:.3f}/{r2[1]:.2f}")
 
 

@@ -1,0 +1,108 @@
+"""CPU tests of the event engine's response table (stim_b200/csrc/response.cc, host only): every (site, outcome) entry
+the library derives by BACKWARD sensitivity propagation must equal the set of output bits that flip when that single
+event is injected into the FORWARD frame oracle (oracle/frame_oracle.py, pinned against the reference CLI's goldens)."""
+import os
+
+import numpy as np
+import pytest
+
+import stim_b200
+from conftest import ROOT, gen_circuit
+from oracle import sparse_oracle as so
+from test_gpu_parity import ALL_OPS
+
+ALL_OPS_NO_ELSE = "\n".join(l for l in ALL_OPS.split("\n") if not l.startswith("ELSE_CORRELATED_ERROR"))
+
+
+def check_table(text, mode="detectors", entries=None):
+    t = stim_b200.response_table(text, mode)
+    assert t["info"]["eligible"] == 1, t["info"]["why_not"]
+    want = so.responses_by_injection(text, t, mode, entries)
+    assert len(want) > 0
+    bad = [(e, so.entry_ids(t, e), ids) for e, ids in want.items() if so.entry_ids(t, e) != ids]
+    assert not bad, bad[:5]
+    return t
+
+
+@pytest.mark.parametrize("mode", ["detectors", "measurements"])
+def test_every_instruction_matches_forward_injection(mode):
+    t = check_table(ALL_OPS_NO_ELSE, mode)
+    assert t["info"]["overflow_words"] > 0  # responses longer than four bits go through the overflow list
+    if mode == "measurements":
+        assert (t["site_group"] & 0x80000000).any()  # collapse randomisation that reaches an output is a p = 1/2 site
+
+
+GENERATED = [
+    ("repetition_code", "memory", 3, 10, 0.02),
+    ("surface_code", "rotated_memory_z", 3, 3, 0.02),
+    ("surface_code", "rotated_memory_x", 5, 5, 0.01),
+    ("surface_code", "unrotated_memory_z", 3, 2, 0.05),
+    ("color_code", "memory_xyz", 3, 3, 0.02),
+    ("color_code", "memory_xyz", 5, 2, 0.01),
+]
+
+
+@pytest.mark.parametrize("code,task,d,r,p", GENERATED)
+def test_generated_circuits_match_forward_injection(code, task, d, r, p):
+    t = check_table(gen_circuit(code, task, d, r, p))
+    # QEC memory circuits have deterministic detectors: no collapse bit reaches an output
+    assert not (t["site_group"] & 0x80000000).any()
+
+
+def test_measurement_mode_of_a_memory_circuit():
+    check_table(gen_circuit("surface_code", "rotated_memory_x", 3, 3, 0.02), "measurements")
+
+
+def test_feedback_and_repeat_blocks():
+    text = """
+    R 0 1 2
+    X_ERROR(0.1) 0 1
+    REPEAT 4 {
+        CX 0 2 1 2
+        DEPOLARIZE2(0.05) 0 2
+        MR 2
+        CX rec[-1] 0
+        CZ rec[-1] 1
+        DETECTOR rec[-1]
+        HERALDED_ERASE(0.1) 1
+        DETECTOR rec[-1] rec[-2]
+    }
+    M 0 1
+    DETECTOR rec[-1] rec[-2] rec[-4]
+    OBSERVABLE_INCLUDE(0) rec[-1]
+    OBSERVABLE_INCLUDE(1) X0 Z1
+    """
+    check_table(text)
+    check_table(text, "measurements")
+
+
+def test_headline_circuit_table():
+    """c3 (d = 25): table statistics, and a random sample of entries against forward injection."""
+    with open(os.path.join(ROOT, "tests", "golden", "circuits", "c3_surface_z_d25_r25.stim")) as f:
+        text = f.read()
+    t = stim_b200.response_table(text)
+    info = t["info"]
+    assert info["eligible"] == 1 and info["num_sites"] == 124299 and info["num_classes"] == 3
+    assert abs(info["events_per_shot"] - 124.299) < 0.01 and info["max_response"] == 4 and info["overflow_words"] == 0
+    rng = np.random.default_rng(5)
+    pick = set(int(v) for v in rng.choice(int(info["num_entries"]), size=384, replace=False))
+    want = so.responses_by_injection(text, t, "detectors", pick)
+    assert len(want) == 384
+    for e, ids in want.items():
+        assert so.entry_ids(t, e) == ids, e
+
+
+def test_else_chain_is_reported_as_not_eligible():
+    t = stim_b200.response_table(ALL_OPS)
+    assert t["info"]["eligible"] == 0 and "ELSE_CORRELATED_ERROR" in t["info"]["why_not"]
+
+
+def test_oracle_sampler_statistics_on_a_tiny_circuit():
+    """The sampler restatement itself: flip rates of a two-site toy table match the probabilities."""
+    text = "X_ERROR(0.25) 0\nM 0\nDETECTOR rec[-1]\nX_ERROR(0.5) 1\nM 1\nDETECTOR rec[-1]\n"
+    t = stim_b200.response_table(text)
+    # slices as the engine builds them for a 128-shot tile: one slice per class covering all its sites
+    slices = np.array([[ci, int(c[21]) * 128, int(c[22]), 0] for ci, c in enumerate(t["classes"])], dtype=np.uint32)
+    out = so.sample(t, slices, 128, seed=7, first_shot=0, n_shots=1 << 14, n_outputs=2)
+    rates = out.mean(axis=0)
+    assert abs(rates[0] - 0.25) < 0.02 and abs(rates[1] - 0.5) < 0.02
