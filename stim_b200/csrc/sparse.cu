@@ -100,11 +100,18 @@ __device__ __forceinline__ uint4 sp_philox(uint32_t c0, uint32_t c1, uint32_t c2
     return make_uint4(c0, c1, c2, c3);
 }
 
-__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
-    return *reinterpret_cast<const volatile uint32_t *>(p);
+// Hand-over flags between the producer warps and the writer warp (shared memory). They are read and written with
+// atomics so that the accesses are ordered by the memory model itself (and compute-sanitizer's racecheck sees them as
+// synchronisation, not as data races); the polls sit behind __nanosleep, so the extra atomic traffic is negligible.
+__device__ __forceinline__ uint32_t ld_volatile_shared(uint32_t *p) {  // whole warp, converged: lane 0 polls
+    uint32_t v = 0;
+    if ((threadIdx.x & 31u) == 0) {
+        v = atomicAdd(p, 0u);
+    }
+    return __shfl_sync(0xFFFFFFFFu, v, 0);
 }
 __device__ __forceinline__ void st_volatile_shared(uint32_t *p, uint32_t v) {
-    *reinterpret_cast<volatile uint32_t *>(p) = v;
+    atomicExch(p, v);
 }
 
 // Copies `nbytes` bytes from shared memory (image coordinate `phase`) to dst, where (dst & 15) == phase; one warp.
