@@ -37,6 +37,15 @@ ALG_BYTES_PER_SHOT = 1951       # ceil((15600 detectors + 1 observable) / 8): re
 ALG_LOP3_PER_SHOT = 168026 / 32  # XOR word-ops of the frame algorithm per shot
 LOP3_LANES_PER_CLK_PER_SM = 64   # fallback only (B300_MICROARCH.md: alu pipe rt_SMSP = 2 -> 16 lanes/clk/SMSP); bench measures it
 C4_CIRCUIT = os.path.join(ROOT, "tests", "golden", "circuits", "c4_color_d15_r15.stim")
+# the other BASELINE.json configurations (--config): parity-test cases, benchable on request
+CONFIGS = {
+    "c1": ("c1_rep_d3_r10.stim", "repetition_code:memory d=3 rounds=10 p=1e-3"),
+    "c2": ("c2_surface_x_d5_r5.stim", "surface_code:rotated_memory_x d=5 rounds=5 p=1e-3"),
+    "c3": ("c3_surface_z_d25_r25.stim", None),
+    "c4": ("c4_color_d15_r15.stim", "color_code:memory_xyz d=15 rounds=15 p=1e-3"),
+    "c4v": ("c4v_color_d15_r15_mpp_dense.stim", "color_code:memory_xyz d=15 rounds=15 with MPP and dense noise"),
+    "c5": ("c5_surface_x_d51_r51.stim", "surface_code:rotated_memory_x d=51 rounds=51 p=1e-3 (5201 qubits)"),
+}
 
 
 def ncu_capture(engine):
@@ -181,6 +190,7 @@ def main():
     ap.add_argument("--e2e-shots-log2", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: the headline c3)")
     ap.add_argument("--engine", default="auto", choices=["auto", "interp", "events"],
                     help="sampling engine (include/gstim.h); auto = the library's own choice (the event engine for this circuit)")
     args = ap.parse_args()
@@ -189,6 +199,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    global CIRCUIT, WORKLOAD, METRIC, ALG_BYTES_PER_SHOT, ALG_LOP3_PER_SHOT
+    if args.config != "c3":
+        fname, wl = CONFIGS[args.config]
+        CIRCUIT = os.path.join(ROOT, "tests", "golden", "circuits", fname)
+        WORKLOAD = wl + ", b8 detection events + observables"
+        METRIC = "detector shots/s, " + wl
+        ALG_BYTES_PER_SHOT = None  # from the circuit below
+        ALG_LOP3_PER_SHOT = float("nan")
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
@@ -228,8 +246,12 @@ def main():
     sampler.shot_offset = rank << 44  # disjoint Philox counter ranges per GPU; no inter-GPU traffic
     D, L = circuit.num_detectors, circuit.num_observables
     nbytes = (D + L + 7) // 8
+    if ALG_BYTES_PER_SHOT is None:
+        ALG_BYTES_PER_SHOT = nbytes
     assert nbytes == ALG_BYTES_PER_SHOT
     shots = 1 << args.shots_log2
+    while shots * nbytes > (40 << 30):  # (c5: 16.6 KB per shot)
+        shots >>= 1
 
     # ---- device-resident arm -----------------------------------------------------------------
     out = torch.empty((shots, nbytes), dtype=torch.uint8, device="cuda")
@@ -266,7 +288,7 @@ def main():
     # ---- end-to-end arm (host buffers, D2H inside the timed region) ----------------------------------
     # Headline: the caller's page-locked buffer at the same 2^24 shots per step when the host can pin 32.7 GB per rank
     # (else the largest power of two it can; every rank uses the same size, so the decision is taken together).
-    e2e_log2 = min(args.e2e_shots_log2, args.shots_log2)
+    e2e_log2 = min(args.e2e_shots_log2, shots.bit_length() - 1)
     host = None
     while host is None:
         try:
@@ -363,9 +385,9 @@ def main():
         "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (bitwise XOR of output words; integer fixed point in the noise gaps)", "data": "synthetic",
         "config": {
-            "workload": WORKLOAD, "shots_per_gpu_per_step": shots, "output": "b8 dets+obs, 1951 B/shot, resident in HBM",
-            "circuit": "tests/golden/circuits/c3_surface_z_d25_r25.stim",
-            "l2": "each step writes 32.7 GB of fresh output (>> 126 MB L2); nothing is reused across steps",
+            "workload": WORKLOAD, "shots_per_gpu_per_step": shots, "output": f"b8 dets+obs, {nbytes} B/shot, resident in HBM",
+            "circuit": os.path.relpath(CIRCUIT, ROOT),
+            "l2": f"each step writes {shots * nbytes / 1e9:.1f} GB of fresh output (>> 126 MB L2); nothing is reused across steps",
             "engine": engine,
             "engine_info": {k: info[k] for k in ("tile_shots", "num_sites", "num_entries", "num_slices", "events_per_shot", "flips_per_shot")},
             "threads": 1024 if engine == "events" else int(sampler.stats.threads),

@@ -277,7 +277,7 @@ int gstim_get_engine_info(const gstim_sampler *s, gstim_engine_info *out);
  * Call with words == NULL to get the length in *n_words. */
 int gstim_get_response_table(const gstim_sampler *s, int what, uint32_t *words, size_t *n_words);
 /* Host-only (no GPU needed): lowers the circuit and builds its response table; `what` selectors 0-5 as above.
- * gstim_response_table_info fills the table statistics of gstim_engine_info (eligible, why_not, sites, entries, ...). */
+ * gstim_response_table_info fills the table statistics of a gstim_engine_info struct: eligible, why_not, sites, entries, .... */
 typedef struct gstim_response_table gstim_response_table;
 int gstim_response_table_create(const char *circuit_text, size_t text_len, int mode, gstim_response_table **out);
 void gstim_response_table_destroy(gstim_response_table *t);

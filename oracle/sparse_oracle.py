@@ -24,7 +24,7 @@ from . import philox as px
 NONE = 0xFFFFFFFF
 OVERFLOW = 0x80000000
 SPARSE_TAG = 0x53500000
-RK_SINGLE, RK_UNIFORM, RK_THRESH = 0, 1, 2
+RK_SINGLE, RK_UNIFORM, RK_THRESH, RK_CHAIN = 0, 1, 2, 3
 
 
 def entry_ids(table, e):
@@ -79,12 +79,15 @@ def responses_by_injection(text, table, mode="detectors", entries=None):
     D = L = None
     todo = []  # (entry, group, index, word)
     for ci, c, s0, o0 in class_sites(table):
-        n_out, n_sites, entry0 = int(c[5]), int(c[21]), int(c[22])
+        kind, n_out, n_sites, entry0 = int(c[4]), int(c[5]), int(c[21]), int(c[22])
         for s in range(n_sites):
             for o in range(n_out):
                 e = entry0 + s * n_out + o
                 if entries is None or e in entries:
-                    todo.append((e, int(table["site_group"][s0 + s]), int(table["site_index"][s0 + s]), int(table["outcome_word"][o0 + o])))
+                    g, i, w = int(table["site_group"][s0 + s]), int(table["site_index"][s0 + s]), int(table["outcome_word"][o0 + o])
+                    if kind == RK_CHAIN:  # outcome o = element o of an E / ELSE chain: its own noise group, fired alone
+                        g, w = g + w, 0
+                    todo.append((e, g, i, w))
     noise, collapse = {}, {}
     for shot, (e, g, i, w) in enumerate(todo):
         if g & 0x80000000:
@@ -103,7 +106,7 @@ def responses_by_injection(text, table, mode="detectors", entries=None):
 def choose(kind, n_out, thr, word):
     if kind == RK_UNIFORM:
         return (word * n_out) >> 32
-    if kind == RK_THRESH:
+    if kind in (RK_THRESH, RK_CHAIN):
         return sum(1 for j in range(n_out - 1) if word >= int(thr[j]))
     return 0
 

@@ -142,6 +142,7 @@ struct gstim_sampler {
     // event-driven engine (sparse.cu): present when the circuit's response table exists (response.h)
     std::unique_ptr<SparseEngine> sparse;
     std::string sparse_why;     // why the circuit is not eligible ("" when it is)
+    std::string interp_why;     // why the interpreter cannot run the circuit ("" when it can)
     int engine_pref = GSTIM_ENGINE_AUTO;
     int last_engine = GSTIM_ENGINE_INTERPRETER;
     bool sparse_favoured = false;  // the cost model's choice for GSTIM_ENGINE_AUTO
@@ -269,9 +270,25 @@ void configure(gstim_sampler *s) {
     size_t fixed = interp_smem_bytes(q_pitch, Q, 0, s->chunk_words, s->n_noise);
     size_t per_k = (size_t)2 * q_pitch * 16 + 16;
     if (fixed + per_k > s->smem_optin) {
-        throw std::invalid_argument(
-            "Circuit frame (" + std::to_string(Q) + " active qubits) does not fit in " + std::to_string(s->smem_optin) +
-            " bytes of shared memory; the HBM-tiled frame path is not implemented yet.");
+        // The interpreter keeps the whole frame of a 128-shot column in shared memory. Such circuits are sampled by the
+        // event engine (no frame at all) when they are eligible for it; the interpreter reports this when asked to run.
+        s->interp_why = "Circuit frame (" + std::to_string(Q) + " active qubits) does not fit in " + std::to_string(s->smem_optin) +
+                        " bytes of shared memory: the interpreter cannot sample this circuit (the event engine can, when the "
+                        "circuit is eligible for it).";
+        s->plan = GstimPlan{};
+        s->plan.num_qubits = Q;
+        s->plan.q_pitch = q_pitch;
+        s->plan.num_meas = (uint32_t)s->lc.stats.num_measurements;
+        s->plan.num_det = (uint32_t)s->lc.stats.num_detectors;
+        s->plan.num_obs = (uint32_t)s->lc.stats.num_observables;
+        s->plan.rec_ring = s->lc.rec_ring;
+        s->plan.mode = s->lc.mode;
+        s->plan.max_items = s->lc.max_items;
+        s->plan.n_batches = (uint32_t)s->lc.batches.size();
+        s->slots = slots;
+        s->threads = slots;
+        s->K_max = 0;
+        return;
     }
     uint32_t K_max = (uint32_t)std::min<size_t>((s->smem_optin - fixed) / per_k, 32);
 
@@ -371,6 +388,12 @@ void configure_event_engine(gstim_sampler *s) {
 }
 
 bool use_events(const gstim_sampler *s) {
+    if (!s->interp_why.empty()) {
+        if (s->sparse && s->engine_pref != GSTIM_ENGINE_INTERPRETER) {
+            return true;
+        }
+        throw std::invalid_argument(s->interp_why);
+    }
     if (!s->sparse || s->engine_pref == GSTIM_ENGINE_INTERPRETER) {
         return false;
     }
@@ -1310,6 +1333,9 @@ int gstim_create_from_text(const char *circuit_text, size_t text_len, int mode, 
         CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
         configure(s.get());
         configure_event_engine(s.get());
+        if (!s->interp_why.empty() && !s->sparse) {
+            throw std::invalid_argument(s->interp_why + " Event engine: " + s->sparse_why + ".");
+        }
         *out = s.release();
     });
 }

@@ -58,6 +58,7 @@ struct ClassKey {
     uint64_t lam;
     uint32_t kind, n_out;
     uint32_t thr[15];
+    uint32_t chain_off[16];  // RK_CHAIN: noise group of element i minus that of element 0
     bool operator<(const ClassKey &o) const {
         if (lam != o.lam) {
             return lam < o.lam;
@@ -68,7 +69,11 @@ struct ClassKey {
         if (n_out != o.n_out) {
             return n_out < o.n_out;
         }
-        return memcmp(thr, o.thr, sizeof(thr)) < 0;
+        const int c = memcmp(thr, o.thr, sizeof(thr));
+        if (c != 0) {
+            return c < 0;
+        }
+        return memcmp(chain_off, o.chain_off, sizeof(chain_off)) < 0;
     }
 };
 
@@ -122,16 +127,12 @@ ResponseTable build_response_table(const LoweredCircuit &lc) {
         return rt;
     };
 
-    // ELSE_CORRELATED_ERROR makes sites dependent on each other (the "already occurred" row); not representable here.
     // Forward pass: index of every noise batch's first site inside its noise group.
     std::vector<uint32_t> gfirst(lc.batches.size(), 0);
     {
         std::map<uint32_t, uint32_t> seen;
         for (size_t b = 0; b < lc.batches.size(); b++) {
             const Batch &B = lc.batches[b];
-            if (B.op == GOP_CORR && !(B.flags & GF_RESET_FLAG) && B.lambda != 0) {
-                return fail("ELSE_CORRELATED_ERROR chain");
-            }
             if (B.op == GOP_NOISE1 || B.op == GOP_NOISE2) {
                 uint32_t &n = seen[B.site0];
                 gfirst[b] = n;
@@ -162,6 +163,66 @@ ResponseTable build_response_table(const LoweredCircuit &lc) {
             accs.back().rep_word.assign(rep, rep + k.n_out);
         }
         return accs[it->second];
+    };
+
+    // E / ELSE_CORRELATED_ERROR chain under construction (elements arrive last to first): "the first element whose coin
+    // comes up applies" (frame_simulator.inl:747-776) is ONE site with total rate sum(lambda_i) whose outcome i has
+    // probability p_i prod_{j<i} (1 - p_j) - the joint distribution of the reference's per-element coins.
+    struct ChainElem {
+        uint64_t lam;
+        uint32_t group;
+        Set response;
+    };
+    std::vector<ChainElem> chain;
+    bool chain_failed = false;
+    auto finish_chain = [&]() {
+        if (chain.empty()) {
+            return;
+        }
+        std::reverse(chain.begin(), chain.end());
+        if (chain.size() > 16) {
+            chain_failed = true;
+            chain.clear();
+            return;
+        }
+        ClassKey k{};
+        uint32_t rep[16];
+        const uint32_t no = (uint32_t)chain.size();
+        double survive = 1.0, cum = 0.0;
+        std::vector<double> cums;
+        unsigned __int128 lam_tot = 0;
+        for (uint32_t i = 0; i < no; i++) {
+            const double pi = chain[i].lam >= LAM_MAX ? 1.0 : -std::expm1(-std::ldexp((double)chain[i].lam, -56));
+            cum += pi * survive;
+            survive *= 1.0 - pi;
+            cums.push_back(cum);
+            lam_tot += chain[i].lam;
+            rep[i] = chain[i].group - chain[0].group;  // chain classes: group offset of the element (see response.h)
+        }
+        k.lam = lam_tot >= LAM_MAX ? LAM_MAX : (uint64_t)lam_tot;
+        k.n_out = no;
+        k.kind = no == 1 ? RK_SINGLE : RK_CHAIN;
+        for (uint32_t i = 0; i + 1 < no; i++) {
+            const double v = std::floor(cums[i] / cum * 4294967296.0);
+            k.thr[i] = v >= 4294967295.0 ? 0xFFFFFFFFu : v < 1.0 ? 1u : (uint32_t)v;
+            if (i > 0 && k.thr[i] <= k.thr[i - 1]) {
+                k.thr[i] = k.thr[i - 1] == 0xFFFFFFFFu ? 0xFFFFFFFFu : k.thr[i - 1] + 1;  // keep the bounds strictly ascending
+            }
+        }
+        if (no > 1) {
+            // the group offsets are part of the class identity (they tell the tests which instruction an outcome is)
+            for (uint32_t i = 0; i < no; i++) {
+                k.chain_off[i] = rep[i];
+            }
+        }
+        ClassAcc &c = get_class(k, rep);
+        for (uint32_t o = no; o-- > 0;) {
+            total_ids += chain[o].response.size();
+            c.responses.push_back(std::move(chain[o].response));
+        }
+        c.group.push_back(chain[0].group);
+        c.index.push_back(0);
+        chain.clear();
     };
 
     for (size_t bi = lc.batches.size(); bi-- > 0;) {
@@ -421,29 +482,22 @@ ResponseTable build_response_table(const LoweredCircuit &lc) {
                 break;
             }
             case GOP_CORR: {
-                if (B.lambda == 0) {
-                    break;
-                }
-                ClassKey k{};
-                k.lam = B.lambda;
-                k.kind = RK_SINGLE;
-                k.n_out = 1;
-                const uint32_t rep = 0;
-                ClassAcc &c = get_class(k, &rep);
-                acc.clear();
-                for (uint32_t i = 0; i < n; i++) {
-                    const uint32_t w = B.payload[i], q = w & 0xFFFFFF;
-                    if (w & ITEM_X) {
-                        xor_into(acc, SX[q], tmp);
+                if (B.lambda != 0) {
+                    acc.clear();
+                    for (uint32_t i = 0; i < n; i++) {
+                        const uint32_t w = B.payload[i], q = w & 0xFFFFFF;
+                        if (w & ITEM_X) {
+                            xor_into(acc, SX[q], tmp);
+                        }
+                        if (w & ITEM_Z) {
+                            xor_into(acc, SZ[q], tmp);
+                        }
                     }
-                    if (w & ITEM_Z) {
-                        xor_into(acc, SZ[q], tmp);
-                    }
+                    chain.push_back({B.lambda, B.site0, acc});
                 }
-                total_ids += acc.size();
-                c.responses.push_back(acc);
-                c.group.push_back(B.site0);
-                c.index.push_back(0);
+                if (B.flags & GF_RESET_FLAG) {
+                    finish_chain();  // CORRELATED_ERROR starts the chain that the ELSEs after it continued
+                }
                 break;
             }
             default:
@@ -454,6 +508,10 @@ ResponseTable build_response_table(const LoweredCircuit &lc) {
         }
     }
 
+    finish_chain();  // (ELSE_CORRELATED_ERRORs before any CORRELATED_ERROR)
+    if (chain_failed) {
+        return fail("ELSE_CORRELATED_ERROR chain with more than 16 elements");
+    }
     // assemble: classes in a deterministic order (rate, then chooser), sites in program order
     std::vector<size_t> order(accs.size());
     for (size_t i = 0; i < order.size(); i++) {

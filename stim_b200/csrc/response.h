@@ -17,9 +17,10 @@
 //   MEASURE (m = x, z <- random)  SX ^= SR[slot] (^ fused detector), SZ <- {} ; the random bit's own response is SZ_after
 //   XORROWS / OBS_PAULI / FEEDBACK add the destination's sensitivity to their sources
 //   NOISE / CORR                  snapshot: response(outcome) = XOR of the flipped components' sets
-// A circuit is ELIGIBLE when every collapse randomisation bit has an empty response (deterministic detectors: the usual
-// case for QEC circuits), it has no ELSE_CORRELATED_ERROR chain, and the table stays within bounds; otherwise the
-// interpreter (interp.cu) samples it.
+// Collapse randomisation bits that reach an output (non-deterministic detectors, measurement sampling) become sites
+// with p = 1/2; an E / ELSE_CORRELATED_ERROR chain becomes one site whose outcomes are its elements. A circuit is
+// ELIGIBLE unless a chain has more than 16 elements or the table would be too large; then the interpreter (interp.cu)
+// samples it.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -36,6 +37,8 @@ enum RespKind : uint32_t {
     RK_SINGLE = 0,   // one outcome
     RK_UNIFORM = 1,  // outcome = mulhi(v, n_out)            (DEPOLARIZE2: frame_simulator.inl:651-659)
     RK_THRESH = 2,   // outcome = number of thresholds <= v  (PAULI_CHANNEL_*, DEPOLARIZE1, HERALDED_*)
+    RK_CHAIN = 3,    // same chooser as RK_THRESH; the outcomes are the elements of an E / ELSE_CORRELATED_ERROR chain
+                     // (outcome i = noise group site_group + outcome_word[i] fired alone)
 };
 
 struct RespClass {

@@ -620,7 +620,7 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
         d.inv = c.inv;
         d.sh = c.sh;
         d.n_out = c.n_out;
-        d.kind = c.kind == RK_SINGLE ? DK_SINGLE : c.kind == RK_UNIFORM ? DK_UNIFORM : c.n_out <= 4 ? DK_THRESH3 : DK_THRESH_N;
+        d.kind = c.kind == RK_SINGLE ? DK_SINGLE : c.kind == RK_UNIFORM ? DK_UNIFORM : c.n_out <= 4 ? DK_THRESH3 : DK_THRESH_N;  // (RK_CHAIN: thresholds too)
         for (uint32_t j = 0; j < 3; j++) {  // registers of the chooser: threshold - 1 (pw > t <=> pw >= threshold), unused: never
             d.thr[j] = (d.kind == DK_THRESH3 && j + 1 < c.n_out) ? c.thr[j] - 1u : 0xFFFFFFFFu;
         }

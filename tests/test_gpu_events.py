@@ -13,7 +13,7 @@ from test_gpu_parity import ALL_OPS
 
 pytestmark = pytest.mark.gpu
 
-ALL_OPS_NO_ELSE = "\n".join(l for l in ALL_OPS.split("\n") if not l.startswith("ELSE_CORRELATED_ERROR"))
+LONG_CHAIN = "E(0.01) X0\n" + "".join(f"ELSE_CORRELATED_ERROR(0.01) X{k}\n" for k in range(1, 17)) + "M 0\nDETECTOR rec[-1]\n"
 
 
 def oracle_rows(s, seed, first_shot, shots, n_outputs):
@@ -49,14 +49,14 @@ def test_generated_detectors_match_oracle(code, task, d, r, p, shots):
 
 
 def test_every_instruction_detectors_match_oracle():
-    s, _ = check_detectors(ALL_OPS_NO_ELSE, 700, seed=2025)
+    s, _ = check_detectors(ALL_OPS, 700, seed=2025)
     info = s.engine_info()
     assert info["eligible"] == 1 and info["max_response"] >= 5 and info["overflow_words"] > 0
 
 
 def test_every_instruction_measurements_match_oracle():
     seed = 31
-    s = stim_b200.Circuit(ALL_OPS_NO_ELSE).compile_sampler(seed=seed, skip_reference_sample=True, engine="events")
+    s = stim_b200.Circuit(ALL_OPS).compile_sampler(seed=seed, skip_reference_sample=True, engine="events")
     M = int(s.stats.num_measurements)
     m = s.sample(600)
     assert s.engine_info()["last_engine"] == "events"
@@ -64,12 +64,12 @@ def test_every_instruction_measurements_match_oracle():
     # the reference sample is XORed in (rows start from it)
     ref = np.zeros(M, dtype=np.bool_)
     ref[::3] = True
-    s2 = stim_b200.Circuit(ALL_OPS_NO_ELSE).compile_sampler(seed=seed, reference_sample=ref, engine="events")
+    s2 = stim_b200.Circuit(ALL_OPS).compile_sampler(seed=seed, reference_sample=ref, engine="events")
     np.testing.assert_array_equal(s2.sample(600), m ^ ref[None, :])
 
 
-def test_else_chain_is_not_eligible():
-    s = stim_b200.Circuit(ALL_OPS).compile_detector_sampler(seed=1)
+def test_long_else_chain_is_not_eligible():
+    s = stim_b200.Circuit(LONG_CHAIN).compile_detector_sampler(seed=1)
     info = s.engine_info()
     assert info["eligible"] == 0 and "ELSE" in info["why_not"]
     with pytest.raises(ValueError):
@@ -154,3 +154,39 @@ def test_large_rows_use_small_tiles():
     assert s.engine_info()["eligible"] == 1
     out = s.sample(300, bit_packed=True, append_observables=True)
     assert not out.any()
+
+
+def test_d71_surface_code_beyond_the_interpreters_frame_limit():
+    """10 081 qubits: the frame of one 128-shot column (323 KB) no longer fits in shared memory, so the interpreter
+    refuses the circuit; the event engine needs no frame at all. 45 KB of detection events per shot -> one-shot tiles.
+    Checked against 2^13 shots of the reference CLI (rates of the busiest detectors and the mean detection fraction)."""
+    import os
+    import subprocess
+
+    from conftest import REF_STIM, have_ref
+
+    if not have_ref():
+        pytest.skip("oracle/_ref/stim not built")
+    text = gen_circuit("surface_code", "rotated_memory_z", 71, 9, 0.001)
+    circ = stim_b200.Circuit(text)
+    s = circ.compile_detector_sampler(seed=71)
+    info = s.engine_info()
+    assert info["eligible"] == 1 and info["tile_shots"] <= 4
+    with pytest.raises(ValueError):
+        circ.compile_detector_sampler(seed=71, engine="interp").sample(1)
+    shots = 1 << 15
+    D = int(s.stats.num_detectors)
+    got = s.sample(shots, bit_packed=True)
+    assert s.engine_info()["last_engine"] == "events"
+    n_ref = 1 << 13
+    r = subprocess.run([REF_STIM, "detect", "--shots", str(n_ref), "--out_format", "b8", "--seed", "5"], input=text.encode(),
+                       capture_output=True, check=True)
+    ref = np.frombuffer(r.stdout, dtype=np.uint8).reshape(n_ref, (D + 7) // 8)
+    k_gpu = np.unpackbits(got, axis=1, bitorder="little")[:, :D].sum(axis=0, dtype=np.int64)
+    k_ref = np.unpackbits(ref, axis=1, bitorder="little")[:, :D].sum(axis=0, dtype=np.int64)
+    p = (k_gpu + k_ref) / (shots + n_ref)
+    z = (k_gpu / shots - k_ref / n_ref) / np.sqrt(np.maximum(p * (1 - p), 1e-12) * (1 / shots + 1 / n_ref))
+    busy = (k_gpu + k_ref) > 200
+    assert busy.sum() > 1000 and np.abs(z[busy]).max() < 6.0
+    assert abs(np.sqrt(np.mean(z[busy] ** 2)) - 1.0) < 0.1
+    assert abs(k_gpu.sum() / shots - k_ref.sum() / n_ref) < 0.01 * k_ref.sum() / n_ref

@@ -11,7 +11,7 @@ from conftest import ROOT, gen_circuit
 from oracle import sparse_oracle as so
 from test_gpu_parity import ALL_OPS
 
-ALL_OPS_NO_ELSE = "\n".join(l for l in ALL_OPS.split("\n") if not l.startswith("ELSE_CORRELATED_ERROR"))
+LONG_CHAIN = "E(0.01) X0\n" + "".join(f"ELSE_CORRELATED_ERROR(0.01) X{k}\n" for k in range(1, 17)) + "M 0\nDETECTOR rec[-1]\n"
 
 
 def check_table(text, mode="detectors", entries=None):
@@ -26,7 +26,8 @@ def check_table(text, mode="detectors", entries=None):
 
 @pytest.mark.parametrize("mode", ["detectors", "measurements"])
 def test_every_instruction_matches_forward_injection(mode):
-    t = check_table(ALL_OPS_NO_ELSE, mode)
+    t = check_table(ALL_OPS, mode)
+    assert (t["classes"][:, 4] == 3).any()  # the E / ELSE_CORRELATED_ERROR chain is one categorical site
     assert t["info"]["overflow_words"] > 0  # responses longer than four bits go through the overflow list
     if mode == "measurements":
         assert (t["site_group"] & 0x80000000).any()  # collapse randomisation that reaches an output is a p = 1/2 site
@@ -92,8 +93,18 @@ def test_headline_circuit_table():
         assert so.entry_ids(t, e) == ids, e
 
 
-def test_else_chain_is_reported_as_not_eligible():
-    t = stim_b200.response_table(ALL_OPS)
+def test_else_chains():
+    """A chain is one site with outcome probabilities p_i prod_{j<i} (1 - p_j); more than 16 elements are not eligible."""
+    text = "E(0.25) X0\nELSE_CORRELATED_ERROR(0.5) X1\nELSE_CORRELATED_ERROR(1) X2\nM 0 1 2\nDETECTOR rec[-3]\nDETECTOR rec[-2]\nDETECTOR rec[-1]\n"
+    t = check_table(text)
+    c = t["classes"][0]
+    assert len(t["classes"]) == 1 and c[4] == 3 and c[5] == 3 and c[2] == 0  # always fires (the last element has p = 1)
+    assert abs(int(c[6]) / 2**32 - 0.25) < 1e-6 and abs(int(c[7]) / 2**32 - 0.625) < 1e-6
+    slices = np.array([[0, 128, int(c[22]), 0]], dtype=np.uint32)
+    out = so.sample(t, slices, 128, seed=3, first_shot=0, n_shots=1 << 13, n_outputs=3)
+    assert (out.sum(axis=1) == 1).all()  # exactly one element applies in every shot
+    assert np.abs(out.mean(axis=0) - [0.25, 0.375, 0.375]).max() < 0.02
+    t = stim_b200.response_table(LONG_CHAIN)
     assert t["info"]["eligible"] == 0 and "ELSE_CORRELATED_ERROR" in t["info"]["why_not"]
 
 

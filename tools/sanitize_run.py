@@ -11,9 +11,8 @@ import numpy as np
 import stim_b200
 from test_gpu_parity import ALL_OPS
 
-no_else = "\n".join(l for l in ALL_OPS.split("\n") if not l.startswith("ELSE_CORRELATED_ERROR"))
 d3 = open(os.path.join(ROOT, "tests", "golden", "circuits", "c2_surface_x_d5_r5.stim")).read()
-for name, text in (("all_ops", ALL_OPS), ("all_ops_no_else", no_else), ("surface_d5", d3)):
+for name, text in (("all_ops", ALL_OPS), ("surface_d5", d3)):
     for engine in ("interp", "events"):
         try:
             s = stim_b200.Circuit(text).compile_detector_sampler(seed=5, engine=engine)
