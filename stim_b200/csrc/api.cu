@@ -371,10 +371,16 @@ void configure_event_engine(gstim_sampler *s) {
         s->sparse_why = rt.why_not;
         return;
     }
-    // Cost model (profiles/r2_notes.md): an event costs ~2.2 SM-cycles plus ~0.3 per flipped bit; the interpreter
-    // costs ~0.009 SM-cycles per lowered item and shot.
+    // Cost model in SM-cycles per shot (profiles/r2_notes.md): the event engine pays ~2.2 per event plus ~0.3 per flipped
+    // bit; the interpreter ~0.009 per lowered item plus ~6 per noise event (its event application). Long responses
+    // (measurement sampling with many live collapse bits) are what makes the interpreter the better choice.
+    double noise_events = 0;
+    for (size_t i = 0; i < s->lc.noise.n_sites.size(); i++) {
+        const double lam = std::ldexp((double)s->lc.noise.lams[i], -56);
+        noise_events += (double)s->lc.noise.n_sites[i] * (s->lc.noise.lams[i] >= (1ull << 62) ? 1.0 : -std::expm1(-lam));
+    }
     const double ev_cost = rt.events_per_shot * 2.2 + rt.flips_per_shot * 0.3;
-    const double interp_cost = (double)s->lc.total_items * 0.009;
+    const double interp_cost = (double)s->lc.total_items * 0.009 + noise_events * 6.0;
     const bool favoured = ev_cost < interp_cost;
     try {
         s->sparse = std::make_unique<SparseEngine>(
