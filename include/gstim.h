@@ -284,6 +284,24 @@ void gstim_response_table_destroy(gstim_response_table *t);
 int gstim_response_table_info(const gstim_response_table *t, gstim_engine_info *out);
 int gstim_response_table_get(const gstim_response_table *t, int what, uint32_t *words, size_t *n_words);
 
+/* ---- measurements -> detection events ----------------------------------------------------
+ * Replaces: measurements_to_detection_events_helper<W>          src/stim/simulators/measurements_to_detection_events.inl:30-131
+ *           stim m2d (stream_measurements_to_detection_events)   src/stim/simulators/measurements_to_detection_events.inl:147-330
+ *           stim.CompiledMeasurementsToDetectionEventsConverter.convert
+ *                                                                src/stim/simulators/measurements_to_detection_events.pybind.cc:78-137
+ * The circuit's noise is ignored (the reference converts with circuit.aliased_noiseless_circuit()). With
+ * skip_reference_sample = 0 the noiseless reference sample (host stabilizer simulation) decides which detectors are
+ * inverted. All rows are shot-major, bit-packed little-endian, in HOST memory; strides in bytes (0 = dense):
+ * measurements [shots][ceil(M/8)], sweep_bits [shots][ceil(S/8)] or NULL (all zero), dets_out [shots][ceil(n/8)] with
+ * n = D (+ L with GSTIM_APPEND_OBS), obs_out [shots][ceil(L/8)] or NULL (GSTIM_SEPARATE_OBS). */
+typedef struct gstim_m2d gstim_m2d;
+int gstim_m2d_create_from_text(const char *circuit_text, size_t text_len, int skip_reference_sample, int device, gstim_m2d **out);
+void gstim_m2d_destroy(gstim_m2d *h);
+int gstim_m2d_get_sizes(const gstim_m2d *h, uint64_t *num_measurements, uint64_t *num_detectors, uint64_t *num_observables,
+                        uint64_t *num_sweep_bits);
+int gstim_m2d_convert(gstim_m2d *h, uint64_t shots, uint32_t flags, const void *measurements, int64_t meas_stride, const void *sweep_bits,
+                      int64_t sweep_stride, void *dets_out, int64_t dets_stride, void *obs_out, int64_t obs_stride);
+
 /* Pins the number of 128-shot columns per thread block (0 = choose per call from the shot count, the default). The
  * random stream is a function of (seed, shot offset, columns per block): callers that split one global shot range over
  * several handles / GPUs and need the union to equal a single-handle run pin the same value everywhere and keep every

@@ -225,6 +225,14 @@ class FrameOracle:
         self.mgroup = 0  # measure group counter (Philox counter word 0 of collapse draws)
 
     NOISE_SLICE = 32  # GSTIM_NOISE_SLICE (program.h)
+    sweep_rows = None  # see sweep_row
+    randomize = True   # False: m2d's frame simulator (see measure)
+
+    def sweep_row(self, k):
+        """Row of sweep bit k over the shots, or None when there is no sweep table (sampling)."""
+        if self.sweep_rows is None:
+            return None
+        return self.sweep_rows.get(k, np.zeros(self.W, dtype=np.uint32))
 
     # -- randomness ---------------------------------------------------------------------------
     def collapse_words(self, mgroup, q):
@@ -295,8 +303,26 @@ class FrameOracle:
 
     def measure(self, basis, kind, q, mgroup):
         """M/MX/MY :173-208, R/RX/RY :211-219,255-274, MR/MRX/MRY :277-317 (one target)."""
-        rnd = self.collapse_words(mgroup, q)
         x, z = self.x[q], self.z[q]
+        if not self.randomize:
+            # guarantee_anticommutation_via_frame_randomization = false (m2d): the conjugate component is KEPT where the
+            # sampler would replace it by fresh random bits (the `if (guarantee...)` branches of :173-317)
+            if basis == "Z":
+                m = x.copy()
+                if kind != "M":
+                    x[:] = 0
+            elif basis == "X":
+                m = z.copy()
+                if kind != "M":
+                    z[:] = 0
+            else:
+                m = x ^ z
+                if kind != "M":
+                    x[:] = z
+            if kind != "R":
+                self.rec.append(m)
+            return
+        rnd = self.collapse_words(mgroup, q)
         if basis == "Z":
             m = x.copy()
             if kind != "M":
@@ -380,8 +406,13 @@ class FrameOracle:
                 return
             bit, qt, comps = (ta, tb, "z") if a_bit else (tb, ta, "z")
         if bit & T_SWEEP:
-            return
-        r = self.rec_at(bit & T_VAL, name)
+            # no sweep data when sampling (frame_simulator.inl:146-148: the sweep table is empty); the measurement
+            # converter (oracle/m2d_oracle.py) supplies one: sweep_rows[k] = uint32[W] row of sweep bit k
+            r = self.sweep_row(bit & T_VAL)
+            if r is None:
+                return
+        else:
+            r = self.rec_at(bit & T_VAL, name)
         q = self.qmap[qt & T_VAL]
         if "x" in comps:
             self.x[q] ^= r
@@ -490,6 +521,9 @@ class FrameOracle:
                     self.cliff2("CX", q, focus)
                 for b in bits:
                     if b & T_SWEEP:
+                        r = self.sweep_row(b & T_VAL)
+                        if r is not None:
+                            self.x[focus] ^= r
                         continue
                     self.x[focus] ^= self.rec_at(b & T_VAL, name)
 

@@ -23,7 +23,7 @@ from ._native import GstimCudaError, GstimStats
 from .dem import CompiledDemSampler, DetectorErrorModel  # noqa: E402,F401
 
 __all__ = ["Circuit", "CompiledDetectorSampler", "CompiledMeasurementSampler", "GstimCudaError", "measure_lop3_peak", "response_table",
-           "DetectorErrorModel", "CompiledDemSampler"]
+           "DetectorErrorModel", "CompiledDemSampler", "CompiledMeasurementsToDetectionEventsConverter"]
 
 
 def measure_lop3_peak(device: int = 0) -> dict:
@@ -94,6 +94,9 @@ class Circuit:
     def compile_detector_sampler(self, *, seed=None, device: int = 0, engine: str = "auto") -> "CompiledDetectorSampler":
         """`engine` (not in the reference): "auto" | "interp" | "events" — include/gstim.h "sampling engines"."""
         return CompiledDetectorSampler(self, seed=seed, device=device, engine=engine)
+
+    def compile_m2d_converter(self, *, skip_reference_sample: bool = False, device: int = 0) -> "CompiledMeasurementsToDetectionEventsConverter":
+        return CompiledMeasurementsToDetectionEventsConverter(self, skip_reference_sample=skip_reference_sample, device=device)
 
     def compile_sampler(self, *, skip_reference_sample: bool = False, seed=None, reference_sample=None,
                         device: int = 0, engine: str = "auto") -> "CompiledMeasurementSampler":
@@ -478,3 +481,74 @@ class CompiledMeasurementSampler(_Sampler):
 
     def __repr__(self) -> str:
         return f"stim_b200.CompiledMeasurementSampler({self._circuit!r})"
+
+
+class CompiledMeasurementsToDetectionEventsConverter:
+    """Mirror of stim.CompiledMeasurementsToDetectionEventsConverter
+    (/root/reference/src/stim/simulators/measurements_to_detection_events.pybind.cc:78-137) on gstim_m2d_convert."""
+
+    def __init__(self, circuit: Circuit, *, skip_reference_sample: bool = False, device: int = 0):
+        if isinstance(circuit, str):
+            circuit = Circuit(circuit)
+        self._circuit = circuit
+        self._skip = bool(skip_reference_sample)
+        self._handle = ctypes.c_void_p()
+        data = str(circuit).encode("utf-8")
+        _native.check(_native.lib().gstim_m2d_create_from_text(data, len(data), int(self._skip), int(device), ctypes.byref(self._handle)))
+        v = [ctypes.c_uint64(0) for _ in range(4)]
+        _native.check(_native.lib().gstim_m2d_get_sizes(self._handle, *[ctypes.byref(x) for x in v]))
+        self.num_measurements, self.num_detectors, self.num_observables, self.num_sweep_bits = [int(x.value) for x in v]
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value and _native is not None:
+            _native.lib().gstim_m2d_destroy(h)
+            self._handle = ctypes.c_void_p()
+
+    @staticmethod
+    def _packed_rows(a, n_bits: int, what: str):
+        """bool_[shots, n_bits] or uint8[shots, ceil(n_bits / 8)] -> (packed C-contiguous uint8 rows, shots), like
+        numpy_array_to_transposed_simd_table (/root/reference/src/stim/py/numpy.pybind.cc)."""
+        a = np.asarray(a)
+        if a.ndim != 2:
+            raise ValueError(f"{what} must be a 2-dimensional numpy array.")
+        if a.dtype == np.bool_:
+            if a.shape[1] != n_bits:
+                raise ValueError(f"{what}.dtype == bool_ but {what}.shape[1] != {n_bits}")
+            return np.ascontiguousarray(np.packbits(a, axis=1, bitorder="little")) if n_bits else np.zeros((a.shape[0], 0), np.uint8), a.shape[0]
+        if a.dtype == np.uint8:
+            if a.shape[1] != (n_bits + 7) // 8:
+                raise ValueError(f"{what}.dtype == uint8 but {what}.shape[1] != ceil({n_bits} / 8)")
+            return np.ascontiguousarray(a), a.shape[0]
+        raise ValueError(f"{what} must have dtype bool_ or uint8.")
+
+    def convert(self, *, measurements, sweep_bits=None, separate_observables=None, append_observables=None,
+                bit_packed: bool = False, bit_pack_result: bool = False):
+        bit_packed = bool(bit_packed or bit_pack_result)
+        if separate_observables is None and append_observables is None:
+            raise ValueError(
+                "To ignore observable flip data, you must explicitly specify either separate_observables=False or "
+                "append_observables=False.")
+        separate, append = bool(separate_observables), bool(append_observables)
+        meas, shots = self._packed_rows(measurements, self.num_measurements, "measurements")
+        sweep = None
+        if sweep_bits is not None:
+            sweep, n2 = self._packed_rows(sweep_bits, self.num_sweep_bits, "sweep_bits")
+            if n2 != shots:
+                raise ValueError("Need sweep_bits.shape[0] == measurements.shape[0]")
+        D, L = self.num_detectors, self.num_observables
+        n_main = D + (L if append else 0)
+        dets = np.zeros((shots, (n_main + 7) // 8), dtype=np.uint8)
+        obs = np.zeros((shots, (L + 7) // 8), dtype=np.uint8) if separate else None
+        flags = _native.BIT_PACKED | (_native.APPEND_OBS if append else 0) | (_native.SEPARATE_OBS if separate else 0)
+        _native.check(_native.lib().gstim_m2d_convert(
+            self._handle, shots, flags, _ptr(meas), _stride(meas), _ptr(sweep), _stride(sweep), _ptr(dets), _stride(dets),
+            _ptr(obs), _stride(obs)))
+        if not bit_packed:
+            dets = np.unpackbits(dets, axis=1, bitorder="little", count=n_main).astype(np.bool_) if n_main else np.zeros((shots, 0), np.bool_)
+            if separate:
+                obs = np.unpackbits(obs, axis=1, bitorder="little", count=L).astype(np.bool_) if L else np.zeros((shots, 0), np.bool_)
+        return (dets, obs) if separate else dets
+
+    def __repr__(self) -> str:
+        return f"stim_b200.CompiledMeasurementsToDetectionEventsConverter({self._circuit!r}, skip_reference_sample={self._skip})"

@@ -117,6 +117,12 @@ _SIGNATURES = [
     ("gstim_response_table_destroy", None, [_P]),
     ("gstim_response_table_info", ctypes.c_int, [_P, ctypes.POINTER(GstimEngineInfo)]),
     ("gstim_response_table_get", ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_size_t)]),
+    ("gstim_m2d_create_from_text", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_P)]),
+    ("gstim_m2d_destroy", None, [_P]),
+    ("gstim_m2d_get_sizes", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
+                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    ("gstim_m2d_convert", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_uint32, _P, ctypes.c_int64, _P, ctypes.c_int64, _P, ctypes.c_int64,
+                                         _P, ctypes.c_int64]),
     ("gstim_set_block_columns", ctypes.c_int, [_P, ctypes.c_uint32]),
     ("gstim_measure_lop3_peak", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                                ctypes.POINTER(ctypes.c_double)]),

@@ -145,8 +145,8 @@ const GateInfo GATES[] = {
     {"RY", GateCat::MEASURE, meas(GB_Y, GK_R), 0, TR_QUBITS, false},
     {"MPAD", GateCat::MPAD, 0, ARGS_ZERO_OR_ONE, TR_MPAD, true},
     {"MPP", GateCat::MPP, 0, ARGS_ZERO_OR_ONE, TR_PRODUCTS, true},
-    {"SPP", GateCat::SPP, 0, 0, TR_PRODUCTS_BITS, false},
-    {"SPP_DAG", GateCat::SPP, 0, 0, TR_PRODUCTS_BITS, false},
+    {"SPP", GateCat::SPP, 0, 0, TR_PRODUCTS, false},
+    {"SPP_DAG", GateCat::SPP, 0, 0, TR_PRODUCTS, false},
     {"MXX", GateCat::MPAIR, GB_X, ARGS_ZERO_OR_ONE, TR_PAIRS_INV, true},
     {"MYY", GateCat::MPAIR, GB_Y, ARGS_ZERO_OR_ONE, TR_PAIRS_INV, true},
     {"MZZ", GateCat::MPAIR, GB_Z, ARGS_ZERO_OR_ONE, TR_PAIRS_INV, true},

@@ -498,6 +498,14 @@ struct Lowerer {
             }
         }
     }
+    bool with_sweep = false;
+    void sweep(uint32_t sweep_index, uint32_t q, uint32_t comps) {
+        Key k;
+        k.op = GOP_SWEEP;
+        uint32_t w[2] = {sweep_index, q | comps};
+        uint32_t r = q | RES_WRITE;
+        add(k, w, 2, &r, 1, false, 0, false, 0, false, 0);
+    }
     void rec_zero(uint64_t rec_index) {
         Key k;
         k.op = GOP_RECZERO;
@@ -578,6 +586,9 @@ struct Lowerer {
             comps = ITEM_Z;
         }
         if (bit & T_SWEEP) {
+            if (with_sweep) {
+                sweep(bit & T_VALUE_MASK, q_of(qt), comps);
+            }
             return;  // no sweep data when sampling (frame_simulator.inl:146-148)
         }
         feedback(rec_abs(bit, g.name), q_of(qt), comps);
@@ -771,6 +782,9 @@ struct Lowerer {
                 }
                 for (uint32_t b : p.bits) {
                     if (b & T_SWEEP) {
+                        if (with_sweep) {
+                            sweep(b & T_VALUE_MASK, focus, ITEM_X);
+                        }
                         continue;
                     }
                     feedback(rec_abs(b, op.gate->name), focus, ITEM_X);
@@ -952,6 +966,9 @@ struct Lowerer {
             for (uint32_t t : op.targets) {
                 recs.push_back(rec_abs(t, "DETECTOR"));
             }
+            if (with_sweep) {
+                lc.out_recs[det] = recs;
+            }
             xor_rows((uint32_t)det, recs, false);
         } else {
             for (uint32_t t : op.targets) {
@@ -971,6 +988,9 @@ struct Lowerer {
         }
         if (lc.mode != 0) {
             return;
+        }
+        if (with_sweep) {
+            lc.out_recs[row].insert(lc.out_recs[row].end(), recs.begin(), recs.end());
         }
         if (!recs.empty()) {
             xor_rows(row, recs, true);
@@ -1144,6 +1164,7 @@ void assign_physical_rows(LoweredCircuit &lc) {
                 break;
             case GOP_OBS_PAULI:
             case GOP_FEEDBACK:
+            case GOP_SWEEP:
                 for (size_t i = 1; i < b.payload.size(); i += 2) {
                     b.payload[i] = lo24(b.payload[i]);
                 }
@@ -1270,8 +1291,9 @@ void spread_banks(Batch &b) {
 
 }  // namespace
 
-LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words) {
+LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words, bool with_sweep) {
     Lowerer lw(max_batch_words);
+    lw.with_sweep = with_sweep;
     LoweredCircuit &lc = lw.lc;
     lc.mode = mode;
     lc.stats = compute_stats(c);
@@ -1338,6 +1360,9 @@ LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch
     lw.rd_stamp.assign(lc.num_resources, 0);
     lw.wr_stamp.assign(lc.num_resources, 0);
 
+    if (with_sweep) {
+        lc.out_recs.assign(lc.stats.num_detectors + lc.stats.num_observables, {});
+    }
     // Start of every shot: x <- 0, z <- random for all qubits (frame_simulator.inl:153-163).
     // Measure group 0 is reserved for this.
     {

@@ -56,13 +56,19 @@ struct LoweredCircuit {
     uint32_t max_items = 0;
     uint64_t total_items = 0;
     uint64_t num_sites = 0, num_csites = 0;
+    // with_sweep lowering only (m2d.cu): absolute measurement indices XORed into every detector / observable (output id
+    // d, or D + l), with multiplicity
+    std::vector<std::vector<uint64_t>> out_recs;
 };
 
 // Probability -> rate key of the detector-error-model sampler's gap arithmetic (dem.cu): bit 63 = valid, (INV << 8) | SH.
 uint64_t gstim_rate_key(double p);
 
 // Pass 1: semantics. Throws std::invalid_argument / std::out_of_range like the reference would.
-LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words);
+// with_sweep: sweep-controlled Paulis become GOP_SWEEP batches (instead of being dropped: there is no sweep data when
+// sampling, frame_simulator.inl:146-148) and out_recs is filled; such a lowering is for response.cc / m2d.cu only and must
+// not be serialised for the interpreter.
+LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words, bool with_sweep = false);
 
 // Pass 2: hazard analysis for `slots` concurrent thread groups + serialisation into chunks.
 std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint32_t chunk_words, GstimPlan *plan);

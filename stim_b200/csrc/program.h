@@ -35,6 +35,7 @@ enum GstimOp : uint32_t {
     GOP_FEEDBACK = 10,   // frame ^= record row. payload per item: rec index, qubit | x<<30 | z<<31
     GOP_CORR = 11,       // E / ELSE_CORRELATED_ERROR: one site, payload = Pauli targets qubit | x<<30 | z<<31
     GOP_QMAP = 12,       // not executed: payload[i] = logical index of physical frame row GH_EXTRA + i
+    GOP_SWEEP = 13,      // never serialised (m2d lowering only): frame ^= sweep bit. payload per item: sweep index, qubit | x<<30 | z<<31
 };
 
 // header word indices

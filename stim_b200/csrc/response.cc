@@ -108,7 +108,7 @@ bool gap_params(uint64_t lam, uint32_t *inv, uint32_t *sh) {
 
 }  // namespace
 
-ResponseTable build_response_table(const LoweredCircuit &lc) {
+ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate) {
     ResponseTable rt;
     const uint32_t D = (uint32_t)lc.stats.num_detectors, L = (uint32_t)lc.stats.num_observables;
     const uint32_t M = (uint32_t)lc.stats.num_measurements;
@@ -124,6 +124,7 @@ ResponseTable build_response_table(const LoweredCircuit &lc) {
         rt.classes.clear();
         rt.entries.clear();
         rt.overflow.clear();
+        rt.sweep_responses.clear();
         return rt;
     };
 
@@ -298,6 +299,27 @@ ResponseTable build_response_table(const LoweredCircuit &lc) {
                         xor_into(sm, SR[slot], tmp);
                         SR[slot].clear();
                     }
+                    if (keep_conjugate) {
+                        if (basis == GB_Z) {  // m = x; x kept or cleared; z kept
+                            if (kind != GK_M) {
+                                SX[q].clear();
+                            }
+                            xor_into(SX[q], sm, tmp);
+                        } else if (basis == GB_X) {
+                            if (kind != GK_M) {
+                                SZ[q].clear();
+                            }
+                            xor_into(SZ[q], sm, tmp);
+                        } else if (kind == GK_M) {  // m = x ^ z, frame unchanged
+                            xor_into(SX[q], sm, tmp);
+                            xor_into(SZ[q], sm, tmp);
+                        } else {  // m = x ^ z; x <- z, z kept
+                            xor_into(SZ[q], SX[q], tmp);
+                            xor_into(SZ[q], sm, tmp);
+                            SX[q] = sm;
+                        }
+                        continue;
+                    }
                     Set rr;  // response of the collapse randomisation bit
                     if (basis == GB_Z) {
                         rr.swap(SZ[q]);
@@ -376,6 +398,20 @@ ResponseTable build_response_table(const LoweredCircuit &lc) {
                     }
                     if (wq & ITEM_Z) {
                         xor_into(SR[ri], SZ[q], tmp);
+                    }
+                }
+                break;
+            case GOP_SWEEP:
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t k = B.payload[2 * i], wq = B.payload[2 * i + 1], q = wq & 0xFFFFFF;
+                    if (rt.sweep_responses.size() <= k) {
+                        rt.sweep_responses.resize(k + 1);
+                    }
+                    if (wq & ITEM_X) {
+                        xor_into(rt.sweep_responses[k], SX[q], tmp);
+                    }
+                    if (wq & ITEM_Z) {
+                        xor_into(rt.sweep_responses[k], SZ[q], tmp);
                     }
                 }
                 break;

@@ -63,6 +63,8 @@ struct ResponseTable {
     std::vector<uint32_t> site_index;  // index of the site inside its group
     // outcome -> representative Pauli word v of the interpreter's chooser, per class (n_out values each), for the same tests
     std::vector<uint32_t> outcome_word;
+    // with_sweep lowerings: output ids flipped by sweep bit k (XOR over every Pauli it controls), for m2d.cu
+    std::vector<std::vector<uint32_t>> sweep_responses;
     uint64_t n_sites = 0, n_entries = 0;
     uint32_t max_response = 0;       // largest number of output bits of one entry
     double events_per_shot = 0;      // expected number of events per shot
@@ -70,6 +72,9 @@ struct ResponseTable {
 };
 
 // Builds the table from the lowered batches (before or after serialisation; only lc.batches / lc.mode / lc.rec_ring are read).
-ResponseTable build_response_table(const LoweredCircuit &lc);
+// keep_conjugate: the frame simulator of the measurement converter (m2d.cu) runs with frame randomisation off, where a
+// measurement / reset KEEPS the conjugate frame component instead of replacing it by random bits (the `if
+// (guarantee_anticommutation_via_frame_randomization)` branches of frame_simulator.inl:173-317); no collapse sites then.
+ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate = false);
 
 }  // namespace gstim
