@@ -114,6 +114,13 @@ int gstim_lower_text(
 int gstim_create_from_text(
     const char *circuit_text, size_t text_len, int mode, uint64_t seed, int device, gstim_sampler **out);
 
+/* Same, on several CUDA devices of this process ("devices[], n_devices"). The host-output calls
+ * (gstim_sample_detectors, gstim_sample_measurements) cut their shots into one contiguous range per device, sample the
+ * ranges concurrently and fill the caller's arrays; there is no inter-GPU traffic. With the event engine the result equals
+ * a single-device call bit for bit. Every other call acts on devices[0]. */
+int gstim_create_from_text_multi(
+    const char *circuit_text, size_t text_len, int mode, uint64_t seed, const int *devices, int n_devices, gstim_sampler **out);
+
 void gstim_destroy(gstim_sampler *s);
 
 int gstim_get_stats(const gstim_sampler *s, gstim_stats *out);

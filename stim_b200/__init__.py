@@ -152,8 +152,14 @@ class _Sampler:
         self._circuit = circuit
         self._handle = ctypes.c_void_p()
         data = str(circuit).encode("utf-8")
-        _native.check(_native.lib().gstim_create_from_text(
-            data, len(data), mode, ctypes.c_uint64(_seed_to_u64(seed)), int(device), ctypes.byref(self._handle)))
+        if isinstance(device, (list, tuple)):
+            # several GPUs of this process: host-output sample() calls shard their shots over them (gstim_create_from_text_multi)
+            devs = (ctypes.c_int * len(device))(*[int(d) for d in device])
+            _native.check(_native.lib().gstim_create_from_text_multi(
+                data, len(data), mode, ctypes.c_uint64(_seed_to_u64(seed)), devs, len(device), ctypes.byref(self._handle)))
+        else:
+            _native.check(_native.lib().gstim_create_from_text(
+                data, len(data), mode, ctypes.c_uint64(_seed_to_u64(seed)), int(device), ctypes.byref(self._handle)))
         st = GstimStats()
         _native.check(_native.lib().gstim_get_stats(self._handle, ctypes.byref(st)))
         self.stats = st

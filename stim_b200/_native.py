@@ -84,6 +84,8 @@ _SIGNATURES = [
                                         _P, ctypes.POINTER(ctypes.c_size_t), _P]),
     ("gstim_create_from_text", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, ctypes.c_int,
                                               ctypes.POINTER(_P)]),
+    ("gstim_create_from_text_multi", ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64,
+                                                    ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(_P)]),
     ("gstim_destroy", None, [_P]),
     ("gstim_get_stats", ctypes.c_int, [_P, ctypes.POINTER(GstimStats)]),
     ("gstim_get_program", ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_size_t)]),

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <exception>
 #include <string>
 #include <thread>
 #include <vector>
@@ -147,6 +148,10 @@ struct gstim_sampler {
     int last_engine = GSTIM_ENGINE_INTERPRETER;
     bool sparse_favoured = false;  // the cost model's choice for GSTIM_ENGINE_AUTO
 
+    // multi-device sampler (gstim_create_from_text_multi): samplers of the other devices; host-output calls split their
+    // shots over all of them
+    std::vector<gstim_sampler *> peers;
+
     uint64_t last_launches = 0;
     uint32_t last_K = 0;
     uint32_t K_fixed = 0;  // gstim_set_block_columns: 0 = chosen per call from the shot count
@@ -154,6 +159,11 @@ struct gstim_sampler {
     cudaEvent_t call_start = nullptr, call_end = nullptr;
 
     ~gstim_sampler() {
+        for (gstim_sampler *p : peers) {
+            cudaSetDevice(p->device);
+            delete p;
+        }
+        cudaSetDevice(device);
         for (auto e : events) {
             cudaEventDestroy(e);
         }
@@ -958,6 +968,61 @@ void sample_to_host(
     drain(cur ^ 1);
 }
 
+// Host-output sampling of a multi-device sampler: the shots are cut into one contiguous range per device (multiples of
+// 128 shots, the remainder to the last), every device samples its range of the SAME global shot index space on its own
+// thread and writes its rows of the caller's arrays. With the event engine the stream is a function of (seed, global shot
+// index) only, so the result is identical to a single-device call (shots shard with no inter-GPU traffic).
+template <typename MAPS>
+void sample_to_host_multi(
+    gstim_sampler *s, uint64_t shots, MAPS &&maps_of, uint32_t layout_flags, bool bit_packed, uint8_t *main_out, int64_t main_stride,
+    uint8_t *obs_out, int64_t obs_stride) {
+    std::vector<gstim_sampler *> all{s};
+    all.insert(all.end(), s->peers.begin(), s->peers.end());
+    const uint64_t cols = (shots + GSTIM_COL_SHOTS - 1) / GSTIM_COL_SHOTS;
+    const uint64_t per = cols / all.size();
+    const uint64_t base_col = s->next_col;
+    std::vector<std::exception_ptr> errors(all.size());
+    std::vector<std::thread> threads;
+    uint64_t launches = 0;
+    for (size_t i = 0; i < all.size(); i++) {
+        const uint64_t c0 = per * i, c1 = i + 1 == all.size() ? cols : per * (i + 1);
+        const uint64_t first = c0 * GSTIM_COL_SHOTS, last = std::min<uint64_t>(c1 * GSTIM_COL_SHOTS, shots);
+        if (last <= first) {
+            continue;
+        }
+        threads.emplace_back([&, i, first, last, c0] {
+            try {
+                gstim_sampler *d = all[i];
+                d->next_col = base_col + c0;
+                d->engine_pref = s->engine_pref;
+                d->ref_bits = s->ref_bits;
+                RowMaps maps = maps_of(d);
+                const uint64_t main_row = bit_packed ? (maps.main.size() + 7) / 8 : maps.main.size();
+                const uint64_t obs_row = bit_packed ? (maps.obs.size() + 7) / 8 : maps.obs.size();
+                const uint64_t mp = main_stride ? (uint64_t)main_stride : main_row, op = obs_stride ? (uint64_t)obs_stride : obs_row;
+                sample_to_host(d, last - first, maps, layout_flags, bit_packed, main_out ? main_out + first * mp : nullptr, (int64_t)mp,
+                               obs_out ? obs_out + first * op : nullptr, (int64_t)op);
+            } catch (...) {
+                errors[i] = std::current_exception();
+            }
+        });
+    }
+    for (auto &t : threads) {
+        t.join();
+    }
+    for (auto &e : errors) {
+        if (e) {
+            std::rethrow_exception(e);
+        }
+    }
+    for (gstim_sampler *d : all) {
+        launches += d->last_launches;
+    }
+    s->last_launches = launches;
+    s->next_col = base_col + cols;
+    CK(cudaSetDevice(s->device));
+}
+
 void check_flag_combo(uint32_t flags) {
     int n = ((flags & GSTIM_PREPEND_OBS) != 0) + ((flags & GSTIM_APPEND_OBS) != 0) + ((flags & GSTIM_SEPARATE_OBS) != 0);
     if (n > 1) {
@@ -1346,6 +1411,40 @@ int gstim_create_from_text(const char *circuit_text, size_t text_len, int mode, 
     });
 }
 
+int gstim_create_from_text_multi(
+    const char *circuit_text, size_t text_len, int mode, uint64_t seed, const int *devices, int n_devices, gstim_sampler **out) {
+    if (out != nullptr) {
+        *out = nullptr;
+    }
+    if (devices == nullptr || n_devices < 1 || out == nullptr) {
+        return guarded([&] { require(false, "devices must name at least one CUDA device."); });
+    }
+    for (int i = 0; i < n_devices; i++) {
+        for (int j = 0; j < i; j++) {
+            if (devices[i] == devices[j]) {
+                return guarded([&] { require(false, "devices must be distinct."); });
+            }
+        }
+    }
+    gstim_sampler *first = nullptr;
+    int rc = gstim_create_from_text(circuit_text, text_len, mode, seed, devices[0], &first);
+    if (rc != GSTIM_OK) {
+        return rc;
+    }
+    for (int i = 1; i < n_devices; i++) {
+        gstim_sampler *p = nullptr;
+        rc = gstim_create_from_text(circuit_text, text_len, mode, seed, devices[i], &p);
+        if (rc != GSTIM_OK) {
+            gstim_destroy(first);
+            return rc;
+        }
+        first->peers.push_back(p);
+    }
+    cudaSetDevice(devices[0]);
+    *out = first;
+    return GSTIM_OK;
+}
+
 void gstim_destroy(gstim_sampler *s) {
     if (s) {
         cudaSetDevice(s->device);
@@ -1428,6 +1527,12 @@ int gstim_sample_detectors(
         require(s->mode == GSTIM_MODE_DETECTORS, "Not a detector sampler.");
         require(dets_shot_stride >= 0 && obs_shot_stride >= 0, "negative strides are not supported.");
         check_flag_combo(flags);
+        if (!s->peers.empty()) {
+            sample_to_host_multi(
+                s, shots, [&](gstim_sampler *d) { return detector_row_maps(d, flags); }, flags, (flags & GSTIM_BIT_PACKED) != 0,
+                (uint8_t *)dets_out, dets_shot_stride, (uint8_t *)obs_out, obs_shot_stride);
+            return;
+        }
         RowMaps maps = detector_row_maps(s, flags);
         sample_to_host(
             s, shots, maps, flags, (flags & GSTIM_BIT_PACKED) != 0, (uint8_t *)dets_out, dets_shot_stride, (uint8_t *)obs_out, obs_shot_stride);
@@ -1439,6 +1544,12 @@ int gstim_sample_measurements(gstim_sampler *s, uint64_t shots, uint32_t flags, 
         require(s != nullptr, "NULL sampler.");
         require(s->mode == GSTIM_MODE_MEASUREMENTS, "Not a measurement sampler.");
         require(shot_stride >= 0, "negative strides are not supported.");
+        if (!s->peers.empty()) {
+            sample_to_host_multi(
+                s, shots, [&](gstim_sampler *d) { return measurement_row_maps(d); }, 0, (flags & GSTIM_BIT_PACKED) != 0, (uint8_t *)out,
+                shot_stride, nullptr, 0);
+            return;
+        }
         RowMaps maps = measurement_row_maps(s);
         sample_to_host(s, shots, maps, 0, (flags & GSTIM_BIT_PACKED) != 0, (uint8_t *)out, shot_stride, nullptr, 0);
     });

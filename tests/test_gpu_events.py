@@ -190,3 +190,27 @@ def test_d71_surface_code_beyond_the_interpreters_frame_limit():
     assert busy.sum() > 1000 and np.abs(z[busy]).max() < 6.0
     assert abs(np.sqrt(np.mean(z[busy] ** 2)) - 1.0) < 0.1
     assert abs(k_gpu.sum() / shots - k_ref.sum() / n_ref) < 0.01 * k_ref.sum() / n_ref
+
+
+def test_multi_device_sampler_equals_single_device():
+    """gstim_create_from_text_multi: one sample() call sharded over two GPUs of this process returns exactly the shots
+    a single-device sampler returns (the event engine's stream depends on the seed and the global shot index only)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    text = gen_circuit("surface_code", "rotated_memory_x", 5, 5, 0.01)
+    shots = 100_000 + 77
+    one = stim_b200.Circuit(text).compile_detector_sampler(seed=3, engine="events")
+    two = stim_b200.Circuit(text).compile_detector_sampler(seed=3, engine="events", device=[0, 1])
+    a = one.sample(shots, bit_packed=True, append_observables=True)
+    b = two.sample(shots, bit_packed=True, append_observables=True)
+    np.testing.assert_array_equal(a, b)
+    assert two.shot_offset == one.shot_offset
+    a2, ao = one.sample(1000, separate_observables=True)
+    b2, bo = two.sample(1000, separate_observables=True)
+    np.testing.assert_array_equal(a2, b2)
+    np.testing.assert_array_equal(ao, bo)
+    m1 = stim_b200.Circuit(text).compile_sampler(seed=4, engine="events").sample(5000, bit_packed=True)
+    m2 = stim_b200.Circuit(text).compile_sampler(seed=4, engine="events", device=[0, 1]).sample(5000, bit_packed=True)
+    np.testing.assert_array_equal(m1, m2)
