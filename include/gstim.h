@@ -309,6 +309,33 @@ int gstim_m2d_get_sizes(const gstim_m2d *h, uint64_t *num_measurements, uint64_t
 int gstim_m2d_convert(gstim_m2d *h, uint64_t shots, uint32_t flags, const void *measurements, int64_t meas_stride, const void *sweep_bits,
                       int64_t sweep_stride, void *dets_out, int64_t dets_stride, void *obs_out, int64_t obs_stride);
 
+/* ---- interactive flip simulator -----------------------------------------------------------
+ * Replaces: stim.FlipSimulator over FrameSimulator<W>   src/stim/simulators/frame_simulator.pybind.cc:507-1561,
+ *           src/stim/simulators/frame_simulator.inl:153-1113 (safe_do_circuit / do_gate one fragment at a time).
+ * A batch of shots whose frame (x, z rows per qubit), measurement flip record, detector flips and observable flips live
+ * in device memory between calls. Tables are bit-major: a row = row_words uint32 words over the instances (instance i =
+ * bit i % 32 of word i / 32; bits beyond batch_size are unspecified). Table selectors: 0 x, 1 z, 2 measurement flips,
+ * 3 detector flips, 4 observable flips. */
+typedef struct gstim_flipsim gstim_flipsim;
+int gstim_flipsim_create(uint64_t batch_size, int disable_stabilizer_randomization, uint64_t num_qubits, uint64_t seed, int device,
+                         gstim_flipsim **out);
+void gstim_flipsim_destroy(gstim_flipsim *h);
+int gstim_flipsim_sizes(const gstim_flipsim *h, uint64_t *batch_size, uint64_t *num_qubits, uint64_t *num_measurements,
+                        uint64_t *num_detectors, uint64_t *num_observables, uint64_t *row_words);
+/* FlipSimulator.do: applies a circuit fragment (any instructions, REPEAT blocks, noise, detectors; rec[-k] looks back
+ * over everything measured so far). */
+int gstim_flipsim_do_text(gstim_flipsim *h, const char *circuit_text, size_t text_len);
+/* Rows [first_row, first_row + n_rows) of a table to / from host memory (n_rows * row_words words). set_rows with
+ * xor_in != 0 XORs instead of overwriting; writing measurement rows at first_row == num_measurements appends them
+ * (append_measurement_flips); writing x / z rows beyond num_qubits grows the simulator. */
+int gstim_flipsim_get_rows(gstim_flipsim *h, int what, uint64_t first_row, uint64_t n_rows, uint32_t *words_out);
+int gstim_flipsim_set_rows(gstim_flipsim *h, int what, uint64_t first_row, uint64_t n_rows, const uint32_t *words_in, int xor_in);
+/* broadcast_pauli_errors: pauli (0 I, 1 X, 2 Y, 3 Z) applied where mask (n_rows qubit rows, bit-major) is set, each with
+ * probability p. generate_bernoulli_samples: n_words words of Bernoulli(p) bits. clear: back to the start state. */
+int gstim_flipsim_broadcast(gstim_flipsim *h, int pauli, const uint32_t *mask_words, uint64_t n_rows, double p);
+int gstim_flipsim_bernoulli(gstim_flipsim *h, uint64_t n_words, double p, uint32_t *words_out);
+int gstim_flipsim_clear(gstim_flipsim *h);
+
 /* Pins the number of 128-shot columns per thread block (0 = choose per call from the shot count, the default). The
  * random stream is a function of (seed, shot offset, columns per block): callers that split one global shot range over
  * several handles / GPUs and need the union to equal a single-handle run pin the same value everywhere and keep every

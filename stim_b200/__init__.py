@@ -21,9 +21,10 @@ from . import _native
 from ._native import GstimCudaError, GstimStats
 
 from .dem import CompiledDemSampler, DetectorErrorModel  # noqa: E402,F401
+from .flipsim import FlipSimulator  # noqa: E402,F401
 
 __all__ = ["Circuit", "CompiledDetectorSampler", "CompiledMeasurementSampler", "GstimCudaError", "measure_lop3_peak", "response_table",
-           "DetectorErrorModel", "CompiledDemSampler", "CompiledMeasurementsToDetectionEventsConverter"]
+           "DetectorErrorModel", "CompiledDemSampler", "CompiledMeasurementsToDetectionEventsConverter", "FlipSimulator"]
 
 
 def measure_lop3_peak(device: int = 0) -> dict:

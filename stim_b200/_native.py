@@ -125,6 +125,15 @@ _SIGNATURES = [
                                            ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     ("gstim_m2d_convert", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_uint32, _P, ctypes.c_int64, _P, ctypes.c_int64, _P, ctypes.c_int64,
                                          _P, ctypes.c_int64]),
+    ("gstim_flipsim_create", ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(_P)]),
+    ("gstim_flipsim_destroy", None, [_P]),
+    ("gstim_flipsim_sizes", ctypes.c_int, [_P] + [ctypes.POINTER(ctypes.c_uint64)] * 6),
+    ("gstim_flipsim_do_text", ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_size_t]),
+    ("gstim_flipsim_get_rows", ctypes.c_int, [_P, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    ("gstim_flipsim_set_rows", ctypes.c_int, [_P, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _P, ctypes.c_int]),
+    ("gstim_flipsim_broadcast", ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_uint64, ctypes.c_double]),
+    ("gstim_flipsim_bernoulli", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_double, _P]),
+    ("gstim_flipsim_clear", ctypes.c_int, [_P]),
     ("gstim_set_block_columns", ctypes.c_int, [_P, ctypes.c_uint32]),
     ("gstim_measure_lop3_peak", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                                ctypes.POINTER(ctypes.c_double)]),

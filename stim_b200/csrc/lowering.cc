@@ -1391,6 +1391,44 @@ LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch
     return std::move(lw.lc);
 }
 
+LoweredCircuit lower_fragment(const Circuit &c, uint32_t num_qubits, uint64_t meas0) {
+    Lowerer lw(1u << 20);
+    LoweredCircuit &lc = lw.lc;
+    lc.mode = 0;
+    lc.stats = compute_stats(c);
+    const uint64_t total_meas = meas0 + lc.stats.num_measurements;
+    if (total_meas >= (1ull << 31) || lc.stats.num_detectors + lc.stats.num_observables >= (1ull << 31)) {
+        throw std::invalid_argument("Too many measurements or detectors for the interactive simulator.");
+    }
+    const uint32_t Q = std::max<uint32_t>(num_qubits, (uint32_t)lc.stats.num_qubits);
+    if (Q > 65535) {
+        throw std::invalid_argument("Circuits with more than 65535 qubits are not supported by this build.");
+    }
+    lc.qubit_map.resize(Q);
+    for (uint32_t q = 0; q < Q; q++) {
+        lc.qubit_map[q] = q;
+    }
+    lc.num_qubits = Q;
+    lw.Q = Q;
+    lc.rec_ring = 0;
+    lw.rec_mask = 0xFFFFFFFFu;
+    lw.meas = meas0;
+    lw.res_clock = Q;
+    lw.res_flag = Q + 1;
+    lw.res_rec0 = Q + 2;
+    lw.res_out0 = lw.res_rec0 + (uint32_t)std::max<uint64_t>(total_meas, 1);
+    lc.num_resources = lw.res_out0 + (uint32_t)(lc.stats.num_detectors + lc.stats.num_observables) + 1;
+    lw.rd_stamp.assign(lc.num_resources, 0);
+    lw.wr_stamp.assign(lc.num_resources, 0);
+    c.for_each_operation([&](const Instruction &op) {
+        lw.do_op(op);
+    });
+    lw.flush();
+    lc.num_sites = lw.ngroup;
+    lc.num_csites = lw.mgroup;
+    return std::move(lw.lc);
+}
+
 std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint32_t chunk_words, GstimPlan *plan) {
     std::vector<uint32_t> out;
     const uint32_t NONE = 0xFFFFFFFFu, MULTI = 0xFFFFFFFEu;

@@ -70,6 +70,12 @@ uint64_t gstim_rate_key(double p);
 // not be serialised for the interpreter.
 LoweredCircuit lower_circuit(const Circuit &c, uint32_t mode, uint32_t max_batch_words, bool with_sweep = false);
 
+// Lowers a fragment of a circuit for the interactive simulator (flipsim.cu): no implicit reset at the start, qubit index =
+// frame row (no compaction; rows [0, num_qubits)), measurement results numbered from meas0 with ABSOLUTE record indices,
+// detectors numbered from 0 within the fragment, observable l at output row (fragment's detector count + l), no detector
+// fusion and no layout post-pass. Batches keep the "items of a batch touch disjoint resources" property.
+LoweredCircuit lower_fragment(const Circuit &c, uint32_t num_qubits, uint64_t meas0);
+
 // Pass 2: hazard analysis for `slots` concurrent thread groups + serialisation into chunks.
 std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint32_t chunk_words, GstimPlan *plan);
 

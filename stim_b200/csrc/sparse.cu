@@ -45,6 +45,9 @@ constexpr uint32_t SPARSE_TAG = 0x53500000u;  // 'SP' << 20
 constexpr uint32_t MAX_CLASSES = 64;          // classes are mirrored in shared memory
 constexpr uint32_t MAX_BUFFERS = 8;           // tile images per block
 constexpr uint32_t SPARSE_THREADS = 1024;     // 31 producer warps + 1 writer warp
+#ifndef GSTIM_PRODUCER_SLEEP_NS
+#define GSTIM_PRODUCER_SLEEP_NS 32
+#endif
 constexpr uint32_t CTL_WORDS = 8;             // per buffer: next slice, lanes that left, full seq, ready seq, phase main, phase obs
 
 enum : uint32_t { DK_SINGLE = 0, DK_UNIFORM = 1, DK_THRESH3 = 2, DK_THRESH_N = 3 };
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         if (!entered) {
             // wait until the buffer has been recycled for sequence q
             while (ld_volatile_shared(c + 3) != q + 1) {
-                __nanosleep(32);
+                __nanosleep(GSTIM_PRODUCER_SLEEP_NS);
             }
             __threadfence_block();
             const uint64_t gt = p.tile0 + blockIdx.x + (uint64_t)q * gridDim.x;
