@@ -276,7 +276,7 @@ typedef struct gstim_engine_info {
 int gstim_set_engine(gstim_sampler *s, int engine);
 int gstim_get_engine_info(const gstim_sampler *s, gstim_engine_info *out);
 /* Copies one array of the response table (tests / the oracle re-derive the responses by forward injection and restate
- * the sampling from it). what: 0 classes (23 words each: lam lo, lam hi, inv, sh, kind, n_out, thr[15], n_sites, entry0),
+ * the sampling from it). what: 0 classes (24 words each: lam lo, lam hi, inv, sh, kind, n_out, thr[15], n_sites, entry0, dense threshold),
  * 1 entries (4 words each: output ids - detector d, observable D + l, measurement m - 0xFFFFFFFF = empty, a 4th word with
  * bit 31 = offset into the overflow array), 2 overflow (count, ids...), 3 site noise group (bit 31: collapse site of that
  * measure group), 4 site index in its group (collapse sites: logical qubit), 5 representative chooser word per class

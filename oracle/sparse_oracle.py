@@ -128,6 +128,33 @@ def sample(table, slices, tile_shots, seed, first_shot, n_shots, n_outputs):
             rate = (int(c[2]), int(c[3]))
             kind, n_out, thr = int(c[4]), int(c[5]), c[6:21]
             total, ebase = int(total), int(ebase)
+            dense_thr = int(c[23]) if len(c) > 23 else 0
+            if dense_thr:
+                # packed Bernoulli words (sparse.cu "Dense class"): P(bit) = dense_thr / 2^32 by the binary expansion of the
+                # threshold, lowest set bit first (the bit-sliced part of biased_randomize_bits, probability_util.cc:74-132)
+                i0 = (dense_thr & -dense_thr).bit_length() - 1
+                for j in range((total + 31) // 32):
+                    acc, r = 0, None
+                    for i in range(i0, 32):
+                        if i == i0 or i % 4 == 0:
+                            r = [int(v) for v in px.philox4x32_10(sl, 8 * j + (i >> 2), c2, c3, k0, k1)]
+                        acc = (acc | r[i & 3]) if (dense_thr >> i) & 1 else (acc & r[i & 3])
+                    left = total - 32 * j
+                    if left < 32:
+                        acc &= (1 << left) - 1
+                    for b in range(32):
+                        if not (acc >> b) & 1:
+                            continue
+                        tr = 32 * j + b
+                        site, shot = tr >> log_s, tr & (S - 1)
+                        o = 0
+                        if n_out > 1:
+                            o = choose(kind, n_out, thr, int(px.philox4x32_10(sl, 0x80000000 | tr, c2, c3, k0, k1)[0]))
+                        row = t * S + shot
+                        if row < n_shots:
+                            for v in entry_ids(table, ebase + site * n_out + o):
+                                out[row, v] ^= 1
+                continue
             a = call = 0
             done = False
             while not done:

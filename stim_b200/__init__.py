@@ -110,7 +110,7 @@ _TABLE_ARRAYS = ["classes", "entries", "overflow", "site_group", "site_index", "
 
 
 def _shape_table(out: dict) -> dict:
-    out["classes"] = out["classes"].reshape(-1, 23)
+    out["classes"] = out["classes"].reshape(-1, 24)
     out["entries"] = out["entries"].reshape(-1, 4)
     if "slices" in out:
         out["slices"] = out["slices"].reshape(-1, 4)

@@ -1231,6 +1231,7 @@ void export_table_array(const ResponseTable &rt, const std::vector<uint32_t> *sl
                 tmp.insert(tmp.end(), c.thr, c.thr + 15);
                 tmp.push_back(c.n_sites);
                 tmp.push_back(c.entry0);
+                tmp.push_back(c.dense_thr);
             }
             break;
         case 1:

@@ -576,6 +576,20 @@ ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate
         rc.entry0 = (uint32_t)(rt.entries.size() / 4);
         const double lam = std::ldexp((double)a.key.lam, -56);
         const double p = a.key.lam >= LAM_MAX ? 1.0 : -std::expm1(-lam);
+        if (p < 1.0) {
+            // packed Bernoulli words pay when the words per trial (0.47 instructions per level and trial) cost less than the
+            // draws of the geometric walk (46 instructions per event): p = 1/2 needs one level, p = 1/4 two, a generic p ~30
+            const double t = std::floor(p * 4294967296.0 + 0.5);
+            const uint32_t thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+            if (a.key.lam == LAM_HALF) {
+                rc.dense_thr = 0x80000000u;  // collapse bits: a fair coin, exactly
+            } else if (thr != 0) {
+                const int levels = 32 - __builtin_ctz(thr);
+                if (levels * 0.47 < 46.0 * p) {
+                    rc.dense_thr = thr;
+                }
+            }
+        }
         rt.events_per_shot += p * rc.n_sites;
         uint64_t class_ids = 0;
         for (const Set &s : a.responses) {

@@ -49,6 +49,11 @@ struct RespClass {
     uint32_t thr[15] = {0};      // RK_THRESH: ascending upper bounds of outcomes 0 .. n_out - 2 on a uniform u32
     uint32_t n_sites = 0;
     uint32_t entry0 = 0;         // table entry of (site s, outcome o) = entry0 + s * n_out + o
+    // Dense classes (p large, e.g. the p = 1/2 collapse bits): the trials are drawn 32 at a time as packed Bernoulli words,
+    // P(bit) = dense_thr / 2^32 exactly, built from 32 - ctz(dense_thr) random words by the binary expansion of the
+    // probability (the bit-sliced part of biased_randomize_bits, /root/reference/src/stim/util_bot/probability_util.cc:74-132).
+    // 0 = walk the class with geometric gaps.
+    uint32_t dense_thr = 0;
 };
 
 struct ResponseTable {

@@ -63,7 +63,8 @@ struct EvClass {  // 64 bytes, shared memory
     uint32_t n_out;
     uint32_t thr[3];     // DK_THRESH3: thresholds - 1 (outcome = number of thr[j] < word); unused ones 0xFFFFFFFF
     uint32_t thr_off;    // DK_THRESH_N: word offset of the 15 thresholds in `thr_all`
-    uint32_t pad[3];
+    uint32_t dense_thr;  // != 0: packed Bernoulli words with P(bit) = dense_thr / 2^32 instead of geometric gaps
+    uint32_t pad[2];
 };
 
 struct SparseParams {
@@ -372,7 +373,53 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         const uint32_t s0 = (sl - w0.y) * w0.z;
         const uint32_t total = min(w0.z, w0.w - s0) << p.log_s;  // trials of the slice (<= 2^30)
         const uint32_t n_out = w2.x, ebase = w1.x + s0 * n_out, inv = w1.y, sh = w1.z, kind = w1.w;
-        const uint32_t t0 = w2.y, t1 = w2.z, t2 = w2.w, thr_off = cls[k].thr_off;
+        const uint32_t t0 = w2.y, t1 = w2.z, t2 = w2.w, thr_off = cls[k].thr_off, dense_thr = cls[k].dense_thr;
+
+        if (dense_thr != 0) {
+            // Dense class: the trials of the slice as packed Bernoulli words, 32 trials per lane and pass. A word with
+            // P(bit) = thr / 2^32 comes from the binary expansion of thr, lowest set bit first: acc = b_i ? acc | r_i :
+            // acc & r_i halves the probability and adds b_i / 2 (the bit-sliced part of biased_randomize_bits,
+            // probability_util.cc:74-132; a fair coin is ONE random word). Random word i of trial word j = word (i & 3) of
+            // Philox call 8 j + (i >> 2); the outcome word of the event at trial t = word 0 of call 0x80000000 | t.
+            const uint32_t i0 = (uint32_t)__ffs((int)dense_thr) - 1u, n_words = (total + 31u) >> 5;
+            for (uint32_t j = lane; j < n_words; j += 32) {
+                uint32_t acc = 0;
+                uint4 r = make_uint4(0, 0, 0, 0);
+                for (uint32_t i = i0; i < 32; i++) {
+                    if (i == i0 || (i & 3u) == 0) {
+                        r = sp_philox(sl, 8u * j + (i >> 2), c2, c3, p.rk);
+                    }
+                    const uint32_t ri = (i & 3u) == 0 ? r.x : (i & 3u) == 1 ? r.y : (i & 3u) == 2 ? r.z : r.w;
+                    acc = ((dense_thr >> i) & 1u) ? (acc | ri) : (acc & ri);
+                }
+                const uint32_t left = total - 32u * j;
+                if (left < 32u) {
+                    acc &= (1u << left) - 1u;
+                }
+                while (acc) {
+                    const uint32_t t = 32u * j + (uint32_t)__ffs((int)acc) - 1u;
+                    acc &= acc - 1u;
+                    const uint32_t site = t >> p.log_s, shot = t & smask;
+                    uint32_t o = 0;
+                    if (n_out > 1) {
+                        const uint32_t pw = sp_philox(sl, 0x80000000u | t, c2, c3, p.rk).x;
+                        if (kind == DK_UNIFORM) {
+                            o = __umulhi(pw, n_out);
+                        } else if (kind == DK_THRESH3) {
+                            o = (pw > t0 ? 1u : 0u) + (pw > t1 ? 1u : 0u) + (pw > t2 ? 1u : 0u);
+                        } else {
+                            for (uint32_t jj = 0; jj + 1 < n_out; jj++) {
+                                o += pw >= __ldg(p.thr_all + thr_off + jj) ? 1u : 0u;
+                            }
+                        }
+                    }
+                    const uint4 e = __ldg(p.entries + (ebase + site * n_out + o));
+                    apply(e, rowbase_m + shot * main_bits, rowbase_o + shot * obs_bits);
+                }
+            }
+            __syncwarp();
+            continue;
+        }
 
         uint32_t a0 = 0;  // trials consumed by the previous steps
         for (uint32_t call0 = 0;; call0 += 32) {
@@ -613,7 +660,8 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
     for (const RespClass &c : I.rt.classes) {
         const double lam = std::ldexp((double)c.lam, -56);
         const double pr = c.inv == 0 ? 1.0 : -std::expm1(-lam);
-        const double want = (double)slice_events / (pr * S);
+        // (dense classes: 4096 trials per slice = four 32-trial words per lane)
+        const double want = c.dense_thr ? 4096.0 / S : (double)slice_events / (pr * S);
         const uint32_t per = (uint32_t)std::max(1.0, std::min(want, (double)((1u << 30) >> I.log_s)));
         EvClass d{};
         d.slice0 = (uint32_t)(I.slices_host.size() / 4);
@@ -627,6 +675,7 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
         for (uint32_t j = 0; j < 3; j++) {  // registers of the chooser: threshold - 1 (pw > t <=> pw >= threshold), unused: never
             d.thr[j] = (d.kind == DK_THRESH3 && j + 1 < c.n_out) ? c.thr[j] - 1u : 0xFFFFFFFFu;
         }
+        d.dense_thr = c.dense_thr;
         d.thr_off = (uint32_t)thr_all.size();
         thr_all.insert(thr_all.end(), c.thr, c.thr + 15);
         for (uint32_t s0 = 0; s0 < c.n_sites; s0 += per) {

@@ -214,3 +214,35 @@ def test_multi_device_sampler_equals_single_device():
     m1 = stim_b200.Circuit(text).compile_sampler(seed=4, engine="events").sample(5000, bit_packed=True)
     m2 = stim_b200.Circuit(text).compile_sampler(seed=4, engine="events", device=[0, 1]).sample(5000, bit_packed=True)
     np.testing.assert_array_equal(m1, m2)
+
+
+def test_dense_noise_takes_the_packed_word_path_and_matches_oracle_and_interpreter():
+    """Packed Bernoulli words for dense sites (north_star; probability_util.cc:74-132): bit for bit against the oracle, and
+    statistically against the interpreter's geometric walk on the same circuit."""
+    text = """
+    R 0 1 2 3 4 5
+    X_ERROR(0.5) 0 1
+    DEPOLARIZE1(0.75) 2
+    DEPOLARIZE2(0.5) 3 4
+    Z_ERROR(0.25) 5
+    H 5
+    CX 0 1 2 3
+    M 0 1 2 3 4 5
+    DETECTOR rec[-6]
+    DETECTOR rec[-5]
+    DETECTOR rec[-4] rec[-3]
+    DETECTOR rec[-3]
+    DETECTOR rec[-2]
+    DETECTOR rec[-1]
+    OBSERVABLE_INCLUDE(0) rec[-6] rec[-1]
+    """
+    s, _ = check_detectors(text, 3000, seed=8)
+    cl = s.response_table()["classes"]
+    assert (cl[:, 23] != 0).sum() >= 4
+    shots = 1 << 20
+    ev, _ = stim_b200.Circuit(text).compile_detector_sampler(seed=1, engine="events").bit_counts(shots)
+    it, _ = stim_b200.Circuit(text).compile_detector_sampler(seed=2, engine="interp").bit_counts(shots)
+    p = (ev + it) / (2.0 * shots)
+    z = (ev.astype(np.float64) - it.astype(np.float64)) / shots / np.sqrt(np.maximum(p * (1 - p), 1e-12) * 2 / shots)
+    assert np.abs(z).max() < 5.0, z
+    np.testing.assert_allclose(ev[:2] / shots, [0.5, 0.5], atol=0.003)

@@ -117,3 +117,19 @@ def test_oracle_sampler_statistics_on_a_tiny_circuit():
     out = so.sample(t, slices, 128, seed=7, first_shot=0, n_shots=1 << 14, n_outputs=2)
     rates = out.mean(axis=0)
     assert abs(rates[0] - 0.25) < 0.02 and abs(rates[1] - 0.5) < 0.02
+
+
+def test_dense_classes_use_packed_bernoulli_words():
+    """p = 1/2 and 1/4 need one and two random words per 32 trials, float32(0.3) 24 of them (still cheaper than 0.3 draws per
+    trial); p = 0.1 stays with the geometric walk; collapse bits that reach an output are fair coins. The oracle's word
+    method has the right rates."""
+    text = "X_ERROR(0.5) 0\nX_ERROR(0.25) 1\nX_ERROR(0.3) 2\nDEPOLARIZE1(0.75) 3\nX_ERROR(0.1) 4\nM 0 1 2 3 4\n" + "".join(
+        f"DETECTOR rec[-{k}]\n" for k in (5, 4, 3, 2, 1))
+    t = check_table(text)
+    by_p = {round(-np.expm1(-float(int(c[0]) | (int(c[1]) << 32)) * 2.0**-56), 3): int(c[23]) for c in t["classes"]}
+    assert by_p[0.5] == 1 << 31 and by_p[0.25] == 1 << 30 and by_p[0.3] == 0x4CCCCD00 and by_p[0.75] == 3 << 30 and by_p[0.1] == 0
+    slices = np.array([[ci, int(c[21]) * 128, int(c[22]), 0] for ci, c in enumerate(t["classes"])], dtype=np.uint32)
+    out = so.sample(t, slices, 128, seed=11, first_shot=0, n_shots=1 << 13, n_outputs=5)
+    np.testing.assert_allclose(out.mean(axis=0), [0.5, 0.25, 0.3, 0.5, 0.1], atol=0.025)  # DEPOLARIZE1(0.75): X or Y flips the result
+    m = stim_b200.response_table("H 0\nM 0\nDETECTOR rec[-1]\n")
+    assert len(m["classes"]) == 1 and int(m["classes"][0][23]) == 1 << 31 and (m["site_group"] & 0x80000000).all()
