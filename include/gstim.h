@@ -268,6 +268,7 @@ typedef struct gstim_engine_info {
     uint32_t max_response;     /* most output bits flipped by one (site, outcome) */
     uint64_t num_sites;        /* noise + live collapse sites */
     uint64_t num_entries;      /* (site, outcome) table entries of 16 bytes */
+    uint64_t device_entries;   /* entries stored on the device (tables beyond GSTIM_TABLE_COMPRESS_MB are folded to one round) */
     uint64_t overflow_words;
     double events_per_shot;    /* expected events per shot */
     double flips_per_shot;     /* expected bit flips per shot */
@@ -280,10 +281,11 @@ int gstim_get_engine_info(const gstim_sampler *s, gstim_engine_info *out);
  * 1 entries (4 words each: output ids - detector d, observable D + l, measurement m - 0xFFFFFFFF = empty, a 4th word with
  * bit 31 = offset into the overflow array), 2 overflow (count, ids...), 3 site noise group (bit 31: collapse site of that
  * measure group), 4 site index in its group (collapse sites: logical qubit), 5 representative chooser word per class
- * outcome, 6 slices (4 words each: class, trials = sites * tile_shots, first entry, 0).
+ * outcome, 6 slices (4 words each: class, trials = sites * tile_shots, first entry, 0), 7 round structure per class (4 words: a, p, n,
+ * delta: entries of site s + p = entries of site s with delta added to the detector ids, for s in [a, a + n - p); p = 0 none).
  * Call with words == NULL to get the length in *n_words. */
 int gstim_get_response_table(const gstim_sampler *s, int what, uint32_t *words, size_t *n_words);
-/* Host-only (no GPU needed): lowers the circuit and builds its response table; `what` selectors 0-5 as above.
+/* Host-only (no GPU needed): lowers the circuit and builds its response table; `what` selectors 0-5 and 7 as above.
  * gstim_response_table_info fills the table statistics of a gstim_engine_info struct: eligible, why_not, sites, entries, .... */
 typedef struct gstim_response_table gstim_response_table;
 int gstim_response_table_create(const char *circuit_text, size_t text_len, int mode, gstim_response_table **out);

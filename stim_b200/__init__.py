@@ -114,6 +114,8 @@ def _shape_table(out: dict) -> dict:
     out["entries"] = out["entries"].reshape(-1, 4)
     if "slices" in out:
         out["slices"] = out["slices"].reshape(-1, 4)
+    if "periods" in out:
+        out["periods"] = out["periods"].reshape(-1, 4)
     return out
 
 
@@ -132,7 +134,7 @@ def response_table(circuit, mode: str = "detectors") -> dict:
         out = {"info": d}
         if not info.eligible:
             return out
-        for what, name in enumerate(_TABLE_ARRAYS[:6]):
+        for what, name in list(enumerate(_TABLE_ARRAYS[:6])) + [(7, "periods")]:
             n = ctypes.c_size_t(0)
             _native.check(_native.lib().gstim_response_table_get(h, what, None, ctypes.byref(n)))
             a = np.zeros(n.value, dtype=np.uint32)

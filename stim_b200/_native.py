@@ -61,6 +61,7 @@ class GstimEngineInfo(ctypes.Structure):
         ("max_response", ctypes.c_uint32),
         ("num_sites", ctypes.c_uint64),
         ("num_entries", ctypes.c_uint64),
+        ("device_entries", ctypes.c_uint64),
         ("overflow_words", ctypes.c_uint64),
         ("events_per_shot", ctypes.c_double),
         ("flips_per_shot", ctypes.c_double),

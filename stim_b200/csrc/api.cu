@@ -395,7 +395,7 @@ void configure_event_engine(gstim_sampler *s) {
     try {
         s->sparse = std::make_unique<SparseEngine>(
             std::move(rt), (uint32_t)s->mode, s->plan.num_det, s->plan.num_obs, s->plan.num_meas, s->device, env_u32("GSTIM_SLICE_EVENTS", 0),
-            env_u32("GSTIM_TILE_BUFFERS", 0));
+            env_u32("GSTIM_TILE_BUFFERS", 0), env_u32("GSTIM_TABLE_COMPRESS_MB", 48));
         s->sparse_favoured = favoured;
         s->sparse_why.clear();
     } catch (const std::invalid_argument &e) {
@@ -1216,7 +1216,8 @@ void fill_table_info(const ResponseTable &rt, gstim_engine_info *out) {
     out->flips_per_shot = rt.flips_per_shot;
 }
 
-void export_table_array(const ResponseTable &rt, const std::vector<uint32_t> *slices, int what, uint32_t *words, size_t *n_words) {
+void export_table_array(const ResponseTable &rt, const std::vector<uint32_t> *slices, uint32_t n_det, int what, uint32_t *words,
+                        size_t *n_words) {
     std::vector<uint32_t> tmp;
     const std::vector<uint32_t> *src = &tmp;
     switch (what) {
@@ -1248,6 +1249,15 @@ void export_table_array(const ResponseTable &rt, const std::vector<uint32_t> *sl
             break;
         case 5:
             src = &rt.outcome_word;
+            break;
+        case 7:  // round structure per class: a, p, n, delta (response.h ResponsePeriod)
+            for (const RespClass &c : rt.classes) {
+                const ResponsePeriod pd = find_response_period(rt, c, n_det);
+                tmp.push_back(pd.a);
+                tmp.push_back(pd.p);
+                tmp.push_back(pd.n);
+                tmp.push_back(pd.delta);
+            }
             break;
         case 6:
             if (slices == nullptr) {
@@ -1744,6 +1754,7 @@ int gstim_get_engine_info(const gstim_sampler *s, gstim_engine_info *out) {
         out->tile_shots = s->sparse->tile_shots();
         out->blocks_per_sm = s->sparse->blocks_per_sm();
         out->num_slices = (uint32_t)(s->sparse->slices().size() / 4);
+        out->device_entries = s->sparse->device_table_entries();
     });
 }
 
@@ -1751,12 +1762,13 @@ int gstim_get_response_table(const gstim_sampler *s, int what, uint32_t *words, 
     return guarded([&] {
         require(s && n_words, "NULL argument.");
         require(s->sparse != nullptr, "The circuit has no response table.");
-        export_table_array(s->sparse->table(), &s->sparse->slices(), what, words, n_words);
+        export_table_array(s->sparse->table(), &s->sparse->slices(), s->mode == GSTIM_MODE_DETECTORS ? s->plan.num_det : 0, what, words, n_words);
     });
 }
 
 struct gstim_response_table {
     ResponseTable rt;
+    uint32_t n_det = 0;
 };
 
 int gstim_response_table_create(const char *circuit_text, size_t text_len, int mode, gstim_response_table **out) {
@@ -1768,6 +1780,7 @@ int gstim_response_table_create(const char *circuit_text, size_t text_len, int m
         LoweredCircuit lc = lower_circuit(c, (uint32_t)mode, 2048 - GSTIM_HDR_WORDS);
         auto t = std::make_unique<gstim_response_table>();
         t->rt = build_response_table(lc);
+        t->n_det = mode == GSTIM_MODE_DETECTORS ? (uint32_t)lc.stats.num_detectors : 0;
         *out = t.release();
     });
 }
@@ -1791,7 +1804,7 @@ int gstim_response_table_get(const gstim_response_table *t, int what, uint32_t *
     return guarded([&] {
         require(t && n_words, "NULL argument.");
         require(t->rt.eligible, "The circuit has no response table.");
-        export_table_array(t->rt, nullptr, what, words, n_words);
+        export_table_array(t->rt, nullptr, t->n_det, what, words, n_words);
     });
 }
 

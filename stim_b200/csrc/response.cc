@@ -633,4 +633,107 @@ ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate
     return rt;
 }
 
+namespace {
+
+// Output ids of one table entry (with its overflow list).
+void entry_ids(const ResponseTable &rt, size_t e, std::vector<uint32_t> &ids) {
+    ids.clear();
+    const uint32_t *w = &rt.entries[4 * e];
+    for (int j = 0; j < 4; j++) {
+        if (w[j] == RESP_NONE) {
+            break;
+        }
+        if (j == 3 && (w[j] & RESP_OVERFLOW)) {
+            const uint32_t off = w[j] & 0x7FFFFFFFu, cnt = rt.overflow[off];
+            ids.insert(ids.end(), rt.overflow.begin() + off + 1, rt.overflow.begin() + off + 1 + cnt);
+            break;
+        }
+        ids.push_back(w[j]);
+    }
+}
+
+// Looks for the round structure of a class: a period P and a detector shift delta with
+//   entries(site s + P) == entries(site s) with delta added to every detector id (ids < D), observables unchanged,
+// for all s in [a, a + n - P). Unrolled REPEAT blocks of QEC circuits have it (P = sites of the class per round, delta =
+// detectors per round). Returns p = 0 when there is no such structure covering at least three periods.
+}  // namespace
+
+ResponsePeriod find_response_period(const ResponseTable &rt, const RespClass &c, uint32_t D) {
+    ResponsePeriod out;
+    const uint32_t n = c.n_sites, no = c.n_out;
+    if (n < 6) {
+        return out;
+    }
+    // per site: hash of its responses relative to its smallest detector id, and that id
+    std::vector<uint64_t> h(n);
+    std::vector<uint32_t> base(n);
+    std::vector<uint32_t> ids;
+    for (uint32_t s = 0; s < n; s++) {
+        uint32_t b = 0xFFFFFFFFu;
+        for (uint32_t o = 0; o < no; o++) {
+            entry_ids(rt, (size_t)c.entry0 + (size_t)s * no + o, ids);
+            for (uint32_t v : ids) {
+                if (v < D) {
+                    b = std::min(b, v);
+                }
+            }
+        }
+        uint64_t x = 1469598103934665603ull;
+        for (uint32_t o = 0; o < no; o++) {
+            entry_ids(rt, (size_t)c.entry0 + (size_t)s * no + o, ids);
+            x = (x ^ (0x100u + ids.size())) * 1099511628211ull;
+            for (uint32_t v : ids) {
+                x = (x ^ (v < D ? v - b : 0x80000000u | v)) * 1099511628211ull;
+            }
+        }
+        h[s] = x;
+        base[s] = b;
+    }
+    auto match = [&](uint32_t s, uint32_t t, uint32_t delta) {
+        if (h[s] != h[t]) {
+            return false;
+        }
+        return base[s] == 0xFFFFFFFFu ? base[t] == 0xFFFFFFFFu : (base[t] != 0xFFFFFFFFu && base[t] - base[s] == delta);
+    };
+    const uint32_t mid = n / 2;
+    uint64_t work = 0;  // (many sites of a round share their relative shape: most candidates fail within a few sites)
+    uint32_t best_saving = 0;
+    for (uint32_t P = 1; P <= n / 3 && mid + 2 * P <= n && work < (1ull << 27); P++) {
+        if (h[mid + P] != h[mid] || base[mid] == 0xFFFFFFFFu || base[mid + P] == 0xFFFFFFFFu || base[mid + P] <= base[mid]) {
+            continue;
+        }
+        const uint32_t delta = base[mid + P] - base[mid];
+        bool ok = true;
+        for (uint32_t j = 0; j < P && ok; j++) {
+            ok = match(mid + j, mid + j + P, delta);
+            work++;
+        }
+        if (!ok) {
+            continue;
+        }
+        uint32_t a = mid, e = mid + P;  // match(s, s + P) holds for s in [a, e)
+        while (a > 0 && match(a - 1, a - 1 + P, delta)) {
+            a--;
+        }
+        while (e + P < n && match(e, e + P, delta)) {
+            e++;
+        }
+        work += (mid - a) + (e - mid - P);
+        const uint32_t covered = e + P - a;
+        // (short periods exist too - neighbouring sites of a lattice row look alike - so keep the candidate that folds the
+        // most sites away, and stop once most of the class is covered)
+        if (covered >= 3 * P && covered - P > best_saving) {
+            best_saving = covered - P;
+            out.a = a;
+            out.p = P;
+            out.n = covered;
+            out.delta = delta;
+            if (best_saving >= n / 2) {
+                break;
+            }
+        }
+    }
+    return out;
+}
+
 }  // namespace gstim

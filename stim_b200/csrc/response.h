@@ -82,4 +82,13 @@ struct ResponseTable {
 // (guarantee_anticommutation_via_frame_randomization)` branches of frame_simulator.inl:173-317); no collapse sites then.
 ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate = false);
 
+// Round structure of a class: entries(site s + p) == entries(site s) with `delta` added to every detector id (< D) and the
+// observables unchanged, for all s in [a, a + n - p). Unrolled REPEAT blocks of QEC circuits have it (p = sites of the class
+// per round, delta = detectors per round); the device table then stores head + ONE period + tail (sparse.cu PERIODIC). p = 0:
+// no such structure covering at least three periods.
+struct ResponsePeriod {
+    uint32_t a = 0, p = 0, n = 0, delta = 0;
+};
+ResponsePeriod find_response_period(const ResponseTable &rt, const RespClass &c, uint32_t D);
+
 }  // namespace gstim

@@ -27,6 +27,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -52,7 +54,7 @@ constexpr uint32_t CTL_WORDS = 8;             // per buffer: next slice, lanes t
 
 enum : uint32_t { DK_SINGLE = 0, DK_UNIFORM = 1, DK_THRESH3 = 2, DK_THRESH_N = 3 };
 
-struct EvClass {  // 64 bytes, shared memory
+struct EvClass {  // 96 bytes, shared memory
     uint32_t slice_end;  // cumulative slice count up to and including this class
     uint32_t slice0;     // first slice of the class
     uint32_t per;        // sites per slice
@@ -65,6 +67,11 @@ struct EvClass {  // 64 bytes, shared memory
     uint32_t thr_off;    // DK_THRESH_N: word offset of the 15 thresholds in `thr_all`
     uint32_t dense_thr;  // != 0: packed Bernoulli words with P(bit) = dense_thr / 2^32 instead of geometric gaps
     uint32_t pad[2];
+    // periodic tables (PERIODIC kernels): sites [per_a + per_p, per_a + per_n) are not stored; site s of that range uses the
+    // entries of site per_a + (s - per_a) % per_p with per_delta * ((s - per_a) / per_p) added to its detector ids; the
+    // sites behind the range follow the first period in the table. per_p = 0: the class is stored in full.
+    uint32_t per_a, per_p, per_n, per_delta;
+    uint32_t pad2[4];
 };
 
 struct SparseParams {
@@ -89,6 +96,7 @@ struct SparseParams {
     uint32_t obs_img_off;  // byte offset of the observable image inside a tile image (multiple of 16)
     uint32_t img_bytes;    // bytes of one tile image, both parts (multiple of 16)
     uint32_t rk[20];       // Philox round keys: (k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85), r = 0..9
+    uint32_t det_lo, n_det;  // PERIODIC: table values in [det_lo, det_lo + n_det) are detectors (they take the period shift)
 };
 
 __device__ __forceinline__ uint4 sp_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20]) {
@@ -158,7 +166,7 @@ __device__ __forceinline__ void store_span(const uint8_t *img, uint32_t img_sadd
 //     at a tile boundary; it only waits when buffer (q + 1) % n_buffers has not been recycled yet;
 //   the writer warp waits until every producer lane has left sequence q, stores the image to global memory, clears it
 //     and hands the buffer to sequence q + n_buffers.
-template <bool SEPARATE>
+template <bool SEPARATE, bool PERIODIC>
 __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const __grid_constant__ SparseParams p) {
     extern __shared__ uint4 smem4[];
     uint2 *const lt = reinterpret_cast<uint2 *>(smem4);                        // 256 x (base, diff): 2 KiB
@@ -291,14 +299,18 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
     // the flips of a step's events are applied one step later, so their table entries have time to arrive
     uint4 pend0 = make_uint4(RESP_NONE, RESP_NONE, RESP_NONE, RESP_NONE), pend1 = pend0;
     uint32_t pm0 = 0, po0 = 0, pm1 = 0, po1 = 0;
+    uint32_t ps0 = 0, ps1 = 0;  // PERIODIC: detector-id shift of the pending events
 
     // flips output bit v of a row unless v is an empty slot / overflow link (bit 31 set): predicated, no branch
-    auto flip = [&](uint32_t row_m, uint32_t row_o, uint32_t v) {
+    auto flip = [&](uint32_t row_m, uint32_t row_o, uint32_t v, uint32_t shift = 0) {
         uint32_t bit;
         if (SEPARATE) {
             bit = ((v & 0x40000000u) ? row_o : row_m) + (v & 0x3FFFFFFFu);
         } else {
             bit = row_m + v;
+        }
+        if (PERIODIC) {
+            bit += (v - p.det_lo) < p.n_det ? shift : 0u;
         }
         asm volatile(
             "{\n"
@@ -309,18 +321,40 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
             "r"(1u << (bit & 31u)), "r"(v)
             : "memory");
     };
-    auto apply = [&](const uint4 &e, uint32_t row_m, uint32_t row_o) {
-        flip(row_m, row_o, e.x);
-        flip(row_m, row_o, e.y);
-        flip(row_m, row_o, e.z);
-        flip(row_m, row_o, e.w);
+    auto apply = [&](const uint4 &e, uint32_t row_m, uint32_t row_o, uint32_t shift = 0) {
+        flip(row_m, row_o, e.x, shift);
+        flip(row_m, row_o, e.y, shift);
+        flip(row_m, row_o, e.z, shift);
+        flip(row_m, row_o, e.w, shift);
         if (e.w != RESP_NONE && (e.w & RESP_OVERFLOW)) {
             const uint32_t *ov = p.overflow + (e.w & 0x7FFFFFFFu);
             const uint32_t cnt = __ldg(ov);
             for (uint32_t j = 1; j <= cnt; j++) {
-                flip(row_m, row_o, __ldg(ov + j));
+                flip(row_m, row_o, __ldg(ov + j), shift);
             }
         }
+    };
+    // table entry of (site `cs` of the class, outcome o); PERIODIC: folds the site into the stored period, *shift = what to
+    // add to its detector ids
+    uint32_t c_entry0 = 0, c_ebase = 0, c_s0 = 0, c_a = 0, c_p = 0, c_n = 0, c_delta = 0;
+    auto entry_of = [&](uint32_t site, uint32_t n_out, uint32_t o, uint32_t *shift) -> uint32_t {
+        if (!PERIODIC) {
+            return c_ebase + site * n_out + o;  // (site counts from the slice's first site)
+        }
+        uint32_t cs = c_s0 + site;
+        {
+            *shift = 0;
+            if (c_p != 0 && cs >= c_a + c_p) {
+                if (cs < c_a + c_n) {
+                    const uint32_t k = (cs - c_a) / c_p;
+                    cs -= k * c_p;
+                    *shift = k * c_delta;
+                } else {
+                    cs -= c_n - c_p;
+                }
+            }
+        }
+        return c_entry0 + cs * n_out + o;
     };
 
     while (q < n_seq) {
@@ -344,8 +378,8 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         sl = __shfl_sync(0xFFFFFFFFu, sl, 0);
         if (sl >= p.n_slices) {
             // the pool of sequence q is dry: apply what is pending, count this warp out, move on
-            apply(pend0, pm0, po0);
-            apply(pend1, pm1, po1);
+            apply(pend0, pm0, po0, ps0);
+            apply(pend1, pm1, po1, ps1);
             pend0.x = pend0.y = pend0.z = pend0.w = RESP_NONE;
             pend1 = pend0;
             __threadfence_block();
@@ -372,8 +406,18 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         const uint4 w0 = cw[0], w1 = cw[1], w2 = cw[2];  // (slice_end, slice0, per, n_sites) (entry0, inv, sh, kind) (n_out, thr)
         const uint32_t s0 = (sl - w0.y) * w0.z;
         const uint32_t total = min(w0.z, w0.w - s0) << p.log_s;  // trials of the slice (<= 2^30)
-        const uint32_t n_out = w2.x, ebase = w1.x + s0 * n_out, inv = w1.y, sh = w1.z, kind = w1.w;
+        const uint32_t n_out = w2.x, inv = w1.y, sh = w1.z, kind = w1.w;
         const uint32_t t0 = w2.y, t1 = w2.z, t2 = w2.w, thr_off = cls[k].thr_off, dense_thr = cls[k].dense_thr;
+        c_entry0 = w1.x;
+        c_s0 = s0;
+        c_ebase = w1.x + s0 * n_out;
+        if (PERIODIC) {
+            const uint4 w4 = cw[4];
+            c_a = w4.x;
+            c_p = w4.y;
+            c_n = w4.z;
+            c_delta = w4.w;
+        }
 
         if (dense_thr != 0) {
             // Dense class: the trials of the slice as packed Bernoulli words, 32 trials per lane and pass. A word with
@@ -413,8 +457,9 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
                             }
                         }
                     }
-                    const uint4 e = __ldg(p.entries + (ebase + site * n_out + o));
-                    apply(e, rowbase_m + shot * main_bits, rowbase_o + shot * obs_bits);
+                    uint32_t shift = 0;
+                    const uint4 e = __ldg(p.entries + entry_of(site, n_out, o, &shift));
+                    apply(e, rowbase_m + shot * main_bits, rowbase_o + shot * obs_bits, shift);
                 }
             }
             __syncwarp();
@@ -458,8 +503,8 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
             const uint32_t off0 = excl + G[0], off1 = excl + s_a + G[1];
             const bool ok0 = off0 < rem, ok1 = ok0 && off1 < rem;
             // last step's events first (their entries have arrived by now), then this step's loads take their place
-            apply(pend0, pm0, po0);
-            apply(pend1, pm1, po1);
+            apply(pend0, pm0, po0, ps0);
+            apply(pend1, pm1, po1, ps1);
             pend0.x = pend0.y = pend0.z = pend0.w = RESP_NONE;
             pend1 = pend0;
 #pragma unroll
@@ -479,11 +524,14 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
                     }
                 }
                 if (ok) {
-                    const uint4 e = __ldg(p.entries + (ebase + site * n_out + o));
+                    uint32_t shift = 0;
+                    const uint4 e = __ldg(p.entries + entry_of(site, n_out, o, &shift));
                     if (h) {
                         pend1 = e;
+                        ps1 = shift;
                     } else {
                         pend0 = e;
+                        ps0 = shift;
                     }
                 }
                 if (h) {
@@ -554,7 +602,7 @@ uint32_t align16(uint32_t v) {
 }
 
 constexpr size_t FIXED_SMEM = 256 * 8 + MAX_CLASSES * sizeof(EvClass) + MAX_BUFFERS * CTL_WORDS * 4;
-static_assert(sizeof(EvClass) == 64 && FIXED_SMEM % 16 == 0, "shared memory layout");
+static_assert(sizeof(EvClass) == 96 && FIXED_SMEM % 16 == 0, "shared memory layout");
 
 }  // namespace
 
@@ -572,6 +620,8 @@ cudaError_t launch_count_b8(const uint8_t *rows, uint64_t pitch, uint64_t n_shot
 // ------------------------------------------------------------------------------------------------
 // SparseEngine
 // ------------------------------------------------------------------------------------------------
+using SparseEngine_Period = ResponsePeriod;
+
 struct SparseEngine::Impl {
     int device = 0;
     int num_sms = 0;
@@ -585,6 +635,10 @@ struct SparseEngine::Impl {
     void *d_thr = nullptr, *d_classes = nullptr, *d_entries = nullptr, *d_overflow = nullptr, *d_init = nullptr;
     uint32_t n_slices = 0;
     std::vector<uint32_t> slices_host;  // 4 words per slice (tests / oracle)
+    // periodic storage of the device table (tables beyond the L2-friendly size): per class the stored period, or p = 0
+    std::vector<SparseEngine_Period> periods;
+    bool periodic = false;
+    uint64_t device_entries = 0;  // entries in d_entries (after folding the periods)
     ~Impl() {
         for (void *p : {d_thr, d_classes, d_entries, d_overflow, d_init}) {
             if (p) {
@@ -595,7 +649,7 @@ struct SparseEngine::Impl {
 };
 
 SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32_t L, uint32_t M, int device, uint32_t slice_events,
-                           uint32_t tile_buffers)
+                           uint32_t tile_buffers, uint32_t compress_mb)
     : impl(new Impl()) {
     Impl &I = *impl;
     I.rt = std::move(rt);
@@ -637,6 +691,14 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
     }
     const uint32_t S = 1u << I.log_s;
 
+    // Periodic storage: a table that would not stay in L2 (c5: 142 MB) is stored as head + one period + tail per class.
+    I.periods.assign(I.rt.classes.size(), SparseEngine_Period());
+    if (I.rt.entries.size() * 4 > ((size_t)compress_mb << 20) && mode == 0) {
+        for (size_t ci = 0; ci < I.rt.classes.size(); ci++) {
+            I.periods[ci] = find_response_period(I.rt, I.rt.classes[ci], D);
+            I.periodic |= I.periods[ci].p != 0;
+        }
+    }
     // slices: runs of sites with about `slice_events` expected events per tile. A producer warp walks a slice 64 draws at
     // a time, so ~48 events per slice keep most draws of a step useful; circuits with few events per tile get smaller
     // slices so that there is work for every warp (0 = this automatic choice; it is part of the stream's definition).
@@ -667,7 +729,13 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
         d.slice0 = (uint32_t)(I.slices_host.size() / 4);
         d.per = per;
         d.n_sites = c.n_sites;
-        d.entry0 = c.entry0;
+        const SparseEngine_Period &pd = I.periods[cls.size()];
+        d.entry0 = (uint32_t)I.device_entries;  // (== c.entry0 when nothing is folded)
+        d.per_a = pd.a;
+        d.per_p = pd.p;
+        d.per_n = pd.n;
+        d.per_delta = pd.delta;
+        I.device_entries += (uint64_t)(c.n_sites - (pd.p ? pd.n - pd.p : 0)) * c.n_out;
         d.inv = c.inv;
         d.sh = c.sh;
         d.n_out = c.n_out;
@@ -699,9 +767,11 @@ SparseEngine::SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32
     up(&I.d_thr, thr_all.data(), thr_all.size() * 4);
     up(&I.d_classes, cls.data(), cls.size() * sizeof(EvClass));
     up(&I.d_overflow, nullptr, I.rt.overflow.size() * 4);
-    up(&I.d_entries, nullptr, I.rt.entries.size() * 4);
-    ck(cudaFuncSetAttribute(gstim_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_optin), "smem attribute");
-    ck(cudaFuncSetAttribute(gstim_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_optin), "smem attribute");
+    up(&I.d_entries, nullptr, I.device_entries * 16);
+    ck(cudaFuncSetAttribute(gstim_sparse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_optin), "smem attribute");
+    ck(cudaFuncSetAttribute(gstim_sparse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_optin), "smem attribute");
+    ck(cudaFuncSetAttribute(gstim_sparse_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_optin), "smem attribute");
+    ck(cudaFuncSetAttribute(gstim_sparse_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I.smem_optin), "smem attribute");
 }
 
 SparseEngine::~SparseEngine() {
@@ -713,6 +783,9 @@ const ResponseTable &SparseEngine::table() const {
 }
 uint32_t SparseEngine::tile_shots() const {
     return 1u << impl->log_s;
+}
+uint64_t SparseEngine::device_table_entries() const {
+    return impl->device_entries;
 }
 uint32_t SparseEngine::blocks_per_sm() const {
     return 1;
@@ -819,6 +892,24 @@ void SparseEngine::set_layout(uint32_t flags, cudaStream_t stream) {
         }
         memcpy(&ent[e], o, 16);
     }
+    if (I.periodic) {
+        // fold the periods: per class keep the sites before the end of the first period and the sites behind the range
+        std::vector<uint32_t> folded;
+        folded.reserve(I.device_entries * 4);
+        for (size_t ci = 0; ci < I.rt.classes.size(); ci++) {
+            const RespClass &c = I.rt.classes[ci];
+            const SparseEngine_Period &pd = I.periods[ci];
+            const uint32_t *src = ent.data() + (size_t)c.entry0 * 4;
+            const size_t per_site = (size_t)c.n_out * 4;
+            if (pd.p == 0) {
+                folded.insert(folded.end(), src, src + c.n_sites * per_site);
+            } else {
+                folded.insert(folded.end(), src, src + (size_t)(pd.a + pd.p) * per_site);
+                folded.insert(folded.end(), src + (size_t)(pd.a + pd.n) * per_site, src + c.n_sites * per_site);
+            }
+        }
+        ent.swap(folded);
+    }
     ck(cudaSetDevice(I.device), "cudaSetDevice");
     ck(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
     if (!ent.empty()) {
@@ -881,10 +972,18 @@ void SparseEngine::launch(uint64_t first_shot, uint64_t n_shots, uint8_t *main_o
     }
     const size_t smem = FIXED_SMEM + (size_t)p.n_buffers * p.img_bytes;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)I.num_sms);
+    p.det_lo = (I.mode == 0 && (I.layout_flags & 0x02u)) ? I.L : 0;  // prepended observables come first
+    p.n_det = I.mode == 0 ? I.D : 0;
     if (I.obs_bits) {
-        gstim_sparse_kernel<true><<<grid, SPARSE_THREADS, smem, stream>>>(p);
+        if (I.periodic) {
+            gstim_sparse_kernel<true, true><<<grid, SPARSE_THREADS, smem, stream>>>(p);
+        } else {
+            gstim_sparse_kernel<true, false><<<grid, SPARSE_THREADS, smem, stream>>>(p);
+        }
+    } else if (I.periodic) {
+        gstim_sparse_kernel<false, true><<<grid, SPARSE_THREADS, smem, stream>>>(p);
     } else {
-        gstim_sparse_kernel<false><<<grid, SPARSE_THREADS, smem, stream>>>(p);
+        gstim_sparse_kernel<false, false><<<grid, SPARSE_THREADS, smem, stream>>>(p);
     }
     ck(cudaGetLastError(), "gstim_sparse_kernel launch");
 }

@@ -9,19 +9,16 @@
 
 namespace gstim {
 
-struct SparseClassDev {  // 80 bytes
-    uint32_t inv, sh, kind, n_out;
-    uint32_t thr[15];
-    uint32_t pad;
-};
-
 // Owns the device copy of a response table and launches the sampling kernel. Not thread-safe (like the sampler handle).
 class SparseEngine {
   public:
     // slice_events: expected events per slice and tile (part of the random stream's definition; 0 = automatic)
     // tile_buffers: tile images a block should be able to hold (decides the tile height; 0 = default 3)
+    // compress_mb: tables larger than this many MB are stored periodically (per class: head + one period + tail) when the
+    // circuit has a round structure
     SparseEngine(ResponseTable &&rt, uint32_t mode, uint32_t D, uint32_t L, uint32_t M, int device, uint32_t slice_events,
-                 uint32_t tile_buffers);
+                 uint32_t tile_buffers, uint32_t compress_mb);
+    uint64_t device_table_entries() const;  // entries stored on the device (after folding)
     ~SparseEngine();
     SparseEngine(const SparseEngine &) = delete;
     SparseEngine &operator=(const SparseEngine &) = delete;

@@ -133,3 +133,31 @@ def test_dense_classes_use_packed_bernoulli_words():
     np.testing.assert_allclose(out.mean(axis=0), [0.5, 0.25, 0.3, 0.5, 0.1], atol=0.025)  # DEPOLARIZE1(0.75): X or Y flips the result
     m = stim_b200.response_table("H 0\nM 0\nDETECTOR rec[-1]\n")
     assert len(m["classes"]) == 1 and int(m["classes"][0][23]) == 1 << 31 and (m["site_group"] & 0x80000000).all()
+
+
+@pytest.mark.parametrize("name", ["c2_surface_x_d5_r5", "c3_surface_z_d25_r25"])
+def test_round_structure_folds_the_table_exactly(name):
+    """The periods the device table is folded by (response.h ResponsePeriod): every site of a folded range equals its image
+    in the first period with the detector ids shifted; c3 folds 8x (one of 25 rounds is stored)."""
+    with open(os.path.join(ROOT, "tests", "golden", "circuits", name + ".stim")) as f:
+        text = f.read()
+    t = stim_b200.response_table(text)
+    D = stim_b200.Circuit(text).num_detectors
+    rng = np.random.default_rng(1)
+    kept = 0
+    for c, (a, p, n, delta) in zip(t["classes"], t["periods"].astype(np.int64)):
+        n_out, n_sites, entry0 = int(c[5]), int(c[21]), int(c[22])
+        kept += n_out * (n_sites - (n - p if p else 0))
+        if p == 0:
+            continue
+        assert n >= 3 * p and a + n <= n_sites and delta > 0
+        sites = np.arange(a + p, a + n)
+        if sites.size > 3000:
+            sites = np.concatenate([sites[:50], sites[-50:], rng.choice(sites, 2900, replace=False)])
+        for s in sites:
+            k, img = divmod(int(s) - a, p)
+            for o in range(n_out):
+                want = [v + k * delta if v < D else v for v in so.entry_ids(t, entry0 + (a + img) * n_out + o)]
+                assert so.entry_ids(t, entry0 + int(s) * n_out + o) == want, (int(c[4]), int(s), o)
+    if name.startswith("c3"):
+        assert kept * 8 < len(t["entries"])
