@@ -229,6 +229,11 @@ int gstim_dem_set_shot_offset(gstim_dem_sampler *s, uint64_t offset);
  * (the reference's return_errors / --err_out). Replaying recorded errors (--replay_err_in) is not supported. */
 int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void *dets_out, int64_t dets_stride, void *obs_out,
                      int64_t obs_stride, void *errs_out, int64_t errs_stride);
+/* A detector error model is a response table (one site per error mechanism, classes of equal probability): unless the
+ * fired errors are asked for (errs_out / err_fd), the model is sampled by the event engine (GSTIM_ENGINE=interp switches
+ * that off). Arrays of the table as in gstim_get_response_table (site_group = index of the mechanism in the flattened
+ * model); what = 8: one word, the tile height. */
+int gstim_dem_get_response_table(gstim_dem_sampler *s, int what, uint32_t *words, size_t *n_words);
 /* Flip counts of the D + L output bits (detectors, then observables) and of adjacent pairs over `shots` fresh shots,
  * reduced on the device (the statistic of the parity tests; see gstim_bit_counts). pair_host may be NULL. */
 int gstim_dem_bit_counts(gstim_dem_sampler *s, uint64_t shots, uint64_t *single_host, uint64_t *pair_host);

@@ -857,7 +857,7 @@ void sample_to_host(
         uint64_t first = 0, n = 0;
     } pending[2];
     auto scatter_rows = [&](const uint8_t *src, uint64_t src_bytes, uint32_t n_bits, uint8_t *dst0, uint64_t pitch, uint64_t n) {
-        const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         const unsigned nt = n * src_bytes < (1u << 20) ? 1u : hw;
         auto work = [&](uint64_t a, uint64_t b) {
             for (uint64_t i = a; i < b; i++) {
@@ -1280,6 +1280,12 @@ void export_table_array(const ResponseTable &rt, const std::vector<uint32_t> *sl
 }
 
 }  // namespace
+
+// (used by dem.cu) copies one array of a response table, see gstim_get_response_table
+void gstim_export_table_array(const ResponseTable &rt, const std::vector<uint32_t> *slices, uint32_t n_det, int what, uint32_t *words,
+                              size_t *n_words) {
+    export_table_array(rt, slices, n_det, what, words, n_words);
+}
 
 // (used by dem.cu: one error channel for the whole library)
 void gstim_set_last_error(const char *msg) {

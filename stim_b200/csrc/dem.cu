@@ -35,6 +35,7 @@
 #include "../../include/gstim.h"
 #include "kernels.cuh"
 #include "lowering.h"
+#include "sparse.cuh"
 #include "writers.h"
 
 #define GSTIM_TABLE_QUAL __device__ const
@@ -420,6 +421,12 @@ struct gstim_dem_sampler {
     uint64_t seed = 0;
     uint64_t next_col = 0;
     DemModel model;
+    // Event engine (sparse.cu): a detector error model IS a response table (one site per error mechanism, its targets the
+    // response). Used whenever the fired errors themselves are not asked for; built on first use, null if not possible
+    // (more than 64 distinct probabilities, rows beyond shared memory).
+    std::unique_ptr<SparseEngine> events;
+    bool events_tried = false;
+    int engine_pref = GSTIM_ENGINE_AUTO;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     DevMem d_rates, d_tgt_off, d_tgt_row, d_table, d_rowmap, d_stage;
@@ -432,6 +439,8 @@ struct gstim_dem_sampler {
 
 // (gstim_last_error lives in api.cu; DEM errors are reported through the same thread-local channel)
 void gstim_set_last_error(const char *msg);
+void gstim_export_table_array(const gstim::ResponseTable &rt, const std::vector<uint32_t> *slices, uint32_t n_det, int what, uint32_t *words,
+                              size_t *n_words);
 
 namespace {
 
@@ -449,6 +458,163 @@ int dem_guarded(F &&f) {
     } catch (const std::exception &e) {
         gstim_set_last_error(e.what());
         return std::string(e.what()).rfind("CUDA", 0) == 0 ? GSTIM_ERR_CUDA : GSTIM_ERR_INTERNAL;
+    }
+}
+
+// The model as a response table: mechanisms grouped into classes of equal probability (ascending), model order inside a
+// class, one outcome each, response = detector ids then D + observable ids (a target named twice cancels).
+ResponseTable dem_response_table(const DemModel &m) {
+    ResponseTable rt;
+    rt.n_outputs = (uint32_t)(m.num_detectors + m.num_observables);
+    const size_t E = m.probs.size();
+    std::vector<uint64_t> keys(E);
+    std::vector<uint32_t> order;
+    for (size_t e = 0; e < E; e++) {
+        keys[e] = gstim_rate_key(m.probs[e]);
+        if (keys[e] != 0) {
+            order.push_back((uint32_t)e);
+        }
+    }
+    auto lam_of = [](double p) -> uint64_t {
+        const float f = (float)p;
+        if (f >= 1) {
+            return 1ull << 62;
+        }
+        return (uint64_t)std::ldexp(-std::log1p(-(double)f), 56);
+    };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return lam_of(m.probs[a]) < lam_of(m.probs[b]); });
+    std::vector<uint32_t> ids;
+    for (size_t i = 0; i < order.size();) {
+        const uint32_t e0 = order[i];
+        RespClass rc;
+        rc.lam = lam_of(m.probs[e0]);
+        rc.inv = (keys[e0] & (1ull << 63)) && (float)m.probs[e0] < 1 ? (uint32_t)((keys[e0] & ~(1ull << 63)) >> 8) : 0u;
+        rc.sh = (float)m.probs[e0] < 1 ? (uint32_t)(keys[e0] & 0xFF) : 0u;
+        rc.kind = RK_SINGLE;
+        rc.n_out = 1;
+        rc.entry0 = (uint32_t)(rt.entries.size() / 4);
+        const double pr = rc.lam >= (1ull << 62) ? 1.0 : -std::expm1(-std::ldexp((double)rc.lam, -56));
+        size_t j = i;
+        while (j < order.size() && lam_of(m.probs[order[j]]) == rc.lam) {
+            const uint32_t e = order[j];
+            ids.clear();
+            for (uint32_t k = m.tgt_off[e]; k < m.tgt_off[e + 1]; k++) {
+                const uint32_t t = m.tgt[k];
+                ids.push_back((t & 0x80000000u) ? (uint32_t)m.num_detectors + (t & 0x7FFFFFFFu) : t);
+            }
+            std::sort(ids.begin(), ids.end());
+            size_t n = 0;
+            for (size_t a = 0; a < ids.size(); a++) {  // pairs cancel
+                if (a + 1 < ids.size() && ids[a] == ids[a + 1]) {
+                    a++;
+                    continue;
+                }
+                ids[n++] = ids[a];
+            }
+            ids.resize(n);
+            uint32_t w[4] = {RESP_NONE, RESP_NONE, RESP_NONE, RESP_NONE};
+            if (n <= 4) {
+                for (size_t a = 0; a < n; a++) {
+                    w[a] = ids[a];
+                }
+            } else {
+                for (size_t a = 0; a < 3; a++) {
+                    w[a] = ids[a];
+                }
+                w[3] = RESP_OVERFLOW | (uint32_t)rt.overflow.size();
+                rt.overflow.push_back((uint32_t)(n - 3));
+                rt.overflow.insert(rt.overflow.end(), ids.begin() + 3, ids.end());
+            }
+            rt.entries.insert(rt.entries.end(), w, w + 4);
+            rt.site_group.push_back(e);  // (provenance: the mechanism's index in the flattened model)
+            rt.site_index.push_back(0);
+            rt.max_response = std::max<uint32_t>(rt.max_response, (uint32_t)n);
+            rt.flips_per_shot += pr * (double)n;
+            rc.n_sites++;
+            j++;
+        }
+        rt.events_per_shot += pr * rc.n_sites;
+        rt.outcome_word.push_back(0);
+        rt.n_sites += rc.n_sites;
+        rt.classes.push_back(rc);
+        i = j;
+    }
+    rt.n_entries = rt.entries.size() / 4;
+    rt.eligible = true;
+    return rt;
+}
+
+// The event engine of a sampler, or null (more than 64 classes / rows too long / switched off).
+SparseEngine *dem_events(gstim_dem_sampler *s) {
+    if (s->engine_pref == GSTIM_ENGINE_INTERPRETER) {
+        return nullptr;
+    }
+    if (!s->events_tried) {
+        s->events_tried = true;
+        const char *env = getenv("GSTIM_ENGINE");
+        if (env != nullptr && (strcmp(env, "interp") == 0 || strcmp(env, "interpreter") == 0)) {
+            return nullptr;
+        }
+        try {
+            const uint32_t D = (uint32_t)s->model.num_detectors, L = (uint32_t)s->model.num_observables;
+            s->events = std::make_unique<SparseEngine>(dem_response_table(s->model), 0u, D, L, 0u, s->device, 0u, 0u, 1u << 20);
+        } catch (const std::invalid_argument &) {
+            s->events.reset();
+        }
+    }
+    return s->events.get();
+}
+
+// Event-engine pass: dense b8 rows [dets | obs appended] per chunk in device staging, handed to sink(first, n, rows, pitch).
+template <typename SINK>
+void dem_run_events(gstim_dem_sampler *s, SparseEngine &E, uint64_t shots, SINK &&sink) {
+    ck(cudaSetDevice(s->device), "cudaSetDevice");
+    if (shots == 0) {
+        return;
+    }
+    const uint64_t cols = (shots + GSTIM_COL_SHOTS - 1) / GSTIM_COL_SHOTS;
+    if (s->next_col + cols >= (1ull << 47)) {
+        throw std::invalid_argument("shot offset + shots must stay below 2^54");
+    }
+    E.set_layout(GSTIM_APPEND_OBS, s->stream);
+    const uint64_t pitch = (E.main_bits() + 7) / 8;
+    const uint64_t chunk = std::max<uint64_t>(((256ull << 20) / std::max<uint64_t>(pitch, 1)) / GSTIM_COL_SHOTS, 1) * GSTIM_COL_SHOTS;
+    const uint64_t base = s->next_col * GSTIM_COL_SHOTS;
+    for (uint64_t first = 0; first < shots; first += chunk) {
+        const uint64_t n = std::min(chunk, shots - first);
+        s->d_stage.ensure(n * pitch + 16);
+        try {
+            E.launch(base + first, n, (uint8_t *)s->d_stage.p, pitch, nullptr, 0, s->seed, s->stream);
+        } catch (const std::runtime_error &e) {
+            throw std::runtime_error(std::string("CUDA: ") + e.what());
+        }
+        sink(first, n, (const uint8_t *)s->d_stage.p, pitch);
+    }
+    ck(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize");
+    s->next_col += cols;
+}
+
+// bits [bit0, bit0 + n_bits) of packed rows -> packed (or one byte per bit) rows of the caller
+void dem_slice_rows(const uint8_t *rows, uint64_t pitch, uint64_t n, uint32_t bit0, uint32_t n_bits, bool packed, uint8_t *dst0, uint64_t dst_pitch) {
+    const uint64_t out_bytes = (n_bits + 7) / 8;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *r = rows + i * pitch;
+        uint8_t *dst = dst0 + i * dst_pitch;
+        if (!packed) {
+            for (uint32_t b = 0; b < n_bits; b++) {
+                dst[b] = (r[(bit0 + b) >> 3] >> ((bit0 + b) & 7)) & 1;
+            }
+        } else if ((bit0 & 7) == 0) {
+            memcpy(dst, r + (bit0 >> 3), out_bytes);
+            if (n_bits & 7) {
+                dst[out_bytes - 1] &= (uint8_t)((1u << (n_bits & 7)) - 1);
+            }
+        } else {
+            memset(dst, 0, out_bytes);
+            for (uint32_t b = 0; b < n_bits; b++) {
+                dst[b >> 3] |= (uint8_t)(((r[(bit0 + b) >> 3] >> ((bit0 + b) & 7)) & 1) << (b & 7));
+            }
+        }
     }
 }
 
@@ -632,6 +798,23 @@ int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void 
         const uint32_t D = (uint32_t)m.num_detectors, L = (uint32_t)m.num_observables, E = (uint32_t)m.probs.size();
         DemOut outs[3] = {{(uint8_t *)dets_out, dets_stride, 0, D}, {(uint8_t *)obs_out, obs_stride, D, L}, {(uint8_t *)errs_out, errs_stride, D + L, E}};
         std::vector<uint8_t> host;
+        SparseEngine *ev = errs_out == nullptr ? dem_events(s) : nullptr;
+        if (ev != nullptr) {
+            dem_run_events(s, *ev, shots, [&](uint64_t first, uint64_t n, const uint8_t *rows, uint64_t pitch) {
+                host.resize(n * pitch + 1);
+                ck(cudaMemcpyAsync(host.data(), rows, n * pitch, cudaMemcpyDeviceToHost, s->stream), "D2H");
+                ck(cudaStreamSynchronize(s->stream), "sync");
+                for (int k = 0; k < 2; k++) {
+                    const DemOut &o = outs[k];
+                    if (o.ptr == nullptr || o.n_bits == 0) {
+                        continue;
+                    }
+                    const uint64_t row = packed ? (o.n_bits + 7) / 8 : o.n_bits, dp = o.stride ? (uint64_t)o.stride : row;
+                    dem_slice_rows(host.data(), pitch, n, o.row0, o.n_bits, packed, o.ptr + first * dp, dp);
+                }
+            });
+            return;
+        }
         dem_run(s, shots, errs_out != nullptr, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
             for (const DemOut &o : outs) {
                 if (o.ptr == nullptr || o.n_bits == 0) {
@@ -655,6 +838,27 @@ int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void 
     });
 }
 
+int gstim_dem_get_response_table(gstim_dem_sampler *s, int what, uint32_t *words, size_t *n_words) {
+    return dem_guarded([&] {
+        if (s == nullptr || n_words == nullptr) {
+            throw std::invalid_argument("NULL argument.");
+        }
+        ck(cudaSetDevice(s->device), "cudaSetDevice");
+        SparseEngine *ev = dem_events(s);
+        if (ev == nullptr) {
+            throw std::invalid_argument("This model is not sampled by the event engine.");
+        }
+        if (what == 8) {  // tile height
+            if (words != nullptr && *n_words >= 1) {
+                words[0] = ev->tile_shots();
+            }
+            *n_words = 1;
+            return;
+        }
+        gstim_export_table_array(ev->table(), &ev->slices(), (uint32_t)s->model.num_detectors, what, words, n_words);
+    });
+}
+
 int gstim_dem_bit_counts(gstim_dem_sampler *s, uint64_t shots, uint64_t *single_host, uint64_t *pair_host) {
     return dem_guarded([&] {
         if (s == nullptr) {
@@ -666,6 +870,11 @@ int gstim_dem_bit_counts(gstim_dem_sampler *s, uint64_t shots, uint64_t *single_
         counts.ensure((size_t)std::max<uint32_t>(n, 1) * 16);
         ck(cudaMemsetAsync(counts.p, 0, (size_t)std::max<uint32_t>(n, 1) * 16, s->stream), "memset");
         unsigned long long *d_single = (unsigned long long *)counts.p, *d_pair = d_single + n;
+        if (SparseEngine *ev = dem_events(s)) {
+            dem_run_events(s, *ev, shots, [&](uint64_t, uint64_t cnt, const uint8_t *rows, uint64_t pitch) {
+                ck(launch_count_b8(rows, pitch, cnt, n, d_single, pair_host ? d_pair : nullptr, s->stream), "bit counts");
+            });
+        } else
         dem_run(s, shots, false, [&](uint64_t first, uint64_t cnt, const uint32_t *table, uint64_t n_rows) {
             (void)first;
             ck(launch_bit_counts(table, n_rows, cnt, nullptr, n, d_single, pair_host ? d_pair : nullptr, s->stream), "bit counts");
@@ -712,6 +921,42 @@ int gstim_dem_sample_to_fd(gstim_dem_sampler *s, uint64_t shots, int det_fd, con
         std::vector<uint8_t> host;
         std::vector<uint32_t> host_table, map;
         try {
+            SparseEngine *ev = err_fd < 0 ? dem_events(s) : nullptr;
+            if (ev != nullptr) {
+                std::vector<uint8_t> part;
+                dem_run_events(s, *ev, shots, [&](uint64_t, uint64_t n, const uint8_t *rows, uint64_t pitch) {
+                    host.resize(n * pitch + 1);
+                    ck(cudaMemcpyAsync(host.data(), rows, n * pitch, cudaMemcpyDeviceToHost, s->stream), "D2H");
+                    ck(cudaStreamSynchronize(s->stream), "sync");
+                    for (Sink &k : sinks) {
+                        if (!k.f) {
+                            continue;
+                        }
+                        const uint64_t bytes = (k.o.n_bits + 7) / 8;
+                        part.assign(n * bytes + 1, 0);
+                        dem_slice_rows(host.data(), pitch, n, k.o.row0, k.o.n_bits, true, part.data(), bytes);
+                        if (k.format == Format::PTB64) {
+                            // bit-major rows for the ptb64 writer
+                            const size_t n_cols = (n + 127) / 128;
+                            host_table.assign(n_cols * (size_t)std::max<uint32_t>(k.o.n_bits, 1) * 4, 0);
+                            map.resize(k.o.n_bits);
+                            for (uint64_t sh = 0; sh < n; sh++) {
+                                for (uint32_t b = 0; b < k.o.n_bits; b++) {
+                                    if ((part[sh * bytes + (b >> 3)] >> (b & 7)) & 1) {
+                                        host_table[((sh >> 7) * k.o.n_bits + b) * 4 + ((sh >> 5) & 3)] |= 1u << (sh & 31);
+                                    }
+                                }
+                            }
+                            for (uint32_t b = 0; b < k.o.n_bits; b++) {
+                                map[b] = b;
+                            }
+                            write_ptb64(k.f, host_table.data(), k.o.n_bits, map.data(), map.size(), n);
+                        } else {
+                            write_shots(k.f, part.data(), bytes, n, k.o.n_bits, k.format, k.prefix, k.prefix, k.o.n_bits);
+                        }
+                    }
+                });
+            } else
             dem_run(s, shots, err_fd >= 0, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
                 (void)first;
                 for (Sink &k : sinks) {  // (the reference writes errors, then observables, then detectors: dem_sampler.inl:98-127)

@@ -87,6 +87,21 @@ class CompiledDemSampler:
             self._handle, shots, _native.BIT_PACKED if bit_packed else 0, ptr(dets), 0, ptr(obs), 0, ptr(errs), 0))
         return dets, obs, errs
 
+    def response_table(self) -> dict:
+        """Arrays of the event engine's table for this model (gstim_dem_get_response_table) + "tile_shots", for the oracle."""
+        out = {}
+        for what, name in [(0, "classes"), (1, "entries"), (2, "overflow"), (3, "site_group"), (6, "slices"), (8, "tile")]:
+            n = ctypes.c_size_t(0)
+            _native.check(_native.lib().gstim_dem_get_response_table(self._handle, what, None, ctypes.byref(n)))
+            a = np.zeros(max(n.value, 1), dtype=np.uint32)
+            _native.check(_native.lib().gstim_dem_get_response_table(self._handle, what, a.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n)))
+            out[name] = a[:n.value]
+        out["classes"] = out["classes"].reshape(-1, 24)
+        out["entries"] = out["entries"].reshape(-1, 4)
+        out["slices"] = out["slices"].reshape(-1, 4)
+        out["tile_shots"] = int(out.pop("tile")[0])
+        return out
+
     def bit_counts(self, shots: int):
         """(single[D + L], pair[D + L - 1]) uint64 flip counts over `shots` fresh shots, reduced on the device."""
         n = self._dem.num_detectors + self._dem.num_observables

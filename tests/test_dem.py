@@ -140,3 +140,38 @@ def test_dem_statistics_match_reference(name, fixture):
     check(single[:D], n, ref["single"], n_ref, name + " detector rates")
     check(pair[: D - 1], n, ref["pair"], n_ref, name + " adjacent-pair correlations")
     check(single[D:], n, ref["obs"], n_ref, name + " observable rates")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shots", [1, 300, 4096 + 77])
+def test_cuda_dem_sampler_on_the_event_engine_equals_oracle(shots):
+    """Without return_errors the model is sampled by the event engine: its table must be the model itself (one site per
+    mechanism, response = targets) and the shots must equal oracle/sparse_oracle.sample on that table."""
+    from oracle import sparse_oracle as so
+
+    s = stim_b200.DetectorErrorModel(NOISY).compile_sampler(seed=7)
+    D, L, errors = do.parse_dem(NOISY)
+    t = s.response_table()
+    site = 0
+    for c in t["classes"]:
+        for k in range(int(c[21])):
+            e = int(t["site_group"][site])
+            p, tg = errors[e]
+            want = sorted(x if not isinstance(x, tuple) else D + x[1] for x in tg)
+            want = [v for v in set(want) if want.count(v) % 2]
+            assert so.entry_ids(t, int(c[22]) + k) == sorted(want), e
+            site += 1
+    assert site == sum(1 for p, _ in errors if p > 0)
+    dets, obs, errs = s.sample(shots)
+    assert errs is None
+    rows = so.sample(t, t["slices"], t["tile_shots"], 7, 0, shots, D + L)
+    np.testing.assert_array_equal(dets.astype(np.uint8), rows[:, :D])
+    np.testing.assert_array_equal(obs.astype(np.uint8), rows[:, D:])
+    # packed output and the stream continuing across calls
+    s2 = stim_b200.DetectorErrorModel(NOISY).compile_sampler(seed=7)
+    pd, po, _ = s2.sample(shots, bit_packed=True)
+    np.testing.assert_array_equal(np.unpackbits(pd, axis=1, bitorder="little")[:, :D], rows[:, :D])
+    np.testing.assert_array_equal(np.unpackbits(po, axis=1, bitorder="little")[:, :L], rows[:, D:])
+    more = s2.sample(200)[0]
+    first = (shots + 127) // 128 * 128
+    np.testing.assert_array_equal(more.astype(np.uint8), so.sample(t, t["slices"], t["tile_shots"], 7, first, 200, D + L)[:, :D])
