@@ -552,38 +552,105 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
 }
 
 // ------------------------------------------------------------------------------------------------
-// flip counts of dense b8 rows: single[b] += popcount over shots of bit b, pair[b] += bit b AND bit b + 1
+// flip counts of dense b8 rows: single[b] += number of shots with bit b set, pair[b] += bit b AND bit b + 1
 // (the statistics the 5-sigma tests and the per-detector count allreduce use; the reference has no such kernel — it is
 // what a caller computes from the b8 array).
+// A thread owns one 32-bit column of the rows (bits 32 j .. 32 j + 31) over a run of shots and counts all 32 bits at once
+// in bit-sliced ("vertical") counters: eight bit planes, plane k holding bit k of every column bit's count, advanced by a
+// ripple-carry add of the shot's word; every 255 shots the planes are folded into the global counters. Rows may start at
+// any byte (c3: 1951 B pitch): the word is assembled from two aligned loads with a funnel shift.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gstim_count_b8_kernel(const uint8_t *rows, uint64_t pitch, uint64_t n_shots, uint32_t n_bits,
-                                                            unsigned long long *single, unsigned long long *pair) {
-    const uint32_t n_bytes = (n_bits + 7) / 8;
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_bytes) {
-        return;
+__device__ __forceinline__ void vadd(uint32_t (&c)[8], uint32_t w) {
+    uint32_t carry = w;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t t = c[k] & carry;
+        c[k] ^= carry;
+        carry = t;
     }
-    const uint64_t per = (n_shots + gridDim.y - 1) / gridDim.y;
-    const uint64_t s0 = (uint64_t)blockIdx.y * per, s1 = min(n_shots, s0 + per);
-    uint32_t c1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const bool has_next = j + 1 < n_bytes;
-    for (uint64_t s = s0; s < s1; s++) {
-        const uint8_t *row = rows + s * pitch;
-        const uint32_t b = row[j] | (has_next ? (uint32_t)row[j + 1] << 8 : 0u);
+}
+__device__ __forceinline__ void vflush(uint32_t (&c)[8], unsigned long long *dst, uint32_t bit0, uint32_t n_bits) {
+#pragma unroll 4
+    for (uint32_t b = 0; b < 32; b++) {
+        uint32_t v = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            c1[k] += (b >> k) & 1u;
-            c2[k] += (b >> k) & (b >> (k + 1)) & 1u;
+            v |= ((c[k] >> b) & 1u) << k;
+        }
+        if (v != 0 && bit0 + b < n_bits) {
+            atomicAdd(dst + bit0 + b, (unsigned long long)v);
         }
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const uint32_t bit = j * 8 + k;
-        if (bit < n_bits && c1[k]) {
-            atomicAdd(single + bit, (unsigned long long)c1[k]);
+        c[k] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(128) gstim_count_b8_kernel(const uint8_t *rows, uint64_t pitch, uint64_t n_shots, uint32_t n_bits,
+                                                            unsigned long long *single, unsigned long long *pair) {
+    const uint32_t n_words = (n_bits + 31) / 32, n_bytes = (n_bits + 7) / 8;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_words) {
+        return;
+    }
+    const uint64_t per = (n_shots + gridDim.y - 1) / gridDim.y;
+    const uint64_t s0 = (uint64_t)blockIdx.y * per, s1 = min(n_shots, s0 + per);
+    const uint32_t valid = n_bits - 32 * j >= 32 ? 0xFFFFFFFFu : ((1u << (n_bits - 32 * j)) - 1u);
+    const uint32_t bytes_here = min(4u, n_bytes - 4 * j);        // bytes of this column that exist in a row
+    const bool has_next = 4 * j + 4 < n_bytes;
+    uint32_t c1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t pending = 0;
+    auto load = [&](uint64_t s, uint32_t *w, uint32_t *nxt) {
+        const uint8_t *a = rows + s * pitch + 4 * j;
+        if (bytes_here == 4) {
+            const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
+            const uint32_t *al = reinterpret_cast<const uint32_t *>(ai & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(ai & 3) * 8;
+            *w = sh == 0 ? al[0] : __funnelshift_r(al[0], al[1], sh);  // (the rows' buffer has 16 spare bytes behind it)
+        } else {
+            *w = 0;
+            for (uint32_t k = 0; k < bytes_here; k++) {
+                *w |= (uint32_t)a[k] << (8 * k);
+            }
         }
-        if (pair != nullptr && bit + 1 < n_bits && c2[k]) {
-            atomicAdd(pair + bit, (unsigned long long)c2[k]);
+        *w &= valid;
+        *nxt = (pair != nullptr && has_next) ? (uint32_t)(a[4] & 1u) : 0u;
+    };
+    auto add = [&](uint32_t w, uint32_t nxt) {
+        vadd(c1, w);
+        if (pair != nullptr) {
+            vadd(c2, w & ((w >> 1) | (nxt << 31)));
+        }
+        if (++pending == 255) {
+            vflush(c1, single, 32 * j, n_bits);
+            if (pair != nullptr) {
+                vflush(c2, pair, 32 * j, n_bits - 1);
+            }
+            pending = 0;
+        }
+    };
+    uint64_t s = s0;
+    for (; s + 8 <= s1; s += 8) {  // eight rows in flight per thread: the loop is bound by load latency otherwise
+        uint32_t w[8], nx[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            load(s + u, &w[u], &nx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            add(w[u], nx[u]);
+        }
+    }
+    for (; s < s1; s++) {
+        uint32_t w, nx;
+        load(s, &w, &nx);
+        add(w, nx);
+    }
+    if (pending) {
+        vflush(c1, single, 32 * j, n_bits);
+        if (pair != nullptr) {
+            vflush(c2, pair, 32 * j, n_bits - 1);
         }
     }
 }
@@ -611,8 +678,10 @@ cudaError_t launch_count_b8(const uint8_t *rows, uint64_t pitch, uint64_t n_shot
     if (n_bits == 0 || n_shots == 0) {
         return cudaSuccess;
     }
-    const uint32_t n_bytes = (n_bits + 7) / 8;
-    dim3 grid((n_bytes + 127) / 128, (unsigned)std::min<uint64_t>((n_shots + 255) / 256, 4096));
+    // (the buffer holding `rows` must have 4 readable bytes behind its last row: the library's staging buffers have 16)
+    const uint32_t n_words = (n_bits + 31) / 32;
+    const unsigned gx = (n_words + 127) / 128;
+    dim3 grid(gx, (unsigned)std::min<uint64_t>((n_shots + 1019) / 1020, std::max<uint64_t>(1, 148ull * 64 / gx)));
     gstim_count_b8_kernel<<<grid, 128, 0, stream>>>(rows, pitch, n_shots, n_bits, single, pair);
     return cudaGetLastError();
 }
