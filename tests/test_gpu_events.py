@@ -246,3 +246,46 @@ def test_dense_noise_takes_the_packed_word_path_and_matches_oracle_and_interpret
     z = (ev.astype(np.float64) - it.astype(np.float64)) / shots / np.sqrt(np.maximum(p * (1 - p), 1e-12) * 2 / shots)
     assert np.abs(z).max() < 5.0, z
     np.testing.assert_allclose(ev[:2] / shots, [0.5, 0.5], atol=0.003)
+
+
+def test_sinter_shaped_consumer_counts_on_the_device():
+    """stim_b200.sinter_hook.StimThenDecodeSampler = sinter's sample -> decode -> count loop with the shots left on the GPU.
+    Its counts must equal the reference loop restated in numpy (_stim_then_decode_sampler.py:162-223) over the SAME shots
+    (same seed -> same stream) pulled to the host through sample()."""
+    import torch
+
+    from stim_b200.sinter_hook import StimThenDecodeSampler
+
+    text = gen_circuit("surface_code", "rotated_memory_x", 5, 5, 0.01)
+    circ = stim_b200.Circuit(text)
+    D, L = circ.num_detectors, circ.num_observables
+    shots = 50_000
+    rng = np.random.default_rng(3)
+    post = np.zeros((D + 7) // 8, dtype=np.uint8)
+    post[:2] = 0x0F  # post-select on the first few detectors
+    weights = rng.integers(0, 256, size=(D + 7) // 8, dtype=np.uint8)
+
+    def decoder(dets):
+        # a stand-in decoder that runs on the device: predicts the observable as a fixed parity of the detection events
+        assert isinstance(dets, torch.Tensor) and dets.is_cuda
+        w = torch.as_tensor(weights, device=dets.device)
+        v = dets & w
+        par = torch.zeros(dets.shape[0], dtype=torch.uint8, device=dets.device)
+        for b in range(8):
+            par ^= ((v >> b) & 1).sum(dim=1).to(torch.uint8) & 1
+        return par.reshape(-1, 1)
+
+    stats = StimThenDecodeSampler(circ, decoder, count_detection_events=True, postselection_mask=post, seed=44).sample(shots)
+    # the reference loop on the host
+    dets, obs = circ.compile_detector_sampler(seed=44).sample(shots, bit_packed=True, separate_observables=True)
+    n_events = sum(int(np.count_nonzero(dets & (1 << b))) for b in range(8))
+    discarded = np.any(dets & post, axis=1)
+    kept_d, kept_o = dets[~discarded], obs[~discarded]
+    pred = np.zeros(kept_d.shape[0], dtype=np.uint8)
+    v = kept_d & weights
+    for b in range(8):
+        pred ^= (((v >> b) & 1).sum(axis=1) & 1).astype(np.uint8)
+    errors = int(np.count_nonzero(np.any((pred.reshape(-1, 1) ^ kept_o) != 0, axis=1)))
+    assert stats.shots == shots and stats.discards == int(discarded.sum()) and stats.errors == errors
+    assert stats.custom_counts["detection_events"] == n_events and stats.custom_counts["detectors_checked"] == D * shots
+    assert 0 < stats.discards < shots and 0 < stats.errors < shots
