@@ -148,6 +148,22 @@ struct gstim_sampler {
     int last_engine = GSTIM_ENGINE_INTERPRETER;
     bool sparse_favoured = false;  // the cost model's choice for GSTIM_ENGINE_AUTO
 
+    // sparse host delivery (sample_to_host_sparse): three pipeline slots
+    struct SparseSlot {
+        DevBuf d_rows, d_strm, d_idx, d_ctl;   // dense rows (+ obs rows), record stream, per-shot offsets, cursor + overflow flag
+        PinnedBuf h_strm, h_idx, h_ctl, h_obs;
+        cudaEvent_t ev_kernels = nullptr, ev_copy = nullptr;
+        uint64_t first = 0, n = 0;
+        int state = 0;  // 0 free, 1 kernels enqueued, 2 copy enqueued
+        ~SparseSlot() {
+            if (ev_kernels) {
+                cudaEventDestroy(ev_kernels);
+                cudaEventDestroy(ev_copy);
+            }
+        }
+    } sparse_slot[3];
+    int last_d2h_sparse = 0;
+
     // multi-device sampler (gstim_create_from_text_multi): samplers of the other devices; host-output calls split their
     // shots over all of them
     std::vector<gstim_sampler *> peers;
@@ -808,6 +824,197 @@ void unpack_bits(const uint8_t *packed, size_t n_bits, uint8_t *out) {
     }
 }
 
+// Host delivery of event-engine results as SPARSE records (sparse.cu "Sparse host delivery"): per chunk the GPU rewrites the
+// dense rows as (count, offsets, values) of their non-zero bytes, only those cross PCIe, and host threads rebuild the caller's
+// rows (memset + scatter). Three chunks are in flight: kernels of chunk k, the copy of chunk k - 1, the rebuild of chunk k - 2.
+// Returns false (nothing sampled) when the path does not apply.
+bool sample_to_host_sparse(
+    gstim_sampler *s, uint64_t shots, const RowMaps &maps, uint32_t layout_flags, bool bit_packed, uint8_t *main_out, uint64_t main_pitch,
+    uint8_t *obs_out, uint64_t obs_pitch) {
+    const uint32_t nb_main = (uint32_t)maps.main.size(), nb_obs = (uint32_t)maps.obs.size();
+    const uint64_t R = (nb_main + 7) / 8, obs_bytes = (nb_obs + 7) / 8;
+    // Opt-in (GSTIM_D2H=sparse). Measured on the 16-core host of the B200 box (profiles/r2_notes.md): rebuilding c3's rows on
+    // the CPU reaches 11 M shots/s against 28.5 M for the DMA engine writing dense rows - the host's cores and DRAM cannot
+    // zero and patch 32.7 GB per step faster than PCIe delivers it. Hosts with many more cores may see it differently.
+    const char *mode = getenv("GSTIM_D2H");
+    const bool force = mode != nullptr && strcmp(mode, "sparse") == 0;
+    if (!force) {
+        return false;
+    }
+    const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (main_out == nullptr || R == 0 || R >= 65536 || shots == 0) {
+        return false;
+    }
+    CK(cudaSetDevice(s->device));
+    const uint64_t chunk = std::max<uint64_t>((((uint64_t)env_u32("GSTIM_STAGE_MB", 512) << 20) / R) / GSTIM_COL_SHOTS, 1) * GSTIM_COL_SHOTS;
+    const uint64_t n_chunks = (shots + chunk - 1) / chunk;
+    auto rebuild = [&](const gstim_sampler::SparseSlot &sl) {
+        const unsigned long long *idx = (const unsigned long long *)sl.h_idx.p;
+        const uint8_t *strm = (const uint8_t *)sl.h_strm.p;
+        const unsigned nt = sl.n * R < (4u << 20) ? 1u : hw;
+        auto work = [&](uint64_t a, uint64_t b) {
+            for (uint64_t i = a; i < b; i++) {
+                const uint8_t *rec = strm + idx[i];
+                const uint32_t cnt = *reinterpret_cast<const uint16_t *>(rec);
+                const uint16_t *offs = reinterpret_cast<const uint16_t *>(rec + 2);
+                const uint8_t *vals = rec + 2 + 2 * (size_t)cnt;
+                uint8_t *dst = main_out + (sl.first + i) * main_pitch;
+                if (bit_packed) {
+                    memset(dst, 0, R);
+                    for (uint32_t k = 0; k < cnt; k++) {
+                        dst[offs[k]] = vals[k];
+                    }
+                } else {
+                    memset(dst, 0, nb_main);
+                    for (uint32_t k = 0; k < cnt; k++) {
+                        uint32_t v = vals[k];
+                        uint8_t *d8 = dst + 8 * (size_t)offs[k];
+                        while (v) {
+                            d8[__builtin_ctz(v)] = 1;
+                            v &= v - 1;
+                        }
+                    }
+                }
+                if (obs_out != nullptr && nb_obs) {
+                    const uint8_t *src = (const uint8_t *)sl.h_obs.p + i * obs_bytes;
+                    uint8_t *od = obs_out + (sl.first + i) * obs_pitch;
+                    if (bit_packed) {
+                        memcpy(od, src, obs_bytes);
+                    } else {
+                        unpack_bits(src, nb_obs, od);
+                    }
+                }
+            }
+        };
+        if (nt == 1) {
+            work(0, sl.n);
+            return;
+        }
+        std::vector<std::thread> ts;
+        for (unsigned t = 0; t < nt; t++) {
+            ts.emplace_back(work, sl.n * t / nt, sl.n * (t + 1) / nt);
+        }
+        for (auto &t : ts) {
+            t.join();
+        }
+    };
+    // stage B: the kernels of the slot are done -> enqueue its copies; stage C: copies done -> rebuild the rows
+    auto stage_b = [&](gstim_sampler::SparseSlot &sl) {
+        CK(cudaEventSynchronize(sl.ev_kernels));
+        const unsigned long long used = ((const unsigned long long *)sl.h_ctl.p)[0];
+        const bool overflow = ((const unsigned long long *)sl.h_ctl.p)[1] != 0;
+        if (overflow) {
+            // (denser than expected: this chunk goes out as dense rows)
+            std::vector<uint8_t> tmp(sl.n * R);
+            CK(cudaMemcpy(tmp.data(), sl.d_rows.p, sl.n * R, cudaMemcpyDeviceToHost));
+            for (uint64_t i = 0; i < sl.n; i++) {
+                uint8_t *dst = main_out + (sl.first + i) * main_pitch;
+                if (bit_packed) {
+                    memcpy(dst, tmp.data() + i * R, R);
+                } else {
+                    unpack_bits(tmp.data() + i * R, nb_main, dst);
+                }
+            }
+            ((unsigned long long *)sl.h_ctl.p)[1] = 2;  // marks "main rows already delivered"
+        } else {
+            sl.h_strm.ensure(used + 16);
+            CK(cudaMemcpyAsync(sl.h_strm.p, sl.d_strm.p, used, cudaMemcpyDeviceToHost, s->copy_stream));
+            sl.h_idx.ensure(sl.n * 8);
+            CK(cudaMemcpyAsync(sl.h_idx.p, sl.d_idx.p, sl.n * 8, cudaMemcpyDeviceToHost, s->copy_stream));
+        }
+        if (obs_out != nullptr && nb_obs) {
+            sl.h_obs.ensure(sl.n * obs_bytes);
+            CK(cudaMemcpyAsync(sl.h_obs.p, (const uint8_t *)sl.d_rows.p + sl.n * R, sl.n * obs_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+        }
+        CK(cudaEventRecord(sl.ev_copy, s->copy_stream));
+        sl.state = 2;
+    };
+    auto stage_c = [&](gstim_sampler::SparseSlot &sl) {
+        CK(cudaEventSynchronize(sl.ev_copy));
+        if (((const unsigned long long *)sl.h_ctl.p)[1] == 2) {
+            if (obs_out != nullptr && nb_obs) {
+                for (uint64_t i = 0; i < sl.n; i++) {
+                    const uint8_t *src = (const uint8_t *)sl.h_obs.p + i * obs_bytes;
+                    uint8_t *od = obs_out + (sl.first + i) * obs_pitch;
+                    if (bit_packed) {
+                        memcpy(od, src, obs_bytes);
+                    } else {
+                        unpack_bits(src, nb_obs, od);
+                    }
+                }
+            }
+        } else {
+            rebuild(sl);
+        }
+        sl.state = 0;
+    };
+    uint64_t k = 0;
+    try {
+        run_events(
+            s, shots, layout_flags, chunk,
+            [&](uint64_t first, uint64_t n, uint8_t **m, uint64_t *mp, uint8_t **o, uint64_t *op) {
+                gstim_sampler::SparseSlot &sl = s->sparse_slot[k % 3];
+                if (sl.state == 2) {
+                    stage_c(sl);  // (the slot's previous chunk, k - 3)
+                }
+                if (!sl.ev_kernels) {
+                    CK(cudaEventCreateWithFlags(&sl.ev_kernels, cudaEventDisableTiming));
+                    CK(cudaEventCreateWithFlags(&sl.ev_copy, cudaEventDisableTiming));
+                }
+                sl.d_rows.ensure(n * (R + obs_bytes) + 16);
+                sl.d_strm.ensure(n * R + 2 * n + 16);
+                sl.d_idx.ensure(n * 8);
+                sl.d_ctl.ensure(16);
+                sl.h_ctl.ensure(16);
+                sl.first = first;
+                sl.n = n;
+                *m = (uint8_t *)sl.d_rows.p;
+                *mp = R;
+                *o = nb_obs ? (uint8_t *)sl.d_rows.p + n * R : nullptr;
+                *op = obs_bytes;
+            },
+            [&](uint64_t, uint64_t n) {
+                gstim_sampler::SparseSlot &sl = s->sparse_slot[k % 3];
+                CK(cudaMemsetAsync(sl.d_ctl.p, 0, 16, s->stream));
+                CK(launch_compress_rows((const uint8_t *)sl.d_rows.p, R, (uint32_t)R, n, (uint8_t *)sl.d_strm.p, n * R + 2 * n,
+                                        (unsigned long long *)sl.d_ctl.p, (unsigned long long *)sl.d_idx.p,
+                                        (uint32_t *)((unsigned long long *)sl.d_ctl.p + 1), s->stream));
+                CK(cudaMemcpyAsync(sl.h_ctl.p, sl.d_ctl.p, 16, cudaMemcpyDeviceToHost, s->stream));
+                CK(cudaEventRecord(sl.ev_kernels, s->stream));
+                sl.state = 1;
+                s->last_launches++;
+                // pipeline: copies of the previous chunk, rebuild of the one before
+                if (k >= 1 && s->sparse_slot[(k - 1) % 3].state == 1) {
+                    stage_b(s->sparse_slot[(k - 1) % 3]);
+                }
+                if (k >= 2 && s->sparse_slot[(k - 2) % 3].state == 2) {
+                    stage_c(s->sparse_slot[(k - 2) % 3]);
+                }
+                k++;
+            });
+        // drain
+        for (uint64_t j = (k >= 2 ? k - 2 : 0); j < k; j++) {
+            gstim_sampler::SparseSlot &sl = s->sparse_slot[j % 3];
+            if (sl.state == 1) {
+                stage_b(sl);
+            }
+            if (sl.state == 2) {
+                stage_c(sl);
+            }
+        }
+    } catch (...) {
+        cudaStreamSynchronize(s->copy_stream);
+        cudaStreamSynchronize(s->stream);
+        for (auto &sl : s->sparse_slot) {
+            sl.state = 0;
+        }
+        throw;
+    }
+    (void)n_chunks;
+    s->last_d2h_sparse = 1;
+    return true;
+}
+
 // host output: transposed chunks are staged in device memory, copied to pinned host memory on a
 // second stream (double buffered) and scattered into the caller's (possibly strided / unpacked) rows.
 void sample_to_host(
@@ -827,6 +1034,10 @@ void sample_to_host(
     const uint64_t obs_pitch = obs_stride ? (uint64_t)obs_stride : obs_row;
     const uint64_t stage_pitch = main_bytes + obs_bytes;  // per shot in the staging buffers
     CK(cudaSetDevice(s->device));
+    s->last_d2h_sparse = 0;
+    if (use_events(s) && sample_to_host_sparse(s, shots, maps, layout_flags, bit_packed, main_out, main_pitch, obs_out, obs_pitch)) {
+        return;
+    }
     s->d_rowmap.ensure((size_t)(nb_main + nb_obs + 1) * 4);
     upload_row_map(s, maps.main, 0);
     upload_row_map(s, maps.obs, nb_main);

@@ -655,6 +655,59 @@ __global__ void __launch_bounds__(128) gstim_count_b8_kernel(const uint8_t *rows
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sparse host delivery: detection-event rows are mostly zero bytes (c3: 88 %), and the D2H copy of dense rows is what
+// bounds the end-to-end rate. This kernel rewrites dense rows as per-shot records
+//     u16 count, count x u16 byte offset, count x u8 value          (2-byte aligned, at index[shot] in the stream)
+// so that only the non-zero bytes cross PCIe; host threads rebuild the caller's dense rows (api.cu). One warp per shot:
+// pass A counts the non-zero bytes (ballots), lane 0 reserves the record in the stream with one atomic, pass B writes it.
+// A stream that would overflow its buffer sets *overflow and the chunk is delivered densely instead.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gstim_compress_rows_kernel(const uint8_t *rows, uint64_t pitch, uint32_t row_bytes, uint64_t n_shots,
+                                                                uint8_t *stream, uint64_t capacity, unsigned long long *cursor,
+                                                                unsigned long long *index, uint32_t *overflow) {
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t shot = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; shot < n_shots; shot += warps) {
+        const uint8_t *row = rows + shot * pitch;
+        uint32_t cnt = 0;
+        for (uint32_t c0 = 0; c0 < row_bytes; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const uint32_t b = c < row_bytes ? row[c] : 0u;
+            cnt += __popc(__ballot_sync(0xFFFFFFFFu, b != 0));
+        }
+        unsigned long long o = 0;
+        if (lane == 0) {
+            o = atomicAdd(cursor, (unsigned long long)((2u + 3u * cnt + 1u) & ~1u));
+            index[shot] = o;
+        }
+        o = __shfl_sync(0xFFFFFFFFu, o, 0);
+        if (o + 2 + 3ull * cnt > capacity) {
+            if (lane == 0) {
+                *overflow = 1;
+            }
+            continue;
+        }
+        if (lane == 0) {
+            *reinterpret_cast<uint16_t *>(stream + o) = (uint16_t)cnt;
+        }
+        uint16_t *offs = reinterpret_cast<uint16_t *>(stream + o + 2);
+        uint8_t *vals = stream + o + 2 + 2ull * cnt;
+        uint32_t base = 0;
+        for (uint32_t c0 = 0; c0 < row_bytes; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const uint32_t b = c < row_bytes ? row[c] : 0u;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, b != 0);
+            if (b != 0) {
+                const uint32_t k = base + __popc(m & lt);
+                offs[k] = (uint16_t)c;
+                vals[k] = (uint8_t)b;
+            }
+            base += __popc(m);
+        }
+    }
+}
+
 void ck(cudaError_t e, const char *what) {
     if (e != cudaSuccess) {
         if (e == cudaErrorMemoryAllocation) {
@@ -683,6 +736,17 @@ cudaError_t launch_count_b8(const uint8_t *rows, uint64_t pitch, uint64_t n_shot
     const unsigned gx = (n_words + 127) / 128;
     dim3 grid(gx, (unsigned)std::min<uint64_t>((n_shots + 1019) / 1020, std::max<uint64_t>(1, 148ull * 64 / gx)));
     gstim_count_b8_kernel<<<grid, 128, 0, stream>>>(rows, pitch, n_shots, n_bits, single, pair);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compress_rows(const uint8_t *rows, uint64_t pitch, uint32_t row_bytes, uint64_t n_shots, uint8_t *stream_buf,
+                                 uint64_t capacity, unsigned long long *cursor, unsigned long long *index, uint32_t *overflow,
+                                 cudaStream_t stream) {
+    if (n_shots == 0) {
+        return cudaSuccess;
+    }
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_shots + 7) / 8, 148ull * 16);
+    gstim_compress_rows_kernel<<<grid, 256, 0, stream>>>(rows, pitch, row_bytes, n_shots, stream_buf, capacity, cursor, index, overflow);
     return cudaGetLastError();
 }
 

@@ -50,4 +50,11 @@ class SparseEngine {
 cudaError_t launch_count_b8(const uint8_t *rows, uint64_t pitch, uint64_t n_shots, uint32_t n_bits, unsigned long long *single,
                             unsigned long long *pair, cudaStream_t stream);
 
+// Dense b8 rows -> per-shot records of their non-zero bytes (u16 count, u16 offsets, u8 values; sparse.cu "Sparse host
+// delivery"): index[shot] = byte offset of the record in stream_buf, *cursor = bytes used (start it at 0), *overflow = 1 when a
+// record did not fit in `capacity`. row_bytes must be below 65536.
+cudaError_t launch_compress_rows(const uint8_t *rows, uint64_t pitch, uint32_t row_bytes, uint64_t n_shots, uint8_t *stream_buf,
+                                 uint64_t capacity, unsigned long long *cursor, unsigned long long *index, uint32_t *overflow,
+                                 cudaStream_t stream);
+
 }  // namespace gstim

@@ -289,3 +289,33 @@ def test_sinter_shaped_consumer_counts_on_the_device():
     assert stats.shots == shots and stats.discards == int(discarded.sum()) and stats.errors == errors
     assert stats.custom_counts["detection_events"] == n_events and stats.custom_counts["detectors_checked"] == D * shots
     assert 0 < stats.discards < shots and 0 < stats.errors < shots
+
+
+def test_sparse_host_delivery_equals_dense_delivery(monkeypatch):
+    """GSTIM_D2H=sparse: rows cross PCIe as records of their non-zero bytes and are rebuilt by host threads; the caller sees
+    the same arrays as with the dense copy (packed, unpacked, separate observables, strided rows, several chunks)."""
+    text = gen_circuit("surface_code", "rotated_memory_x", 5, 5, 0.01)
+    circ = stim_b200.Circuit(text)
+    D = circ.num_detectors
+    shots = 70_001
+    monkeypatch.setenv("GSTIM_D2H", "dense")
+    want_p = circ.compile_detector_sampler(seed=5, engine="events").sample(shots, bit_packed=True, append_observables=True)
+    want_d, want_o = circ.compile_detector_sampler(seed=5, engine="events").sample(shots, separate_observables=True)
+    monkeypatch.setenv("GSTIM_D2H", "sparse")
+    monkeypatch.setenv("GSTIM_STAGE_MB", "1")  # many chunks: the three-stage pipeline wraps around
+    got_p = circ.compile_detector_sampler(seed=5, engine="events").sample(shots, bit_packed=True, append_observables=True)
+    np.testing.assert_array_equal(got_p, want_p)
+    got_d, got_o = circ.compile_detector_sampler(seed=5, engine="events").sample(shots, separate_observables=True)
+    np.testing.assert_array_equal(got_d, want_d)
+    np.testing.assert_array_equal(got_o, want_o)
+    buf = np.full((shots, 40), 0xAA, dtype=np.uint8)
+    circ.compile_detector_sampler(seed=5, engine="events").sample(shots, bit_packed=True, dets_out=buf[:, 5:5 + (D + 7) // 8])
+    np.testing.assert_array_equal(np.unpackbits(buf[:, 5:5 + (D + 7) // 8], axis=1, bitorder="little")[:, :D], want_d.astype(np.uint8))
+    assert (buf[:, :5] == 0xAA).all() and (buf[:, 5 + (D + 7) // 8:] == 0xAA).all()
+    # a dense circuit overflows the record stream and falls back to dense rows chunk by chunk
+    dense = "X_ERROR(0.5) " + " ".join(str(q) for q in range(64)) + "\nM " + " ".join(str(q) for q in range(64)) + "\n" + "".join(
+        f"DETECTOR rec[-{k}]\n" for k in range(64, 0, -1))
+    a = stim_b200.Circuit(dense).compile_detector_sampler(seed=6, engine="events").sample(20_000, bit_packed=True)
+    monkeypatch.setenv("GSTIM_D2H", "dense")
+    b = stim_b200.Circuit(dense).compile_detector_sampler(seed=6, engine="events").sample(20_000, bit_packed=True)
+    np.testing.assert_array_equal(a, b)
