@@ -933,6 +933,10 @@ __device__ __noinline__ const uint32_t *op_feedback(const BlockCtx *bc, const ui
 __device__ __noinline__ const uint32_t *op_corr(const BlockCtx *bc, const uint32_t *hdr) {
     const SmemWords hw{smem_u32(hdr)};
     prefetch_events(bc, hw[GH_CSITE0] + 1);  // keeps the staging pipeline of op_noise going (this op reads its records directly)
+    // This batch's own staged records are never read, but their copy group must have landed before a later batch stages into
+    // the same buffer: otherwise two in-flight async copies target the same addresses (compute-sanitizer racecheck,
+    // profiles/r2_notes.md). Same wait as op_noise.
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     if (threadIdx.x != 0) {
         return hdr + hw[GH_WORDS];
     }
