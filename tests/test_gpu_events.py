@@ -319,3 +319,33 @@ def test_sparse_host_delivery_equals_dense_delivery(monkeypatch):
     monkeypatch.setenv("GSTIM_D2H", "dense")
     b = stim_b200.Circuit(dense).compile_detector_sampler(seed=6, engine="events").sample(20_000, bit_packed=True)
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_circuits_match_oracle_on_both_engines(seed):
+    """Random instruction sequences (tests/test_response_table.py:_random_circuit): the event engine bit for bit against
+    its oracle (detectors and measurements), the interpreter bit for bit against the frame oracle, and the two engines against
+    each other statistically (their random streams differ)."""
+    from oracle import frame_oracle as fo
+    from test_response_table import _random_circuit
+
+    text = _random_circuit(np.random.default_rng(2000 + seed))
+    circ = stim_b200.Circuit(text)
+    ev = circ.compile_detector_sampler(seed=seed, engine="interp")
+    if not ev.engine_info()["eligible"]:
+        pytest.skip(ev.engine_info()["why_not"])
+    check_detectors(text, 400, seed=50 + seed)
+    ms = circ.compile_sampler(seed=seed, skip_reference_sample=True, engine="events")
+    m = ms.sample(300)
+    np.testing.assert_array_equal(m.astype(np.uint8), oracle_rows(ms, seed, 0, 300, circ.num_measurements))
+    it = circ.compile_detector_sampler(seed=seed, engine="interp")
+    dets, obs = it.sample(400, separate_observables=True)
+    od, oo = fo.sample(text, 400, seed, it.last_block_columns(), "detectors")
+    np.testing.assert_array_equal(dets.astype(np.uint8), od)
+    np.testing.assert_array_equal(obs.astype(np.uint8), oo)
+    shots = 1 << 18
+    a, _ = circ.compile_detector_sampler(seed=1, engine="events").bit_counts(shots)
+    b, _ = circ.compile_detector_sampler(seed=2, engine="interp").bit_counts(shots)
+    p = (a + b) / (2.0 * shots)
+    z = (a.astype(np.float64) - b.astype(np.float64)) / shots / np.sqrt(np.maximum(p * (1 - p), 1e-12) * 2 / shots)
+    assert np.abs(z).max() < 5.5, (z, text)

@@ -161,3 +161,113 @@ def test_round_structure_folds_the_table_exactly(name):
                 assert so.entry_ids(t, entry0 + int(s) * n_out + o) == want, (int(c[4]), int(s), o)
     if name.startswith("c3"):
         assert kept * 8 < len(t["entries"])
+
+
+def _random_circuit(rng, n_qubits=6, n_ops=60):
+    """Random circuits over every kind of instruction the lowering knows (gates in random order, resets and measurements in
+    all bases with repeated targets, feedback, MPP / SPP / pair measurements, every noise channel, heralded errors, E / ELSE
+    chains, REPEAT blocks, detectors and observables with record and Pauli targets)."""
+    one = ["H", "S", "S_DAG", "SQRT_X", "SQRT_X_DAG", "SQRT_Y", "SQRT_Y_DAG", "H_XY", "H_YZ", "C_XYZ", "C_ZYX", "X", "Y", "Z", "I"]
+    two = ["CX", "CY", "CZ", "XCX", "XCY", "XCZ", "YCX", "YCY", "YCZ", "SWAP", "ISWAP", "ISWAP_DAG", "CXSWAP", "SWAPCX", "CZSWAP",
+           "SQRT_XX", "SQRT_XX_DAG", "SQRT_YY", "SQRT_YY_DAG", "SQRT_ZZ", "SQRT_ZZ_DAG"]
+    meas = ["M", "MX", "MY", "MR", "MRX", "MRY"]
+    lines, n_meas = [], 0
+    q = lambda k=1: [int(v) for v in rng.choice(n_qubits, size=k, replace=False)]
+
+    def emit(depth):
+        nonlocal n_meas
+        kind = rng.integers(0, 14)
+        if kind == 0:
+            lines.append(f"{rng.choice(one)} " + " ".join(map(str, q(rng.integers(1, 4)))))
+        elif kind == 1:
+            a = q(2)
+            lines.append(f"{rng.choice(two)} {a[0]} {a[1]}")
+        elif kind == 2:
+            ts = [int(v) for v in rng.integers(0, n_qubits, size=rng.integers(1, 4))]  # (targets may repeat)
+            name = rng.choice(meas)
+            arg = f"({rng.choice([0.1, 0.25])})" if rng.random() < 0.3 else ""
+            lines.append(f"{name}{arg} " + " ".join(("!" if rng.random() < 0.2 else "") + str(t) for t in ts))
+            n_meas += len(ts)
+        elif kind == 3:
+            lines.append(f"{rng.choice(['R', 'RX', 'RY'])} " + " ".join(map(str, q(rng.integers(1, 3)))))
+        elif kind == 4 and n_meas:
+            k = int(rng.integers(1, min(n_meas, 5) + 1))
+            g = rng.choice(["CX", "CY", "CZ"])
+            lines.append(f"{g} rec[-{k}] {q()[0]}" if g != "CZ" or rng.random() < 0.5 else f"CZ {q()[0]} rec[-{k}]")
+        elif kind == 5:
+            a = q(3)
+            ps = rng.choice(list("XYZ"), size=3)
+            lines.append(f"MPP {ps[0]}{a[0]}*{ps[1]}{a[1]} {'!' if rng.random() < 0.3 else ''}{ps[2]}{a[2]}")
+            n_meas += 2
+        elif kind == 6:
+            a = q(2)
+            ps = rng.choice(list("XYZ"), size=2)
+            lines.append(f"{rng.choice(['SPP', 'SPP_DAG'])} {ps[0]}{a[0]}*{ps[1]}{a[1]}")
+        elif kind == 7:
+            a = q(2)
+            lines.append(f"{rng.choice(['MXX', 'MYY', 'MZZ'])} {a[0]} {a[1]}")
+            n_meas += 1
+        elif kind == 8:
+            name = rng.choice(["X_ERROR", "Y_ERROR", "Z_ERROR", "DEPOLARIZE1"])
+            lines.append(f"{name}({rng.choice([0.01, 0.3, 0.5])}) " + " ".join(map(str, q(rng.integers(1, 4)))))
+        elif kind == 9:
+            a = q(2)
+            if rng.random() < 0.5:
+                lines.append(f"DEPOLARIZE2({rng.choice([0.02, 0.4])}) {a[0]} {a[1]}")
+            else:
+                ps = rng.dirichlet(np.ones(15)) * 0.3
+                lines.append("PAULI_CHANNEL_2(" + ", ".join(f"{v:.4f}" for v in ps) + f") {a[0]} {a[1]}")
+        elif kind == 10:
+            r = rng.random()
+            if r < 0.4:
+                lines.append(f"PAULI_CHANNEL_1(0.05, 0.1, 0.02) {q()[0]}")
+            elif r < 0.7:
+                lines.append(f"HERALDED_ERASE(0.2) {q()[0]}")
+                n_meas += 1
+            else:
+                lines.append(f"HERALDED_PAULI_CHANNEL_1(0.02, 0.05, 0.1, 0.03) {q()[0]}")
+                n_meas += 1
+        elif kind == 11:
+            a = q(2)
+            lines.append(f"E(0.1) X{a[0]} Z{a[1]}")
+            for _ in range(rng.integers(0, 3)):
+                lines.append(f"ELSE_CORRELATED_ERROR(0.2) {rng.choice(list('XYZ'))}{q()[0]}")
+        elif kind == 12 and n_meas:
+            ks = sorted({int(v) for v in rng.integers(1, min(n_meas, 6) + 1, size=rng.integers(1, 4))})
+            if rng.random() < 0.7:
+                lines.append("DETECTOR " + " ".join(f"rec[-{k}]" for k in ks))
+            else:
+                extra = f" {rng.choice(list('XYZ'))}{q()[0]}" if rng.random() < 0.5 else ""
+                lines.append(f"OBSERVABLE_INCLUDE({rng.integers(0, 3)}) " + " ".join(f"rec[-{k}]" for k in ks) + extra)
+        elif kind == 13 and depth == 0 and n_meas >= 2:
+            reps = int(rng.integers(2, 4))
+            lines.append(f"REPEAT {reps} {{")
+            before, m0 = len(lines), n_meas
+            for _ in range(rng.integers(2, 6)):
+                emit(1)
+            lines.append("}")
+            n_meas = m0 + (n_meas - m0) * reps
+            if before == len(lines) - 1:
+                lines.insert(before, f"H {q()[0]}")
+
+    for _ in range(n_ops):
+        emit(0)
+    lines.append("M " + " ".join(map(str, range(n_qubits))))
+    lines.append("DETECTOR rec[-1] rec[-2]")
+    lines.append("OBSERVABLE_INCLUDE(0) rec[-3]")
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_circuits_match_forward_injection(seed):
+    """Differential test of the backward pass against the forward frame oracle on random instruction sequences."""
+    rng = np.random.default_rng(1000 + seed)
+    text = _random_circuit(rng)
+    for mode in ("detectors", "measurements"):
+        t = stim_b200.response_table(text, mode)
+        if not t["info"]["eligible"]:
+            assert "ELSE_CORRELATED_ERROR" in t["info"]["why_not"] or "large" in t["info"]["why_not"]
+            continue
+        want = so.responses_by_injection(text, t, mode)
+        bad = [(e, so.entry_ids(t, e), ids) for e, ids in want.items() if so.entry_ids(t, e) != ids]
+        assert not bad, (mode, bad[:3], text)
