@@ -468,12 +468,13 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
 
         uint32_t a0 = 0;  // trials consumed by the previous steps
         for (uint32_t call0 = 0;; call0 += 32) {
-            // last step's events first (their entries have arrived by now; the flips are independent of everything below and
-            // overlap the Philox rounds), then this step's loads take their place
-            apply(pend0, pm0, po0, ps0);
-            apply(pend1, pm1, po1, ps1);
-            pend0.x = pend0.y = pend0.z = pend0.w = RESP_NONE;
-            pend1 = pend0;
+            // Last step's events are applied before this step's loads take their place: after the scan in the plain kernels
+            // (the entry loads get a whole scan more to arrive: long scoreboard 7 % instead of 14 %), at the top of the step
+            // in the folded ones (frees their registers earlier: fewer spills).
+            if (PERIODIC) {
+                apply(pend0, pm0, po0, ps0);
+                apply(pend1, pm1, po1, ps1);
+            }
             const uint4 r = sp_philox(sl, call0 + lane, c2, c3, p.rk);
             const uint32_t rem = total - a0;  // > 0
             // gaps of the lane's two draws, clamped to rem (a clamped gap is an overshoot)
@@ -508,6 +509,12 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
             // event of draw h sits at trial a0 + (trials before the draw) + gap; it exists iff that is < total
             const uint32_t off0 = excl + G[0], off1 = excl + s_a + G[1];
             const bool ok0 = off0 < rem, ok1 = ok0 && off1 < rem;
+            if (!PERIODIC) {
+                apply(pend0, pm0, po0, ps0);
+                apply(pend1, pm1, po1, ps1);
+            }
+            pend0.x = pend0.y = pend0.z = pend0.w = RESP_NONE;
+            pend1 = pend0;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const bool ok = h ? ok1 : ok0;
