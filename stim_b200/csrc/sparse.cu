@@ -35,6 +35,9 @@
 #include <vector>
 
 #include "sparse.cuh"
+#ifndef GSTIM_SPARSE_TIMING  // 1: block 0 prints where its warps spent their cycles (profiling builds only)
+#define GSTIM_SPARSE_TIMING 0
+#endif
 
 #define GSTIM_TABLE_QUAL __device__ const
 #include "log2_q26_table.h"
@@ -161,25 +164,27 @@ __device__ __forceinline__ void store_span(const uint8_t *img, uint32_t img_sadd
 
 // One persistent block per SM. The block keeps n_buffers tile images in shared memory; tile sequence q of the block
 // (global tile blockIdx.x + q * gridDim.x) lives in buffer q % n_buffers.
-//   producer lanes (all warps but the last) walk the sequences in order: claim slices of sequence q until its pool is
-//     dry, then LEAVE it (count themselves out) and go on to q + 1 without waiting for anybody — so a lane never idles
-//     at a tile boundary; it only waits when buffer (q + 1) % n_buffers has not been recycled yet;
-//   the writer warp waits until every producer lane has left sequence q, stores the image to global memory, clears it
-//     and hands the buffer to sequence q + n_buffers.
+//   producer warps (all warps but the last) draw TICKETS from one counter of the block: ticket T is slice T % n_slices
+//     of sequence T / n_slices, so a warp goes from slice to slice without visiting sequences it has no work in and
+//     without waiting for anybody; it only waits when the buffer of its ticket's sequence has not been recycled yet.
+//     A finished slice is counted on its sequence once its last flips are applied (one step later, see below);
+//   the writer warp waits until all n_slices slices of sequence q are counted, stores the image to global memory,
+//     clears it and hands the buffer to sequence q + n_buffers.
 template <bool SEPARATE, bool PERIODIC>
 __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const __grid_constant__ SparseParams p) {
     extern __shared__ uint4 smem4[];
     uint2 *const lt = reinterpret_cast<uint2 *>(smem4);                        // 256 x (base, diff): 2 KiB
     EvClass *const cls = reinterpret_cast<EvClass *>(lt + 256);                 // MAX_CLASSES x 64 B
     uint32_t *const ctl = reinterpret_cast<uint32_t *>(cls + MAX_CLASSES);      // MAX_BUFFERS x CTL_WORDS
-    uint8_t *const img0 = reinterpret_cast<uint8_t *>(ctl + MAX_BUFFERS * CTL_WORDS);  // 16-byte aligned
+    uint32_t *const sink = ctl + MAX_BUFFERS * CTL_WORDS;                       // 32 words nobody reads (see flip)
+    uint8_t *const img0 = reinterpret_cast<uint8_t *>(sink + 32);               // 16-byte aligned
     const uint32_t img0_saddr = (uint32_t)__cvta_generic_to_shared(img0);
 
     const uint32_t S = 1u << p.log_s, smask = S - 1u, NB = p.n_buffers;
     const uint32_t main_bits = p.main_bytes * 8u, obs_bits = p.obs_bytes * 8u;
     const bool main_dense = p.main_pitch == p.main_bytes, obs_dense = p.obs_pitch == p.obs_bytes;
     const uint32_t n_seq = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles of this block
-    const uint32_t n_prod = blockDim.x - 32, n_prod_warps = n_prod / 32;
+    const uint32_t n_prod = blockDim.x - 32;
 
     auto phases_of = [&](uint32_t q, uint32_t *pm, uint32_t *po) {
         const uint64_t shot0 = ((uint64_t)blockIdx.x + (uint64_t)q * gridDim.x) << p.log_s;
@@ -206,8 +211,9 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         uint32_t *c = ctl + threadIdx.x * CTL_WORDS;
         uint32_t pm, po;
         phases_of(threadIdx.x, &pm, &po);
-        c[0] = 0;                                   // next slice
-        c[1] = 0;                                   // producer lanes that left the sequence
+        c[0] = 0;                                   // (unused)
+        c[1] = 0;                                   // finished slices of the sequence
+        c[6] = 0;                                   // buffer 0 only: next ticket of the block
         c[2] = 0;                                   // full: sequence + 1 whose events are all applied
         c[3] = threadIdx.x < n_seq ? threadIdx.x + 1 : 0;  // ready: sequence + 1 the buffer is cleared for
         c[4] = pm;
@@ -224,14 +230,20 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
     if (threadIdx.x >= n_prod) {
         // ---- writer warp -------------------------------------------------------------------------------------
         const uint32_t lane = threadIdx.x & 31u;
+#if GSTIM_SPARSE_TIMING
+        long long t_wait = 0, t_store = 0, t_zero = 0, t_a = clock64(), t_b;
+#endif
         for (uint32_t q = 0; q < n_seq; q++) {
             const uint32_t b = q % NB;
             uint32_t *c = ctl + b * CTL_WORDS;
             uint8_t *img = img0 + b * p.img_bytes;
-            while (ld_volatile_shared(c + 2) != q + 1) {
+            while (p.n_slices != 0 && ld_volatile_shared(c + 2) != q + 1) {
                 __nanosleep(64);
             }
             __threadfence_block();
+#if GSTIM_SPARSE_TIMING
+            t_b = clock64(); t_wait += t_b - t_a; t_a = t_b;
+#endif
             const uint64_t shot0 = ((uint64_t)blockIdx.x + (uint64_t)q * gridDim.x) << p.log_s;
             const uint32_t n_valid = (uint32_t)min((uint64_t)S, p.n_shots - shot0);
             const uint32_t pm = c[4], po = c[5];
@@ -256,6 +268,9 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
                     }
                 }
             }
+#if GSTIM_SPARSE_TIMING
+            t_b = clock64(); t_store += t_b - t_a; t_a = t_b;
+#endif
             if (q + NB < n_seq) {  // recycle the buffer for sequence q + NB
                 __syncwarp();
 #pragma unroll 8
@@ -270,7 +285,6 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    c[0] = 0;
                     c[1] = 0;
                     c[4] = npm;
                     c[5] = npo;
@@ -279,7 +293,15 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
                 }
                 __syncwarp();
             }
+#if GSTIM_SPARSE_TIMING
+            t_b = clock64(); t_zero += t_b - t_a; t_a = t_b;
+#endif
         }
+#if GSTIM_SPARSE_TIMING
+        if (blockIdx.x == 0 && lane == 0) {
+            printf("writer: n_seq %u wait %lld store %lld zero %lld cycles per tile\n", n_seq, t_wait / n_seq, t_store / n_seq, t_zero / n_seq);
+        }
+#endif
         return;
     }
 
@@ -290,9 +312,16 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
     // at sum_{j <= d} (gap_j + 1) - 1. Draws whose position falls beyond the slice are dropped; the first of them ends
     // the slice. All 32 lanes execute the same instructions (no divergence), valid draws only differ in predicates.
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t q = 0, b = 0;  // sequence this warp works on, its buffer (warp-uniform)
+    if (p.n_slices == 0) {
+        return;  // nothing random: the writer stores the constant rows
+    }
+    uint32_t q = 0, b = 0, q_end = p.n_slices;  // sequence of the warp's ticket, its buffer, first ticket of sequence q + 1
     uint32_t *c = ctl;
-    bool entered = false;
+    uint32_t entered_q = 0xFFFFFFFFu;  // sequence whose buffer the warp has entered
+    // the slice the warp finished last is counted on its sequence (c_owe, q_owe) once its pending flips are applied
+    bool owe = false;
+    uint32_t *c_owe = ctl;
+    uint32_t q_owe = 0;
     uint32_t rowbase_m = 0, rowbase_o = 0, c2 = 0, c3 = 0;
     const uint32_t e0 = p.n_classes > 0 ? cls[0].slice_end : 0xFFFFFFFFu, e1 = p.n_classes > 1 ? cls[1].slice_end : 0xFFFFFFFFu,
                    e2 = p.n_classes > 2 ? cls[2].slice_end : 0xFFFFFFFFu;
@@ -301,6 +330,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
     uint32_t pm0 = 0, po0 = 0, pm1 = 0, po1 = 0;
     uint32_t ps0 = 0, ps1 = 0;  // PERIODIC: detector-id shift of the pending events
 
+    const uint32_t sink_saddr = (uint32_t)__cvta_generic_to_shared(sink) + lane * 4u;
     // flips output bit v of a row unless v is an empty slot / overflow link (bit 31 set): predicated, no branch
     auto flip = [&](uint32_t row_m, uint32_t row_o, uint32_t v, uint32_t shift = 0) {
         uint32_t bit;
@@ -312,14 +342,22 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         if (PERIODIC) {
             bit += (v - p.det_lo) < p.n_det ? shift : 0u;
         }
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "setp.lt.u32 p, %2, 0x80000000;\n"
-            "@p red.shared.xor.b32 [%0], %1;\n"
-            "}" ::"r"(img0_saddr + ((bit >> 5) << 2)),
-            "r"(1u << (bit & 31u)), "r"(v)
-            : "memory");
+        if (!PERIODIC) {
+            // No predicate: an empty slot flips a bit of the lane's own sink word instead. (ptxas turns a predicated shared
+            // atomic into a branch around it and its address arithmetic: 8 x BSSY/BRA/BSYNC per step, 10 % of the stall
+            // samples were branch resolution. The folded kernels keep the predicate: the extra selects spill there.)
+            const uint32_t a = (v < 0x80000000u) ? img0_saddr + ((bit >> 3) & 0x1FFFFFFCu) : sink_saddr;
+            asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(1u << (bit & 31u)) : "memory");
+        } else {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.lt.u32 p, %2, 0x80000000;\n"
+                "@p red.shared.xor.b32 [%0], %1;\n"
+                "}" ::"r"(img0_saddr + ((bit >> 5) << 2)),
+                "r"(1u << (bit & 31u)), "r"(v)
+                : "memory");
+        }
     };
     auto apply = [&](const uint4 &e, uint32_t row_m, uint32_t row_o, uint32_t shift = 0) {
         flip(row_m, row_o, e.x, shift);
@@ -357,11 +395,65 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         return c_entry0 + cs * n_out + o;
     };
 
-    while (q < n_seq) {
-        if (!entered) {
-            // wait until the buffer has been recycled for sequence q
-            while (ld_volatile_shared(c + 3) != q + 1) {
-                __nanosleep(GSTIM_PRODUCER_SLEEP_NS);
+    auto settle = [&]() {  // every flip of the owed slice has been issued by this warp: count the slice
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(c_owe + 1, 1u) + 1 == p.n_slices) {
+                __threadfence_block();
+                st_volatile_shared(c_owe + 2, q_owe + 1);
+            }
+        }
+        owe = false;
+    };
+    auto flush = [&]() {
+        apply(pend0, pm0, po0, ps0);
+        apply(pend1, pm1, po1, ps1);
+        pend0.x = pend0.y = pend0.z = pend0.w = RESP_NONE;
+        pend1 = pend0;
+        if (owe) {
+            settle();
+        }
+    };
+
+#if GSTIM_SPARSE_TIMING
+    long long t_pwait = 0, t_p0 = clock64();
+    uint32_t n_pwait = 0, n_slices_done = 0, n_steps = 0;
+#endif
+    for (;;) {
+        uint32_t T = 0;
+        if (lane == 0) {
+            T = atomicAdd(ctl + 6, 1u);
+        }
+        T = __shfl_sync(0xFFFFFFFFu, T, 0);
+        while (T >= q_end) {
+            q++;
+            q_end += p.n_slices;
+            b = b + 1 == NB ? 0 : b + 1;
+        }
+        if (q >= n_seq) {
+            flush();
+            break;
+        }
+#if GSTIM_SPARSE_TIMING
+        n_slices_done++;
+#endif
+        if (q != entered_q) {
+            c = ctl + b * CTL_WORDS;
+            if (ld_volatile_shared(c + 3) != q + 1) {
+                // the buffer has not been recycled for sequence q yet. A warp never sleeps on debts: the sequence it owes
+                // a slice to may be the one this buffer is waiting for.
+                flush();
+#if GSTIM_SPARSE_TIMING
+                const long long tw = clock64();
+#endif
+                while (ld_volatile_shared(c + 3) != q + 1) {
+                    __nanosleep(GSTIM_PRODUCER_SLEEP_NS);
+                }
+#if GSTIM_SPARSE_TIMING
+                t_pwait += clock64() - tw;
+                n_pwait++;
+#endif
             }
             __threadfence_block();
             const uint64_t gt = p.tile0 + blockIdx.x + (uint64_t)q * gridDim.x;
@@ -369,33 +461,9 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
             c3 = SPARSE_TAG | (uint32_t)(gt >> 32);
             rowbase_m = (b * p.img_bytes + c[4]) * 8u;
             rowbase_o = (b * p.img_bytes + p.obs_img_off + c[5]) * 8u;
-            entered = true;
+            entered_q = q;
         }
-        uint32_t sl = 0;
-        if (lane == 0) {
-            sl = atomicAdd(c, 1u);
-        }
-        sl = __shfl_sync(0xFFFFFFFFu, sl, 0);
-        if (sl >= p.n_slices) {
-            // the pool of sequence q is dry: apply what is pending, count this warp out, move on
-            apply(pend0, pm0, po0, ps0);
-            apply(pend1, pm1, po1, ps1);
-            pend0.x = pend0.y = pend0.z = pend0.w = RESP_NONE;
-            pend1 = pend0;
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) {
-                if (atomicAdd(c + 1, 1u) + 1 == n_prod_warps) {
-                    __threadfence_block();
-                    st_volatile_shared(c + 2, q + 1);
-                }
-            }
-            q++;
-            b = b + 1 == NB ? 0 : b + 1;
-            c = ctl + b * CTL_WORDS;
-            entered = false;
-            continue;
-        }
+        const uint32_t sl = T - (q_end - p.n_slices);
         uint32_t k = (sl >= e0 ? 1u : 0u) + (sl >= e1 ? 1u : 0u) + (sl >= e2 ? 1u : 0u);
         if (k == 3) {
             while (sl >= cls[k].slice_end) {
@@ -420,6 +488,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         }
 
         if (dense_thr != 0) {
+            flush();  // (the dense path applies its flips at once: nothing may be pending across it)
             // Dense class: the trials of the slice as packed Bernoulli words, 32 trials per lane and pass. A word with
             // P(bit) = thr / 2^32 comes from the binary expansion of thr, lowest set bit first: acc = b_i ? acc | r_i :
             // acc & r_i halves the probability and adds b_i / 2 (the bit-sliced part of biased_randomize_bits,
@@ -462,7 +531,9 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
                     apply(e, rowbase_m + shot * main_bits, rowbase_o + shot * obs_bits, shift);
                 }
             }
-            __syncwarp();
+            c_owe = c;
+            q_owe = q;
+            settle();
             continue;
         }
 
@@ -474,6 +545,9 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
             if (PERIODIC) {
                 apply(pend0, pm0, po0, ps0);
                 apply(pend1, pm1, po1, ps1);
+                if (owe) {
+                    settle();
+                }
             }
             const uint4 r = sp_philox(sl, call0 + lane, c2, c3, p.rk);
             const uint32_t rem = total - a0;  // > 0
@@ -512,6 +586,9 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
             if (!PERIODIC) {
                 apply(pend0, pm0, po0, ps0);
                 apply(pend1, pm1, po1, ps1);
+                if (owe) {
+                    settle();
+                }
             }
             pend0.x = pend0.y = pend0.z = pend0.w = RESP_NONE;
             pend1 = pend0;
@@ -551,12 +628,24 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
                 }
             }
             a0 += consumed;
+#if GSTIM_SPARSE_TIMING
+            n_steps++;
+#endif
             if (a0 >= total) {  // (warp-uniform) some draw of this step overshot, or the last trial fired
                 break;
             }
         }
+        owe = true;  // (the first step of every slice has settled the previous debt)
+        c_owe = c;
+        q_owe = q;
     }
-    // (q == n_seq: every sequence has been left with nothing pending)
+#if GSTIM_SPARSE_TIMING
+    if (blockIdx.x == 0 && lane == 0) {
+        printf("producer warp %2u: total %lld cycles, waiting for a buffer %lld (%u waits), %u slices, %u steps\n", threadIdx.x >> 5,
+               clock64() - t_p0, t_pwait, n_pwait, n_slices_done, n_steps);
+    }
+#endif
+    // (ticket beyond the last sequence: nothing pending, nothing owed)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -729,7 +818,7 @@ uint32_t align16(uint32_t v) {
     return (v + 15u) & ~15u;
 }
 
-constexpr size_t FIXED_SMEM = 256 * 8 + MAX_CLASSES * sizeof(EvClass) + MAX_BUFFERS * CTL_WORDS * 4;
+constexpr size_t FIXED_SMEM = 256 * 8 + MAX_CLASSES * sizeof(EvClass) + MAX_BUFFERS * CTL_WORDS * 4 + 32 * 4;
 static_assert(sizeof(EvClass) == 96 && FIXED_SMEM % 16 == 0, "shared memory layout");
 
 }  // namespace
@@ -1078,6 +1167,19 @@ void SparseEngine::launch(uint64_t first_shot, uint64_t n_shots, uint8_t *main_o
     const uint32_t S = 1u << I.log_s;
     if (first_shot % S != 0) {
         throw std::invalid_argument("shot offset must be a multiple of the engine's tile height (" + std::to_string(S) + " shots)");
+    }
+    {
+        // a block numbers its (sequence, slice) tickets with 32 bits: cut launches that would run out of numbers
+        const uint64_t seq_max = 0xFFFF0000ull / std::max<uint32_t>(1u, I.n_slices) - 1;
+        const uint64_t shots_max = seq_max * (uint64_t)I.num_sms * S;
+        if (n_shots > shots_max) {
+            const uint64_t mb = ((uint64_t)I.main_bits + 7) / 8, ob = ((uint64_t)I.obs_bits + 7) / 8;
+            for (uint64_t done = 0; done < n_shots; done += shots_max) {
+                launch(first_shot + done, std::min(shots_max, n_shots - done), main_out ? main_out + done * (main_pitch ? main_pitch : mb) : nullptr,
+                       main_pitch, obs_out ? obs_out + done * (obs_pitch ? obs_pitch : ob) : nullptr, obs_pitch, seed, stream);
+            }
+            return;
+        }
     }
     SparseParams p{};
     p.classes = (const EvClass *)I.d_classes;
