@@ -422,12 +422,12 @@ def main():
             "alu_bound": {"lop3_per_shot": ALG_LOP3_PER_SHOT, "achieved_lop3_per_s": per_gpu_rate_interp * ALG_LOP3_PER_SHOT,
                           "peak_lop3_per_s": lop3_peak, "frac": per_gpu_rate_interp * ALG_LOP3_PER_SHOT / lop3_peak,
                           "note": "word-ops of the reference's frame algorithm; the event engine does not execute them (it is "
-                                  "bound by instruction issue, see issue_bound)" if engine == "events" else "",
+                                  "latency-bound at 32 warps per SM, see issue_bound and profiles/r2_notes.md)" if engine == "events" else "",
                           "peak_basis": f"measured: LOP3 microbenchmark in this run = {lanes:.2f} lanes/clk/SM "
                                         f"({lop3['lane_ops_per_sec'] / 1e12:.2f} T lane-ops/s at {lop3['sm_mhz']:.0f} MHz) x 148 SMs x "
                                         f"{sm_mhz:.0f} MHz sampled during the timed region",
                           "lop3_probe": lop3},
-            # what binds the event engine: warp instructions per shot (ncu capture) against 4 issue slots per clock and SM
+            # the event engine's instruction stream: warp instructions per shot (ncu capture) against 4 issue slots per clock and SM
             "issue_bound": (None if cap is None or engine != "events" else {
                 "warp_instructions_per_shot": float(cap["warp_instructions"]) / float(cap["shots"]),
                 "achieved_warp_inst_per_s": per_gpu_rate_interp * float(cap["warp_instructions"]) / float(cap["shots"]),
