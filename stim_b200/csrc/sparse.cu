@@ -459,8 +459,10 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
             const uint64_t gt = p.tile0 + blockIdx.x + (uint64_t)q * gridDim.x;
             c2 = (uint32_t)gt;
             c3 = SPARSE_TAG | (uint32_t)(gt >> 32);
-            rowbase_m = (b * p.img_bytes + c[4]) * 8u;
-            rowbase_o = (b * p.img_bytes + p.obs_img_off + c[5]) * 8u;
+            uint32_t pm, po;
+            phases_of(q, &pm, &po);  // (recomputed here rather than read from the writer's control words)
+            rowbase_m = (b * p.img_bytes + pm) * 8u;
+            rowbase_o = (b * p.img_bytes + p.obs_img_off + po) * 8u;
             entered_q = q;
         }
         const uint32_t sl = T - (q_end - p.n_slices);
