@@ -289,6 +289,17 @@ def main():
     # Headline: the caller's page-locked buffer at the same 2^24 shots per step when the host can pin 32.7 GB per rank
     # (else the largest power of two it can; every rank uses the same size, so the decision is taken together).
     e2e_log2 = min(args.e2e_shots_log2, shots.bit_length() - 1)
+    try:  # never pin more than 40 % of the host memory that is available, all ranks together
+        with open("/proc/meminfo") as f:
+            avail = next(int(ln.split()[1]) * 1024 for ln in f if ln.startswith("MemAvailable"))
+        while e2e_log2 > 16 and world * (nbytes << e2e_log2) > 0.4 * avail:
+            e2e_log2 -= 1
+    except (OSError, StopIteration, ValueError):
+        pass
+    if world > 1:
+        t = torch.tensor([float(e2e_log2)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        e2e_log2 = int(t.item())
     host = None
     while host is None:
         try:
