@@ -180,11 +180,31 @@ struct Sim {
     std::vector<uint8_t> sign;
     std::vector<uint8_t> record;
 
-    explicit Sim(size_t n) : n(n), nw((n + 63) / 64 + 1), X(2 * n * nw, 0), Z(2 * n * nw, 0), sign(2 * n, 0) {
+    // Words [lo[r], hi[r]) contain every non-zero word of row r (a superset is fine): the rows of a QEC circuit have local
+    // support, a product only needs the words of its right-hand side (d = 51: 3-5 of 83). Not used by the step-by-step
+    // path (GSTIM_TABLEAU_SLOW=1), which the tests compare against.
+    std::vector<uint32_t> lo, hi;
+
+    explicit Sim(size_t n)
+        : n(n), nw((n + 63) / 64 + 1), X(2 * n * nw, 0), Z(2 * n * nw, 0), sign(2 * n, 0), lo(2 * n, 0), hi(2 * n, 0) {
         for (size_t q = 0; q < n; q++) {
             X[(2 * q) * nw + q / 64] |= 1ull << (q % 64);
             Z[(2 * q + 1) * nw + q / 64] |= 1ull << (q % 64);
+            lo[2 * q] = lo[2 * q + 1] = (uint32_t)(q / 64);
+            hi[2 * q] = hi[2 * q + 1] = (uint32_t)(q / 64 + 1);
         }
+    }
+    void touch(size_t r, size_t w) {
+        lo[r] = std::min<uint32_t>(lo[r], (uint32_t)w);
+        hi[r] = std::max<uint32_t>(hi[r], (uint32_t)w + 1);
+    }
+    void rescan(size_t r) {
+        const uint64_t *x = &X[r * nw], *z = &Z[r * nw];
+        size_t a = 0, b = nw;
+        while (a < nw && (x[a] | z[a]) == 0) a++;
+        while (b > a && (x[b - 1] | z[b - 1]) == 0) b--;
+        lo[r] = (uint32_t)(a < b ? a : 0);
+        hi[r] = (uint32_t)(a < b ? b : 0);
     }
     uint64_t *xr(size_t r) { return &X[r * nw]; }
     uint64_t *zr(size_t r) { return &Z[r * nw]; }
@@ -193,7 +213,8 @@ struct Sim {
     int mul_into(uint64_t *ax, uint64_t *az, size_t r) {
         const uint64_t *bx = xr(r), *bz = zr(r);
         long plus = 0, minus = 0;
-        for (size_t w = 0; w < nw; w++) {
+        const size_t w0 = slow_column_ops ? 0 : lo[r], w1 = slow_column_ops ? nw : hi[r];
+        for (size_t w = w0; w < w1; w++) {
             uint64_t xa = ax[w], za = az[w], xb = bx[w], zb = bz[w];
             uint64_t p = (xa & ~za & xb & zb) | (xa & za & ~xb & zb) | (~xa & za & xb & ~zb);
             uint64_t m = (xa & za & xb & ~zb) | (~xa & za & xb & zb) | (xa & ~za & ~xb & zb);
@@ -227,6 +248,16 @@ struct Sim {
     uint64_t *sz(int g) { return &scratch[(size_t)(2 * g + 1) * nw]; }
 
     void gate1(const Table1 &t, size_t q) {
+        if (!slow_column_ops && t.img[1] == 2 && t.img[2] == 1 && !t.sgn[1] && !t.sgn[2]) {
+            // H: the two generator images trade places (a third of a surface-code circuit's gates)
+            const size_t a = std::min(lo[2 * q], lo[2 * q + 1]), b = std::max(hi[2 * q], hi[2 * q + 1]);
+            std::swap_ranges(xr(2 * q) + a, xr(2 * q) + b, xr(2 * q + 1) + a);
+            std::swap_ranges(zr(2 * q) + a, zr(2 * q) + b, zr(2 * q + 1) + a);
+            std::swap(sign[2 * q], sign[2 * q + 1]);
+            std::swap(lo[2 * q], lo[2 * q + 1]);
+            std::swap(hi[2 * q], hi[2 * q + 1]);
+            return;
+        }
         scratch.resize(8 * nw);
         uint8_t ns[2];
         bool changed[2];
@@ -242,6 +273,7 @@ struct Sim {
                 memcpy(xr(2 * q + g), sx(g), nw * 8);
                 memcpy(zr(2 * q + g), sz(g), nw * 8);
                 sign[2 * q + g] = ns[g];
+                rescan(2 * q + g);
             }
         }
     }
@@ -278,6 +310,10 @@ struct Sim {
                     throw std::logic_error("internal: non-Hermitian row in the inverse tableau");
                 }
                 sign[rows_of[g]] = (uint8_t)((e >> 1) & 1);
+                if (hi[rows_of[h]] > lo[rows_of[h]]) {
+                    touch(rows_of[g], lo[rows_of[h]]);
+                    touch(rows_of[g], hi[rows_of[h]] - 1);
+                }
                 changed[g] = false;
             }
         }
@@ -293,6 +329,7 @@ struct Sim {
                 memcpy(xr(rows[g]), sx(g), nw * 8);
                 memcpy(zr(rows[g]), sz(g), nw * 8);
                 sign[rows[g]] = ns[g];
+                rescan(rows[g]);
             }
         }
     }
@@ -303,9 +340,266 @@ struct Sim {
         gate2(tables().inv2.at(name), a, b);
     }
     void pauli(int code, size_t q) {  // X: 1, Z: 2, Y: 3 applied to the state
+        if (tmode) {
+            const size_t rz = phys_row(2 * q + 1), rx = phys_row(2 * q);
+            if (code & 1) ST[rz / 64] ^= 1ull << (rz % 64);
+            if (code & 2) ST[rx / 64] ^= 1ull << (rx % 64);
+            return;
+        }
         if (code & 1) sign[2 * q + 1] ^= 1;  // X flips the sign of T^dag Z_q T
         if (code & 2) sign[2 * q] ^= 1;
     }
+
+    // ---- transposed working copy for runs of random measurements ------------------------------------------------
+    // A random measurement applies a handful of input-side column operations to ALL 2n rows; in the row-major layout
+    // every one of them touches 2n cache lines (d = 51: 10 402 rows, 0.6 ms per collapse, 5 201 collapses). An instruction
+    // with many targets (RX on every data qubit, the first round's MR) therefore switches to a column-major copy — XT[j] /
+    // ZT[j] = the bits of column j over all rows, ST = the signs as one bit vector — in which a column operation is a
+    // word-parallel pass over ~2n/64 words, evaluated generically from the gate's (image, sign) table by minterms. The only
+    // output-side gate needed while the copy is live is H (X-basis targets): it swaps the adjacent rows 2q, 2q+1.
+    // The copy is transposed back at the end of the instruction. Same operations in the same order as the
+    // step-by-step path (GSTIM_TABLEAU_SLOW=1), which the tests compare against.
+    bool tmode = false, t_allowed = false;
+    bool t_swapped = false;  // rows 2 t_swap_q and 2 t_swap_q + 1 are to be read as exchanged (a pending H)
+    size_t t_swap_q = 0;
+    size_t phys_row(size_t r) const {
+        return (t_swapped && r / 2 == t_swap_q) ? (r ^ 1) : r;
+    }
+    // row-major cache of one 64-row block of the column-major copy (word t_blk of every column): consecutive targets sit
+    // in the same block, and a collapse changes only the columns it touches
+    size_t t_blk = SIZE_MAX;
+    std::vector<uint64_t> t_bx, t_bz;
+    void load_block(size_t blk) {
+        t_bx.resize(n);
+        t_bz.resize(n);
+        for (size_t j = 0; j < n; j++) {
+            t_bx[j] = XT[j * rw + blk];
+            t_bz[j] = ZT[j * rw + blk];
+        }
+        t_blk = blk;
+    }
+    void refresh_col(size_t j) {
+        if (t_blk != SIZE_MAX) {
+            t_bx[j] = XT[j * rw + t_blk];
+            t_bz[j] = ZT[j * rw + t_blk];
+        }
+    }
+    int t_policy = 1;  // 0 never, 1 automatic, 2 at the first random measurement (tests)
+    size_t t_randoms = 0, t_remaining = 0;
+    size_t rw = 0;
+    std::vector<uint64_t> XT, ZT, ST;
+
+    bool want_transposed() {
+        if (!t_allowed || t_policy == 0) {
+            return false;
+        }
+        if (t_policy == 2) {
+            return true;
+        }
+        // the two transpositions cost about as much as twenty collapse passes
+        return ++t_randoms >= 4 && t_remaining >= 32 && n >= 256;
+    }
+    static void transpose64(uint64_t *a) {  // bit c of a[r] <-> bit r of a[c]
+        uint64_t m = 0x00000000FFFFFFFFull;
+        for (unsigned j = 32; j != 0; j >>= 1, m ^= m << j) {
+            for (unsigned k = 0; k < 64; k = (k + j + 1) & ~j) {
+                const uint64_t t = ((a[k] >> j) ^ a[k + j]) & m;
+                a[k] ^= t << j;
+                a[k + j] ^= t;
+            }
+        }
+    }
+    void transpose_to(const std::vector<uint64_t> &rows, std::vector<uint64_t> &cols) {
+        cols.assign(nw * 64 * rw, 0);
+        uint64_t a[64];
+        for (size_t rb = 0; rb < rw; rb++) {
+            for (size_t w = 0; w < nw; w++) {
+                bool any = false;
+                for (size_t i = 0; i < 64; i++) {
+                    const size_t r = rb * 64 + i;
+                    a[i] = r < 2 * n ? rows[r * nw + w] : 0;
+                    any |= a[i] != 0;
+                }
+                if (!any) {
+                    continue;
+                }
+                transpose64(a);
+                for (size_t c = 0; c < 64; c++) {
+                    cols[(w * 64 + c) * rw + rb] = a[c];
+                }
+            }
+        }
+    }
+    void transpose_from(const std::vector<uint64_t> &cols, std::vector<uint64_t> &rows) {
+        uint64_t a[64];
+        for (size_t rb = 0; rb < rw; rb++) {
+            for (size_t w = 0; w < nw; w++) {
+                for (size_t c = 0; c < 64; c++) {
+                    a[c] = cols[(w * 64 + c) * rw + rb];
+                }
+                transpose64(a);
+                for (size_t i = 0; i < 64; i++) {
+                    const size_t r = rb * 64 + i;
+                    if (r < 2 * n) {
+                        rows[r * nw + w] = a[i];
+                    }
+                }
+            }
+        }
+    }
+    void enter_t() {
+        rw = (2 * n + 63) / 64;
+        transpose_to(X, XT);
+        transpose_to(Z, ZT);
+        ST.assign(rw, 0);
+        for (size_t r = 0; r < 2 * n; r++) {
+            ST[r / 64] |= (uint64_t)(sign[r] & 1) << (r % 64);
+        }
+        t_blk = SIZE_MAX;
+        t_swapped = false;
+        tmode = true;
+    }
+    void exit_t() {
+        if (!tmode) {
+            return;
+        }
+        if (t_swapped) {
+            swap_rows_t(t_swap_q);
+            t_swapped = false;
+        }
+        transpose_from(XT, X);
+        transpose_from(ZT, Z);
+        for (size_t r = 0; r < 2 * n; r++) {
+            sign[r] = (uint8_t)((ST[r / 64] >> (r % 64)) & 1);
+            rescan(r);
+        }
+        tmode = false;
+    }
+    bool bit_t(const std::vector<uint64_t> &m, size_t col, size_t row) const {
+        return (m[col * rw + row / 64] >> (row % 64)) & 1;
+    }
+    void swap_rows_t(size_t q) {  // H on qubit q: T^dag X_q T <-> T^dag Z_q T
+        const size_t w = (2 * q) / 64, b = (2 * q) % 64;  // (2q is even: both rows sit in the same word)
+        auto swap_in = [&](uint64_t &v) {
+            const uint64_t t = ((v >> b) ^ (v >> (b + 1))) & 1ull;
+            v ^= (t << b) | (t << (b + 1));
+        };
+        for (size_t j = 0; j < n; j++) {
+            swap_in(XT[j * rw + w]);
+            swap_in(ZT[j * rw + w]);
+        }
+        swap_in(ST[w]);
+        if (w == t_blk) {
+            t_blk = SIZE_MAX;
+        }
+    }
+    // every row R <- C^dag R C for a two-column / one-column operation given by its table, all rows at once
+    void col2_t(const Table2 &t, size_t k, size_t j) {
+        int codes[16], nc = 0;
+        for (int c = 1; c < 16; c++) {
+            if (t.img[c] != c || t.sgn[c]) {
+                codes[nc++] = c;
+            }
+        }
+        uint64_t *xk = &XT[k * rw], *zk = &ZT[k * rw], *xj = &XT[j * rw], *zj = &ZT[j * rw];
+        for (size_t w = 0; w < rw; w++) {
+            const uint64_t v[4] = {xk[w], zk[w], xj[w], zj[w]};
+            if ((v[0] | v[1] | v[2] | v[3]) == 0) {
+                continue;
+            }
+            uint64_t d[4] = {0, 0, 0, 0}, ds = 0;
+            for (int i = 0; i < nc; i++) {
+                const int c = codes[i];
+                uint64_t m = ~0ull;
+                for (int b = 0; b < 4; b++) {
+                    m &= ((c >> b) & 1) ? v[b] : ~v[b];
+                }
+                if (m == 0) {
+                    continue;
+                }
+                const int delta = t.img[c] ^ c;
+                for (int b = 0; b < 4; b++) {
+                    if ((delta >> b) & 1) {
+                        d[b] |= m;
+                    }
+                }
+                if (t.sgn[c]) {
+                    ds |= m;
+                }
+            }
+            xk[w] = v[0] ^ d[0];
+            zk[w] = v[1] ^ d[1];
+            xj[w] = v[2] ^ d[2];
+            zj[w] = v[3] ^ d[3];
+            ST[w] ^= ds;
+        }
+    }
+    void col1_t(const Table1 &t, size_t k) {
+        uint64_t *xk = &XT[k * rw], *zk = &ZT[k * rw];
+        for (size_t w = 0; w < rw; w++) {
+            const uint64_t x = xk[w], z = zk[w];
+            uint64_t dx = 0, dz = 0, ds = 0;
+            for (int c = 1; c < 4; c++) {
+                const uint64_t m = ((c & 1) ? x : ~x) & ((c & 2) ? z : ~z);
+                const int delta = t.img[c] ^ c;
+                if (delta & 1) dx |= m;
+                if (delta & 2) dz |= m;
+                if (t.sgn[c]) ds |= m;
+            }
+            xk[w] = x ^ dx;
+            zk[w] = z ^ dz;
+            ST[w] ^= ds;
+        }
+    }
+    bool measure_z_t(size_t q) {
+        const size_t r = phys_row(2 * q + 1);
+        if (r / 64 != t_blk) {
+            load_block(r / 64);
+        }
+        const unsigned rb = (unsigned)(r % 64);
+        size_t k = SIZE_MAX;
+        std::vector<size_t> &cols = t_cols;
+        cols.clear();
+        for (size_t j = 0; j < n; j++) {
+            if ((t_bx[j] >> rb) & 1) {
+                if (k == SIZE_MAX) {
+                    k = j;
+                } else {
+                    cols.push_back(j);
+                }
+            }
+        }
+        if (k == SIZE_MAX) {
+            return bit_t(ST, 0, r);
+        }
+        const Tables &tb = tables();
+        const Table2 &cx = tb.inv2.at("CX"), &cz = tb.inv2.at("CZ");
+        for (size_t j : cols) {
+            col2_t(cx, k, j);
+            refresh_col(j);
+        }
+        refresh_col(k);
+        cols.clear();
+        for (size_t j = 0; j < n; j++) {
+            if (j != k && ((t_bz[j] >> rb) & 1)) {
+                cols.push_back(j);
+            }
+        }
+        for (size_t j : cols) {
+            col2_t(cz, k, j);
+            refresh_col(j);
+        }
+        if (bit_t(ZT, k, r)) {
+            col1_t(tb.inv1.at("S"), k);
+        }
+        col1_t(tb.inv1.at("H"), k);
+        if (bit_t(ST, 0, r)) {
+            col1_t(tb.inv1.at("X"), k);
+        }
+        refresh_col(k);
+        return false;
+    }
+    std::vector<size_t> t_cols;
 
     // ---- input-side column operations: T <- T C, every row R <- C^dag R C -----------------------------------
     void col1(const Table1 &t, size_t k) {
@@ -339,9 +633,12 @@ struct Sim {
 
     // Z-basis measurement of qubit q; a random outcome is forced to 0.
     bool measure_z(size_t q) {
+        if (tmode) {
+            return measure_z_t(q);
+        }
         const size_t r = 2 * q + 1;
         size_t k = SIZE_MAX;
-        for (size_t w = 0; w < nw && k == SIZE_MAX; w++) {
+        for (size_t w = slow_column_ops ? 0 : lo[r]; w < (slow_column_ops ? nw : hi[r]) && k == SIZE_MAX; w++) {
             if (xr(r)[w]) {
                 k = w * 64 + (size_t)__builtin_ctzll(xr(r)[w]);
             }
@@ -351,6 +648,10 @@ struct Sim {
         }
         const Tables &tb = tables();
         if (!slow_column_ops) {
+            if (want_transposed()) {
+                enter_t();
+                return measure_z_t(q);
+            }
             collapse_fused(r, k);
             return false;
         }
@@ -423,6 +724,9 @@ struct Sim {
                         const int dj = d >> 2;
                         x[wj] = (x[wj] & ~bj) | ((dj & 1) ? bj : 0);
                         z[wj] = (z[wj] & ~bj) | ((dj & 2) ? bj : 0);
+                        if (dj) {
+                            touch(row, wj);
+                        }
                     }
                 } else if (ck) {
                     sg ^= st.t1->sgn[ck];
@@ -431,6 +735,9 @@ struct Sim {
             }
             x[wk] = (x[wk] & ~bk) | ((ck & 1) ? bk : 0);
             z[wk] = (z[wk] & ~bk) | ((ck & 2) ? bk : 0);
+            if (ck) {
+                touch(row, wk);
+            }
         };
         // row r first (it decides S and X), then every other row with the complete list
         const size_t n2 = steps.size();
@@ -470,6 +777,7 @@ struct Sim {
             }
             xr(r)[wk] = (xr(r)[wk] & ~bk) | ((c & 1) ? bk : 0);
             zr(r)[wk] = (zr(r)[wk] & ~bk) | ((c & 2) ? bk : 0);
+            touch(r, wk);
         }
         for (size_t row = 0; row < 2 * n; row++) {
             if (row != r) {
@@ -480,6 +788,20 @@ struct Sim {
     }
 
     void to_z_basis(uint32_t basis, size_t q) {
+        if (tmode && basis == GB_Y) {
+            exit_t();  // (never entered for Y-basis instructions; kept for safety)
+        }
+        if (tmode) {
+            if (basis == GB_X) {  // H on q = the two rows of q trade places: done by renaming while the copy is live
+                if (t_swapped && t_swap_q != q) {
+                    swap_rows_t(t_swap_q);
+                    t_swapped = false;
+                }
+                t_swapped = !t_swapped;
+                t_swap_q = q;
+            }
+            return;
+        }
         if (basis == GB_X) {
             gate1("H", q);
         } else if (basis == GB_Y) {
@@ -558,6 +880,8 @@ std::vector<uint8_t> reference_sample(const Circuit &circuit) {
     {
         const char *e = getenv("GSTIM_TABLEAU_SLOW");  // differential testing of the fused column pass
         sim.slow_column_ops = e != nullptr && e[0] == '1';
+        const char *t = getenv("GSTIM_TABLEAU_TRANSPOSE");  // off | force (tests); default: automatic
+        sim.t_policy = t == nullptr ? 1 : std::string(t) == "off" ? 0 : std::string(t) == "force" ? 2 : 1;
     }
     auto rec_value = [&](uint32_t t, const char *gate) -> bool {
         uint64_t k = t & T_VALUE_MASK;
@@ -613,7 +937,11 @@ std::vector<uint8_t> reference_sample(const Circuit &circuit) {
             } break;
             case GateCat::MEASURE: {
                 uint32_t basis = g.param & 3, kind = g.param >> 2;
+                sim.t_allowed = basis != GB_Y;
+                sim.t_randoms = 0;
+                sim.t_remaining = op.targets.size();
                 for (uint32_t t : op.targets) {
+                    sim.t_remaining--;
                     size_t q = t & T_VALUE_MASK;
                     if (kind == GK_R) {
                         sim.reset(basis, q);
@@ -628,6 +956,8 @@ std::vector<uint8_t> reference_sample(const Circuit &circuit) {
                         sim.to_z_basis(basis, q);
                     }
                 }
+                sim.exit_t();
+                sim.t_allowed = false;
             } break;
             case GateCat::MPAD:
                 for (uint32_t t : op.targets) {

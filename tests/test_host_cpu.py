@@ -313,7 +313,8 @@ def test_lowered_golden_circuits_reproduce_the_reference_on_the_emulator(case):
 def test_reference_sample_matches_the_reference_and_its_own_slow_path(monkeypatch):
     """gstim_reference_sample (host inverse-tableau simulator, replaces TableauSimulator::reference_sample_circuit):
     equals the reference's sample on the golden circuits, and its fast paths (fused column pass for random measurements,
-    in-place row products) equal the step-by-step path on random Clifford circuits."""
+    transposed working copy for instructions with many targets, in-place row products) equal the step-by-step path on
+    random Clifford circuits."""
     import random
 
     from golden_util import load_cases
@@ -341,8 +342,12 @@ def test_reference_sample_matches_the_reference_and_its_own_slow_path(monkeypatc
             elif r < 0.8:
                 a, b = rng.sample(range(n), 2)
                 lines.append(f"{rng.choice(g2)} {a} {b}")
-            elif r < 0.95:
+            elif r < 0.9:
                 lines.append(f"{rng.choice(ms)} {rng.randrange(n)}")
+            elif r < 0.95:  # many targets in one instruction (the transposed working copy of tableau_ref.cc)
+                gate = rng.choice(ms)
+                lines.append(f"{gate} " + " ".join(("!" if gate[0] == "M" and rng.random() < 0.1 else "") + str(q)
+                                                   for q in rng.sample(range(n), rng.randrange(1, n + 1))))
             else:
                 lines.append("MPP " + "*".join(rng.choice("XYZ") + str(q) for q in rng.sample(range(n), min(n, 3))))
         lines.append("M " + " ".join(map(str, range(n))))
@@ -351,5 +356,10 @@ def test_reference_sample_matches_the_reference_and_its_own_slow_path(monkeypatc
         monkeypatch.setenv("GSTIM_TABLEAU_SLOW", "1")
         slow = rs.reference_sample_bits(text, m)
         monkeypatch.setenv("GSTIM_TABLEAU_SLOW", "0")
+        monkeypatch.setenv("GSTIM_TABLEAU_TRANSPOSE", "off")
         fast = rs.reference_sample_bits(text, m)
         np.testing.assert_array_equal(fast, slow)
+        monkeypatch.setenv("GSTIM_TABLEAU_TRANSPOSE", "force")
+        transposed = rs.reference_sample_bits(text, m)
+        np.testing.assert_array_equal(transposed, slow)
+        monkeypatch.delenv("GSTIM_TABLEAU_TRANSPOSE")
