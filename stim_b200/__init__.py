@@ -559,5 +559,76 @@ class CompiledMeasurementsToDetectionEventsConverter:
                 obs = np.unpackbits(obs, axis=1, bitorder="little", count=L).astype(np.bool_) if L else np.zeros((shots, 0), np.bool_)
         return (dets, obs) if separate else dets
 
+    def convert_file(self, *, measurements_filepath, measurements_format: str = "01", sweep_bits_filepath=None,
+                     sweep_bits_format: str = "01", detection_events_filepath, detection_events_format: str = "01",
+                     append_observables: bool = False, obs_out_filepath=None, obs_out_format: str = "01") -> None:
+        """File-to-file conversion (measurements_to_detection_events.pybind.cc:convert_file, command_m2d.cc): every one of the
+        six formats on either side."""
+        from . import _formats
+
+        with open(measurements_filepath, "rb") as f:
+            meas = _formats.read_shots(f.read(), measurements_format, self.num_measurements)
+        sweep = None
+        if sweep_bits_filepath is not None:
+            with open(sweep_bits_filepath, "rb") as f:
+                sweep = _formats.read_shots(f.read(), sweep_bits_format, self.num_sweep_bits)
+        D, L = self.num_detectors, self.num_observables
+        separate = obs_out_filepath is not None
+        res = self.convert(measurements=meas, sweep_bits=sweep, append_observables=bool(append_observables),
+                           separate_observables=separate, bit_packed=True)
+        dets, obs = res if separate else (res, None)
+        _write_rows(dets, D + (L if append_observables else 0), detection_events_filepath, detection_events_format, b"D", b"L", D)
+        if separate:
+            _write_rows(obs, L, obs_out_filepath, obs_out_format, b"L", b"L", L)
+
     def __repr__(self) -> str:
         return f"stim_b200.CompiledMeasurementsToDetectionEventsConverter({self._circuit!r}, skip_reference_sample={self._skip})"
+
+
+def _write_rows(rows: np.ndarray, n_bits: int, path, fmt: str, prefix1: bytes, prefix2: bytes, transition: int) -> None:
+    """Packed shot-major rows -> file in any of the six formats (writers.cc through gstim_write_shots_to_fd)."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    rows = rows if rows.size else rows.reshape(rows.shape[0], 0)
+    with open(path, "wb") as f:
+        buf = rows.ctypes.data_as(ctypes.c_void_p) if rows.size else None
+        _native.check(_native.lib().gstim_write_shots_to_fd(
+            buf, rows.shape[1], rows.shape[0], n_bits, f.fileno(), fmt.encode(), prefix1, prefix2, transition))
+
+
+def read_shot_data_file(*, path, format: str, bit_packed: bool = False, num_measurements: Optional[int] = None,
+                        num_detectors: Optional[int] = None, num_observables: Optional[int] = None,
+                        separate_observables: bool = False, bit_pack: bool = False):
+    """Mirror of stim.read_shot_data_file (/root/reference/src/stim/io/read_write.pybind.cc:99-142)."""
+    from . import _formats
+
+    if num_measurements is None and num_detectors is None and num_observables is None:
+        raise ValueError("Must specify num_measurements, num_detectors, num_observables.")
+    nm, nd, no = int(num_measurements or 0), int(num_detectors or 0), int(num_observables or 0)
+    bit_packed = bool(bit_packed or bit_pack)
+    with open(path, "rb") as f:
+        rows = _formats.read_shots(f.read(), format, nm + nd + no, num_measurements=nm, num_detectors=nd, num_observables=no)
+    bits = np.unpackbits(rows, axis=1, bitorder="little", count=nm + nd + no).astype(np.bool_) if nm + nd + no else \
+        np.zeros((rows.shape[0], 0), np.bool_)
+
+    def out(lo, hi):
+        part = bits[:, lo:hi]
+        if not bit_packed:
+            return np.ascontiguousarray(part)
+        return np.packbits(part, axis=1, bitorder="little") if hi > lo else np.zeros((bits.shape[0], 0), np.uint8)
+
+    if separate_observables:
+        return out(0, nm + nd), out(nm + nd, nm + nd + no)
+    return out(0, nm + nd + no)
+
+
+def write_shot_data_file(*, data, path, format: str, num_measurements: Optional[int] = None,
+                         num_detectors: Optional[int] = None, num_observables: Optional[int] = None) -> None:
+    """Mirror of stim.write_shot_data_file (/root/reference/src/stim/io/read_write.pybind.cc:144-181)."""
+    if num_measurements is None and num_detectors is None and num_observables is None:
+        raise ValueError("Must specify num_measurements, num_detectors, num_observables.")
+    nm, nd, no = int(num_measurements or 0), int(num_detectors or 0), int(num_observables or 0)
+    if nm != 0 and (nd != 0 or no != 0):
+        raise ValueError("num_measurements and (num_detectors or num_observables)")
+    n_bits = nm + nd + no
+    rows, _ = CompiledMeasurementsToDetectionEventsConverter._packed_rows(data, n_bits, "data")
+    _write_rows(rows, n_bits, path, format, b"D" if nm == 0 else b"M", b"L" if nm == 0 else b"M", nm + nd)

@@ -5,14 +5,13 @@
     python -m stim_b200 sample --shots N [--in FILE] [--out FILE] [--out_format F] [--seed S] [--skip_reference_sample]
     python -m stim_b200 sample_dem --shots N [--in FILE] [--out FILE] [--out_format F] [--obs_out FILE] [--obs_out_format F]
                                [--err_out FILE] [--err_out_format F] [--seed S]
-    python -m stim_b200 m2d --circuit FILE [--in FILE] [--in_format 01|b8] [--out FILE] [--out_format F]
-                            [--sweep FILE] [--sweep_format 01|b8] [--append_observables] [--obs_out FILE] [--obs_out_format F]
+    python -m stim_b200 m2d --circuit FILE [--in FILE] [--in_format F] [--out FILE] [--out_format F]
+                            [--sweep FILE] [--sweep_format F] [--append_observables] [--obs_out FILE] [--obs_out_format F]
                             [--skip_reference_sample]
 
 Same flags, defaults and output bytes as `stim detect` / `stim sample` / `stim sample_dem`
 (/root/reference/src/stim/cmd/command_detect.cc:23-79, command_sample.cc:25-71, command_sample_dem.cc:25-93, command_m2d.cc;
-m2d reads its measurement / sweep data in the 01 and b8 formats only,
-doc/usage_command_line.md); the sampling itself
+every format F is one of 01 b8 r8 hits dets ptb64 on both sides, doc/usage_command_line.md); the sampling itself
 runs on the GPU through the C ABI (there is no CPU fallback). Errors print to stderr and exit with status 1 like
 /root/reference/src/stim/main_namespaced.cc:113-122."""
 import argparse
@@ -50,9 +49,9 @@ def _parser():
     q = sub.add_parser("m2d", allow_abbrev=False)
     q.add_argument("--circuit", required=True)
     q.add_argument("--in", dest="inp", default=None)
-    q.add_argument("--in_format", default="01", choices=("01", "b8"))
+    q.add_argument("--in_format", default="01", choices=FORMATS)
     q.add_argument("--sweep", default=None)
-    q.add_argument("--sweep_format", default="01", choices=("01", "b8"))
+    q.add_argument("--sweep_format", default="01", choices=FORMATS)
     q.add_argument("--out", default=None)
     q.add_argument("--out_format", default="01", choices=FORMATS)
     q.add_argument("--obs_out", default=None)
@@ -62,55 +61,14 @@ def _parser():
     return p
 
 
-def _read_rows(data: bytes, fmt: str, n_bits: int):
-    """01 / b8 records -> packed uint8 rows (measure_record_reader.inl: one record per shot)."""
-    import numpy as np
-
-    nb = (n_bits + 7) // 8
-    if fmt == "b8":
-        if nb == 0:
-            raise ValueError("b8 data with zero bits per shot does not say how many shots there are.")
-        if len(data) % nb:
-            raise ValueError("b8 data ended in the middle of a record.")
-        return np.frombuffer(data, dtype=np.uint8).reshape(-1, nb).copy()
-    lines = data.decode().split("\n")
-    if lines and lines[-1] == "":
-        lines.pop()
-    bits = np.zeros((len(lines), n_bits), dtype=np.uint8)
-    for i, ln in enumerate(lines):
-        if len(ln) != n_bits or ln.strip("01"):
-            raise ValueError("01 data didn't have the expected number of 0/1 characters per line.")
-        bits[i] = np.frombuffer(ln.encode(), dtype=np.uint8) - 48
-    return np.packbits(bits, axis=1, bitorder="little") if n_bits else np.zeros((len(lines), 0), dtype=np.uint8)
-
-
 def _m2d(args) -> int:
-    import ctypes
-
-    from . import _native
-
     conv = stim_b200.Circuit(open(args.circuit).read()).compile_m2d_converter(skip_reference_sample=args.skip_reference_sample)
-    data = sys.stdin.buffer.read() if args.inp is None else open(args.inp, "rb").read()
-    meas = _read_rows(data, args.in_format, conv.num_measurements)
-    sweep = None if args.sweep is None else _read_rows(open(args.sweep, "rb").read(), args.sweep_format, conv.num_sweep_bits)
-    D, L = conv.num_detectors, conv.num_observables
-    want_obs_file = args.obs_out is not None
-    res = conv.convert(measurements=meas, sweep_bits=sweep, append_observables=args.append_observables,
-                       separate_observables=want_obs_file, bit_packed=True)
-    dets, obs = res if want_obs_file else (res, None)
-
-    def write(rows, n_bits, path, fmt, p1, p2, transition):
-        rows = rows if rows.size else rows.reshape(rows.shape[0], 0)
-        with open(path, "wb") as f:
-            buf = rows.ctypes.data_as(ctypes.c_void_p) if rows.size else None
-            _native.check(_native.lib().gstim_write_shots_to_fd(
-                buf, rows.shape[1], rows.shape[0], n_bits, f.fileno(), fmt.encode(), p1, p2, transition))
-
     sys.stdout.flush()
-    write(dets, D + (L if args.append_observables else 0), args.out if args.out is not None else "/dev/stdout", args.out_format,
-          b"D", b"L", D)
-    if want_obs_file:
-        write(obs, L, args.obs_out, args.obs_out_format, b"L", b"L", L)
+    conv.convert_file(
+        measurements_filepath=args.inp if args.inp is not None else "/dev/stdin", measurements_format=args.in_format,
+        sweep_bits_filepath=args.sweep, sweep_bits_format=args.sweep_format,
+        detection_events_filepath=args.out if args.out is not None else "/dev/stdout", detection_events_format=args.out_format,
+        append_observables=args.append_observables, obs_out_filepath=args.obs_out, obs_out_format=args.obs_out_format)
     return 0
 
 

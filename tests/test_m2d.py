@@ -129,3 +129,27 @@ def test_command_line_mirror_of_m2d(tmp_path):
     D = stim_b200.Circuit(case["circuit"]).num_detectors
     want = "".join("shot" + "".join(f" {'D' if j < D else 'L'}{j if j < D else j - D}" for j in np.flatnonzero(row)) + "\n" for row in exp)
     assert r.stdout.decode() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["r8", "hits", "dets", "b8"])
+def test_convert_file_reads_and_writes_every_format(tmp_path, fmt):
+    """convert_file (measurements_to_detection_events.pybind.cc, command_m2d.cc): measurement and sweep data in `fmt`, the
+    detection events written in `fmt` and the observables separately — decoded again they equal the reference's 01 output."""
+    case = next(c for c in CASES if c["name"] == "sweep_feedback_repeat")
+    circ = stim_b200.Circuit(case["circuit"])
+    conv = circ.compile_m2d_converter()
+    shots = case["shots"]
+    meas = bits01(case["measurements"]).reshape(shots, -1).astype(np.bool_)
+    sweep = bits01(case["sweep"]).reshape(shots, -1).astype(np.bool_)
+    stim_b200.write_shot_data_file(data=meas, path=str(tmp_path / "m"), format=fmt, num_measurements=meas.shape[1])
+    stim_b200.write_shot_data_file(data=sweep, path=str(tmp_path / "s"), format=fmt, num_measurements=sweep.shape[1])
+    conv.convert_file(measurements_filepath=str(tmp_path / "m"), measurements_format=fmt, sweep_bits_filepath=str(tmp_path / "s"),
+                      sweep_bits_format=fmt, detection_events_filepath=str(tmp_path / "d"), detection_events_format=fmt,
+                      obs_out_filepath=str(tmp_path / "o"), obs_out_format=fmt)
+    D, L = circ.num_detectors, circ.num_observables
+    dets = stim_b200.read_shot_data_file(path=str(tmp_path / "d"), format=fmt, num_detectors=D)
+    obs = stim_b200.read_shot_data_file(path=str(tmp_path / "o"), format=fmt, num_observables=L)
+    want = bits01(case["outputs"]["skip=0,sweep=1"]).reshape(shots, -1).astype(np.bool_)  # (detectors + appended observables)
+    np.testing.assert_array_equal(dets, want[:, :D])
+    np.testing.assert_array_equal(obs, want[:, D:])
