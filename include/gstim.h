@@ -233,6 +233,11 @@ int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void 
  * fired errors are asked for (errs_out / err_fd), the model is sampled by the event engine (GSTIM_ENGINE=interp switches
  * that off). Arrays of the table as in gstim_get_response_table (site_group = index of the mechanism in the flattened
  * model); what = 8: one word, the tile height. */
+/* Replays recorded errors instead of sampling (DemSampler::resample with replay_errors, src/stim/simulators/dem_sampler.inl:52-130;
+ * sample_dem --replay_err_in): errors [shots][ceil(E/8)] bit-packed host rows in, detector / observable rows out
+ * (bit-packed, host; NULL to skip; strides in bytes, 0 = dense). No randomness is consumed. */
+int gstim_dem_replay(gstim_dem_sampler *s, uint64_t shots, const void *errors, int64_t errors_stride, void *dets_out, int64_t dets_stride,
+                     void *obs_out, int64_t obs_stride);
 int gstim_dem_get_response_table(gstim_dem_sampler *s, int what, uint32_t *words, size_t *n_words);
 /* Flip counts of the D + L output bits (detectors, then observables) and of adjacent pairs over `shots` fresh shots,
  * reduced on the device (the statistic of the parity tests; see gstim_bit_counts). pair_host may be NULL. */
@@ -327,6 +332,9 @@ typedef struct gstim_flipsim gstim_flipsim;
 int gstim_flipsim_create(uint64_t batch_size, int disable_stabilizer_randomization, uint64_t num_qubits, uint64_t seed, int device,
                          gstim_flipsim **out);
 void gstim_flipsim_destroy(gstim_flipsim *h);
+/* FlipSimulator.copy (frame_simulator.pybind.cc:1476-1488): an independent simulator with the same frame, records and sizes.
+ * copy_rng != 0: the copy continues the same random stream as `src` (seed is ignored); else it starts the stream of `seed`. */
+int gstim_flipsim_copy(const gstim_flipsim *src, int copy_rng, uint64_t seed, gstim_flipsim **out);
 int gstim_flipsim_sizes(const gstim_flipsim *h, uint64_t *batch_size, uint64_t *num_qubits, uint64_t *num_measurements,
                         uint64_t *num_detectors, uint64_t *num_observables, uint64_t *row_words);
 /* FlipSimulator.do: applies a circuit fragment (any instructions, REPEAT blocks, noise, detectors; rec[-k] looks back

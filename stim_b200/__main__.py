@@ -4,7 +4,7 @@
                                [--append_observables | --prepend_observables] [--obs_out FILE] [--obs_out_format F]
     python -m stim_b200 sample --shots N [--in FILE] [--out FILE] [--out_format F] [--seed S] [--skip_reference_sample]
     python -m stim_b200 sample_dem --shots N [--in FILE] [--out FILE] [--out_format F] [--obs_out FILE] [--obs_out_format F]
-                               [--err_out FILE] [--err_out_format F] [--seed S]
+                               [--err_out FILE] [--err_out_format F] [--replay_err_in FILE] [--replay_err_in_format F] [--seed S]
     python -m stim_b200 m2d --circuit FILE [--in FILE] [--in_format F] [--out FILE] [--out_format F]
                             [--sweep FILE] [--sweep_format F] [--append_observables] [--obs_out FILE] [--obs_out_format F]
                             [--skip_reference_sample]
@@ -43,7 +43,7 @@ def _parser():
     q.add_argument("--shots", type=int, default=1)
     q.add_argument("--in", dest="inp", default=None)
     q.add_argument("--seed", type=int, default=None)
-    for flag in ("out", "obs_out", "err_out"):
+    for flag in ("out", "obs_out", "err_out", "replay_err_in"):
         q.add_argument("--" + flag, default=None)
         q.add_argument("--" + flag + "_format", default="01", choices=FORMATS)
     q = sub.add_parser("m2d", allow_abbrev=False)
@@ -85,7 +85,8 @@ def main(argv=None) -> int:
                 sampler.sample_write(
                     args.shots, det_out_file=args.out if args.out is not None else "/dev/stdout", det_out_format=args.out_format,
                     obs_out_file=args.obs_out, obs_out_format=args.obs_out_format, err_out_file=args.err_out,
-                    err_out_format=args.err_out_format)
+                    err_out_format=args.err_out_format, replay_err_in_file=args.replay_err_in,
+                    replay_err_in_format=args.replay_err_in_format)
             return 0
         circuit = stim_b200.Circuit(text)
         out_path = args.out if args.out is not None else "/dev/stdout"

@@ -110,6 +110,7 @@ _SIGNATURES = [
     ("gstim_dem_destroy", None, [_P]),
     ("gstim_dem_set_shot_offset", ctypes.c_int, [_P, ctypes.c_uint64]),
     ("gstim_dem_sample", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_uint32, _P, ctypes.c_int64, _P, ctypes.c_int64, _P, ctypes.c_int64]),
+    ("gstim_dem_replay", ctypes.c_int, [_P, ctypes.c_uint64, _P, ctypes.c_int64, _P, ctypes.c_int64, _P, ctypes.c_int64]),
     ("gstim_dem_get_response_table", ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_size_t)]),
     ("gstim_dem_bit_counts", ctypes.c_int, [_P, ctypes.c_uint64, _P, _P]),
     ("gstim_dem_sample_to_fd", ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p,
@@ -129,6 +130,7 @@ _SIGNATURES = [
                                          _P, ctypes.c_int64]),
     ("gstim_flipsim_create", ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(_P)]),
     ("gstim_flipsim_destroy", None, [_P]),
+    ("gstim_flipsim_copy", ctypes.c_int, [_P, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(_P)]),
     ("gstim_flipsim_sizes", ctypes.c_int, [_P] + [ctypes.POINTER(ctypes.c_uint64)] * 6),
     ("gstim_flipsim_do_text", ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_size_t]),
     ("gstim_flipsim_get_rows", ctypes.c_int, [_P, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _P]),

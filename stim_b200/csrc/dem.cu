@@ -430,12 +430,17 @@ struct gstim_dem_sampler {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     DevMem d_rates, d_tgt_off, d_tgt_row, d_table, d_rowmap, d_stage;
+    gstim_m2d *replay = nullptr;  // recorded errors -> detectors / observables (m2d.cu), built on first use
     ~gstim_dem_sampler() {
+        if (replay) {
+            gstim_m2d_destroy(replay);
+        }
         if (stream) {
             cudaStreamDestroy(stream);
         }
     }
 };
+gstim_m2d *gstim_m2d_from_lists(int device, uint64_t n_inputs, uint64_t D, uint64_t L, std::vector<std::vector<uint32_t>> recs);
 
 // (gstim_last_error lives in api.cu; DEM errors are reported through the same thread-local channel)
 void gstim_set_last_error(const char *msg);
@@ -785,6 +790,37 @@ int gstim_dem_set_shot_offset(gstim_dem_sampler *s, uint64_t offset) {
         }
         s->next_col = offset / GSTIM_COL_SHOTS;
     });
+}
+
+int gstim_dem_replay(gstim_dem_sampler *s, uint64_t shots, const void *errors, int64_t errors_stride, void *dets_out, int64_t dets_stride,
+                     void *obs_out, int64_t obs_stride) {
+    int built = dem_guarded([&] {
+        if (s == nullptr) {
+            throw std::invalid_argument("NULL sampler.");
+        }
+        if (s->replay == nullptr) {
+            const DemModel &m = s->model;
+            const uint64_t D = m.num_detectors, L = m.num_observables;
+            std::vector<std::vector<uint32_t>> recs(D + L);
+            for (size_t e = 0; e + 1 < m.tgt_off.size(); e++) {
+                for (uint32_t k = m.tgt_off[e]; k < m.tgt_off[e + 1]; k++) {
+                    const uint32_t t = m.tgt[k];
+                    std::vector<uint32_t> &row = recs[(t & 0x80000000u) ? D + (t & 0x7FFFFFFFu) : t];
+                    if (!row.empty() && row.back() == (uint32_t)e) {
+                        row.pop_back();  // a target listed twice by one mechanism cancels
+                    } else {
+                        row.push_back((uint32_t)e);
+                    }
+                }
+            }
+            s->replay = gstim_m2d_from_lists(s->device, m.probs.size(), D, L, std::move(recs));
+        }
+    });
+    if (built != GSTIM_OK) {
+        return built;
+    }
+    return gstim_m2d_convert(s->replay, shots, GSTIM_BIT_PACKED | (obs_out != nullptr ? GSTIM_SEPARATE_OBS : 0u), errors, errors_stride, nullptr, 0,
+                             dets_out, dets_stride, obs_out, obs_stride);
 }
 
 int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void *dets_out, int64_t dets_stride, void *obs_out,

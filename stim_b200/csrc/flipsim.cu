@@ -533,6 +533,37 @@ int gstim_flipsim_create(uint64_t batch_size, int disable_stabilizer_randomizati
     });
 }
 
+int gstim_flipsim_copy(const gstim_flipsim *src, int copy_rng, uint64_t seed, gstim_flipsim **out) {
+    return fs_guarded([&] {
+        if (src == nullptr || out == nullptr) {
+            throw std::invalid_argument("NULL argument.");
+        }
+        *out = nullptr;
+        auto h = std::make_unique<gstim_flipsim>();
+        h->device = src->device;
+        h->batch = src->batch;
+        h->W = src->W;
+        h->randomize = src->randomize;
+        h->seed = copy_rng ? src->seed : seed;
+        h->ordinal = copy_rng ? src->ordinal : 0;
+        ck(cudaSetDevice(h->device), "cudaSetDevice");
+        ck(cudaStreamSynchronize(src->stream), "sync");
+        ck(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        ck(cudaMalloc(&h->FLAG, (size_t)h->W * 4), "cudaMalloc");
+        ck(cudaMemcpyAsync(h->FLAG, src->FLAG, (size_t)h->W * 4, cudaMemcpyDeviceToDevice, h->stream), "copy");
+        const Table *from[5] = {&src->X, &src->Z, &src->REC, &src->DET, &src->OBS};
+        Table *to[5] = {&h->X, &h->Z, &h->REC, &h->DET, &h->OBS};
+        for (int i = 0; i < 5; i++) {
+            grow(h.get(), *to[i], from[i]->rows);
+            if (from[i]->rows) {
+                ck(cudaMemcpyAsync(to[i]->p, from[i]->p, from[i]->rows * (uint64_t)h->W * 4, cudaMemcpyDeviceToDevice, h->stream), "copy");
+            }
+        }
+        ck(cudaStreamSynchronize(h->stream), "sync");
+        *out = h.release();
+    });
+}
+
 void gstim_flipsim_destroy(gstim_flipsim *h) {
     if (h) {
         cudaSetDevice(h->device);

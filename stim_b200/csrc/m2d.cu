@@ -223,6 +223,28 @@ void upload_layout(gstim_m2d *h, bool append_obs) {
 
 }  // namespace
 
+// A converter from explicit source lists: output j = XOR of the input bits recs[j] (the DEM sampler's error replay, dem.cu).
+gstim_m2d *gstim_m2d_from_lists(int device, uint64_t n_inputs, uint64_t D, uint64_t L, std::vector<std::vector<uint32_t>> recs) {
+    auto h = std::make_unique<gstim_m2d>();
+    h->M = n_inputs;
+    h->D = D;
+    h->L = L;
+    h->n_sweep = 0;
+    h->recs = std::move(recs);
+    h->recs.resize(D + L);
+    h->sweeps.resize(D + L);
+    h->konst.assign(D + L, 0);
+    h->device = device;
+    ck(cudaSetDevice(device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    ck(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    ck(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    ck(cudaFuncSetAttribute(gstim_m2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin), "smem attribute");
+    return h.release();
+}
+
 extern "C" {
 
 int gstim_m2d_create_from_text(const char *circuit_text, size_t text_len, int skip_reference_sample, int device, gstim_m2d **out) {

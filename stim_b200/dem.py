@@ -67,11 +67,11 @@ class CompiledDemSampler:
 
     def sample(self, shots: int, *, bit_packed: bool = False, return_errors: bool = False,
                recorded_errors_to_replay=None) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]:
-        if recorded_errors_to_replay is not None:
-            raise ValueError("recorded_errors_to_replay is not supported by this sampler")
         shots = int(shots)
         if shots < 0:
             raise ValueError("shots must be non-negative")
+        if recorded_errors_to_replay is not None:
+            return self._replay(shots, recorded_errors_to_replay, bit_packed, return_errors)
         dt = np.uint8 if bit_packed else np.bool_
 
         def alloc(n_bits):
@@ -85,6 +85,39 @@ class CompiledDemSampler:
 
         _native.check(_native.lib().gstim_dem_sample(
             self._handle, shots, _native.BIT_PACKED if bit_packed else 0, ptr(dets), 0, ptr(obs), 0, ptr(errs), 0))
+        return dets, obs, errs
+
+    def _replay(self, shots: int, recorded, bit_packed: bool, return_errors: bool):
+        """recorded_errors_to_replay (dem_sampler.pybind.cc:sample): bool_[shots, num_errors] or uint8[shots, ceil(num_errors / 8)];
+        the detectors / observables those errors flip, no sampling."""
+        D, L, E = self._dem.num_detectors, self._dem.num_observables, self._dem.num_errors
+        a = np.asarray(recorded)
+        if a.ndim != 2 or a.shape[0] != shots:
+            raise ValueError("recorded_errors_to_replay.shape[0] != shots")
+        if a.dtype == np.bool_:
+            if a.shape[1] != E:
+                raise ValueError(f"recorded_errors_to_replay.dtype == bool_ but shape[1] != num_errors ({E})")
+            packed = np.packbits(a, axis=1, bitorder="little") if E else np.zeros((shots, 0), np.uint8)
+        elif a.dtype == np.uint8:
+            if a.shape[1] != (E + 7) // 8:
+                raise ValueError(f"recorded_errors_to_replay.dtype == uint8 but shape[1] != ceil(num_errors / 8) ({(E + 7) // 8})")
+            packed = np.ascontiguousarray(a)
+        else:
+            raise ValueError("recorded_errors_to_replay must have dtype bool_ or uint8")
+        dets = np.zeros((shots, (D + 7) // 8), dtype=np.uint8)
+        obs = np.zeros((shots, (L + 7) // 8), dtype=np.uint8)
+
+        def ptr(x):
+            return None if x.size == 0 else x.ctypes.data_as(ctypes.c_void_p)
+
+        if shots:
+            _native.check(_native.lib().gstim_dem_replay(self._handle, shots, ptr(packed), 0, ptr(dets), 0, ptr(obs), 0))
+        errs = packed if return_errors else None
+        if not bit_packed:
+            def unpack(x, n):
+                return np.unpackbits(x, axis=1, bitorder="little", count=n).astype(np.bool_) if n else np.zeros((shots, 0), np.bool_)
+            dets, obs = unpack(dets, D), unpack(obs, L)
+            errs = unpack(errs, E) if return_errors else None
         return dets, obs, errs
 
     def response_table(self) -> dict:
@@ -115,7 +148,21 @@ class CompiledDemSampler:
                      obs_out_format: str = "01", err_out_file=None, err_out_format: str = "01",
                      replay_err_in_file=None, replay_err_in_format: str = "01") -> None:
         if replay_err_in_file is not None:
-            raise ValueError("replay_err_in_file is not supported by this sampler")
+            from . import _formats
+            from . import _write_rows
+
+            with open(os.fspath(replay_err_in_file), "rb") as f:
+                errors = _formats.read_shots(f.read(), replay_err_in_format, self._dem.num_errors)
+            if errors.shape[0] < int(shots):
+                raise ValueError("The replay file held fewer shots than were requested.")
+            errors = errors[: int(shots)]
+            dets, obs, _ = self._replay(int(shots), errors, True, False)
+            D, L, E = self._dem.num_detectors, self._dem.num_observables, self._dem.num_errors
+            for rows, n, path, fmt, prefix in ((dets, D, det_out_file, det_out_format, b"D"), (obs, L, obs_out_file, obs_out_format, b"L"),
+                                               (errors, E, err_out_file, err_out_format, b"M")):
+                if path is not None:
+                    _write_rows(rows, n, os.fspath(path), fmt, prefix, prefix, n)
+            return
         files = []
         try:
             fds = []

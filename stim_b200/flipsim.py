@@ -32,6 +32,19 @@ class FlipSimulator:
             int(batch_size), int(bool(disable_stabilizer_randomization)), int(num_qubits), ctypes.c_uint64(int(seed)), int(device),
             ctypes.byref(self._handle)))
 
+    def copy(self, *, copy_rng: bool = False, seed=None) -> "FlipSimulator":
+        """Mirror of FlipSimulator.copy (frame_simulator.pybind.cc:1476-1488): same state; the copy's random stream is fresh
+        (seed or OS entropy) unless copy_rng=True."""
+        if copy_rng and seed is not None:
+            raise ValueError("seed and copy_rng are incompatible")
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        other = FlipSimulator.__new__(FlipSimulator)
+        other._handle = ctypes.c_void_p()
+        _native.check(_native.lib().gstim_flipsim_copy(self._handle, int(bool(copy_rng)), ctypes.c_uint64(int(seed)),
+                                                       ctypes.byref(other._handle)))
+        return other
+
     def __del__(self):
         h = getattr(self, "_handle", None)
         if h is not None and h.value and _native is not None:

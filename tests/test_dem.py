@@ -175,3 +175,44 @@ def test_cuda_dem_sampler_on_the_event_engine_equals_oracle(shots):
     more = s2.sample(200)[0]
     first = (shots + 127) // 128 * 128
     np.testing.assert_array_equal(more.astype(np.uint8), so.sample(t, t["slices"], t["tile_shots"], 7, first, 200, D + L)[:, :D])
+
+
+REPLAY = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "dem_replay_cases.json")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", REPLAY, ids=[c["name"] for c in REPLAY])
+def test_replaying_recorded_errors_reproduces_the_reference(case, tmp_path):
+    """sample(recorded_errors_to_replay=...) / --replay_err_in (dem_sampler.inl:52-130): the errors the reference sampled from a
+    noisy model give the detectors and observables the reference derived from them."""
+    dem = stim_b200.DetectorErrorModel(case["dem"])
+    D, L, E = dem.num_detectors, dem.num_observables, dem.num_errors
+    shots = case["shots"]
+    raw = {k: np.frombuffer(base64.b64decode(case[k]), dtype=np.uint8) for k in ("det", "obs", "err")}
+    errs = raw["err"].reshape(shots, (E + 7) // 8)
+    want_d = raw["det"].reshape(shots, (D + 7) // 8)
+    want_o = raw["obs"].reshape(shots, (L + 7) // 8)
+    sampler = dem.compile_sampler(seed=3)
+    d, o, e = sampler.sample(shots, bit_packed=True, return_errors=True, recorded_errors_to_replay=errs)
+    np.testing.assert_array_equal(d, want_d)
+    np.testing.assert_array_equal(o, want_o)
+    np.testing.assert_array_equal(e, errs)
+    d2, o2, e2 = sampler.sample(shots, recorded_errors_to_replay=np.unpackbits(errs, axis=1, bitorder="little", count=E).astype(np.bool_))
+    np.testing.assert_array_equal(np.packbits(d2, axis=1, bitorder="little") if D else d2.astype(np.uint8), want_d)
+    np.testing.assert_array_equal(np.packbits(o2, axis=1, bitorder="little") if L else o2.astype(np.uint8), want_o)
+    assert e2 is None
+    # files, through the command line mirror
+    import subprocess
+    import sys
+
+    (tmp_path / "m.dem").write_text(case["dem"])
+    (tmp_path / "e.b8").write_bytes(raw["err"].tobytes())
+    r = subprocess.run([sys.executable, "-m", "stim_b200", "sample_dem", "--shots", str(shots), "--in", str(tmp_path / "m.dem"),
+                        "--replay_err_in", str(tmp_path / "e.b8"), "--replay_err_in_format", "b8", "--out", str(tmp_path / "d.b8"),
+                        "--out_format", "b8", "--obs_out", str(tmp_path / "o.b8"), "--obs_out_format", "b8"],
+                       capture_output=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stderr.decode()
+    assert (tmp_path / "d.b8").read_bytes() == raw["det"].tobytes()
+    assert (tmp_path / "o.b8").read_bytes() == raw["obs"].tobytes()
+    with pytest.raises(ValueError):
+        sampler.sample(shots + 1, recorded_errors_to_replay=errs)

@@ -228,3 +228,28 @@ def test_noisy_instructions_match_the_bulk_sampler_statistically():
     p = (c1 + c2) / (2 * shots)
     z = (c1 - c2) / shots / np.sqrt(np.maximum(p * (1 - p), 1e-12) * 2 / shots)
     assert np.abs(z).max() < 5.0
+
+
+def test_copy_is_independent_and_copy_rng_continues_the_same_stream():
+    """FlipSimulator.copy (frame_simulator.pybind.cc:1476-1488)."""
+    s1 = stim_b200.FlipSimulator(batch_size=256, num_qubits=3, seed=11, disable_stabilizer_randomization=True)
+    s1.do("X_ERROR(0.4) 0 1 2\nM 0 1\nDETECTOR rec[-1]\nOBSERVABLE_INCLUDE(0) rec[-2]")
+    s2 = s1.copy(copy_rng=True)
+    s3 = s1.copy(seed=5)
+    for s in (s2, s3):
+        assert (s.batch_size, s.num_qubits, s.num_measurements, s.num_detectors, s.num_observables) == (256, 3, 2, 1, 1)
+        np.testing.assert_array_equal(s.get_measurement_flips(), s1.get_measurement_flips())
+        np.testing.assert_array_equal(s.get_detector_flips(), s1.get_detector_flips())
+        np.testing.assert_array_equal(s.get_observable_flips(), s1.get_observable_flips())
+        assert [str(p) for p in s.peek_pauli_flips()] == [str(p) for p in s1.peek_pauli_flips()]
+    more = "DEPOLARIZE1(0.3) 0 1 2\nM 0 1 2"
+    s1.do(more)
+    s2.do(more)
+    s3.do(more)
+    np.testing.assert_array_equal(s2.get_measurement_flips(), s1.get_measurement_flips())      # same stream
+    assert not np.array_equal(s3.get_measurement_flips(), s1.get_measurement_flips())          # its own stream
+    assert s3.num_measurements == 5
+    s2.clear()
+    assert s1.num_measurements == 5 and s2.num_measurements == 0                                # independent storage
+    with pytest.raises(ValueError, match="incompatible"):
+        s1.copy(copy_rng=True, seed=1)

@@ -6,7 +6,10 @@
   tests/golden/stats_big/dem_*.npz     per-detector flip counts, adjacent-pair counts and per-observable counts of
                                        `stim sample_dem` over 2^24 shots, for the 5 sigma tests
 
-    python tools/gen_dem_golden.py [cases] [stats]"""
+  tests/golden/dem_replay_cases.json   errors sampled by the reference from noisy models + the detectors / observables it derives
+                                       from them (also through its own --replay_err_in)
+
+    python tools/gen_dem_golden.py [cases] [replay] [stats]"""
 import base64
 import gzip
 import json
@@ -43,6 +46,33 @@ def run_sample_dem(text, shots, seed, fmt):
                         "--out_format", fmt, "--obs_out", p["obs"], "--obs_out_format", fmt, "--err_out", p["err"],
                         "--err_out_format", fmt], check=True)
         return {k: open(p[k], "rb").read() for k in ("det", "obs", "err")}
+
+
+def gen_replay():
+    """Noisy models: errors sampled by the reference, the detectors / observables it derives from them, and the reference's own
+    `--replay_err_in` run on those errors (must agree) -> tests/golden/dem_replay_cases.json (b8, base64)."""
+    import re
+
+    models = {name: re.sub(r"\((0|1)\)", "(0.3)", text) for name, text in CASES.items()}
+    models["c2_surface_d5"] = open(os.path.join(ROOT, "tests", "golden", "dem", "c2_surface_x_d5_r5.dem")).read()
+    out = []
+    for name, text in models.items():
+        shots = 96
+        with tempfile.TemporaryDirectory() as d:
+            p = {k: os.path.join(d, k) for k in ("in", "det", "obs", "err", "det2", "obs2")}
+            with open(p["in"], "w") as f:
+                f.write(text)
+            subprocess.run([STIM, "sample_dem", "--shots", str(shots), "--seed", "7", "--in", p["in"], "--out", p["det"], "--out_format", "b8",
+                            "--obs_out", p["obs"], "--obs_out_format", "b8", "--err_out", p["err"], "--err_out_format", "b8"], check=True)
+            subprocess.run([STIM, "sample_dem", "--shots", str(shots), "--in", p["in"], "--out", p["det2"], "--out_format", "b8",
+                            "--obs_out", p["obs2"], "--obs_out_format", "b8", "--replay_err_in", p["err"], "--replay_err_in_format", "b8"],
+                           check=True)
+            files = {k: open(p[k], "rb").read() for k in ("det", "obs", "err", "det2", "obs2")}
+        assert files["det"] == files["det2"] and files["obs"] == files["obs2"], name
+        out.append({"name": name, "dem": text, "shots": shots, **{k: base64.b64encode(files[k]).decode() for k in ("det", "obs", "err")}})
+    with open(os.path.join(ROOT, "tests", "golden", "dem_replay_cases.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("wrote", len(out), "replay cases")
 
 
 def gen_cases():
@@ -115,5 +145,7 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["cases", "stats"]
     if "cases" in what:
         gen_cases()
+    if "replay" in what:
+        gen_replay()
     if "stats" in what:
         gen_stats()
