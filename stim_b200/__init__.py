@@ -92,6 +92,15 @@ class Circuit:
     def num_observables(self) -> int:
         return int(self._stats.num_observables)
 
+    def reference_sample(self, *, bit_packed: bool = False) -> np.ndarray:
+        """Mirror of stim.Circuit.reference_sample (TableauSimulator::reference_sample_circuit, tableau_simulator.inl:1435-1438):
+        the noiseless sample with every random measurement result forced to 0; host stabilizer simulation (tableau_ref.cc)."""
+        from . import _reference_sample
+
+        m = self.num_measurements
+        packed = _reference_sample.reference_sample_bits(self._text, m)
+        return packed if bit_packed else np.unpackbits(packed, bitorder="little", count=m).astype(np.bool_)
+
     def compile_detector_sampler(self, *, seed=None, device: int = 0, engine: str = "auto") -> "CompiledDetectorSampler":
         """`engine` (not in the reference): "auto" | "interp" | "events" — include/gstim.h "sampling engines"."""
         return CompiledDetectorSampler(self, seed=seed, device=device, engine=engine)

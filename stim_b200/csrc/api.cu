@@ -17,6 +17,7 @@
 #include <stdexcept>
 #include <exception>
 #include <string>
+#include <sys/mman.h>
 #include <thread>
 #include <vector>
 
@@ -1062,6 +1063,15 @@ void sample_to_host(
         return attr.type == cudaMemoryTypeHost;
     };
     const bool direct = bit_packed && is_pinned(main_out) && is_pinned(obs_out);
+    if (!direct && main_out != nullptr && shots * main_pitch >= (64ull << 20) && env_u32("GSTIM_HUGEPAGE_HINT", 1)) {
+        // A fresh pageable result array is first touched by the copy threads below: ask for transparent huge pages so that the
+        // kernel zeroes and maps 2 MiB at a time instead of 4 KiB (a hint; ignored where THP is off).
+        const uintptr_t a = (reinterpret_cast<uintptr_t>(main_out) + 4095) & ~(uintptr_t)4095;
+        const uintptr_t b = (reinterpret_cast<uintptr_t>(main_out) + shots * main_pitch) & ~(uintptr_t)4095;
+        if (b > a) {
+            madvise(reinterpret_cast<void *>(a), b - a, MADV_HUGEPAGE);
+        }
+    }
 
     struct Pending {
         bool active = false;

@@ -327,6 +327,10 @@ def test_reference_sample_matches_the_reference_and_its_own_slow_path(monkeypatc
         got = np.unpackbits(rs.reference_sample_bits(case["circuit"], ref.size), bitorder="little")[: ref.size]
         np.testing.assert_array_equal(got, ref, err_msg=case["name"])
 
+    c = stim_b200.Circuit("X 1\nM 0 1\nH 2\nM 2\nMR !1")  # Circuit.reference_sample mirror
+    np.testing.assert_array_equal(c.reference_sample(), [False, True, False, False])
+    np.testing.assert_array_equal(c.reference_sample(bit_packed=True), [2])
+
     g1 = ["H", "S", "S_DAG", "SQRT_X", "SQRT_X_DAG", "SQRT_Y", "SQRT_Y_DAG", "H_XY", "H_YZ", "C_XYZ", "C_ZYX", "X", "Y", "Z"]
     g2 = ["CX", "CY", "CZ", "SWAP", "ISWAP", "ISWAP_DAG", "SQRT_XX", "SQRT_YY", "SQRT_ZZ", "XCX", "XCY", "XCZ", "YCX", "YCY", "YCZ",
           "CXSWAP", "SWAPCX", "CZSWAP"]
