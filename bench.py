@@ -94,21 +94,59 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region: NVML polled every ~2 ms from a thread of this process
+    (the timed region of a multi-GPU run is ~90 ms, shorter than one `nvidia-smi -lms` period when eight of them start at
+    once); `nvidia-smi` is the fallback when pynvml is missing."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index = index
-        self.samples = []
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            self.index = int(vis.split(",")[index]) if vis else index
+        except (ValueError, IndexError):
+            self.index = index
+        self.samples = []   # nvidia-smi lines
+        self.nvml = []      # (sm_mhz, reason bits)
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.max_mhz = None
+        self.source = None
+
+    def _poll_nvml(self, pynvml, handle):
+        while not self.stop_flag:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                try:
+                    bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    bits = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.nvml.append((float(sm), int(bits)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(pynvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -118,6 +156,16 @@ class ClockSampler:
             self.samples.append(line.strip())
 
     def stop(self):
+        if self.source == "nvml":
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(v for v, _ in self.nvml)
+            bits = 0
+            for _, b in self.nvml:
+                bits |= b
+            reasons = sorted(name for mask, name in self.NVML_REASONS if bits & mask)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -137,7 +185,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 def run_reference(shots_per_proc, nproc, seed0):
