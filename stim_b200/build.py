@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgstim.so")
 SOURCES = ["circuit.cc", "lowering.cc", "response.cc", "writers.cc", "tableau_ref.cc", "interp.cu", "kernels.cu", "sparse.cu", "api.cu", "dem.cu", "m2d.cu", "flipsim.cu"]
-HEADERS = ["circuit.h", "lowering.h", "response.h", "sparse.cuh", "writers.h", "tableau_ref.h", "kernels.cuh", "program.h", "log2_table.h", "log2_q26_table.h", "../../include/gstim.h"]
+HEADERS = ["circuit.h", "lowering.h", "response.h", "sparse.cuh", "hostpipe.h", "writers.h", "tableau_ref.h", "kernels.cuh", "program.h", "log2_table.h", "log2_q26_table.h", "../../include/gstim.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

@@ -35,6 +35,7 @@
 #include "../../include/gstim.h"
 #include "kernels.cuh"
 #include "lowering.h"
+#include "hostpipe.h"
 #include "sparse.cuh"
 #include "writers.h"
 
@@ -431,6 +432,7 @@ struct gstim_dem_sampler {
     cudaStream_t stream = nullptr;
     DevMem d_rates, d_tgt_off, d_tgt_row, d_table, d_rowmap, d_stage;
     gstim_m2d *replay = nullptr;  // recorded errors -> detectors / observables (m2d.cu), built on first use
+    HostStager host_stage;        // page-locked staging pair of the host-output paths (hostpipe.h)
     ~gstim_dem_sampler() {
         if (replay) {
             gstim_m2d_destroy(replay);
@@ -836,18 +838,39 @@ int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void 
         std::vector<uint8_t> host;
         SparseEngine *ev = errs_out == nullptr ? dem_events(s) : nullptr;
         if (ev != nullptr) {
-            dem_run_events(s, *ev, shots, [&](uint64_t first, uint64_t n, const uint8_t *rows, uint64_t pitch) {
-                host.resize(n * pitch + 1);
-                ck(cudaMemcpyAsync(host.data(), rows, n * pitch, cudaMemcpyDeviceToHost, s->stream), "D2H");
-                ck(cudaStreamSynchronize(s->stream), "sync");
-                for (int k = 0; k < 2; k++) {
-                    const DemOut &o = outs[k];
-                    if (o.ptr == nullptr || o.n_bits == 0) {
-                        continue;
-                    }
-                    const uint64_t row = packed ? (o.n_bits + 7) / 8 : o.n_bits, dp = o.stride ? (uint64_t)o.stride : row;
-                    dem_slice_rows(host.data(), pitch, n, o.row0, o.n_bits, packed, o.ptr + first * dp, dp);
+            // rows [detectors | observables] leave the device once: by direct DMA when the caller's arrays are page-locked and
+            // byte-aligned slices of the rows, else through the page-locked staging pair with the slicing / unpacking done by
+            // host threads while the next sub-chunk is in flight (hostpipe.h)
+            uint64_t dpitch[2];
+            bool direct = packed;
+            for (int k = 0; k < 2; k++) {
+                const DemOut &o = outs[k];
+                const uint64_t row = packed ? (o.n_bits + 7) / 8 : o.n_bits;
+                dpitch[k] = o.stride ? (uint64_t)o.stride : row;
+                if (o.ptr != nullptr && o.n_bits != 0) {
+                    // (a slice may end inside a byte only at the end of the row, where the padding bits are zero)
+                    direct = direct && (o.row0 & 7) == 0 && (((o.row0 + o.n_bits) & 7) == 0 || o.row0 + o.n_bits == D + L) && hp_is_pinned(o.ptr);
                 }
+            }
+            dem_run_events(s, *ev, shots, [&](uint64_t first, uint64_t n, const uint8_t *rows, uint64_t pitch) {
+                if (direct) {
+                    for (int k = 0; k < 2; k++) {
+                        const DemOut &o = outs[k];
+                        if (o.ptr != nullptr && o.n_bits != 0) {
+                            ck(cudaMemcpy2DAsync(o.ptr + first * dpitch[k], dpitch[k], rows + (o.row0 >> 3), pitch, (o.n_bits + 7) / 8, n,
+                                                 cudaMemcpyDeviceToHost, s->stream), "D2H");
+                        }
+                    }
+                    return;
+                }
+                hp_staged_d2h(s->host_stage, s->stream, rows, pitch, n, [&](const uint8_t *row, uint64_t i) {
+                    for (int k = 0; k < 2; k++) {
+                        const DemOut &o = outs[k];
+                        if (o.ptr != nullptr && o.n_bits != 0) {
+                            hp_slice_row(row, o.row0, o.n_bits, packed, o.ptr + (first + i) * dpitch[k]);
+                        }
+                    }
+                });
             });
             return;
         }

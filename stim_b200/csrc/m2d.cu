@@ -22,6 +22,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -31,6 +34,7 @@
 
 #include "../../include/gstim.h"
 #include "circuit.h"
+#include "hostpipe.h"
 #include "lowering.h"
 #include "response.h"
 #include "tableau_ref.h"
@@ -96,6 +100,80 @@ __global__ void __launch_bounds__(512) gstim_m2d_kernel(const M2dParams p) {
     }
 }
 
+// 32 x 32 bit transpose across a warp: lane l gives row l, gets column l (bit s of the result = bit l of lane s's word).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane) {
+#pragma unroll
+    for (uint32_t j = 16, m = 0x0000FFFFu; j != 0; j >>= 1, m ^= m << j) {
+        const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+        x = (lane & j) ? (((y >> j) & m) | (x & ~m)) : ((x & m) | ((y & m) << j));
+    }
+    return x;
+}
+
+// Bit-sliced converter: a block takes 32 shots at a time. Their packed rows are staged in shared memory (coalesced), turned
+// into one 32-bit word per input bit (bit s = shot s; warp transposes of 32 x 32 bit blocks), every output is the XOR of its
+// source WORDS (one shared-memory load per source and 32 shots, where the row-wise kernel above does one per source and shot),
+// and the output words are transposed back into packed rows. Used when the three arrays fit in shared memory.
+//   smem: stage[32][pitch_w] words (pitch_w odd), inT[in_words * 32], outT[out_words * 32]
+__global__ void __launch_bounds__(512) gstim_m2d_sliced_kernel(const M2dParams p, uint32_t pitch_w, uint32_t in_words, uint32_t out_words) {
+    extern __shared__ uint4 smem4[];
+    uint32_t *const stage = reinterpret_cast<uint32_t *>(smem4);
+    uint32_t *const inT = stage + 32u * pitch_w;
+    uint32_t *const outT = inT + in_words * 32u;
+    uint8_t *const stage8 = reinterpret_cast<uint8_t *>(stage);
+    const uint32_t in_bytes = p.meas_bytes + p.sweep_bytes, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t pitch_b = pitch_w * 4u;
+    for (uint64_t t0 = (uint64_t)blockIdx.x * 32u; t0 < p.n_shots; t0 += (uint64_t)gridDim.x * 32u) {
+        const uint32_t n = (uint32_t)min((uint64_t)32u, p.n_shots - t0);
+        __syncthreads();
+        // stage the rows (zero padding behind each row and for missing shots)
+        for (uint32_t i = threadIdx.x; i < 32u * pitch_w; i += blockDim.x) {
+            stage[i] = 0;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n * in_bytes; i += blockDim.x) {
+            const uint32_t s = i / in_bytes, b = i - s * in_bytes;
+            stage8[s * pitch_b + b] =
+                b < p.meas_bytes ? p.meas[(t0 + s) * p.meas_pitch + b] : (p.sweep ? p.sweep[(t0 + s) * p.sweep_pitch + (b - p.meas_bytes)] : (uint8_t)0);
+        }
+        __syncthreads();
+        for (uint32_t w = warp; w < in_words; w += n_warps) {
+            inT[w * 32u + lane] = warp_transpose32(stage[lane * pitch_w + w], lane);
+        }
+        __syncthreads();
+        auto emit = [&](uint32_t first_out, uint32_t n_bits, uint32_t n_bytes, uint8_t *dst, uint64_t pitch) {
+            const uint32_t words = (n_bits + 31u) / 32u;
+            for (uint32_t j = threadIdx.x; j < words * 32u; j += blockDim.x) {
+                uint32_t v = 0;
+                if (j < n_bits) {
+                    const uint32_t o = first_out + j;
+                    v = ((p.const_bits[o >> 3] >> (o & 7)) & 1u) ? 0xFFFFFFFFu : 0u;
+                    for (uint32_t e = p.src_off[o]; e < p.src_off[o + 1]; e++) {
+                        v ^= inT[p.src[e]];
+                    }
+                }
+                outT[j] = v;
+            }
+            __syncthreads();
+            for (uint32_t w = warp; w < words; w += n_warps) {
+                stage[lane * pitch_w + w] = warp_transpose32(outT[w * 32u + lane], lane);
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n * n_bytes; i += blockDim.x) {
+                const uint32_t s = i / n_bytes, b = i - s * n_bytes;
+                dst[(t0 + s) * pitch + b] = stage8[s * pitch_b + b];
+            }
+            __syncthreads();
+        };
+        if (p.out != nullptr && p.out_bytes) {
+            emit(0, p.n_out, p.out_bytes, p.out, p.out_pitch);
+        }
+        if (p.obs_out != nullptr && p.obs_bytes) {
+            emit(p.obs0, p.n_obs, p.obs_bytes, p.obs_out, p.obs_pitch);
+        }
+    }
+}
+
 }  // namespace gstim
 
 using namespace gstim;
@@ -115,6 +193,7 @@ struct gstim_m2d {
     void *d_off = nullptr, *d_src = nullptr, *d_const = nullptr, *d_in = nullptr, *d_sweep = nullptr, *d_out = nullptr, *d_obs = nullptr;
     size_t cap_in = 0, cap_sweep = 0, cap_out = 0, cap_obs = 0;
     cudaStream_t stream = nullptr;
+    gstim::HostStager stage_in, stage_out;  // page-locked staging pairs (hostpipe.h)
     ~gstim_m2d() {
         for (void *p : {d_off, d_src, d_const, d_in, d_sweep, d_out, d_obs}) {
             if (p) {
@@ -242,6 +321,7 @@ gstim_m2d *gstim_m2d_from_lists(int device, uint64_t n_inputs, uint64_t D, uint6
     h->smem_optin = prop.sharedMemPerBlockOptin;
     ck(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate");
     ck(cudaFuncSetAttribute(gstim_m2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin), "smem attribute");
+    ck(cudaFuncSetAttribute(gstim_m2d_sliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin), "smem attribute");
     return h.release();
 }
 
@@ -302,6 +382,7 @@ int gstim_m2d_create_from_text(const char *circuit_text, size_t text_len, int sk
         h->smem_optin = prop.sharedMemPerBlockOptin;
         ck(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate");
         ck(cudaFuncSetAttribute(gstim_m2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin), "smem attribute");
+    ck(cudaFuncSetAttribute(gstim_m2d_sliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin), "smem attribute");
         *out = h.release();
     });
 }
@@ -367,17 +448,22 @@ int gstim_m2d_convert(gstim_m2d *h, uint64_t shots, uint32_t flags, const void *
         }
         // chunks of shots through device staging (dense rows on the device)
         const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / std::max<uint32_t>(in_bytes + out_bytes + obs_bytes, 1));
+        const bool timing = getenv("GSTIM_M2D_TIMING") != nullptr;
+        double t_in = 0, t_kernel = 0, t_out = 0;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         for (uint64_t s0 = 0; s0 < shots; s0 += chunk) {
             const uint64_t n = std::min(chunk, shots - s0);
+            double t0 = timing ? now() : 0;
             ensure(&h->d_in, &h->cap_in, std::max<uint64_t>(n * meas_bytes, 16));
             ensure(&h->d_out, &h->cap_out, std::max<uint64_t>(n * out_bytes, 16));
+            // caller rows -> device: threaded packing into page-locked staging + async DMA (direct DMA from page-locked memory)
             if (meas_bytes) {
-                ck(cudaMemcpy2DAsync(h->d_in, meas_bytes, (const uint8_t *)measurements + s0 * mp, mp, meas_bytes, n, cudaMemcpyHostToDevice, h->stream), "H2D");
+                hp_h2d_rows(h->stage_in, h->stream, (const uint8_t *)measurements + s0 * mp, mp, (uint8_t *)h->d_in, meas_bytes, n);
             }
             const bool have_sweep = sweep_bits != nullptr && sweep_bytes > 0;
             if (have_sweep) {
                 ensure(&h->d_sweep, &h->cap_sweep, n * sweep_bytes);
-                ck(cudaMemcpy2DAsync(h->d_sweep, sweep_bytes, (const uint8_t *)sweep_bits + s0 * sp, sp, sweep_bytes, n, cudaMemcpyHostToDevice, h->stream), "H2D");
+                hp_h2d_rows(h->stage_in, h->stream, (const uint8_t *)sweep_bits + s0 * sp, sp, (uint8_t *)h->d_sweep, sweep_bytes, n);
             }
             if (obs_bytes) {
                 ensure(&h->d_obs, &h->cap_obs, n * obs_bytes);
@@ -403,16 +489,52 @@ int gstim_m2d_convert(gstim_m2d *h, uint64_t shots, uint32_t flags, const void *
             p.obs_pitch = obs_bytes;
             p.n_shots = n;
             p.tile_shots = tile;
-            const uint32_t grid = (uint32_t)std::min<uint64_t>((n + tile - 1) / tile, (uint64_t)h->num_sms * 2);
-            gstim_m2d_kernel<<<grid, 512, (size_t)tile * in_bytes + 16, h->stream>>>(p);
+            if (timing) {
+                cudaStreamSynchronize(h->stream);
+                t_in += now() - t0;
+                t0 = now();
+            }
+            // bit-sliced kernel when its three shared-memory arrays fit, else the row-wise one
+            const uint32_t widest = std::max(std::max(in_bytes, out_bytes), obs_bytes);
+            const uint32_t pitch_w = ((widest + 3) / 4 + 1) | 1u, in_words = (in_bytes * 8 + 31) / 32;
+            const uint32_t out_words = (std::max<uint32_t>(n_out, separate ? (uint32_t)h->L : 0) + 31) / 32;
+            const size_t sliced_smem = ((size_t)32 * pitch_w + (size_t)in_words * 32 + (size_t)out_words * 32) * 4;
+            if (sliced_smem <= h->smem_optin && !getenv("GSTIM_M2D_ROWWISE")) {
+                const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 31) / 32, (uint64_t)h->num_sms);
+                gstim_m2d_sliced_kernel<<<grid, 512, sliced_smem, h->stream>>>(p, pitch_w, in_words, out_words);
+            } else {
+                const uint32_t grid = (uint32_t)std::min<uint64_t>((n + tile - 1) / tile, (uint64_t)h->num_sms * 2);
+                gstim_m2d_kernel<<<grid, 512, (size_t)tile * in_bytes + 16, h->stream>>>(p);
+            }
             ck(cudaGetLastError(), "gstim_m2d_kernel launch");
+            if (timing) {
+                cudaStreamSynchronize(h->stream);
+                t_kernel += now() - t0;
+                t0 = now();
+            }
+            // device rows -> caller: direct DMA into page-locked memory, else staged sub-chunks copied out by host threads
+            auto rows_out = [&](const void *d, uint64_t row_bytes, uint8_t *dst, uint64_t pitch) {
+                if (hp_is_pinned(dst)) {
+                    ck(cudaMemcpy2DAsync(dst, pitch, d, row_bytes, row_bytes, n, cudaMemcpyDeviceToHost, h->stream), "D2H");
+                } else {
+                    hp_staged_d2h(h->stage_out, h->stream, (const uint8_t *)d, row_bytes, n,
+                                  [&](const uint8_t *row, uint64_t i) { memcpy(dst + i * pitch, row, row_bytes); });
+                }
+            };
             if (dets_out && out_bytes) {
-                ck(cudaMemcpy2DAsync((uint8_t *)dets_out + s0 * dp, dp, h->d_out, out_bytes, out_bytes, n, cudaMemcpyDeviceToHost, h->stream), "D2H");
+                rows_out(h->d_out, out_bytes, (uint8_t *)dets_out + s0 * dp, dp);
             }
             if (obs_out && obs_bytes) {
-                ck(cudaMemcpy2DAsync((uint8_t *)obs_out + s0 * op, op, h->d_obs, obs_bytes, obs_bytes, n, cudaMemcpyDeviceToHost, h->stream), "D2H");
+                rows_out(h->d_obs, obs_bytes, (uint8_t *)obs_out + s0 * op, op);
             }
             ck(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize");
+            if (timing) {
+                t_out += now() - t0;
+            }
+        }
+        if (timing) {
+            fprintf(stderr, "m2d: %llu shots, tile %u, in %.1f ms, kernel %.1f ms, out %.1f ms\n", (unsigned long long)shots, tile, t_in * 1e3,
+                    t_kernel * 1e3, t_out * 1e3);
         }
     });
 }
