@@ -25,6 +25,7 @@
 #include "circuit.h"
 #include "kernels.cuh"
 #include "lowering.h"
+#include "hostpipe.h"
 #include "sparse.cuh"
 #include "tableau_ref.h"
 #include "writers.h"
@@ -112,6 +113,7 @@ uint32_t env_u32(const char *name, uint32_t dflt) {
 }  // namespace
 
 struct gstim_sampler {
+    HostStager file_stage;  // page-locked staging pair of the file-output path (hostpipe.h)
     int device = 0;
     int mode = 0;
     uint64_t seed = 0;
@@ -1305,19 +1307,7 @@ struct FdFile {
 
 // shot-major packed rows -> bit-major 32-bit rows, then the ptb64 writer (shots % 64 == 0 is checked by the callers)
 void write_ptb64_rows(FILE *out, const uint8_t *rows, size_t row_pitch, uint64_t shots, uint64_t n_bits) {
-    const size_t n_cols = (shots + 127) / 128;
-    std::vector<uint32_t> table(n_cols * n_bits * 4, 0), map(n_bits);
-    for (uint64_t sh = 0; sh < shots; sh++) {
-        for (uint64_t b = 0; b < n_bits; b++) {
-            if ((rows[sh * row_pitch + (b >> 3)] >> (b & 7)) & 1) {
-                table[((sh >> 7) * n_bits + b) * 4 + ((sh >> 5) & 3)] |= 1u << (sh & 31);
-            }
-        }
-    }
-    for (uint64_t b = 0; b < n_bits; b++) {
-        map[b] = (uint32_t)b;
-    }
-    write_ptb64(out, table.data(), n_bits, map.data(), n_bits, shots);
+    write_ptb64_from_rows(out, rows, row_pitch, shots, n_bits);
 }
 
 // Streams shots to a file in any format; chunked through the host sampler.
@@ -1359,20 +1349,21 @@ void sample_to_file(
                 *op = nbytes_o;
             },
             [&](uint64_t, uint64_t n) {
-                host.resize(n * (nbytes + nbytes_o) + 1);
-                CK(cudaMemcpyAsync(host.data(), dmain, n * (nbytes + nbytes_o), cudaMemcpyDeviceToHost, s->stream));
-                CK(cudaStreamSynchronize(s->stream));
-                if (obs_f && obs_map) {
-                    if (obs_fmt == Format::PTB64) {
-                        write_ptb64_rows(obs_f, host.data() + n * nbytes, nbytes_o, n, nbo);
-                    } else {
-                        write_shots(obs_f, host.data() + n * nbytes, nbytes_o, n, nbo, obs_fmt, 'L', 'L', nbo);
-                    }
+                // rows leave through the page-locked staging pair: the DMA of one sub-chunk overlaps the (threaded) encoding of
+                // the previous one; sub-chunks hold whole groups of 64 shots for ptb64
+                if (obs_f && obs_map && nbytes_o) {
+                    hp_staged_d2h_blocks(s->file_stage, s->stream, dobs, nbytes_o, n, 64, [&](const uint8_t *rows, uint64_t, uint64_t cnt) {
+                        write_shots(obs_f, rows, nbytes_o, cnt, nbo, obs_fmt, 'L', 'L', nbo);
+                    });
+                } else if (obs_f && obs_map) {
+                    write_shots(obs_f, (const uint8_t *)"", 0, n, 0, obs_fmt, 'L', 'L', 0);
                 }
-                if (fmt == Format::PTB64) {
-                    write_ptb64_rows(f, host.data(), nbytes, n, nb);
+                if (nbytes) {
+                    hp_staged_d2h_blocks(s->file_stage, s->stream, dmain, nbytes, n, 64, [&](const uint8_t *rows, uint64_t, uint64_t cnt) {
+                        write_shots(f, rows, nbytes, cnt, nb, fmt, p1, p2, transition);
+                    });
                 } else {
-                    write_shots(f, host.data(), nbytes, n, nb, fmt, p1, p2, transition);
+                    write_shots(f, (const uint8_t *)"", 0, n, 0, fmt, p1, p2, transition);
                 }
             });
         if (fflush(f) != 0 || (obs_f && fflush(obs_f) != 0)) {

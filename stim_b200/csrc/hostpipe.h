@@ -136,6 +136,35 @@ void hp_staged_d2h(HostStager &S, cudaStream_t st, const uint8_t *d, uint64_t pi
     process(n_sub - 1);
 }
 
+// The same, handing whole staged sub-chunks to blockfn(rows, first_row, count) in order (for consumers that parallelise over
+// the rows themselves, e.g. the result-format encoders).
+template <typename BLOCKFN>
+void hp_staged_d2h_blocks(HostStager &S, cudaStream_t st, const uint8_t *d, uint64_t pitch, uint64_t n, uint64_t align_rows, BLOCKFN &&blockfn) {
+    if (n == 0 || pitch == 0) {
+        return;
+    }
+    uint64_t sub = std::max<uint64_t>(1, HP_SUB_BYTES / pitch);
+    sub = std::max<uint64_t>(align_rows, sub / align_rows * align_rows);
+    S.ensure(sub * pitch);
+    const uint64_t n_sub = (n + sub - 1) / sub;
+    auto process = [&](uint64_t k) {
+        const uint64_t r0 = k * sub, cnt = std::min(sub, n - r0);
+        S.wait((int)(k & 1));
+        blockfn((const uint8_t *)S.buf[k & 1], r0, cnt);
+    };
+    for (uint64_t k = 0; k < n_sub; k++) {
+        const uint64_t r0 = k * sub, cnt = std::min(sub, n - r0);
+        S.wait((int)(k & 1));
+        hp_ck(cudaMemcpyAsync(S.buf[k & 1], d + r0 * pitch, cnt * pitch, cudaMemcpyDeviceToHost, st), "D2H");
+        hp_ck(cudaEventRecord(S.ev[k & 1], st), "cudaEventRecord");
+        S.busy[k & 1] = true;
+        if (k > 0) {
+            process(k - 1);
+        }
+    }
+    process(n_sub - 1);
+}
+
 // Caller rows (row_bytes each, src_pitch apart) -> dense device rows (row_bytes apart), through the staging buffers unless the
 // caller's memory is page-locked.
 inline void hp_h2d_rows(HostStager &S, cudaStream_t st, const uint8_t *h, uint64_t src_pitch, uint8_t *d, uint64_t row_bytes, uint64_t n) {
