@@ -852,6 +852,9 @@ int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void 
                     direct = direct && (o.row0 & 7) == 0 && (((o.row0 + o.n_bits) & 7) == 0 || o.row0 + o.n_bits == D + L) && hp_is_pinned(o.ptr);
                 }
             }
+            if (!direct && outs[0].ptr != nullptr) {
+                hp_hugepage_hint(outs[0].ptr, shots * dpitch[0]);
+            }
             dem_run_events(s, *ev, shots, [&](uint64_t first, uint64_t n, const uint8_t *rows, uint64_t pitch) {
                 if (direct) {
                     for (int k = 0; k < 2; k++) {

@@ -5,6 +5,7 @@
 // detector-error-model sampler (dem.cu); the bulk samplers have their own pipeline in api.cu.
 #pragma once
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <cstdint>
@@ -33,6 +34,19 @@ inline bool hp_is_pinned(const void *ptr) {
         return false;
     }
     return attr.type == cudaMemoryTypeHost;
+}
+
+// A large result array that host threads are about to touch for the first time: ask for transparent huge pages, so that the
+// kernel zeroes and maps 2 MiB at a time instead of 4 KiB (a hint; ignored where THP is off or the range is already mapped).
+inline void hp_hugepage_hint(void *ptr, uint64_t bytes) {
+    if (ptr == nullptr || bytes < (64ull << 20)) {
+        return;
+    }
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(ptr) + 4095) & ~(uintptr_t)4095;
+    const uintptr_t b = (reinterpret_cast<uintptr_t>(ptr) + bytes) & ~(uintptr_t)4095;
+    if (b > a) {
+        madvise(reinterpret_cast<void *>(a), b - a, MADV_HUGEPAGE);
+    }
 }
 
 // f(i0, i1) over [0, n) on up to 16 threads (at least `grain` rows per thread)

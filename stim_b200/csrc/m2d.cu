@@ -448,6 +448,9 @@ int gstim_m2d_convert(gstim_m2d *h, uint64_t shots, uint32_t flags, const void *
         }
         // chunks of shots through device staging (dense rows on the device)
         const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / std::max<uint32_t>(in_bytes + out_bytes + obs_bytes, 1));
+        if (dets_out && !hp_is_pinned(dets_out)) {
+            hp_hugepage_hint(dets_out, shots * dp);
+        }
         const bool timing = getenv("GSTIM_M2D_TIMING") != nullptr;
         double t_in = 0, t_kernel = 0, t_out = 0;
         auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
