@@ -1399,10 +1399,13 @@ void sample_to_file(
         } else {
             s->d_stage[0].ensure(n * bytes + 16);
             transpose_to(s, table, n_rows, d_m, (uint32_t)m.size(), n, (uint8_t *)s->d_stage[0].p, bytes);
-            host.resize(n * bytes + 1);
-            CK(cudaMemcpyAsync(host.data(), s->d_stage[0].p, n * bytes, cudaMemcpyDeviceToHost, s->stream));
-            CK(cudaStreamSynchronize(s->stream));
-            write_shots(out, host.data(), bytes, n, m.size(), of, c1, c2, tr);
+            if (bytes) {
+                hp_staged_d2h_blocks(s->file_stage, s->stream, (const uint8_t *)s->d_stage[0].p, bytes, n, 64,
+                                     [&](const uint8_t *rows, uint64_t, uint64_t cnt) { write_shots(out, rows, bytes, cnt, m.size(), of, c1, c2, tr); });
+            } else {
+                CK(cudaStreamSynchronize(s->stream));
+                write_shots(out, (const uint8_t *)"", 0, n, 0, of, c1, c2, tr);
+            }
         }
     };
     run_sampler(s, shots, [&](uint64_t first, uint64_t n, const uint32_t *table, uint64_t n_rows) {
