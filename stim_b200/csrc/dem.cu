@@ -702,10 +702,9 @@ void dem_run(gstim_dem_sampler *s, uint64_t shots, bool record_errors, SINK &&si
     s->next_col += total_blocks * K;
 }
 
-// Transposes rows [row0, row0 + n_bits) of the table to dense b8 rows in device staging and copies them to `host`.
-void dem_fetch(gstim_dem_sampler *s, const uint32_t *table, uint64_t n_rows, uint64_t n, const DemOut &o, std::vector<uint8_t> &host) {
+// Transposes rows [row0, row0 + n_bits) of the table to dense b8 rows in device staging (s->d_stage), enqueued on the stream.
+void dem_transpose_rows(gstim_dem_sampler *s, const uint32_t *table, uint64_t n_rows, uint64_t n, const DemOut &o) {
     const uint64_t bytes = (o.n_bits + 7) / 8;
-    host.assign(n * bytes + 1, 0);
     if (o.n_bits == 0 || n == 0) {
         return;
     }
@@ -725,6 +724,16 @@ void dem_fetch(gstim_dem_sampler *s, const uint32_t *table, uint64_t n_rows, uin
     t.out = (uint8_t *)s->d_stage.p;
     t.out_pitch = bytes;
     ck(launch_transpose_b8(t, s->stream), "transpose");
+}
+
+// ... and copies them to `host` (the file writers).
+void dem_fetch(gstim_dem_sampler *s, const uint32_t *table, uint64_t n_rows, uint64_t n, const DemOut &o, std::vector<uint8_t> &host) {
+    const uint64_t bytes = (o.n_bits + 7) / 8;
+    host.resize(n * bytes + 1);
+    if (o.n_bits == 0 || n == 0) {
+        return;
+    }
+    dem_transpose_rows(s, table, n_rows, n, o);
     ck(cudaMemcpyAsync(host.data(), s->d_stage.p, n * bytes, cudaMemcpyDeviceToHost, s->stream), "D2H");
     ck(cudaStreamSynchronize(s->stream), "sync");
 }
@@ -882,18 +891,19 @@ int gstim_dem_sample(gstim_dem_sampler *s, uint64_t shots, uint32_t flags, void 
                 if (o.ptr == nullptr || o.n_bits == 0) {
                     continue;
                 }
-                dem_fetch(s, table, n_rows, n, o, host);
+                // rows of this output transposed to dense b8 rows on the device, then through the page-locked staging pair:
+                // host threads copy / unpack one sub-chunk while the next is in flight (error rows are 44 KB per shot for c3)
                 const uint64_t bytes = (o.n_bits + 7) / 8;
                 const uint64_t row = packed ? bytes : o.n_bits, pitch = o.stride ? (uint64_t)o.stride : row;
-                for (uint64_t i = 0; i < n; i++) {
-                    uint8_t *dst = o.ptr + (first + i) * pitch;
-                    if (packed) {
-                        memcpy(dst, host.data() + i * bytes, bytes);
-                    } else {
-                        for (uint32_t b = 0; b < o.n_bits; b++) {
-                            dst[b] = (host[i * bytes + (b >> 3)] >> (b & 7)) & 1;
-                        }
-                    }
+                dem_transpose_rows(s, table, n_rows, n, o);
+                uint8_t *dst0 = o.ptr + first * pitch;
+                if (packed && hp_is_pinned(o.ptr)) {
+                    ck(cudaMemcpy2DAsync(dst0, pitch, s->d_stage.p, bytes, bytes, n, cudaMemcpyDeviceToHost, s->stream), "D2H");
+                    ck(cudaStreamSynchronize(s->stream), "sync");  // (d_stage is reused by the next output)
+                } else {
+                    hp_staged_d2h(s->host_stage, s->stream, (const uint8_t *)s->d_stage.p, bytes, n, [&](const uint8_t *r, uint64_t i) {
+                        hp_slice_row(r, 0, o.n_bits, packed, dst0 + i * pitch);
+                    });
                 }
             }
         });
