@@ -800,6 +800,7 @@ __device__ __noinline__ const uint32_t *op_reczero(const BlockCtx *bc, const uin
     SLOT_SUB;
     (void)pitch_b;
     (void)kstep;
+    (void)X_s;
     const uint32_t n = hw[GH_N], rec0 = hw[GH_REC0];
     uint4 *const rec = bc->rec;
     const uint32_t rec_mask = bc->rec_mask;
@@ -818,6 +819,7 @@ __device__ __noinline__ const uint32_t *op_xorrows(const BlockCtx *bc, const uin
     SLOT_SUB;
     (void)pitch_b;
     (void)kstep;
+    (void)X_s;
     const uint32_t flags = (hw[GH_OP] >> 8) & 0xFF, n = hw[GH_N];
     const SmemWords pay = hw + GSTIM_HDR_WORDS;
     const SmemWords dst = pay, off = pay + n, idx = pay + 2 * n + 1;

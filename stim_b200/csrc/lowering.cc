@@ -1579,7 +1579,6 @@ std::vector<uint32_t> serialize_program(LoweredCircuit &lc, uint32_t slots, uint
             }
             out[base + GH_CSITE0] = nbi;
             const bool table = b.op == GOP_NOISE2 && (b.flags & GF_TABLE);
-            const uint32_t items_off = (uint32_t)(base + GSTIM_HDR_WORDS + (table ? 15 : 0));
             uint32_t info[GSTIM_NOISE_INFO_WORDS] = {};
             info[GNI_H0] = out[base + GH_OP];
             info[GNI_N] = b.op == GOP_CORR ? 1u : b.n_items;
