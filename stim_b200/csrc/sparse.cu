@@ -655,8 +655,9 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
 // (the statistics the 5-sigma tests and the per-detector count allreduce use; the reference has no such kernel — it is
 // what a caller computes from the b8 array).
 // A thread owns one 32-bit column of the rows (bits 32 j .. 32 j + 31) over a run of shots and counts all 32 bits at once
-// in bit-sliced ("vertical") counters: eight bit planes, plane k holding bit k of every column bit's count, advanced by a
-// ripple-carry add of the shot's word; every 255 shots the planes are folded into the global counters. Rows may start at
+// in bit-sliced ("vertical") counters: eight shots are reduced by seven carry-save adders (Harley-Seal: XOR3 + MAJ3, two LOP3
+// each) to residues of weight 1, 2, 4 and ONE word of weight 8, which a ripple-carry add pushes into eight bit planes; every
+// 255 groups the planes and residues are folded into the global counters (3.6 word-ops per shot and column instead of 24). Rows may start at
 // any byte (c3: 1951 B pitch): the word is assembled from two aligned loads with a funnel shift.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void vadd(uint32_t (&c)[8], uint32_t w) {
@@ -668,58 +669,95 @@ __device__ __forceinline__ void vadd(uint32_t (&c)[8], uint32_t w) {
         carry = t;
     }
 }
-__device__ __forceinline__ void vflush(uint32_t (&c)[8], unsigned long long *dst, uint32_t bit0, uint32_t n_bits) {
+// Carry-save state of one column: `ones`, `twos`, `fours` hold the count of the shots seen so far modulo 8 (bit-sliced), the
+// planes c[k] count whole groups of eight (weight 8 << k).
+struct VCount {
+    uint32_t ones = 0, twos = 0, fours = 0;
+    uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+// (h, l) = a + b + c per bit: the sum bit stays at this weight, the majority carries to the next one (two LOP3)
+#define GSTIM_CSA(h, l, a, b, c)         \
+    {                                    \
+        const uint32_t u_ = (a) ^ (b);   \
+        const uint32_t c_ = (c);         \
+        h = ((a) & (b)) | (u_ & c_);     \
+        l = u_ ^ c_;                     \
+    }
+// eight shots' words at once (Harley-Seal): seven carry-save adders leave one word of weight eight for the planes
+__device__ __forceinline__ void vadd8(VCount &v, const uint32_t (&w)[8]) {
+    uint32_t ta, tb, fa, fb, e;
+    GSTIM_CSA(ta, v.ones, v.ones, w[0], w[1]);
+    GSTIM_CSA(tb, v.ones, v.ones, w[2], w[3]);
+    GSTIM_CSA(fa, v.twos, v.twos, ta, tb);
+    GSTIM_CSA(ta, v.ones, v.ones, w[4], w[5]);
+    GSTIM_CSA(tb, v.ones, v.ones, w[6], w[7]);
+    GSTIM_CSA(fb, v.twos, v.twos, ta, tb);
+    GSTIM_CSA(e, v.fours, v.fours, fa, fb);
+    vadd(v.c, e);
+}
+__device__ __forceinline__ void vflush(VCount &v, unsigned long long *dst, uint32_t bit0, uint32_t n_bits) {
 #pragma unroll 4
     for (uint32_t b = 0; b < 32; b++) {
-        uint32_t v = 0;
+        uint32_t x = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            v |= ((c[k] >> b) & 1u) << k;
+            x |= ((v.c[k] >> b) & 1u) << k;
         }
-        if (v != 0 && bit0 + b < n_bits) {
-            atomicAdd(dst + bit0 + b, (unsigned long long)v);
+        x = 8u * x + ((v.ones >> b) & 1u) + 2u * ((v.twos >> b) & 1u) + 4u * ((v.fours >> b) & 1u);
+        if (x != 0 && bit0 + b < n_bits) {
+            atomicAdd(dst + bit0 + b, (unsigned long long)x);
         }
     }
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        c[k] = 0;
-    }
+    v = VCount();
 }
 
-__global__ void __launch_bounds__(128) gstim_count_b8_kernel(const uint8_t *rows, uint64_t pitch, uint64_t n_shots, uint32_t n_bits,
+__global__ void __launch_bounds__(512) gstim_count_b8_kernel(const uint8_t *rows, uint64_t pitch, uint64_t n_shots, uint32_t n_bits,
                                                             unsigned long long *single, unsigned long long *pair) {
     const uint32_t n_words = (n_bits + 31) / 32, n_bytes = (n_bits + 7) / 8;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_words) {
         return;
     }
-    const uint64_t per = (n_shots + gridDim.y - 1) / gridDim.y;
-    const uint64_t s0 = (uint64_t)blockIdx.y * per, s1 = min(n_shots, s0 + per);
+    // (narrow rows: a block holds blockDim.y runs of shots side by side, so that its threads are all in use)
+    const uint64_t n_runs = (uint64_t)gridDim.y * blockDim.y, ry = (uint64_t)blockIdx.y * blockDim.y + threadIdx.y;
+    const uint64_t per = (n_shots + n_runs - 1) / n_runs;
+    const uint64_t s0 = min(n_shots, ry * per), s1 = min(n_shots, s0 + per);
     const uint32_t valid = n_bits - 32 * j >= 32 ? 0xFFFFFFFFu : ((1u << (n_bits - 32 * j)) - 1u);
     const uint32_t bytes_here = min(4u, n_bytes - 4 * j);        // bytes of this column that exist in a row
     const bool has_next = 4 * j + 4 < n_bytes;
-    uint32_t c1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t pending = 0;
-    auto load = [&](uint64_t s, uint32_t *w, uint32_t *nxt) {
+    VCount c1, c2;
+    uint32_t pending = 0;  // groups of eight shots in the planes
+    // A column with all four bytes inside the row (every thread but the one on the ragged end) is read branch-free: two aligned
+    // words and a funnel shift; the first bit of the next column (for the pair counts) sits in the second word. Without
+    // branches the compiler issues the sixteen loads of a group back to back — with a branch per row they went out one row at
+    // a time and the kernel ran at one DRAM round trip per row (0.9 TB/s).
+    const uint32_t next_mask = (pair != nullptr && has_next) ? 1u : 0u;
+    auto load_full = [&](uint64_t s, uint32_t *w, uint32_t *nxt) {
+        const uintptr_t ai = reinterpret_cast<uintptr_t>(rows + s * pitch + 4 * j);
+        const uint32_t *al = reinterpret_cast<const uint32_t *>(ai & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(ai & 3) * 8;
+        const uint32_t lo = __ldg(al), hi = __ldg(al + 1);  // (the rows' buffer has 16 spare bytes behind it)
+        *w = __funnelshift_r(lo, hi, sh) & valid;
+        *nxt = (hi >> sh) & next_mask;
+    };
+    auto load_ragged = [&](uint64_t s, uint32_t *w, uint32_t *nxt) {
         const uint8_t *a = rows + s * pitch + 4 * j;
-        if (bytes_here == 4) {
-            const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
-            const uint32_t *al = reinterpret_cast<const uint32_t *>(ai & ~(uintptr_t)3);
-            const uint32_t sh = (uint32_t)(ai & 3) * 8;
-            *w = sh == 0 ? al[0] : __funnelshift_r(al[0], al[1], sh);  // (the rows' buffer has 16 spare bytes behind it)
-        } else {
-            *w = 0;
-            for (uint32_t k = 0; k < bytes_here; k++) {
-                *w |= (uint32_t)a[k] << (8 * k);
-            }
+        *w = 0;
+        for (uint32_t k = 0; k < bytes_here; k++) {
+            *w |= (uint32_t)a[k] << (8 * k);
         }
         *w &= valid;
-        *nxt = (pair != nullptr && has_next) ? (uint32_t)(a[4] & 1u) : 0u;
+        *nxt = 0;  // (nothing follows the last column)
     };
-    auto add = [&](uint32_t w, uint32_t nxt) {
-        vadd(c1, w);
+    auto add8 = [&](const uint32_t (&w)[8], const uint32_t (&nx)[8]) {
+        vadd8(c1, w);
         if (pair != nullptr) {
-            vadd(c2, w & ((w >> 1) | (nxt << 31)));
+            uint32_t pw[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                pw[u] = w[u] & ((w[u] >> 1) | (nx[u] << 31));
+            }
+            vadd8(c2, pw);
         }
         if (++pending == 255) {
             vflush(c1, single, 32 * j, n_bits);
@@ -729,28 +767,41 @@ __global__ void __launch_bounds__(128) gstim_count_b8_kernel(const uint8_t *rows
             pending = 0;
         }
     };
+    const bool full = bytes_here == 4;
     uint64_t s = s0;
-    for (; s + 8 <= s1; s += 8) {  // eight rows in flight per thread: the loop is bound by load latency otherwise
+    for (; s + 8 <= s1; s += 8) {  // eight rows in flight per thread (load latency), counted together (carry-save)
+        uint32_t w[8], nx[8];
+        if (full) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                load_full(s + u, &w[u], &nx[u]);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                load_ragged(s + u, &w[u], &nx[u]);
+            }
+        }
+        add8(w, nx);
+    }
+    if (s < s1) {  // the last, partial group: missing shots count as zero words
         uint32_t w[8], nx[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            load(s + u, &w[u], &nx[u]);
+            w[u] = nx[u] = 0;
+            if (s + u < s1) {
+                if (full) {
+                    load_full(s + u, &w[u], &nx[u]);
+                } else {
+                    load_ragged(s + u, &w[u], &nx[u]);
+                }
+            }
         }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            add(w[u], nx[u]);
-        }
+        add8(w, nx);
     }
-    for (; s < s1; s++) {
-        uint32_t w, nx;
-        load(s, &w, &nx);
-        add(w, nx);
-    }
-    if (pending) {
-        vflush(c1, single, 32 * j, n_bits);
-        if (pair != nullptr) {
-            vflush(c2, pair, 32 * j, n_bits - 1);
-        }
+    vflush(c1, single, 32 * j, n_bits);  // (the residues may hold counts even when no group reached the planes)
+    if (pair != nullptr) {
+        vflush(c2, pair, 32 * j, n_bits - 1);
     }
 }
 
@@ -831,10 +882,20 @@ cudaError_t launch_count_b8(const uint8_t *rows, uint64_t pitch, uint64_t n_shot
         return cudaSuccess;
     }
     // (the buffer holding `rows` must have 4 readable bytes behind its last row: the library's staging buffers have 16)
+    // A block covers up to 512 columns = 2 KB of a row: for rows up to that size one block reads whole rows, eight at a time,
+    // so DRAM sees ~16 KB of nearly contiguous bytes per block step instead of 512-byte quarters of a row from four blocks at
+    // different times (the same row-locality lesson as round 1's transposer).
     const uint32_t n_words = (n_bits + 31) / 32;
-    const unsigned gx = (n_words + 127) / 128;
-    dim3 grid(gx, (unsigned)std::min<uint64_t>((n_shots + 1019) / 1020, std::max<uint64_t>(1, 148ull * 64 / gx)));
-    gstim_count_b8_kernel<<<grid, 128, 0, stream>>>(rows, pitch, n_shots, n_bits, single, pair);
+    unsigned bx = 1;
+    while (bx < 512 && bx < n_words) {
+        bx *= 2;
+    }
+    const unsigned by = 512 / bx, gx = (n_words + bx - 1) / bx;
+    const uint64_t runs_wanted = std::max<uint64_t>(1, 148ull * 2048 * 2 / ((uint64_t)gx * bx));  // two waves of full occupancy
+    const uint64_t run = std::max<uint64_t>(256, (n_shots + runs_wanted - 1) / runs_wanted);
+    const uint64_t n_runs = (n_shots + run - 1) / run;
+    dim3 grid(gx, (unsigned)((n_runs + by - 1) / by)), block(bx, by);
+    gstim_count_b8_kernel<<<grid, block, 0, stream>>>(rows, pitch, n_shots, n_bits, single, pair);
     return cudaGetLastError();
 }
 
