@@ -467,9 +467,15 @@ __global__ void __launch_bounds__(SPARSE_THREADS, 1) gstim_sparse_kernel(const _
         }
         const uint32_t sl = T - (q_end - p.n_slices);
         uint32_t k = (sl >= e0 ? 1u : 0u) + (sl >= e1 ? 1u : 0u) + (sl >= e2 ? 1u : 0u);
-        if (k == 3) {
-            while (sl >= cls[k].slice_end) {
-                k++;
+        if (k == 3) {  // more than three classes (detector error models: one per distinct probability): binary search
+            uint32_t hi = p.n_classes - 1;
+            while (k < hi) {
+                const uint32_t mid = (k + hi) >> 1;
+                if (sl >= cls[mid].slice_end) {
+                    k = mid + 1;
+                } else {
+                    hi = mid;
+                }
             }
         }
         const uint4 *cw = reinterpret_cast<const uint4 *>(cls + k);
