@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <exception>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -117,6 +118,21 @@ struct HostStager {
 
 constexpr uint64_t HP_SUB_BYTES = 32ull << 20;  // staging sub-chunk
 
+// If a consumer throws while copies into / out of the staging buffers are still in flight, wait for them before the exception
+// leaves (the buffers may be freed or reused by whoever handles it).
+struct HpDrainOnUnwind {
+    cudaStream_t st;
+    HostStager &S;
+    int live;
+    HpDrainOnUnwind(cudaStream_t st, HostStager &S) : st(st), S(S), live(std::uncaught_exceptions()) {}
+    ~HpDrainOnUnwind() {
+        if (std::uncaught_exceptions() > live) {
+            cudaStreamSynchronize(st);
+            S.busy[0] = S.busy[1] = false;
+        }
+    }
+};
+
 // Device rows (dense, `pitch` bytes apart) -> rowfn(staged_row, i) for every row i in [0, n), the DMA of one sub-chunk
 // overlapping the host work on the previous one. The device rows must stay valid until the stream has passed the copies.
 template <typename ROWFN>
@@ -126,6 +142,7 @@ void hp_staged_d2h(HostStager &S, cudaStream_t st, const uint8_t *d, uint64_t pi
     }
     const uint64_t sub = std::max<uint64_t>(1, HP_SUB_BYTES / pitch);
     S.ensure(sub * pitch);
+    HpDrainOnUnwind guard(st, S);
     const uint64_t n_sub = (n + sub - 1) / sub;
     auto process = [&](uint64_t k) {
         const uint64_t r0 = k * sub, cnt = std::min(sub, n - r0);
@@ -160,6 +177,7 @@ void hp_staged_d2h_blocks(HostStager &S, cudaStream_t st, const uint8_t *d, uint
     uint64_t sub = std::max<uint64_t>(1, HP_SUB_BYTES / pitch);
     sub = std::max<uint64_t>(align_rows, sub / align_rows * align_rows);
     S.ensure(sub * pitch);
+    HpDrainOnUnwind guard(st, S);
     const uint64_t n_sub = (n + sub - 1) / sub;
     auto process = [&](uint64_t k) {
         const uint64_t r0 = k * sub, cnt = std::min(sub, n - r0);
@@ -191,6 +209,7 @@ inline void hp_h2d_rows(HostStager &S, cudaStream_t st, const uint8_t *h, uint64
     }
     const uint64_t sub = std::max<uint64_t>(1, HP_SUB_BYTES / row_bytes);
     S.ensure(sub * row_bytes);
+    HpDrainOnUnwind guard(st, S);
     for (uint64_t k = 0, r0 = 0; r0 < n; k++, r0 += sub) {
         const uint64_t cnt = std::min(sub, n - r0);
         S.wait((int)(k & 1));
