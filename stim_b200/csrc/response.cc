@@ -81,7 +81,17 @@ struct ClassKey {
 struct ClassAcc {
     ClassKey key;
     std::vector<uint32_t> rep_word;   // outcome -> representative chooser word
-    std::vector<Set> responses;       // n_out per site, in discovery (reverse) order
+    // responses, n_out per site, in discovery (reverse) order: one flat array of ids + end offsets (a vector per response
+    // meant nine million small allocations for a d = 51 memory experiment)
+    std::vector<uint32_t> resp_ids;
+    std::vector<uint64_t> resp_end;
+    void push(const Set &s) {
+        resp_ids.insert(resp_ids.end(), s.begin(), s.end());
+        resp_end.push_back(resp_ids.size());
+    }
+    size_t n_responses() const {
+        return resp_end.size();
+    }
     std::vector<uint32_t> group, index;
 };
 
@@ -149,7 +159,7 @@ ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate
             SR[m] = {m};
         }
     }
-    Set tmp, acc, comp[4];
+    Set tmp, acc, comp[4], by_mask[16];
     std::map<ClassKey, size_t> class_of;
     std::vector<ClassAcc> accs;
     uint64_t total_ids = 0;
@@ -219,7 +229,7 @@ ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate
         ClassAcc &c = get_class(k, rep);
         for (uint32_t o = no; o-- > 0;) {
             total_ids += chain[o].response.size();
-            c.responses.push_back(std::move(chain[o].response));
+            c.push(chain[o].response);
         }
         c.group.push_back(chain[0].group);
         c.index.push_back(0);
@@ -350,7 +360,7 @@ ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate
                         const uint32_t rep = 0;
                         ClassAcc &c = get_class(k, &rep);
                         total_ids += rr.size();
-                        c.responses.push_back(std::move(rr));
+                        c.push(rr);
                         c.group.push_back(0x80000000u | B.csite0);
                         c.index.push_back(lq);
                     }
@@ -456,7 +466,7 @@ ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate
                             xor_into(acc, SR[(B.rec0 + ii) & rec_mask], tmp);
                         }
                         total_ids += acc.size();
-                        c.responses.push_back(acc);
+                        c.push(acc);
                     }
                     c.group.push_back(B.site0);
                     c.index.push_back(gfirst[bi] + ii);
@@ -502,15 +512,31 @@ ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate
                 for (uint32_t ii = n; ii-- > 0;) {
                     const uint32_t q1 = items[ii] & 0xFFFF, q2 = items[ii] >> 16;
                     const Set *cs[4] = {&SX[q1], &SZ[q1], &SX[q2], &SZ[q2]};
-                    for (uint32_t o = no; o-- > 0;) {
-                        acc.clear();
-                        for (int j = 0; j < 4; j++) {
-                            if ((masks[o] >> j) & 1) {
-                                xor_into(acc, *cs[j], tmp);
-                            }
+                    if (no >= 8) {
+                        // (DEPOLARIZE2) the XOR of every subset of the four sets, in Gray-code order: one merge per subset
+                        by_mask[0].clear();
+                        for (uint32_t g = 1, prev = 0; g < 16; g++) {
+                            const uint32_t cur = g ^ (g >> 1), bit = (uint32_t)__builtin_ctz(cur ^ prev);
+                            by_mask[cur] = by_mask[prev];
+                            xor_into(by_mask[cur], *cs[bit], tmp);
+                            prev = cur;
                         }
-                        total_ids += acc.size();
-                        c.responses.push_back(acc);
+                        for (uint32_t o = no; o-- > 0;) {
+                            const Set &r = by_mask[masks[o] & 15u];
+                            total_ids += r.size();
+                            c.push(r);
+                        }
+                    } else {
+                        for (uint32_t o = no; o-- > 0;) {
+                            acc.clear();
+                            for (int j = 0; j < 4; j++) {
+                                if ((masks[o] >> j) & 1) {
+                                    xor_into(acc, *cs[j], tmp);
+                                }
+                            }
+                            total_ids += acc.size();
+                            c.push(acc);
+                        }
                     }
                     c.group.push_back(B.site0);
                     c.index.push_back(gfirst[bi] + ii);
@@ -556,7 +582,7 @@ ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return accs[a].key < accs[b].key; });
     uint64_t n_entries = 0;
     for (size_t ci : order) {
-        n_entries += accs[ci].responses.size();
+        n_entries += accs[ci].n_responses();
     }
     if (n_entries >= (1ull << 31) / 4) {
         return fail("response table too large");
@@ -591,29 +617,27 @@ ResponseTable build_response_table(const LoweredCircuit &lc, bool keep_conjugate
             }
         }
         rt.events_per_shot += p * rc.n_sites;
-        uint64_t class_ids = 0;
-        for (const Set &s : a.responses) {
-            class_ids += s.size();
-        }
+        const uint64_t class_ids = a.resp_ids.size();
         rt.flips_per_shot += p * (double)class_ids / rc.n_out;
-        for (size_t r = a.responses.size(); r-- > 0;) {  // reverse discovery order = program order, outcomes ascending
-            const Set &s = a.responses[r];
-            rt.max_response = std::max<uint32_t>(rt.max_response, (uint32_t)s.size());
+        for (size_t r = a.n_responses(); r-- > 0;) {  // reverse discovery order = program order, outcomes ascending
+            const uint32_t *s = a.resp_ids.data() + (r ? a.resp_end[r - 1] : 0);
+            const size_t sn = (size_t)(a.resp_end[r] - (r ? a.resp_end[r - 1] : 0));
+            rt.max_response = std::max<uint32_t>(rt.max_response, (uint32_t)sn);
             uint32_t w[4] = {RESP_NONE, RESP_NONE, RESP_NONE, RESP_NONE};
-            if (s.size() <= 4) {
-                for (size_t j = 0; j < s.size(); j++) {
+            if (sn <= 4) {
+                for (size_t j = 0; j < sn; j++) {
                     w[j] = s[j];
                 }
             } else {
                 for (size_t j = 0; j < 3; j++) {
                     w[j] = s[j];
                 }
-                if (rt.overflow.size() + s.size() >= (1ull << 30)) {
+                if (rt.overflow.size() + sn >= (1ull << 30)) {
                     return fail("response table too large");
                 }
                 w[3] = RESP_OVERFLOW | (uint32_t)rt.overflow.size();
-                rt.overflow.push_back((uint32_t)(s.size() - 3));
-                rt.overflow.insert(rt.overflow.end(), s.begin() + 3, s.end());
+                rt.overflow.push_back((uint32_t)(sn - 3));
+                rt.overflow.insert(rt.overflow.end(), s + 3, s + sn);
             }
             rt.entries.insert(rt.entries.end(), w, w + 4);
         }
