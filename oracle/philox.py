@@ -25,6 +25,8 @@ TAG_COLLAPSE = 0x434F4C4C
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
     """All arguments broadcastable integer arrays (values < 2**32). Returns 4 uint32 arrays."""
+    if all(isinstance(a, (int, np.integer)) for a in (c0, c1, c2, c3)):
+        return _philox_scalar(int(c0), int(c1), int(c2), int(c3), int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF)
     c0, c1, c2, c3 = np.broadcast_arrays(*(np.asarray(a, dtype=np.uint64) for a in (c0, c1, c2, c3)))
     c0 = c0.copy()
     c1 = c1.copy()
@@ -43,6 +45,17 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
         k0 = (k0 + W0) & 0xFFFFFFFF
         k1 = (k1 + W1) & 0xFFFFFFFF
     return tuple(a.astype(np.uint32) for a in (c0, c1, c2, c3))
+
+
+def _philox_scalar(c0, c1, c2, c3, k0, k1):
+    """The same ten rounds on Python integers (one counter): the serial event walks of the oracles call this ~10^6 times."""
+    for _ in range(10):
+        p0 = 0xD2511F53 * c0
+        p1 = 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = (p1 >> 32) ^ c1 ^ k0, p1 & 0xFFFFFFFF, (p0 >> 32) ^ c3 ^ k1, p0 & 0xFFFFFFFF
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return np.uint32(c0), np.uint32(c1), np.uint32(c2), np.uint32(c3)
 
 
 _COEFS = [1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0, 1.0]
