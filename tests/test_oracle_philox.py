@@ -17,8 +17,10 @@ def test_philox4x32_10_known_answers():
          (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
     ]
     for ctr, key, want in kat:
-        got = px.philox4x32_10(*ctr, *key)
+        got = px.philox4x32_10(*ctr, *key)  # Python-integer path (single counter)
         assert tuple(int(v) for v in got) == want
+        got = px.philox4x32_10(*(np.array([c, c], dtype=np.uint64) for c in ctr), *key)  # array path
+        assert tuple(int(v[1]) for v in got) == want
 
 
 def test_philox_is_vectorised_consistently():
