@@ -8,9 +8,13 @@
     python -m stim_b200 m2d --circuit FILE [--in FILE] [--in_format F] [--out FILE] [--out_format F]
                             [--sweep FILE] [--sweep_format F] [--append_observables] [--obs_out FILE] [--obs_out_format F]
                             [--skip_reference_sample]
+    python -m stim_b200 convert --in_format F [--out_format F] [--in FILE] [--out FILE] [--obs_out FILE] [--obs_out_format F]
+                            [--num_measurements N] [--num_detectors N] [--num_observables N] [--bits_per_shot N]
+                            [--circuit FILE --types MDL] [--dem FILE]
 
 Same flags, defaults and output bytes as `stim detect` / `stim sample` / `stim sample_dem`
-(/root/reference/src/stim/cmd/command_detect.cc:23-79, command_sample.cc:25-71, command_sample_dem.cc:25-93, command_m2d.cc;
+(/root/reference/src/stim/cmd/command_detect.cc:23-79, command_sample.cc:25-71, command_sample_dem.cc:25-93, command_m2d.cc,
+command_convert.cc:31-244 - a host-only re-encoding of shot data between the formats either side of the path;
 every format F is one of 01 b8 r8 hits dets ptb64 on both sides, doc/usage_command_line.md); the sampling itself
 runs on the GPU through the C ABI (there is no CPU fallback). Errors print to stderr and exit with status 1 like
 /root/reference/src/stim/main_namespaced.cc:113-122."""
@@ -58,6 +62,18 @@ def _parser():
     q.add_argument("--obs_out_format", default="01", choices=FORMATS)
     q.add_argument("--append_observables", action="store_true")
     q.add_argument("--skip_reference_sample", action="store_true")
+    q = sub.add_parser("convert", allow_abbrev=False)
+    q.add_argument("--in_format", required=True, choices=FORMATS)
+    q.add_argument("--out_format", default="01", choices=FORMATS)
+    q.add_argument("--obs_out_format", default="01", choices=FORMATS)
+    q.add_argument("--in", dest="inp", default=None)
+    q.add_argument("--out", default=None)
+    q.add_argument("--obs_out", default=None)
+    q.add_argument("--circuit", default=None)
+    q.add_argument("--dem", default=None)
+    q.add_argument("--types", default=None)
+    for flag in ("num_measurements", "num_detectors", "num_observables", "bits_per_shot"):
+        q.add_argument("--" + flag, type=int, default=0)
     return p
 
 
@@ -72,11 +88,81 @@ def _m2d(args) -> int:
     return 0
 
 
+def _convert(args) -> int:
+    """`stim convert` (/root/reference/src/stim/cmd/command_convert.cc:31-244): the record layout comes from the explicit
+    counts, else a detector error model, else a circuit + --types, else --bits_per_shot (anonymous bits; not for dets)."""
+    import numpy as np
+
+    from . import _formats
+
+    for flag in ("num_measurements", "num_detectors", "num_observables", "bits_per_shot"):
+        if getattr(args, flag) < 0:
+            raise ValueError(f"--{flag} must be non-negative.")
+    nm, nd, no = args.num_measurements, args.num_detectors, args.num_observables
+    inc_m, inc_d, inc_l = nm > 0, nd > 0, no > 0
+    if args.dem is not None:
+        dem = stim_b200.DetectorErrorModel.from_file(args.dem)
+        nd, no = dem.num_detectors, dem.num_observables
+        inc_d, inc_l = nd > 0, no > 0
+    if args.circuit is not None:
+        if args.types is None:
+            raise ValueError("--types required when passing circuit")
+        circuit = stim_b200.Circuit(open(args.circuit).read())
+        nm, nd, no = circuit.num_measurements, circuit.num_detectors, circuit.num_observables
+        inc = {"M": inc_m, "D": inc_d, "L": inc_l}
+        for c in args.types:
+            if c not in inc:
+                raise ValueError("Unknown type passed to --types")
+            if inc[c]:
+                raise ValueError("Each type in types should only be specified once")
+            inc[c] = True
+        inc_m, inc_d, inc_l = inc["M"], inc["D"], inc["L"]
+    if not (inc_m or inc_d or inc_l):
+        if args.out_format == "dets":
+            raise ValueError("Not enough information given to parse input file to write to dets. Please given a circuit "
+                             "with --types, a DEM file, or explicit number of each desired type")
+        if args.bits_per_shot == 0:
+            raise ValueError("Not enough information given to parse input file.")
+        inc_m, nm = True, args.bits_per_shot
+    nm, nd, no = (nm if inc_m else 0), (nd if inc_d else 0), (no if inc_l else 0)
+    n = nm + nd + no
+    data = sys.stdin.buffer.read() if args.inp is None else open(args.inp, "rb").read()
+    rows = _formats.read_shots(data, args.in_format, n, num_measurements=nm, num_detectors=nd, num_observables=no)
+    shots = rows.shape[0]
+    bits = np.unpackbits(rows, axis=1, bitorder="little", count=n) if n else np.zeros((shots, 0), np.uint8)
+
+    def write(lo, hi, segments, path, fmt):
+        # segments: (prefix, count) of the value types inside [lo, hi); the dets writer takes up to two of them
+        segments = [(p, c) for p, c in segments if c] or [(b"M", 0)]
+        if fmt == "dets" and len(segments) == 3:
+            with open(path, "wb") as f:
+                for r in bits[:, lo:hi]:
+                    toks, base = [b"shot"], 0
+                    for p, c in segments:
+                        toks += [p + str(i).encode() for i in np.flatnonzero(r[base:base + c])]
+                        base += c
+                    f.write(b" ".join(toks) + b"\n")
+            return
+        packed = np.packbits(bits[:, lo:hi], axis=1, bitorder="little") if hi > lo else np.zeros((shots, 0), np.uint8)
+        stim_b200._write_rows(packed, hi - lo, path, fmt, segments[0][0], segments[-1][0], segments[0][1])
+
+    sys.stdout.flush()
+    out_path = args.out if args.out is not None else "/dev/stdout"
+    if args.obs_out is not None:
+        write(0, nm + nd, [(b"M", nm), (b"D", nd)], out_path, args.out_format)
+        write(nm + nd, n, [(b"L", no)], args.obs_out, args.obs_out_format)
+    else:
+        write(0, n, [(b"M", nm), (b"D", nd), (b"L", no)], out_path, args.out_format)
+    return 0
+
+
 def main(argv=None) -> int:
     args = _parser().parse_args(argv)
     try:
         if args.command == "m2d":
             return _m2d(args)
+        if args.command == "convert":
+            return _convert(args)
         text = sys.stdin.read() if args.inp is None else open(args.inp).read()
         if args.command == "sample_dem":
             sampler = stim_b200.DetectorErrorModel(text).compile_sampler(seed=args.seed)
