@@ -140,6 +140,9 @@ def read_shots(data: bytes, fmt: str, n_bits: int, *, num_measurements=None, num
         lines = data.replace(b"\r\n", b"\n").split(b"\n")
         if lines and lines[-1] == b"":
             lines.pop()
+        elif lines and len(lines[-1]) == n_bits and not lines[-1].strip(b"01"):
+            # (/root/reference/src/stim/io/measure_record_reader.inl: every record of the 01 format is closed by a newline)
+            raise ValueError(f"01 data didn't end with a newline after the expected data length of '{n_bits}'.")
         bits = np.zeros((len(lines), max(n_bits, 1)), dtype=np.uint8)
         for i, ln in enumerate(lines):
             if len(ln) != n_bits or ln.strip(b"01"):

@@ -68,11 +68,31 @@ with tempfile.TemporaryDirectory() as tmp:
                 for fout, fobs in (("dets", "hits"), ("b8", "01"), ("01", "dets"), ("r8", "b8")):
                     run(f"counts_{nm}_{nd}_{no}_{fin}_to_{fout}_obs_{fobs}",
                         ["--in_format", fin, "--out_format", fout, "--obs_out_format", fobs] + counts, data, obs_out=True)
+    # ptb64 on the input side (the reference's per-record converter reads it but cannot write it): 64 shots per group, one
+    # 64-bit little-endian word per bit
+    for (nm, nd, no, shots) in [(5, 0, 0, 64), (0, 70, 3, 128), (2, 3, 1, 64)]:
+        n = nm + nd + no
+        bits = (rng.random((shots, n)) < 0.2).astype(np.uint8)
+        raw = np.packbits(bits.reshape(shots // 64, 64, n).transpose(0, 2, 1), axis=2, bitorder="little").tobytes()
+        counts = ["--num_measurements", str(nm), "--num_detectors", str(nd), "--num_observables", str(no)]
+        for fout in ("01", "b8", "r8", "hits", "dets"):
+            run(f"ptb64_{nm}_{nd}_{no}_to_{fout}", ["--in_format", "ptb64", "--out_format", fout] + counts, raw)
+        if no:
+            run(f"ptb64_{nm}_{nd}_{no}_obs_out", ["--in_format", "ptb64", "--out_format", "dets", "--obs_out_format", "01"] + counts,
+                raw, obs_out=True)
     bits = (rng.random((11, 13)) < 0.3).astype(np.uint8)
     for fin in ("01", "b8", "r8", "hits"):
         data = to(fin, bits, 13, 0, 0)
         for fout in ("01", "b8", "r8", "hits", "dets"):
             run(f"bits_per_shot_{fin}_to_{fout}", ["--in_format", fin, "--out_format", fout, "--bits_per_shot", "13"], data)
+    # malformed input: the reference exits with status 1 (its partial output before the error is not compared)
+    m4 = ["--out_format", "01", "--num_measurements", "4"]
+    for name, fin, data in [("short_01_line", "01", b"010\n01\n"), ("bad_01_character", "01", b"0120\n"), ("01_without_newline", "01", b"0101"),
+                            ("truncated_b8", "b8", b"abc"), ("hit_too_large", "hits", b"1,9\n"), ("hit_not_a_number", "hits", b"1,x\n"),
+                            ("r8_past_the_end", "r8", b"\x02\x09"), ("r8_truncated", "r8", b"\x02"), ("dets_too_large", "dets", b"shot M9\n"),
+                            ("dets_wrong_type", "dets", b"shot D0\n"), ("dets_without_shot", "dets", b"shut M0\n"), ("empty_input", "01", b"")]:
+        flags = ["--in_format", fin] + (["--out_format", "01", "--num_measurements", "16"] if name == "truncated_b8" else m4)
+        run("malformed_" + name, flags, data)
     run("nothing_known", ["--in_format", "01", "--out_format", "hits"], text01(bits))
     for types, (nm, nd, no) in (("M", (5, 0, 0)), ("D", (0, 3, 0)), ("L", (0, 0, 2)), ("DL", (0, 3, 2)), ("MDL", (5, 3, 2)),
                                 ("LD", (0, 3, 2)), ("MD", (5, 3, 0)), ("ML", (5, 0, 2))):
