@@ -39,3 +39,40 @@ def test_convert_reads_stdin_and_writes_stdout(tmp_path):
     r = subprocess.run([sys.executable, "-m", "stim_b200", "convert", "--in_format", "01", "--out_format", "dets", "--num_measurements",
                         "1", "--num_detectors", "2", "--num_observables", "1"], input=b"0101\n1100\n", capture_output=True, cwd=root)
     assert r.returncode == 0 and r.stdout == b"shot D0 L0\nshot M0 D0\n"
+
+
+# Known answers restated from the reference's own tests (/root/reference/src/stim/cmd/command_convert.test.cc:22-51, 53-100,
+# 308-313, 334-344): the same records in four input formats, the `--flag=value` spelling included.
+MEAS_CIRCUIT = "X 0\nM 0 1\nDETECTOR rec[-2]\nDETECTOR rec[-1]\nOBSERVABLE_INCLUDE(2) rec[-1]\n"
+DET_CIRCUIT = ("CX 0 2 1 2\nM 2\nCX rec[-1] 2\nDETECTOR rec[-1]\nTICK\n" + "CX 0 2 1 2\nM 2\nCX rec[-1] 2\nDETECTOR rec[-1] rec[-2]\nTICK\n" * 2
+               + "M 0 1\nDETECTOR rec[-1] rec[-2] rec[-3]\nOBSERVABLE_INCLUDE(0) rec[-1]\n")
+
+
+def _run(tmp_path, flags, data, circuit=None):
+    (tmp_path / "in.dat").write_bytes(data)
+    if circuit is not None:
+        (tmp_path / "c.stim").write_text(circuit)
+        flags = flags + ["--circuit", str(tmp_path / "c.stim")]
+    rc = cli.main(["convert"] + flags + ["--in", str(tmp_path / "in.dat"), "--out", str(tmp_path / "out.dat")])
+    return rc, (tmp_path / "out.dat").read_bytes() if rc == 0 else None
+
+
+@pytest.mark.parametrize("fmt,data", [("01", b"00\n01\n10\n11\n"), ("b8", bytes([0, 2, 1, 3])), ("hits", b"\n1\n0\n0,1\n"),
+                                      ("r8", bytes([2, 1, 0, 0, 1, 0, 0, 0]))])
+def test_reference_known_answers_measurements_to_dets(tmp_path, fmt, data):
+    assert _run(tmp_path, ["--in_format", fmt, "--out_format", "dets", "--types=M"], data, MEAS_CIRCUIT) == (
+        0, b"shot\nshot M1\nshot M0\nshot M0 M1\n")
+
+
+@pytest.mark.parametrize("fmt,data", [("01", b"00000\n11000\n01100\n00110\n00010\n00011\n"), ("b8", bytes([0, 3, 6, 12, 8, 24])),
+                                      ("hits", b"\n0,1\n1,2\n2,3\n3\n3,4\n"),
+                                      ("r8", bytes([5, 0, 0, 3, 1, 0, 2, 2, 0, 1, 3, 1, 3, 0, 0]))])
+def test_reference_known_answers_detections_and_observables_to_dets(tmp_path, fmt, data):
+    assert _run(tmp_path, ["--in_format", fmt, "--out_format", "dets", "--types=DL"], data, DET_CIRCUIT) == (
+        0, b"shot\nshot D0 D1\nshot D1 D2\nshot D2 D3\nshot D3\nshot D3 L0\n")
+
+
+def test_reference_known_answers_wide_records_and_refusals(tmp_path):
+    assert _run(tmp_path, ["--in_format=b8", "--out_format=b8", "--bits_per_shot=2048"], b"\x6b" * 256) == (0, b"\x6b" * 256)
+    assert _run(tmp_path, ["--in_format=r8", "--out_format=b8"], b"")[0] == 1
+    assert _run(tmp_path, ["--in_format=01", "--out_format", "dets", "--bits_per_shot=2"], b"")[0] == 1
