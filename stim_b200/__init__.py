@@ -383,8 +383,8 @@ class CompiledDetectorSampler(_Sampler):
         path = _path_str(filepath, "to ")
         obs_path = None if obs_out_filepath is None else _path_str(obs_out_filepath, "observables to ")
         flags = (_native.PREPEND_OBS if prepend_observables else 0) | (_native.APPEND_OBS if append_observables else 0)
-        with open(path, "wb") as f:
-            of = open(obs_path, "wb") if obs_path is not None else None
+        with _native.open_out(path) as f:
+            of = _native.open_out(obs_path) if obs_path is not None else None
             try:
                 _native.check(_native.lib().gstim_sample_detectors_to_fd(
                     self._handle, int(shots), flags, f.fileno(), format.encode(), of.fileno() if of else -1,
@@ -490,7 +490,7 @@ class CompiledMeasurementSampler(_Sampler):
 
     def sample_write(self, shots: int, *, filepath, format: str = "01") -> None:
         path = _path_str(filepath, "to ")
-        with open(path, "wb") as f:
+        with _native.open_out(path) as f:
             _native.check(_native.lib().gstim_sample_measurements_to_fd(self._handle, int(shots), f.fileno(), format.encode()))
 
     def sample_device(self, shots: int, out_ptr: int, *, shot_stride: int = 0) -> None:
@@ -598,7 +598,7 @@ def _write_rows(rows: np.ndarray, n_bits: int, path, fmt: str, prefix1: bytes, p
     """Packed shot-major rows -> file in any of the six formats (writers.cc through gstim_write_shots_to_fd)."""
     rows = np.ascontiguousarray(rows, dtype=np.uint8)
     rows = rows if rows.size else rows.reshape(rows.shape[0], 0)
-    with open(path, "wb") as f:
+    with _native.open_out(path) as f:
         buf = rows.ctypes.data_as(ctypes.c_void_p) if rows.size else None
         _native.check(_native.lib().gstim_write_shots_to_fd(
             buf, rows.shape[1], rows.shape[0], n_bits, f.fileno(), fmt.encode(), prefix1, prefix2, transition))

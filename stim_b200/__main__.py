@@ -135,7 +135,7 @@ def _convert(args) -> int:
         # segments: (prefix, count) of the value types inside [lo, hi); the dets writer takes up to two of them
         segments = [(p, c) for p, c in segments if c] or [(b"M", 0)]
         if fmt == "dets" and len(segments) == 3:
-            with open(path, "wb") as f:
+            with stim_b200._native.open_out(path) as f:
                 for r in bits[:, lo:hi]:
                     toks, base = [b"shot"], 0
                     for p, c in segments:

@@ -13,16 +13,18 @@ def _pack(bits: np.ndarray, n_bits: int) -> np.ndarray:
     return np.packbits(bits, axis=1, bitorder="little")
 
 
-def _rows_from_hits(shot_of_hit: np.ndarray, bit_of_hit: np.ndarray, shots: int, n_bits: int) -> np.ndarray:
-    """Sparse (shot, bit) pairs -> packed rows; a bit listed twice toggles back (the readers XOR, :314). Sort-based: no
-    per-hit Python work and no dense one-byte-per-bit intermediate."""
+def _rows_from_hits(shot_of_hit: np.ndarray, bit_of_hit: np.ndarray, shots: int, n_bits: int, toggle: bool = True) -> np.ndarray:
+    """Sparse (shot, bit) pairs -> packed rows. toggle: a bit listed twice toggles back (the reference's per-record hits reader
+    XORs, measure_record_reader.inl:315) - its dets reader SETS the bit instead (:484). Sort-based: no per-hit Python work and
+    no dense one-byte-per-bit intermediate."""
     nb = (n_bits + 7) // 8
     out = np.zeros((shots, nb), dtype=np.uint8)
     if len(shot_of_hit) == 0 or nb == 0:
         return out
     flat = shot_of_hit.astype(np.int64) * n_bits + bit_of_hit.astype(np.int64)
     u, c = np.unique(flat, return_counts=True)
-    u = u[(c & 1) == 1]
+    if toggle:
+        u = u[(c & 1) == 1]
     if len(u) == 0:
         return out
     shot, bit = np.divmod(u, n_bits)
@@ -112,7 +114,7 @@ def _fast_dets(data: bytes, n_bits: int, nm: int, nd: int, no: int):
     if np.any(vals >= length):
         return None  # (the strict parser words the error)
     rec = (np.cumsum(nl)[pi]).astype(np.int64) if len(pi) else np.zeros(0, np.int64)
-    return _rows_from_hits(rec, off + vals, len(shot_pos), n_bits)
+    return _rows_from_hits(rec, off + vals, len(shot_pos), n_bits, toggle=False)
 
 
 def read_shots(data: bytes, fmt: str, n_bits: int, *, num_measurements=None, num_detectors: int = 0,
@@ -176,14 +178,16 @@ def read_shots(data: bytes, fmt: str, n_bits: int, *, num_measurements=None, num
         lines = data.replace(b"\r\n", b"\n").split(b"\n")
         if lines and lines[-1] == b"":
             lines.pop()
+        elif lines:  # (the reference's reader wants every record closed by a newline and nothing but digits and commas)
+            raise ValueError("HITS data wasn't comma-separated integers terminated by a newline.")
         s_idx, b_idx = [], []
         for i, ln in enumerate(lines):
             if ln == b"":
                 continue
-            try:
-                vals = [int(tok) for tok in ln.split(b",")]
-            except ValueError:
-                raise ValueError("HITS data wasn't comma-separated integers terminated by a newline.") from None
+            toks = ln.split(b",")
+            if not all(tok.isdigit() for tok in toks):
+                raise ValueError("HITS data wasn't comma-separated integers terminated by a newline.")
+            vals = [int(tok) for tok in toks]
             for v in vals:
                 if v < 0 or v >= n_bits:
                     raise ValueError("hit index is too large.")
@@ -221,7 +225,7 @@ def read_shots(data: bytes, fmt: str, n_bits: int, *, num_measurements=None, num
                     s_idx.append(shots)
                     b_idx.append(off + v)
             shots += 1
-        return _rows_from_hits(np.array(s_idx, dtype=np.int64), np.array(b_idx, dtype=np.int64), shots, n_bits)
+        return _rows_from_hits(np.array(s_idx, dtype=np.int64), np.array(b_idx, dtype=np.int64), shots, n_bits, toggle=False)
     if fmt == "ptb64":
         if n_bits == 0:
             if len(data):

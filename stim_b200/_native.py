@@ -187,3 +187,18 @@ def check(code):
     if code == ERR_CUDA:
         raise GstimCudaError(msg)
     raise RuntimeError(msg)
+
+
+def open_out(path):
+    """Opens a result file for writing. "/dev/stdout" means this process's standard output as it is (a duplicate of
+    descriptor 1: no truncation, the offset shared with whoever else writes there) like the reference writing to its `stdout`
+    FILE* (/root/reference/src/stim/util_bot/arg_parse.cc find_open_file_argument) - opening the path again would truncate a
+    regular file that stdout was redirected or appended to."""
+    import os
+    import sys
+
+    path = os.fspath(path)
+    if path == "/dev/stdout":
+        sys.stdout.flush()
+        return os.fdopen(os.dup(1), "wb")
+    return open(path, "wb")

@@ -170,7 +170,7 @@ class CompiledDemSampler:
                 if path is None:
                     fds.append(-1)
                 else:
-                    f = open(os.fspath(path), "wb")
+                    f = _native.open_out(path)
                     files.append(f)
                     fds.append(f.fileno())
             _native.check(_native.lib().gstim_dem_sample_to_fd(

@@ -76,3 +76,19 @@ def test_reference_known_answers_wide_records_and_refusals(tmp_path):
     assert _run(tmp_path, ["--in_format=b8", "--out_format=b8", "--bits_per_shot=2048"], b"\x6b" * 256) == (0, b"\x6b" * 256)
     assert _run(tmp_path, ["--in_format=r8", "--out_format=b8"], b"")[0] == 1
     assert _run(tmp_path, ["--in_format=01", "--out_format", "dets", "--bits_per_shot=2"], b"")[0] == 1
+
+
+def test_writing_to_stdout_appends_to_a_redirected_file(tmp_path):
+    """The reference writes to its `stdout` stream; opening "/dev/stdout" again would truncate a file that stdout was
+    appended to (`>> log`) or that several commands share."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    log = tmp_path / "log.txt"
+    log.write_bytes(b"first line\n")
+    for data in (b"0,2\n", b"1\n"):
+        with open(log, "ab") as f:
+            r = subprocess.run([sys.executable, "-m", "stim_b200", "convert", "--in_format", "hits", "--out_format", "01",
+                                "--num_measurements", "4"], input=data, stdout=f, cwd=root)
+        assert r.returncode == 0
+    assert log.read_bytes() == b"first line\n1010\n0100\n"

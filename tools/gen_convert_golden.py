@@ -90,7 +90,12 @@ with tempfile.TemporaryDirectory() as tmp:
     for name, fin, data in [("short_01_line", "01", b"010\n01\n"), ("bad_01_character", "01", b"0120\n"), ("01_without_newline", "01", b"0101"),
                             ("truncated_b8", "b8", b"abc"), ("hit_too_large", "hits", b"1,9\n"), ("hit_not_a_number", "hits", b"1,x\n"),
                             ("r8_past_the_end", "r8", b"\x02\x09"), ("r8_truncated", "r8", b"\x02"), ("dets_too_large", "dets", b"shot M9\n"),
-                            ("dets_wrong_type", "dets", b"shot D0\n"), ("dets_without_shot", "dets", b"shut M0\n"), ("empty_input", "01", b"")]:
+                            ("dets_wrong_type", "dets", b"shot D0\n"), ("dets_without_shot", "dets", b"shut M0\n"), ("empty_input", "01", b""), ("hits_without_newline", "hits", b"1"), ("hits_with_spaces", "hits", b" 1, 2\n"),
+                            ("hits_trailing_comma", "hits", b"1,\n"), ("hits_crlf", "hits", b"1\r\n\r\n"), ("hits_listed_twice", "hits", b"1,1\n"),
+                            ("dets_listed_twice", "dets", b"shot M0 M0\n"), ("dets_double_space", "dets", b"shot  M0   M3\n"),
+                            ("dets_indented_and_blank", "dets", b"  shot M0\n\nshot\n"), ("dets_without_newline", "dets", b"shot M1"),
+                            ("01_crlf", "01", b"0101\r\n"), ("01_blank_line", "01", b"0101\n\n"), ("r8_exact", "r8", b"\x04"),
+                            ("r8_one_too_far", "r8", b"\x05")]:
         flags = ["--in_format", fin] + (["--out_format", "01", "--num_measurements", "16"] if name == "truncated_b8" else m4)
         run("malformed_" + name, flags, data)
     run("nothing_known", ["--in_format", "01", "--out_format", "hits"], text01(bits))
