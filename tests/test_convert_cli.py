@@ -92,3 +92,20 @@ def test_writing_to_stdout_appends_to_a_redirected_file(tmp_path):
                                 "--num_measurements", "4"], input=data, stdout=f, cwd=root)
         assert r.returncode == 0
     assert log.read_bytes() == b"first line\n1010\n0100\n"
+
+
+def test_convert_also_writes_ptb64(tmp_path):
+    """Beyond the reference (its per-record converter refuses to WRITE ptb64): the bytes equal the ptb64 files of
+    tests/golden/formats_cases.json, which the reference CLI reads back into the original records (tools/gen_formats_golden.py)."""
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "formats_cases.json")))
+    n = 0
+    for c in cases:
+        if "ptb64" not in c["files"]:
+            continue
+        counts = [f"--num_measurements={c['num_measurements']}", f"--num_detectors={c['num_detectors']}",
+                  f"--num_observables={c['num_observables']}"]
+        rc, out = _run(tmp_path, ["--in_format=01", "--out_format=ptb64"] + counts, base64.b64decode(c["files"]["01"]))
+        assert rc == 0 and out == base64.b64decode(c["files"]["ptb64"])
+        n += 1
+    assert n >= 5
+    assert _run(tmp_path, ["--in_format=01", "--out_format=ptb64", "--num_measurements=3"], b"010\n")[0] == 1  # shots % 64 != 0
