@@ -26,8 +26,16 @@ import stim_b200
 FORMATS = ("01", "b8", "ptb64", "hits", "r8", "dets")
 
 
+class _Parser(argparse.ArgumentParser):
+    """Bad command lines end like the reference's (red message on stderr, exit status 1:
+    /root/reference/src/stim/util_bot/arg_parse.cc check_for_unknown_arguments / find_*_argument), not with argparse's status 2."""
+
+    def error(self, message):
+        raise ValueError(message)
+
+
 def _parser():
-    p = argparse.ArgumentParser(prog="python -m stim_b200", allow_abbrev=False)
+    p = _Parser(prog="python -m stim_b200", allow_abbrev=False)
     sub = p.add_subparsers(dest="command", required=True)
     for name in ("detect", "sample"):
         q = sub.add_parser(name, allow_abbrev=False)
@@ -157,8 +165,8 @@ def _convert(args) -> int:
 
 
 def main(argv=None) -> int:
-    args = _parser().parse_args(argv)
     try:
+        args = _parser().parse_args(argv)
         if args.command == "m2d":
             return _m2d(args)
         if args.command == "convert":

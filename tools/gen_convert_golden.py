@@ -98,6 +98,10 @@ with tempfile.TemporaryDirectory() as tmp:
                             ("r8_one_too_far", "r8", b"\x05")]:
         flags = ["--in_format", fin] + (["--out_format", "01", "--num_measurements", "16"] if name == "truncated_b8" else m4)
         run("malformed_" + name, flags, data)
+    run("unknown_flag", ["--in_format", "01", "--out_format", "01", "--num_measurements", "4", "--bogus", "1"], b"0101\n")
+    run("missing_in_format", ["--out_format", "01", "--num_measurements", "4"], b"0101\n")
+    run("unknown_format_name", ["--in_format", "01", "--out_format", "xyz", "--num_measurements", "4"], b"0101\n")
+    run("count_not_a_number", ["--in_format", "01", "--out_format", "01", "--num_measurements", "four"], b"0101\n")
     run("nothing_known", ["--in_format", "01", "--out_format", "hits"], text01(bits))
     for types, (nm, nd, no) in (("M", (5, 0, 0)), ("D", (0, 3, 0)), ("L", (0, 0, 2)), ("DL", (0, 3, 2)), ("MDL", (5, 3, 2)),
                                 ("LD", (0, 3, 2)), ("MD", (5, 3, 0)), ("ML", (5, 0, 2))):
